@@ -1,0 +1,127 @@
+// common.cuh -- internal declarations shared by the libhsg translation units.
+#pragma once
+#include <cuda_runtime.h>
+#include <cuda_bf16.h>
+#include <stdint.h>
+#include <string>
+#include <vector>
+
+#include "../../include/hsg.h"
+
+#define HSG_NHEAD 8
+#define HSG_DK 16
+#define HSG_HD 128                 // n_head * d_k = n_head * d_v   (Higashi_wrapper.py:834-845)
+#define HSG_LN_EPS 1e-5f
+#define HSG_PDF0 0.3989422804014327f   // scipy.stats.norm.pdf(0)   (Impute.py:19)
+
+void hsg_set_error(const std::string& msg);
+
+#define HSG_CUDA(call)                                                                         \
+    do {                                                                                       \
+        cudaError_t e__ = (call);                                                              \
+        if (e__ != cudaSuccess) {                                                              \
+            hsg_set_error(std::string(#call) + " failed: " + cudaGetErrorString(e__) + " at " + \
+                          __FILE__ + ":" + std::to_string(__LINE__));                          \
+            return 1;                                                                          \
+        }                                                                                      \
+    } while (0)
+
+#define HSG_CHECK(cond, msg)                                                                   \
+    do {                                                                                       \
+        if (!(cond)) {                                                                         \
+            hsg_set_error(std::string(msg) + " (" + #cond + ")");                              \
+            return 2;                                                                          \
+        }                                                                                      \
+    } while (0)
+
+// Weights derived once per hsg_prepare (transposed so that the output index is contiguous).
+struct DerivedWeights {
+    float* sageT = nullptr;    // [2d][d]      encode1.dynamic_nn.nn.weight^T
+    float* wqT = nullptr;      // [d][128]
+    float* wkT = nullptr;      // [d][128]
+    float* wvT = nullptr;      // [d][128]
+    float* fc1T = nullptr;     // [128][d]
+    float* fc2T = nullptr;     // [128][d]
+    float* w0T = nullptr;      // [d][d]       pff_n1 layer 0
+    float* w1T = nullptr;      // [d][d]       pff_n1 layer 1
+    float* c0T = nullptr;      // [d][d/2]     pff_classifier layer 0
+};
+
+struct hsg_ctx {
+    int device = 0;
+    int d = 0, n_cells = 0, n_chrom = 0, cf = 0, n_bins = 0;
+    std::vector<int> bins, bin_off;          // host copies
+    int* d_bin_off = nullptr;                // [C+1]
+    int* d_bin_chrom = nullptr;              // [n_bins]
+
+    float* w[HSG_W_COUNT] = {nullptr};
+    int64_t wcount[HSG_W_COUNT] = {0};
+
+    float* E_cell = nullptr;                 // [n_cells, d]   off-hooked cell table
+    float* E_bin = nullptr;                  // [n_bins, d]    off-hooked bin tables, chromosomes concatenated
+    std::vector<char> table_set;             // per branch
+
+    // contacts: packed CSR
+    int64_t* row_ptr = nullptr; int32_t* col = nullptr; float* val = nullptr;
+    int64_t n_rows = 0, nnz = 0;
+    // neighbours
+    int32_t* nbr = nullptr; float* nbr_w = nullptr; int k1 = 1; bool weighted = false;
+
+    // pairs
+    int64_t P = 0;
+    int2* pairs = nullptr;                   // [P] genome-wide 0-based (bin_i, bin_j)
+    float* pair_bias = nullptr;              // [P] extra_proba2 on the pair (cell-invariant, only_model=True)
+    std::vector<int> sel_chroms;
+    std::vector<int64_t> sel_P, sel_off;
+    std::vector<int2> h_pairs;
+
+    // prepared state
+    bool prepared = false;
+    int precision = HSG_PREC_FP32, ltr = 0, act = HSG_ACT_SIGMOID;
+    DerivedWeights dw;
+    float* cellQ = nullptr; float* cellK = nullptr; float* cellV = nullptr; float* cellS = nullptr;  // [n_cells, 128|d]
+    float* binV = nullptr;  float* binS = nullptr;                                                   // [n_bins, 128|d]
+
+    // per-batch workspace
+    int batch_cells = 0;
+    float* neigh = nullptr;                  // [batch, n_bins, d]
+    float* QK = nullptr;                     // [batch, n_bins, 2, 128]
+    int fixed_cell = -1;                     // 0-based cell whose tokens sit in QK slot 0 (hsg_fix_cell)
+
+    cudaStream_t stream = nullptr;           // internal work stream
+    cudaStream_t copy_stream = nullptr;
+    cudaEvent_t ev[8] = {nullptr};
+    float* stage_out[2] = {nullptr, nullptr}; size_t stage_bytes = 0;
+    cudaEvent_t stage_ev[2] = {nullptr, nullptr};
+    bool profiling = false;
+    float last_ms[4] = {0, 0, 0, 0};
+    int64_t launches = 0;
+};
+
+// ---- kernel launchers (definitions in the .cu files) ---------------------------------------
+int launch_embed_table(hsg_ctx* c, const float* x, int64_t rows, int in_dim, const float* w, const float* b,
+                       int apply_swish, float* out, cudaStream_t s);
+int launch_static_tokens(hsg_ctx* c, const float* E, int64_t rows, float* Q, float* K, float* V, float* S, cudaStream_t s);
+int launch_pair_bias(hsg_ctx* c, cudaStream_t s);
+int launch_gather(hsg_ctx* c, const int* cells_dev_unused, int cell_start, int n_cells_batch, cudaStream_t s);
+int launch_token_project(hsg_ctx* c, int cell_start, int n_cells_batch, cudaStream_t s);
+int launch_score_pairs_f32(hsg_ctx* c, int cell_start, int n_cells_batch, float* out, cudaStream_t s);
+int launch_score_triplets_f32(hsg_ctx* c, const int64_t* x, int64_t B, float* out, cudaStream_t s);
+
+// ---- small device helpers -------------------------------------------------------------------
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+
+// fp32-mode activations: accurate libm versions (parity bar 1e-5 absolute on the score)
+__device__ __forceinline__ float swish_acc(float x) { return x / (1.0f + expf(-x)); }
+__device__ __forceinline__ float sigmoid_acc(float x) { return 1.0f / (1.0f + expf(-x)); }
+// torch.nn.functional.softplus(beta=1, threshold=20)
+__device__ __forceinline__ float softplus_acc(float x) { return x > 20.0f ? x : log1pf(expf(x)); }
+__device__ __forceinline__ float apply_act(float x, int act) {
+    if (act == HSG_ACT_SIGMOID) return sigmoid_acc(x);
+    if (act == HSG_ACT_SOFTPLUS) return softplus_acc(x);
+    return x;
+}

@@ -1,0 +1,329 @@
+// gather_kernels.cu -- K1: node embedding of every (cell, bin) token of a batch of cells.
+//
+//   K1a neigh_gather_kernel  : weighted merge of the k+1 neighbour cells' CSR rows (+ optional row-shift
+//                              smoothing), x pdf(0), log1p, L1 row normalisation, then the sparse gather
+//                              A_hat[b,:] . E_bin   (Impute.py:78-121 prep_one + Modules.py:1364-1371 forward_GCN)
+//   K1b token_project_kernel : dyn = swish(nn([neigh | E_self]))  (Modules.py:1480), Q = w_qs.LN1(dyn),
+//                              K = w_ks.LN2(dyn)                   (Modules.py:1035-1044)
+#include "common.cuh"
+
+// ---------------------------------------------------------------------------------------------
+// K1a.  One warp per (cell, bin) token.  Per-warp scratch in shared memory:
+//   acc[max_nc] (+ tmp[max_nc] when local_transfer_range > 0), touched-column lists and bit masks.
+// Values of one CSR row have unique columns, so the lanes of a warp never collide on acc[].
+// ---------------------------------------------------------------------------------------------
+struct GatherSmem {
+    float* acc; float* tmp; unsigned* amask; unsigned* tmask; unsigned short* alist; unsigned short* tlist;
+};
+
+__host__ __device__ inline size_t gather_warp_bytes(int max_nc, int ltr) {
+    size_t words = (max_nc + 31) / 32;
+    size_t b = (size_t)max_nc * 4 + words * 4 + (((size_t)max_nc * 2 + 3) & ~(size_t)3);
+    if (ltr > 0) b *= 2;
+    return (b + 15) & ~(size_t)15;
+}
+
+__device__ __forceinline__ float norm_pdf_dev(float x) { return expf(-0.5f * x * x) * HSG_PDF0; }
+
+// accumulate  T[col] (+)= w * val  over one CSR row, recording first-touched columns
+__device__ __forceinline__ void merge_row(const int32_t* __restrict__ col, const float* __restrict__ val,
+                                          int64_t lo, int64_t hi, float w, bool scale, float* T, unsigned* mask,
+                                          unsigned short* list, int& count, int lane) {
+    for (int64_t e0 = lo; e0 < hi; e0 += 32) {
+        int64_t e = e0 + lane;
+        bool valid = e < hi;
+        bool is_new = false;
+        int cidx = 0;
+        if (valid) {
+            cidx = __ldg(col + e);
+            float v = __ldg(val + e);
+            float prod = scale ? __fmul_rn(w, v) : v;
+            T[cidx] = __fadd_rn(T[cidx], prod);
+            unsigned bit = 1u << (cidx & 31);
+            unsigned old = atomicOr(&mask[cidx >> 5], bit);
+            is_new = !(old & bit);
+        }
+        unsigned b = __ballot_sync(0xffffffffu, is_new);
+        if (is_new) list[count + __popc(b & ((1u << lane) - 1u))] = (unsigned short)cidx;
+        count += __popc(b);
+    }
+    __syncwarp();
+}
+
+template <int D>
+__global__ void neigh_gather_kernel(const int64_t* __restrict__ row_ptr, const int32_t* __restrict__ col,
+                                    const float* __restrict__ val, const int32_t* __restrict__ nbr,
+                                    const float* __restrict__ nbr_w, int k1, int weighted,
+                                    const float* __restrict__ E_bin, const int* __restrict__ bin_chrom,
+                                    const int* __restrict__ bin_off, int n_bins, int cell_start,
+                                    int n_batch_cells, int ltr, int max_nc, float* __restrict__ neigh) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, wpb = blockDim.x >> 5;
+    const size_t wbytes = gather_warp_bytes(max_nc, ltr);
+    unsigned char* base = smem_raw + (size_t)warp * wbytes;
+    const int words = (max_nc + 31) / 32;
+    const size_t lbytes = (((size_t)max_nc * 2 + 3) & ~(size_t)3);
+    GatherSmem S;
+    S.acc = (float*)base;
+    S.amask = (unsigned*)(base + (size_t)max_nc * 4);
+    S.alist = (unsigned short*)(base + (size_t)max_nc * 4 + (size_t)words * 4);
+    unsigned char* b2 = base + (size_t)max_nc * 4 + (size_t)words * 4 + lbytes;
+    S.tmp = (float*)b2;
+    S.tmask = (unsigned*)(b2 + (size_t)max_nc * 4);
+    S.tlist = (unsigned short*)(b2 + (size_t)max_nc * 4 + (size_t)words * 4);
+    for (int i = lane; i < max_nc; i += 32) { S.acc[i] = 0.f; if (ltr > 0) S.tmp[i] = 0.f; }
+    for (int i = lane; i < words; i += 32) { S.amask[i] = 0u; if (ltr > 0) S.tmask[i] = 0u; }
+    __syncwarp();
+
+    const int64_t n_tok = (int64_t)n_batch_cells * n_bins;
+    for (int64_t tok = (int64_t)blockIdx.x * wpb + warp; tok < n_tok; tok += (int64_t)gridDim.x * wpb) {
+        const int cb = (int)(tok / n_bins), g = (int)(tok - (int64_t)cb * n_bins);
+        const int cell = cell_start + cb;
+        const int c = bin_chrom[g], off = bin_off[c], nc = bin_off[c + 1] - off, l = g - off;
+        int acount = 0;
+        if (ltr == 0) {
+            for (int nb = 0; nb < k1; ++nb) {
+                int src = weighted ? nbr[(int64_t)cell * k1 + nb] : cell;
+                float w = weighted ? nbr_w[(int64_t)cell * k1 + nb] : 1.0f;
+                int64_t row = (int64_t)src * n_bins + off + l;
+                merge_row(col, val, row_ptr[row], row_ptr[row + 1], w, weighted != 0, S.acc, S.amask, S.alist,
+                          acount, lane);
+            }
+            for (int i = lane; i < acount; i += 32) {           // adj * norm.pdf(0)   (Impute.py:19)
+                int ci = S.alist[i];
+                S.acc[ci] = __fmul_rn(S.acc[ci], HSG_PDF0);
+            }
+            __syncwarp();
+        } else {
+            // adj = M*pdf(0) + sum_i (M[row+i+1] + M[row-i-1]) * pdf((i+1)/range), rows clamped (Impute.py:16-26)
+            for (int s = -2 * ltr; s <= 2 * ltr; ++s) {
+                int as = s < 0 ? -s : s;
+                float pdf = (s == 0) ? HSG_PDF0 : norm_pdf_dev((float)as / (float)ltr);
+                int sl = min(max(l + s, 0), nc - 1);
+                int tcount = 0;
+                for (int nb = 0; nb < k1; ++nb) {
+                    int src = weighted ? nbr[(int64_t)cell * k1 + nb] : cell;
+                    float w = weighted ? nbr_w[(int64_t)cell * k1 + nb] : 1.0f;
+                    int64_t row = (int64_t)src * n_bins + off + sl;
+                    merge_row(col, val, row_ptr[row], row_ptr[row + 1], w, weighted != 0, S.tmp, S.tmask, S.tlist,
+                              tcount, lane);
+                }
+                for (int i0 = 0; i0 < tcount; i0 += 32) {
+                    int i = i0 + lane;
+                    bool valid = i < tcount, is_new = false;
+                    int ci = 0;
+                    if (valid) {
+                        ci = S.tlist[i];
+                        S.acc[ci] = __fadd_rn(S.acc[ci], __fmul_rn(S.tmp[ci], pdf));
+                        S.tmp[ci] = 0.f;
+                        unsigned bit = 1u << (ci & 31);
+                        unsigned old = atomicOr(&S.amask[ci >> 5], bit);
+                        is_new = !(old & bit);
+                        S.tmask[ci >> 5] = 0u;
+                    }
+                    unsigned b = __ballot_sync(0xffffffffu, is_new);
+                    if (is_new) S.alist[acount + __popc(b & ((1u << lane) - 1u))] = (unsigned short)ci;
+                    acount += __popc(b);
+                }
+                __syncwarp();
+            }
+        }
+        // log1p + L1 normalisation (Impute.py:91-92)
+        float part = 0.f;
+        for (int i = lane; i < acount; i += 32) {
+            int ci = S.alist[i];
+            float v = log1pf(S.acc[ci]);
+            S.acc[ci] = v;
+            part += fabsf(v);
+        }
+        float total = warp_sum(part);
+        __syncwarp();
+        // sparse gather: neigh = sum_t A_hat[b,t] * E_bin[t,:]   (lanes split the d columns)
+        constexpr int VPL = D / 32;
+        float out[VPL];
+#pragma unroll
+        for (int q = 0; q < VPL; ++q) out[q] = 0.f;
+        const float* Ec = E_bin + (int64_t)off * D;
+        for (int i = 0; i < acount; ++i) {
+            int ci = S.alist[i];
+            float a = (total > 0.f) ? __fdiv_rn(S.acc[ci], total) : S.acc[ci];
+            const float* er = Ec + (int64_t)ci * D + lane * VPL;
+            if (VPL == 2) {
+                float2 ev = __ldg(reinterpret_cast<const float2*>(er));
+                out[0] = fmaf(a, ev.x, out[0]); out[1] = fmaf(a, ev.y, out[1]);
+            } else {
+                float4 ev = __ldg(reinterpret_cast<const float4*>(er));
+                out[0] = fmaf(a, ev.x, out[0]); out[1] = fmaf(a, ev.y, out[1]);
+                out[2 % VPL] = fmaf(a, ev.z, out[2 % VPL]); out[3 % VPL] = fmaf(a, ev.w, out[3 % VPL]);
+            }
+        }
+        float* dst = neigh + tok * D + lane * VPL;
+        if (VPL == 2) *reinterpret_cast<float2*>(dst) = make_float2(out[0], out[1]);
+        else *reinterpret_cast<float4*>(dst) = make_float4(out[0], out[1], out[2 % VPL], out[3 % VPL]);
+        __syncwarp();
+        for (int i = lane; i < acount; i += 32) {            // reset scratch for the next token
+            int ci = S.alist[i];
+            S.acc[ci] = 0.f;
+            S.amask[ci >> 5] = 0u;
+        }
+        __syncwarp();
+    }
+}
+
+int launch_gather(hsg_ctx* c, const int*, int cell_start, int n_batch, cudaStream_t s) {
+    int max_nc = 0;
+    for (int b : c->bins) max_nc = b > max_nc ? b : max_nc;
+    HSG_CHECK(max_nc < 65536, "chromosomes with >= 65536 bins are not supported by the gather kernel");
+    size_t wbytes = gather_warp_bytes(max_nc, c->ltr);
+    int wpb = (int)((200 * 1024) / wbytes);
+    if (wpb > 16) wpb = 16;
+    HSG_CHECK(wpb >= 1, "chromosome too long for the gather scratch");
+    size_t smem = wbytes * wpb;
+    int64_t n_tok = (int64_t)n_batch * c->n_bins;
+    int64_t blocks = (n_tok + wpb - 1) / wpb;
+    int64_t cap = 148LL * 8;
+    unsigned grid = (unsigned)(blocks < cap ? blocks : cap);
+    if (c->d == 64) {
+        HSG_CUDA(cudaFuncSetAttribute(neigh_gather_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        neigh_gather_kernel<64><<<grid, wpb * 32, smem, s>>>(c->row_ptr, c->col, c->val, c->nbr, c->nbr_w, c->k1,
+                                                             c->weighted ? 1 : 0, c->E_bin, c->d_bin_chrom, c->d_bin_off,
+                                                             c->n_bins, cell_start, n_batch, c->ltr, max_nc, c->neigh);
+    } else {
+        HSG_CUDA(cudaFuncSetAttribute(neigh_gather_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        neigh_gather_kernel<128><<<grid, wpb * 32, smem, s>>>(c->row_ptr, c->col, c->val, c->nbr, c->nbr_w, c->k1,
+                                                              c->weighted ? 1 : 0, c->E_bin, c->d_bin_chrom, c->d_bin_off,
+                                                              c->n_bins, cell_start, n_batch, c->ltr, max_nc, c->neigh);
+    }
+    c->launches++;
+    HSG_CUDA(cudaGetLastError());
+    return 0;
+}
+
+// ---------------------------------------------------------------------------------------------
+// K1b.  32 tokens per block, 256 threads; register-tiled fp32 GEMMs with the activations staged
+// transposed in shared memory ([feature][token]) and the (transposed) weights read through L1.
+// ---------------------------------------------------------------------------------------------
+#define TP_TOK 32
+#define TP_LDA 36        // padded token stride (multiple of 4 for 128-bit loads)
+
+// acc[4][CT] += sum_k A^T[k][row0..row0+3] * Wt[k][col0..col0+CT-1]
+template <int CT>
+__device__ __forceinline__ void tile_gemm(const float* __restrict__ sA, int K, int row0,
+                                          const float* __restrict__ Wt, int ldw, int col0, float (&acc)[4][CT]) {
+#pragma unroll 4
+    for (int k = 0; k < K; ++k) {
+        float4 a = *reinterpret_cast<const float4*>(sA + k * TP_LDA + row0);
+        float wv[CT];
+#pragma unroll
+        for (int q = 0; q < CT; q += 4) {
+            float4 w4 = __ldg(reinterpret_cast<const float4*>(Wt + (size_t)k * ldw + col0 + q));
+            wv[q] = w4.x; wv[q + 1] = w4.y; wv[q + 2] = w4.z; wv[q + 3] = w4.w;
+        }
+#pragma unroll
+        for (int q = 0; q < CT; ++q) {
+            acc[0][q] = fmaf(a.x, wv[q], acc[0][q]);
+            acc[1][q] = fmaf(a.y, wv[q], acc[1][q]);
+            acc[2][q] = fmaf(a.z, wv[q], acc[2][q]);
+            acc[3][q] = fmaf(a.w, wv[q], acc[3][q]);
+        }
+    }
+}
+
+template <int D>
+__global__ void __launch_bounds__(256) token_project_kernel(
+    const float* __restrict__ neigh, const float* __restrict__ E_bin, int n_bins, int64_t n_tok,
+    const float* __restrict__ sageT, const float* __restrict__ sage_b,
+    const float* __restrict__ g1, const float* __restrict__ b1, const float* __restrict__ g2,
+    const float* __restrict__ b2, const float* __restrict__ wqT, const float* __restrict__ wkT,
+    float* __restrict__ QK) {
+    extern __shared__ __align__(16) float sm[];
+    float* xT = sm;                              // [2D][LDA]
+    float* dT = xT + 2 * D * TP_LDA;             // [D][LDA]   dyn, then LN1 input
+    float* kT = dT + D * TP_LDA;                 // [D][LDA]   LN2 input
+    const int tid = threadIdx.x;
+    const int64_t tok0 = (int64_t)blockIdx.x * TP_TOK;
+    // stage [neigh | E_self] transposed
+    for (int i = tid; i < TP_TOK * 2 * D; i += 256) {
+        int tk = i / (2 * D), f = i - tk * 2 * D;
+        int64_t tok = tok0 + tk;
+        float v = 0.f;
+        if (tok < n_tok) {
+            if (f < D) v = neigh[tok * D + f];
+            else v = E_bin[(int64_t)(tok % n_bins) * D + (f - D)];
+        }
+        xT[f * TP_LDA + tk] = v;
+    }
+    __syncthreads();
+    // GEMM1: dyn = swish(x . sageT + b)   [32][D]
+    {
+        constexpr int NCG = D / 4;
+        for (int t = tid; t < (TP_TOK / 4) * NCG; t += 256) {
+            int rg = t % (TP_TOK / 4), cg = t / (TP_TOK / 4);
+            float acc[4][4] = {};
+            tile_gemm<4>(xT, 2 * D, rg * 4, sageT, D, cg * 4, acc);
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+                float bb = sage_b[cg * 4 + q];
+#pragma unroll
+                for (int r = 0; r < 4; ++r) dT[(cg * 4 + q) * TP_LDA + rg * 4 + r] = swish_acc(acc[r][q] + bb);
+            }
+        }
+    }
+    __syncthreads();
+    // LayerNorm statistics per token (shared by layer_norm1 and layer_norm2), 8 threads per token
+    {
+        int tk = tid >> 3, sub = tid & 7;
+        float s = 0.f;
+        for (int f = sub; f < D; f += 8) s += dT[f * TP_LDA + tk];
+        s += __shfl_xor_sync(0xffffffffu, s, 1); s += __shfl_xor_sync(0xffffffffu, s, 2); s += __shfl_xor_sync(0xffffffffu, s, 4);
+        float mean = s / (float)D;
+        float v = 0.f;
+        for (int f = sub; f < D; f += 8) { float dd = dT[f * TP_LDA + tk] - mean; v = fmaf(dd, dd, v); }
+        v += __shfl_xor_sync(0xffffffffu, v, 1); v += __shfl_xor_sync(0xffffffffu, v, 2); v += __shfl_xor_sync(0xffffffffu, v, 4);
+        float rstd = 1.0f / sqrtf(v / (float)D + HSG_LN_EPS);
+        for (int f = sub; f < D; f += 8) {
+            float xh = (dT[f * TP_LDA + tk] - mean) * rstd;
+            dT[f * TP_LDA + tk] = fmaf(xh, g1[f], b1[f]);
+            kT[f * TP_LDA + tk] = fmaf(xh, g2[f], b2[f]);
+        }
+    }
+    __syncthreads();
+    // GEMM2: Q = LN1(dyn) . wqT, K = LN2(dyn) . wkT   [32][128] each
+    for (int t = tid; t < 2 * (TP_TOK / 4) * (HSG_HD / 4); t += 256) {
+        int which = t / ((TP_TOK / 4) * (HSG_HD / 4));
+        int u = t - which * ((TP_TOK / 4) * (HSG_HD / 4));
+        int rg = u % (TP_TOK / 4), cg = u / (TP_TOK / 4);
+        float acc[4][4] = {};
+        tile_gemm<4>(which ? kT : dT, D, rg * 4, which ? wkT : wqT, HSG_HD, cg * 4, acc);
+#pragma unroll
+        for (int r = 0; r < 4; ++r) {
+            int64_t tok = tok0 + rg * 4 + r;
+            if (tok < n_tok)
+                *reinterpret_cast<float4*>(QK + (tok * 2 + which) * HSG_HD + cg * 4) =
+                    make_float4(acc[r][0], acc[r][1], acc[r][2], acc[r][3]);
+        }
+    }
+}
+
+int launch_token_project(hsg_ctx* c, int cell_start, int n_batch, cudaStream_t s) {
+    (void)cell_start;
+    int64_t n_tok = (int64_t)n_batch * c->n_bins;
+    unsigned grid = (unsigned)((n_tok + TP_TOK - 1) / TP_TOK);
+    float** w = c->w;
+    if (c->d == 64) {
+        size_t smem = (size_t)4 * 64 * TP_LDA * sizeof(float);
+        HSG_CUDA(cudaFuncSetAttribute(token_project_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        token_project_kernel<64><<<grid, 256, smem, s>>>(c->neigh, c->E_bin, c->n_bins, n_tok, c->dw.sageT, w[HSG_W_SAGE_B],
+                                                         w[HSG_W_ALN1_G], w[HSG_W_ALN1_B], w[HSG_W_ALN2_G], w[HSG_W_ALN2_B],
+                                                         c->dw.wqT, c->dw.wkT, c->QK);
+    } else {
+        size_t smem = (size_t)4 * 128 * TP_LDA * sizeof(float);
+        HSG_CUDA(cudaFuncSetAttribute(token_project_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        token_project_kernel<128><<<grid, 256, smem, s>>>(c->neigh, c->E_bin, c->n_bins, n_tok, c->dw.sageT, w[HSG_W_SAGE_B],
+                                                          w[HSG_W_ALN1_G], w[HSG_W_ALN1_B], w[HSG_W_ALN2_G], w[HSG_W_ALN2_B],
+                                                          c->dw.wqT, c->dw.wkT, c->QK);
+    }
+    c->launches++;
+    HSG_CUDA(cudaGetLastError());
+    return 0;
+}

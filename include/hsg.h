@@ -1,0 +1,141 @@
+/* hsg.h -- C ABI of libhsg.so: the B200-native Hyper-SAGNN hyperedge scorer
+ * (Higashi's one data-parallel hot path: scoring (cell, bin_i, bin_j) triplets).
+ *
+ * The reference (ma-compbio/Higashi) has no FFI layer: its boundary for this path is the Python
+ * module API.  Each entry point below names the reference interface it replaces (file:line
+ * relative to the reference repo); INTEGRATION.md shows the ctypes binding a maintainer adds.
+ *
+ * Conventions
+ *   - every function returns 0 on success, non-zero on failure; hsg_last_error() then holds a
+ *     message (thread-local).  The host mirror raises a Python exception from it.
+ *   - plain pointers and sizes only.  "host" pointers are ordinary (ideally pinned) host memory,
+ *     "dev" pointers are device memory on the context's GPU.  `stream` is a cudaStream_t passed
+ *     as void* (NULL = legacy default stream).
+ *   - one context per device; calls on one context are serialised by the caller.
+ *   - ids follow the reference's node-id space where stated: 0 = pad, 1..n_cells = cells,
+ *     then bins in chromosome order (Process.py:795-797); "local" ids are 0-based.
+ *   - there is NO CPU fallback: every compute call fails if the device is unusable.
+ */
+#ifndef HSG_H_
+#define HSG_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct hsg_ctx hsg_ctx;
+
+#define HSG_ABI_VERSION 1
+
+/* precision of the fused scorer (BASELINE north_star: 1e-5 abs in fp32 mode, 1e-3 in bf16 mode) */
+#define HSG_PREC_FP32 0   /* CUDA-core fp32 everywhere                                            */
+#define HSG_PREC_BF16 1   /* tcgen05 bf16 operands / fp32 accumulate for the d_model projections  */
+
+/* activation applied to the `mean` head (Impute.py:218-221, Modules.py:814-817) */
+#define HSG_ACT_NONE     0
+#define HSG_ACT_SIGMOID  1   /* loss_mode == "classification" */
+#define HSG_ACT_SOFTPLUS 2   /* zinb / rank / regression      */
+
+/* Weight slots.  Shapes use d = d_model, H*dk = 128, C = n_chrom, cf = cell_feats width.
+ * Names on the right are the reference's state_dict keys (Modules.py:657-710, 975-1027, 1098-1134,
+ * 1387-1424).  All tensors are fp32, row-major, exactly as stored in the state_dict.            */
+enum hsg_weight {
+    HSG_W_QS = 0,        /* [128,d]  encode1.mul_head_attn.w_qs.weight                     */
+    HSG_W_KS,            /* [128,d]  encode1.mul_head_attn.w_ks.weight                     */
+    HSG_W_VS,            /* [128,d]  encode1.mul_head_attn.w_vs.weight                     */
+    HSG_W_FC1,           /* [d,128]  encode1.mul_head_attn.fc1.w_stack.0.weight            */
+    HSG_W_FC2,           /* [d,128]  encode1.mul_head_attn.fc2.w_stack.0.weight            */
+    HSG_W_ALN1_G, HSG_W_ALN1_B,   /* [d] encode1.mul_head_attn.layer_norm1.{weight,bias}  */
+    HSG_W_ALN2_G, HSG_W_ALN2_B,   /* [d] encode1.mul_head_attn.layer_norm2.{weight,bias}  */
+    HSG_W_ALN3_G, HSG_W_ALN3_B,   /* [d] encode1.mul_head_attn.layer_norm3.{weight,bias}  */
+    HSG_W_PFF_LN_G, HSG_W_PFF_LN_B, /* [d] encode1.pff_n1.layer_norm.{weight,bias}        */
+    HSG_W_PFF_W0, HSG_W_PFF_B0,   /* [d,d],[d] encode1.pff_n1.w_stack.0.{weight[:,:,0],bias} */
+    HSG_W_PFF_W1, HSG_W_PFF_B1,   /* [d,d],[d] encode1.pff_n1.w_stack.1.{weight[:,:,0],bias} */
+    HSG_W_LN1_G, HSG_W_LN1_B,     /* [d] layer_norm1.{weight,bias}                         */
+    HSG_W_LN2_G, HSG_W_LN2_B,     /* [d] layer_norm2.{weight,bias}                         */
+    HSG_W_CLS_W0, HSG_W_CLS_B0,   /* [d/2,d],[d/2] pff_classifier.w_stack.0                */
+    HSG_W_CLS_W1, HSG_W_CLS_B1,   /* [1,d/2],[1]   pff_classifier.w_stack.1                */
+    HSG_W_VAR_W0, HSG_W_VAR_B0, HSG_W_VAR_W1, HSG_W_VAR_B1,     /* pff_classifier_var.*   */
+    HSG_W_PRB_W0, HSG_W_PRB_B0, HSG_W_PRB_W1, HSG_W_PRB_B1,     /* pff_classifier_proba.* */
+    HSG_W_SAGE_W, HSG_W_SAGE_B,   /* [d,2d],[d] encode1.dynamic_nn.nn.{weight,bias}        */
+    HSG_W_XP_W0, HSG_W_XP_B0, HSG_W_XP_W1, HSG_W_XP_B1,         /* extra_proba.w_stack.*  : [4,2(C+1)+cf],[4],[1,4],[1] */
+    HSG_W_XP2_W0, HSG_W_XP2_B0, HSG_W_XP2_W1, HSG_W_XP2_B1,     /* extra_proba2.w_stack.* */
+    HSG_W_XP3_W0, HSG_W_XP3_B0, HSG_W_XP3_W1, HSG_W_XP3_B1,     /* extra_proba3.w_stack.* */
+    HSG_W_ATTR,          /* [n_cells+1+n_bins, C+1] attribute_dict_embedding.weight        */
+    HSG_W_CELL_FEATS,    /* [n_cells+1, cf]         Hyper_SAGNN.cell_feats (buffer)        */
+    HSG_W_COUNT
+};
+
+/* ---- lifetime -------------------------------------------------------------------------- */
+int  hsg_abi_version(void);
+const char* hsg_last_error(void);
+/* replaces: module-level `device` selection (Modules.py:25) / torch.cuda.set_device (Impute.py:333) */
+int  hsg_create(hsg_ctx** out, int device_ordinal);
+int  hsg_destroy(hsg_ctx* ctx);
+
+/* ---- model ----------------------------------------------------------------------------- */
+/* replaces: Hyper_SAGNN.__init__ shape bookkeeping (Modules.py:658-710); bins[C] = bins per chromosome */
+int  hsg_set_dims(hsg_ctx* ctx, int d_model, int n_cells, int n_chrom, const int32_t* bins, int cf);
+/* replaces: nn.Module.load_state_dict / .to(device) for one tensor */
+int  hsg_set_weight(hsg_ctx* ctx, int slot, const float* host, int64_t count);
+/* replaces: MultipleEmbedding.off_hook (Modules.py:605-631) = TiedAutoEncoder.encoder (:235-253) over
+ * all nodes of one branch.  branch 0 = cells (linear), branch j>0 = chromosome j-1 (swish).
+ * x host [rows,in_dim], w host [d,in_dim] (wstack.i.weight_list.0), b host [d] (wstack.i.bias_list.0).
+ * The [rows,d] table stays on the device; table_out (host, may be NULL) receives a copy.           */
+int  hsg_embed_table(hsg_ctx* ctx, int branch, const float* x, int64_t rows, int in_dim,
+                     const float* w, const float* b, float* table_out);
+/* alternative to hsg_embed_table: hand over an already computed table (SparseEmbedding(embed), Modules.py:627) */
+int  hsg_set_table(hsg_ctx* ctx, int branch, const float* table, int64_t rows);
+
+/* ---- data ------------------------------------------------------------------------------ */
+/* replaces: np.load(sparse_nondiag_adj_nbr_1.npy) (Impute.py:154) -- all (cell, chromosome) contact
+ * matrices as one CSR: row (cell, chrom j, local bin b) = cell*n_bins + bin_off[j] + b, columns local. */
+int  hsg_set_contacts(hsg_ctx* ctx, const int64_t* row_ptr, const int32_t* col, const float* val,
+                      int64_t n_rows, int64_t nnz);
+/* replaces: weighted_info.npy = (cell_neighbor_list, weight_dict) (Higashi_wrapper.py:1520-1545, Impute.py:245)
+ * nbr [n_cells,k1] 0-based cell ids (self first), w [n_cells,k1].  nbr == NULL => no neighbours (k1 = 1).   */
+int  hsg_set_neighbors(hsg_ctx* ctx, const int32_t* nbr, const float* w, int k1);
+/* replaces: Higashi.get_cell_neighbor (Higashi_wrapper.py:1303-1324): kNN graph from cell embeddings
+ * embed host [n_cells,dim]; fills nbr_out [n_cells,k1] (0-based) and w_out [n_cells,k1] and installs them. */
+int  hsg_build_neighbors(hsg_ctx* ctx, const float* embed, int dim, int k1, int32_t* nbr_out, float* w_out);
+
+/* ---- triplet enumeration (K3) ------------------------------------------------------------ */
+/* replaces: generate_binpair + skip set + big_samples assembly (Impute.py:49-61, 186-237).
+ * chroms[n_sel]: chromosome indices of impute_list in order; skip[n_skip][3] = (chrom, first_bin, end_bin)
+ * local; max_bin < 0 => unlimited.  P_total and per_chrom_P[n_sel] are outputs.                           */
+int  hsg_set_pairs(hsg_ctx* ctx, int n_sel, const int32_t* chroms, int min_bin, int max_bin,
+                   const int32_t* skip, int n_skip, int64_t* P_total, int64_t* per_chrom_P);
+/* the `coordinates` dataset (Impute.py:228-230): int64 [P_c,2] local 0-based, for selected chromosome slot */
+int  hsg_get_coordinates(hsg_ctx* ctx, int sel_slot, int64_t* host_out);
+
+/* ---- imputation (K1 + K2 + K3 epilogue) --------------------------------------------------- */
+/* replaces: model.eval(); only_model=True; off_hook(); start_fix() (Impute.py:163-177) and fixes the
+ * run options.  Must be called after weights/tables/contacts/pairs are set.                       */
+int  hsg_prepare(hsg_ctx* ctx, int precision, int local_transfer_range, int activation);
+/* replaces: the hot loop of impute_process (Impute.py:253-277): prep_one + fix_cell2 + predict for cells
+ * [cell_start, cell_end).  out_dev: device float [n_cells_in_range, P_total], row-major.               */
+int  hsg_impute_cells(hsg_ctx* ctx, int cell_start, int cell_end, float* out_dev, void* stream);
+/* same, result delivered to HOST memory (D2H overlapped with compute); out_host [n, P_total]. */
+int  hsg_impute_cells_host(hsg_ctx* ctx, int cell_start, int cell_end, float* out_host);
+
+/* ---- explicit triplets (Hyper_SAGNN.predict / forward) ------------------------------------- */
+/* replaces: GraphSageEncoder_with_weights.fix_cell2 (Modules.py:1432-1469) for one 1-based cell id */
+int  hsg_fix_cell(hsg_ctx* ctx, int cell_1based, void* stream);
+/* replaces: Hyper_SAGNN.predict (Modules.py:786-827) after fix_cell2: x dev int64 [B,3] node ids
+ * (cell+1, bin_i, bin_j); out dev float [B] = act(mean head).                                       */
+int  hsg_score_triplets(hsg_ctx* ctx, const int64_t* x_dev, int64_t B, float* out_dev, void* stream);
+
+/* ---- introspection ------------------------------------------------------------------------ */
+/* number of kernels this library launched since the context was created (bench.py gpu_launches) */
+int64_t hsg_launch_count(hsg_ctx* ctx);
+/* device time (ms, CUDA events on the work stream) of the last hsg_impute_cells* call, split by stage:
+ * ms[0] = gather (K1a), ms[1] = token projection (K1b), ms[2] = fused scorer (K2), ms[3] = total */
+int  hsg_last_timing(hsg_ctx* ctx, float* ms4);
+int  hsg_set_profiling(hsg_ctx* ctx, int enabled);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* HSG_H_ */

@@ -1,0 +1,216 @@
+"""GPU parity tests: the CUDA path (through the C ABI) against the golden fixtures minted from the
+unmodified reference and against the CPU oracle on seeded synthetic inputs.
+
+Tolerances (BASELINE.json north_star): bin-pair enumeration bit-exact; scores within 1e-5 absolute in
+fp32 mode, 1e-3 absolute in bf16 mode."""
+import hashlib
+
+import numpy as np
+import pytest
+import torch
+
+from tests._util import FixtureDataset, load
+
+pytestmark = pytest.mark.gpu
+
+TOL_FP32 = 1e-5
+TOL_BF16 = 1e-3
+
+
+def _engine():
+    from higashi_b200.engine import ScorerEngine
+    return ScorerEngine(0)
+
+
+def _sd(g, prefix):
+    return {k[len(prefix):]: v for k, v in g.items() if k.startswith(prefix)}
+
+
+# ------------------------------------------------------------------ K3: triplet enumeration, bit-exact
+@pytest.mark.parametrize("case", ["full_250", "min0_60", "offset_band", "skip_band", "skip_edges", "empty", "banded_4864"])
+def test_pairs_bit_exact(case):
+    g = load("binpair.npz")
+    s, e, mn, mx = [int(v) for v in g[case + "/args"]]
+    skip = sorted(int(v) - s for v in g[case + "/skip"])
+    eng = _engine()
+    # a second, unselected chromosome makes sure genome-wide offsets are handled
+    eng.ctx.set_dims(64, 7, [11, e - s], 1)
+    sk = [[1, b, b + 1] for b in skip]
+    P = eng.set_pairs([1], mn, mx, sk)
+    coords = eng.coordinates(0)
+    assert coords.dtype == np.int64 and coords.shape == (P, 2)
+    if case + "/pairs" in g:
+        ref = g[case + "/pairs"].astype(np.int64).reshape(-1, 2) - s - 1
+        assert np.array_equal(coords, ref)
+    else:
+        glob = (coords + s + 1).astype(np.int32)
+        assert len(glob) == int(g[case + "/count"])
+        assert hashlib.sha256(np.ascontiguousarray(glob).tobytes()).hexdigest() == str(g[case + "/sha256"])
+    eng.close()
+
+
+# ------------------------------------------------------------------ off-hook tables
+@pytest.mark.parametrize("d", [64, 128])
+def test_embed_tables(d):
+    g = load("scorer_d%d.npz" % d)
+    ds = FixtureDataset(g)
+    sd = _sd(g, "stage2/sd/")
+    eng = _engine()
+    eng.load_model(sd, ds.num, feats=ds.feats, cell_feats=ds.cell_feats)
+    np.testing.assert_allclose(eng.tables[0], g["impute/cell_table"], atol=TOL_FP32, rtol=0)
+    for j in range(len(ds.bins)):
+        np.testing.assert_allclose(eng.tables[j + 1], g["impute/bin_table_%d" % j], atol=TOL_FP32, rtol=0)
+    eng.close()
+
+
+# ------------------------------------------------------------------ imputation: golden payloads of impute_process
+def _run_impute_fixture(tag, precision):
+    from higashi_b200 import engine as E
+    g = load("impute_%s.npz" % tag)
+    ds = FixtureDataset(g)
+    sd = _sd(g, "sd/")
+    k, ltr = int(g["cfg/k"]), int(g["cfg/ltr"])
+    act = E.ACT_SIGMOID if str(g["cfg/mode"]) == "classification" else E.ACT_SOFTPLUS
+    mn, mx = [int(v) for v in g["cfg/band"]]
+    eng = _engine()
+    eng.load_model(sd, ds.num, feats=ds.feats, cell_feats=ds.cell_feats)
+    eng.set_contacts(ds.csr)
+    if k > 0:
+        eng.set_neighbors(g["knn/nbr"], g["knn/w"])
+    chroms = list(range(len(ds.bins)))
+    eng.set_pairs(chroms, mn, mx, g["cfg/skip"])
+    eng.prepare(precision, ltr, act)
+    c0, c1 = [int(v) for v in g["cfg/cell_range"]]
+    out = eng.impute_to_host(c0, c1)
+    off = 0
+    res = []
+    for j in chroms:
+        coords = eng.coordinates(j)
+        assert np.array_equal(coords, g["out/chr%d/coordinates" % (j + 1)])
+        n = len(coords)
+        res.append((out[:, off:off + n], g["out/chr%d/cells" % (j + 1)]))
+        off += n
+    assert off == eng.P
+    eng.close()
+    return res
+
+
+@pytest.mark.parametrize("tag", ["k0_r0", "k4_r0", "k4_r1", "k0_r1_band"])
+def test_impute_golden_fp32(tag):
+    from higashi_b200 import engine as E
+    for got, ref in _run_impute_fixture(tag, E.PREC_FP32):
+        np.testing.assert_allclose(got, ref, atol=TOL_FP32, rtol=0)
+
+
+# ------------------------------------------------------------------ Hyper_SAGNN.predict on explicit triplets
+@pytest.mark.parametrize("d", [64, 128])
+def test_predict_explicit_triplets(d):
+    from higashi_b200 import engine as E
+    g = load("scorer_d%d.npz" % d)
+    ds = FixtureDataset(g)
+    sd = _sd(g, "stage2/sd/")
+    pairs = g["impute/pairs"]
+    for act_name, act in (("sigmoid", E.ACT_SIGMOID), ("softplus", E.ACT_SOFTPLUS)):
+        eng = _engine()
+        eng.load_model(sd, ds.num, feats=ds.feats, cell_feats=ds.cell_feats)
+        eng.set_contacts(ds.csr)
+        eng.set_pairs(list(range(len(ds.bins))), 1, -1)
+        eng.prepare(E.PREC_FP32, 0, act)
+        for n, cell in enumerate(g["impute/cells"]):
+            x = np.concatenate([np.full((len(pairs), 1), int(cell), dtype=np.int64), pairs], axis=-1)
+            xt = torch.from_numpy(x).cuda()
+            out = torch.empty(len(x), dtype=torch.float32, device="cuda")
+            eng.fix_cell(int(cell))
+            eng.score_triplets(xt, out)
+            torch.cuda.synchronize()
+            np.testing.assert_allclose(out.cpu().numpy(), g["impute/%s" % act_name][n], atol=TOL_FP32, rtol=0)
+        # the implicit enumeration must agree with the explicit list
+        cells0 = [int(c) - 1 for c in g["impute/cells"]]
+        full = eng.impute_to_host(0, ds.n_cells)
+        np.testing.assert_allclose(full[cells0], g["impute/%s" % act_name], atol=TOL_FP32, rtol=0)
+        eng.close()
+
+
+# ------------------------------------------------------------------ synthetic C1-shaped data vs the oracle
+def _random_state(ds, d, seed):
+    """Random-init weights with the reference's shapes (names of the reference state_dict)."""
+    rng = np.random.Generator(np.random.PCG64(seed))
+    C = len(ds.bins)
+    xin = 2 * (C + 1) + ds.cell_feats.shape[-1]
+
+    def U(*shape, fan_in):
+        b = 1.0 / np.sqrt(fan_in)
+        return rng.uniform(-b, b, size=shape).astype(np.float32)
+
+    def ln(name, sd):
+        sd[name + ".weight"] = (1 + 0.2 * rng.standard_normal(d)).astype(np.float32)
+        sd[name + ".bias"] = (0.1 * rng.standard_normal(d)).astype(np.float32)
+
+    sd = {}
+    for nm in ("w_qs", "w_ks", "w_vs"):
+        sd["encode1.mul_head_attn.%s.weight" % nm] = (rng.standard_normal((128, d)) * np.sqrt(2.0 / (d + 16))).astype(np.float32)
+    sd["encode1.mul_head_attn.fc1.w_stack.0.weight"] = U(d, 128, fan_in=128)
+    sd["encode1.mul_head_attn.fc2.w_stack.0.weight"] = U(d, 128, fan_in=128)
+    for nm in ("encode1.mul_head_attn.layer_norm1", "encode1.mul_head_attn.layer_norm2", "encode1.mul_head_attn.layer_norm3",
+               "encode1.pff_n1.layer_norm", "layer_norm1", "layer_norm2"):
+        ln(nm, sd)
+    for i in (0, 1):
+        sd["encode1.pff_n1.w_stack.%d.weight" % i] = U(d, d, 1, fan_in=d)
+        sd["encode1.pff_n1.w_stack.%d.bias" % i] = U(d, fan_in=d)
+    for head in ("pff_classifier", "pff_classifier_var", "pff_classifier_proba"):
+        sd[head + ".w_stack.0.weight"] = U(d // 2, d, 1, fan_in=d)
+        sd[head + ".w_stack.0.bias"] = U(d // 2, fan_in=d)
+        sd[head + ".w_stack.1.weight"] = U(1, d // 2, 1, fan_in=d // 2)
+        sd[head + ".w_stack.1.bias"] = U(1, fan_in=d // 2)
+    sd["encode1.dynamic_nn.nn.weight"] = U(d, 2 * d, fan_in=2 * d)
+    sd["encode1.dynamic_nn.nn.bias"] = U(d, fan_in=2 * d)
+    for xp in ("extra_proba", "extra_proba2", "extra_proba3"):
+        sd[xp + ".w_stack.0.weight"] = U(4, xin, fan_in=xin)
+        sd[xp + ".w_stack.0.bias"] = U(4, fan_in=xin)
+        sd[xp + ".w_stack.1.weight"] = U(1, 4, fan_in=4)
+        sd[xp + ".w_stack.1.bias"] = U(1, fan_in=4)
+    sd["attribute_dict_embedding.weight"] = ds.attribute_dict
+    feats = [ds.cell_embed_feats] + list(ds.bin_feats)
+    for i, f in enumerate(feats):
+        sd["encode1.static_nn.wstack.%d.weight_list.0" % i] = U(d, f.shape[1], fan_in=f.shape[1])
+        sd["encode1.static_nn.wstack.%d.bias_list.0" % i] = U(d, fan_in=f.shape[1])
+    return sd, feats
+
+
+@pytest.mark.parametrize("k,ltr,d", [(0, 0, 64), (4, 0, 64), (3, 1, 128)])
+def test_synthetic_vs_oracle(k, ltr, d):
+    """Seeded synthetic data (two chr1-sized chromosomes): CUDA vs oracle on a handful of cells."""
+    from higashi_b200 import engine as E
+    from higashi_b200 import synthetic as S
+    from oracle import impute as OI
+    from oracle import prep as OP
+    from oracle import scorer as OS
+    ds = S.make_dataset("C1", n_cells=40, bins=[250, 97], seed=5)
+    ds.d = d
+    sd, feats = _random_state(ds, d, seed=42 + d)
+    nbr = nbr_w = None
+    if k > 0:
+        rng = np.random.Generator(np.random.PCG64(9))
+        nbr, nbr_w = OP.cell_neighbors(rng.standard_normal((ds.n_cells, 16)).astype(np.float32), k + 1)
+        nbr_w = nbr_w.astype(np.float32)
+    eng = _engine()
+    eng.load_model(sd, ds.num, feats=feats, cell_feats=ds.cell_feats)
+    eng.set_contacts(ds.csr)
+    eng.set_neighbors(nbr, nbr_w)
+    chroms = [0, 1]
+    eng.set_pairs(chroms, 1, -1)
+    eng.prepare(E.PREC_FP32, ltr, E.ACT_SIGMOID)
+    cells = [0, 17, 39]
+    got_all = eng.impute_to_host(0, ds.n_cells)
+    # oracle
+    tsd = {k_: torch.from_numpy(np.asarray(v)) for k_, v in sd.items()}
+    with torch.no_grad():
+        tables = OS.embed_tables(tsd, feats)
+    big, big_chrom, slices, coords = OI.enumerate_pairs(ds.num_list, chroms, 1, int(1e5))
+    ref = OI.impute_cells(tsd, tables, ds.cell_feats, ds.num_list, lambda c, cell: ds.csr.matrix(c, cell - 1), cells,
+                          chroms, big, ltr, nbr, nbr_w, "sigmoid")
+    assert eng.P == len(big)
+    for j in chroms:
+        assert np.array_equal(eng.coordinates(j), coords[j])
+    np.testing.assert_allclose(got_all[cells], ref, atol=TOL_FP32, rtol=0)
+    eng.close()
