@@ -1,0 +1,352 @@
+#!/usr/bin/env python
+"""bench.py -- imputed (cell, bin_i, bin_j) triplets / s on synthetic scHi-C data (BASELINE.json metric).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload C2]
+
+Workload (N=1): BASELINE.json configs[1] -- synthetic 4DN sci-Hi-C Kim-shaped data, 6000 cells, hg19 @ 1 Mb
+genome-wide (2897 bins, P = 225 023 bin pairs per cell), impute_with_nbr (k = 4), d_model = 64.
+One "step" = one pass of the hot path (K1 gather + projection, K2 fused scorer, K3 scatter) over one batch
+of `--cells-per-step` cells.  Inputs are larger than L2 across steps (every step touches a new cell range
+and writes a fresh [cells, P] fp32 block far above 126 MB).
+
+`value`  : whole-job triplets/s with inputs resident in HBM, device-timed (CUDA events, max over ranks).
+`e2e`    : same metric through the C ABI with HOST buffers: every step uploads the packed contact CSR and
+           kNN lists from pinned host memory and reads the scores back into pinned host memory.
+`--impl reference` : the reference's CPU algorithm (oracle/ port, torch-CPU fp32, all host threads) on a
+           bounded sample of the same workload.
+
+Multi-GPU (torchrun): imputation shards by cell range, one rank per GPU, no data-path collective; every
+rank imputes its own synthetic shard (weak scaling); torch.distributed is only the barrier + max-time.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+FLOP_PER_TRIPLET_TENSOR = 110592.0      # fc1 + pff_n1 + classifier layer 1 at d = 64
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=12)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default="C2")
+    ap.add_argument("--cells-per-step", type=int, default=256)
+    ap.add_argument("--precision", default=os.environ.get("HSG_PRECISION", "auto"))
+    ap.add_argument("--n-cells", type=int, default=0, help="shrink the dataset (debug only; marks the run invalid)")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true")
+    return ap.parse_args()
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md)."""
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index, self.rows, self.proc = index, [], None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append(line.strip())
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        for r in self.rows:
+            f = [x.strip() for x in r.split(",")]
+            if len(f) < 8:
+                continue
+            try:
+                sm.append(float(f[0])); mx.append(float(f[1]))
+            except ValueError:
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[4:8]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        busy = [s for s in sm if s > 0]
+        return {"sm_mhz": float(np.median(busy)) if busy else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def build_dataset(args, rank):
+    from higashi_b200 import synthetic as S
+    kw = {}
+    if args.n_cells:
+        kw["n_cells"] = args.n_cells
+    ds = S.make_dataset(args.workload, shard=rank, **kw)
+    sd, feats = S.random_state_dict(ds, ds.d, seed=0)
+    return ds, sd, feats
+
+
+def knn_lists(ds, k, seed):
+    """kNN cell graph for the synthetic shard (oracle-free: random embeddings -> exact top-k by numpy)."""
+    if k <= 0:
+        return None, None
+    rng = np.random.Generator(np.random.PCG64(seed))
+    emb = rng.standard_normal((ds.n_cells, 16)).astype(np.float32)
+    emb[:, :3] += rng.integers(0, 6, size=(ds.n_cells, 1)) * 2.0
+    x = emb.astype(np.float64)
+    xx = (x * x).sum(-1)
+    d2 = np.maximum(xx[:, None] + xx[None, :] - 2 * x @ x.T, 0)
+    np.fill_diagonal(d2, 0)
+    dist = np.sqrt(d2).astype(np.float32)
+    part = np.argpartition(dist, k + 1, axis=-1)[:, :k + 1]
+    pd = np.take_along_axis(dist, part, axis=-1)
+    order = np.argsort(pd, axis=-1, kind="stable")
+    nbr = np.take_along_axis(part, order, axis=-1)
+    dsel = np.take_along_axis(pd, order, axis=-1)
+    nbr[:, 0] = np.arange(ds.n_cells)          # self first (distance 0)
+    scale = np.quantile(dsel[:, 1:].reshape(-1), 0.25)
+    w = np.exp(-dsel / scale)
+    w = (w / w.sum(-1, keepdims=True)).astype(np.float32)
+    return (nbr + 1).astype(np.int64), w
+
+
+# ------------------------------------------------------------------------------------------ reference arm
+def run_reference(args):
+    import torch
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    from oracle import impute as OI, scorer as OS
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    # the oracle needs only the cells it imputes (+ neighbours): a shrunken shard of the same shape
+    n_small = 64
+    from higashi_b200 import synthetic as S
+    ds = S.make_dataset(args.workload, shard=0, n_cells=n_small)
+    sd, feats = S.random_state_dict(ds, ds.d, seed=0)
+    nbr, w = knn_lists(ds, ds.k, 99)
+    tsd = {k: torch.from_numpy(np.asarray(v)) for k, v in sd.items()}
+    chroms = list(range(len(ds.bins)))
+    with torch.no_grad():
+        tables = OS.embed_tables(tsd, feats)
+    mx = int(1e5) if ds.max_bin < 0 else ds.max_bin
+    big, _, _, _ = OI.enumerate_pairs(ds.num_list, chroms, ds.min_bin, mx)
+    P = len(big)
+    mats = lambda c, cell: ds.csr.matrix(c, cell - 1)
+    cells_per_step = 1
+    times = []
+    for it in range(args.warmup + args.steps):
+        cells = [(it * cells_per_step + q) % n_small for q in range(cells_per_step)]
+        t0 = time.perf_counter()
+        OI.impute_cells(tsd, tables, ds.cell_feats, ds.num_list, mats, cells, chroms, big, 0, nbr, w, "sigmoid")
+        dt = time.perf_counter() - t0
+        if it >= args.warmup:
+            times.append(dt)
+    total = sum(times)
+    val = args.steps * cells_per_step * P / total
+    line = {"impl": "reference", "metric": "imputed (cell,bin_i,bin_j) triplets/s", "value": val, "unit": "triplets/s",
+            "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * total / args.steps,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": "%s: %d-cell sample of the synthetic shape, %d bins, P=%d pairs/cell, k=%d, d=%d"
+                       % (args.workload, n_small, sum(ds.bins), P, ds.k, ds.d)},
+            "cpu_baseline": {"value": val, "unit": "triplets/s", "cores": cores, "kind": "port",
+                             "sample": "%d cell(s) per step x %d steps of %s (oracle/ torch-CPU fp32 restatement of "
+                                       "Impute.impute_process: prep_one + fix_cell2 + predict(batch 1e5))"
+                                       % (cells_per_step, args.steps, args.workload)},
+            "e2e": {"value": val, "unit": "triplets/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0}
+    print(json.dumps(line), flush=True)
+
+
+def cpu_baseline(args, ds_shape):
+    """Bounded CPU sample (oracle port) for the `cpu_baseline` object of the main line."""
+    import torch
+    from higashi_b200 import synthetic as S
+    from oracle import impute as OI, scorer as OS
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    n_small = 48
+    ds = S.make_dataset(args.workload, shard=0, n_cells=n_small)
+    sd, feats = S.random_state_dict(ds, ds.d, seed=0)
+    nbr, w = knn_lists(ds, ds.k, 99)
+    tsd = {k: torch.from_numpy(np.asarray(v)) for k, v in sd.items()}
+    chroms = list(range(len(ds.bins)))
+    with torch.no_grad():
+        tables = OS.embed_tables(tsd, feats)
+    mx = int(1e5) if ds.max_bin < 0 else ds.max_bin
+    big, _, _, _ = OI.enumerate_pairs(ds.num_list, chroms, ds.min_bin, mx)
+    mats = lambda c, cell: ds.csr.matrix(c, cell - 1)
+    OI.impute_cells(tsd, tables, ds.cell_feats, ds.num_list, mats, [0], chroms, big[: 20000], 0, nbr, w, "sigmoid")  # warm-up
+    done, t0 = 0, time.perf_counter()
+    while True:
+        OI.impute_cells(tsd, tables, ds.cell_feats, ds.num_list, mats, [done % n_small], chroms, big, 0, nbr, w, "sigmoid")
+        done += 1
+        el = time.perf_counter() - t0
+        if el > 12.0 or done >= 16:
+            break
+    return {"value": done * len(big) / el, "unit": "triplets/s", "cores": cores, "kind": "port",
+            "sample": "%d cells of %s (P=%d) in %.1f s; oracle/ torch-CPU fp32 port of Impute.impute_process inner loop"
+                      % (done, args.workload, len(big), el)}
+
+
+# ------------------------------------------------------------------------------------------ our arm
+def main():
+    args = parse()
+    if args.impl == "reference":
+        run_reference(args)
+        return
+    import torch
+    import torch.distributed as dist
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    assert torch.cuda.is_available(), "bench.py needs a GPU (no CPU fallback)"
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    from higashi_b200 import engine as E
+
+    ds, sd, feats = build_dataset(args, rank)
+    nbr, w = knn_lists(ds, ds.k, 99 + rank)
+    eng = E.ScorerEngine(local)
+    eng.load_model(sd, ds.num, feats=feats, cell_feats=ds.cell_feats)
+    chroms = list(range(len(ds.bins)))
+    P = eng.set_pairs(chroms, ds.min_bin, ds.max_bin)
+    precision = {"fp32": E.PREC_FP32, "bf16": E.PREC_BF16, "auto": getattr(E, "DEFAULT_PRECISION", E.PREC_FP32)}[args.precision]
+    # pinned host copies of the inputs (for the e2e leg) -- the engine keeps its own device copy
+    pin = lambda a: torch.from_numpy(np.ascontiguousarray(a)).pin_memory()
+    h_rowptr, h_col, h_val = pin(ds.csr.row_ptr), pin(ds.csr.col), pin(ds.csr.val)
+    eng.ctx.set_contacts(h_rowptr.numpy(), h_col.numpy(), h_val.numpy())
+    eng.set_neighbors(nbr, w)
+    eng.prepare(precision, 0, E.ACT_SIGMOID)
+
+    cps = min(args.cells_per_step, ds.n_cells)
+    n_ranges = max(1, ds.n_cells // cps)
+    out = torch.empty((cps, P), dtype=torch.float32, device="cuda")
+    stream = torch.cuda.current_stream()
+
+    def step(i):
+        c0 = (i % n_ranges) * cps
+        eng.impute_to_device(c0, c0 + cps, out, stream.cuda_stream)
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for i in range(args.warmup):
+        step(i)
+    barrier()
+    l0 = eng.ctx.launch_count()
+    sampler = ClockSampler(local)
+    sampler.start()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    ev0.record(stream)
+    for i in range(args.steps):
+        step(args.warmup + i)
+    ev1.record(stream)
+    barrier()
+    clocks = sampler.stop()
+    ms = ev0.elapsed_time(ev1)
+    launches = eng.ctx.launch_count() - l0
+    tmax = torch.tensor([ms], device="cuda")
+    if world > 1:
+        dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
+    ms_all = float(tmax.item())
+    triplets_per_rank = args.steps * cps * P
+    value = world * triplets_per_rank / (ms_all * 1e-3)
+
+    # ---- per-kernel device times (separate pass: the profiling mode synchronises after each batch)
+    eng.ctx.set_profiling(True)
+    stage = np.zeros(4)
+    for i in range(min(args.steps, 4)):
+        step(i)
+        torch.cuda.synchronize()
+        stage += np.array(eng.ctx.last_timing())
+    nprof = min(args.steps, 4)
+    eng.ctx.set_profiling(False)
+    k2_ms_per_step = stage[2] / nprof
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except Exception:
+        pass
+    peak_tf = float(peaks.get("bf16_tflops_sustained", 1400.0))
+    achieved_tf = FLOP_PER_TRIPLET_TENSOR * cps * P / (k2_ms_per_step * 1e-3) / 1e12 * (ds.d / 64.0) ** 2 if k2_ms_per_step > 0 else 0.0
+    roofline = {"kernel": "K2 fused scorer", "bound": "tensor", "achieved": achieved_tf, "peak": peak_tf, "unit": "TFLOP/s",
+                "frac": achieved_tf / peak_tf, "traffic": None,
+                "peak_source": "MEASURED_PEAKS.json bf16_tflops_sustained" if peaks else "fallback 1.4 PFLOP/s sustained",
+                "stage_ms_per_step": {"gather_K1a": stage[0] / nprof, "project_K1b": stage[1] / nprof, "scorer_K2": k2_ms_per_step},
+                "k2_share_of_step": float(stage[2] / max(stage[3], 1e-9))}
+
+    # ---- e2e: host buffers in, host buffers out, through the C ABI
+    e2e = None
+    if not args.no_e2e:
+        h_out = torch.empty((cps, P), dtype=torch.float32).pin_memory()
+        nbr0 = None if nbr is None else np.ascontiguousarray(nbr - 1, dtype=np.int32)
+
+        def e2e_step(i):
+            c0 = (i % n_ranges) * cps
+            eng.ctx.set_contacts(h_rowptr.numpy(), h_col.numpy(), h_val.numpy())      # H2D of the step's inputs
+            if nbr0 is not None:
+                eng.ctx.set_neighbors(nbr0, w)
+            eng.ctx.impute_cells_host_ptr(c0, c0 + cps, h_out.data_ptr())             # compute + D2H of the result
+        for i in range(min(args.warmup, 2)):
+            e2e_step(i)
+        barrier()
+        t0 = time.perf_counter()
+        for i in range(args.steps):
+            e2e_step(args.warmup + i)
+        barrier()
+        dt = time.perf_counter() - t0
+        tt = torch.tensor([dt], device="cuda")
+        if world > 1:
+            dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        h2d = h_rowptr.numel() * 8 + h_col.numel() * 4 + h_val.numel() * 4 + (0 if nbr0 is None else nbr0.size * 8)
+        e2e = {"value": world * triplets_per_rank / float(tt.item()), "unit": "triplets/s",
+               "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(cps * P * 4)}
+
+    if rank == 0:
+        cpu = None
+        if not args.no_cpu_baseline and world == 1:
+            cpu = cpu_baseline(args, ds)
+        line = {"metric": "imputed (cell,bin_i,bin_j) triplets/s", "value": value, "unit": "triplets/s", "n_gpus": world,
+                "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_all / args.steps, "higher_is_better": True,
+                "scaling": "weak", "vs_baseline": None,
+                "dtype": "bf16" if precision == E.PREC_BF16 else "f32", "data": "synthetic",
+                "config": {"workload": "%s: synthetic %d cells x %d bins (%d chromosomes), P=%d pairs/cell, k=%d, d_model=%d, "
+                                       "impute_with_nbr" % (args.workload, ds.n_cells, sum(ds.bins), len(ds.bins), P, ds.k, ds.d),
+                           "cells_per_step": cps, "triplets_per_step": cps * P, "sharding": "cell range per rank, no collective",
+                           "l2_policy": "each step reads a new cell range and writes a fresh %d MB score block (> 126 MB L2)"
+                                        % (cps * P * 4 // (1 << 20))},
+                "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches), "roofline": roofline, "cpu_baseline": cpu}
+        if args.n_cells:
+            line["invalid"] = "dataset shrunk with --n-cells (debug run)"
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

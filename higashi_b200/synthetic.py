@@ -274,3 +274,48 @@ def make_dataset(name: str = "C1", *, n_cells: Optional[int] = None, bins: Optio
         cf = np.log1p(reads.reshape(-1, 1))
         ds.cell_feats = np.concatenate([np.zeros((1, 1)), cf], axis=0).astype(np.float32)
     return ds
+
+
+def random_state_dict(ds: "SynthDataset", d: int, seed: int = 0):
+    """Random-init weights with the reference's state_dict names and shapes (Modules.py constructors:
+    Linear/Conv1d default init U(-1/sqrt(fan_in), 1/sqrt(fan_in)); attention projections N(0, 2/(d+16)),
+    Modules.py:998-1003; LayerNorm affine perturbed so that no term is an identity).
+    Returns (sd, feats) with feats = [cell features, bin features per chromosome]."""
+    rng = np.random.Generator(np.random.PCG64(seed))
+    C = len(ds.bins)
+    xin = 2 * (C + 1) + ds.cell_feats.shape[-1]
+
+    def U(*shape, fan_in):
+        b = 1.0 / np.sqrt(fan_in)
+        return rng.uniform(-b, b, size=shape).astype(np.float32)
+
+    sd = {}
+    for nm in ("w_qs", "w_ks", "w_vs"):
+        sd["encode1.mul_head_attn.%s.weight" % nm] = (rng.standard_normal((128, d)) * np.sqrt(2.0 / (d + 16))).astype(np.float32)
+    sd["encode1.mul_head_attn.fc1.w_stack.0.weight"] = U(d, 128, fan_in=128)
+    sd["encode1.mul_head_attn.fc2.w_stack.0.weight"] = U(d, 128, fan_in=128)
+    for nm in ("encode1.mul_head_attn.layer_norm1", "encode1.mul_head_attn.layer_norm2", "encode1.mul_head_attn.layer_norm3",
+               "encode1.pff_n1.layer_norm", "layer_norm1", "layer_norm2"):
+        sd[nm + ".weight"] = (1 + 0.2 * rng.standard_normal(d)).astype(np.float32)
+        sd[nm + ".bias"] = (0.1 * rng.standard_normal(d)).astype(np.float32)
+    for i in (0, 1):
+        sd["encode1.pff_n1.w_stack.%d.weight" % i] = U(d, d, 1, fan_in=d)
+        sd["encode1.pff_n1.w_stack.%d.bias" % i] = U(d, fan_in=d)
+    for head in ("pff_classifier", "pff_classifier_var", "pff_classifier_proba"):
+        sd[head + ".w_stack.0.weight"] = U(d // 2, d, 1, fan_in=d)
+        sd[head + ".w_stack.0.bias"] = U(d // 2, fan_in=d)
+        sd[head + ".w_stack.1.weight"] = U(1, d // 2, 1, fan_in=d // 2)
+        sd[head + ".w_stack.1.bias"] = U(1, fan_in=d // 2)
+    sd["encode1.dynamic_nn.nn.weight"] = U(d, 2 * d, fan_in=2 * d)
+    sd["encode1.dynamic_nn.nn.bias"] = U(d, fan_in=2 * d)
+    for xp in ("extra_proba", "extra_proba2", "extra_proba3"):
+        sd[xp + ".w_stack.0.weight"] = U(4, xin, fan_in=xin)
+        sd[xp + ".w_stack.0.bias"] = U(4, fan_in=xin)
+        sd[xp + ".w_stack.1.weight"] = U(1, 4, fan_in=4)
+        sd[xp + ".w_stack.1.bias"] = U(1, fan_in=4)
+    sd["attribute_dict_embedding.weight"] = ds.attribute_dict
+    feats = [ds.cell_embed_feats] + list(ds.bin_feats)
+    for i, f in enumerate(feats):
+        sd["encode1.static_nn.wstack.%d.weight_list.0" % i] = U(d, f.shape[1], fan_in=f.shape[1])
+        sd["encode1.static_nn.wstack.%d.bias_list.0" % i] = U(d, fan_in=f.shape[1])
+    return sd, feats

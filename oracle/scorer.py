@@ -21,11 +21,13 @@ parity oracle and an honest CPU baseline:
 `sd` is a dict name -> torch.Tensor with the REFERENCE's state_dict names.
 """
 import math
+import warnings
 
 import numpy as np
 import torch
 import torch.nn.functional as F
 
+warnings.filterwarnings("ignore", message="Sparse invariant checks")
 N_HEAD, D_K, D_V = 8, 16, 16          # Higashi_wrapper.py:834-845
 
 

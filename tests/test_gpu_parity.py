@@ -133,48 +133,8 @@ def test_predict_explicit_triplets(d):
 
 # ------------------------------------------------------------------ synthetic C1-shaped data vs the oracle
 def _random_state(ds, d, seed):
-    """Random-init weights with the reference's shapes (names of the reference state_dict)."""
-    rng = np.random.Generator(np.random.PCG64(seed))
-    C = len(ds.bins)
-    xin = 2 * (C + 1) + ds.cell_feats.shape[-1]
-
-    def U(*shape, fan_in):
-        b = 1.0 / np.sqrt(fan_in)
-        return rng.uniform(-b, b, size=shape).astype(np.float32)
-
-    def ln(name, sd):
-        sd[name + ".weight"] = (1 + 0.2 * rng.standard_normal(d)).astype(np.float32)
-        sd[name + ".bias"] = (0.1 * rng.standard_normal(d)).astype(np.float32)
-
-    sd = {}
-    for nm in ("w_qs", "w_ks", "w_vs"):
-        sd["encode1.mul_head_attn.%s.weight" % nm] = (rng.standard_normal((128, d)) * np.sqrt(2.0 / (d + 16))).astype(np.float32)
-    sd["encode1.mul_head_attn.fc1.w_stack.0.weight"] = U(d, 128, fan_in=128)
-    sd["encode1.mul_head_attn.fc2.w_stack.0.weight"] = U(d, 128, fan_in=128)
-    for nm in ("encode1.mul_head_attn.layer_norm1", "encode1.mul_head_attn.layer_norm2", "encode1.mul_head_attn.layer_norm3",
-               "encode1.pff_n1.layer_norm", "layer_norm1", "layer_norm2"):
-        ln(nm, sd)
-    for i in (0, 1):
-        sd["encode1.pff_n1.w_stack.%d.weight" % i] = U(d, d, 1, fan_in=d)
-        sd["encode1.pff_n1.w_stack.%d.bias" % i] = U(d, fan_in=d)
-    for head in ("pff_classifier", "pff_classifier_var", "pff_classifier_proba"):
-        sd[head + ".w_stack.0.weight"] = U(d // 2, d, 1, fan_in=d)
-        sd[head + ".w_stack.0.bias"] = U(d // 2, fan_in=d)
-        sd[head + ".w_stack.1.weight"] = U(1, d // 2, 1, fan_in=d // 2)
-        sd[head + ".w_stack.1.bias"] = U(1, fan_in=d // 2)
-    sd["encode1.dynamic_nn.nn.weight"] = U(d, 2 * d, fan_in=2 * d)
-    sd["encode1.dynamic_nn.nn.bias"] = U(d, fan_in=2 * d)
-    for xp in ("extra_proba", "extra_proba2", "extra_proba3"):
-        sd[xp + ".w_stack.0.weight"] = U(4, xin, fan_in=xin)
-        sd[xp + ".w_stack.0.bias"] = U(4, fan_in=xin)
-        sd[xp + ".w_stack.1.weight"] = U(1, 4, fan_in=4)
-        sd[xp + ".w_stack.1.bias"] = U(1, fan_in=4)
-    sd["attribute_dict_embedding.weight"] = ds.attribute_dict
-    feats = [ds.cell_embed_feats] + list(ds.bin_feats)
-    for i, f in enumerate(feats):
-        sd["encode1.static_nn.wstack.%d.weight_list.0" % i] = U(d, f.shape[1], fan_in=f.shape[1])
-        sd["encode1.static_nn.wstack.%d.bias_list.0" % i] = U(d, fan_in=f.shape[1])
-    return sd, feats
+    from higashi_b200.synthetic import random_state_dict
+    return random_state_dict(ds, d, seed)
 
 
 @pytest.mark.parametrize("k,ltr,d", [(0, 0, 64), (4, 0, 64), (3, 1, 128)])
