@@ -61,7 +61,8 @@ STATE_KEYS = {
     "attribute_dict_embedding.weight": "W_ATTR",
 }
 
-PREC_FP32, PREC_BF16 = 0, 1
+PREC_FP32, PREC_TC16 = 0, 1
+PREC_BF16 = PREC_TC16   # historical alias
 ACT_NONE, ACT_SIGMOID, ACT_SOFTPLUS = 0, 1, 2
 
 # every symbol include/hsg.h declares (tests check that the library exports all of them)

@@ -4,6 +4,8 @@
 #include <cstring>
 #include <cub/cub.cuh>
 
+#include <cuda_fp16.h>
+
 #include "common.cuh"
 
 static thread_local std::string g_err;
@@ -53,6 +55,7 @@ extern "C" int hsg_create(hsg_ctx** out, int device_ordinal) {
     }
     hsg_ctx* c = new hsg_ctx();
     c->device = device_ordinal;
+    c->n_sm = prop.multiProcessorCount;
     HSG_CUDA(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
     HSG_CUDA(cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking));
     for (int i = 0; i < 8; ++i) HSG_CUDA(cudaEventCreate(&c->ev[i]));
@@ -67,6 +70,11 @@ static void free_derived(hsg_ctx* c) {
     dev_free(c->dw.fc2T); dev_free(c->dw.w0T); dev_free(c->dw.w1T); dev_free(c->dw.c0T);
     dev_free(c->cellQ); dev_free(c->cellK); dev_free(c->cellV); dev_free(c->cellS); dev_free(c->binV); dev_free(c->binS);
     dev_free(c->neigh); dev_free(c->QK); dev_free(c->pair_bias);
+    { __half* p = (__half*)c->QK16; dev_free(p); c->QK16 = nullptr; }
+    { __half* p = (__half*)c->binV16; dev_free(p); c->binV16 = nullptr; }
+    { __half* p = (__half*)c->cellV16; dev_free(p); c->cellV16 = nullptr; }
+    dev_free(c->XS); dev_free(c->binSb); dev_free(c->cellSb); dev_free(c->wimg); dev_free(c->cst);
+    c->use_umma = false;
     dev_free(c->stage_out[0]); dev_free(c->stage_out[1]); c->stage_bytes = 0;
     c->prepared = false;
 }
@@ -389,7 +397,7 @@ static int upload_transposed(float** dst, const std::vector<float>& src, int row
 extern "C" int hsg_prepare(hsg_ctx* c, int precision, int local_transfer_range, int activation) {
     CTX_GUARD(c);
     HSG_CHECK(c->d > 0, "call hsg_set_dims first");
-    HSG_CHECK(precision == HSG_PREC_FP32 || precision == HSG_PREC_BF16, "unknown precision");
+    HSG_CHECK(precision == HSG_PREC_FP32 || precision == HSG_PREC_TC16, "unknown precision");
     HSG_CHECK(local_transfer_range >= 0 && local_transfer_range <= 8, "local_transfer_range out of range");
     HSG_CHECK(activation >= HSG_ACT_NONE && activation <= HSG_ACT_SOFTPLUS, "unknown activation");
     static const int needed[] = {HSG_W_QS, HSG_W_KS, HSG_W_VS, HSG_W_FC1, HSG_W_FC2, HSG_W_ALN1_G, HSG_W_ALN1_B, HSG_W_ALN2_G,
@@ -424,11 +432,44 @@ extern "C" int hsg_prepare(hsg_ctx* c, int precision, int local_transfer_range, 
     // pair bias
     if (dev_alloc(&c->pair_bias, (size_t)std::max<int64_t>(c->P, 1))) return 1;
     if (launch_pair_bias(c, c->stream)) return 1;
-    // batch workspace: keep neigh + QK of a batch within ~96 MB so K2 finds them in L2
-    size_t per_cell = (size_t)c->n_bins * (2 * HSG_HD + d) * sizeof(float);
+    // Tensor-core mode is used where it is proven to hold the 1e-3 score bar with margin: d_model = 64 and the
+    // sigmoid head (max |err| 2.4e-4).  softplus / raw heads pass the logit error through with slope ~1
+    // (measured 1.06e-3), and d_model = 128 has no tcgen05 variant yet: both keep the fp32 kernels.
+    c->use_umma = (precision == HSG_PREC_TC16 && d == 64 && activation == HSG_ACT_SIGMOID);
+    size_t per_cell;
+    if (c->use_umma) {
+        std::vector<unsigned char> wimg(umma_wimg_bytes());
+        std::vector<float> cst(umma_cst_count(), 0.f);
+        umma_build_weights(h->v[HSG_W_FC1].data(), h->v[HSG_W_PFF_W0].data(), h->v[HSG_W_PFF_B0].data(),
+                           h->v[HSG_W_PFF_LN_G].data(), h->v[HSG_W_PFF_LN_B].data(), h->v[HSG_W_PFF_W1].data(),
+                           h->v[HSG_W_PFF_B1].data(), h->v[HSG_W_LN1_G].data(), h->v[HSG_W_CLS_W0].data(),
+                           h->v[HSG_W_CLS_B0].data(), h->v[HSG_W_CLS_W1].data(), h->v[HSG_W_CLS_B1].data(), wimg.data(),
+                           cst.data());
+        if (dev_alloc(&c->wimg, wimg.size()) || dev_alloc(&c->cst, cst.size())) return 1;
+        HSG_CUDA(cudaMemcpy(c->wimg, wimg.data(), wimg.size(), cudaMemcpyHostToDevice));
+        HSG_CUDA(cudaMemcpy(c->cst, cst.data(), cst.size() * sizeof(float), cudaMemcpyHostToDevice));
+        __half *bv = nullptr, *cv = nullptr;
+        if (dev_alloc(&bv, (size_t)c->n_bins * HSG_HD) || dev_alloc(&cv, (size_t)c->n_cells * HSG_HD) ||
+            dev_alloc(&c->binSb, (size_t)c->n_bins * d) || dev_alloc(&c->cellSb, (size_t)c->n_cells * d)) return 1;
+        c->binV16 = bv; c->cellV16 = cv;
+        if (launch_convert_static(c, c->binV, c->binS, c->n_bins, c->binV16, c->binSb, c->stream)) return 1;
+        if (launch_convert_static(c, c->cellV, c->cellS, c->n_cells, c->cellV16, c->cellSb, c->stream)) return 1;
+        per_cell = (size_t)c->n_bins * (2 * HSG_HD * sizeof(__half) + 16 * sizeof(float) + d * sizeof(float));
+    } else {
+        per_cell = (size_t)c->n_bins * (2 * HSG_HD + d) * sizeof(float);
+    }
+    // batch workspace: keep the token tables of a batch within ~96 MB so K2 finds them in L2
     int batch = (int)std::max<size_t>(1, std::min<size_t>(64, (96u << 20) / per_cell));
     c->batch_cells = batch;
-    if (dev_alloc(&c->neigh, (size_t)batch * c->n_bins * d) || dev_alloc(&c->QK, (size_t)batch * c->n_bins * 2 * HSG_HD)) return 1;
+    if (dev_alloc(&c->neigh, (size_t)batch * c->n_bins * d)) return 1;
+    if (c->use_umma) {
+        __half* qk16 = nullptr;
+        if (dev_alloc(&qk16, (size_t)batch * c->n_bins * 2 * HSG_HD) || dev_alloc(&c->XS, (size_t)batch * c->n_bins * 16) ||
+            dev_alloc(&c->QK, (size_t)c->n_bins * 2 * HSG_HD)) return 1;
+        c->QK16 = qk16;
+    } else {
+        if (dev_alloc(&c->QK, (size_t)batch * c->n_bins * 2 * HSG_HD)) return 1;
+    }
     HSG_CUDA(cudaStreamSynchronize(c->stream));
     c->fixed_cell = -1;
     c->prepared = true;
@@ -439,9 +480,10 @@ static int run_batch(hsg_ctx* c, int cell0, int nb, float* out, cudaStream_t s, 
     if (prof) HSG_CUDA(cudaEventRecord(c->ev[0], s));
     if (launch_gather(c, nullptr, cell0, nb, s)) return 1;
     if (prof) HSG_CUDA(cudaEventRecord(c->ev[1], s));
-    if (launch_token_project(c, cell0, nb, s)) return 1;
+    if (launch_token_project(c, cell0, nb, c->use_umma, s)) return 1;
     if (prof) HSG_CUDA(cudaEventRecord(c->ev[2], s));
-    if (launch_score_pairs_f32(c, cell0, nb, out, s)) return 1;
+    if (c->use_umma) { if (launch_score_pairs_umma(c, cell0, nb, out, s)) return 1; }
+    else if (launch_score_pairs_f32(c, cell0, nb, out, s)) return 1;
     if (prof) {
         HSG_CUDA(cudaEventRecord(c->ev[3], s));
         HSG_CUDA(cudaEventSynchronize(c->ev[3]));
@@ -506,7 +548,7 @@ extern "C" int hsg_fix_cell(hsg_ctx* c, int cell_1based, void* stream) {
     HSG_CHECK(cell_1based >= 1 && cell_1based <= c->n_cells, "cell id out of range");
     cudaStream_t s = (cudaStream_t)stream;
     if (launch_gather(c, nullptr, cell_1based - 1, 1, s)) return 1;
-    if (launch_token_project(c, cell_1based - 1, 1, s)) return 1;
+    if (launch_token_project(c, cell_1based - 1, 1, false, s)) return 1;
     c->fixed_cell = cell_1based - 1;
     return 0;
 }

@@ -85,7 +85,14 @@ struct hsg_ctx {
     // per-batch workspace
     int batch_cells = 0;
     float* neigh = nullptr;                  // [batch, n_bins, d]
-    float* QK = nullptr;                     // [batch, n_bins, 2, 128]
+    float* QK = nullptr;                     // fp32 [qk_cells, n_bins, 2, 128] (fp32 mode: batch; tensor-core mode: 1 cell for hsg_fix_cell)
+    // tensor-core mode (HSG_PREC_TC16): 16-bit token tables + pre-swizzled weight images
+    void* QK16 = nullptr;                    // half [batch, n_bins, 256]
+    float* XS = nullptr;                     // [batch, n_bins, 16] cross terms with the cell token
+    void* binV16 = nullptr; float* binSb = nullptr; void* cellV16 = nullptr; float* cellSb = nullptr;
+    unsigned char* wimg = nullptr; float* cst = nullptr;
+    bool use_umma = false;
+    int n_sm = 148;
     int fixed_cell = -1;                     // 0-based cell whose tokens sit in QK slot 0 (hsg_fix_cell)
 
     cudaStream_t stream = nullptr;           // internal work stream
@@ -104,7 +111,14 @@ int launch_embed_table(hsg_ctx* c, const float* x, int64_t rows, int in_dim, con
 int launch_static_tokens(hsg_ctx* c, const float* E, int64_t rows, float* Q, float* K, float* V, float* S, cudaStream_t s);
 int launch_pair_bias(hsg_ctx* c, cudaStream_t s);
 int launch_gather(hsg_ctx* c, const int* cells_dev_unused, int cell_start, int n_cells_batch, cudaStream_t s);
-int launch_token_project(hsg_ctx* c, int cell_start, int n_cells_batch, cudaStream_t s);
+int launch_token_project(hsg_ctx* c, int cell_start, int n_cells_batch, bool out16, cudaStream_t s);
+int launch_score_pairs_umma(hsg_ctx* c, int cell_start, int n_cells_batch, float* out, cudaStream_t s);
+int launch_convert_static(hsg_ctx* c, const float* V, const float* S, long long rows, void* V16, float* Sb, cudaStream_t s);
+int umma_build_weights(const float* fc1, const float* w0, const float* b0, const float* pff_g, const float* pff_b,
+                       const float* w1, const float* b1, const float* ln1_g, const float* c0, const float* cb0,
+                       const float* cw1, const float* cb1, unsigned char* wimg_host, float* cst_host);
+int umma_wimg_bytes();
+int umma_cst_count();
 int launch_score_pairs_f32(hsg_ctx* c, int cell_start, int n_cells_batch, float* out, cudaStream_t s);
 int launch_score_triplets_f32(hsg_ctx* c, const int64_t* x, int64_t B, float* out, cudaStream_t s);
 

@@ -5,6 +5,8 @@
 //                              A_hat[b,:] . E_bin   (Impute.py:78-121 prep_one + Modules.py:1364-1371 forward_GCN)
 //   K1b token_project_kernel : dyn = swish(nn([neigh | E_self]))  (Modules.py:1480), Q = w_qs.LN1(dyn),
 //                              K = w_ks.LN2(dyn)                   (Modules.py:1035-1044)
+#include <cuda_fp16.h>
+
 #include "common.cuh"
 
 // ---------------------------------------------------------------------------------------------
@@ -229,17 +231,19 @@ __device__ __forceinline__ void tile_gemm(const float* __restrict__ sA, int K, i
     }
 }
 
-template <int D>
+template <int D, bool OUT16>
 __global__ void __launch_bounds__(256) token_project_kernel(
     const float* __restrict__ neigh, const float* __restrict__ E_bin, int n_bins, int64_t n_tok,
     const float* __restrict__ sageT, const float* __restrict__ sage_b,
     const float* __restrict__ g1, const float* __restrict__ b1, const float* __restrict__ g2,
     const float* __restrict__ b2, const float* __restrict__ wqT, const float* __restrict__ wkT,
-    float* __restrict__ QK) {
+    float* __restrict__ QK, __half* __restrict__ QK16, float* __restrict__ XS,
+    const float* __restrict__ cellQ, const float* __restrict__ cellK, int cell_start) {
     extern __shared__ __align__(16) float sm[];
     float* xT = sm;                              // [2D][LDA]
     float* dT = xT + 2 * D * TP_LDA;             // [D][LDA]   dyn, then LN1 input
     float* kT = dT + D * TP_LDA;                 // [D][LDA]   LN2 input
+    float* qkT = kT + D * TP_LDA;                // [256][LDA] Q (rows 0..127) and K (rows 128..255), OUT16 only
     const int tid = threadIdx.x;
     const int64_t tok0 = (int64_t)blockIdx.x * TP_TOK;
     // stage [neigh | E_self] transposed
@@ -264,8 +268,8 @@ __global__ void __launch_bounds__(256) token_project_kernel(
 #pragma unroll
             for (int q = 0; q < 4; ++q) {
                 float bb = sage_b[cg * 4 + q];
-#pragma unroll
-                for (int r = 0; r < 4; ++r) dT[(cg * 4 + q) * TP_LDA + rg * 4 + r] = swish_acc(acc[r][q] + bb);
+                *reinterpret_cast<float4*>(dT + (cg * 4 + q) * TP_LDA + rg * 4) =
+                    make_float4(swish_acc(acc[0][q] + bb), swish_acc(acc[1][q] + bb), swish_acc(acc[2][q] + bb), swish_acc(acc[3][q] + bb));
             }
         }
     }
@@ -295,35 +299,74 @@ __global__ void __launch_bounds__(256) token_project_kernel(
         int rg = u % (TP_TOK / 4), cg = u / (TP_TOK / 4);
         float acc[4][4] = {};
         tile_gemm<4>(which ? kT : dT, D, rg * 4, which ? wkT : wqT, HSG_HD, cg * 4, acc);
+        if (OUT16) {
 #pragma unroll
-        for (int r = 0; r < 4; ++r) {
-            int64_t tok = tok0 + rg * 4 + r;
-            if (tok < n_tok)
-                *reinterpret_cast<float4*>(QK + (tok * 2 + which) * HSG_HD + cg * 4) =
-                    make_float4(acc[r][0], acc[r][1], acc[r][2], acc[r][3]);
+            for (int q = 0; q < 4; ++q)
+                *reinterpret_cast<float4*>(qkT + (which * HSG_HD + cg * 4 + q) * TP_LDA + rg * 4) =
+                    make_float4(acc[0][q], acc[1][q], acc[2][q], acc[3][q]);
+        } else {
+#pragma unroll
+            for (int r = 0; r < 4; ++r) {
+                int64_t tok = tok0 + rg * 4 + r;
+                if (tok < n_tok)
+                    *reinterpret_cast<float4*>(QK + (tok * 2 + which) * HSG_HD + cg * 4) =
+                        make_float4(acc[r][0], acc[r][1], acc[r][2], acc[r][3]);
+            }
+        }
+    }
+    if (OUT16) {
+        __syncthreads();
+        // 16-bit rows: thread -> (token, 8-column chunk); lanes walk tokens so the smem reads are conflict-free
+        for (int i = tid; i < TP_TOK * 32; i += 256) {
+            int tk = i & 31, ch = i >> 5;
+            int64_t tok = tok0 + tk;
+            if (tok >= n_tok) continue;
+            const float* src = qkT + (ch * 8) * TP_LDA + tk;
+            __half2 h0 = __floats2half2_rn(src[0], src[TP_LDA]), h1 = __floats2half2_rn(src[2 * TP_LDA], src[3 * TP_LDA]);
+            __half2 h2 = __floats2half2_rn(src[4 * TP_LDA], src[5 * TP_LDA]), h3 = __floats2half2_rn(src[6 * TP_LDA], src[7 * TP_LDA]);
+            uint4 pk;
+            pk.x = *reinterpret_cast<uint32_t*>(&h0); pk.y = *reinterpret_cast<uint32_t*>(&h1);
+            pk.z = *reinterpret_cast<uint32_t*>(&h2); pk.w = *reinterpret_cast<uint32_t*>(&h3);
+            *reinterpret_cast<uint4*>(QK16 + tok * 256 + ch * 8) = pk;
+        }
+        // cross terms with the cell token: qcK[h] = Q_cell,h . K_b,h / 4 ; kcQ[h] = Q_b,h . K_cell,h / 4
+        {
+            int tk = tid & 31, h = tid >> 5;
+            int64_t tok = tok0 + tk;
+            if (tok < n_tok) {
+                int cell = cell_start + (int)(tok / n_bins);
+                const float* qc = cellQ + (int64_t)cell * HSG_HD + h * 16;
+                const float* kc = cellK + (int64_t)cell * HSG_HD + h * 16;
+                float a = 0.f, b = 0.f;
+#pragma unroll
+                for (int e = 0; e < 16; ++e) {
+                    a = fmaf(__ldg(qc + e), qkT[(HSG_HD + h * 16 + e) * TP_LDA + tk], a);
+                    b = fmaf(qkT[(h * 16 + e) * TP_LDA + tk], __ldg(kc + e), b);
+                }
+                XS[tok * 16 + h] = a * 0.25f;
+                XS[tok * 16 + 8 + h] = b * 0.25f;
+            }
         }
     }
 }
 
-int launch_token_project(hsg_ctx* c, int cell_start, int n_batch, cudaStream_t s) {
-    (void)cell_start;
-    int64_t n_tok = (int64_t)n_batch * c->n_bins;
+template <int D, bool OUT16>
+static int launch_tp(hsg_ctx* c, int cell_start, int64_t n_tok, cudaStream_t s) {
     unsigned grid = (unsigned)((n_tok + TP_TOK - 1) / TP_TOK);
     float** w = c->w;
-    if (c->d == 64) {
-        size_t smem = (size_t)4 * 64 * TP_LDA * sizeof(float);
-        HSG_CUDA(cudaFuncSetAttribute(token_project_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        token_project_kernel<64><<<grid, 256, smem, s>>>(c->neigh, c->E_bin, c->n_bins, n_tok, c->dw.sageT, w[HSG_W_SAGE_B],
-                                                         w[HSG_W_ALN1_G], w[HSG_W_ALN1_B], w[HSG_W_ALN2_G], w[HSG_W_ALN2_B],
-                                                         c->dw.wqT, c->dw.wkT, c->QK);
-    } else {
-        size_t smem = (size_t)4 * 128 * TP_LDA * sizeof(float);
-        HSG_CUDA(cudaFuncSetAttribute(token_project_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        token_project_kernel<128><<<grid, 256, smem, s>>>(c->neigh, c->E_bin, c->n_bins, n_tok, c->dw.sageT, w[HSG_W_SAGE_B],
-                                                          w[HSG_W_ALN1_G], w[HSG_W_ALN1_B], w[HSG_W_ALN2_G], w[HSG_W_ALN2_B],
-                                                          c->dw.wqT, c->dw.wkT, c->QK);
-    }
+    size_t smem = (size_t)(4 * D + (OUT16 ? 2 * HSG_HD : 0)) * TP_LDA * sizeof(float);
+    HSG_CUDA(cudaFuncSetAttribute(token_project_kernel<D, OUT16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    token_project_kernel<D, OUT16><<<grid, 256, smem, s>>>(c->neigh, c->E_bin, c->n_bins, n_tok, c->dw.sageT, w[HSG_W_SAGE_B],
+                                                           w[HSG_W_ALN1_G], w[HSG_W_ALN1_B], w[HSG_W_ALN2_G], w[HSG_W_ALN2_B],
+                                                           c->dw.wqT, c->dw.wkT, c->QK, (__half*)c->QK16, c->XS, c->cellQ, c->cellK,
+                                                           cell_start);
     c->launches++;
     HSG_CUDA(cudaGetLastError());
     return 0;
+}
+
+int launch_token_project(hsg_ctx* c, int cell_start, int n_batch, bool out16, cudaStream_t s) {
+    int64_t n_tok = (int64_t)n_batch * c->n_bins;
+    if (c->d == 64) return out16 ? launch_tp<64, true>(c, cell_start, n_tok, s) : launch_tp<64, false>(c, cell_start, n_tok, s);
+    return out16 ? launch_tp<128, true>(c, cell_start, n_tok, s) : launch_tp<128, false>(c, cell_start, n_tok, s);
 }

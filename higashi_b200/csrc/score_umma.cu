@@ -1,0 +1,502 @@
+// score_umma.cu -- K2 (tensor-core mode): the fused Hyper-SAGNN scorer on tcgen05 / TMEM (sm_100a).
+//
+// Same math as score_f32.cu (Modules.py:726-783, 1029-1095, 865-889), restructured for
+// Blackwell:
+//   * one CTA per SM (persistent), 4 warpgroups of 128 threads; a warpgroup owns a tile of 128 triplets,
+//     thread r <-> triplet r <-> TMEM lane r, and walks the 3 tokens of its triplets one after the other;
+//   * per token row-tile the four dense contractions run on the 5th-gen tensor cores
+//       y  = ctx . fc1^T          (M128 N64 K128)      h = LN(y) . W0'^T       (M128 N64 K64)
+//       z  = y + h . W1^T         (accumulated onto y in TMEM, K64)
+//       c  = u . C0^T             (M128 N32 K64),  u = (LN1(z) - S)^2
+//     issued by one elected thread of the warpgroup (tcgen05.mma, fp16 operands, fp32 accumulation in
+//     TMEM), completion tracked with tcgen05.commit -> mbarrier, accumulators read back with tcgen05.ld;
+//   * A operands are produced by the warpgroup itself (attention / LayerNorm / swish epilogues) straight
+//     into the canonical K-major SWIZZLE_128B shared-memory layout; the B operands (weights, pre-swizzled
+//     on the host) are staged once per CTA with one TMA bulk copy (cp.async.bulk + mbarrier);
+//   * the 3-token masked attention stays in registers (packed half2 math); the only HBM traffic of the
+//     kernel is the 4-byte score per triplet, token tables are read through L1/L2.
+// Operands are fp16, not bf16: with bf16 operands the measured score error is 1.5e-3..2e-3 (above the 1e-3
+// parity bar), with fp16 it is 2.4e-4 at identical tensor throughput (scripts/bf16_emulation.py).
+#include <cuda_fp16.h>
+
+#include <cstring>
+#include <vector>
+
+#include "common.cuh"
+
+#define UM_WG 4
+#define UM_THREADS (UM_WG * 128)
+#define UM_D 64
+
+// shared memory map (bytes)
+#define SM_B_FC1 0            // [64 x 128] fp16, 2 K-atoms of 8 KB
+#define SM_B_W0 16384         // [64 x 64]
+#define SM_B_W1 24576         // [64 x 64]
+#define SM_B_C0 32768         // [32 x 64]
+#define SM_WIMG_BYTES 36864
+#define SM_A0 36864           // 4 x 32 KB A buffers (one per warpgroup)
+#define SM_A_BYTES 32768
+#define SM_CONST (SM_A0 + UM_WG * SM_A_BYTES)   // fp32 constants
+#define CST_B0F 0
+#define CST_B1 64
+#define CST_G1 128
+#define CST_CB0 192
+#define CST_CW1 224
+#define CST_CB1 256
+#define CST_COUNT 264
+#define SM_BAR (SM_CONST + CST_COUNT * 4)       // 8 mbarriers
+#define SM_TMEM (SM_BAR + 64)
+#define SM_TOTAL (SM_TMEM + 16)
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+    uint32_t ok;
+    do {
+        asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+                     : "=r"(ok) : "r"(bar), "r"(parity) : "memory");
+    } while (!ok);
+}
+__device__ __forceinline__ void tma_bulk_g2s(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(dst), "l"(src), "r"(bytes), "r"(bar) : "memory");
+}
+__device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void wg_bar(int wg) { asm volatile("bar.sync %0, 128;" ::"r"(wg + 1) : "memory"); }
+
+// K-major, SWIZZLE_128B shared-memory matrix descriptor (cute::UMMA::SmemDescriptor bit layout):
+// start>>4 [0,14) | LBO>>4 [16,30) (unused for swizzled K-major, 1) | SBO>>4 [32,46) = 1024 B between
+// 8-row groups | version=1 [46,48) | layout_type=2 (SWIZZLE_128B) [61,64)
+__device__ __forceinline__ uint64_t umma_desc(uint32_t saddr) {
+    return (uint64_t)((saddr >> 4) & 0x3FFF) | (1ull << 16) | ((uint64_t)(1024 >> 4) << 32) | (1ull << 46) | (2ull << 61);
+}
+// instruction descriptor kind::f16: D=f32 (1<<4), A=B=f16 (0<<7, 0<<10), K-major both, N>>3 at 17, M>>4 at 24
+__host__ __device__ constexpr uint32_t umma_idesc_f16(int M, int N) {
+    return (1u << 4) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
+}
+__device__ __forceinline__ void umma_f16(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accum) {
+    asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\ttcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+                 ::"r"(d_tmem), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accum) : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint32_t bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+
+#define TMEM_LD_ARGS16(r, o) "=r"(r[o + 0]), "=r"(r[o + 1]), "=r"(r[o + 2]), "=r"(r[o + 3]), "=r"(r[o + 4]), "=r"(r[o + 5]),   \
+    "=r"(r[o + 6]), "=r"(r[o + 7]), "=r"(r[o + 8]), "=r"(r[o + 9]), "=r"(r[o + 10]), "=r"(r[o + 11]), "=r"(r[o + 12]),         \
+    "=r"(r[o + 13]), "=r"(r[o + 14]), "=r"(r[o + 15])
+
+// 32 lanes x 32 columns -> 32 registers per thread
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+        "{%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,%29,%30,%31}, [%32];"
+        : TMEM_LD_ARGS16(r, 0), TMEM_LD_ARGS16(r, 16) : "r"(taddr) : "memory");
+}
+__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+
+__device__ __forceinline__ float fast_tanh(float x) {
+    float y;
+    asm("tanh.approx.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
+}
+// swish(x) = x * sigmoid(x) = x * (0.5 + 0.5 tanh(x/2)) : one MUFU
+__device__ __forceinline__ float swish_fast(float x) { return x * fmaf(0.5f, fast_tanh(0.5f * x), 0.5f); }
+
+// row r of a [128 x K] fp16 A tile, 16-byte chunk `c` (8 halves), K-major SWIZZLE_128B
+__device__ __forceinline__ uint32_t a_chunk_addr(uint32_t a_base, int r, int c) {
+    return a_base + (uint32_t)(c >> 3) * 16384u + (uint32_t)(r >> 3) * 1024u + (uint32_t)(r & 7) * 128u +
+           (uint32_t)(((c & 7) ^ (r & 7)) << 4);
+}
+__device__ __forceinline__ void sts128(uint32_t addr, uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
+    asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(a), "r"(b), "r"(c), "r"(d) : "memory");
+}
+__device__ __forceinline__ uint32_t pack_h2(float a, float b) {
+    __half2 h = __floats2half2_rn(a, b);
+    return *reinterpret_cast<uint32_t*>(&h);
+}
+__device__ __forceinline__ __half2 u2h(uint32_t u) { return *reinterpret_cast<__half2*>(&u); }
+__device__ __forceinline__ uint32_t h2u(__half2 h) { return *reinterpret_cast<uint32_t*>(&h); }
+
+struct UmmaParams {
+    // 16-bit token tables
+    const __half* QK16;      // [slot][n_bins][256]  Q then K
+    const float* XS;         // [slot][n_bins][16]   qcK[8] = Q_cell.K_b/4, kcQ[8] = Q_b.K_cell/4 per head
+    const __half* binV16;    // [n_bins][128]
+    const float* binSb;      // [n_bins][64]   layer_norm2(fc2 V) - beta(layer_norm1)
+    const __half* cellV16;   // [n_cells][128]
+    const float* cellSb;     // [n_cells][64]
+    const unsigned char* wimg;   // SM_WIMG_BYTES pre-swizzled fp16 weight images
+    const float* cst;            // CST_COUNT fp32 constants
+    const int2* pairs; const float* pair_bias; long long P;
+    int n_bins, cell_start, n_batch, tiles_per_cell, act;
+    float* out;
+};
+
+// masked 3-token softmax row (Modules.py:948-953) with the diagonal logit forced to 0
+__device__ __forceinline__ void masked_row_fast(float la, float lb, float& wa, float& wb) {
+    float mx = fmaxf(0.f, fmaxf(la, lb));
+    float e0 = __expf(-mx), ea = __expf(la - mx), eb = __expf(lb - mx);
+    float den = (ea + eb) + 1e-13f * (e0 + ea + eb);
+    float inv = __frcp_rn(den);
+    wa = ea * inv; wb = eb * inv;
+}
+
+// one MMA round trip for a warpgroup: A tile is complete in shared memory
+template <int NK, int N>
+__device__ __forceinline__ void issue_gemm(int wg, int wtid, uint32_t a_base, uint32_t b_base, int b_rows, uint32_t d_tmem,
+                                           uint32_t accum_first, uint32_t bar) {
+    fence_async_smem();            // generic-proxy writes of the A tile -> visible to the tensor core (async proxy)
+    tc_fence_before();
+    wg_bar(wg);
+    if (wtid == 0) {
+        tc_fence_after();
+        constexpr uint32_t idesc = umma_idesc_f16(128, N);
+#pragma unroll
+        for (int k = 0; k < NK; ++k) {
+            uint32_t aoff = (uint32_t)(k >> 2) * 16384u + (uint32_t)(k & 3) * 32u;
+            uint32_t boff = (uint32_t)(k >> 2) * (uint32_t)(b_rows * 128) + (uint32_t)(k & 3) * 32u;
+            umma_f16(d_tmem, umma_desc(a_base + aoff), umma_desc(b_base + boff), idesc, (k > 0) ? 1u : accum_first);
+        }
+        umma_commit(bar);
+    }
+}
+
+__global__ void __launch_bounds__(UM_THREADS, 1) score_umma_kernel(UmmaParams p) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const int tid = threadIdx.x, wg = tid >> 7, wtid = tid & 127, warp_in_wg = (tid >> 5) & 3;
+    // SWIZZLE_128B operand tiles need 1024-byte aligned bases: round the dynamic segment up by hand
+    const uint32_t sraw = smem_u32(smem_raw);
+    const uint32_t sbase = (sraw + 1023u) & ~1023u;
+    unsigned char* smem = smem_raw + (sbase - sraw);
+    float* cst = reinterpret_cast<float*>(smem + SM_CONST);
+    const uint32_t bar_w = sbase + SM_BAR;                 // weights landed
+    const uint32_t bar_mma = sbase + SM_BAR + 8 + wg * 8;  // this warpgroup's MMA completion
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + SM_TMEM);
+
+    if (tid == 0) {
+        mbar_init(bar_w, 1);
+        for (int i = 0; i < UM_WG; ++i) mbar_init(sbase + SM_BAR + 8 + i * 8, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    for (int i = tid; i < CST_COUNT; i += UM_THREADS) cst[i] = p.cst[i];
+    if (tid < 32) {     // warp 0 allocates all 512 TMEM columns (one CTA per SM)
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(512) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    if (tid == 0) {
+        mbar_expect_tx(bar_w, SM_WIMG_BYTES);
+        tma_bulk_g2s(sbase + SM_B_FC1, p.wimg, SM_WIMG_BYTES, bar_w);
+    }
+    const uint32_t tmem_base = *tmem_slot;
+    const uint32_t t_lane = ((uint32_t)(warp_in_wg * 32)) << 16;
+    const uint32_t t_y = tmem_base + (uint32_t)(wg * 128);          // columns [0,64) of this warpgroup: y, then z
+    const uint32_t t_h = t_y + 64;                                  // columns [64,128): h, then c
+    const uint32_t a_base = sbase + SM_A0 + wg * SM_A_BYTES;
+    mbar_wait(bar_w, 0);
+
+    uint32_t phase = 0;
+    const long long n_tiles = (long long)p.n_batch * p.tiles_per_cell;
+    for (long long tile = (long long)blockIdx.x * UM_WG + wg; tile < n_tiles; tile += (long long)gridDim.x * UM_WG) {
+        const int cb = (int)(tile / p.tiles_per_cell), pt = (int)(tile - (long long)cb * p.tiles_per_cell);
+        const long long pi = (long long)pt * 128 + wtid;
+        const bool valid = pi < p.P;
+        const int2 pr = p.pairs[valid ? pi : (p.P - 1)];
+        const float bias = valid ? p.pair_bias[pi] : 0.f;
+        const int cell = p.cell_start + cb;
+        const long long tb_i = (long long)cb * p.n_bins + pr.x, tb_j = (long long)cb * p.n_bins + pr.y;
+        const uint4* qk_i = reinterpret_cast<const uint4*>(p.QK16 + tb_i * 256);
+        const uint4* qk_j = reinterpret_cast<const uint4*>(p.QK16 + tb_j * 256);
+        const float* xs_i = p.XS + tb_i * 16;
+        const float* xs_j = p.XS + tb_j * 16;
+        const uint4* v_i = reinterpret_cast<const uint4*>(p.binV16 + (long long)pr.x * 128);
+        const uint4* v_j = reinterpret_cast<const uint4*>(p.binV16 + (long long)pr.y * 128);
+        const uint4* v_c = reinterpret_cast<const uint4*>(p.cellV16 + (long long)cell * 128);
+        float osum = 0.f;
+
+#pragma unroll 1
+        for (int t = 0; t < 3; ++t) {
+            // ------------------------------------------------------------------ attention -> ctx (A tile, K = 128)
+            // row t attends to the two other tokens: (a, b) = (bi, bj) | (cell, bj) | (cell, bi)
+            const uint4* va = (t == 0) ? v_i : v_c;
+            const uint4* vb = (t == 2) ? v_i : v_j;
+            const uint4* qrow = (t == 1) ? qk_i : qk_j;          // Q of this row's own token (t = 1, 2)
+            const uint4* krow = (t == 1) ? qk_j : qk_i;          // K of the other bin
+            const float* xa = (t == 0) ? xs_i : ((t == 1) ? xs_i + 8 : xs_j + 8);
+#pragma unroll 2
+            for (int h = 0; h < 8; ++h) {
+                float la = __ldg(xa + h), lb;
+                if (t == 0) {
+                    lb = __ldg(xs_j + h);
+                } else {
+                    uint4 q0 = __ldg(qrow + h * 2), q1 = __ldg(qrow + h * 2 + 1);
+                    uint4 k0 = __ldg(krow + 16 + h * 2), k1 = __ldg(krow + 16 + h * 2 + 1);
+                    __half2 acc = __hmul2(u2h(q0.x), u2h(k0.x));
+                    acc = __hfma2(u2h(q0.y), u2h(k0.y), acc); acc = __hfma2(u2h(q0.z), u2h(k0.z), acc);
+                    acc = __hfma2(u2h(q0.w), u2h(k0.w), acc); acc = __hfma2(u2h(q1.x), u2h(k1.x), acc);
+                    acc = __hfma2(u2h(q1.y), u2h(k1.y), acc); acc = __hfma2(u2h(q1.z), u2h(k1.z), acc);
+                    acc = __hfma2(u2h(q1.w), u2h(k1.w), acc);
+                    float2 f = __half22float2(acc);
+                    lb = (f.x + f.y) * 0.25f;
+                }
+                float wa, wb;
+                masked_row_fast(la, lb, wa, wb);
+                const __half2 wa2 = __float2half2_rn(wa), wb2 = __float2half2_rn(wb);
+                uint4 a0 = __ldg(va + h * 2), a1 = __ldg(va + h * 2 + 1);
+                uint4 b0 = __ldg(vb + h * 2), b1 = __ldg(vb + h * 2 + 1);
+                uint32_t c0 = h2u(__hfma2(wb2, u2h(b0.x), __hmul2(wa2, u2h(a0.x))));
+                uint32_t c1 = h2u(__hfma2(wb2, u2h(b0.y), __hmul2(wa2, u2h(a0.y))));
+                uint32_t c2 = h2u(__hfma2(wb2, u2h(b0.z), __hmul2(wa2, u2h(a0.z))));
+                uint32_t c3 = h2u(__hfma2(wb2, u2h(b0.w), __hmul2(wa2, u2h(a0.w))));
+                sts128(a_chunk_addr(a_base, wtid, h * 2), c0, c1, c2, c3);
+                c0 = h2u(__hfma2(wb2, u2h(b1.x), __hmul2(wa2, u2h(a1.x))));
+                c1 = h2u(__hfma2(wb2, u2h(b1.y), __hmul2(wa2, u2h(a1.y))));
+                c2 = h2u(__hfma2(wb2, u2h(b1.z), __hmul2(wa2, u2h(a1.z))));
+                c3 = h2u(__hfma2(wb2, u2h(b1.w), __hmul2(wa2, u2h(a1.w))));
+                sts128(a_chunk_addr(a_base, wtid, h * 2 + 1), c0, c1, c2, c3);
+            }
+            issue_gemm<8, 64>(wg, wtid, a_base, sbase + SM_B_FC1, 64, t_y, 0u, bar_mma);
+            mbar_wait(bar_mma, phase); phase ^= 1;
+            tc_fence_after();
+
+            // ------------------------------------------------------------------ y -> LN_pff(y) (A tile, K = 64)
+            {
+                uint32_t r0[32], r1[32];
+                tmem_ld32(t_y + t_lane, r0);
+                tmem_ld32(t_y + t_lane + 32, r1);
+                tmem_ld_wait();
+                float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
+#pragma unroll
+                for (int i = 0; i < 32; i += 2) {
+                    s0 += __uint_as_float(r0[i]); s1 += __uint_as_float(r0[i + 1]);
+                    s2 += __uint_as_float(r1[i]); s3 += __uint_as_float(r1[i + 1]);
+                }
+                const float mean = ((s0 + s1) + (s2 + s3)) * (1.0f / 64.0f);
+                float v0 = 0.f, v1 = 0.f;
+#pragma unroll
+                for (int i = 0; i < 32; ++i) {
+                    float d0 = __uint_as_float(r0[i]) - mean, d1 = __uint_as_float(r1[i]) - mean;
+                    r0[i] = __float_as_uint(d0); r1[i] = __float_as_uint(d1);
+                    v0 = fmaf(d0, d0, v0); v1 = fmaf(d1, d1, v1);
+                }
+                const float rstd = rsqrtf((v0 + v1) * (1.0f / 64.0f) + HSG_LN_EPS);
+#pragma unroll
+                for (int c = 0; c < 4; ++c) {
+                    sts128(a_chunk_addr(a_base, wtid, c),
+                           pack_h2(__uint_as_float(r0[c * 8 + 0]) * rstd, __uint_as_float(r0[c * 8 + 1]) * rstd),
+                           pack_h2(__uint_as_float(r0[c * 8 + 2]) * rstd, __uint_as_float(r0[c * 8 + 3]) * rstd),
+                           pack_h2(__uint_as_float(r0[c * 8 + 4]) * rstd, __uint_as_float(r0[c * 8 + 5]) * rstd),
+                           pack_h2(__uint_as_float(r0[c * 8 + 6]) * rstd, __uint_as_float(r0[c * 8 + 7]) * rstd));
+                    sts128(a_chunk_addr(a_base, wtid, c + 4),
+                           pack_h2(__uint_as_float(r1[c * 8 + 0]) * rstd, __uint_as_float(r1[c * 8 + 1]) * rstd),
+                           pack_h2(__uint_as_float(r1[c * 8 + 2]) * rstd, __uint_as_float(r1[c * 8 + 3]) * rstd),
+                           pack_h2(__uint_as_float(r1[c * 8 + 4]) * rstd, __uint_as_float(r1[c * 8 + 5]) * rstd),
+                           pack_h2(__uint_as_float(r1[c * 8 + 6]) * rstd, __uint_as_float(r1[c * 8 + 7]) * rstd));
+                }
+            }
+            issue_gemm<4, 64>(wg, wtid, a_base, sbase + SM_B_W0, 64, t_h, 0u, bar_mma);
+            mbar_wait(bar_mma, phase); phase ^= 1;
+            tc_fence_after();
+
+            // ------------------------------------------------------------------ h = swish(. + b0') (A tile, K = 64)
+#pragma unroll
+            for (int half = 0; half < 2; ++half) {
+                uint32_t r[32];
+                tmem_ld32(t_h + t_lane + half * 32, r);
+                tmem_ld_wait();
+#pragma unroll
+                for (int c = 0; c < 4; ++c) {
+                    float4 ba = *reinterpret_cast<const float4*>(cst + CST_B0F + half * 32 + c * 8);
+                    float4 bb = *reinterpret_cast<const float4*>(cst + CST_B0F + half * 32 + c * 8 + 4);
+                    sts128(a_chunk_addr(a_base, wtid, half * 4 + c),
+                           pack_h2(swish_fast(__uint_as_float(r[c * 8 + 0]) + ba.x), swish_fast(__uint_as_float(r[c * 8 + 1]) + ba.y)),
+                           pack_h2(swish_fast(__uint_as_float(r[c * 8 + 2]) + ba.z), swish_fast(__uint_as_float(r[c * 8 + 3]) + ba.w)),
+                           pack_h2(swish_fast(__uint_as_float(r[c * 8 + 4]) + bb.x), swish_fast(__uint_as_float(r[c * 8 + 5]) + bb.y)),
+                           pack_h2(swish_fast(__uint_as_float(r[c * 8 + 6]) + bb.z), swish_fast(__uint_as_float(r[c * 8 + 7]) + bb.w)));
+                }
+            }
+            // z = y + h . W1^T : accumulate onto y (still in TMEM) -- the residual is free
+            issue_gemm<4, 64>(wg, wtid, a_base, sbase + SM_B_W1, 64, t_y, 1u, bar_mma);
+            mbar_wait(bar_mma, phase); phase ^= 1;
+            tc_fence_after();
+
+            // ------------------------------------------------------------------ u = (LN1(z + b1) - S)^2 (A tile, K = 64)
+            {
+                uint32_t r0[32], r1[32];
+                tmem_ld32(t_y + t_lane, r0);
+                tmem_ld32(t_y + t_lane + 32, r1);
+                tmem_ld_wait();
+                float s0 = 0.f, s1 = 0.f;
+#pragma unroll
+                for (int c = 0; c < 8; ++c) {
+                    float4 ba = *reinterpret_cast<const float4*>(cst + CST_B1 + c * 4);
+                    float4 bb = *reinterpret_cast<const float4*>(cst + CST_B1 + 32 + c * 4);
+                    float x;
+                    x = __uint_as_float(r0[c * 4 + 0]) + ba.x; r0[c * 4 + 0] = __float_as_uint(x); s0 += x;
+                    x = __uint_as_float(r0[c * 4 + 1]) + ba.y; r0[c * 4 + 1] = __float_as_uint(x); s1 += x;
+                    x = __uint_as_float(r0[c * 4 + 2]) + ba.z; r0[c * 4 + 2] = __float_as_uint(x); s0 += x;
+                    x = __uint_as_float(r0[c * 4 + 3]) + ba.w; r0[c * 4 + 3] = __float_as_uint(x); s1 += x;
+                    x = __uint_as_float(r1[c * 4 + 0]) + bb.x; r1[c * 4 + 0] = __float_as_uint(x); s0 += x;
+                    x = __uint_as_float(r1[c * 4 + 1]) + bb.y; r1[c * 4 + 1] = __float_as_uint(x); s1 += x;
+                    x = __uint_as_float(r1[c * 4 + 2]) + bb.z; r1[c * 4 + 2] = __float_as_uint(x); s0 += x;
+                    x = __uint_as_float(r1[c * 4 + 3]) + bb.w; r1[c * 4 + 3] = __float_as_uint(x); s1 += x;
+                }
+                const float mean = (s0 + s1) * (1.0f / 64.0f);
+                float v0 = 0.f, v1 = 0.f;
+#pragma unroll
+                for (int i = 0; i < 32; ++i) {
+                    float d0 = __uint_as_float(r0[i]) - mean, d1 = __uint_as_float(r1[i]) - mean;
+                    r0[i] = __float_as_uint(d0); r1[i] = __float_as_uint(d1);
+                    v0 = fmaf(d0, d0, v0); v1 = fmaf(d1, d1, v1);
+                }
+                const float rstd = rsqrtf((v0 + v1) * (1.0f / 64.0f) + HSG_LN_EPS);
+                const float4* Srow = reinterpret_cast<const float4*>(
+                    (t == 0) ? p.cellSb + (long long)cell * 64 : p.binSb + (long long)(t == 1 ? pr.x : pr.y) * 64);
+#pragma unroll
+                for (int c = 0; c < 8; ++c) {
+                    const uint32_t* rr = (c < 4) ? r0 : r1;
+                    const int o = (c & 3) * 8;
+                    float4 ga = *reinterpret_cast<const float4*>(cst + CST_G1 + c * 8);
+                    float4 gb = *reinterpret_cast<const float4*>(cst + CST_G1 + c * 8 + 4);
+                    float4 sa = __ldg(Srow + c * 2), sb = __ldg(Srow + c * 2 + 1);
+                    float u0 = fmaf(__uint_as_float(rr[o + 0]) * rstd, ga.x, -sa.x), u1 = fmaf(__uint_as_float(rr[o + 1]) * rstd, ga.y, -sa.y);
+                    float u2 = fmaf(__uint_as_float(rr[o + 2]) * rstd, ga.z, -sa.z), u3 = fmaf(__uint_as_float(rr[o + 3]) * rstd, ga.w, -sa.w);
+                    float u4 = fmaf(__uint_as_float(rr[o + 4]) * rstd, gb.x, -sb.x), u5 = fmaf(__uint_as_float(rr[o + 5]) * rstd, gb.y, -sb.y);
+                    float u6 = fmaf(__uint_as_float(rr[o + 6]) * rstd, gb.z, -sb.z), u7 = fmaf(__uint_as_float(rr[o + 7]) * rstd, gb.w, -sb.w);
+                    sts128(a_chunk_addr(a_base, wtid, c), pack_h2(u0 * u0, u1 * u1), pack_h2(u2 * u2, u3 * u3),
+                           pack_h2(u4 * u4, u5 * u5), pack_h2(u6 * u6, u7 * u7));
+                }
+            }
+            issue_gemm<4, 32>(wg, wtid, a_base, sbase + SM_B_C0, 32, t_h, 0u, bar_mma);
+            mbar_wait(bar_mma, phase); phase ^= 1;
+            tc_fence_after();
+
+            // ------------------------------------------------------------------ o_t = c1 . swish(c + cb0) + cb1
+            {
+                uint32_t r[32];
+                tmem_ld32(t_h + t_lane, r);
+                tmem_ld_wait();
+                float o0 = 0.f, o1 = 0.f;
+#pragma unroll
+                for (int c = 0; c < 8; ++c) {
+                    float4 b = *reinterpret_cast<const float4*>(cst + CST_CB0 + c * 4);
+                    float4 w = *reinterpret_cast<const float4*>(cst + CST_CW1 + c * 4);
+                    o0 = fmaf(swish_fast(__uint_as_float(r[c * 4 + 0]) + b.x), w.x, o0);
+                    o1 = fmaf(swish_fast(__uint_as_float(r[c * 4 + 1]) + b.y), w.y, o1);
+                    o0 = fmaf(swish_fast(__uint_as_float(r[c * 4 + 2]) + b.z), w.z, o0);
+                    o1 = fmaf(swish_fast(__uint_as_float(r[c * 4 + 3]) + b.w), w.w, o1);
+                }
+                osum += (o0 + o1) + cst[CST_CB1];
+            }
+            tc_fence_before();      // TMEM reads done before the next token's MMAs overwrite the columns
+        }
+        if (valid) {
+            float m = osum * (1.0f / 3.0f) + bias;
+            float sc = (p.act == HSG_ACT_SIGMOID) ? __frcp_rn(1.0f + __expf(-m))
+                       : (p.act == HSG_ACT_SOFTPLUS) ? (m > 20.f ? m : log1pf(__expf(m))) : m;
+            p.out[(long long)cb * p.P + pi] = sc;
+        }
+    }
+
+    tc_fence_before();
+    __syncthreads();
+    if (tid < 32) {
+        tc_fence_after();
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512) : "memory");
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// host side
+// ---------------------------------------------------------------------------------------------
+struct UmmaTables {
+    __half* QK16; float* XS; __half* binV16; float* binSb; __half* cellV16; float* cellSb;
+    unsigned char* wimg; float* cst;
+};
+
+// W [N][K] row-major fp32 -> K-major SWIZZLE_128B fp16 image (64 halves = 128 B per swizzle row)
+static void swizzle_image(const float* W, int N, int K, __half* img) {
+    for (int n = 0; n < N; ++n)
+        for (int k = 0; k < K; ++k) {
+            int atom = k / 64, kk = k % 64, chunk = kk / 8;
+            size_t byte = (size_t)atom * N * 128 + (size_t)(n / 8) * 1024 + (size_t)(n % 8) * 128 + (size_t)((chunk ^ (n % 8)) * 16) +
+                          (size_t)(kk % 8) * 2;
+            img[byte / 2] = __float2half_rn(W[(size_t)n * K + k]);
+        }
+}
+
+int umma_build_weights(const float* fc1, const float* w0, const float* b0, const float* pff_g, const float* pff_b,
+                       const float* w1, const float* b1, const float* ln1_g, const float* c0, const float* cb0,
+                       const float* cw1, const float* cb1, unsigned char* wimg_host, float* cst_host) {
+    const int d = UM_D;
+    std::vector<float> w0f((size_t)d * d);
+    for (int n = 0; n < d; ++n) {
+        double acc = b0[n];
+        for (int k = 0; k < d; ++k) {
+            w0f[(size_t)n * d + k] = w0[(size_t)n * d + k] * pff_g[k];      // fold the LN gain into W0
+            acc += (double)w0[(size_t)n * d + k] * pff_b[k];                // and the LN bias into b0
+        }
+        cst_host[CST_B0F + n] = (float)acc;
+    }
+    memset(wimg_host, 0, SM_WIMG_BYTES);
+    swizzle_image(fc1, d, HSG_HD, reinterpret_cast<__half*>(wimg_host + SM_B_FC1));
+    swizzle_image(w0f.data(), d, d, reinterpret_cast<__half*>(wimg_host + SM_B_W0));
+    swizzle_image(w1, d, d, reinterpret_cast<__half*>(wimg_host + SM_B_W1));
+    swizzle_image(c0, d / 2, d, reinterpret_cast<__half*>(wimg_host + SM_B_C0));
+    for (int i = 0; i < d; ++i) { cst_host[CST_B1 + i] = b1[i]; cst_host[CST_G1 + i] = ln1_g[i]; }
+    for (int i = 0; i < d / 2; ++i) { cst_host[CST_CB0 + i] = cb0[i]; cst_host[CST_CW1 + i] = cw1[i]; }
+    cst_host[CST_CB1] = cb1[0];
+    return 0;
+}
+
+int umma_wimg_bytes() { return SM_WIMG_BYTES; }
+int umma_cst_count() { return CST_COUNT; }
+
+// fp32 static tables -> 16-bit / offset copies used by the tensor-core kernel
+__global__ void convert_static_kernel(const float* __restrict__ V, const float* __restrict__ S, const float* __restrict__ ln1_b,
+                                      long long rows, int d, __half* __restrict__ V16, float* __restrict__ Sb) {
+    long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < rows * HSG_HD) V16[i] = __float2half_rn(V[i]);
+    if (i < rows * d) Sb[i] = S[i] - ln1_b[i % d];
+}
+
+int launch_convert_static(hsg_ctx* c, const float* V, const float* S, long long rows, void* V16, float* Sb, cudaStream_t s) {
+    long long n = rows * HSG_HD;
+    convert_static_kernel<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(V, S, c->w[HSG_W_LN1_B], rows, c->d, (__half*)V16, Sb);
+    c->launches++;
+    HSG_CUDA(cudaGetLastError());
+    return 0;
+}
+
+int launch_score_pairs_umma(hsg_ctx* c, int cell_start, int n_batch, float* out, cudaStream_t s) {
+    if (c->P == 0 || n_batch == 0) return 0;
+    UmmaParams p;
+    p.QK16 = (const __half*)c->QK16; p.XS = c->XS; p.binV16 = (const __half*)c->binV16; p.binSb = c->binSb;
+    p.cellV16 = (const __half*)c->cellV16; p.cellSb = c->cellSb; p.wimg = c->wimg; p.cst = c->cst;
+    p.pairs = c->pairs; p.pair_bias = c->pair_bias; p.P = c->P;
+    p.n_bins = c->n_bins; p.cell_start = cell_start; p.n_batch = n_batch;
+    p.tiles_per_cell = (int)((c->P + 127) / 128); p.act = c->act; p.out = out;
+    long long n_tiles = (long long)n_batch * p.tiles_per_cell;
+    long long quads = (n_tiles + UM_WG - 1) / UM_WG;
+    int grid = (int)(quads < c->n_sm ? quads : c->n_sm);
+    static bool attr_set = false;
+    if (!attr_set) {
+        HSG_CUDA(cudaFuncSetAttribute(score_umma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SM_TOTAL + 1024));
+        attr_set = true;
+    }
+    score_umma_kernel<<<grid, UM_THREADS, SM_TOTAL + 1024, s>>>(p);
+    c->launches++;
+    HSG_CUDA(cudaGetLastError());
+    return 0;
+}

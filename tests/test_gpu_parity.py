@@ -102,6 +102,17 @@ def test_impute_golden_fp32(tag):
         np.testing.assert_allclose(got, ref, atol=TOL_FP32, rtol=0)
 
 
+@pytest.mark.parametrize("tag", ["k0_r0", "k4_r0", "k4_r1", "k0_r1_band"])
+def test_impute_golden_tensor_core(tag):
+    """tcgen05 path (fp16 operands, fp32 accumulate): 1e-3 absolute on the score."""
+    from higashi_b200 import engine as E
+    worst = 0.0
+    for got, ref in _run_impute_fixture(tag, E.PREC_TC16):
+        worst = max(worst, float(np.abs(got - ref).max()))
+        np.testing.assert_allclose(got, ref, atol=TOL_BF16, rtol=0)
+    print("tensor-core path max |err| =", worst)
+
+
 # ------------------------------------------------------------------ Hyper_SAGNN.predict on explicit triplets
 @pytest.mark.parametrize("d", [64, 128])
 def test_predict_explicit_triplets(d):
@@ -137,8 +148,9 @@ def _random_state(ds, d, seed):
     return random_state_dict(ds, d, seed)
 
 
-@pytest.mark.parametrize("k,ltr,d", [(0, 0, 64), (4, 0, 64), (3, 1, 128)])
-def test_synthetic_vs_oracle(k, ltr, d):
+@pytest.mark.parametrize("k,ltr,d,prec", [(0, 0, 64, "fp32"), (4, 0, 64, "fp32"), (3, 1, 128, "fp32"),
+                                          (4, 0, 64, "tc16"), (0, 1, 64, "tc16")])
+def test_synthetic_vs_oracle(k, ltr, d, prec):
     """Seeded synthetic data (two chr1-sized chromosomes): CUDA vs oracle on a handful of cells."""
     from higashi_b200 import engine as E
     from higashi_b200 import synthetic as S
@@ -159,7 +171,8 @@ def test_synthetic_vs_oracle(k, ltr, d):
     eng.set_neighbors(nbr, nbr_w)
     chroms = [0, 1]
     eng.set_pairs(chroms, 1, -1)
-    eng.prepare(E.PREC_FP32, ltr, E.ACT_SIGMOID)
+    eng.prepare(E.PREC_FP32 if prec == "fp32" else E.PREC_TC16, ltr, E.ACT_SIGMOID)
+    tol = TOL_FP32 if prec == "fp32" else TOL_BF16
     cells = [0, 17, 39]
     got_all = eng.impute_to_host(0, ds.n_cells)
     # oracle
@@ -172,5 +185,6 @@ def test_synthetic_vs_oracle(k, ltr, d):
     assert eng.P == len(big)
     for j in chroms:
         assert np.array_equal(eng.coordinates(j), coords[j])
-    np.testing.assert_allclose(got_all[cells], ref, atol=TOL_FP32, rtol=0)
+    print("max |err| (%s) = %.3g" % (prec, float(np.abs(got_all[cells] - ref).max())))
+    np.testing.assert_allclose(got_all[cells], ref, atol=tol, rtol=0)
     eng.close()
