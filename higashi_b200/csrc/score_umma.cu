@@ -131,13 +131,13 @@ struct UmmaParams {
     const __half* QK16;      // [slot][n_bins][256]  Q then K
     const float* XS;         // [slot][n_bins][16]   qcK[8] = Q_cell.K_b/4, kcQ[8] = Q_b.K_cell/4 per head
     const __half* binV16;    // [n_bins][128]
-    const float* binSb;      // [n_bins][64]   layer_norm2(fc2 V) - beta(layer_norm1)
+    const float* binSb;      // [64][n_bins]   feature-major: layer_norm2(fc2 V) - beta(layer_norm1)
     const __half* cellV16;   // [n_cells][128]
-    const float* cellSb;     // [n_cells][64]
+    const float* cellSb;     // [64][n_cells]  feature-major
     const unsigned char* wimg;   // SM_WIMG_BYTES pre-swizzled fp16 weight images
     const float* cst;            // CST_COUNT fp32 constants
     const int2* pairs; const float* pair_bias; long long P;
-    int n_bins, cell_start, n_batch, tiles_per_cell, act;
+    int n_bins, n_cells, cell_start, n_batch, tiles_per_cell, act;
     float* out;
 };
 
@@ -172,7 +172,7 @@ __device__ __forceinline__ void issue_gemm(int wg, int wtid, uint32_t a_base, ui
 
 __global__ void __launch_bounds__(UM_THREADS, 1) score_umma_kernel(UmmaParams p) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    const int tid = threadIdx.x, wg = tid >> 7, wtid = tid & 127, warp_in_wg = (tid >> 5) & 3;
+    const int tid = threadIdx.x, wg = tid >> 7, wtid = tid & 127, warp_in_wg = (tid >> 5) & 3, lane = tid & 31;
     // SWIZZLE_128B operand tiles need 1024-byte aligned bases: round the dynamic segment up by hand
     const uint32_t sraw = smem_u32(smem_raw);
     const uint32_t sbase = (sraw + 1023u) & ~1023u;
@@ -215,33 +215,34 @@ __global__ void __launch_bounds__(UM_THREADS, 1) score_umma_kernel(UmmaParams p)
         const int2 pr = p.pairs[valid ? pi : (p.P - 1)];
         const float bias = valid ? p.pair_bias[pi] : 0.f;
         const int cell = p.cell_start + cb;
-        const long long tb_i = (long long)cb * p.n_bins + pr.x, tb_j = (long long)cb * p.n_bins + pr.y;
-        const uint4* qk_i = reinterpret_cast<const uint4*>(p.QK16 + tb_i * 256);
-        const uint4* qk_j = reinterpret_cast<const uint4*>(p.QK16 + tb_j * 256);
-        const float* xs_i = p.XS + tb_i * 16;
-        const float* xs_j = p.XS + tb_j * 16;
-        const uint4* v_i = reinterpret_cast<const uint4*>(p.binV16 + (long long)pr.x * 128);
-        const uint4* v_j = reinterpret_cast<const uint4*>(p.binV16 + (long long)pr.y * 128);
-        const uint4* v_c = reinterpret_cast<const uint4*>(p.cellV16 + (long long)cell * 128);
         float osum = 0.f;
 
 #pragma unroll 1
         for (int t = 0; t < 3; ++t) {
             // ------------------------------------------------------------------ attention -> ctx (A tile, K = 128)
-            // row t attends to the two other tokens: (a, b) = (bi, bj) | (cell, bj) | (cell, bi)
-            const uint4* va = (t == 0) ? v_i : v_c;
-            const uint4* vb = (t == 2) ? v_i : v_j;
-            const uint4* qrow = (t == 1) ? qk_i : qk_j;          // Q of this row's own token (t = 1, 2)
-            const uint4* krow = (t == 1) ? qk_j : qk_i;          // K of the other bin
-            const float* xa = (t == 0) ? xs_i : ((t == 1) ? xs_i + 8 : xs_j + 8);
+            // Row t attends to the two other tokens: (a, b) = (bi, bj) | (cell, bj) | (cell, bi).
+            // Lane mapping for this phase: lane = (row-in-group rho = lane>>3, head h = lane&7); a warp walks its
+            // own 32 rows four at a time, so the 8 lanes of a row read one contiguous 256-byte table row
+            // (coalesced) instead of every lane streaming through a private row.
 #pragma unroll 2
-            for (int h = 0; h < 8; ++h) {
-                float la = __ldg(xa + h), lb;
+            for (int it = 0; it < 8; ++it) {
+                const int rw = it * 4 + (lane >> 3), h = lane & 7;
+                const int bi_r = __shfl_sync(0xffffffffu, pr.x, rw), bj_r = __shfl_sync(0xffffffffu, pr.y, rw);
+                const long long ti = (long long)cb * p.n_bins + bi_r, tj = (long long)cb * p.n_bins + bj_r;
+                float la, lb;
+                const uint4 *va, *vb;
                 if (t == 0) {
-                    lb = __ldg(xs_j + h);
+                    la = __ldg(p.XS + ti * 16 + h);
+                    lb = __ldg(p.XS + tj * 16 + h);
+                    va = reinterpret_cast<const uint4*>(p.binV16 + (long long)bi_r * 128) + h * 2;
+                    vb = reinterpret_cast<const uint4*>(p.binV16 + (long long)bj_r * 128) + h * 2;
                 } else {
-                    uint4 q0 = __ldg(qrow + h * 2), q1 = __ldg(qrow + h * 2 + 1);
-                    uint4 k0 = __ldg(krow + 16 + h * 2), k1 = __ldg(krow + 16 + h * 2 + 1);
+                    const long long tq = (t == 1) ? ti : tj, tk = (t == 1) ? tj : ti;
+                    la = __ldg(p.XS + tq * 16 + 8 + h);
+                    const uint4* qrow = reinterpret_cast<const uint4*>(p.QK16 + tq * 256) + h * 2;
+                    const uint4* krow = reinterpret_cast<const uint4*>(p.QK16 + tk * 256) + 16 + h * 2;
+                    uint4 q0 = __ldg(qrow), q1 = __ldg(qrow + 1);
+                    uint4 k0 = __ldg(krow), k1 = __ldg(krow + 1);
                     __half2 acc = __hmul2(u2h(q0.x), u2h(k0.x));
                     acc = __hfma2(u2h(q0.y), u2h(k0.y), acc); acc = __hfma2(u2h(q0.z), u2h(k0.z), acc);
                     acc = __hfma2(u2h(q0.w), u2h(k0.w), acc); acc = __hfma2(u2h(q1.x), u2h(k1.x), acc);
@@ -249,22 +250,25 @@ __global__ void __launch_bounds__(UM_THREADS, 1) score_umma_kernel(UmmaParams p)
                     acc = __hfma2(u2h(q1.w), u2h(k1.w), acc);
                     float2 f = __half22float2(acc);
                     lb = (f.x + f.y) * 0.25f;
+                    va = reinterpret_cast<const uint4*>(p.cellV16 + (long long)cell * 128) + h * 2;
+                    vb = reinterpret_cast<const uint4*>(p.binV16 + (long long)((t == 1) ? bj_r : bi_r) * 128) + h * 2;
                 }
+                uint4 a0 = __ldg(va), a1 = __ldg(va + 1);
+                uint4 b0 = __ldg(vb), b1 = __ldg(vb + 1);
                 float wa, wb;
                 masked_row_fast(la, lb, wa, wb);
                 const __half2 wa2 = __float2half2_rn(wa), wb2 = __float2half2_rn(wb);
-                uint4 a0 = __ldg(va + h * 2), a1 = __ldg(va + h * 2 + 1);
-                uint4 b0 = __ldg(vb + h * 2), b1 = __ldg(vb + h * 2 + 1);
+                const int arow = warp_in_wg * 32 + rw;
                 uint32_t c0 = h2u(__hfma2(wb2, u2h(b0.x), __hmul2(wa2, u2h(a0.x))));
                 uint32_t c1 = h2u(__hfma2(wb2, u2h(b0.y), __hmul2(wa2, u2h(a0.y))));
                 uint32_t c2 = h2u(__hfma2(wb2, u2h(b0.z), __hmul2(wa2, u2h(a0.z))));
                 uint32_t c3 = h2u(__hfma2(wb2, u2h(b0.w), __hmul2(wa2, u2h(a0.w))));
-                sts128(a_chunk_addr(a_base, wtid, h * 2), c0, c1, c2, c3);
+                sts128(a_chunk_addr(a_base, arow, h * 2), c0, c1, c2, c3);
                 c0 = h2u(__hfma2(wb2, u2h(b1.x), __hmul2(wa2, u2h(a1.x))));
                 c1 = h2u(__hfma2(wb2, u2h(b1.y), __hmul2(wa2, u2h(a1.y))));
                 c2 = h2u(__hfma2(wb2, u2h(b1.z), __hmul2(wa2, u2h(a1.z))));
                 c3 = h2u(__hfma2(wb2, u2h(b1.w), __hmul2(wa2, u2h(a1.w))));
-                sts128(a_chunk_addr(a_base, wtid, h * 2 + 1), c0, c1, c2, c3);
+                sts128(a_chunk_addr(a_base, arow, h * 2 + 1), c0, c1, c2, c3);
             }
             issue_gemm<8, 64>(wg, wtid, a_base, sbase + SM_B_FC1, 64, t_y, 0u, bar_mma);
             mbar_wait(bar_mma, phase); phase ^= 1;
@@ -361,15 +365,21 @@ __global__ void __launch_bounds__(UM_THREADS, 1) score_umma_kernel(UmmaParams p)
                     v0 = fmaf(d0, d0, v0); v1 = fmaf(d1, d1, v1);
                 }
                 const float rstd = rsqrtf((v0 + v1) * (1.0f / 64.0f) + HSG_LN_EPS);
-                const float4* Srow = reinterpret_cast<const float4*>(
-                    (t == 0) ? p.cellSb + (long long)cell * 64 : p.binSb + (long long)(t == 1 ? pr.x : pr.y) * 64);
+                // S tables are stored feature-major ([64][n_tokens]) so that consecutive rows (consecutive bins)
+                // read consecutive addresses: 64 coalesced 4-byte loads instead of 16 row-scattered 16-byte loads
+                const float* Scol = (t == 0) ? p.cellSb + cell : p.binSb + (t == 1 ? pr.x : pr.y);
+                const long long sstr = (t == 0) ? p.n_cells : p.n_bins;
 #pragma unroll
                 for (int c = 0; c < 8; ++c) {
                     const uint32_t* rr = (c < 4) ? r0 : r1;
                     const int o = (c & 3) * 8;
                     float4 ga = *reinterpret_cast<const float4*>(cst + CST_G1 + c * 8);
                     float4 gb = *reinterpret_cast<const float4*>(cst + CST_G1 + c * 8 + 4);
-                    float4 sa = __ldg(Srow + c * 2), sb = __ldg(Srow + c * 2 + 1);
+                    float4 sa, sb;
+                    sa.x = __ldg(Scol + (c * 8 + 0) * sstr); sa.y = __ldg(Scol + (c * 8 + 1) * sstr);
+                    sa.z = __ldg(Scol + (c * 8 + 2) * sstr); sa.w = __ldg(Scol + (c * 8 + 3) * sstr);
+                    sb.x = __ldg(Scol + (c * 8 + 4) * sstr); sb.y = __ldg(Scol + (c * 8 + 5) * sstr);
+                    sb.z = __ldg(Scol + (c * 8 + 6) * sstr); sb.w = __ldg(Scol + (c * 8 + 7) * sstr);
                     float u0 = fmaf(__uint_as_float(rr[o + 0]) * rstd, ga.x, -sa.x), u1 = fmaf(__uint_as_float(rr[o + 1]) * rstd, ga.y, -sa.y);
                     float u2 = fmaf(__uint_as_float(rr[o + 2]) * rstd, ga.z, -sa.z), u3 = fmaf(__uint_as_float(rr[o + 3]) * rstd, ga.w, -sa.w);
                     float u4 = fmaf(__uint_as_float(rr[o + 4]) * rstd, gb.x, -sb.x), u5 = fmaf(__uint_as_float(rr[o + 5]) * rstd, gb.y, -sb.y);
@@ -468,7 +478,7 @@ __global__ void convert_static_kernel(const float* __restrict__ V, const float* 
                                       long long rows, int d, __half* __restrict__ V16, float* __restrict__ Sb) {
     long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (i < rows * HSG_HD) V16[i] = __float2half_rn(V[i]);
-    if (i < rows * d) Sb[i] = S[i] - ln1_b[i % d];
+    if (i < rows * d) { long long r = i / d; int f = (int)(i - r * d); Sb[(long long)f * rows + r] = S[i] - ln1_b[f]; }
 }
 
 int launch_convert_static(hsg_ctx* c, const float* V, const float* S, long long rows, void* V16, float* Sb, cudaStream_t s) {
@@ -485,7 +495,7 @@ int launch_score_pairs_umma(hsg_ctx* c, int cell_start, int n_batch, float* out,
     p.QK16 = (const __half*)c->QK16; p.XS = c->XS; p.binV16 = (const __half*)c->binV16; p.binSb = c->binSb;
     p.cellV16 = (const __half*)c->cellV16; p.cellSb = c->cellSb; p.wimg = c->wimg; p.cst = c->cst;
     p.pairs = c->pairs; p.pair_bias = c->pair_bias; p.P = c->P;
-    p.n_bins = c->n_bins; p.cell_start = cell_start; p.n_batch = n_batch;
+    p.n_bins = c->n_bins; p.n_cells = c->n_cells; p.cell_start = cell_start; p.n_batch = n_batch;
     p.tiles_per_cell = (int)((c->P + 127) / 128); p.act = c->act; p.out = out;
     long long n_tiles = (long long)n_batch * p.tiles_per_cell;
     long long quads = (n_tiles + UM_WG - 1) / UM_WG;
