@@ -11,7 +11,7 @@ import os
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libhsg.so")
+LIB_PATH = os.environ.get("HSG_LIB_PATH", os.path.join(_HERE, "libhsg.so"))
 
 # enum hsg_weight (include/hsg.h) -- order matters
 WEIGHT_SLOTS = [

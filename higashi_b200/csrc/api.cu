@@ -448,6 +448,8 @@ extern "C" int hsg_prepare(hsg_ctx* c, int precision, int local_transfer_range, 
         if (dev_alloc(&c->wimg, wimg.size()) || dev_alloc(&c->cst, cst.size())) return 1;
         HSG_CUDA(cudaMemcpy(c->wimg, wimg.data(), wimg.size(), cudaMemcpyHostToDevice));
         HSG_CUDA(cudaMemcpy(c->cst, cst.data(), cst.size() * sizeof(float), cudaMemcpyHostToDevice));
+        HSG_CHECK(cst.size() <= 512, "constant block too large");
+        memcpy(c->h_cst, cst.data(), cst.size() * sizeof(float));
         __half *bv = nullptr, *cv = nullptr;
         if (dev_alloc(&bv, (size_t)c->n_bins * HSG_HD) || dev_alloc(&cv, (size_t)c->n_cells * HSG_HD) ||
             dev_alloc(&c->binSb, (size_t)c->n_bins * d) || dev_alloc(&c->cellSb, (size_t)c->n_cells * d)) return 1;

@@ -90,7 +90,7 @@ struct hsg_ctx {
     void* QK16 = nullptr;                    // half [batch, n_bins, 256]
     float* XS = nullptr;                     // [batch, n_bins, 16] cross terms with the cell token
     void* binV16 = nullptr; float* binSb = nullptr; void* cellV16 = nullptr; float* cellSb = nullptr;
-    unsigned char* wimg = nullptr; float* cst = nullptr;
+    unsigned char* wimg = nullptr; float* cst = nullptr; float h_cst[512] = {0};
     bool use_umma = false;
     int n_sm = 148;
     int fixed_cell = -1;                     // 0-based cell whose tokens sit in QK slot 0 (hsg_fix_cell)

@@ -27,6 +27,9 @@
 #define UM_WG 4
 #define UM_THREADS (UM_WG * 128)
 #define UM_D 64
+#ifndef UM_ATT_PREFETCH
+#define UM_ATT_PREFETCH 0
+#endif
 
 // shared memory map (bytes)
 #define SM_B_FC1 0            // [64 x 128] fp16, 2 K-atoms of 8 KB
@@ -59,8 +62,8 @@ __device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
 __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
     uint32_t ok;
     do {
-        asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
-                     : "=r"(ok) : "r"(bar), "r"(parity) : "memory");
+        asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+                     : "=r"(ok) : "r"(bar), "r"(parity), "r"(0x989680u) : "memory");
     } while (!ok);
 }
 __device__ __forceinline__ void tma_bulk_g2s(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
@@ -108,8 +111,9 @@ __device__ __forceinline__ float fast_tanh(float x) {
     asm("tanh.approx.f32 %0, %1;" : "=f"(y) : "f"(x));
     return y;
 }
-// swish(x) = x * sigmoid(x) = x * (0.5 + 0.5 tanh(x/2)) : one MUFU
-__device__ __forceinline__ float swish_fast(float x) { return x * fmaf(0.5f, fast_tanh(0.5f * x), 0.5f); }
+// swish(x) = x * sigmoid(x) = x * (0.5 + 0.5 tanh(x/2)).  The GEMMs that feed a swish carry the factor 1/2 in
+// their (pre-scaled) weights and biases, so the epilogue sees w = x/2 and swish(x) = w + w tanh(w): MUFU + FFMA.
+__device__ __forceinline__ float swish_half(float w) { return fmaf(w, fast_tanh(w), w); }
 
 // row r of a [128 x K] fp16 A tile, 16-byte chunk `c` (8 halves), K-major SWIZZLE_128B
 __device__ __forceinline__ uint32_t a_chunk_addr(uint32_t a_base, int r, int c) {
@@ -135,7 +139,7 @@ struct UmmaParams {
     const __half* cellV16;   // [n_cells][128]
     const float* cellSb;     // [64][n_cells]  feature-major
     const unsigned char* wimg;   // SM_WIMG_BYTES pre-swizzled fp16 weight images
-    const float* cst;            // CST_COUNT fp32 constants
+    float cst[CST_COUNT];        // fp32 constants, by value: they become constant-bank operands of the epilogue math
     const int2* pairs; const float* pair_bias; long long P;
     int n_bins, n_cells, cell_start, n_batch, tiles_per_cell, act;
     float* out;
@@ -177,7 +181,7 @@ __global__ void __launch_bounds__(UM_THREADS, 1) score_umma_kernel(UmmaParams p)
     const uint32_t sraw = smem_u32(smem_raw);
     const uint32_t sbase = (sraw + 1023u) & ~1023u;
     unsigned char* smem = smem_raw + (sbase - sraw);
-    float* cst = reinterpret_cast<float*>(smem + SM_CONST);
+    const float* cst = p.cst;
     const uint32_t bar_w = sbase + SM_BAR;                 // weights landed
     const uint32_t bar_mma = sbase + SM_BAR + 8 + wg * 8;  // this warpgroup's MMA completion
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + SM_TMEM);
@@ -187,7 +191,6 @@ __global__ void __launch_bounds__(UM_THREADS, 1) score_umma_kernel(UmmaParams p)
         for (int i = 0; i < UM_WG; ++i) mbar_init(sbase + SM_BAR + 8 + i * 8, 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
-    for (int i = tid; i < CST_COUNT; i += UM_THREADS) cst[i] = p.cst[i];
     if (tid < 32) {     // warp 0 allocates all 512 TMEM columns (one CTA per SM)
         asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(512) : "memory");
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
@@ -224,51 +227,83 @@ __global__ void __launch_bounds__(UM_THREADS, 1) score_umma_kernel(UmmaParams p)
             // Lane mapping for this phase: lane = (row-in-group rho = lane>>3, head h = lane&7); a warp walks its
             // own 32 rows four at a time, so the 8 lanes of a row read one contiguous 256-byte table row
             // (coalesced) instead of every lane streaming through a private row.
-#pragma unroll 2
-            for (int it = 0; it < 8; ++it) {
-                const int rw = it * 4 + (lane >> 3), h = lane & 7;
-                const int bi_r = __shfl_sync(0xffffffffu, pr.x, rw), bj_r = __shfl_sync(0xffffffffu, pr.y, rw);
-                const long long ti = (long long)cb * p.n_bins + bi_r, tj = (long long)cb * p.n_bins + bj_r;
-                float la, lb;
-                const uint4 *va, *vb;
-                if (t == 0) {
-                    la = __ldg(p.XS + ti * 16 + h);
-                    lb = __ldg(p.XS + tj * 16 + h);
-                    va = reinterpret_cast<const uint4*>(p.binV16 + (long long)bi_r * 128) + h * 2;
-                    vb = reinterpret_cast<const uint4*>(p.binV16 + (long long)bj_r * 128) + h * 2;
-                } else {
-                    const long long tq = (t == 1) ? ti : tj, tk = (t == 1) ? tj : ti;
-                    la = __ldg(p.XS + tq * 16 + 8 + h);
-                    const uint4* qrow = reinterpret_cast<const uint4*>(p.QK16 + tq * 256) + h * 2;
-                    const uint4* krow = reinterpret_cast<const uint4*>(p.QK16 + tk * 256) + 16 + h * 2;
-                    uint4 q0 = __ldg(qrow), q1 = __ldg(qrow + 1);
-                    uint4 k0 = __ldg(krow), k1 = __ldg(krow + 1);
-                    __half2 acc = __hmul2(u2h(q0.x), u2h(k0.x));
-                    acc = __hfma2(u2h(q0.y), u2h(k0.y), acc); acc = __hfma2(u2h(q0.z), u2h(k0.z), acc);
-                    acc = __hfma2(u2h(q0.w), u2h(k0.w), acc); acc = __hfma2(u2h(q1.x), u2h(k1.x), acc);
-                    acc = __hfma2(u2h(q1.y), u2h(k1.y), acc); acc = __hfma2(u2h(q1.z), u2h(k1.z), acc);
-                    acc = __hfma2(u2h(q1.w), u2h(k1.w), acc);
-                    float2 f = __half22float2(acc);
-                    lb = (f.x + f.y) * 0.25f;
-                    va = reinterpret_cast<const uint4*>(p.cellV16 + (long long)cell * 128) + h * 2;
-                    vb = reinterpret_cast<const uint4*>(p.binV16 + (long long)((t == 1) ? bj_r : bi_r) * 128) + h * 2;
+            {
+                const int h = lane & 7, rsub = lane >> 3;
+                // each lane owns the two 16-byte chunks of head h; lanes with h >= 4 handle them in swapped order so that
+                // the 8 lanes of a quarter-warp hit 8 distinct swizzle slots when storing (no 2-way bank conflict)
+                const int cA = h * 2 + (h >> 2), cB = h * 2 + 1 - (h >> 2);
+                const uint4* QK4 = reinterpret_cast<const uint4*>(p.QK16);
+                const uint4* BV4 = reinterpret_cast<const uint4*>(p.binV16);
+                const uint32_t tokbase = (uint32_t)cb * (uint32_t)p.n_bins;
+                uint4 vc0 = make_uint4(0, 0, 0, 0), vc1 = vc0;        // V of the cell token, head h (t = 1, 2)
+                if (t != 0) {
+                    const uint4* vc = reinterpret_cast<const uint4*>(p.cellV16) + (uint32_t)cell * 16u + h * 2;
+                    vc0 = __ldg(vc + (cA - h * 2)); vc1 = __ldg(vc + (cB - h * 2));
                 }
-                uint4 a0 = __ldg(va), a1 = __ldg(va + 1);
-                uint4 b0 = __ldg(vb), b1 = __ldg(vb + 1);
-                float wa, wb;
-                masked_row_fast(la, lb, wa, wb);
-                const __half2 wa2 = __float2half2_rn(wa), wb2 = __float2half2_rn(wb);
-                const int arow = warp_in_wg * 32 + rw;
-                uint32_t c0 = h2u(__hfma2(wb2, u2h(b0.x), __hmul2(wa2, u2h(a0.x))));
-                uint32_t c1 = h2u(__hfma2(wb2, u2h(b0.y), __hmul2(wa2, u2h(a0.y))));
-                uint32_t c2 = h2u(__hfma2(wb2, u2h(b0.z), __hmul2(wa2, u2h(a0.z))));
-                uint32_t c3 = h2u(__hfma2(wb2, u2h(b0.w), __hmul2(wa2, u2h(a0.w))));
-                sts128(a_chunk_addr(a_base, arow, h * 2), c0, c1, c2, c3);
-                c0 = h2u(__hfma2(wb2, u2h(b1.x), __hmul2(wa2, u2h(a1.x))));
-                c1 = h2u(__hfma2(wb2, u2h(b1.y), __hmul2(wa2, u2h(a1.y))));
-                c2 = h2u(__hfma2(wb2, u2h(b1.z), __hmul2(wa2, u2h(a1.z))));
-                c3 = h2u(__hfma2(wb2, u2h(b1.w), __hmul2(wa2, u2h(a1.w))));
-                sts128(a_chunk_addr(a_base, arow, h * 2 + 1), c0, c1, c2, c3);
+                struct AttLoad { uint4 q0, q1, k0, k1, a0, a1, b0, b1; float la, lb; };
+                AttLoad L[2];
+                auto issue_loads = [&](int it, AttLoad& X) {
+                    const int rw = it * 4 + rsub;
+                    const uint32_t bi_r = (uint32_t)__shfl_sync(0xffffffffu, pr.x, rw), bj_r = (uint32_t)__shfl_sync(0xffffffffu, pr.y, rw);
+                    const uint32_t ti = tokbase + bi_r, tj = tokbase + bj_r;
+                    if (t == 0) {
+                        X.la = __ldg(p.XS + ti * 16u + h);
+                        X.lb = __ldg(p.XS + tj * 16u + h);
+                        X.a0 = __ldg(BV4 + bi_r * 16u + cA); X.a1 = __ldg(BV4 + bi_r * 16u + cB);
+                        X.b0 = __ldg(BV4 + bj_r * 16u + cA); X.b1 = __ldg(BV4 + bj_r * 16u + cB);
+                    } else {
+                        const uint32_t tq = (t == 1) ? ti : tj, tk = (t == 1) ? tj : ti, bv = (t == 1) ? bj_r : bi_r;
+                        X.la = __ldg(p.XS + tq * 16u + 8 + h);
+                        X.q0 = __ldg(QK4 + tq * 32u + h * 2); X.q1 = __ldg(QK4 + tq * 32u + h * 2 + 1);
+                        X.k0 = __ldg(QK4 + tk * 32u + 16 + h * 2); X.k1 = __ldg(QK4 + tk * 32u + 16 + h * 2 + 1);
+                        X.b0 = __ldg(BV4 + bv * 16u + cA); X.b1 = __ldg(BV4 + bv * 16u + cB);
+                    }
+                };
+                auto compute = [&](int it, const AttLoad& X) {
+                    float lb = X.lb;
+                    uint4 a0 = X.a0, a1 = X.a1;
+                    if (t != 0) {
+                        __half2 acc = __hmul2(u2h(X.q0.x), u2h(X.k0.x));
+                        acc = __hfma2(u2h(X.q0.y), u2h(X.k0.y), acc); acc = __hfma2(u2h(X.q0.z), u2h(X.k0.z), acc);
+                        acc = __hfma2(u2h(X.q0.w), u2h(X.k0.w), acc); acc = __hfma2(u2h(X.q1.x), u2h(X.k1.x), acc);
+                        acc = __hfma2(u2h(X.q1.y), u2h(X.k1.y), acc); acc = __hfma2(u2h(X.q1.z), u2h(X.k1.z), acc);
+                        acc = __hfma2(u2h(X.q1.w), u2h(X.k1.w), acc);
+                        float2 f = __half22float2(acc);
+                        lb = (f.x + f.y) * 0.25f;
+                        a0 = vc0; a1 = vc1;
+                    }
+                    float wa, wb;
+                    masked_row_fast(X.la, lb, wa, wb);
+                    const __half2 wa2 = __float2half2_rn(wa), wb2 = __float2half2_rn(wb);
+                    const int arow = warp_in_wg * 32 + it * 4 + rsub;
+                    uint32_t c0 = h2u(__hfma2(wb2, u2h(X.b0.x), __hmul2(wa2, u2h(a0.x))));
+                    uint32_t c1 = h2u(__hfma2(wb2, u2h(X.b0.y), __hmul2(wa2, u2h(a0.y))));
+                    uint32_t c2 = h2u(__hfma2(wb2, u2h(X.b0.z), __hmul2(wa2, u2h(a0.z))));
+                    uint32_t c3 = h2u(__hfma2(wb2, u2h(X.b0.w), __hmul2(wa2, u2h(a0.w))));
+                    sts128(a_chunk_addr(a_base, arow, cA), c0, c1, c2, c3);
+                    c0 = h2u(__hfma2(wb2, u2h(X.b1.x), __hmul2(wa2, u2h(a1.x))));
+                    c1 = h2u(__hfma2(wb2, u2h(X.b1.y), __hmul2(wa2, u2h(a1.y))));
+                    c2 = h2u(__hfma2(wb2, u2h(X.b1.z), __hmul2(wa2, u2h(a1.z))));
+                    c3 = h2u(__hfma2(wb2, u2h(X.b1.w), __hmul2(wa2, u2h(a1.w))));
+                    sts128(a_chunk_addr(a_base, arow, cB), c0, c1, c2, c3);
+                };
+                // software pipeline, two rows-groups per trip: the next group's loads are in flight while one computes
+#if UM_ATT_PREFETCH
+                issue_loads(0, L[0]);
+#pragma unroll 1
+                for (int it = 0; it < 8; it += 2) {
+                    issue_loads(it + 1, L[1]);
+                    compute(it, L[0]);
+                    if (it + 2 < 8) issue_loads(it + 2, L[0]);
+                    compute(it + 1, L[1]);
+                }
+#else
+#pragma unroll 2
+                for (int it = 0; it < 8; ++it) {
+                    issue_loads(it, L[0]);
+                    compute(it, L[0]);
+                }
+#endif
             }
             issue_gemm<8, 64>(wg, wtid, a_base, sbase + SM_B_FC1, 64, t_y, 0u, bar_mma);
             mbar_wait(bar_mma, phase); phase ^= 1;
@@ -321,13 +356,13 @@ __global__ void __launch_bounds__(UM_THREADS, 1) score_umma_kernel(UmmaParams p)
                 tmem_ld_wait();
 #pragma unroll
                 for (int c = 0; c < 4; ++c) {
-                    float4 ba = *reinterpret_cast<const float4*>(cst + CST_B0F + half * 32 + c * 8);
-                    float4 bb = *reinterpret_cast<const float4*>(cst + CST_B0F + half * 32 + c * 8 + 4);
+                    const float* bq = cst + CST_B0F + half * 32 + c * 8;
+                    const float4 ba = make_float4(bq[0], bq[1], bq[2], bq[3]), bb = make_float4(bq[4], bq[5], bq[6], bq[7]);
                     sts128(a_chunk_addr(a_base, wtid, half * 4 + c),
-                           pack_h2(swish_fast(__uint_as_float(r[c * 8 + 0]) + ba.x), swish_fast(__uint_as_float(r[c * 8 + 1]) + ba.y)),
-                           pack_h2(swish_fast(__uint_as_float(r[c * 8 + 2]) + ba.z), swish_fast(__uint_as_float(r[c * 8 + 3]) + ba.w)),
-                           pack_h2(swish_fast(__uint_as_float(r[c * 8 + 4]) + bb.x), swish_fast(__uint_as_float(r[c * 8 + 5]) + bb.y)),
-                           pack_h2(swish_fast(__uint_as_float(r[c * 8 + 6]) + bb.z), swish_fast(__uint_as_float(r[c * 8 + 7]) + bb.w)));
+                           pack_h2(swish_half(__uint_as_float(r[c * 8 + 0]) + ba.x), swish_half(__uint_as_float(r[c * 8 + 1]) + ba.y)),
+                           pack_h2(swish_half(__uint_as_float(r[c * 8 + 2]) + ba.z), swish_half(__uint_as_float(r[c * 8 + 3]) + ba.w)),
+                           pack_h2(swish_half(__uint_as_float(r[c * 8 + 4]) + bb.x), swish_half(__uint_as_float(r[c * 8 + 5]) + bb.y)),
+                           pack_h2(swish_half(__uint_as_float(r[c * 8 + 6]) + bb.z), swish_half(__uint_as_float(r[c * 8 + 7]) + bb.w)));
                 }
             }
             // z = y + h . W1^T : accumulate onto y (still in TMEM) -- the residual is free
@@ -344,8 +379,8 @@ __global__ void __launch_bounds__(UM_THREADS, 1) score_umma_kernel(UmmaParams p)
                 float s0 = 0.f, s1 = 0.f;
 #pragma unroll
                 for (int c = 0; c < 8; ++c) {
-                    float4 ba = *reinterpret_cast<const float4*>(cst + CST_B1 + c * 4);
-                    float4 bb = *reinterpret_cast<const float4*>(cst + CST_B1 + 32 + c * 4);
+                    const float* bq = cst + CST_B1 + c * 4;
+                    const float4 ba = make_float4(bq[0], bq[1], bq[2], bq[3]), bb = make_float4(bq[32], bq[33], bq[34], bq[35]);
                     float x;
                     x = __uint_as_float(r0[c * 4 + 0]) + ba.x; r0[c * 4 + 0] = __float_as_uint(x); s0 += x;
                     x = __uint_as_float(r0[c * 4 + 1]) + ba.y; r0[c * 4 + 1] = __float_as_uint(x); s1 += x;
@@ -373,8 +408,8 @@ __global__ void __launch_bounds__(UM_THREADS, 1) score_umma_kernel(UmmaParams p)
                 for (int c = 0; c < 8; ++c) {
                     const uint32_t* rr = (c < 4) ? r0 : r1;
                     const int o = (c & 3) * 8;
-                    float4 ga = *reinterpret_cast<const float4*>(cst + CST_G1 + c * 8);
-                    float4 gb = *reinterpret_cast<const float4*>(cst + CST_G1 + c * 8 + 4);
+                    const float* gq = cst + CST_G1 + c * 8;
+                    const float4 ga = make_float4(gq[0], gq[1], gq[2], gq[3]), gb = make_float4(gq[4], gq[5], gq[6], gq[7]);
                     float4 sa, sb;
                     sa.x = __ldg(Scol + (c * 8 + 0) * sstr); sa.y = __ldg(Scol + (c * 8 + 1) * sstr);
                     sa.z = __ldg(Scol + (c * 8 + 2) * sstr); sa.w = __ldg(Scol + (c * 8 + 3) * sstr);
@@ -400,12 +435,12 @@ __global__ void __launch_bounds__(UM_THREADS, 1) score_umma_kernel(UmmaParams p)
                 float o0 = 0.f, o1 = 0.f;
 #pragma unroll
                 for (int c = 0; c < 8; ++c) {
-                    float4 b = *reinterpret_cast<const float4*>(cst + CST_CB0 + c * 4);
-                    float4 w = *reinterpret_cast<const float4*>(cst + CST_CW1 + c * 4);
-                    o0 = fmaf(swish_fast(__uint_as_float(r[c * 4 + 0]) + b.x), w.x, o0);
-                    o1 = fmaf(swish_fast(__uint_as_float(r[c * 4 + 1]) + b.y), w.y, o1);
-                    o0 = fmaf(swish_fast(__uint_as_float(r[c * 4 + 2]) + b.z), w.z, o0);
-                    o1 = fmaf(swish_fast(__uint_as_float(r[c * 4 + 3]) + b.w), w.w, o1);
+                    const float* bq = cst + CST_CB0 + c * 4; const float* wq = cst + CST_CW1 + c * 4;
+                    const float4 b = make_float4(bq[0], bq[1], bq[2], bq[3]), w = make_float4(wq[0], wq[1], wq[2], wq[3]);
+                    o0 = fmaf(swish_half(__uint_as_float(r[c * 4 + 0]) + b.x), w.x, o0);
+                    o1 = fmaf(swish_half(__uint_as_float(r[c * 4 + 1]) + b.y), w.y, o1);
+                    o0 = fmaf(swish_half(__uint_as_float(r[c * 4 + 2]) + b.z), w.z, o0);
+                    o1 = fmaf(swish_half(__uint_as_float(r[c * 4 + 3]) + b.w), w.w, o1);
                 }
                 osum += (o0 + o1) + cst[CST_CB1];
             }
@@ -454,18 +489,20 @@ int umma_build_weights(const float* fc1, const float* w0, const float* b0, const
     for (int n = 0; n < d; ++n) {
         double acc = b0[n];
         for (int k = 0; k < d; ++k) {
-            w0f[(size_t)n * d + k] = w0[(size_t)n * d + k] * pff_g[k];      // fold the LN gain into W0
+            w0f[(size_t)n * d + k] = 0.5f * w0[(size_t)n * d + k] * pff_g[k];   // LN gain and the swish 1/2 folded into W0
             acc += (double)w0[(size_t)n * d + k] * pff_b[k];                // and the LN bias into b0
         }
-        cst_host[CST_B0F + n] = (float)acc;
+        cst_host[CST_B0F + n] = (float)(0.5 * acc);
     }
     memset(wimg_host, 0, SM_WIMG_BYTES);
     swizzle_image(fc1, d, HSG_HD, reinterpret_cast<__half*>(wimg_host + SM_B_FC1));
     swizzle_image(w0f.data(), d, d, reinterpret_cast<__half*>(wimg_host + SM_B_W0));
     swizzle_image(w1, d, d, reinterpret_cast<__half*>(wimg_host + SM_B_W1));
-    swizzle_image(c0, d / 2, d, reinterpret_cast<__half*>(wimg_host + SM_B_C0));
+    std::vector<float> c0h((size_t)(d / 2) * d);
+    for (size_t i = 0; i < c0h.size(); ++i) c0h[i] = 0.5f * c0[i];
+    swizzle_image(c0h.data(), d / 2, d, reinterpret_cast<__half*>(wimg_host + SM_B_C0));
     for (int i = 0; i < d; ++i) { cst_host[CST_B1 + i] = b1[i]; cst_host[CST_G1 + i] = ln1_g[i]; }
-    for (int i = 0; i < d / 2; ++i) { cst_host[CST_CB0 + i] = cb0[i]; cst_host[CST_CW1 + i] = cw1[i]; }
+    for (int i = 0; i < d / 2; ++i) { cst_host[CST_CB0 + i] = 0.5f * cb0[i]; cst_host[CST_CW1 + i] = cw1[i]; }
     cst_host[CST_CB1] = cb1[0];
     return 0;
 }
@@ -493,7 +530,8 @@ int launch_score_pairs_umma(hsg_ctx* c, int cell_start, int n_batch, float* out,
     if (c->P == 0 || n_batch == 0) return 0;
     UmmaParams p;
     p.QK16 = (const __half*)c->QK16; p.XS = c->XS; p.binV16 = (const __half*)c->binV16; p.binSb = c->binSb;
-    p.cellV16 = (const __half*)c->cellV16; p.cellSb = c->cellSb; p.wimg = c->wimg; p.cst = c->cst;
+    p.cellV16 = (const __half*)c->cellV16; p.cellSb = c->cellSb; p.wimg = c->wimg;
+    memcpy(p.cst, c->h_cst, sizeof(p.cst));
     p.pairs = c->pairs; p.pair_bias = c->pair_bias; p.P = c->P;
     p.n_bins = c->n_bins; p.n_cells = c->n_cells; p.cell_start = cell_start; p.n_batch = n_batch;
     p.tiles_per_cell = (int)((c->P + 127) / 128); p.act = c->act; p.out = out;
