@@ -127,6 +127,7 @@ __device__ __forceinline__ uint32_t pack_h2(float a, float b) {
     __half2 h = __floats2half2_rn(a, b);
     return *reinterpret_cast<uint32_t*>(&h);
 }
+__device__ __forceinline__ float2 f2(uint32_t a, uint32_t b) { return make_float2(__uint_as_float(a), __uint_as_float(b)); }
 __device__ __forceinline__ __half2 u2h(uint32_t u) { return *reinterpret_cast<__half2*>(&u); }
 __device__ __forceinline__ uint32_t h2u(__half2 h) { return *reinterpret_cast<uint32_t*>(&h); }
 
@@ -263,13 +264,12 @@ __global__ void __launch_bounds__(UM_THREADS, 1) score_umma_kernel(UmmaParams p)
                     float lb = X.lb;
                     uint4 a0 = X.a0, a1 = X.a1;
                     if (t != 0) {
-                        __half2 acc = __hmul2(u2h(X.q0.x), u2h(X.k0.x));
-                        acc = __hfma2(u2h(X.q0.y), u2h(X.k0.y), acc); acc = __hfma2(u2h(X.q0.z), u2h(X.k0.z), acc);
-                        acc = __hfma2(u2h(X.q0.w), u2h(X.k0.w), acc); acc = __hfma2(u2h(X.q1.x), u2h(X.k1.x), acc);
-                        acc = __hfma2(u2h(X.q1.y), u2h(X.k1.y), acc); acc = __hfma2(u2h(X.q1.z), u2h(X.k1.z), acc);
-                        acc = __hfma2(u2h(X.q1.w), u2h(X.k1.w), acc);
-                        float2 f = __half22float2(acc);
-                        lb = (f.x + f.y) * 0.25f;
+                        __half2 acc = __hmul2(u2h(X.q0.x), u2h(X.k0.x)), acc2 = __hmul2(u2h(X.q1.x), u2h(X.k1.x));
+                        acc = __hfma2(u2h(X.q0.y), u2h(X.k0.y), acc); acc2 = __hfma2(u2h(X.q1.y), u2h(X.k1.y), acc2);
+                        acc = __hfma2(u2h(X.q0.z), u2h(X.k0.z), acc); acc2 = __hfma2(u2h(X.q1.z), u2h(X.k1.z), acc2);
+                        acc = __hfma2(u2h(X.q0.w), u2h(X.k0.w), acc); acc2 = __hfma2(u2h(X.q1.w), u2h(X.k1.w), acc2);
+                        float2 f = __half22float2(acc), f2_ = __half22float2(acc2);
+                        lb = ((f.x + f.y) + (f2_.x + f2_.y)) * 0.25f;
                         a0 = vc0; a1 = vc1;
                     }
                     float wa, wb;
@@ -309,39 +309,41 @@ __global__ void __launch_bounds__(UM_THREADS, 1) score_umma_kernel(UmmaParams p)
             mbar_wait(bar_mma, phase); phase ^= 1;
             tc_fence_after();
 
+            // The row-wise epilogues below use the packed fp32x2 instructions of sm_100 (FADD2/FMUL2/FFMA2 via
+            // __fadd2_rn/__fmul2_rn/__ffma2_rn): two columns per issue slot.
             // ------------------------------------------------------------------ y -> LN_pff(y) (A tile, K = 64)
             {
                 uint32_t r0[32], r1[32];
                 tmem_ld32(t_y + t_lane, r0);
                 tmem_ld32(t_y + t_lane + 32, r1);
                 tmem_ld_wait();
-                float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
+                float2 x[32];
 #pragma unroll
-                for (int i = 0; i < 32; i += 2) {
-                    s0 += __uint_as_float(r0[i]); s1 += __uint_as_float(r0[i + 1]);
-                    s2 += __uint_as_float(r1[i]); s3 += __uint_as_float(r1[i + 1]);
+                for (int i = 0; i < 16; ++i) { x[i] = f2(r0[2 * i], r0[2 * i + 1]); x[16 + i] = f2(r1[2 * i], r1[2 * i + 1]); }
+                float2 sA = x[0], sB = x[1], sC = x[2], sD = x[3];        // 4 independent chains (ILP)
+#pragma unroll
+                for (int i = 4; i < 32; i += 4) {
+                    sA = __fadd2_rn(sA, x[i]); sB = __fadd2_rn(sB, x[i + 1]); sC = __fadd2_rn(sC, x[i + 2]); sD = __fadd2_rn(sD, x[i + 3]);
                 }
-                const float mean = ((s0 + s1) + (s2 + s3)) * (1.0f / 64.0f);
-                float v0 = 0.f, v1 = 0.f;
+                sA = __fadd2_rn(__fadd2_rn(sA, sB), __fadd2_rn(sC, sD));
+                const float mean = (sA.x + sA.y) * (1.0f / 64.0f);
+                const float2 nm = make_float2(-mean, -mean);
+                float2 vA = make_float2(0.f, 0.f), vB = vA, vC = vA, vD = vA;
 #pragma unroll
-                for (int i = 0; i < 32; ++i) {
-                    float d0 = __uint_as_float(r0[i]) - mean, d1 = __uint_as_float(r1[i]) - mean;
-                    r0[i] = __float_as_uint(d0); r1[i] = __float_as_uint(d1);
-                    v0 = fmaf(d0, d0, v0); v1 = fmaf(d1, d1, v1);
+                for (int i = 0; i < 32; i += 4) {
+                    x[i] = __fadd2_rn(x[i], nm); x[i + 1] = __fadd2_rn(x[i + 1], nm);
+                    x[i + 2] = __fadd2_rn(x[i + 2], nm); x[i + 3] = __fadd2_rn(x[i + 3], nm);
+                    vA = __ffma2_rn(x[i], x[i], vA); vB = __ffma2_rn(x[i + 1], x[i + 1], vB);
+                    vC = __ffma2_rn(x[i + 2], x[i + 2], vC); vD = __ffma2_rn(x[i + 3], x[i + 3], vD);
                 }
-                const float rstd = rsqrtf((v0 + v1) * (1.0f / 64.0f) + HSG_LN_EPS);
+                vA = __fadd2_rn(__fadd2_rn(vA, vB), __fadd2_rn(vC, vD));
+                const float rstd = rsqrtf((vA.x + vA.y) * (1.0f / 64.0f) + HSG_LN_EPS);
+                const float2 rs = make_float2(rstd, rstd);
 #pragma unroll
-                for (int c = 0; c < 4; ++c) {
-                    sts128(a_chunk_addr(a_base, wtid, c),
-                           pack_h2(__uint_as_float(r0[c * 8 + 0]) * rstd, __uint_as_float(r0[c * 8 + 1]) * rstd),
-                           pack_h2(__uint_as_float(r0[c * 8 + 2]) * rstd, __uint_as_float(r0[c * 8 + 3]) * rstd),
-                           pack_h2(__uint_as_float(r0[c * 8 + 4]) * rstd, __uint_as_float(r0[c * 8 + 5]) * rstd),
-                           pack_h2(__uint_as_float(r0[c * 8 + 6]) * rstd, __uint_as_float(r0[c * 8 + 7]) * rstd));
-                    sts128(a_chunk_addr(a_base, wtid, c + 4),
-                           pack_h2(__uint_as_float(r1[c * 8 + 0]) * rstd, __uint_as_float(r1[c * 8 + 1]) * rstd),
-                           pack_h2(__uint_as_float(r1[c * 8 + 2]) * rstd, __uint_as_float(r1[c * 8 + 3]) * rstd),
-                           pack_h2(__uint_as_float(r1[c * 8 + 4]) * rstd, __uint_as_float(r1[c * 8 + 5]) * rstd),
-                           pack_h2(__uint_as_float(r1[c * 8 + 6]) * rstd, __uint_as_float(r1[c * 8 + 7]) * rstd));
+                for (int c = 0; c < 8; ++c) {
+                    float2 a0 = __fmul2_rn(x[c * 4 + 0], rs), a1 = __fmul2_rn(x[c * 4 + 1], rs);
+                    float2 a2 = __fmul2_rn(x[c * 4 + 2], rs), a3 = __fmul2_rn(x[c * 4 + 3], rs);
+                    sts128(a_chunk_addr(a_base, wtid, c), pack_h2(a0.x, a0.y), pack_h2(a1.x, a1.y), pack_h2(a2.x, a2.y), pack_h2(a3.x, a3.y));
                 }
             }
             issue_gemm<4, 64>(wg, wtid, a_base, sbase + SM_B_W0, 64, t_h, 0u, bar_mma);
@@ -357,12 +359,15 @@ __global__ void __launch_bounds__(UM_THREADS, 1) score_umma_kernel(UmmaParams p)
 #pragma unroll
                 for (int c = 0; c < 4; ++c) {
                     const float* bq = cst + CST_B0F + half * 32 + c * 8;
-                    const float4 ba = make_float4(bq[0], bq[1], bq[2], bq[3]), bb = make_float4(bq[4], bq[5], bq[6], bq[7]);
-                    sts128(a_chunk_addr(a_base, wtid, half * 4 + c),
-                           pack_h2(swish_half(__uint_as_float(r[c * 8 + 0]) + ba.x), swish_half(__uint_as_float(r[c * 8 + 1]) + ba.y)),
-                           pack_h2(swish_half(__uint_as_float(r[c * 8 + 2]) + ba.z), swish_half(__uint_as_float(r[c * 8 + 3]) + ba.w)),
-                           pack_h2(swish_half(__uint_as_float(r[c * 8 + 4]) + bb.x), swish_half(__uint_as_float(r[c * 8 + 5]) + bb.y)),
-                           pack_h2(swish_half(__uint_as_float(r[c * 8 + 6]) + bb.z), swish_half(__uint_as_float(r[c * 8 + 7]) + bb.w)));
+                    uint32_t pk[4];
+#pragma unroll
+                    for (int q = 0; q < 4; ++q) {
+                        float2 w = __fadd2_rn(f2(r[c * 8 + 2 * q], r[c * 8 + 2 * q + 1]), make_float2(bq[2 * q], bq[2 * q + 1]));
+                        float2 th = make_float2(fast_tanh(w.x), fast_tanh(w.y));
+                        float2 hh = __ffma2_rn(w, th, w);
+                        pk[q] = pack_h2(hh.x, hh.y);
+                    }
+                    sts128(a_chunk_addr(a_base, wtid, half * 4 + c), pk[0], pk[1], pk[2], pk[3]);
                 }
             }
             // z = y + h . W1^T : accumulate onto y (still in TMEM) -- the residual is free
@@ -376,51 +381,48 @@ __global__ void __launch_bounds__(UM_THREADS, 1) score_umma_kernel(UmmaParams p)
                 tmem_ld32(t_y + t_lane, r0);
                 tmem_ld32(t_y + t_lane + 32, r1);
                 tmem_ld_wait();
-                float s0 = 0.f, s1 = 0.f;
+                float2 x[32];
+                float2 sA = make_float2(0.f, 0.f), sB = sA;
 #pragma unroll
-                for (int c = 0; c < 8; ++c) {
-                    const float* bq = cst + CST_B1 + c * 4;
-                    const float4 ba = make_float4(bq[0], bq[1], bq[2], bq[3]), bb = make_float4(bq[32], bq[33], bq[34], bq[35]);
-                    float x;
-                    x = __uint_as_float(r0[c * 4 + 0]) + ba.x; r0[c * 4 + 0] = __float_as_uint(x); s0 += x;
-                    x = __uint_as_float(r0[c * 4 + 1]) + ba.y; r0[c * 4 + 1] = __float_as_uint(x); s1 += x;
-                    x = __uint_as_float(r0[c * 4 + 2]) + ba.z; r0[c * 4 + 2] = __float_as_uint(x); s0 += x;
-                    x = __uint_as_float(r0[c * 4 + 3]) + ba.w; r0[c * 4 + 3] = __float_as_uint(x); s1 += x;
-                    x = __uint_as_float(r1[c * 4 + 0]) + bb.x; r1[c * 4 + 0] = __float_as_uint(x); s0 += x;
-                    x = __uint_as_float(r1[c * 4 + 1]) + bb.y; r1[c * 4 + 1] = __float_as_uint(x); s1 += x;
-                    x = __uint_as_float(r1[c * 4 + 2]) + bb.z; r1[c * 4 + 2] = __float_as_uint(x); s0 += x;
-                    x = __uint_as_float(r1[c * 4 + 3]) + bb.w; r1[c * 4 + 3] = __float_as_uint(x); s1 += x;
+                for (int i = 0; i < 16; i += 2) {
+                    const float* bq = cst + CST_B1 + 2 * i;
+                    x[i] = __fadd2_rn(f2(r0[2 * i], r0[2 * i + 1]), make_float2(bq[0], bq[1]));
+                    x[i + 1] = __fadd2_rn(f2(r0[2 * i + 2], r0[2 * i + 3]), make_float2(bq[2], bq[3]));
+                    x[16 + i] = __fadd2_rn(f2(r1[2 * i], r1[2 * i + 1]), make_float2(bq[32], bq[33]));
+                    x[17 + i] = __fadd2_rn(f2(r1[2 * i + 2], r1[2 * i + 3]), make_float2(bq[34], bq[35]));
+                    sA = __fadd2_rn(sA, __fadd2_rn(x[i], x[16 + i]));
+                    sB = __fadd2_rn(sB, __fadd2_rn(x[i + 1], x[17 + i]));
                 }
-                const float mean = (s0 + s1) * (1.0f / 64.0f);
-                float v0 = 0.f, v1 = 0.f;
+                const float mean = ((sA.x + sA.y) + (sB.x + sB.y)) * (1.0f / 64.0f);
+                const float2 nm = make_float2(-mean, -mean);
+                float2 vA = make_float2(0.f, 0.f), vB = vA, vC = vA, vD = vA;
 #pragma unroll
-                for (int i = 0; i < 32; ++i) {
-                    float d0 = __uint_as_float(r0[i]) - mean, d1 = __uint_as_float(r1[i]) - mean;
-                    r0[i] = __float_as_uint(d0); r1[i] = __float_as_uint(d1);
-                    v0 = fmaf(d0, d0, v0); v1 = fmaf(d1, d1, v1);
+                for (int i = 0; i < 32; i += 4) {
+                    x[i] = __fadd2_rn(x[i], nm); x[i + 1] = __fadd2_rn(x[i + 1], nm);
+                    x[i + 2] = __fadd2_rn(x[i + 2], nm); x[i + 3] = __fadd2_rn(x[i + 3], nm);
+                    vA = __ffma2_rn(x[i], x[i], vA); vB = __ffma2_rn(x[i + 1], x[i + 1], vB);
+                    vC = __ffma2_rn(x[i + 2], x[i + 2], vC); vD = __ffma2_rn(x[i + 3], x[i + 3], vD);
                 }
-                const float rstd = rsqrtf((v0 + v1) * (1.0f / 64.0f) + HSG_LN_EPS);
+                vA = __fadd2_rn(__fadd2_rn(vA, vB), __fadd2_rn(vC, vD));
+                const float rstd = rsqrtf((vA.x + vA.y) * (1.0f / 64.0f) + HSG_LN_EPS);
+                const float2 rs = make_float2(rstd, rstd);
                 // S tables are stored feature-major ([64][n_tokens]) so that consecutive rows (consecutive bins)
                 // read consecutive addresses: 64 coalesced 4-byte loads instead of 16 row-scattered 16-byte loads
                 const float* Scol = (t == 0) ? p.cellSb + cell : p.binSb + (t == 1 ? pr.x : pr.y);
                 const long long sstr = (t == 0) ? p.n_cells : p.n_bins;
 #pragma unroll
                 for (int c = 0; c < 8; ++c) {
-                    const uint32_t* rr = (c < 4) ? r0 : r1;
-                    const int o = (c & 3) * 8;
                     const float* gq = cst + CST_G1 + c * 8;
-                    const float4 ga = make_float4(gq[0], gq[1], gq[2], gq[3]), gb = make_float4(gq[4], gq[5], gq[6], gq[7]);
-                    float4 sa, sb;
-                    sa.x = __ldg(Scol + (c * 8 + 0) * sstr); sa.y = __ldg(Scol + (c * 8 + 1) * sstr);
-                    sa.z = __ldg(Scol + (c * 8 + 2) * sstr); sa.w = __ldg(Scol + (c * 8 + 3) * sstr);
-                    sb.x = __ldg(Scol + (c * 8 + 4) * sstr); sb.y = __ldg(Scol + (c * 8 + 5) * sstr);
-                    sb.z = __ldg(Scol + (c * 8 + 6) * sstr); sb.w = __ldg(Scol + (c * 8 + 7) * sstr);
-                    float u0 = fmaf(__uint_as_float(rr[o + 0]) * rstd, ga.x, -sa.x), u1 = fmaf(__uint_as_float(rr[o + 1]) * rstd, ga.y, -sa.y);
-                    float u2 = fmaf(__uint_as_float(rr[o + 2]) * rstd, ga.z, -sa.z), u3 = fmaf(__uint_as_float(rr[o + 3]) * rstd, ga.w, -sa.w);
-                    float u4 = fmaf(__uint_as_float(rr[o + 4]) * rstd, gb.x, -sb.x), u5 = fmaf(__uint_as_float(rr[o + 5]) * rstd, gb.y, -sb.y);
-                    float u6 = fmaf(__uint_as_float(rr[o + 6]) * rstd, gb.z, -sb.z), u7 = fmaf(__uint_as_float(rr[o + 7]) * rstd, gb.w, -sb.w);
-                    sts128(a_chunk_addr(a_base, wtid, c), pack_h2(u0 * u0, u1 * u1), pack_h2(u2 * u2, u3 * u3),
-                           pack_h2(u4 * u4, u5 * u5), pack_h2(u6 * u6, u7 * u7));
+                    uint32_t pk[4];
+#pragma unroll
+                    for (int q = 0; q < 4; ++q) {
+                        float2 sv = make_float2(-__ldg(Scol + (c * 8 + 2 * q) * sstr), -__ldg(Scol + (c * 8 + 2 * q + 1) * sstr));
+                        float2 tz = __fmul2_rn(x[c * 4 + q], rs);
+                        float2 u = __ffma2_rn(tz, make_float2(gq[2 * q], gq[2 * q + 1]), sv);
+                        u = __fmul2_rn(u, u);
+                        pk[q] = pack_h2(u.x, u.y);
+                    }
+                    sts128(a_chunk_addr(a_base, wtid, c), pk[0], pk[1], pk[2], pk[3]);
                 }
             }
             issue_gemm<4, 32>(wg, wtid, a_base, sbase + SM_B_C0, 32, t_h, 0u, bar_mma);
@@ -432,17 +434,18 @@ __global__ void __launch_bounds__(UM_THREADS, 1) score_umma_kernel(UmmaParams p)
                 uint32_t r[32];
                 tmem_ld32(t_h + t_lane, r);
                 tmem_ld_wait();
-                float o0 = 0.f, o1 = 0.f;
+                float2 oA = make_float2(0.f, 0.f), oB = oA;
 #pragma unroll
-                for (int c = 0; c < 8; ++c) {
-                    const float* bq = cst + CST_CB0 + c * 4; const float* wq = cst + CST_CW1 + c * 4;
-                    const float4 b = make_float4(bq[0], bq[1], bq[2], bq[3]), w = make_float4(wq[0], wq[1], wq[2], wq[3]);
-                    o0 = fmaf(swish_half(__uint_as_float(r[c * 4 + 0]) + b.x), w.x, o0);
-                    o1 = fmaf(swish_half(__uint_as_float(r[c * 4 + 1]) + b.y), w.y, o1);
-                    o0 = fmaf(swish_half(__uint_as_float(r[c * 4 + 2]) + b.z), w.z, o0);
-                    o1 = fmaf(swish_half(__uint_as_float(r[c * 4 + 3]) + b.w), w.w, o1);
+                for (int i = 0; i < 16; i += 2) {
+                    const float* bq = cst + CST_CB0 + 2 * i; const float* wq = cst + CST_CW1 + 2 * i;
+                    float2 w0 = __fadd2_rn(f2(r[2 * i], r[2 * i + 1]), make_float2(bq[0], bq[1]));
+                    float2 w1 = __fadd2_rn(f2(r[2 * i + 2], r[2 * i + 3]), make_float2(bq[2], bq[3]));
+                    float2 h0 = __ffma2_rn(w0, make_float2(fast_tanh(w0.x), fast_tanh(w0.y)), w0);
+                    float2 h1 = __ffma2_rn(w1, make_float2(fast_tanh(w1.x), fast_tanh(w1.y)), w1);
+                    oA = __ffma2_rn(h0, make_float2(wq[0], wq[1]), oA);
+                    oB = __ffma2_rn(h1, make_float2(wq[2], wq[3]), oB);
                 }
-                osum += (o0 + o1) + cst[CST_CB1];
+                osum += ((oA.x + oA.y) + (oB.x + oB.y)) + cst[CST_CB1];
             }
             tc_fence_before();      // TMEM reads done before the next token's MMAs overwrite the columns
         }
