@@ -1,0 +1,164 @@
+"""The Python host mirror of the reference interface (Higashi_backend.Modules, Impute.impute_process):
+state_dict compatibility and pickling on CPU; the end-to-end file-level imputation on the GPU."""
+import json
+import os
+import pickle
+
+import numpy as np
+import pytest
+import torch
+
+from tests._util import FixtureDataset, load
+
+
+def build_mirror_model(ds, d, sd=None):
+    from higashi_b200.Higashi_backend import Modules as M
+    feats = [ds.cell_embed_feats] + list(ds.bin_feats)
+    emb = M.MultipleEmbedding(feats, d, False, ds.num_list, feats)
+    model = M.Hyper_SAGNN(n_head=8, d_model=d, d_k=16, d_v=16, diag_mask=True, bottle_neck=d,
+                          attribute_dict=ds.attribute_dict, cell_feats=ds.cell_feats, encoder_dynamic_nn=emb,
+                          encoder_static_nn=emb, chrom_num=len(ds.bins))
+    n_nodes = int(ds.num_list[-1])
+    enc = M.GraphSageEncoder_with_weights(features=emb, linear_features=emb, feature_dim=d, embed_dim=d, num_sample=8,
+                                          gcn=False, num_list=ds.num_list, transfer_range=0,
+                                          start_end_dict=np.zeros((n_nodes + 1, 2), dtype="int"), pass_pseudo_id=False,
+                                          remove=True, pass_remove=False)
+    model.encode1.dynamic_nn = enc
+    if sd is not None:
+        missing, unexpected = model.load_state_dict({k: torch.from_numpy(np.asarray(v)) for k, v in sd.items()}, strict=False)
+        assert not unexpected, unexpected
+    return model
+
+
+def test_state_dict_is_reference_compatible():
+    """Every tensor of a reference state_dict (golden fixture) has a same-named, same-shaped slot in the mirror."""
+    g = load("impute_k4_r0.npz")
+    ds = FixtureDataset(g)
+    sd = {k[3:]: v for k, v in g.items() if k.startswith("sd/")}
+    model = build_mirror_model(ds, 64, sd)
+    own = model.state_dict()
+    for k, v in sd.items():
+        assert k in own, k
+        assert tuple(own[k].shape) == tuple(v.shape), k
+        np.testing.assert_array_equal(own[k].numpy(), v)
+
+
+def test_model_pickles_without_engine(tmp_path):
+    g = load("impute_k4_r0.npz")
+    ds = FixtureDataset(g)
+    model = build_mirror_model(ds, 64)
+    p = tmp_path / "model.pkl"
+    torch.save(model, p)
+    m2 = torch.load(p, weights_only=False)
+    assert type(m2).__name__ == "Hyper_SAGNN" and m2._engine is None
+    assert m2.encode1.dynamic_nn.forward.__name__ == "forward_on_hook"
+
+
+def test_reference_module_aliases():
+    import sys
+    import higashi_b200
+    higashi_b200.install_aliases()
+    from higashi_b200.Higashi_backend import Modules as M
+    assert sys.modules["Higashi_backend.Modules"] is M
+    assert pickle.loads(pickle.dumps(M.Hyper_SAGNN)) is M.Hyper_SAGNN
+
+
+def test_data_generator_matches_reference_semantics():
+    from higashi_b200.Higashi_backend.Modules import DataGenerator
+    rng = np.random.default_rng(0)
+    edges = [np.sort(rng.integers(1, 50, size=(30, 3)), axis=-1) for _ in range(2)]
+    gen = DataGenerator(edges, [np.zeros(30, "int8"), np.ones(30, "int8")], [np.ones(30), np.ones(30)], 8, True,
+                        num_list=[10, 30, 50], k=1)
+    np.random.seed(1)
+    e, c, w, chroms = gen.next_iter()
+    assert e.shape == (8, 3) and len(c) == 8 and len(chroms) == 1 and (c == chroms[0]).all()
+    gen.filter_edges(2, 20)
+    for ed in gen.edges:
+        dist = ed[:, 2] - ed[:, 1]
+        assert ((dist > 2) & (dist < 20)).all()
+
+
+def test_forward_without_gpu_fails_loudly():
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    g = load("impute_k4_r0.npz")
+    model = build_mirror_model(FixtureDataset(g), 64)
+    with pytest.raises(RuntimeError):
+        model.predict(np.ones((3, 3), dtype=np.int64), np.zeros(3))
+
+
+# ------------------------------------------------------------------------------------------ GPU: file-level run
+def _write_run_dir(tmp, g, ds, chrom_list):
+    cfg = dict(resolution=1000000, impute_list=chrom_list, chrom_list=chrom_list, temp_dir=str(tmp), minimum_distance=1000000,
+               maximum_distance=-1, local_transfer_range=int(g["cfg/ltr"]), embedding_name="emb", impute_verbose=0)
+    mn, mx = [int(v) for v in g["cfg/band"]]
+    if mx > 0:
+        cfg["minimum_impute_distance"] = mn * 1000000
+        cfg["maximum_impute_distance"] = mx * 1000000
+    if len(g["cfg/skip"]):
+        # a cytoband file that reproduces the fixture's skip intervals: bins [a,b) <- acen [ (a)*res+1e5 , (b)*res-1e5 ]
+        with open(tmp / "cyto.txt", "w") as f:
+            for j, a, b in g["cfg/skip"]:
+                f.write("%s\t%d\t%d\tx\tacen\n" % (chrom_list[int(j)], int(a) * 1000000 + 100000, int(b) * 1000000 - 100000))
+        cfg["cytoband_path"] = str(tmp / "cyto.txt")
+    json.dump(cfg, open(tmp / "config.json", "w"))
+    np.savez(tmp / "node_feats.npz", num=ds.num)
+    np.save(tmp / "sparse_nondiag_adj_nbr_1.npy", ds.csr.to_object_array(), allow_pickle=True)
+    winfo = None
+    if int(g["cfg/k"]) > 0:
+        nl = [[]] + [list(r) for r in g["knn/nbr"]]
+        wd = {}
+        for i in range(1, len(nl)):
+            for c, w in zip(nl[i], g["knn/w"][i - 1]):
+                wd[(int(c), i)] = np.float32(w)
+        np.save(tmp / "weighted_info.npy", np.array([np.array(nl, dtype=object), wd], dtype=object), allow_pickle=True)
+        winfo = str(tmp / "weighted_info.npy")
+    return str(tmp / "config.json"), str(tmp / "sparse_nondiag_adj_nbr_1.npy"), winfo
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("tag,prec", [("k4_r0", "fp32"), ("k4_r0", "tc16"), ("k0_r1_band", "fp32"), ("k4_r1", "tc16")])
+def test_impute_process_files(tmp_path, tag, prec):
+    """impute_process(config, model, name, mode, cell_start, cell_end, sparse_path, weighted_info) end to end."""
+    from higashi_b200 import engine as E
+    from higashi_b200 import sink
+    from higashi_b200.Impute import impute_process
+    g = load("impute_%s.npz" % tag)
+    ds = FixtureDataset(g)
+    sd = {k[3:]: v for k, v in g.items() if k.startswith("sd/")}
+    model = build_mirror_model(ds, 64, sd)
+    chrom_list = ["chr%d" % (j + 1) for j in range(len(ds.bins))]
+    cfg_path, sparse_path, winfo = _write_run_dir(tmp_path, g, ds, chrom_list)
+    c0, c1 = [int(v) for v in g["cfg/cell_range"]]
+    name = "emb_nbr_%d_impute" % int(g["cfg/k"])
+    impute_process(cfg_path, model, name, str(g["cfg/mode"]), c0, c1, sparse_path, winfo,
+                   precision=E.PREC_FP32 if prec == "fp32" else E.PREC_TC16)
+    tol = 1e-5 if prec == "fp32" else 1e-3
+    for j, chrom in enumerate(chrom_list):
+        f = sink.read_container(str(tmp_path), chrom, name)
+        ref_c = g["out/%s/coordinates" % chrom]
+        assert f["coordinates"].dtype == np.int64 and np.array_equal(f["coordinates"], ref_c)
+        for n, cell in enumerate(range(c0, c1)):
+            v = f["cell_%d" % cell]
+            assert v.dtype == np.float32 and v.shape == (len(ref_c),)
+            np.testing.assert_allclose(v, g["out/%s/cells" % chrom][n], atol=tol, rtol=0)
+    assert model.training and model.only_model is False        # state restored like Impute.py:288-292
+
+
+@pytest.mark.gpu
+def test_predict_api_like_reference():
+    """model.encode1.dynamic_nn.fix_cell2(cell, ...) then model.predict(triplets, chrom, activation=torch.sigmoid)."""
+    g = load("scorer_d64.npz")
+    ds = FixtureDataset(g)
+    sd = {k[len("stage2/sd/"):]: v for k, v in g.items() if k.startswith("stage2/sd/")}
+    model = build_mirror_model(ds, 64, sd)
+    model.eval()
+    model.only_model = True
+    model.build_engine(ds.csr)
+    pairs = g["impute/pairs"]
+    for n, cell in enumerate(g["impute/cells"]):
+        x = np.concatenate([np.full((len(pairs), 1), int(cell), dtype=np.int64), pairs], axis=-1)
+        model.encode1.dynamic_nn.fix_cell2(int(cell), None, None, 0, route_nn_list=None)
+        out = model.predict(x, np.zeros(len(x), dtype=int), verbose=False, batch_size=int(1e5), activation=torch.sigmoid)
+        assert out.shape == (len(x), 1) and out.dtype == np.float32
+        np.testing.assert_allclose(out.reshape(-1), g["impute/sigmoid"][n], atol=1e-5, rtol=0)
