@@ -1,0 +1,73 @@
+"""Multi-GPU plumbing of the imputation path: shard by cell range, one process per GPU, no data-path collective.
+
+Reference: Higashi.impute_no_nbr / impute_with_nbr (Higashi_wrapper.py:1457-1475, 1578-1599) split the cells with
+`np.array_split(arange(n_cells), gpu_num - 1)`, run `python Impute.py ... cell_start cell_end ... gpu_id` per shard and
+merge the part files with `linkhdf5` (utils.py:217-253), which also divides every cell vector by its mean.
+Here the split is over ALL `world` GPUs (no idle GPU), the workers are `python -m higashi_b200.Impute` processes (or the
+ranks of a torchrun job), and `link_parts` is the merge."""
+import os
+import subprocess
+import sys
+
+import numpy as np
+
+from . import sink as S
+
+
+def cell_shards(n_cells: int, world: int):
+    """Contiguous cell ranges [(start, end)] as np.array_split would produce them."""
+    parts = np.array_split(np.arange(n_cells), world)
+    return [(int(p[0]), int(p[-1]) + 1) if len(p) else (0, 0) for p in parts]
+
+
+def max_over_ranks(value: float) -> float:
+    """Device-time reduction used by bench.py: MAX over ranks (gloo on CPU tests, nccl on GPUs)."""
+    import torch
+    import torch.distributed as dist
+    if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size() == 1:
+        return float(value)
+    dev = "cuda" if dist.get_backend() == "nccl" else "cpu"
+    t = torch.tensor([float(value)], dtype=torch.float64, device=dev)
+    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    return float(t.item())
+
+
+def link_parts(name, shards, temp_dir, impute_list, normalise=True):
+    """linkhdf5 (utils.py:217-253): merge `{chrom}_{name}_part_{i}` containers into `{chrom}_{name}`; every cell
+    vector is divided by its mean (utils.py:234) unless normalise=False; part files are removed."""
+    for chrom in impute_list:
+        out = S.ChromSink(temp_dir, chrom, name)
+        for i, (c0, c1) in enumerate(shards):
+            part = S.read_container(temp_dir, chrom, "%s_part_%d" % (name, i))
+            if i == 0:
+                out.create_dataset("coordinates", part["coordinates"])
+            for cell in range(c0, c1):
+                v = part["cell_%d" % cell]
+                if normalise:
+                    v = v / np.mean(v)
+                out.create_dataset("cell_%d" % cell, v.astype(np.float32), compress=True)
+        out.close()
+        for i in range(len(shards)):
+            for ext in (".hdf5", ".npz"):
+                p = os.path.join(temp_dir, "%s_%s_part_%d%s" % (chrom, name, i, ext))
+                if os.path.exists(p):
+                    os.remove(p)
+
+
+def impute_multi_gpu(config_path, model_path, name, mode, n_cells, sparse_path, weighted_info=None, gpus=None,
+                     impute_list=None, temp_dir=None, normalise=True):
+    """One `python -m higashi_b200.Impute` worker per GPU over contiguous cell shards, then link_parts."""
+    import torch
+    gpus = list(range(torch.cuda.device_count())) if gpus is None else list(gpus)
+    shards = cell_shards(n_cells, len(gpus))
+    procs = []
+    for i, ((c0, c1), g) in enumerate(zip(shards, gpus)):
+        cmd = [sys.executable, "-m", "higashi_b200.Impute", config_path, model_path, "%s_part_%d" % (name, i), mode, str(c0), str(c1),
+               sparse_path, weighted_info if weighted_info is not None else "None", str(g)]
+        procs.append(subprocess.Popen(cmd))
+    rcs = [p.wait() for p in procs]
+    if any(rcs):
+        raise RuntimeError("imputation worker failed: return codes %s" % rcs)
+    if impute_list is not None and temp_dir is not None:
+        link_parts(name, shards, temp_dir, impute_list, normalise)
+    return shards

@@ -1,0 +1,52 @@
+"""Host-side logic of the multi-GPU path on CPU: world_size-2 gloo ranks shard the cells, write part containers,
+reduce the max time, and the merge reproduces linkhdf5 (utils.py:217-253)."""
+import os
+
+import numpy as np
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+from higashi_b200 import parallel, sink
+
+
+def test_cell_shards_match_array_split():
+    for n, w in [(620, 8), (7, 2), (6000, 3), (5, 8)]:
+        sh = parallel.cell_shards(n, w)
+        ref = np.array_split(np.arange(n), w)
+        assert len(sh) == w
+        for (a, b), r in zip(sh, ref):
+            assert b - a == len(r)
+            if len(r):
+                assert a == r[0] and b == r[-1] + 1
+        assert sum(b - a for a, b in sh) == n
+
+
+def _worker(rank, world, tmp, port):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    n_cells, P = 11, 7
+    c0, c1 = parallel.cell_shards(n_cells, world)[rank]
+    sk = sink.ChromSink(tmp, "chr1", "emb_nbr_0_impute_part_%d" % rank)
+    sk.create_dataset("coordinates", np.arange(2 * P, dtype=np.int64).reshape(P, 2))
+    for cell in range(c0, c1):
+        sk.create_dataset("cell_%d" % cell, (np.arange(P) + 1 + cell).astype(np.float32), compress=True)
+    sk.close()
+    t = parallel.max_over_ranks(10.0 + rank)            # rank 1 is the slowest
+    assert t == 10.0 + world - 1
+    dist.barrier()
+    if rank == 0:
+        parallel.link_parts("emb_nbr_0_impute", parallel.cell_shards(n_cells, world), tmp, ["chr1"])
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_two_rank_gloo_shard_and_link(tmp_path):
+    world, port = 2, 29500 + (os.getpid() % 2000)
+    mp.spawn(_worker, args=(world, str(tmp_path), port), nprocs=world, join=True)
+    f = sink.read_container(str(tmp_path), "chr1", "emb_nbr_0_impute")
+    assert f["coordinates"].shape == (7, 2)
+    for cell in range(11):
+        v = (np.arange(7) + 1 + cell).astype(np.float32)
+        np.testing.assert_allclose(f["cell_%d" % cell], v / v.mean(), rtol=1e-6)      # utils.py:234
+    assert not [p for p in os.listdir(tmp_path) if "_part_" in p]
