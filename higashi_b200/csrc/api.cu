@@ -236,11 +236,14 @@ extern "C" int hsg_set_neighbors(hsg_ctx* c, const int32_t* nbr, const float* w,
     return 0;
 }
 
+int knn_build(hsg_ctx* c, const float* embed_host, int dim, int k1, int32_t* nbr_out, float* w_out);
+
 extern "C" int hsg_build_neighbors(hsg_ctx* c, const float* embed, int dim, int k1, int32_t* nbr_out, float* w_out) {
     CTX_GUARD(c);
-    (void)embed; (void)dim; (void)k1; (void)nbr_out; (void)w_out;
-    hsg_set_error("hsg_build_neighbors: not implemented in this build; pass the kNN lists via hsg_set_neighbors");
-    return 3;
+    HSG_CHECK(c->d > 0, "call hsg_set_dims first");
+    HSG_CHECK(embed && nbr_out && w_out && dim > 0, "bad kNN arguments");
+    if (knn_build(c, embed, dim, k1, nbr_out, w_out)) return 1;
+    return hsg_set_neighbors(c, nbr_out, w_out, k1);
 }
 
 // ---------------------------------------------------------------------------------------------

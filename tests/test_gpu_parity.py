@@ -188,3 +188,16 @@ def test_synthetic_vs_oracle(k, ltr, d, prec):
     print("max |err| (%s) = %.3g" % (prec, float(np.abs(got_all[cells] - ref).max())))
     np.testing.assert_allclose(got_all[cells], ref, atol=tol, rtol=0)
     eng.close()
+
+
+# ------------------------------------------------------------------ kNN cell graph (get_cell_neighbor): indices bit-exact
+@pytest.mark.parametrize("tag", ["a", "b", "c"])
+def test_knn_graph_bit_exact(tag):
+    g = load("knn.npz")
+    emb, k = g[tag + "/embed"], int(g[tag + "/k"])
+    eng = _engine()
+    eng.ctx.set_dims(64, emb.shape[0], [10], 1)
+    nbr0, w = eng.ctx.build_neighbors(emb, k + 1)
+    assert np.array_equal(nbr0.astype(np.int64) + 1, g[tag + "/nbr"])
+    np.testing.assert_allclose(w, g[tag + "/w"], rtol=3e-6, atol=1e-7)
+    eng.close()
