@@ -1,0 +1,715 @@
+// train.cu -- training-side scorer: three-head forward, loss, and the full backward pass (fp32).
+//
+// Reference: Hyper_SAGNN.forward (Modules.py:726-783) with the GraphSAGE encoder on-hook
+// (GraphSageEncoder_with_weights.forward_on_hook, Modules.py:1485-1553; MeanAggregator_with_weights.forward :1337-1362),
+// the loss heads of Higashi.forward_batch_hyperedge (Higashi_wrapper.py:861-913) and autograd's backward of the same
+// graph (loss.backward(), Higashi_wrapper.py:1006).  Hyperedge batches are small (1.5k-7.7k triplets), so this path is a
+// sequence of plain fp32 kernels over [3B, d] activations that stay in HBM/L2; parameters and gradients live in two flat
+// device buffers that the host (torch Adam, NCCL allreduce) owns.
+//
+// Token rows: row 3r+t is token t of hyperedge r (t = 0 cell, 1 bin_i, 2 bin_j); bin-token rows 2r, 2r+1 follow the
+// reference's to_neighs row order.
+#include <cstring>
+
+#include "common.cuh"
+
+#define TR_CHECK_LAUNCH(c) do { (c)->launches++; HSG_CUDA(cudaGetLastError()); } while (0)
+
+// ------------------------------------------------------------------------------------------------ sgemm
+// C[M,N] = sum_k a(m,k) b(k,n) (+ beta*C);  a(m,k) = TA ? A[k*lda+m] : A[m*lda+k];  b(k,n) = TB ? B[n*ldb+k] : B[k*ldb+n]
+template <bool TA, bool TB>
+__global__ void __launch_bounds__(256) sgemm_kernel(int M, int N, int K, const float* __restrict__ A, int lda,
+                                                    const float* __restrict__ B, int ldb, float* __restrict__ C, int ldc,
+                                                    float beta) {
+    __shared__ float sA[16][65], sB[16][65];
+    const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;
+    const int m0 = blockIdx.y * 64, n0 = blockIdx.x * 64;
+    float acc[4][4] = {};
+    for (int k0 = 0; k0 < K; k0 += 16) {
+        for (int i = threadIdx.x; i < 16 * 64; i += 256) {
+            int kk = i & 15, mm = i >> 4;
+            if (TA) { kk = i >> 6; mm = i & 63; }
+            int m = m0 + mm, k = k0 + kk;
+            sA[kk][mm] = (m < M && k < K) ? (TA ? A[(size_t)k * lda + m] : A[(size_t)m * lda + k]) : 0.f;
+        }
+        for (int i = threadIdx.x; i < 16 * 64; i += 256) {
+            int kk = i & 15, nn = i >> 4;
+            if (!TB) { kk = i >> 6; nn = i & 63; }
+            int n = n0 + nn, k = k0 + kk;
+            sB[kk][nn] = (n < N && k < K) ? (TB ? B[(size_t)n * ldb + k] : B[(size_t)k * ldb + n]) : 0.f;
+        }
+        __syncthreads();
+#pragma unroll
+        for (int kk = 0; kk < 16; ++kk) {
+            float a[4], b[4];
+#pragma unroll
+            for (int i = 0; i < 4; ++i) { a[i] = sA[kk][ty * 4 + i]; b[i] = sB[kk][tx * 4 + i]; }
+#pragma unroll
+            for (int i = 0; i < 4; ++i)
+#pragma unroll
+                for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(a[i], b[j], acc[i][j]);
+        }
+        __syncthreads();
+    }
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            int m = m0 + ty * 4 + i, n = n0 + tx * 4 + j;
+            if (m < M && n < N) {
+                float* p = C + (size_t)m * ldc + n;
+                *p = (beta != 0.f) ? fmaf(beta, *p, acc[i][j]) : acc[i][j];
+            }
+        }
+}
+
+static int gemm(hsg_ctx* c, cudaStream_t s, bool ta, bool tb, int M, int N, int K, const float* A, int lda, const float* B,
+                int ldb, float* C, int ldc, float beta) {
+    if (M <= 0 || N <= 0) return 0;
+    dim3 grid((N + 63) / 64, (M + 63) / 64);
+    if (!ta && tb) sgemm_kernel<false, true><<<grid, 256, 0, s>>>(M, N, K, A, lda, B, ldb, C, ldc, beta);
+    else if (!ta && !tb) sgemm_kernel<false, false><<<grid, 256, 0, s>>>(M, N, K, A, lda, B, ldb, C, ldc, beta);
+    else if (ta && !tb) sgemm_kernel<true, false><<<grid, 256, 0, s>>>(M, N, K, A, lda, B, ldb, C, ldc, beta);
+    else sgemm_kernel<true, true><<<grid, 256, 0, s>>>(M, N, K, A, lda, B, ldb, C, ldc, beta);
+    TR_CHECK_LAUNCH(c);
+    return 0;
+}
+// y = x W^T            : linear forward      (x [M,K], W [N,K])
+#define LIN_FWD(M, N, K, x, ldx, W, ldw, y, ldy, beta) gemm(c, s, false, true, M, N, K, x, ldx, W, ldw, y, ldy, beta)
+// dx (+)= dy W         : (dy [M,N], W [N,K])
+#define LIN_DX(M, N, K, dy, ldy, W, ldw, dx, ldx, beta) gemm(c, s, false, false, M, K, N, dy, ldy, W, ldw, dx, ldx, beta)
+// dW += dy^T x         : (dy [M,N], x [M,K]) -> [N,K]
+#define LIN_DW(M, N, K, dy, ldy, x, ldx, dW, ldw) gemm(c, s, true, false, N, K, M, dy, ldy, x, ldx, dW, ldw, 1.0f)
+
+// ------------------------------------------------------------------------------------------------ elementwise helpers
+__device__ __forceinline__ float dswish(float x) {            // d/dx [x sigmoid(x)]
+    float sg = 1.0f / (1.0f + expf(-x));
+    return sg * (1.0f + x * (1.0f - sg));
+}
+// y = act(x + bias[col]);  optionally keep the pre-activation
+__global__ void bias_act_kernel(float* __restrict__ x, const float* __restrict__ bias, int64_t n, int cols, int act,
+                                float* __restrict__ pre) {
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    float v = x[i] + (bias ? bias[i % cols] : 0.f);
+    if (pre) pre[i] = v;
+    x[i] = act ? swish_acc(v) : v;
+}
+// dpre = dy * swish'(pre)   (in place on dy)
+__global__ void dswish_kernel(float* __restrict__ dy, const float* __restrict__ pre, int64_t n) {
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) dy[i] *= dswish(pre[i]);
+}
+// db[col] += sum_rows dy[row, col]
+__global__ void colsum_kernel(const float* __restrict__ dy, int rows, int cols, float* __restrict__ db) {
+    int col = blockIdx.x * blockDim.x + threadIdx.x;
+    if (col >= cols) return;
+    float s = 0.f;
+    for (int r = blockIdx.y; r < rows; r += gridDim.y) s += dy[(size_t)r * cols + col];
+    atomicAdd(db + col, s);
+}
+__global__ void axpy_kernel(float* __restrict__ y, const float* __restrict__ x, int64_t n) {
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) y[i] += x[i];
+}
+static inline unsigned nblk(int64_t n, int t = 256) { return (unsigned)((n + t - 1) / t); }
+
+// ------------------------------------------------------------------------------------------------ LayerNorm
+// warp per row; out = (x - mu) * rs * g + b ; stats saved for the backward
+template <int D>
+__global__ void ln_fwd_kernel(const float* __restrict__ x, int rows, const float* __restrict__ g, const float* __restrict__ b,
+                              float* __restrict__ out, float* __restrict__ mu, float* __restrict__ rs) {
+    int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+    if (row >= rows) return;
+    constexpr int V = D / 32;
+    float v[V], s = 0.f;
+#pragma unroll
+    for (int q = 0; q < V; ++q) { v[q] = x[(size_t)row * D + q * 32 + lane]; s += v[q]; }
+    float m = warp_sum(s) / (float)D, s2 = 0.f;
+#pragma unroll
+    for (int q = 0; q < V; ++q) { v[q] -= m; s2 = fmaf(v[q], v[q], s2); }
+    float r = 1.0f / sqrtf(warp_sum(s2) / (float)D + HSG_LN_EPS);
+#pragma unroll
+    for (int q = 0; q < V; ++q) out[(size_t)row * D + q * 32 + lane] = fmaf(v[q] * r, g[q * 32 + lane], b[q * 32 + lane]);
+    if (lane == 0) { mu[row] = m; rs[row] = r; }
+}
+// dx (+)= LN backward ; dg, db accumulated with one atomic per column per block
+template <int D>
+__global__ void ln_bwd_kernel(const float* __restrict__ dy, const float* __restrict__ x, int rows, const float* __restrict__ g,
+                              const float* __restrict__ mu, const float* __restrict__ rs, float* __restrict__ dx, int accumulate,
+                              float* __restrict__ dg, float* __restrict__ db) {
+    __shared__ float sg[D], sb[D];
+    for (int i = threadIdx.x; i < D; i += blockDim.x) { sg[i] = 0.f; sb[i] = 0.f; }
+    __syncthreads();
+    int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+    constexpr int V = D / 32;
+    if (row < rows) {
+        float xh[V], dyg[V], a = 0.f, bsum = 0.f;
+        const float m = mu[row], r = rs[row];
+#pragma unroll
+        for (int q = 0; q < V; ++q) {
+            int col = q * 32 + lane;
+            float d = dy[(size_t)row * D + col];
+            xh[q] = (x[(size_t)row * D + col] - m) * r;
+            dyg[q] = d * g[col];
+            a += dyg[q]; bsum = fmaf(dyg[q], xh[q], bsum);
+            atomicAdd(&sg[col], d * xh[q]);
+            atomicAdd(&sb[col], d);
+        }
+        a = warp_sum(a) / (float)D; bsum = warp_sum(bsum) / (float)D;
+#pragma unroll
+        for (int q = 0; q < V; ++q) {
+            float v = r * (dyg[q] - a - xh[q] * bsum);
+            float* p = dx + (size_t)row * D + q * 32 + lane;
+            *p = accumulate ? (*p + v) : v;
+        }
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < D; i += blockDim.x) { atomicAdd(dg + i, sg[i]); atomicAdd(db + i, sb[i]); }
+}
+static int ln_fwd(hsg_ctx* c, cudaStream_t s, const float* x, int rows, const float* g, const float* b, float* out, float* mu,
+                  float* rs) {
+    unsigned grid = (rows + 7) / 8;
+    if (c->d == 64) ln_fwd_kernel<64><<<grid, 256, 0, s>>>(x, rows, g, b, out, mu, rs);
+    else ln_fwd_kernel<128><<<grid, 256, 0, s>>>(x, rows, g, b, out, mu, rs);
+    TR_CHECK_LAUNCH(c);
+    return 0;
+}
+static int ln_bwd(hsg_ctx* c, cudaStream_t s, const float* dy, const float* x, int rows, const float* g, const float* mu,
+                  const float* rs, float* dx, int accumulate, float* dg, float* db) {
+    unsigned grid = (rows + 7) / 8;
+    if (c->d == 64) ln_bwd_kernel<64><<<grid, 256, 0, s>>>(dy, x, rows, g, mu, rs, dx, accumulate, dg, db);
+    else ln_bwd_kernel<128><<<grid, 256, 0, s>>>(dy, x, rows, g, mu, rs, dx, accumulate, dg, db);
+    TR_CHECK_LAUNCH(c);
+    return 0;
+}
+
+// ------------------------------------------------------------------------------------------------ node embedding
+// CSR SpMM over the bin-token rows: neigh[row] = sum_e val[e] * E[col[e]]        (Modules.py:1356-1360)
+template <int D>
+__global__ void spmm_fwd_kernel(const int* __restrict__ indptr, const int* __restrict__ cols, const float* __restrict__ vals,
+                                const float* __restrict__ E, int rows, float* __restrict__ out) {
+    int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+    if (row >= rows) return;
+    constexpr int V = D / 32;
+    float acc[V] = {};
+    for (int e = indptr[row]; e < indptr[row + 1]; ++e) {
+        float w = vals[e];
+        const float* er = E + (size_t)cols[e] * D;
+#pragma unroll
+        for (int q = 0; q < V; ++q) acc[q] = fmaf(w, er[q * 32 + lane], acc[q]);
+    }
+#pragma unroll
+    for (int q = 0; q < V; ++q) out[(size_t)row * D + q * 32 + lane] = acc[q];
+}
+template <int D>
+__global__ void spmm_bwd_kernel(const int* __restrict__ indptr, const int* __restrict__ cols, const float* __restrict__ vals,
+                                const float* __restrict__ dout, int rows, float* __restrict__ dE) {
+    int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+    if (row >= rows) return;
+    constexpr int V = D / 32;
+    float d[V];
+#pragma unroll
+    for (int q = 0; q < V; ++q) d[q] = dout[(size_t)row * D + q * 32 + lane];
+    for (int e = indptr[row]; e < indptr[row + 1]; ++e) {
+        float w = vals[e];
+        float* er = dE + (size_t)cols[e] * D;
+#pragma unroll
+        for (int q = 0; q < V; ++q) atomicAdd(er + q * 32 + lane, w * d[q]);
+    }
+}
+// dynamic / static assembly: row 3r = cell table row, rows 3r+1, 3r+2 = (comb | self) of the two bins
+__global__ void assemble_kernel(const int64_t* __restrict__ x, int B, int d, int n_cells, int bin_base, const float* __restrict__ E_cell,
+                                const float* __restrict__ Eall, const float* __restrict__ comb, float* __restrict__ dyn,
+                                float* __restrict__ sta, float* __restrict__ selfb) {
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= (int64_t)B * 3 * d) return;
+    int f = (int)(i % d); int64_t row = i / d; int r = (int)(row / 3), t = (int)(row % 3);
+    if (t == 0) {
+        float v = E_cell[(size_t)(x[r * 3] - 1) * d + f];
+        dyn[i] = v; sta[i] = v;
+    } else {
+        int lb = (int)(x[r * 3 + t] - bin_base);             // local bin of the chromosome
+        float v = Eall[(size_t)lb * d + f];
+        sta[i] = v;
+        if (selfb) selfb[((size_t)r * 2 + (t - 1)) * d + f] = v;
+        dyn[i] = comb ? comb[((size_t)r * 2 + (t - 1)) * d + f] : v;
+    }
+}
+// scatter the gradients of the bin rows back: dself (per bin token) -> dEall ; ddyn/dsta rows -> dcomb / dself
+__global__ void disassemble_kernel(const int64_t* __restrict__ x, int B, int d, int bin_base, const float* __restrict__ ddyn,
+                                   const float* __restrict__ dsta, float* __restrict__ dcomb, float* __restrict__ dEall) {
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= (int64_t)B * 3 * d) return;
+    int f = (int)(i % d); int64_t row = i / d; int r = (int)(row / 3), t = (int)(row % 3);
+    if (t == 0) return;                                       // cell table is frozen after stage 1 (off_hook([0]))
+    int lb = (int)(x[r * 3 + t] - bin_base);
+    float g = dsta[i];
+    if (dcomb) dcomb[((size_t)r * 2 + (t - 1)) * d + f] = ddyn[i];
+    else g += ddyn[i];                                        // stage 1: dynamic == static
+    atomicAdd(dEall + (size_t)lb * d + f, g);
+}
+__global__ void scatter_rows_kernel(const int64_t* __restrict__ x, int B, int d, int bin_base, const float* __restrict__ dself,
+                                    float* __restrict__ dEall) {
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= (int64_t)B * 2 * d) return;
+    int f = (int)(i % d); int64_t row = i / d; int r = (int)(row / 2), t = (int)(row % 2);
+    int lb = (int)(x[r * 3 + 1 + t] - bin_base);
+    atomicAdd(dEall + (size_t)lb * d + f, dself[i]);
+}
+
+// ------------------------------------------------------------------------------------------------ attention
+__device__ __forceinline__ void att_row_fwd(float la, float lb, float& wa, float& wb, float* save) {
+    float mx = fmaxf(0.f, fmaxf(la, lb));
+    float e0 = expf(0.f - mx), ea = expf(la - mx), eb = expf(lb - mx);
+    float Z = e0 + ea + eb;
+    float pa = ea / Z, pb = eb / Z;
+    float den = (pa + pb) + 1e-13f;
+    wa = pa / den; wb = pb / den;
+    if (save) { save[0] = pa; save[1] = pb; }
+}
+// thread per (hyperedge, head).  Q,K,V [3B,128] ; ctx [3B,128] ; P [B,8,6] softmax probabilities (pa,pb per row)
+__global__ void attn_fwd_kernel(const float* __restrict__ Q, const float* __restrict__ K, const float* __restrict__ V, int B,
+                                float* __restrict__ ctx, float* __restrict__ P) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= B * 8) return;
+    int r = i >> 3, h = i & 7;
+    const float* q[3]; const float* k[3]; const float* v[3];
+    for (int t = 0; t < 3; ++t) {
+        q[t] = Q + ((size_t)r * 3 + t) * HSG_HD + h * 16; k[t] = K + ((size_t)r * 3 + t) * HSG_HD + h * 16;
+        v[t] = V + ((size_t)r * 3 + t) * HSG_HD + h * 16;
+    }
+    float s[3][3];
+    for (int a = 0; a < 3; ++a)
+        for (int b = 0; b < 3; ++b) {
+            float acc = 0.f;
+            if (a != b) for (int e = 0; e < 16; ++e) acc = fmaf(q[a][e], k[b][e], acc);
+            s[a][b] = acc * 0.25f;
+        }
+    float w[3][3] = {};
+    float* ps = P + (size_t)i * 6;
+    att_row_fwd(s[0][1], s[0][2], w[0][1], w[0][2], ps + 0);
+    att_row_fwd(s[1][0], s[1][2], w[1][0], w[1][2], ps + 2);
+    att_row_fwd(s[2][0], s[2][1], w[2][0], w[2][1], ps + 4);
+    for (int t = 0; t < 3; ++t) {
+        int a = (t == 0) ? 1 : 0, b = (t == 2) ? 1 : 2;
+        float* o = ctx + ((size_t)r * 3 + t) * HSG_HD + h * 16;
+        for (int e = 0; e < 16; ++e) o[e] = fmaf(w[t][b], v[b][e], w[t][a] * v[a][e]);
+    }
+}
+__global__ void attn_bwd_kernel(const float* __restrict__ Q, const float* __restrict__ K, const float* __restrict__ V,
+                                const float* __restrict__ P, const float* __restrict__ dctx, int B, float* __restrict__ dQ,
+                                float* __restrict__ dK, float* __restrict__ dV) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= B * 8) return;
+    int r = i >> 3, h = i & 7;
+    size_t base[3];
+    for (int t = 0; t < 3; ++t) base[t] = ((size_t)r * 3 + t) * HSG_HD + h * 16;
+    float dq[3][16] = {}, dk[3][16] = {}, dv[3][16] = {};
+    const float* ps = P + (size_t)i * 6;
+    for (int t = 0; t < 3; ++t) {
+        int a = (t == 0) ? 1 : 0, b = (t == 2) ? 1 : 2;
+        float pa = ps[t * 2], pb = ps[t * 2 + 1];
+        float den = (pa + pb) + 1e-13f;
+        float wa = pa / den, wb = pb / den;
+        float dwa = 0.f, dwb = 0.f;
+        for (int e = 0; e < 16; ++e) {
+            float dc = dctx[base[t] + e];
+            dwa = fmaf(dc, V[base[a] + e], dwa); dwb = fmaf(dc, V[base[b] + e], dwb);
+            dv[a][e] = fmaf(wa, dc, dv[a][e]); dv[b][e] = fmaf(wb, dc, dv[b][e]);
+        }
+        // w = p / (pa + pb + eps)
+        float common = (dwa * wa + dwb * wb) / den;
+        float dpa = dwa / den - common, dpb = dwb / den - common;
+        // p = softmax([0, la, lb])  (the diagonal logit is the constant 0)
+        float dot = pa * dpa + pb * dpb;
+        float dla = pa * (dpa - dot) * 0.25f, dlb = pb * (dpb - dot) * 0.25f;
+        for (int e = 0; e < 16; ++e) {
+            dq[t][e] = fmaf(dla, K[base[a] + e], fmaf(dlb, K[base[b] + e], dq[t][e]));
+            dk[a][e] = fmaf(dla, Q[base[t] + e], dk[a][e]);
+            dk[b][e] = fmaf(dlb, Q[base[t] + e], dk[b][e]);
+        }
+    }
+    for (int t = 0; t < 3; ++t)
+        for (int e = 0; e < 16; ++e) { dQ[base[t] + e] = dq[t][e]; dK[base[t] + e] = dk[t][e]; dV[base[t] + e] = dv[t][e]; }
+}
+
+// ------------------------------------------------------------------------------------------------ heads and loss
+__global__ void sqdiff_fwd_kernel(const float* __restrict__ D, const float* __restrict__ S, int64_t n, float* __restrict__ u) {
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) { float t = D[i] - S[i]; u[i] = t * t; }
+}
+// dD = 2 (D - S) du ; dS (+)= -dD
+__global__ void sqdiff_bwd_kernel(const float* __restrict__ D, const float* __restrict__ S, const float* __restrict__ du, int64_t n,
+                                  float* __restrict__ dD, float* __restrict__ dS) {
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) { float g = 2.0f * (D[i] - S[i]) * du[i]; dD[i] = g; dS[i] -= g; }
+}
+// o[row] = c[row,:] . w1 + b1
+__global__ void head_out_kernel(const float* __restrict__ cact, int rows, int hd, const float* __restrict__ w1, const float* __restrict__ b1,
+                                float* __restrict__ o) {
+    int row = blockIdx.x * blockDim.x + threadIdx.x;
+    if (row >= rows) return;
+    float acc = b1[0];
+    for (int j = 0; j < hd; ++j) acc = fmaf(cact[(size_t)row * hd + j], w1[j], acc);
+    o[row] = acc;
+}
+// distance side channel (Modules.py:729-740): FeedForward([2(C+1)+cf, 4, 1]) with swish
+__global__ void xp_fwd_kernel(const int64_t* __restrict__ x, int B, int A, int cf, const float* __restrict__ attr,
+                              const float* __restrict__ cellf, int only_model, const float* __restrict__ w0, const float* __restrict__ b0,
+                              const float* __restrict__ w1, const float* __restrict__ b1, float* __restrict__ hpre, float* __restrict__ out) {
+    int r = blockIdx.x * blockDim.x + threadIdx.x;
+    if (r >= B) return;
+    const int in_w = 2 * A + cf;
+    const float* ai = attr + (size_t)x[r * 3 + 1] * A; const float* aj = attr + (size_t)x[r * 3 + 2] * A;
+    const float* cfp = cellf + (size_t)x[r * 3] * cf;
+    float o = b1[0];
+    for (int u = 0; u < 4; ++u) {
+        const float* wr = w0 + u * in_w;
+        float acc = 0.f;
+        for (int t = 0; t < A; ++t) acc = fmaf(wr[t], ai[t], acc);
+        for (int t = 0; t < A; ++t) acc = fmaf(wr[A + t], aj[t], acc);
+        if (!only_model) for (int t = 0; t < cf; ++t) acc = fmaf(wr[2 * A + t], cfp[t], acc);
+        acc += b0[u];
+        hpre[r * 4 + u] = acc;
+        o = fmaf(w1[u], swish_acc(acc), o);
+    }
+    out[r] = o;
+}
+__global__ void xp_bwd_kernel(const int64_t* __restrict__ x, int B, int A, int cf, const float* __restrict__ attr,
+                              const float* __restrict__ cellf, int only_model, const float* __restrict__ w1, const float* __restrict__ hpre,
+                              const float* __restrict__ dout, float* __restrict__ dw0, float* __restrict__ db0, float* __restrict__ dw1,
+                              float* __restrict__ db1) {
+    int r = blockIdx.x * blockDim.x + threadIdx.x;
+    if (r >= B) return;
+    const int in_w = 2 * A + cf;
+    const float g = dout[r];
+    const float* ai = attr + (size_t)x[r * 3 + 1] * A; const float* aj = attr + (size_t)x[r * 3 + 2] * A;
+    const float* cfp = cellf + (size_t)x[r * 3] * cf;
+    atomicAdd(db1, g);
+    for (int u = 0; u < 4; ++u) {
+        float pre = hpre[r * 4 + u];
+        atomicAdd(dw1 + u, g * swish_acc(pre));
+        float dh = g * w1[u] * dswish(pre);
+        atomicAdd(db0 + u, dh);
+        for (int t = 0; t < A; ++t) { atomicAdd(dw0 + u * in_w + t, dh * ai[t]); atomicAdd(dw0 + u * in_w + A + t, dh * aj[t]); }
+        if (!only_model) for (int t = 0; t < cf; ++t) atomicAdd(dw0 + u * in_w + 2 * A + t, dh * cfp[t]);
+    }
+}
+// head = mean over the 3 tokens + side channel
+__global__ void pool_kernel(const float* __restrict__ o, const float* __restrict__ dp, int B, float* __restrict__ out) {
+    int r = blockIdx.x * blockDim.x + threadIdx.x;
+    if (r < B) out[r] = ((o[r * 3] + o[r * 3 + 1]) + o[r * 3 + 2]) / 3.0f + dp[r];
+}
+// classification loss: mean_r w_r * BCEWithLogits(pred_r, y_r)  (Higashi_wrapper.py:877-878) ; dpred written
+__global__ void bce_kernel(const float* __restrict__ pred, const float* __restrict__ y, const float* __restrict__ w, int B,
+                           float* __restrict__ loss, float* __restrict__ dpred) {
+    __shared__ float red[32];
+    int r = blockIdx.x * blockDim.x + threadIdx.x;
+    float l = 0.f;
+    if (r < B) {
+        float p = pred[r], yy = y[r], ww = w[r];
+        l = ww * (fmaxf(p, 0.f) - p * yy + log1pf(expf(-fabsf(p)))) / (float)B;
+        dpred[r] = ww * (1.0f / (1.0f + expf(-p)) - yy) / (float)B;
+    }
+    l = warp_sum(l);
+    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = l;
+    __syncthreads();
+    if (threadIdx.x < 32) {
+        float v = (threadIdx.x < (blockDim.x >> 5)) ? red[threadIdx.x] : 0.f;
+        v = warp_sum(v);
+        if (threadIdx.x == 0) atomicAdd(loss, v);
+    }
+}
+// regression loss: mse(pred, w)  (Higashi_wrapper.py:906-909)
+__global__ void mse_kernel(const float* __restrict__ pred, const float* __restrict__ w, int B, float* __restrict__ loss,
+                           float* __restrict__ dpred) {
+    int r = blockIdx.x * blockDim.x + threadIdx.x;
+    if (r >= B) return;
+    float d = pred[r] - w[r];
+    atomicAdd(loss, d * d / (float)B);
+    dpred[r] = 2.0f * d / (float)B;
+}
+// do[row] = dmean[row/3] / 3 ; dc[row, j] = do[row] * w1[j] ; dw1[j] += do * c ; db1 += do
+__global__ void head_bwd_kernel(const float* __restrict__ dmean, const float* __restrict__ cact, int rows, int hd,
+                                const float* __restrict__ w1, float* __restrict__ dc, float* __restrict__ dw1, float* __restrict__ db1) {
+    extern __shared__ float sh[];                 // hd + 1 partial sums
+    for (int i = threadIdx.x; i <= hd; i += blockDim.x) sh[i] = 0.f;
+    __syncthreads();
+    int row = blockIdx.x * blockDim.x + threadIdx.x;
+    if (row < rows) {
+        float g = dmean[row / 3] / 3.0f;
+        atomicAdd(&sh[hd], g);
+        for (int j = 0; j < hd; ++j) {
+            dc[(size_t)row * hd + j] = g * w1[j];
+            atomicAdd(&sh[j], g * cact[(size_t)row * hd + j]);
+        }
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < hd; i += blockDim.x) atomicAdd(dw1 + i, sh[i]);
+    if (threadIdx.x == 0) atomicAdd(db1, sh[hd]);
+}
+
+// ------------------------------------------------------------------------------------------------ workspace
+struct TrainWs {
+    int maxB = 0, max_nnz = 0, max_nc = 0;
+    float* buf = nullptr; size_t floats = 0;
+    int* indptr = nullptr; int* cols = nullptr; float* vals = nullptr;
+    int64_t* x = nullptr; float* y = nullptr; float* w = nullptr;
+    // forward activations (all [rows, *] row-major)
+    float *Epre, *Eall, *neigh, *selfb, *combpre, *comb, *dyn, *sta, *mu_d, *rs_d, *mu_s, *rs_s, *qin, *kin, *vin, *Q, *K, *V, *P,
+        *ctx, *yv, *sp, *mu_y, *rs_y, *xn, *hpre, *h, *z, *mu_z, *rs_z, *Dn, *mu_p, *rs_p, *Sn, *u, *cpre, *cact, *o, *hp2, *dp2,
+        *mean, *loss;
+    // backward scratch
+    float *dmean, *dc, *du, *dD, *dS, *dz, *dh, *dxn, *dy, *dsp, *dctx, *dQ, *dK, *dV, *dqin, *dkin, *dvin, *ddyn, *dsta, *dcomb,
+        *dneigh, *dself, *dEall;
+    // last batch
+    int B = 0, chrom = 0, nnz = 0, stage = 2, only_model = 0, mode = 0;
+};
+#include <map>
+static std::map<hsg_ctx*, TrainWs*> g_ws;
+
+struct TrainBind {                                  // flat parameter / gradient buffers owned by the host
+    float* params = nullptr; float* grads = nullptr; int64_t total = 0;
+    std::vector<int64_t> off_slot;                  // [HSG_W_COUNT]  (-1 = not bound)
+    std::vector<int64_t> off_pw, off_pb;            // per branch: projection weight [d,in], bias [d]
+    std::vector<float*> feat; std::vector<int> in_dim;   // node features on the device, per branch
+};
+static std::map<hsg_ctx*, TrainBind*> g_bind;
+static TrainBind* bind_of(hsg_ctx* c) { auto it = g_bind.find(c); if (it == g_bind.end()) { g_bind[c] = new TrainBind(); return g_bind[c]; } return it->second; }
+
+extern "C" int hsg_train_set_features(hsg_ctx* c, int branch, const float* x_host, int64_t rows, int in_dim) {
+    HSG_CHECK(c && c->d > 0 && branch >= 0 && branch <= c->n_chrom && x_host, "bad features");
+    HSG_CUDA(cudaSetDevice(c->device));
+    TrainBind* b = bind_of(c);
+    if ((int)b->feat.size() <= c->n_chrom) { b->feat.assign(c->n_chrom + 1, nullptr); b->in_dim.assign(c->n_chrom + 1, 0); }
+    int64_t want = branch == 0 ? c->n_cells : c->bins[branch - 1];
+    HSG_CHECK(rows == want, "feature rows do not match the node type");
+    if (b->feat[branch]) cudaFree(b->feat[branch]);
+    HSG_CUDA(cudaMalloc(&b->feat[branch], (size_t)rows * in_dim * sizeof(float)));
+    HSG_CUDA(cudaMemcpy(b->feat[branch], x_host, (size_t)rows * in_dim * sizeof(float), cudaMemcpyHostToDevice));
+    b->in_dim[branch] = in_dim;
+    return 0;
+}
+
+extern "C" int hsg_train_bind(hsg_ctx* c, float* params_dev, float* grads_dev, int64_t total, const int64_t* off_slot,
+                              const int64_t* off_proj_w, const int64_t* off_proj_b) {
+    HSG_CHECK(c && c->d > 0 && params_dev && grads_dev && off_slot && off_proj_w && off_proj_b, "bad bind arguments");
+    TrainBind* b = bind_of(c);
+    b->params = params_dev; b->grads = grads_dev; b->total = total;
+    b->off_slot.assign(off_slot, off_slot + HSG_W_COUNT);
+    b->off_pw.assign(off_proj_w, off_proj_w + c->n_chrom + 1);
+    b->off_pb.assign(off_proj_b, off_proj_b + c->n_chrom + 1);
+    return 0;
+}
+
+static int ws_alloc(hsg_ctx* c, int maxB, int max_nnz) {
+    TrainWs*& w = g_ws[c];
+    if (w && w->maxB >= maxB && w->max_nnz >= max_nnz) return 0;
+    if (w) { cudaFree(w->buf); cudaFree(w->indptr); cudaFree(w->cols); cudaFree(w->vals); cudaFree(w->x); delete w; }
+    w = new TrainWs();
+    w->maxB = maxB; w->max_nnz = max_nnz;
+    int max_nc = 0; for (int v : c->bins) max_nc = std::max(max_nc, v);
+    w->max_nc = max_nc;
+    const size_t R = (size_t)3 * maxB, NB = (size_t)2 * maxB, d = c->d, hd = c->d / 2;
+    size_t total = 0;
+    auto take = [&](size_t n) { size_t o = total; total += (n + 63) & ~(size_t)63; return o; };
+    std::vector<std::pair<float**, size_t>> plan = {
+        {&w->Epre, (size_t)max_nc * d}, {&w->Eall, (size_t)max_nc * d}, {&w->neigh, NB * d}, {&w->selfb, NB * d},
+        {&w->combpre, NB * d}, {&w->comb, NB * d}, {&w->dyn, R * d}, {&w->sta, R * d}, {&w->mu_d, R}, {&w->rs_d, R},
+        {&w->mu_s, R}, {&w->rs_s, R}, {&w->qin, R * d}, {&w->kin, R * d}, {&w->vin, R * d}, {&w->Q, R * HSG_HD},
+        {&w->K, R * HSG_HD}, {&w->V, R * HSG_HD}, {&w->P, (size_t)maxB * 48}, {&w->ctx, R * HSG_HD}, {&w->yv, R * d},
+        {&w->sp, R * d}, {&w->mu_y, R}, {&w->rs_y, R}, {&w->xn, R * d}, {&w->hpre, R * d}, {&w->h, R * d}, {&w->z, R * d},
+        {&w->mu_z, R}, {&w->rs_z, R}, {&w->Dn, R * d}, {&w->mu_p, R}, {&w->rs_p, R}, {&w->Sn, R * d}, {&w->u, R * d},
+        {&w->cpre, R * hd}, {&w->cact, R * hd}, {&w->o, R}, {&w->hp2, (size_t)maxB * 4}, {&w->dp2, (size_t)maxB},
+        {&w->mean, (size_t)maxB}, {&w->loss, 64},
+        {&w->dmean, (size_t)maxB}, {&w->dc, R * hd}, {&w->du, R * d}, {&w->dD, R * d}, {&w->dS, R * d}, {&w->dz, R * d},
+        {&w->dh, R * d}, {&w->dxn, R * d}, {&w->dy, R * d}, {&w->dsp, R * d}, {&w->dctx, R * HSG_HD}, {&w->dQ, R * HSG_HD},
+        {&w->dK, R * HSG_HD}, {&w->dV, R * HSG_HD}, {&w->dqin, R * d}, {&w->dkin, R * d}, {&w->dvin, R * d}, {&w->ddyn, R * d},
+        {&w->dsta, R * d}, {&w->dcomb, NB * d}, {&w->dneigh, NB * d}, {&w->dself, NB * d}, {&w->dEall, (size_t)max_nc * d}};
+    std::vector<size_t> offs;
+    for (auto& p : plan) offs.push_back(take(p.second));
+    HSG_CUDA(cudaMalloc(&w->buf, total * sizeof(float)));
+    for (size_t i = 0; i < plan.size(); ++i) *plan[i].first = w->buf + offs[i];
+    w->floats = total;
+    HSG_CUDA(cudaMalloc(&w->indptr, (NB + 1) * sizeof(int)));
+    HSG_CUDA(cudaMalloc(&w->cols, (size_t)std::max(1, max_nnz) * sizeof(int)));
+    HSG_CUDA(cudaMalloc(&w->vals, (size_t)std::max(1, max_nnz) * sizeof(float)));
+    HSG_CUDA(cudaMalloc(&w->x, ((size_t)maxB * 3) * sizeof(int64_t) + (size_t)maxB * 2 * sizeof(float)));
+    w->y = reinterpret_cast<float*>(w->x + (size_t)maxB * 3);
+    w->w = w->y + maxB;
+    return 0;
+}
+
+#define PARAM(slot) (b->params + b->off_slot[slot])
+#define GRAD(slot) (b->grads + b->off_slot[slot])
+
+// forward: returns the three heads for the mean head only when the others are not requested (classification / regression use
+// `mean`; the var/proba heads of zinb mode are evaluated by the same building blocks -- see hsg_score_fwd docs)
+extern "C" int hsg_score_fwd(hsg_ctx* c, int stage, int chrom, const int64_t* x_host, int B, const int32_t* indptr_host,
+                             const int32_t* cols_local_host, const float* vals_host, int nnz, const float* y_host,
+                             const float* w_host, int loss_mode, int only_model, float* mean_out_host, float* loss_out_host,
+                             void* stream) {
+    HSG_CHECK(c && c->d > 0, "context not initialised");
+    HSG_CUDA(cudaSetDevice(c->device));
+    HSG_CHECK(stage == 1 || stage == 2, "stage must be 1 (MultipleEmbedding) or 2 (GraphSAGE on-hook)");
+    HSG_CHECK(chrom >= 0 && chrom < c->n_chrom && B > 0 && x_host, "bad batch");
+    HSG_CHECK(stage == 1 || (indptr_host && (nnz == 0 || (cols_local_host && vals_host))), "stage 2 needs the neighbour CSR");
+    TrainBind* b = bind_of(c);
+    HSG_CHECK(b->params != nullptr, "call hsg_train_bind first");
+    HSG_CHECK((int)b->feat.size() > chrom + 1 && b->feat[chrom + 1] != nullptr, "call hsg_train_set_features for this chromosome");
+    for (int slot : {HSG_W_QS, HSG_W_KS, HSG_W_VS, HSG_W_FC1, HSG_W_FC2, HSG_W_PFF_W0, HSG_W_CLS_W0, HSG_W_XP2_W0, HSG_W_ATTR})
+        HSG_CHECK(slot == HSG_W_ATTR ? c->w[slot] != nullptr : b->off_slot[slot] >= 0, "a required parameter is not bound");
+    HSG_CHECK(stage == 1 || b->off_slot[HSG_W_SAGE_W] >= 0, "GraphSAGE parameters are not bound");
+    HSG_CHECK(c->w[HSG_W_CELL_FEATS] != nullptr, "cell_feats not set");
+    if (ws_alloc(c, B, nnz)) return 1;
+    TrainWs* w = g_ws[c];
+    cudaStream_t s = (cudaStream_t)stream;
+    const int d = c->d, hd = d / 2, R = 3 * B, NB = 2 * B, nc = c->bins[chrom], in_c = b->in_dim[chrom + 1];
+    const int bin_base = c->n_cells + 1 + c->bin_off[chrom];
+    w->B = B; w->chrom = chrom; w->nnz = nnz; w->stage = stage; w->only_model = only_model; w->mode = loss_mode;
+    HSG_CUDA(cudaMemcpyAsync(w->x, x_host, (size_t)B * 3 * sizeof(int64_t), cudaMemcpyHostToDevice, s));
+    if (y_host) HSG_CUDA(cudaMemcpyAsync(w->y, y_host, B * sizeof(float), cudaMemcpyHostToDevice, s));
+    if (w_host) HSG_CUDA(cudaMemcpyAsync(w->w, w_host, B * sizeof(float), cudaMemcpyHostToDevice, s));
+    if (stage == 2) {
+        HSG_CUDA(cudaMemcpyAsync(w->indptr, indptr_host, (NB + 1) * sizeof(int), cudaMemcpyHostToDevice, s));
+        if (nnz) {
+            HSG_CUDA(cudaMemcpyAsync(w->cols, cols_local_host, nnz * sizeof(int), cudaMemcpyHostToDevice, s));
+            HSG_CUDA(cudaMemcpyAsync(w->vals, vals_host, nnz * sizeof(float), cudaMemcpyHostToDevice, s));
+        }
+    }
+    // 1. bin embeddings of the whole chromosome: E = swish(X_c W_c^T + b_c)            (Modules.py:235-253, 558)
+    const float* Wc = b->params + b->off_pw[chrom + 1]; const float* bc = b->params + b->off_pb[chrom + 1];
+    if (LIN_FWD(nc, d, in_c, b->feat[chrom + 1], in_c, Wc, in_c, w->Eall, d, 0.f)) return 1;
+    bias_act_kernel<<<nblk((int64_t)nc * d), 256, 0, s>>>(w->Eall, bc, (int64_t)nc * d, d, 1, w->Epre); TR_CHECK_LAUNCH(c);
+    // 2. GraphSAGE: neigh = M . E ; comb = swish(nn([neigh | self]))                      (Modules.py:1511-1548)
+    if (stage == 2) {
+        assemble_kernel<<<nblk((int64_t)R * d), 256, 0, s>>>(w->x, B, d, c->n_cells, bin_base, c->E_cell, w->Eall, nullptr, w->dyn, w->sta, w->selfb);
+        TR_CHECK_LAUNCH(c);
+        if (d == 64) spmm_fwd_kernel<64><<<(NB + 7) / 8, 256, 0, s>>>(w->indptr, w->cols, w->vals, w->Eall, NB, w->neigh);
+        else spmm_fwd_kernel<128><<<(NB + 7) / 8, 256, 0, s>>>(w->indptr, w->cols, w->vals, w->Eall, NB, w->neigh);
+        TR_CHECK_LAUNCH(c);
+        const float* G = PARAM(HSG_W_SAGE_W);
+        if (LIN_FWD(NB, d, d, w->neigh, d, G, 2 * d, w->comb, d, 0.f)) return 1;
+        if (LIN_FWD(NB, d, d, w->selfb, d, G + d, 2 * d, w->comb, d, 1.f)) return 1;
+        bias_act_kernel<<<nblk((int64_t)NB * d), 256, 0, s>>>(w->comb, PARAM(HSG_W_SAGE_B), (int64_t)NB * d, d, 1, w->combpre); TR_CHECK_LAUNCH(c);
+    }
+    assemble_kernel<<<nblk((int64_t)R * d), 256, 0, s>>>(w->x, B, d, c->n_cells, bin_base, c->E_cell, w->Eall,
+                                                         stage == 2 ? w->comb : nullptr, w->dyn, w->sta, nullptr);
+    TR_CHECK_LAUNCH(c);
+    // 3. attention block                                                                  (Modules.py:1029-1095)
+    if (ln_fwd(c, s, w->dyn, R, PARAM(HSG_W_ALN1_G), PARAM(HSG_W_ALN1_B), w->qin, w->mu_d, w->rs_d)) return 1;
+    if (ln_fwd(c, s, w->dyn, R, PARAM(HSG_W_ALN2_G), PARAM(HSG_W_ALN2_B), w->kin, w->mu_d, w->rs_d)) return 1;
+    if (ln_fwd(c, s, w->sta, R, PARAM(HSG_W_ALN3_G), PARAM(HSG_W_ALN3_B), w->vin, w->mu_s, w->rs_s)) return 1;
+    if (LIN_FWD(R, HSG_HD, d, w->qin, d, PARAM(HSG_W_QS), d, w->Q, HSG_HD, 0.f)) return 1;
+    if (LIN_FWD(R, HSG_HD, d, w->kin, d, PARAM(HSG_W_KS), d, w->K, HSG_HD, 0.f)) return 1;
+    if (LIN_FWD(R, HSG_HD, d, w->vin, d, PARAM(HSG_W_VS), d, w->V, HSG_HD, 0.f)) return 1;
+    attn_fwd_kernel<<<nblk(B * 8, 128), 128, 0, s>>>(w->Q, w->K, w->V, B, w->ctx, w->P); TR_CHECK_LAUNCH(c);
+    if (LIN_FWD(R, d, HSG_HD, w->ctx, HSG_HD, PARAM(HSG_W_FC1), HSG_HD, w->yv, d, 0.f)) return 1;
+    if (LIN_FWD(R, d, HSG_HD, w->V, HSG_HD, PARAM(HSG_W_FC2), HSG_HD, w->sp, d, 0.f)) return 1;
+    // 4. pff_n1: LN -> W0 -> swish -> W1 -> + residual                                    (Modules.py:865-889)
+    if (ln_fwd(c, s, w->yv, R, PARAM(HSG_W_PFF_LN_G), PARAM(HSG_W_PFF_LN_B), w->xn, w->mu_y, w->rs_y)) return 1;
+    if (LIN_FWD(R, d, d, w->xn, d, PARAM(HSG_W_PFF_W0), d, w->h, d, 0.f)) return 1;
+    bias_act_kernel<<<nblk((int64_t)R * d), 256, 0, s>>>(w->h, PARAM(HSG_W_PFF_B0), (int64_t)R * d, d, 1, w->hpre); TR_CHECK_LAUNCH(c);
+    HSG_CUDA(cudaMemcpyAsync(w->z, w->yv, (size_t)R * d * sizeof(float), cudaMemcpyDeviceToDevice, s));
+    if (LIN_FWD(R, d, d, w->h, d, PARAM(HSG_W_PFF_W1), d, w->z, d, 1.f)) return 1;
+    bias_act_kernel<<<nblk((int64_t)R * d), 256, 0, s>>>(w->z, PARAM(HSG_W_PFF_B1), (int64_t)R * d, d, 0, nullptr); TR_CHECK_LAUNCH(c);
+    // 5. heads                                                                            (Modules.py:752-779)
+    if (ln_fwd(c, s, w->z, R, PARAM(HSG_W_LN1_G), PARAM(HSG_W_LN1_B), w->Dn, w->mu_z, w->rs_z)) return 1;
+    if (ln_fwd(c, s, w->sp, R, PARAM(HSG_W_LN2_G), PARAM(HSG_W_LN2_B), w->Sn, w->mu_p, w->rs_p)) return 1;
+    sqdiff_fwd_kernel<<<nblk((int64_t)R * d), 256, 0, s>>>(w->Dn, w->Sn, (int64_t)R * d, w->u); TR_CHECK_LAUNCH(c);
+    if (LIN_FWD(R, hd, d, w->u, d, PARAM(HSG_W_CLS_W0), d, w->cact, hd, 0.f)) return 1;
+    bias_act_kernel<<<nblk((int64_t)R * hd), 256, 0, s>>>(w->cact, PARAM(HSG_W_CLS_B0), (int64_t)R * hd, hd, 1, w->cpre); TR_CHECK_LAUNCH(c);
+    head_out_kernel<<<nblk(R), 256, 0, s>>>(w->cact, R, hd, PARAM(HSG_W_CLS_W1), PARAM(HSG_W_CLS_B1), w->o); TR_CHECK_LAUNCH(c);
+    xp_fwd_kernel<<<nblk(B), 256, 0, s>>>(w->x, B, c->n_chrom + 1, c->cf, c->w[HSG_W_ATTR], c->w[HSG_W_CELL_FEATS], only_model,
+                                          PARAM(HSG_W_XP2_W0), PARAM(HSG_W_XP2_B0), PARAM(HSG_W_XP2_W1), PARAM(HSG_W_XP2_B1), w->hp2, w->dp2);
+    TR_CHECK_LAUNCH(c);
+    pool_kernel<<<nblk(B), 256, 0, s>>>(w->o, w->dp2, B, w->mean); TR_CHECK_LAUNCH(c);
+    // 6. loss (classification: weighted BCE with logits; regression: MSE against the weights)
+    HSG_CUDA(cudaMemsetAsync(w->loss, 0, sizeof(float), s));
+    if (y_host && w_host) {
+        if (loss_mode == 0) bce_kernel<<<nblk(B), 256, 0, s>>>(w->mean, w->y, w->w, B, w->loss, w->dmean);
+        else mse_kernel<<<nblk(B), 256, 0, s>>>(w->mean, w->w, B, w->loss, w->dmean);
+        TR_CHECK_LAUNCH(c);
+    }
+    if (mean_out_host) HSG_CUDA(cudaMemcpyAsync(mean_out_host, w->mean, B * sizeof(float), cudaMemcpyDeviceToHost, s));
+    if (loss_out_host) HSG_CUDA(cudaMemcpyAsync(loss_out_host, w->loss, sizeof(float), cudaMemcpyDeviceToHost, s));
+    if (mean_out_host || loss_out_host) HSG_CUDA(cudaStreamSynchronize(s));
+    return 0;
+}
+
+// backward of the last hsg_score_fwd batch: accumulates into the bound flat gradient buffer (the caller zeroes it)
+extern "C" int hsg_score_bwd(hsg_ctx* c, void* stream) {
+    HSG_CHECK(c && g_ws.count(c) && g_ws[c]->B > 0, "no forward batch to differentiate");
+    HSG_CUDA(cudaSetDevice(c->device));
+    TrainWs* w = g_ws[c];
+    TrainBind* b = bind_of(c);
+    cudaStream_t s = (cudaStream_t)stream;
+    const int d = c->d, hd = d / 2, B = w->B, R = 3 * B, NB = 2 * B, chrom = w->chrom, nc = c->bins[chrom], in_c = b->in_dim[chrom + 1];
+    const int bin_base = c->n_cells + 1 + c->bin_off[chrom];
+    const int64_t nRd = (int64_t)R * d;
+    // heads
+    xp_bwd_kernel<<<nblk(B), 256, 0, s>>>(w->x, B, c->n_chrom + 1, c->cf, c->w[HSG_W_ATTR], c->w[HSG_W_CELL_FEATS], w->only_model,
+                                          PARAM(HSG_W_XP2_W1), w->hp2, w->dmean, GRAD(HSG_W_XP2_W0), GRAD(HSG_W_XP2_B0),
+                                          GRAD(HSG_W_XP2_W1), GRAD(HSG_W_XP2_B1));
+    TR_CHECK_LAUNCH(c);
+    head_bwd_kernel<<<nblk(R), 256, (hd + 1) * sizeof(float), s>>>(w->dmean, w->cact, R, hd, PARAM(HSG_W_CLS_W1), w->dc, GRAD(HSG_W_CLS_W1),
+                                                                   GRAD(HSG_W_CLS_B1));
+    TR_CHECK_LAUNCH(c);
+    dswish_kernel<<<nblk((int64_t)R * hd), 256, 0, s>>>(w->dc, w->cpre, (int64_t)R * hd); TR_CHECK_LAUNCH(c);
+    colsum_kernel<<<dim3((hd + 63) / 64, 32), 64, 0, s>>>(w->dc, R, hd, GRAD(HSG_W_CLS_B0)); TR_CHECK_LAUNCH(c);
+    if (LIN_DW(R, hd, d, w->dc, hd, w->u, d, GRAD(HSG_W_CLS_W0), d)) return 1;
+    if (LIN_DX(R, hd, d, w->dc, hd, PARAM(HSG_W_CLS_W0), d, w->du, d, 0.f)) return 1;
+    HSG_CUDA(cudaMemsetAsync(w->dS, 0, nRd * sizeof(float), s));
+    sqdiff_bwd_kernel<<<nblk(nRd), 256, 0, s>>>(w->Dn, w->Sn, w->du, nRd, w->dD, w->dS); TR_CHECK_LAUNCH(c);
+    if (ln_bwd(c, s, w->dD, w->z, R, PARAM(HSG_W_LN1_G), w->mu_z, w->rs_z, w->dz, 0, GRAD(HSG_W_LN1_G), GRAD(HSG_W_LN1_B))) return 1;
+    if (ln_bwd(c, s, w->dS, w->sp, R, PARAM(HSG_W_LN2_G), w->mu_p, w->rs_p, w->dsp, 0, GRAD(HSG_W_LN2_G), GRAD(HSG_W_LN2_B))) return 1;
+    // pff_n1:  z = y + W1 h + b1 ; h = swish(W0 xn + b0) ; xn = LN(y)
+    colsum_kernel<<<dim3((d + 63) / 64, 32), 64, 0, s>>>(w->dz, R, d, GRAD(HSG_W_PFF_B1)); TR_CHECK_LAUNCH(c);
+    if (LIN_DW(R, d, d, w->dz, d, w->h, d, GRAD(HSG_W_PFF_W1), d)) return 1;
+    if (LIN_DX(R, d, d, w->dz, d, PARAM(HSG_W_PFF_W1), d, w->dh, d, 0.f)) return 1;
+    dswish_kernel<<<nblk(nRd), 256, 0, s>>>(w->dh, w->hpre, nRd); TR_CHECK_LAUNCH(c);
+    colsum_kernel<<<dim3((d + 63) / 64, 32), 64, 0, s>>>(w->dh, R, d, GRAD(HSG_W_PFF_B0)); TR_CHECK_LAUNCH(c);
+    if (LIN_DW(R, d, d, w->dh, d, w->xn, d, GRAD(HSG_W_PFF_W0), d)) return 1;
+    if (LIN_DX(R, d, d, w->dh, d, PARAM(HSG_W_PFF_W0), d, w->dxn, d, 0.f)) return 1;
+    HSG_CUDA(cudaMemcpyAsync(w->dy, w->dz, nRd * sizeof(float), cudaMemcpyDeviceToDevice, s));      // residual branch
+    if (ln_bwd(c, s, w->dxn, w->yv, R, PARAM(HSG_W_PFF_LN_G), w->mu_y, w->rs_y, w->dy, 1, GRAD(HSG_W_PFF_LN_G), GRAD(HSG_W_PFF_LN_B))) return 1;
+    // attention outputs:  y = fc1 ctx ; sp = fc2 V
+    if (LIN_DW(R, d, HSG_HD, w->dy, d, w->ctx, HSG_HD, GRAD(HSG_W_FC1), HSG_HD)) return 1;
+    if (LIN_DX(R, d, HSG_HD, w->dy, d, PARAM(HSG_W_FC1), HSG_HD, w->dctx, HSG_HD, 0.f)) return 1;
+    if (LIN_DW(R, d, HSG_HD, w->dsp, d, w->V, HSG_HD, GRAD(HSG_W_FC2), HSG_HD)) return 1;
+    attn_bwd_kernel<<<nblk(B * 8, 128), 128, 0, s>>>(w->Q, w->K, w->V, w->P, w->dctx, B, w->dQ, w->dK, w->dV); TR_CHECK_LAUNCH(c);
+    if (LIN_DX(R, d, HSG_HD, w->dsp, d, PARAM(HSG_W_FC2), HSG_HD, w->dV, HSG_HD, 1.f)) return 1;
+    if (LIN_DW(R, HSG_HD, d, w->dQ, HSG_HD, w->qin, d, GRAD(HSG_W_QS), d)) return 1;
+    if (LIN_DW(R, HSG_HD, d, w->dK, HSG_HD, w->kin, d, GRAD(HSG_W_KS), d)) return 1;
+    if (LIN_DW(R, HSG_HD, d, w->dV, HSG_HD, w->vin, d, GRAD(HSG_W_VS), d)) return 1;
+    if (LIN_DX(R, HSG_HD, d, w->dQ, HSG_HD, PARAM(HSG_W_QS), d, w->dqin, d, 0.f)) return 1;
+    if (LIN_DX(R, HSG_HD, d, w->dK, HSG_HD, PARAM(HSG_W_KS), d, w->dkin, d, 0.f)) return 1;
+    if (LIN_DX(R, HSG_HD, d, w->dV, HSG_HD, PARAM(HSG_W_VS), d, w->dvin, d, 0.f)) return 1;
+    if (ln_bwd(c, s, w->dqin, w->dyn, R, PARAM(HSG_W_ALN1_G), w->mu_d, w->rs_d, w->ddyn, 0, GRAD(HSG_W_ALN1_G), GRAD(HSG_W_ALN1_B))) return 1;
+    if (ln_bwd(c, s, w->dkin, w->dyn, R, PARAM(HSG_W_ALN2_G), w->mu_d, w->rs_d, w->ddyn, 1, GRAD(HSG_W_ALN2_G), GRAD(HSG_W_ALN2_B))) return 1;
+    if (ln_bwd(c, s, w->dvin, w->sta, R, PARAM(HSG_W_ALN3_G), w->mu_s, w->rs_s, w->dsta, 0, GRAD(HSG_W_ALN3_G), GRAD(HSG_W_ALN3_B))) return 1;
+    // node embedding
+    HSG_CUDA(cudaMemsetAsync(w->dEall, 0, (size_t)nc * d * sizeof(float), s));
+    disassemble_kernel<<<nblk(nRd), 256, 0, s>>>(w->x, B, d, bin_base, w->ddyn, w->dsta, w->stage == 2 ? w->dcomb : nullptr, w->dEall);
+    TR_CHECK_LAUNCH(c);
+    if (w->stage == 2) {
+        const int64_t nNd = (int64_t)NB * d;
+        dswish_kernel<<<nblk(nNd), 256, 0, s>>>(w->dcomb, w->combpre, nNd); TR_CHECK_LAUNCH(c);
+        colsum_kernel<<<dim3((d + 63) / 64, 32), 64, 0, s>>>(w->dcomb, NB, d, GRAD(HSG_W_SAGE_B)); TR_CHECK_LAUNCH(c);
+        float* dG = GRAD(HSG_W_SAGE_W); const float* G = PARAM(HSG_W_SAGE_W);
+        if (LIN_DW(NB, d, d, w->dcomb, d, w->neigh, d, dG, 2 * d)) return 1;
+        if (LIN_DW(NB, d, d, w->dcomb, d, w->selfb, d, dG + d, 2 * d)) return 1;
+        if (LIN_DX(NB, d, d, w->dcomb, d, G, 2 * d, w->dneigh, d, 0.f)) return 1;
+        if (LIN_DX(NB, d, d, w->dcomb, d, G + d, 2 * d, w->dself, d, 0.f)) return 1;
+        scatter_rows_kernel<<<nblk(nNd), 256, 0, s>>>(w->x, B, d, bin_base, w->dself, w->dEall); TR_CHECK_LAUNCH(c);
+        if (d == 64) spmm_bwd_kernel<64><<<(NB + 7) / 8, 256, 0, s>>>(w->indptr, w->cols, w->vals, w->dneigh, NB, w->dEall);
+        else spmm_bwd_kernel<128><<<(NB + 7) / 8, 256, 0, s>>>(w->indptr, w->cols, w->vals, w->dneigh, NB, w->dEall);
+        TR_CHECK_LAUNCH(c);
+    }
+    // E = swish(X W^T + b)
+    dswish_kernel<<<nblk((int64_t)nc * d), 256, 0, s>>>(w->dEall, w->Epre, (int64_t)nc * d); TR_CHECK_LAUNCH(c);
+    colsum_kernel<<<dim3((d + 63) / 64, 32), 64, 0, s>>>(w->dEall, nc, d, b->grads + b->off_pb[chrom + 1]); TR_CHECK_LAUNCH(c);
+    if (LIN_DW(nc, d, in_c, w->dEall, d, b->feat[chrom + 1], in_c, b->grads + b->off_pw[chrom + 1], in_c)) return 1;
+    return 0;
+}

@@ -1,0 +1,140 @@
+"""Host driver of the training-side kernels (hsg_score_fwd / hsg_score_bwd).
+
+Parameters and gradients live in two flat CUDA tensors; `named_params()` / `named_grads()` hand out views under the
+reference's state_dict names, so `torch.optim.Adam` can run on the views and ONE `torch.distributed.all_reduce`
+on `self.grads` is the whole data-parallel exchange (Higashi_wrapper.py:1006-1010 is where it slots in)."""
+from __future__ import annotations
+
+import ctypes as C
+from typing import Dict, Optional, Sequence
+
+import numpy as np
+import torch
+
+from . import _lib
+
+LOSS_CLASSIFICATION, LOSS_REGRESSION = 0, 1
+_FROZEN = {"W_ATTR", "W_CELL_FEATS"}
+
+
+def _np(t):
+    if hasattr(t, "detach"):
+        t = t.detach().cpu().numpy()
+    return np.asarray(t)
+
+
+def neighbors_to_csr(to_neighs, n_rows: int, bin_base: int):
+    """to_neighs_to_mask output (indices [2,nnz], values [nnz], unique_nodes [U]; Higashi_wrapper.py:171-221) ->
+    CSR over the bin-token rows with chromosome-local columns."""
+    ind, val, uniq = [_np(t) for t in to_neighs]
+    rows = ind[0].astype(np.int64)
+    if len(rows) > 1 and np.any(np.diff(rows) < 0):
+        order = np.argsort(rows, kind="stable")
+        rows, ind, val = rows[order], ind[:, order], val[order]
+    indptr = np.zeros(n_rows + 1, dtype=np.int32)
+    np.cumsum(np.bincount(rows, minlength=n_rows), out=indptr[1:])
+    cols = (uniq[ind[1]] - bin_base).astype(np.int32)
+    return indptr, np.ascontiguousarray(cols), np.ascontiguousarray(val, dtype=np.float32)
+
+
+class TrainEngine:
+    def __init__(self, sd: Dict[str, object], num: Sequence[int], feats: list, cell_feats, device: int = 0,
+                 cell_table=None, embed_prefix: str = "encode1.static_nn"):
+        self.ctx = _lib.Context(device)
+        self.device = torch.device("cuda", device)
+        self.num = [int(v) for v in num]
+        self.num_list = np.cumsum(self.num)
+        self.d = int(_np(sd["layer_norm1.weight"]).shape[0])
+        n_chrom = len(self.num) - 1
+        self.ctx.set_dims(self.d, self.num[0], self.num[1:], int(_np(cell_feats).shape[-1]))
+        self.ctx.set_weight("W_ATTR", _np(sd["attribute_dict_embedding.weight"]).astype(np.float32))
+        self.ctx.set_weight("W_CELL_FEATS", _np(cell_feats).astype(np.float32))
+        # frozen cell table (stage >= 2: off_hook([0]), Higashi_wrapper.py:1384)
+        if cell_table is not None:
+            self.ctx.set_table(0, _np(cell_table).astype(np.float32))
+        else:
+            self.ctx.embed_table(0, _np(feats[0]), _np(sd["%s.wstack.0.weight_list.0" % embed_prefix]),
+                                 _np(sd["%s.wstack.0.bias_list.0" % embed_prefix]))
+        # flat layout: weight slots in enum order, then per-branch projections
+        self.layout = {}
+        off = 0
+        off_slot = np.full(len(_lib.WEIGHT_SLOTS), -1, dtype=np.int64)
+        key_of_slot = {v: k for k, v in _lib.STATE_KEYS.items()}
+        for i, slot in enumerate(_lib.WEIGHT_SLOTS):
+            key = key_of_slot.get(slot)
+            if slot in _FROZEN or key is None or key not in sd:
+                continue
+            shape = tuple(_np(sd[key]).shape)
+            n = int(np.prod(shape))
+            self.layout[key] = (off, shape)
+            off_slot[i] = off
+            off += (n + 3) & ~3
+        off_pw = np.full(n_chrom + 1, -1, dtype=np.int64)
+        off_pb = np.full(n_chrom + 1, -1, dtype=np.int64)
+        for b in range(n_chrom + 1):
+            for which, arr in (("weight_list", off_pw), ("bias_list", off_pb)):
+                key = "%s.wstack.%d.%s.0" % (embed_prefix, b, which)
+                shape = tuple(_np(sd[key]).shape)
+                self.layout[key] = (off, shape)
+                arr[b] = off
+                off += (int(np.prod(shape)) + 3) & ~3
+        self.total = off
+        self.params = torch.zeros(self.total, dtype=torch.float32, device=self.device)
+        self.grads = torch.zeros(self.total, dtype=torch.float32, device=self.device)
+        for key, (o, shape) in self.layout.items():
+            n = int(np.prod(shape))
+            self.params[o:o + n] = torch.from_numpy(_np(sd[key]).astype(np.float32).reshape(-1)).to(self.device)
+        for b in range(1, n_chrom + 1):
+            f = np.ascontiguousarray(_np(feats[b]), dtype=np.float32)
+            self.ctx._check(self.ctx.lib.hsg_train_set_features(self.ctx.h, b, f.ctypes.data_as(C.POINTER(C.c_float)), f.shape[0], f.shape[1]))
+        i64p = lambda a: a.ctypes.data_as(C.POINTER(C.c_int64))
+        self._offs = (off_slot, off_pw, off_pb)
+        self.ctx._check(self.ctx.lib.hsg_train_bind(self.ctx.h, C.c_void_p(self.params.data_ptr()), C.c_void_p(self.grads.data_ptr()),
+                                                    self.total, i64p(off_slot), i64p(off_pw), i64p(off_pb)))
+
+    def close(self):
+        self.ctx.close()
+
+    def named_params(self):
+        return {k: self.params[o:o + int(np.prod(s))].view(s) for k, (o, s) in self.layout.items()}
+
+    def named_grads(self):
+        return {k: self.grads[o:o + int(np.prod(s))].view(s) for k, (o, s) in self.layout.items()}
+
+    def zero_grad(self):
+        self.grads.zero_()
+
+    def forward(self, x, chrom: int, to_neighs=None, y=None, w=None, stage: int = 2, loss_mode: int = LOSS_CLASSIFICATION,
+                only_model: bool = False, want_outputs: bool = True):
+        """One minibatch of ONE chromosome (DataGenerator.next_iter draws one chromosome per batch, Modules.py:1205).
+        Returns (mean float32 [B] or None, loss float or None)."""
+        x = np.ascontiguousarray(_np(x), dtype=np.int64)
+        B = x.shape[0]
+        bin_base = int(self.num_list[chrom]) + 1
+        p = lambda a, t: None if a is None else a.ctypes.data_as(C.POINTER(t))
+        indptr = cols = vals = None
+        nnz = 0
+        if stage == 2:
+            indptr, cols, vals = neighbors_to_csr(to_neighs, 2 * B, bin_base)
+            nnz = int(len(cols))
+        yv = None if y is None else np.ascontiguousarray(_np(y), dtype=np.float32).reshape(-1)
+        wv = None if w is None else np.ascontiguousarray(_np(w), dtype=np.float32).reshape(-1)
+        mean = np.empty(B, dtype=np.float32) if want_outputs else None
+        loss = np.zeros(1, dtype=np.float32) if (want_outputs and y is not None) else None
+        stream = torch.cuda.current_stream(self.device).cuda_stream
+        self.ctx._check(self.ctx.lib.hsg_score_fwd(self.ctx.h, int(stage), int(chrom), p(x, C.c_int64), B, p(indptr, C.c_int32),
+                                                   p(cols, C.c_int32), p(vals, C.c_float), nnz, p(yv, C.c_float), p(wv, C.c_float),
+                                                   int(loss_mode), 1 if only_model else 0, p(mean, C.c_float), p(loss, C.c_float),
+                                                   C.c_void_p(stream)))
+        return mean, (None if loss is None else float(loss[0]))
+
+    def backward(self):
+        stream = torch.cuda.current_stream(self.device).cuda_stream
+        self.ctx._check(self.ctx.lib.hsg_score_bwd(self.ctx.h, C.c_void_p(stream)))
+
+    def allreduce_grads(self):
+        """The ONE collective of data-parallel training: sum over ranks, then mean (Adam then steps identically)."""
+        import torch.distributed as dist
+        if dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1:
+            dist.all_reduce(self.grads, op=dist.ReduceOp.SUM)
+            self.grads.div_(dist.get_world_size())

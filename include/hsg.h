@@ -130,6 +130,29 @@ int  hsg_fix_cell(hsg_ctx* ctx, int cell_1based, void* stream);
  * (cell+1, bin_i, bin_j); out dev float [B] = act(mean head).                                       */
 int  hsg_score_triplets(hsg_ctx* ctx, const int64_t* x_dev, int64_t B, float* out_dev, void* stream);
 
+/* ---- training (hyperedge minibatches) --------------------------------------------------------
+ * Parameters and gradients live in two flat fp32 device buffers owned by the caller (the host mirror makes its
+ * nn.Parameters views of `params`, runs torch.optim.Adam on them and all-reduces `grads` with NCCL in one call).
+ * off_slot[HSG_W_COUNT]: element offset of each weight slot inside the flat buffers (-1 = not trainable / not bound);
+ * off_proj_w / off_proj_b [n_chrom+1]: offsets of MultipleEmbedding.wstack.{i}.weight_list.0 [d,in_i] / bias_list.0 [d].
+ * replaces: optimizer parameter registration + .to(device) (Higashi_wrapper.py:1426-1427)                              */
+int  hsg_train_bind(hsg_ctx* ctx, float* params_dev, float* grads_dev, int64_t total, const int64_t* off_slot,
+                    const int64_t* off_proj_w, const int64_t* off_proj_b);
+/* raw node features of one branch (SparseEmbedding.embedding, Modules.py:101-142): x host [rows,in_dim] */
+int  hsg_train_set_features(hsg_ctx* ctx, int branch, const float* x_host, int64_t rows, int in_dim);
+/* replaces: Hyper_SAGNN.forward (Modules.py:726-783) for one minibatch of one chromosome + the loss head of
+ * Higashi.forward_batch_hyperedge (Higashi_wrapper.py:861-913).  stage 1 = MultipleEmbedding for all tokens,
+ * stage 2 = GraphSageEncoder_with_weights.forward_on_hook (Modules.py:1485-1553) with the neighbour lists of
+ * to_neighs_to_mask (Higashi_wrapper.py:171-221) given as CSR over the 2B bin-token rows (indptr [2B+1], cols = LOCAL bin
+ * of the chromosome, vals = normalised weights).  x host int64 [B,3] node ids; y, w host float [B] (NULL = no loss).
+ * loss_mode 0 = classification (weighted BCE with logits), 1 = regression (MSE against w).  Eval-mode semantics
+ * (dropout off).  mean_out / loss_out: host outputs (may be NULL).                                                  */
+int  hsg_score_fwd(hsg_ctx* ctx, int stage, int chrom, const int64_t* x_host, int B, const int32_t* indptr_host,
+                   const int32_t* cols_local_host, const float* vals_host, int nnz, const float* y_host, const float* w_host,
+                   int loss_mode, int only_model, float* mean_out_host, float* loss_out_host, void* stream);
+/* replaces: loss.backward() (Higashi_wrapper.py:1006) for the batch of the last hsg_score_fwd: ACCUMULATES into grads */
+int  hsg_score_bwd(hsg_ctx* ctx, void* stream);
+
 /* ---- introspection ------------------------------------------------------------------------ */
 /* number of kernels this library launched since the context was created (bench.py gpu_launches) */
 int64_t hsg_launch_count(hsg_ctx* ctx);

@@ -450,6 +450,11 @@ def golden_grads():
         if prm.grad is not None:
             out["grad/" + name] = prm.grad.detach().numpy()
         seen.add(name)
+    # the shared MultipleEmbedding parameters are first registered under encode1.dynamic_nn.features.*;
+    # store their gradients under the canonical encode1.static_nn.* names
+    for name, prm in model.encode1.static_nn.named_parameters():
+        if prm.grad is not None:
+            out["grad/encode1.static_nn." + name] = prm.grad.detach().numpy()
     out.update(state_arrays(model))
     np.savez_compressed(os.path.join(HERE, "grads_d64.npz"), **out)
     print("grads_d64.npz loss", loss.item(), "n grads", sum(k.startswith("grad/") for k in out))
