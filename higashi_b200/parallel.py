@@ -71,3 +71,62 @@ def impute_multi_gpu(config_path, model_path, name, mode, n_cells, sparse_path, 
     if impute_list is not None and temp_dir is not None:
         link_parts(name, shards, temp_dir, impute_list, normalise)
     return shards
+
+
+# ----------------------------------------------------------------------------------------------------- training (DP)
+def reduce_gradients(flat_grads, presence):
+    """The single exchange step of data-parallel training.
+
+    flat_grads: 1-D tensor (fixed layout, zeros where a rank produced no gradient); presence: 1-D tensor with one entry
+    per parameter tensor (1 = this rank produced a gradient).  Every rank gets the MEAN gradient over the ranks and the
+    OR of the presence flags -- parameters no rank touched keep `grad = None`, exactly like the reference's single-GPU
+    run where e.g. only the batch chromosome's projection receives a gradient (torch Adam skips grad=None)."""
+    import torch
+    import torch.distributed as dist
+    if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size() == 1:
+        return flat_grads, presence
+    world = dist.get_world_size()
+    dist.all_reduce(flat_grads, op=dist.ReduceOp.SUM)            # NCCL over NVLink on the GPUs, gloo in the CPU tests
+    flat_grads.div_(world)
+    dist.all_reduce(presence, op=dist.ReduceOp.MAX)
+    return flat_grads, presence
+
+
+class DataParallelTrainer:
+    """train_epoch body (Higashi_wrapper.py:916-1010) for stage 2/3 on the CUDA training kernels, data-parallel:
+    every rank draws its own minibatch, forward + backward locally, ONE allreduce of the flat gradient, identical Adam
+    step on every rank."""
+
+    def __init__(self, engine, lr=1e-3):
+        import torch
+        self.eng = engine
+        self.names = list(engine.layout.keys())
+        self.params = [torch.nn.Parameter(v) for v in engine.named_params().values()]
+        self.grad_views = list(engine.named_grads().values())
+        self.opt = torch.optim.Adam(self.params, lr=lr)
+        self.presence = torch.zeros(len(self.names), dtype=torch.float32, device=engine.grads.device)
+
+    def _local_presence(self, chrom, stage):
+        self.presence.zero_()
+        for i, n in enumerate(self.names):
+            if ".wstack." in n:
+                b = int(n.split(".wstack.")[1].split(".")[0])
+                on = (b == chrom + 1) or (b == 0 and stage == 1 and False)
+            else:
+                on = not (n.startswith("pff_classifier_var") or n.startswith("pff_classifier_proba") or
+                          n.startswith("extra_proba.") or n.startswith("extra_proba3") or
+                          (stage == 1 and n.startswith("encode1.dynamic_nn.nn")))
+            if on:
+                self.presence[i] = 1.0
+
+    def step(self, x, chrom, to_neighs, y, w, stage=2, loss_mode=0):
+        self.eng.zero_grad()
+        _, loss = self.eng.forward(x, chrom, to_neighs, y=y, w=w, stage=stage, loss_mode=loss_mode)
+        self.eng.backward()
+        self._local_presence(chrom, stage)
+        reduce_gradients(self.eng.grads, self.presence)
+        pres = self.presence.cpu().numpy()
+        for p, g, on in zip(self.params, self.grad_views, pres):
+            p.grad = g if on > 0 else None
+        self.opt.step()
+        return loss

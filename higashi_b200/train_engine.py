@@ -115,7 +115,10 @@ class TrainEngine:
         indptr = cols = vals = None
         nnz = 0
         if stage == 2:
-            indptr, cols, vals = neighbors_to_csr(to_neighs, 2 * B, bin_base)
+            if isinstance(to_neighs, tuple) and len(to_neighs) == 3 and _np(to_neighs[0]).ndim == 1:
+                indptr, cols, vals = to_neighs                       # already CSR (batches.neighbor_csr)
+            else:
+                indptr, cols, vals = neighbors_to_csr(to_neighs, 2 * B, bin_base)
             nnz = int(len(cols))
         yv = None if y is None else np.ascontiguousarray(_np(y), dtype=np.float32).reshape(-1)
         wv = None if w is None else np.ascontiguousarray(_np(w), dtype=np.float32).reshape(-1)

@@ -88,3 +88,18 @@ def test_adam_step_on_flat_views_reduces_loss():
         opt.step()
     assert losses[-1] < losses[0] - 1e-3, losses
     eng.close()
+
+
+def test_data_parallel_two_gpus():
+    """NCCL path: scripts/dp_train_check.py under torchrun on 2 GPUs (skipped on a 1-GPU box; the exchange step itself is
+    covered on CPU by tests/test_parallel_cpu.py::test_two_rank_gradient_exchange)."""
+    import os
+    import subprocess
+    import sys
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    out = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr",
+                          "127.0.0.1", "--master-port", "29577", os.path.join(root, "scripts", "dp_train_check.py")],
+                         capture_output=True, text=True, timeout=600)
+    assert out.returncode == 0 and "DP_TRAIN_OK world=2" in out.stdout, out.stdout[-2000:] + out.stderr[-2000:]

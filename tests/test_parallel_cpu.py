@@ -50,3 +50,29 @@ def test_two_rank_gloo_shard_and_link(tmp_path):
         v = (np.arange(7) + 1 + cell).astype(np.float32)
         np.testing.assert_allclose(f["cell_%d" % cell], v / v.mean(), rtol=1e-6)      # utils.py:234
     assert not [p for p in os.listdir(tmp_path) if "_part_" in p]
+
+
+# ----------------------------------------------------------------------------------------- training exchange step (gloo)
+def _grad_worker(rank, world, port, ret):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    # 3 parameter tensors of 4 values; rank 0 touches tensors 0 and 1, rank 1 touches 0 and 2 -> nobody skips 0,
+    flat = torch.zeros(12)
+    pres = torch.zeros(3)
+    if rank == 0:
+        flat[0:4] = 1.0; flat[4:8] = 2.0; pres[0] = 1; pres[1] = 1
+    else:
+        flat[0:4] = 3.0; pres[0] = 1
+    parallel.reduce_gradients(flat, pres)
+    if rank == 0:
+        ret["flat"] = flat.tolist(); ret["pres"] = pres.tolist()
+    dist.destroy_process_group()
+
+
+def test_two_rank_gradient_exchange():
+    world, port = 2, 31500 + (os.getpid() % 2000)
+    mgr = mp.Manager()
+    ret = mgr.dict()
+    mp.spawn(_grad_worker, args=(world, port, ret), nprocs=world, join=True)
+    assert ret["flat"] == [2.0] * 4 + [1.0] * 4 + [0.0] * 4         # mean over ranks, zeros where absent
+    assert ret["pres"] == [1.0, 1.0, 0.0]                            # tensor 2: no rank had a gradient -> grad stays None
