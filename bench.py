@@ -232,7 +232,8 @@ def main():
     eng.load_model(sd, ds.num, feats=feats, cell_feats=ds.cell_feats)
     chroms = list(range(len(ds.bins)))
     P = eng.set_pairs(chroms, ds.min_bin, ds.max_bin)
-    precision = {"fp32": E.PREC_FP32, "bf16": E.PREC_BF16, "auto": getattr(E, "DEFAULT_PRECISION", E.PREC_FP32)}[args.precision]
+    precision = {"fp32": E.PREC_FP32, "bf16": E.PREC_BF16, "tc16": E.PREC_TC16, "hi": E.PREC_TC16_HI,
+                 "auto": getattr(E, "DEFAULT_PRECISION", E.PREC_FP32)}[args.precision]
     # pinned host copies of the inputs (for the e2e leg) -- the engine keeps its own device copy
     pin = lambda a: torch.from_numpy(np.ascontiguousarray(a)).pin_memory()
     h_rowptr, h_col, h_val = pin(ds.csr.row_ptr), pin(ds.csr.col), pin(ds.csr.val)
@@ -334,7 +335,7 @@ def main():
         line = {"metric": "imputed (cell,bin_i,bin_j) triplets/s", "value": value, "unit": "triplets/s", "n_gpus": world,
                 "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_all / args.steps, "higher_is_better": True,
                 "scaling": "weak", "vs_baseline": None,
-                "dtype": "bf16" if precision == E.PREC_BF16 else "f32", "data": "synthetic",
+                "dtype": "f32" if precision == E.PREC_FP32 else "f16 operands / f32 accumulate (tcgen05 kind::f16)", "data": "synthetic",
                 "config": {"workload": "%s: synthetic %d cells x %d bins (%d chromosomes), P=%d pairs/cell, k=%d, d_model=%d, "
                                        "impute_with_nbr" % (args.workload, ds.n_cells, sum(ds.bins), len(ds.bins), P, ds.k, ds.d),
                            "cells_per_step": cps, "triplets_per_step": cps * P, "sharding": "cell range per rank, no collective",

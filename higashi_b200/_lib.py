@@ -63,6 +63,7 @@ STATE_KEYS = {
 
 PREC_FP32, PREC_TC16 = 0, 1
 PREC_BF16 = PREC_TC16   # historical alias
+PREC_TC16_HI = 2
 ACT_NONE, ACT_SIGMOID, ACT_SOFTPLUS = 0, 1, 2
 
 # every symbol include/hsg.h declares (tests check that the library exports all of them)

@@ -400,7 +400,7 @@ static int upload_transposed(float** dst, const std::vector<float>& src, int row
 extern "C" int hsg_prepare(hsg_ctx* c, int precision, int local_transfer_range, int activation) {
     CTX_GUARD(c);
     HSG_CHECK(c->d > 0, "call hsg_set_dims first");
-    HSG_CHECK(precision == HSG_PREC_FP32 || precision == HSG_PREC_TC16, "unknown precision");
+    HSG_CHECK(precision == HSG_PREC_FP32 || precision == HSG_PREC_TC16 || precision == HSG_PREC_TC16_HI, "unknown precision");
     HSG_CHECK(local_transfer_range >= 0 && local_transfer_range <= 8, "local_transfer_range out of range");
     HSG_CHECK(activation >= HSG_ACT_NONE && activation <= HSG_ACT_SOFTPLUS, "unknown activation");
     static const int needed[] = {HSG_W_QS, HSG_W_KS, HSG_W_VS, HSG_W_FC1, HSG_W_FC2, HSG_W_ALN1_G, HSG_W_ALN1_B, HSG_W_ALN2_G,
@@ -435,10 +435,10 @@ extern "C" int hsg_prepare(hsg_ctx* c, int precision, int local_transfer_range, 
     // pair bias
     if (dev_alloc(&c->pair_bias, (size_t)std::max<int64_t>(c->P, 1))) return 1;
     if (launch_pair_bias(c, c->stream)) return 1;
-    // Tensor-core mode is used where it is proven to hold the 1e-3 score bar with margin: d_model = 64 and the
-    // sigmoid head (max |err| 2.4e-4).  softplus / raw heads pass the logit error through with slope ~1
-    // (measured 1.06e-3), and d_model = 128 has no tcgen05 variant yet: both keep the fp32 kernels.
-    c->use_umma = (precision == HSG_PREC_TC16 && d == 64 && activation == HSG_ACT_SIGMOID);
+    // Tensor-core mode exists for d_model = 64; d_model = 128 keeps the (more precise) fp32 kernels for now.
+    c->use_umma = (precision != HSG_PREC_FP32 && d == 64);
+    // softplus / raw heads pass the logit error through with slope ~1: they get the high-accuracy variant
+    c->umma_hi = c->use_umma && (precision == HSG_PREC_TC16_HI || activation != HSG_ACT_SIGMOID);
     size_t per_cell;
     if (c->use_umma) {
         std::vector<unsigned char> wimg(umma_wimg_bytes());
@@ -459,7 +459,7 @@ extern "C" int hsg_prepare(hsg_ctx* c, int precision, int local_transfer_range, 
         c->binV16 = bv; c->cellV16 = cv;
         if (launch_convert_static(c, c->binV, c->binS, c->n_bins, c->binV16, c->binSb, c->stream)) return 1;
         if (launch_convert_static(c, c->cellV, c->cellS, c->n_cells, c->cellV16, c->cellSb, c->stream)) return 1;
-        per_cell = (size_t)c->n_bins * (2 * HSG_HD * sizeof(__half) + 16 * sizeof(float) + d * sizeof(float));
+        per_cell = (size_t)c->n_bins * ((c->umma_hi ? 2 * HSG_HD * sizeof(float) : 2 * HSG_HD * sizeof(__half)) + 16 * sizeof(float) + d * sizeof(float));
     } else {
         per_cell = (size_t)c->n_bins * (2 * HSG_HD + d) * sizeof(float);
     }
@@ -469,8 +469,9 @@ extern "C" int hsg_prepare(hsg_ctx* c, int precision, int local_transfer_range, 
     if (dev_alloc(&c->neigh, (size_t)batch * c->n_bins * d)) return 1;
     if (c->use_umma) {
         __half* qk16 = nullptr;
-        if (dev_alloc(&qk16, (size_t)batch * c->n_bins * 2 * HSG_HD) || dev_alloc(&c->XS, (size_t)batch * c->n_bins * 16) ||
-            dev_alloc(&c->QK, (size_t)c->n_bins * 2 * HSG_HD)) return 1;
+        if (dev_alloc(&qk16, c->umma_hi ? (size_t)1 : (size_t)batch * c->n_bins * 2 * HSG_HD) ||
+            dev_alloc(&c->XS, (size_t)batch * c->n_bins * 16) ||
+            dev_alloc(&c->QK, (size_t)(c->umma_hi ? batch : 1) * c->n_bins * 2 * HSG_HD)) return 1;
         c->QK16 = qk16;
     } else {
         if (dev_alloc(&c->QK, (size_t)batch * c->n_bins * 2 * HSG_HD)) return 1;
@@ -485,7 +486,7 @@ static int run_batch(hsg_ctx* c, int cell0, int nb, float* out, cudaStream_t s, 
     if (prof) HSG_CUDA(cudaEventRecord(c->ev[0], s));
     if (launch_gather(c, nullptr, cell0, nb, s)) return 1;
     if (prof) HSG_CUDA(cudaEventRecord(c->ev[1], s));
-    if (launch_token_project(c, cell0, nb, c->use_umma, s)) return 1;
+    if (launch_token_project(c, cell0, nb, c->use_umma ? (c->umma_hi ? 2 : 1) : 0, s)) return 1;
     if (prof) HSG_CUDA(cudaEventRecord(c->ev[2], s));
     if (c->use_umma) { if (launch_score_pairs_umma(c, cell0, nb, out, s)) return 1; }
     else if (launch_score_pairs_f32(c, cell0, nb, out, s)) return 1;
@@ -553,7 +554,7 @@ extern "C" int hsg_fix_cell(hsg_ctx* c, int cell_1based, void* stream) {
     HSG_CHECK(cell_1based >= 1 && cell_1based <= c->n_cells, "cell id out of range");
     cudaStream_t s = (cudaStream_t)stream;
     if (launch_gather(c, nullptr, cell_1based - 1, 1, s)) return 1;
-    if (launch_token_project(c, cell_1based - 1, 1, false, s)) return 1;
+    if (launch_token_project(c, cell_1based - 1, 1, 0, s)) return 1;
     c->fixed_cell = cell_1based - 1;
     return 0;
 }

@@ -92,6 +92,7 @@ struct hsg_ctx {
     void* binV16 = nullptr; float* binSb = nullptr; void* cellV16 = nullptr; float* cellSb = nullptr;
     unsigned char* wimg = nullptr; float* cst = nullptr; float h_cst[512] = {0};
     bool use_umma = false;
+    bool umma_hi = false;                    // high-accuracy tensor-core variant (fp32 tables, hi/lo operand splits)
     int n_sm = 148;
     int fixed_cell = -1;                     // 0-based cell whose tokens sit in QK slot 0 (hsg_fix_cell)
 
@@ -111,7 +112,7 @@ int launch_embed_table(hsg_ctx* c, const float* x, int64_t rows, int in_dim, con
 int launch_static_tokens(hsg_ctx* c, const float* E, int64_t rows, float* Q, float* K, float* V, float* S, cudaStream_t s);
 int launch_pair_bias(hsg_ctx* c, cudaStream_t s);
 int launch_gather(hsg_ctx* c, const int* cells_dev_unused, int cell_start, int n_cells_batch, cudaStream_t s);
-int launch_token_project(hsg_ctx* c, int cell_start, int n_cells_batch, bool out16, cudaStream_t s);
+int launch_token_project(hsg_ctx* c, int cell_start, int n_cells_batch, int mode, cudaStream_t s);   // mode 0: fp32 QK, 1: fp16 QK + XS, 2: fp32 QK + XS
 int launch_score_pairs_umma(hsg_ctx* c, int cell_start, int n_cells_batch, float* out, cudaStream_t s);
 int launch_convert_static(hsg_ctx* c, const float* V, const float* S, long long rows, void* V16, float* Sb, cudaStream_t s);
 int umma_build_weights(const float* fc1, const float* w0, const float* b0, const float* pff_g, const float* pff_b,

@@ -231,7 +231,7 @@ __device__ __forceinline__ void tile_gemm(const float* __restrict__ sA, int K, i
     }
 }
 
-template <int D, bool OUT16>
+template <int D, int MODE>   // MODE 0: fp32 Q/K ; 1: fp16 Q/K + cell cross terms ; 2: fp32 Q/K + cell cross terms
 __global__ void __launch_bounds__(256) token_project_kernel(
     const float* __restrict__ neigh, const float* __restrict__ E_bin, int n_bins, int64_t n_tok,
     const float* __restrict__ sageT, const float* __restrict__ sage_b,
@@ -243,7 +243,8 @@ __global__ void __launch_bounds__(256) token_project_kernel(
     float* xT = sm;                              // [2D][LDA]
     float* dT = xT + 2 * D * TP_LDA;             // [D][LDA]   dyn, then LN1 input
     float* kT = dT + D * TP_LDA;                 // [D][LDA]   LN2 input
-    float* qkT = kT + D * TP_LDA;                // [256][LDA] Q (rows 0..127) and K (rows 128..255), OUT16 only
+    float* qkT = kT + D * TP_LDA;                // [256][LDA] Q (rows 0..127) and K (rows 128..255), MODE != 0 only
+    constexpr bool OUT16 = (MODE == 1);
     const int tid = threadIdx.x;
     const int64_t tok0 = (int64_t)blockIdx.x * TP_TOK;
     // stage [neigh | E_self] transposed
@@ -299,12 +300,13 @@ __global__ void __launch_bounds__(256) token_project_kernel(
         int rg = u % (TP_TOK / 4), cg = u / (TP_TOK / 4);
         float acc[4][4] = {};
         tile_gemm<4>(which ? kT : dT, D, rg * 4, which ? wkT : wqT, HSG_HD, cg * 4, acc);
-        if (OUT16) {
+        if (MODE != 0) {
 #pragma unroll
             for (int q = 0; q < 4; ++q)
                 *reinterpret_cast<float4*>(qkT + (which * HSG_HD + cg * 4 + q) * TP_LDA + rg * 4) =
                     make_float4(acc[0][q], acc[1][q], acc[2][q], acc[3][q]);
-        } else {
+        }
+        if (!OUT16) {
 #pragma unroll
             for (int r = 0; r < 4; ++r) {
                 int64_t tok = tok0 + rg * 4 + r;
@@ -314,10 +316,10 @@ __global__ void __launch_bounds__(256) token_project_kernel(
             }
         }
     }
-    if (OUT16) {
+    if (MODE != 0) {
         __syncthreads();
         // 16-bit rows: thread -> (token, 8-column chunk); lanes walk tokens so the smem reads are conflict-free
-        for (int i = tid; i < TP_TOK * 32; i += 256) {
+        for (int i = tid; OUT16 && i < TP_TOK * 32; i += 256) {
             int tk = i & 31, ch = i >> 5;
             int64_t tok = tok0 + tk;
             if (tok >= n_tok) continue;
@@ -350,13 +352,13 @@ __global__ void __launch_bounds__(256) token_project_kernel(
     }
 }
 
-template <int D, bool OUT16>
+template <int D, int MODE>
 static int launch_tp(hsg_ctx* c, int cell_start, int64_t n_tok, cudaStream_t s) {
     unsigned grid = (unsigned)((n_tok + TP_TOK - 1) / TP_TOK);
     float** w = c->w;
-    size_t smem = (size_t)(4 * D + (OUT16 ? 2 * HSG_HD : 0)) * TP_LDA * sizeof(float);
-    HSG_CUDA(cudaFuncSetAttribute(token_project_kernel<D, OUT16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    token_project_kernel<D, OUT16><<<grid, 256, smem, s>>>(c->neigh, c->E_bin, c->n_bins, n_tok, c->dw.sageT, w[HSG_W_SAGE_B],
+    size_t smem = (size_t)(4 * D + (MODE != 0 ? 2 * HSG_HD : 0)) * TP_LDA * sizeof(float);
+    HSG_CUDA(cudaFuncSetAttribute(token_project_kernel<D, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    token_project_kernel<D, MODE><<<grid, 256, smem, s>>>(c->neigh, c->E_bin, c->n_bins, n_tok, c->dw.sageT, w[HSG_W_SAGE_B],
                                                            w[HSG_W_ALN1_G], w[HSG_W_ALN1_B], w[HSG_W_ALN2_G], w[HSG_W_ALN2_B],
                                                            c->dw.wqT, c->dw.wkT, c->QK, (__half*)c->QK16, c->XS, c->cellQ, c->cellK,
                                                            cell_start);
@@ -365,8 +367,14 @@ static int launch_tp(hsg_ctx* c, int cell_start, int64_t n_tok, cudaStream_t s) 
     return 0;
 }
 
-int launch_token_project(hsg_ctx* c, int cell_start, int n_batch, bool out16, cudaStream_t s) {
+int launch_token_project(hsg_ctx* c, int cell_start, int n_batch, int mode, cudaStream_t s) {
     int64_t n_tok = (int64_t)n_batch * c->n_bins;
-    if (c->d == 64) return out16 ? launch_tp<64, true>(c, cell_start, n_tok, s) : launch_tp<64, false>(c, cell_start, n_tok, s);
-    return out16 ? launch_tp<128, true>(c, cell_start, n_tok, s) : launch_tp<128, false>(c, cell_start, n_tok, s);
+    if (c->d == 64) {
+        if (mode == 1) return launch_tp<64, 1>(c, cell_start, n_tok, s);
+        if (mode == 2) return launch_tp<64, 2>(c, cell_start, n_tok, s);
+        return launch_tp<64, 0>(c, cell_start, n_tok, s);
+    }
+    if (mode == 1) return launch_tp<128, 1>(c, cell_start, n_tok, s);
+    if (mode == 2) return launch_tp<128, 2>(c, cell_start, n_tok, s);
+    return launch_tp<128, 0>(c, cell_start, n_tok, s);
 }

@@ -36,8 +36,10 @@
 #define SM_B_W0 16384         // [64 x 64]
 #define SM_B_W1 24576         // [64 x 64]
 #define SM_B_C0 32768         // [32 x 64]
-#define SM_WIMG_BYTES 36864
-#define SM_A0 36864           // 4 x 32 KB A buffers (one per warpgroup)
+#define SM_B_FC1_LO 36864      // low halves (w - fp16(w)) of fc1 and C0 for the high-accuracy variant
+#define SM_B_C0_LO 53248
+#define SM_WIMG_BYTES 57344
+#define SM_A0 57344           // 4 x 32 KB A buffers (one per warpgroup)
 #define SM_A_BYTES 32768
 #define SM_CONST (SM_A0 + UM_WG * SM_A_BYTES)   // fp32 constants
 #define CST_B0F 0
@@ -138,6 +140,10 @@ struct UmmaParams {
     const __half* binV16;    // [n_bins][128]
     const float* binSb;      // [64][n_bins]   feature-major: layer_norm2(fc2 V) - beta(layer_norm1)
     const __half* cellV16;   // [n_cells][128]
+    // high-accuracy variant: fp32 token tables (Q/K per (cell, bin), V per bin / cell)
+    const float* QK32;       // [slot][n_bins][2][128]
+    const float* binV32;     // [n_bins][128]
+    const float* cellV32;    // [n_cells][128]
     const float* cellSb;     // [64][n_cells]  feature-major
     const unsigned char* wimg;   // SM_WIMG_BYTES pre-swizzled fp16 weight images
     float cst[CST_COUNT];        // fp32 constants, by value: they become constant-bank operands of the epilogue math
@@ -155,26 +161,30 @@ __device__ __forceinline__ void masked_row_fast(float la, float lb, float& wa, f
     wa = ea * inv; wb = eb * inv;
 }
 
-// one MMA round trip for a warpgroup: A tile is complete in shared memory
+// NK k-steps of one [128 x N] += A[128 x 16NK] . B[N x 16NK]^T ; A / B tiles in K-major SWIZZLE_128B
 template <int NK, int N>
-__device__ __forceinline__ void issue_gemm(int wg, int wtid, uint32_t a_base, uint32_t b_base, int b_rows, uint32_t d_tmem,
-                                           uint32_t accum_first, uint32_t bar) {
-    fence_async_smem();            // generic-proxy writes of the A tile -> visible to the tensor core (async proxy)
-    tc_fence_before();
-    wg_bar(wg);
-    if (wtid == 0) {
-        tc_fence_after();
-        constexpr uint32_t idesc = umma_idesc_f16(128, N);
+__device__ __forceinline__ void mma_group(uint32_t a_base, uint32_t b_base, int b_rows, uint32_t d_tmem, uint32_t accum_first) {
+    constexpr uint32_t idesc = umma_idesc_f16(128, N);
 #pragma unroll
-        for (int k = 0; k < NK; ++k) {
-            uint32_t aoff = (uint32_t)(k >> 2) * 16384u + (uint32_t)(k & 3) * 32u;
-            uint32_t boff = (uint32_t)(k >> 2) * (uint32_t)(b_rows * 128) + (uint32_t)(k & 3) * 32u;
-            umma_f16(d_tmem, umma_desc(a_base + aoff), umma_desc(b_base + boff), idesc, (k > 0) ? 1u : accum_first);
-        }
-        umma_commit(bar);
+    for (int k = 0; k < NK; ++k) {
+        uint32_t aoff = (uint32_t)(k >> 2) * 16384u + (uint32_t)(k & 3) * 32u;
+        uint32_t boff = (uint32_t)(k >> 2) * (uint32_t)(b_rows * 128) + (uint32_t)(k & 3) * 32u;
+        umma_f16(d_tmem, umma_desc(a_base + aoff), umma_desc(b_base + boff), idesc, (k > 0) ? 1u : accum_first);
     }
 }
+// one MMA round trip for a warpgroup: the A tile is complete in shared memory.  Generic-proxy writes of the A tile are
+// made visible to the tensor core (async proxy), the warpgroup syncs, one thread issues and commits to the mbarrier.
+#define ISSUE_BEGIN() fence_async_smem(); tc_fence_before(); wg_bar(wg); if (wtid == 0) { tc_fence_after();
+#define ISSUE_END() umma_commit(bar_mma); }
+template <int NK, int N>
+__device__ __forceinline__ void issue_gemm(int wg, int wtid, uint32_t a_base, uint32_t b_base, int b_rows, uint32_t d_tmem,
+                                           uint32_t accum_first, uint32_t bar_mma) {
+    ISSUE_BEGIN()
+    mma_group<NK, N>(a_base, b_base, b_rows, d_tmem, accum_first);
+    ISSUE_END()
+}
 
+template <bool HI>
 __global__ void __launch_bounds__(UM_THREADS, 1) score_umma_kernel(UmmaParams p) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int tid = threadIdx.x, wg = tid >> 7, wtid = tid & 127, warp_in_wg = (tid >> 5) & 3, lane = tid & 31;
@@ -228,6 +238,56 @@ __global__ void __launch_bounds__(UM_THREADS, 1) score_umma_kernel(UmmaParams p)
             // Lane mapping for this phase: lane = (row-in-group rho = lane>>3, head h = lane&7); a warp walks its
             // own 32 rows four at a time, so the 8 lanes of a row read one contiguous 256-byte table row
             // (coalesced) instead of every lane streaming through a private row.
+            if constexpr (HI) {
+                // high-accuracy variant: fp32 Q/K/V tables, fp32 dot products and ctx, one fp16 rounding of ctx
+                const int h = lane & 7, rsub = lane >> 3;
+                const int cA = h * 2 + (h >> 2), cB = h * 2 + 1 - (h >> 2);
+                const float4* QK4 = reinterpret_cast<const float4*>(p.QK32);
+                const float4* BV4 = reinterpret_cast<const float4*>(p.binV32);
+                const float4* CV4 = reinterpret_cast<const float4*>(p.cellV32) + (uint32_t)cell * 32u + h * 4;
+                const uint32_t tokbase = (uint32_t)cb * (uint32_t)p.n_bins;
+#pragma unroll 1
+                for (int it = 0; it < 8; ++it) {
+                    const int rw = it * 4 + rsub;
+                    const uint32_t bi_r = (uint32_t)__shfl_sync(0xffffffffu, pr.x, rw), bj_r = (uint32_t)__shfl_sync(0xffffffffu, pr.y, rw);
+                    const uint32_t ti = tokbase + bi_r, tj = tokbase + bj_r;
+                    float la, lb;
+                    const float4 *va, *vb;
+                    if (t == 0) {
+                        la = __ldg(p.XS + ti * 16u + h); lb = __ldg(p.XS + tj * 16u + h);
+                        va = BV4 + bi_r * 32u + h * 4; vb = BV4 + bj_r * 32u + h * 4;
+                    } else {
+                        const uint32_t tq = (t == 1) ? ti : tj, tk = (t == 1) ? tj : ti;
+                        la = __ldg(p.XS + tq * 16u + 8 + h);
+                        const float4* q = QK4 + tq * 64u + h * 4; const float4* k = QK4 + tk * 64u + 32 + h * 4;
+                        float2 acc = make_float2(0.f, 0.f), acc2 = acc;
+#pragma unroll
+                        for (int e = 0; e < 4; ++e) {
+                            float4 qv = __ldg(q + e), kv = __ldg(k + e);
+                            acc = __ffma2_rn(make_float2(qv.x, qv.y), make_float2(kv.x, kv.y), acc);
+                            acc2 = __ffma2_rn(make_float2(qv.z, qv.w), make_float2(kv.z, kv.w), acc2);
+                        }
+                        lb = ((acc.x + acc.y) + (acc2.x + acc2.y)) * 0.25f;
+                        va = CV4; vb = BV4 + ((t == 1) ? bj_r : bi_r) * 32u + h * 4;
+                    }
+                    float wa, wb;
+                    masked_row_fast(la, lb, wa, wb);
+                    const float2 wa2 = make_float2(wa, wa), wb2 = make_float2(wb, wb);
+                    const int arow = warp_in_wg * 32 + rw;
+                    uint32_t pk[8];
+#pragma unroll
+                    for (int e = 0; e < 4; ++e) {
+                        float4 av = __ldg(va + e), bv = __ldg(vb + e);
+                        float2 c0 = __ffma2_rn(wb2, make_float2(bv.x, bv.y), __fmul2_rn(wa2, make_float2(av.x, av.y)));
+                        float2 c1 = __ffma2_rn(wb2, make_float2(bv.z, bv.w), __fmul2_rn(wa2, make_float2(av.z, av.w)));
+                        pk[e * 2] = pack_h2(c0.x, c0.y); pk[e * 2 + 1] = pack_h2(c1.x, c1.y);
+                    }
+                    // chunk order swapped for h >= 4 (bank-conflict-free stores, see the fast variant)
+                    const bool sw = (h & 4) != 0;         // selects, not a branch: all lanes store together
+                    sts128(a_chunk_addr(a_base, arow, cA), sw ? pk[4] : pk[0], sw ? pk[5] : pk[1], sw ? pk[6] : pk[2], sw ? pk[7] : pk[3]);
+                    sts128(a_chunk_addr(a_base, arow, cB), sw ? pk[0] : pk[4], sw ? pk[1] : pk[5], sw ? pk[2] : pk[6], sw ? pk[3] : pk[7]);
+                }
+            } else
             {
                 const int h = lane & 7, rsub = lane >> 3;
                 // each lane owns the two 16-byte chunks of head h; lanes with h >= 4 handle them in swapped order so that
@@ -305,7 +365,14 @@ __global__ void __launch_bounds__(UM_THREADS, 1) score_umma_kernel(UmmaParams p)
                 }
 #endif
             }
-            issue_gemm<8, 64>(wg, wtid, a_base, sbase + SM_B_FC1, 64, t_y, 0u, bar_mma);
+            if constexpr (HI) {
+                ISSUE_BEGIN()
+                mma_group<8, 64>(a_base, sbase + SM_B_FC1, 64, t_y, 0u);
+                mma_group<8, 64>(a_base, sbase + SM_B_FC1_LO, 64, t_y, 1u);        // + ctx . (fc1 - fp16(fc1))^T
+                ISSUE_END()
+            } else {
+                issue_gemm<8, 64>(wg, wtid, a_base, sbase + SM_B_FC1, 64, t_y, 0u, bar_mma);
+            }
             mbar_wait(bar_mma, phase); phase ^= 1;
             tc_fence_after();
 
@@ -413,7 +480,7 @@ __global__ void __launch_bounds__(UM_THREADS, 1) score_umma_kernel(UmmaParams p)
 #pragma unroll
                 for (int c = 0; c < 8; ++c) {
                     const float* gq = cst + CST_G1 + c * 8;
-                    uint32_t pk[4];
+                    uint32_t pk[4], pl[4];
 #pragma unroll
                     for (int q = 0; q < 4; ++q) {
                         float2 sv = make_float2(-__ldg(Scol + (c * 8 + 2 * q) * sstr), -__ldg(Scol + (c * 8 + 2 * q + 1) * sstr));
@@ -421,11 +488,25 @@ __global__ void __launch_bounds__(UM_THREADS, 1) score_umma_kernel(UmmaParams p)
                         float2 u = __ffma2_rn(tz, make_float2(gq[2 * q], gq[2 * q + 1]), sv);
                         u = __fmul2_rn(u, u);
                         pk[q] = pack_h2(u.x, u.y);
+                        if constexpr (HI) {             // u = hi + lo, both fp16: the classifier GEMM sees ~22 bits of u
+                            float2 hf = __half22float2(u2h(pk[q]));
+                            float2 lo = __fadd2_rn(u, make_float2(-hf.x, -hf.y));
+                            pl[q] = pack_h2(lo.x, lo.y);
+                        }
                     }
                     sts128(a_chunk_addr(a_base, wtid, c), pk[0], pk[1], pk[2], pk[3]);
+                    if constexpr (HI) sts128(a_chunk_addr(a_base + 16384u, wtid, c), pl[0], pl[1], pl[2], pl[3]);
                 }
             }
-            issue_gemm<4, 32>(wg, wtid, a_base, sbase + SM_B_C0, 32, t_h, 0u, bar_mma);
+            if constexpr (HI) {
+                ISSUE_BEGIN()
+                mma_group<4, 32>(a_base, sbase + SM_B_C0, 32, t_h, 0u);                  // u_hi . C0_hi
+                mma_group<4, 32>(a_base + 16384u, sbase + SM_B_C0, 32, t_h, 1u);         // u_lo . C0_hi
+                mma_group<4, 32>(a_base, sbase + SM_B_C0_LO, 32, t_h, 1u);               // u_hi . C0_lo
+                ISSUE_END()
+            } else {
+                issue_gemm<4, 32>(wg, wtid, a_base, sbase + SM_B_C0, 32, t_h, 0u, bar_mma);
+            }
             mbar_wait(bar_mma, phase); phase ^= 1;
             tc_fence_after();
 
@@ -504,6 +585,12 @@ int umma_build_weights(const float* fc1, const float* w0, const float* b0, const
     std::vector<float> c0h((size_t)(d / 2) * d);
     for (size_t i = 0; i < c0h.size(); ++i) c0h[i] = 0.5f * c0[i];
     swizzle_image(c0h.data(), d / 2, d, reinterpret_cast<__half*>(wimg_host + SM_B_C0));
+    // low halves for the high-accuracy variant: w_lo = w - fp16(w)
+    std::vector<float> lo((size_t)d * HSG_HD);
+    for (size_t i = 0; i < lo.size(); ++i) lo[i] = fc1[i] - __half2float(__float2half_rn(fc1[i]));
+    swizzle_image(lo.data(), d, HSG_HD, reinterpret_cast<__half*>(wimg_host + SM_B_FC1_LO));
+    for (size_t i = 0; i < c0h.size(); ++i) lo[i] = c0h[i] - __half2float(__float2half_rn(c0h[i]));
+    swizzle_image(lo.data(), d / 2, d, reinterpret_cast<__half*>(wimg_host + SM_B_C0_LO));
     for (int i = 0; i < d; ++i) { cst_host[CST_B1 + i] = b1[i]; cst_host[CST_G1 + i] = ln1_g[i]; }
     for (int i = 0; i < d / 2; ++i) { cst_host[CST_CB0 + i] = 0.5f * cb0[i]; cst_host[CST_CW1 + i] = cw1[i]; }
     cst_host[CST_CB1] = cb1[0];
@@ -534,6 +621,7 @@ int launch_score_pairs_umma(hsg_ctx* c, int cell_start, int n_batch, float* out,
     UmmaParams p;
     p.QK16 = (const __half*)c->QK16; p.XS = c->XS; p.binV16 = (const __half*)c->binV16; p.binSb = c->binSb;
     p.cellV16 = (const __half*)c->cellV16; p.cellSb = c->cellSb; p.wimg = c->wimg;
+    p.QK32 = c->QK; p.binV32 = c->binV; p.cellV32 = c->cellV;
     memcpy(p.cst, c->h_cst, sizeof(p.cst));
     p.pairs = c->pairs; p.pair_bias = c->pair_bias; p.P = c->P;
     p.n_bins = c->n_bins; p.n_cells = c->n_cells; p.cell_start = cell_start; p.n_batch = n_batch;
@@ -543,10 +631,12 @@ int launch_score_pairs_umma(hsg_ctx* c, int cell_start, int n_batch, float* out,
     int grid = (int)(quads < c->n_sm ? quads : c->n_sm);
     static bool attr_set = false;
     if (!attr_set) {
-        HSG_CUDA(cudaFuncSetAttribute(score_umma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SM_TOTAL + 1024));
+        HSG_CUDA(cudaFuncSetAttribute(score_umma_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, SM_TOTAL + 1024));
+        HSG_CUDA(cudaFuncSetAttribute(score_umma_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, SM_TOTAL + 1024));
         attr_set = true;
     }
-    score_umma_kernel<<<grid, UM_THREADS, SM_TOTAL + 1024, s>>>(p);
+    if (c->umma_hi) score_umma_kernel<true><<<grid, UM_THREADS, SM_TOTAL + 1024, s>>>(p);
+    else score_umma_kernel<false><<<grid, UM_THREADS, SM_TOTAL + 1024, s>>>(p);
     c->launches++;
     HSG_CUDA(cudaGetLastError());
     return 0;

@@ -10,7 +10,7 @@ from typing import Dict, List, Optional, Sequence
 import numpy as np
 
 from . import _lib
-from ._lib import ACT_NONE, ACT_SIGMOID, ACT_SOFTPLUS, PREC_BF16, PREC_FP32, PREC_TC16  # noqa: F401
+from ._lib import ACT_NONE, ACT_SIGMOID, ACT_SOFTPLUS, PREC_BF16, PREC_FP32, PREC_TC16, PREC_TC16_HI  # noqa: F401
 
 
 DEFAULT_PRECISION = PREC_TC16

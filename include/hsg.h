@@ -36,6 +36,10 @@ typedef struct hsg_ctx hsg_ctx;
                              fp16 rather than bf16 operands: same tensor throughput, and the only one of the
                              two that meets the 1e-3 score bar (DESIGN.md "precision")                     */
 
+#define HSG_PREC_TC16_HI 2 /* tensor cores, high-accuracy variant: fp32 Q/K/V tables and attention, hi/lo fp16 splits of the
+                              fc1 / classifier weights and of the squared-difference operand.  HSG_PREC_TC16 selects it
+                              automatically for softplus / raw heads, where the logit error is not damped by a sigmoid    */
+
 /* activation applied to the `mean` head (Impute.py:218-221, Modules.py:814-817) */
 #define HSG_ACT_NONE     0
 #define HSG_ACT_SIGMOID  1   /* loss_mode == "classification" */

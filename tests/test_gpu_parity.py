@@ -113,6 +113,17 @@ def test_impute_golden_tensor_core(tag):
     print("tensor-core path max |err| =", worst)
 
 
+@pytest.mark.parametrize("tag", ["k0_r0", "k4_r0", "k4_r1", "k0_r1_band"])
+def test_impute_golden_tensor_core_high_accuracy(tag):
+    """High-accuracy tcgen05 variant (what softplus heads get automatically): half the bar, 5e-4."""
+    from higashi_b200 import engine as E
+    worst = 0.0
+    for got, ref in _run_impute_fixture(tag, E.PREC_TC16_HI):
+        worst = max(worst, float(np.abs(got - ref).max()))
+    print("high-accuracy tensor-core path max |err| =", worst)
+    assert worst <= 5e-4, worst
+
+
 # ------------------------------------------------------------------ Hyper_SAGNN.predict on explicit triplets
 @pytest.mark.parametrize("d", [64, 128])
 def test_predict_explicit_triplets(d):
