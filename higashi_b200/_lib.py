@@ -72,7 +72,7 @@ EXPORTS = [
     "hsg_embed_table", "hsg_set_table", "hsg_set_contacts", "hsg_set_neighbors", "hsg_build_neighbors",
     "hsg_set_pairs", "hsg_get_coordinates", "hsg_prepare", "hsg_impute_cells", "hsg_impute_cells_host",
     "hsg_fix_cell", "hsg_score_triplets", "hsg_launch_count", "hsg_last_timing", "hsg_set_profiling",
-    "hsg_train_bind", "hsg_train_set_features", "hsg_score_fwd", "hsg_score_bwd",
+    "hsg_train_bind", "hsg_train_set_features", "hsg_score_fwd", "hsg_score_bwd", "hsg_train_options", "hsg_score_heads",
 ]
 
 
@@ -120,6 +120,8 @@ def load():
     lib.hsg_train_set_features.argtypes = [p, i32, f32p, i64, i32]
     lib.hsg_score_fwd.argtypes = [p, i32, i32, i64p, i32, i32p, i32p, f32p, i32, f32p, f32p, i32, i32, f32p, f32p, p]
     lib.hsg_score_bwd.argtypes = [p, p]
+    lib.hsg_train_options.argtypes = [p, f32p, C.c_float]
+    lib.hsg_score_heads.argtypes = [p, f32p, f32p, f32p, f32p, p]
     for name in EXPORTS:
         if name not in ("hsg_last_error", "hsg_launch_count", "hsg_abi_version"):
             getattr(lib, name).restype = i32

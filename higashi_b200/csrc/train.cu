@@ -450,6 +450,80 @@ __global__ void head_bwd_kernel(const float* __restrict__ dmean, const float* __
     if (threadIdx.x == 0) atomicAdd(db1, sh[hd]);
 }
 
+
+// ------------------------------------------------------------------------------------------------ zinb / rank losses
+__device__ __forceinline__ float softplus_t(float x) { return x > 20.0f ? x : log1pf(expf(x)); }   // F.softplus(beta=1, threshold=20)
+__device__ __forceinline__ float sigmoid_t(float x) { return 1.0f / (1.0f + expf(-x)); }
+__device__ float digammaf_dev(float x) {
+    float r = 0.f;
+    while (x < 6.0f) { r -= 1.0f / x; x += 1.0f; }
+    float f = 1.0f / (x * x);
+    return r + logf(x) - 0.5f / x - f * (1.0f / 12.0f - f * (1.0f / 120.0f - f * (1.0f / 252.0f)));
+}
+// -log_zinb_positive(x = w, mu = clamp(softplus(mean) * cell2weight[cell]), theta = clamp(softplus(var)), pi = proba).mean()
+// (Modules.py:30-80, Higashi_wrapper.py:896-905) and its derivatives with respect to the three heads
+__global__ void zinb_kernel(const float* __restrict__ mean, const float* __restrict__ var, const float* __restrict__ proba,
+                            const float* __restrict__ w, const int64_t* __restrict__ x, const float* __restrict__ c2w, int B,
+                            float* __restrict__ loss, float* __restrict__ dmean, float* __restrict__ dvar, float* __restrict__ dproba,
+                            float* __restrict__ pred_out) {
+    int r = blockIdx.x * blockDim.x + threadIdx.x;
+    if (r >= B) return;
+    const float eps = 1e-8f;
+    float xx = w[r], pi = proba[r];
+    float cw = c2w[x[r * 3] - 1];
+    float mu_raw = softplus_t(mean[r]) * cw, th_raw = softplus_t(var[r]);
+    float mu = fminf(fmaxf(mu_raw, 1e-8f), 1e8f), th = fminf(fmaxf(th_raw, 1e-8f), 1e8f);
+    if (pred_out) pred_out[r] = mu;
+    float sp_pi = softplus_t(-pi);
+    float lte = logf(th + eps), ltme = logf(th + mu + eps);
+    float ptl = -pi + th * (lte - ltme);
+    float dptl_dth = (lte - ltme) + th * (1.0f / (th + eps) - 1.0f / (th + mu + eps));
+    float dptl_dmu = -th / (th + mu + eps);
+    float res, d_pi, d_th, d_mu;
+    if (xx < eps) {
+        res = softplus_t(ptl) - sp_pi;
+        float sg = sigmoid_t(ptl);
+        d_pi = -sg + sigmoid_t(-pi); d_th = sg * dptl_dth; d_mu = sg * dptl_dmu;
+    } else if (xx > eps) {
+        res = -sp_pi + ptl + xx * (logf(mu + eps) - ltme) + lgammaf(xx + th) - lgammaf(th) - lgammaf(xx + 1.0f);
+        d_pi = sigmoid_t(-pi) - 1.0f;
+        d_th = dptl_dth - xx / (th + mu + eps) + digammaf_dev(xx + th) - digammaf_dev(th);
+        d_mu = dptl_dmu + xx * (1.0f / (mu + eps) - 1.0f / (th + mu + eps));
+    } else { res = 0.f; d_pi = d_th = d_mu = 0.f; }
+    const float sc = -1.0f / (float)B;
+    atomicAdd(loss, res * sc);
+    float mu_live = (mu_raw > 1e-8f && mu_raw < 1e8f) ? 1.f : 0.f, th_live = (th_raw > 1e-8f && th_raw < 1e8f) ? 1.f : 0.f;
+    dmean[r] = sc * d_mu * mu_live * sigmoid_t(mean[r]) * cw;
+    dvar[r] = sc * d_th * th_live * sigmoid_t(var[r]);
+    dproba[r] = sc * d_pi;
+}
+// rank loss (Higashi_wrapper.py:880-888): BCE-with-logits over all ordered pairs with |w_i - w_j| > thres
+__global__ void rank_pairs_kernel(const float* __restrict__ mean, const float* __restrict__ w, int B, float thres,
+                                  float* __restrict__ gsum, float* __restrict__ acc /* [0]=loss sum, [1]=pair count */) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= B) return;
+    float pi = softplus_t(mean[i]), wi = w[i], g = 0.f, l = 0.f, m = 0.f;
+    for (int j = 0; j < B; ++j) {
+        float dw = wi - w[j];
+        if (fabsf(dw) > thres) {
+            float d = pi - softplus_t(mean[j]);
+            float lab = dw > 0.f ? 1.f : 0.f;
+            l += fmaxf(d, 0.f) - d * lab + log1pf(expf(-fabsf(d)));
+            g += sigmoid_t(d) - lab;
+            m += 1.f;
+        }
+    }
+    gsum[i] = 2.0f * g;                    // (i,j) and (j,i) contribute the same amount to d/d softplus(mean_i)
+    atomicAdd(acc, l); atomicAdd(acc + 1, m);
+}
+__global__ void rank_finish_kernel(const float* __restrict__ mean, const float* __restrict__ gsum, const float* __restrict__ acc, int B,
+                                   float* __restrict__ loss, float* __restrict__ dmean) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    float M = fmaxf(acc[1], 1.f);
+    if (i == 0) *loss = acc[0] / M;
+    if (i < B) dmean[i] = gsum[i] / M * sigmoid_t(mean[i]);
+}
+
 // ------------------------------------------------------------------------------------------------ workspace
 struct TrainWs {
     int maxB = 0, max_nnz = 0, max_nc = 0;
@@ -459,9 +533,9 @@ struct TrainWs {
     // forward activations (all [rows, *] row-major)
     float *Epre, *Eall, *neigh, *selfb, *combpre, *comb, *dyn, *sta, *mu_d, *rs_d, *mu_s, *rs_s, *qin, *kin, *vin, *Q, *K, *V, *P,
         *ctx, *yv, *sp, *mu_y, *rs_y, *xn, *hpre, *h, *z, *mu_z, *rs_z, *Dn, *mu_p, *rs_p, *Sn, *u, *cpre, *cact, *o, *hp2, *dp2,
-        *mean, *loss;
+        *mean, *loss, *vpre, *vact, *ov, *ppre, *pact, *op, *hp1, *dp1, *hp3, *dp3, *varh, *probah, *pred, *gsum;
     // backward scratch
-    float *dmean, *dc, *du, *dD, *dS, *dz, *dh, *dxn, *dy, *dsp, *dctx, *dQ, *dK, *dV, *dqin, *dkin, *dvin, *ddyn, *dsta, *dcomb,
+    float *dvar, *dproba, *dmean, *dc, *du, *dD, *dS, *dz, *dh, *dxn, *dy, *dsp, *dctx, *dQ, *dK, *dV, *dqin, *dkin, *dvin, *ddyn, *dsta, *dcomb,
         *dneigh, *dself, *dEall;
     // last batch
     int B = 0, chrom = 0, nnz = 0, stage = 2, only_model = 0, mode = 0;
@@ -522,7 +596,10 @@ static int ws_alloc(hsg_ctx* c, int maxB, int max_nnz) {
         {&w->sp, R * d}, {&w->mu_y, R}, {&w->rs_y, R}, {&w->xn, R * d}, {&w->hpre, R * d}, {&w->h, R * d}, {&w->z, R * d},
         {&w->mu_z, R}, {&w->rs_z, R}, {&w->Dn, R * d}, {&w->mu_p, R}, {&w->rs_p, R}, {&w->Sn, R * d}, {&w->u, R * d},
         {&w->cpre, R * hd}, {&w->cact, R * hd}, {&w->o, R}, {&w->hp2, (size_t)maxB * 4}, {&w->dp2, (size_t)maxB},
-        {&w->mean, (size_t)maxB}, {&w->loss, 64},
+        {&w->mean, (size_t)maxB}, {&w->loss, 64}, {&w->vpre, R * hd}, {&w->vact, R * hd}, {&w->ov, R}, {&w->ppre, R * hd},
+        {&w->pact, R * hd}, {&w->op, R}, {&w->hp1, (size_t)maxB * 4}, {&w->dp1, (size_t)maxB}, {&w->hp3, (size_t)maxB * 4},
+        {&w->dp3, (size_t)maxB}, {&w->varh, (size_t)maxB}, {&w->probah, (size_t)maxB}, {&w->pred, (size_t)maxB}, {&w->gsum, (size_t)maxB},
+        {&w->dvar, (size_t)maxB}, {&w->dproba, (size_t)maxB},
         {&w->dmean, (size_t)maxB}, {&w->dc, R * hd}, {&w->du, R * d}, {&w->dD, R * d}, {&w->dS, R * d}, {&w->dz, R * d},
         {&w->dh, R * d}, {&w->dxn, R * d}, {&w->dy, R * d}, {&w->dsp, R * d}, {&w->dctx, R * HSG_HD}, {&w->dQ, R * HSG_HD},
         {&w->dK, R * HSG_HD}, {&w->dV, R * HSG_HD}, {&w->dqin, R * d}, {&w->dkin, R * d}, {&w->dvin, R * d}, {&w->ddyn, R * d},
@@ -541,6 +618,34 @@ static int ws_alloc(hsg_ctx* c, int maxB, int max_nnz) {
     return 0;
 }
 
+struct TrainOpts { float* c2w = nullptr; float rank_thres = 0.f; };
+static std::map<hsg_ctx*, TrainOpts> g_opts;
+
+extern "C" int hsg_train_options(hsg_ctx* c, const float* cell2weight_host, float rank_thres) {
+    HSG_CHECK(c && c->d > 0, "context not initialised");
+    HSG_CUDA(cudaSetDevice(c->device));
+    TrainOpts& o = g_opts[c];
+    o.rank_thres = rank_thres;
+    if (cell2weight_host) {
+        if (!o.c2w) HSG_CUDA(cudaMalloc(&o.c2w, (size_t)c->n_cells * sizeof(float)));
+        HSG_CUDA(cudaMemcpy(o.c2w, cell2weight_host, (size_t)c->n_cells * sizeof(float), cudaMemcpyHostToDevice));
+    }
+    return 0;
+}
+
+// heads of the last forward batch (mean always; var / proba only after a zinb-mode forward), host outputs, may be NULL
+extern "C" int hsg_score_heads(hsg_ctx* c, float* mean_host, float* var_host, float* proba_host, float* pred_host, void* stream) {
+    HSG_CHECK(c && g_ws.count(c) && g_ws[c]->B > 0, "no forward batch");
+    TrainWs* w = g_ws[c];
+    cudaStream_t s = (cudaStream_t)stream;
+    if (mean_host) HSG_CUDA(cudaMemcpyAsync(mean_host, w->mean, w->B * sizeof(float), cudaMemcpyDeviceToHost, s));
+    if (var_host) HSG_CUDA(cudaMemcpyAsync(var_host, w->varh, w->B * sizeof(float), cudaMemcpyDeviceToHost, s));
+    if (proba_host) HSG_CUDA(cudaMemcpyAsync(proba_host, w->probah, w->B * sizeof(float), cudaMemcpyDeviceToHost, s));
+    if (pred_host) HSG_CUDA(cudaMemcpyAsync(pred_host, w->pred, w->B * sizeof(float), cudaMemcpyDeviceToHost, s));
+    HSG_CUDA(cudaStreamSynchronize(s));
+    return 0;
+}
+
 #define PARAM(slot) (b->params + b->off_slot[slot])
 #define GRAD(slot) (b->grads + b->off_slot[slot])
 
@@ -554,6 +659,7 @@ extern "C" int hsg_score_fwd(hsg_ctx* c, int stage, int chrom, const int64_t* x_
     HSG_CUDA(cudaSetDevice(c->device));
     HSG_CHECK(stage == 1 || stage == 2, "stage must be 1 (MultipleEmbedding) or 2 (GraphSAGE on-hook)");
     HSG_CHECK(chrom >= 0 && chrom < c->n_chrom && B > 0 && x_host, "bad batch");
+    HSG_CHECK(loss_mode >= 0 && loss_mode <= 3, "loss_mode must be 0..3");
     HSG_CHECK(stage == 1 || (indptr_host && (nnz == 0 || (cols_local_host && vals_host))), "stage 2 needs the neighbour CSR");
     TrainBind* b = bind_of(c);
     HSG_CHECK(b->params != nullptr, "call hsg_train_bind first");
@@ -625,11 +731,39 @@ extern "C" int hsg_score_fwd(hsg_ctx* c, int stage, int chrom, const int64_t* x_
                                           PARAM(HSG_W_XP2_W0), PARAM(HSG_W_XP2_B0), PARAM(HSG_W_XP2_W1), PARAM(HSG_W_XP2_B1), w->hp2, w->dp2);
     TR_CHECK_LAUNCH(c);
     pool_kernel<<<nblk(B), 256, 0, s>>>(w->o, w->dp2, B, w->mean); TR_CHECK_LAUNCH(c);
-    // 6. loss (classification: weighted BCE with logits; regression: MSE against the weights)
-    HSG_CUDA(cudaMemsetAsync(w->loss, 0, sizeof(float), s));
-    if (y_host && w_host) {
+    // var / proba heads on the static branch (zinb mode; Modules.py:760-779)
+    if (loss_mode == 2) {
+        HSG_CHECK(b->off_slot[HSG_W_VAR_W0] >= 0 && b->off_slot[HSG_W_PRB_W0] >= 0 && b->off_slot[HSG_W_XP_W0] >= 0 &&
+                  b->off_slot[HSG_W_XP3_W0] >= 0, "zinb mode needs the var / proba heads bound");
+        HSG_CHECK(g_opts[c].c2w != nullptr, "zinb mode needs hsg_train_options(cell2weight)");
+        if (LIN_FWD(R, hd, d, w->Sn, d, PARAM(HSG_W_VAR_W0), d, w->vact, hd, 0.f)) return 1;
+        bias_act_kernel<<<nblk((int64_t)R * hd), 256, 0, s>>>(w->vact, PARAM(HSG_W_VAR_B0), (int64_t)R * hd, hd, 1, w->vpre); TR_CHECK_LAUNCH(c);
+        head_out_kernel<<<nblk(R), 256, 0, s>>>(w->vact, R, hd, PARAM(HSG_W_VAR_W1), PARAM(HSG_W_VAR_B1), w->ov); TR_CHECK_LAUNCH(c);
+        if (LIN_FWD(R, hd, d, w->Sn, d, PARAM(HSG_W_PRB_W0), d, w->pact, hd, 0.f)) return 1;
+        bias_act_kernel<<<nblk((int64_t)R * hd), 256, 0, s>>>(w->pact, PARAM(HSG_W_PRB_B0), (int64_t)R * hd, hd, 1, w->ppre); TR_CHECK_LAUNCH(c);
+        head_out_kernel<<<nblk(R), 256, 0, s>>>(w->pact, R, hd, PARAM(HSG_W_PRB_W1), PARAM(HSG_W_PRB_B1), w->op); TR_CHECK_LAUNCH(c);
+        xp_fwd_kernel<<<nblk(B), 256, 0, s>>>(w->x, B, c->n_chrom + 1, c->cf, c->w[HSG_W_ATTR], c->w[HSG_W_CELL_FEATS], only_model,
+                                              PARAM(HSG_W_XP3_W0), PARAM(HSG_W_XP3_B0), PARAM(HSG_W_XP3_W1), PARAM(HSG_W_XP3_B1), w->hp3, w->dp3);
+        TR_CHECK_LAUNCH(c);
+        xp_fwd_kernel<<<nblk(B), 256, 0, s>>>(w->x, B, c->n_chrom + 1, c->cf, c->w[HSG_W_ATTR], c->w[HSG_W_CELL_FEATS], only_model,
+                                              PARAM(HSG_W_XP_W0), PARAM(HSG_W_XP_B0), PARAM(HSG_W_XP_W1), PARAM(HSG_W_XP_B1), w->hp1, w->dp1);
+        TR_CHECK_LAUNCH(c);
+        pool_kernel<<<nblk(B), 256, 0, s>>>(w->ov, w->dp3, B, w->varh); TR_CHECK_LAUNCH(c);
+        pool_kernel<<<nblk(B), 256, 0, s>>>(w->op, w->dp1, B, w->probah); TR_CHECK_LAUNCH(c);
+    }
+    // 6. loss: 0 classification (weighted BCE with logits), 1 regression (MSE against w), 2 zinb, 3 rank
+    HSG_CUDA(cudaMemsetAsync(w->loss, 0, 4 * sizeof(float), s));
+    if (w_host && (y_host || loss_mode != 0)) {
         if (loss_mode == 0) bce_kernel<<<nblk(B), 256, 0, s>>>(w->mean, w->y, w->w, B, w->loss, w->dmean);
-        else mse_kernel<<<nblk(B), 256, 0, s>>>(w->mean, w->w, B, w->loss, w->dmean);
+        else if (loss_mode == 1) mse_kernel<<<nblk(B), 256, 0, s>>>(w->mean, w->w, B, w->loss, w->dmean);
+        else if (loss_mode == 2)
+            zinb_kernel<<<nblk(B), 256, 0, s>>>(w->mean, w->varh, w->probah, w->w, w->x, g_opts[c].c2w, B, w->loss, w->dmean, w->dvar,
+                                                w->dproba, w->pred);
+        else {
+            rank_pairs_kernel<<<nblk(B, 128), 128, 0, s>>>(w->mean, w->w, B, g_opts[c].rank_thres, w->gsum, w->loss + 1);
+            TR_CHECK_LAUNCH(c);
+            rank_finish_kernel<<<nblk(B), 256, 0, s>>>(w->mean, w->gsum, w->loss + 1, B, w->loss, w->dmean);
+        }
         TR_CHECK_LAUNCH(c);
     }
     if (mean_out_host) HSG_CUDA(cudaMemcpyAsync(mean_out_host, w->mean, B * sizeof(float), cudaMemcpyDeviceToHost, s));
@@ -661,6 +795,27 @@ extern "C" int hsg_score_bwd(hsg_ctx* c, void* stream) {
     if (LIN_DW(R, hd, d, w->dc, hd, w->u, d, GRAD(HSG_W_CLS_W0), d)) return 1;
     if (LIN_DX(R, hd, d, w->dc, hd, PARAM(HSG_W_CLS_W0), d, w->du, d, 0.f)) return 1;
     HSG_CUDA(cudaMemsetAsync(w->dS, 0, nRd * sizeof(float), s));
+    if (w->mode == 2) {        // zinb: the var and proba heads read the normalised static branch
+        xp_bwd_kernel<<<nblk(B), 256, 0, s>>>(w->x, B, c->n_chrom + 1, c->cf, c->w[HSG_W_ATTR], c->w[HSG_W_CELL_FEATS], w->only_model,
+                                              PARAM(HSG_W_XP3_W1), w->hp3, w->dvar, GRAD(HSG_W_XP3_W0), GRAD(HSG_W_XP3_B0),
+                                              GRAD(HSG_W_XP3_W1), GRAD(HSG_W_XP3_B1));
+        TR_CHECK_LAUNCH(c);
+        xp_bwd_kernel<<<nblk(B), 256, 0, s>>>(w->x, B, c->n_chrom + 1, c->cf, c->w[HSG_W_ATTR], c->w[HSG_W_CELL_FEATS], w->only_model,
+                                              PARAM(HSG_W_XP_W1), w->hp1, w->dproba, GRAD(HSG_W_XP_W0), GRAD(HSG_W_XP_B0),
+                                              GRAD(HSG_W_XP_W1), GRAD(HSG_W_XP_B1));
+        TR_CHECK_LAUNCH(c);
+        const int slots[2][4] = {{HSG_W_VAR_W0, HSG_W_VAR_B0, HSG_W_VAR_W1, HSG_W_VAR_B1}, {HSG_W_PRB_W0, HSG_W_PRB_B0, HSG_W_PRB_W1, HSG_W_PRB_B1}};
+        float* dh[2] = {w->dvar, w->dproba}; float* act[2] = {w->vact, w->pact}; float* pre[2] = {w->vpre, w->ppre};
+        for (int q = 0; q < 2; ++q) {
+            head_bwd_kernel<<<nblk(R), 256, (hd + 1) * sizeof(float), s>>>(dh[q], act[q], R, hd, PARAM(slots[q][2]), w->dc, GRAD(slots[q][2]),
+                                                                           GRAD(slots[q][3]));
+            TR_CHECK_LAUNCH(c);
+            dswish_kernel<<<nblk((int64_t)R * hd), 256, 0, s>>>(w->dc, pre[q], (int64_t)R * hd); TR_CHECK_LAUNCH(c);
+            colsum_kernel<<<dim3((hd + 63) / 64, 32), 64, 0, s>>>(w->dc, R, hd, GRAD(slots[q][1])); TR_CHECK_LAUNCH(c);
+            if (LIN_DW(R, hd, d, w->dc, hd, w->Sn, d, GRAD(slots[q][0]), d)) return 1;
+            if (LIN_DX(R, hd, d, w->dc, hd, PARAM(slots[q][0]), d, w->dS, d, 1.f)) return 1;
+        }
+    }
     sqdiff_bwd_kernel<<<nblk(nRd), 256, 0, s>>>(w->Dn, w->Sn, w->du, nRd, w->dD, w->dS); TR_CHECK_LAUNCH(c);
     if (ln_bwd(c, s, w->dD, w->z, R, PARAM(HSG_W_LN1_G), w->mu_z, w->rs_z, w->dz, 0, GRAD(HSG_W_LN1_G), GRAD(HSG_W_LN1_B))) return 1;
     if (ln_bwd(c, s, w->dS, w->sp, R, PARAM(HSG_W_LN2_G), w->mu_p, w->rs_p, w->dsp, 0, GRAD(HSG_W_LN2_G), GRAD(HSG_W_LN2_B))) return 1;

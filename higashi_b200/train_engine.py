@@ -13,7 +13,8 @@ import torch
 
 from . import _lib
 
-LOSS_CLASSIFICATION, LOSS_REGRESSION = 0, 1
+LOSS_CLASSIFICATION, LOSS_REGRESSION, LOSS_ZINB, LOSS_RANK = 0, 1, 2, 3
+LOSS_MODES = {"classification": 0, "regression": 1, "zinb": 2, "rank": 3}
 _FROZEN = {"W_ATTR", "W_CELL_FEATS"}
 
 
@@ -130,6 +131,25 @@ class TrainEngine:
                                                    int(loss_mode), 1 if only_model else 0, p(mean, C.c_float), p(loss, C.c_float),
                                                    C.c_void_p(stream)))
         return mean, (None if loss is None else float(loss[0]))
+
+    def set_options(self, cell2weight=None, rank_thres: float = 0.0):
+        """cell2weight (zinb mode) / rank threshold (rank mode): Higashi_wrapper.py:898, 884."""
+        cw = None if cell2weight is None else np.ascontiguousarray(_np(cell2weight), dtype=np.float32)
+        self.ctx._check(self.ctx.lib.hsg_train_options(self.ctx.h, None if cw is None else cw.ctypes.data_as(C.POINTER(C.c_float)),
+                                                       C.c_float(rank_thres)))
+
+    def heads(self, B: int, zinb: bool = False):
+        """(mean, var, proba, pred) of the last forward batch; var / proba / pred only after a zinb forward."""
+        fp = lambda a: a.ctypes.data_as(C.POINTER(C.c_float))
+        mean = np.empty(B, np.float32)
+        var = np.empty(B, np.float32) if zinb else None
+        proba = np.empty(B, np.float32) if zinb else None
+        pred = np.empty(B, np.float32) if zinb else None
+        stream = torch.cuda.current_stream(self.device).cuda_stream
+        self.ctx._check(self.ctx.lib.hsg_score_heads(self.ctx.h, fp(mean), None if var is None else fp(var),
+                                                     None if proba is None else fp(proba), None if pred is None else fp(pred),
+                                                     C.c_void_p(stream)))
+        return mean, var, proba, pred
 
     def backward(self):
         stream = torch.cuda.current_stream(self.device).cuda_stream

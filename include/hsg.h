@@ -149,11 +149,18 @@ int  hsg_train_set_features(hsg_ctx* ctx, int branch, const float* x_host, int64
  * stage 2 = GraphSageEncoder_with_weights.forward_on_hook (Modules.py:1485-1553) with the neighbour lists of
  * to_neighs_to_mask (Higashi_wrapper.py:171-221) given as CSR over the 2B bin-token rows (indptr [2B+1], cols = LOCAL bin
  * of the chromosome, vals = normalised weights).  x host int64 [B,3] node ids; y, w host float [B] (NULL = no loss).
- * loss_mode 0 = classification (weighted BCE with logits), 1 = regression (MSE against w).  Eval-mode semantics
+ * loss_mode 0 = classification (weighted BCE with logits), 1 = regression (MSE against w), 2 = zinb (-log_zinb_positive,
+ * Modules.py:30-80, needs hsg_train_options), 3 = rank (pairwise BCE, Higashi_wrapper.py:880-888).  Eval-mode semantics
  * (dropout off).  mean_out / loss_out: host outputs (may be NULL).                                                  */
 int  hsg_score_fwd(hsg_ctx* ctx, int stage, int chrom, const int64_t* x_host, int B, const int32_t* indptr_host,
                    const int32_t* cols_local_host, const float* vals_host, int nnz, const float* y_host, const float* w_host,
                    int loss_mode, int only_model, float* mean_out_host, float* loss_out_host, void* stream);
+/* per-run constants of the loss heads: cell2weight [n_cells] (Higashi_wrapper.py:722,898 `cell_feats1`, zinb mode) and the
+ * rank threshold (config `rank_thres`, Higashi_wrapper.py:884).  cell2weight may be NULL.                              */
+int  hsg_train_options(hsg_ctx* ctx, const float* cell2weight_host, float rank_thres);
+/* the three heads of the last forward batch (var / proba are produced by loss_mode 2 = zinb only) and, in zinb mode, the
+ * clamped mean `pred` that forward_batch_hyperedge returns; host float [B] each, any may be NULL                       */
+int  hsg_score_heads(hsg_ctx* ctx, float* mean_host, float* var_host, float* proba_host, float* pred_host, void* stream);
 /* replaces: loss.backward() (Higashi_wrapper.py:1006) for the batch of the last hsg_score_fwd: ACCUMULATES into grads */
 int  hsg_score_bwd(hsg_ctx* ctx, void* stream);
 

@@ -460,6 +460,105 @@ def golden_grads():
     print("grads_d64.npz loss", loss.item(), "n grads", sum(k.startswith("grad/") for k in out))
 
 
+# ------------------------------------------------------------------ (vii) loss modes + stage-1 reconstruction
+def golden_losses():
+    """forward_batch_hyperedge (Higashi_wrapper.py:861-913) in zinb / rank / regression mode on one stage-2 batch, and the
+    stage-1 batch with the cell auto-encoder reconstruction loss (use_recon=True); autograd gradients of each loss."""
+    d = 64
+    ds = tiny_dataset()
+    sparse_obj = ds.csr.to_object_array()
+    rng = np.random.Generator(np.random.PCG64(999))
+    out = dataset_arrays(ds)
+
+    def batch(chrom, seed, n=14):
+        edges = positives(ds, chrom, n, rng)
+        old_perm, old_rng = np.random.permutation, np.random.default_rng
+        np.random.permutation = lambda k: np.arange(k)
+        RW.np.random.default_rng = lambda: np.random.Generator(np.random.PCG64(seed))
+        np.random.seed(seed)
+        try:
+            res = RW.one_thread_generate_neg(edges, np.full(len(edges), chrom, dtype="int8"),
+                                             (rng.random(len(edges)) * 3 + 0.5).astype("float32"), 1, False, np.array([chrom]))
+        finally:
+            np.random.permutation = old_perm
+            RW.np.random.default_rng = old_rng
+        return res
+
+    def grads_of(model, extra=()):
+        g = {}
+        for name, prm in list(model.named_parameters()):
+            if name.startswith("encode1.dynamic_nn.features.") or name.startswith("encode1.dynamic_nn.linear_features.") or "aggregator" in name:
+                continue
+            if prm.grad is not None:
+                g[name] = prm.grad.detach().numpy().copy()
+        for name, prm in model.encode1.static_nn.named_parameters():
+            if prm.grad is not None:
+                g["encode1.static_nn." + name] = prm.grad.detach().numpy().copy()
+        return g
+
+    cell2weight = (rng.random(ds.n_cells) + 0.5).astype(np.float32)
+    out["cell2weight"] = cell2weight
+    # ---- stage 2, three loss modes
+    model, nei = build_reference_model(ds, d)
+    enc, start_end = to_stage2(model, nei, ds, d)
+    model.eval()
+    set_wrapper_globals(ds, sparse_obj, start_end, neg_num=2, weighted=False, precompute=True)
+    x, y, w, x_chrom, to_neighs, _ = batch(1, 31)
+    # mimic the mode-specific weights: zinb / regression use raw counts as targets (zeros for negatives)
+    w = w.astype(np.float32)
+    ind, val, uniq = to_neighs[0]
+    out["s2/x"] = x.astype(np.int64); out["s2/y"] = y; out["s2/w"] = w
+    out["s2/indices"] = ind.numpy().astype(np.int64); out["s2/values"] = val.numpy(); out["s2/unique"] = uniq.numpy().astype(np.int64)
+    ns = type("NS", (), {})()
+    ns.higashi_model = model; ns.use_recon = False; ns.node_embedding_init = nei
+    ns.cell_feats1 = torch.from_numpy(cell2weight); ns.rank_thres = 1
+    RW.neg_num = 2
+    for mode in ("zinb", "rank", "regression", "classification"):
+        ns.mode = mode
+        model.zero_grad()
+        pred, main_loss, mse_loss = RW.Higashi.forward_batch_hyperedge(
+            ns, torch.from_numpy(x), torch.from_numpy(w).float(), x_chrom, to_neighs[0], torch.from_numpy(y).float(), np.array([1]))
+        main_loss.backward()     # with use_recon=False train_epoch weights mse_loss by ratio1 = 0 (Higashi_wrapper.py:997-1002)
+        out["s2/%s/loss" % mode] = np.array(float(main_loss))
+        out["s2/%s/mse" % mode] = np.array(float(mse_loss.sum()))
+        out["s2/%s/pred" % mode] = pred.detach().numpy()
+        with torch.no_grad():
+            m, v, p = model(torch.from_numpy(x), (x_chrom, to_neighs[0]), chroms_in_batch=np.array([1]) + 1)
+        out["s2/%s/heads" % mode] = torch.cat([m, v, p], dim=1).numpy()
+        for k, g in grads_of(model).items():
+            out["s2/%s/grad/%s" % (mode, k)] = g
+    out.update({"s2/" + k: v for k, v in state_arrays(model).items()})
+
+    # ---- stage 1 with the reconstruction loss
+    model1, nei1 = build_reference_model(ds, d, seed=8)
+    model1.eval()
+    x1 = positives(ds, 0, 18, rng)
+    x1[9:, 2] = np.minimum(x1[9:, 2] + 1, ds.num_list[1])
+    y1 = np.concatenate([np.ones((9, 1)), np.zeros((9, 1))]).astype(np.float32)
+    w1 = (rng.random((18, 1)) + 0.5).astype(np.float32)
+    ns1 = type("NS", (), {})()
+    ns1.higashi_model = model1; ns1.use_recon = True; ns1.node_embedding_init = nei1; ns1.mode = "classification"
+    ns1.cell_ids = torch.arange(ds.n_cells).long()
+    model1.zero_grad()
+    pred, main_loss, mse_loss = RW.Higashi.forward_batch_hyperedge(
+        ns1, torch.from_numpy(x1), torch.from_numpy(w1), np.zeros(18, dtype="int8"), [], torch.from_numpy(y1), np.array([0]))
+    main_loss.backward(retain_graph=True)
+    gm = grads_of(model1)
+    model1.zero_grad()
+    mse_loss.backward()
+    gr = grads_of(model1)
+    out["s1/x"] = x1.astype(np.int64); out["s1/y"] = y1; out["s1/w"] = w1
+    out["s1/loss"] = np.array(float(main_loss)); out["s1/mse"] = np.array(float(mse_loss)); out["s1/pred"] = pred.detach().numpy()
+    for k, g in gm.items():
+        out["s1/grad_main/" + k] = g
+    for k, g in gr.items():
+        out["s1/grad_recon/" + k] = g
+    out.update({"s1/" + k: v for k, v in state_arrays(model1).items()})
+    np.savez_compressed(os.path.join(HERE, "losses_d64.npz"), **out)
+    print("losses_d64.npz", {m: float(out["s2/%s/loss" % m]) for m in ("zinb", "rank", "regression", "classification")},
+          "stage1", float(out["s1/loss"]), float(out["s1/mse"]), "n arrays", len(out))
+
+
 if __name__ == "__main__":
     golden_binpair()
     golden_knn()
@@ -471,5 +570,6 @@ if __name__ == "__main__":
     golden_impute("k4_r1", k=4, ltr=1, mode="zinb")
     golden_impute("k0_r1_band", k=0, ltr=1, band=(2, 12))
     golden_grads()
+    golden_losses()
     tot = sum(os.path.getsize(os.path.join(HERE, f)) for f in os.listdir(HERE) if f.endswith(".npz"))
     print("total fixture bytes", tot)

@@ -103,3 +103,43 @@ def test_data_parallel_two_gpus():
                           "127.0.0.1", "--master-port", "29577", os.path.join(root, "scripts", "dp_train_check.py")],
                          capture_output=True, text=True, timeout=600)
     assert out.returncode == 0 and "DP_TRAIN_OK world=2" in out.stdout, out.stdout[-2000:] + out.stderr[-2000:]
+
+
+@pytest.mark.parametrize("mode", ["classification", "regression", "zinb", "rank"])
+def test_loss_modes_forward_backward(mode):
+    """forward_batch_hyperedge loss heads (Higashi_wrapper.py:877-912) + autograd gradients, all four loss modes."""
+    from higashi_b200.train_engine import LOSS_MODES
+    g = load("losses_d64.npz")
+    ds = FixtureDataset(g)
+    eng, _ = _train_engine(g, "s2/sd/", ds)
+    eng.set_options(cell2weight=g["cell2weight"], rank_thres=1.0)
+    tn = (g["s2/indices"], g["s2/values"], g["s2/unique"])
+    x, y, w = g["s2/x"], g["s2/y"], g["s2/w"]
+    mean, loss = eng.forward(x, 1, tn, y=y, w=w, stage=2, loss_mode=LOSS_MODES[mode])
+    heads = g["s2/%s/heads" % mode]
+    np.testing.assert_allclose(mean, heads[:, 0], atol=1e-5, rtol=0)
+    if mode == "zinb":
+        m, v, p, pred = eng.heads(len(x), zinb=True)
+        np.testing.assert_allclose(v, heads[:, 1], atol=1e-5, rtol=0)
+        np.testing.assert_allclose(p, heads[:, 2], atol=1e-5, rtol=0)
+        np.testing.assert_allclose(pred, g["s2/zinb/pred"].reshape(-1), atol=1e-5, rtol=1e-5)
+    assert abs(loss - float(g["s2/%s/loss" % mode])) < 2e-5 * max(1.0, abs(float(g["s2/%s/loss" % mode]))), (loss, float(g["s2/%s/loss" % mode]))
+    eng.zero_grad()
+    eng.backward()
+    torch.cuda.synchronize()
+    grads = {k: v.cpu().numpy() for k, v in eng.named_grads().items()}
+    pre = "s2/%s/grad/" % mode
+    n = 0
+    for k in g:
+        if not k.startswith(pre):
+            continue
+        name = k[len(pre):]
+        if name not in grads:
+            continue
+        ref = g[k].reshape(grads[name].shape)
+        scale = max(1e-3, float(np.abs(ref).max()))
+        err = float(np.abs(grads[name] - ref).max())
+        assert err <= 5e-5 * max(1.0, scale / 1e-2) + 2e-6, (mode, name, err, scale)
+        n += 1
+    assert n >= 33, n
+    eng.close()
