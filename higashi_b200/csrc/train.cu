@@ -221,12 +221,12 @@ __global__ void spmm_bwd_kernel(const int* __restrict__ indptr, const int* __res
 // dynamic / static assembly: row 3r = cell table row, rows 3r+1, 3r+2 = (comb | self) of the two bins
 __global__ void assemble_kernel(const int64_t* __restrict__ x, int B, int d, int n_cells, int bin_base, const float* __restrict__ E_cell,
                                 const float* __restrict__ Eall, const float* __restrict__ comb, float* __restrict__ dyn,
-                                float* __restrict__ sta, float* __restrict__ selfb) {
+                                float* __restrict__ sta, float* __restrict__ selfb, const float* __restrict__ cellrows = nullptr) {
     int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= (int64_t)B * 3 * d) return;
     int f = (int)(i % d); int64_t row = i / d; int r = (int)(row / 3), t = (int)(row % 3);
     if (t == 0) {
-        float v = E_cell[(size_t)(x[r * 3] - 1) * d + f];
+        float v = cellrows ? cellrows[(size_t)r * d + f] : E_cell[(size_t)(x[r * 3] - 1) * d + f];
         dyn[i] = v; sta[i] = v;
     } else {
         int lb = (int)(x[r * 3 + t] - bin_base);             // local bin of the chromosome
@@ -235,6 +235,59 @@ __global__ void assemble_kernel(const int64_t* __restrict__ x, int B, int d, int
         if (selfb) selfb[((size_t)r * 2 + (t - 1)) * d + f] = v;
         dyn[i] = comb ? comb[((size_t)r * 2 + (t - 1)) * d + f] : v;
     }
+}
+// Xg[r, :] = X[cell(r), :]  (cell feature rows of the batch, stage 1)
+__global__ void gather_cell_rows_kernel(const int64_t* __restrict__ x, int B, int F, const float* __restrict__ X, float* __restrict__ Xg) {
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= (int64_t)B * F) return;
+    int r = (int)(i / F), f = (int)(i % F);
+    Xg[i] = X[(size_t)(x[r * 3] - 1) * F + f];
+}
+// dcell[r, :] = ddyn[3r, :] + dsta[3r, :]   (stage 1: dynamic == static)
+__global__ void cell_grad_rows_kernel(const float* __restrict__ ddyn, const float* __restrict__ dsta, int B, int d, float* __restrict__ dcell) {
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= (int64_t)B * d) return;
+    int r = (int)(i / d), f = (int)(i % d);
+    dcell[i] = ddyn[((size_t)r * 3) * d + f] + dsta[((size_t)r * 3) * d + f];
+}
+// auto-encoder reconstruction: a2 = swish(swish(enc)) ; dE = drecon-side gradient through both swishes
+__global__ void swish2_fwd_kernel(const float* __restrict__ enc, int64_t n, float* __restrict__ a1, float* __restrict__ a2) {
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) { float u = swish_acc(enc[i]); a1[i] = u; a2[i] = swish_acc(u); }
+}
+__global__ void swish2_bwd_kernel(float* __restrict__ da, const float* __restrict__ enc, const float* __restrict__ a1, int64_t n) {
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) da[i] *= dswish(a1[i]) * dswish(enc[i]);
+}
+// diff = recon + bias - target ; loss += mean(diff^2) ; drecon = 2 diff / N
+__global__ void recon_mse_kernel(float* __restrict__ recon, const float* __restrict__ bias, const float* __restrict__ target, int64_t n,
+                                 int F, float* __restrict__ loss) {
+    __shared__ float red[32];
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    float l = 0.f;
+    if (i < n) {
+        float df = recon[i] + bias[i % F] - target[i];
+        l = df * df / (float)n;
+        recon[i] = 2.0f * df / (float)n;
+    }
+    l = warp_sum(l);
+    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = l;
+    __syncthreads();
+    if (threadIdx.x < 32) {
+        float v = (threadIdx.x < (blockDim.x >> 5)) ? red[threadIdx.x] : 0.f;
+        v = warp_sum(v);
+        if (threadIdx.x == 0) atomicAdd(loss, v);
+    }
+}
+__global__ void sumsq_kernel(const float* __restrict__ v, int64_t n, float* __restrict__ out) {
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    float l = (i < n) ? v[i] * v[i] : 0.f;
+    l = warp_sum(l);
+    if ((threadIdx.x & 31) == 0) atomicAdd(out, l);
+}
+__global__ void axpy_scaled_kernel(float* __restrict__ y, const float* __restrict__ x, float a, int64_t n) {
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) y[i] = fmaf(a, x[i], y[i]);
 }
 // scatter the gradients of the bin rows back: dself (per bin token) -> dEall ; ddyn/dsta rows -> dcomb / dself
 __global__ void disassemble_kernel(const int64_t* __restrict__ x, int B, int d, int bin_base, const float* __restrict__ ddyn,
@@ -539,6 +592,8 @@ struct TrainWs {
         *dneigh, *dself, *dEall;
     // last batch
     int B = 0, chrom = 0, nnz = 0, stage = 2, only_model = 0, mode = 0;
+    // stage 1: cell branch on-hook
+    float *Xg = nullptr, *cellrows = nullptr, *dcell = nullptr; size_t cell_cap = 0; bool cell_on_hook = false;
 };
 #include <map>
 static std::map<hsg_ctx*, TrainWs*> g_ws;
@@ -574,6 +629,15 @@ extern "C" int hsg_train_bind(hsg_ctx* c, float* params_dev, float* grads_dev, i
     b->off_slot.assign(off_slot, off_slot + HSG_W_COUNT);
     b->off_pw.assign(off_proj_w, off_proj_w + c->n_chrom + 1);
     b->off_pb.assign(off_proj_b, off_proj_b + c->n_chrom + 1);
+    return 0;
+}
+
+static int ws_cell_alloc(hsg_ctx* c, TrainWs* w, int B, int F) {
+    size_t need = (size_t)B * F + 2 * (size_t)B * c->d;
+    if (w->cell_cap >= need) return 0;
+    if (w->Xg) cudaFree(w->Xg);
+    HSG_CUDA(cudaMalloc(&w->Xg, need * sizeof(float)));
+    w->cellrows = w->Xg + (size_t)B * F; w->dcell = w->cellrows + (size_t)B * c->d; w->cell_cap = need;
     return 0;
 }
 
@@ -700,8 +764,19 @@ extern "C" int hsg_score_fwd(hsg_ctx* c, int stage, int chrom, const int64_t* x_
         if (LIN_FWD(NB, d, d, w->selfb, d, G + d, 2 * d, w->comb, d, 1.f)) return 1;
         bias_act_kernel<<<nblk((int64_t)NB * d), 256, 0, s>>>(w->comb, PARAM(HSG_W_SAGE_B), (int64_t)NB * d, d, 1, w->combpre); TR_CHECK_LAUNCH(c);
     }
+    const float* cellrows = nullptr;
+    if (stage == 1 && b->off_pw[0] >= 0 && !b->feat.empty() && b->feat[0] != nullptr) {
+        // cell branch on-hook (stage 1): rows of X_cell for the batch -> linear encoder (Modules.py:550-552, add_activation=False)
+        const int F = b->in_dim[0];
+        if (ws_cell_alloc(c, w, B, F)) return 1;
+        gather_cell_rows_kernel<<<nblk((int64_t)B * F), 256, 0, s>>>(w->x, B, F, b->feat[0], w->Xg); TR_CHECK_LAUNCH(c);
+        if (LIN_FWD(B, d, F, w->Xg, F, b->params + b->off_pw[0], F, w->cellrows, d, 0.f)) return 1;
+        bias_act_kernel<<<nblk((int64_t)B * d), 256, 0, s>>>(w->cellrows, b->params + b->off_pb[0], (int64_t)B * d, d, 0, nullptr); TR_CHECK_LAUNCH(c);
+        cellrows = w->cellrows;
+    }
+    w->cell_on_hook = cellrows != nullptr;
     assemble_kernel<<<nblk((int64_t)R * d), 256, 0, s>>>(w->x, B, d, c->n_cells, bin_base, c->E_cell, w->Eall,
-                                                         stage == 2 ? w->comb : nullptr, w->dyn, w->sta, nullptr);
+                                                         stage == 2 ? w->comb : nullptr, w->dyn, w->sta, nullptr, cellrows);
     TR_CHECK_LAUNCH(c);
     // 3. attention block                                                                  (Modules.py:1029-1095)
     if (ln_fwd(c, s, w->dyn, R, PARAM(HSG_W_ALN1_G), PARAM(HSG_W_ALN1_B), w->qin, w->mu_d, w->rs_d)) return 1;
@@ -862,9 +937,84 @@ extern "C" int hsg_score_bwd(hsg_ctx* c, void* stream) {
         else spmm_bwd_kernel<128><<<(NB + 7) / 8, 256, 0, s>>>(w->indptr, w->cols, w->vals, w->dneigh, NB, w->dEall);
         TR_CHECK_LAUNCH(c);
     }
+    if (w->stage == 1 && w->cell_on_hook) {
+        const int F = b->in_dim[0];
+        cell_grad_rows_kernel<<<nblk((int64_t)B * d), 256, 0, s>>>(w->ddyn, w->dsta, B, d, w->dcell); TR_CHECK_LAUNCH(c);
+        colsum_kernel<<<dim3((d + 63) / 64, 32), 64, 0, s>>>(w->dcell, B, d, b->grads + b->off_pb[0]); TR_CHECK_LAUNCH(c);
+        if (LIN_DW(B, d, F, w->dcell, d, w->Xg, F, b->grads + b->off_pw[0], F)) return 1;
+    }
     // E = swish(X W^T + b)
     dswish_kernel<<<nblk((int64_t)nc * d), 256, 0, s>>>(w->dEall, w->Epre, (int64_t)nc * d); TR_CHECK_LAUNCH(c);
     colsum_kernel<<<dim3((d + 63) / 64, 32), 64, 0, s>>>(w->dEall, nc, d, b->grads + b->off_pb[chrom + 1]); TR_CHECK_LAUNCH(c);
     if (LIN_DW(nc, d, in_c, w->dEall, d, b->feat[chrom + 1], in_c, b->grads + b->off_pw[chrom + 1], in_c)) return 1;
+    return 0;
+}
+
+
+// ------------------------------------------------------------------------------------------------ stage-1 reconstruction loss
+// TiedAutoEncoder.forward(return_recon=True) for the cell branch over ALL cells + F.mse_loss (Higashi_wrapper.py:869-873,
+// Modules.py:255-288): enc = X W0^T + b0 ; recon = swish(swish(enc)) . R + rb ; loss = mean((recon - target)^2).
+// Gradients go to a scratch block laid out like the flat buffer slots they belong to; hsg_recon_apply adds
+// `scale * scratch` to the bound gradient buffer (train_epoch weights the loss by ratio1 after comparing gradient norms).
+struct ReconState { float* scratch = nullptr; size_t cap = 0; float* act = nullptr; size_t act_cap = 0; int64_t off_rw = -1, off_rb = -1; int F = 0; };
+static std::map<hsg_ctx*, ReconState> g_recon;
+
+extern "C" int hsg_train_bind_recon(hsg_ctx* c, int64_t off_reverse_w, int64_t off_recon_b) {
+    HSG_CHECK(c && c->d > 0, "context not initialised");
+    g_recon[c].off_rw = off_reverse_w; g_recon[c].off_rb = off_recon_b;
+    return 0;
+}
+
+extern "C" int hsg_recon_loss(hsg_ctx* c, float* loss_host, float* gnorm_w0_host, void* stream) {
+    HSG_CHECK(c && c->d > 0, "context not initialised");
+    HSG_CUDA(cudaSetDevice(c->device));
+    TrainBind* b = bind_of(c);
+    ReconState& rs = g_recon[c];
+    HSG_CHECK(b->params && !b->feat.empty() && b->feat[0] && b->off_pw[0] >= 0 && rs.off_rw >= 0 && rs.off_rb >= 0,
+              "bind the cell branch (features, weights, reverse weights) first");
+    cudaStream_t s = (cudaStream_t)stream;
+    const int n = c->n_cells, d = c->d, F = b->in_dim[0];
+    rs.F = F;
+    size_t need_s = 2 * (size_t)d * F + d + F + 8, need_a = 3 * (size_t)n * d + (size_t)n * F;
+    if (rs.cap < need_s) { if (rs.scratch) cudaFree(rs.scratch); HSG_CUDA(cudaMalloc(&rs.scratch, need_s * sizeof(float))); rs.cap = need_s; }
+    if (rs.act_cap < need_a) { if (rs.act) cudaFree(rs.act); HSG_CUDA(cudaMalloc(&rs.act, need_a * sizeof(float))); rs.act_cap = need_a; }
+    float *gW = rs.scratch, *gR = gW + (size_t)d * F, *gb = gR + (size_t)d * F, *grb = gb + d, *misc = grb + F;
+    float *enc = rs.act, *a1 = enc + (size_t)n * d, *a2 = a1 + (size_t)n * d, *rec = a2 + (size_t)n * d;
+    HSG_CUDA(cudaMemsetAsync(rs.scratch, 0, need_s * sizeof(float), s));
+    const float* W0 = b->params + b->off_pw[0]; const float* b0 = b->params + b->off_pb[0];
+    const float* Rw = b->params + rs.off_rw; const float* rb = b->params + rs.off_rb;
+    if (LIN_FWD(n, d, F, b->feat[0], F, W0, F, enc, d, 0.f)) return 1;
+    bias_act_kernel<<<nblk((int64_t)n * d), 256, 0, s>>>(enc, b0, (int64_t)n * d, d, 0, nullptr); TR_CHECK_LAUNCH(c);
+    swish2_fwd_kernel<<<nblk((int64_t)n * d), 256, 0, s>>>(enc, (int64_t)n * d, a1, a2); TR_CHECK_LAUNCH(c);
+    // recon[n,F] = a2[n,d] . R[d,F]
+    if (gemm(c, s, false, false, n, F, d, a2, d, Rw, F, rec, F, 0.f)) return 1;
+    recon_mse_kernel<<<nblk((int64_t)n * F), 256, 0, s>>>(rec, rb, b->feat[0], (int64_t)n * F, F, misc); TR_CHECK_LAUNCH(c);
+    // backward: rec now holds d(loss)/d(recon)
+    colsum_kernel<<<dim3((F + 63) / 64, 32), 64, 0, s>>>(rec, n, F, grb); TR_CHECK_LAUNCH(c);
+    if (gemm(c, s, true, false, d, F, n, a2, d, rec, F, gR, F, 1.f)) return 1;              // dR = a2^T drecon
+    if (gemm(c, s, false, true, n, d, F, rec, F, Rw, F, a2, d, 0.f)) return 1;              // da2 = drecon R^T (reuse a2)
+    swish2_bwd_kernel<<<nblk((int64_t)n * d), 256, 0, s>>>(a2, enc, a1, (int64_t)n * d); TR_CHECK_LAUNCH(c);
+    colsum_kernel<<<dim3((d + 63) / 64, 32), 64, 0, s>>>(a2, n, d, gb); TR_CHECK_LAUNCH(c);
+    if (LIN_DW(n, d, F, a2, d, b->feat[0], F, gW, F)) return 1;
+    sumsq_kernel<<<nblk((int64_t)d * F), 256, 0, s>>>(gW, (int64_t)d * F, misc + 1); TR_CHECK_LAUNCH(c);
+    float h[2] = {0, 0};
+    HSG_CUDA(cudaMemcpyAsync(h, misc, 2 * sizeof(float), cudaMemcpyDeviceToHost, s));
+    HSG_CUDA(cudaStreamSynchronize(s));
+    if (loss_host) *loss_host = h[0];
+    if (gnorm_w0_host) *gnorm_w0_host = sqrtf(h[1]);
+    return 0;
+}
+
+extern "C" int hsg_recon_apply(hsg_ctx* c, float scale, void* stream) {
+    HSG_CHECK(c && g_recon.count(c) && g_recon[c].scratch, "call hsg_recon_loss first");
+    TrainBind* b = bind_of(c);
+    ReconState& rs = g_recon[c];
+    cudaStream_t s = (cudaStream_t)stream;
+    const int d = c->d, F = rs.F;
+    float *gW = rs.scratch, *gR = gW + (size_t)d * F, *gb = gR + (size_t)d * F, *grb = gb + d;
+    axpy_scaled_kernel<<<nblk((int64_t)d * F), 256, 0, s>>>(b->grads + b->off_pw[0], gW, scale, (int64_t)d * F); TR_CHECK_LAUNCH(c);
+    axpy_scaled_kernel<<<nblk((int64_t)d * F), 256, 0, s>>>(b->grads + rs.off_rw, gR, scale, (int64_t)d * F); TR_CHECK_LAUNCH(c);
+    axpy_scaled_kernel<<<nblk(d), 256, 0, s>>>(b->grads + b->off_pb[0], gb, scale, d); TR_CHECK_LAUNCH(c);
+    axpy_scaled_kernel<<<nblk(F), 256, 0, s>>>(b->grads + rs.off_rb, grb, scale, F); TR_CHECK_LAUNCH(c);
     return 0;
 }

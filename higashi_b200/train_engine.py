@@ -40,7 +40,7 @@ def neighbors_to_csr(to_neighs, n_rows: int, bin_base: int):
 
 class TrainEngine:
     def __init__(self, sd: Dict[str, object], num: Sequence[int], feats: list, cell_feats, device: int = 0,
-                 cell_table=None, embed_prefix: str = "encode1.static_nn"):
+                 cell_table=None, embed_prefix: str = "encode1.static_nn", cell_on_hook: bool = False):
         self.ctx = _lib.Context(device)
         self.device = torch.device("cuda", device)
         self.num = [int(v) for v in num]
@@ -79,13 +79,20 @@ class TrainEngine:
                 self.layout[key] = (off, shape)
                 arr[b] = off
                 off += (int(np.prod(shape)) + 3) & ~3
+        self.cell_on_hook = cell_on_hook
+        if cell_on_hook:                       # stage 1: decoder half of the cell auto-encoder (reconstruction loss)
+            for which in ("reverse_weight_list", "recon_bias_list"):
+                key = "%s.wstack.0.%s.0" % (embed_prefix, which)
+                shape = tuple(_np(sd[key]).shape)
+                self.layout[key] = (off, shape)
+                off += (int(np.prod(shape)) + 3) & ~3
         self.total = off
         self.params = torch.zeros(self.total, dtype=torch.float32, device=self.device)
         self.grads = torch.zeros(self.total, dtype=torch.float32, device=self.device)
         for key, (o, shape) in self.layout.items():
             n = int(np.prod(shape))
             self.params[o:o + n] = torch.from_numpy(_np(sd[key]).astype(np.float32).reshape(-1)).to(self.device)
-        for b in range(1, n_chrom + 1):
+        for b in range(0 if cell_on_hook else 1, n_chrom + 1):
             f = np.ascontiguousarray(_np(feats[b]), dtype=np.float32)
             self.ctx._check(self.ctx.lib.hsg_train_set_features(self.ctx.h, b, f.ctypes.data_as(C.POINTER(C.c_float)), f.shape[0], f.shape[1]))
         i64p = lambda a: a.ctypes.data_as(C.POINTER(C.c_int64))
@@ -93,8 +100,25 @@ class TrainEngine:
         self.ctx._check(self.ctx.lib.hsg_train_bind(self.ctx.h, C.c_void_p(self.params.data_ptr()), C.c_void_p(self.grads.data_ptr()),
                                                     self.total, i64p(off_slot), i64p(off_pw), i64p(off_pb)))
 
+        if cell_on_hook:
+            self.ctx._check(self.ctx.lib.hsg_train_bind_recon(
+                self.ctx.h, self.layout["%s.wstack.0.reverse_weight_list.0" % embed_prefix][0],
+                self.layout["%s.wstack.0.recon_bias_list.0" % embed_prefix][0]))
+        self.embed_prefix = embed_prefix
+
     def close(self):
         self.ctx.close()
+
+    def recon_loss(self):
+        """(mse over all cells, ||grad wstack.0.weight_list.0||) of the cell auto-encoder; gradients stay in a scratch block."""
+        loss, gn = C.c_float(0), C.c_float(0)
+        stream = torch.cuda.current_stream(self.device).cuda_stream
+        self.ctx._check(self.ctx.lib.hsg_recon_loss(self.ctx.h, C.byref(loss), C.byref(gn), C.c_void_p(stream)))
+        return float(loss.value), float(gn.value)
+
+    def recon_apply(self, scale: float):
+        stream = torch.cuda.current_stream(self.device).cuda_stream
+        self.ctx._check(self.ctx.lib.hsg_recon_apply(self.ctx.h, C.c_float(scale), C.c_void_p(stream)))
 
     def named_params(self):
         return {k: self.params[o:o + int(np.prod(s))].view(s) for k, (o, s) in self.layout.items()}

@@ -164,6 +164,16 @@ int  hsg_score_heads(hsg_ctx* ctx, float* mean_host, float* var_host, float* pro
 /* replaces: loss.backward() (Higashi_wrapper.py:1006) for the batch of the last hsg_score_fwd: ACCUMULATES into grads */
 int  hsg_score_bwd(hsg_ctx* ctx, void* stream);
 
+/* stage 1 (train_for_embeddings): the cell branch is on-hook (hsg_train_set_features(branch 0) + bound projection) and the
+ * cell auto-encoder reconstruction loss over ALL cells is added (Higashi_wrapper.py:869-873; TiedAutoEncoder.forward with
+ * return_recon, Modules.py:255-288).  off_reverse_w / off_recon_b: offsets of wstack.0.reverse_weight_list.0 [d,F] and
+ * wstack.0.recon_bias_list.0 [F] in the flat buffers.  hsg_recon_loss computes the loss and its gradients into a scratch
+ * block and returns ||d loss / d weight_list.0||; hsg_recon_apply adds scale * scratch to the bound gradients (train_epoch
+ * picks scale = ratio1 from the two gradient norms, Higashi_wrapper.py:970-1002).                                         */
+int  hsg_train_bind_recon(hsg_ctx* ctx, int64_t off_reverse_w, int64_t off_recon_b);
+int  hsg_recon_loss(hsg_ctx* ctx, float* loss_host, float* gnorm_w0_host, void* stream);
+int  hsg_recon_apply(hsg_ctx* ctx, float scale, void* stream);
+
 /* ---- introspection ------------------------------------------------------------------------ */
 /* number of kernels this library launched since the context was created (bench.py gpu_launches) */
 int64_t hsg_launch_count(hsg_ctx* ctx);

@@ -143,3 +143,39 @@ def test_loss_modes_forward_backward(mode):
         n += 1
     assert n >= 33, n
     eng.close()
+
+
+def test_stage1_cell_branch_and_reconstruction():
+    """Stage 1 (train_for_embeddings): cell branch on-hook + auto-encoder reconstruction MSE over all cells; the two
+    gradient sets of train_epoch's separate backward passes (Higashi_wrapper.py:970-983)."""
+    from higashi_b200.train_engine import TrainEngine
+    g = load("losses_d64.npz")
+    ds = FixtureDataset(g)
+    sd = {k[len("s1/sd/"):]: v for k, v in g.items() if k.startswith("s1/sd/")}
+    eng = TrainEngine(sd, ds.num, ds.feats, ds.cell_feats, device=0, cell_on_hook=True)
+    mean, loss = eng.forward(g["s1/x"], 0, None, y=g["s1/y"], w=g["s1/w"], stage=1)
+    np.testing.assert_allclose(mean, g["s1/pred"].reshape(-1), atol=1e-5, rtol=0)
+    assert abs(loss - float(g["s1/loss"])) < 1e-5
+    eng.zero_grad(); eng.backward(); torch.cuda.synchronize()
+    grads = {k: v.cpu().numpy().copy() for k, v in eng.named_grads().items()}
+    n = 0
+    for k in g:
+        if k.startswith("s1/grad_main/") and k[len("s1/grad_main/"):] in grads:
+            name = k[len("s1/grad_main/"):]
+            ref = g[k].reshape(grads[name].shape)
+            assert float(np.abs(grads[name] - ref).max()) <= 3e-5 * max(1.0, float(np.abs(ref).max()) / 1e-2) + 2e-6, name
+            n += 1
+    assert n >= 33 and "encode1.static_nn.wstack.0.weight_list.0" in grads
+    assert float(np.abs(grads["encode1.static_nn.wstack.0.weight_list.0"]).max()) > 0
+    # reconstruction loss: separate gradient set, applied with a scale
+    rl, gn = eng.recon_loss()
+    assert abs(rl - float(g["s1/mse"])) < 1e-4 * float(g["s1/mse"])
+    ref_w = g["s1/grad_recon/encode1.static_nn.wstack.0.weight_list.0"]
+    assert abs(gn - float(np.linalg.norm(ref_w))) < 1e-4 * float(np.linalg.norm(ref_w))
+    eng.zero_grad(); eng.recon_apply(1.0); torch.cuda.synchronize()
+    gr = {k: v.cpu().numpy() for k, v in eng.named_grads().items()}
+    for short in ("weight_list", "reverse_weight_list", "bias_list", "recon_bias_list"):
+        name = "encode1.static_nn.wstack.0.%s.0" % short
+        ref = g["s1/grad_recon/" + name]
+        assert float(np.abs(gr[name] - ref).max()) <= 2e-5 * max(1.0, float(np.abs(ref).max()) / 1e-2) + 1e-6, name
+    eng.close()
