@@ -73,7 +73,7 @@ EXPORTS = [
     "hsg_set_pairs", "hsg_get_coordinates", "hsg_prepare", "hsg_impute_cells", "hsg_impute_cells_host",
     "hsg_fix_cell", "hsg_score_triplets", "hsg_launch_count", "hsg_last_timing", "hsg_set_profiling",
     "hsg_train_bind", "hsg_train_set_features", "hsg_score_fwd", "hsg_score_bwd", "hsg_train_options", "hsg_score_heads",
-    "hsg_train_bind_recon", "hsg_recon_loss", "hsg_recon_apply",
+    "hsg_train_bind_recon", "hsg_recon_loss", "hsg_recon_apply", "hsg_train_set_dropout",
 ]
 
 
@@ -126,6 +126,7 @@ def load():
     lib.hsg_train_bind_recon.argtypes = [p, i64, i64]
     lib.hsg_recon_loss.argtypes = [p, f32p, f32p, p]
     lib.hsg_recon_apply.argtypes = [p, C.c_float, p]
+    lib.hsg_train_set_dropout.argtypes = [p, i32, C.c_uint64]
     for name in EXPORTS:
         if name not in ("hsg_last_error", "hsg_launch_count", "hsg_abi_version"):
             getattr(lib, name).restype = i32

@@ -108,6 +108,17 @@ __global__ void colsum_kernel(const float* __restrict__ dy, int rows, int cols, 
     for (int r = blockIdx.y; r < rows; r += gridDim.y) s += dy[(size_t)r * cols + col];
     atomicAdd(db + col, s);
 }
+// inverted dropout with a counter-based mask (same (seed, tag, index) -> same mask in forward and backward)
+__device__ __forceinline__ float keep_scale(unsigned long long seed, unsigned tag, unsigned long long i, float p) {
+    unsigned long long z = seed + 0x9E3779B97F4A7C15ull * (i + 1) + ((unsigned long long)tag << 56);
+    z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull; z = (z ^ (z >> 27)) * 0x94D049BB133111EBull; z ^= z >> 31;      // splitmix64
+    float u = (float)(z >> 40) * (1.0f / 16777216.0f);
+    return u >= p ? 1.0f / (1.0f - p) : 0.0f;
+}
+__global__ void dropout_kernel(float* __restrict__ x, int64_t n, float p, unsigned long long seed, unsigned tag) {
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) x[i] *= keep_scale(seed, tag, (unsigned long long)i, p);
+}
 __global__ void axpy_kernel(float* __restrict__ y, const float* __restrict__ x, int64_t n) {
     int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i < n) y[i] += x[i];
@@ -593,6 +604,7 @@ struct TrainWs {
     // last batch
     int B = 0, chrom = 0, nnz = 0, stage = 2, only_model = 0, mode = 0;
     // stage 1: cell branch on-hook
+    int dropout = 0; unsigned long long seed = 0;
     float *Xg = nullptr, *cellrows = nullptr, *dcell = nullptr; size_t cell_cap = 0; bool cell_on_hook = false;
 };
 #include <map>
@@ -682,7 +694,7 @@ static int ws_alloc(hsg_ctx* c, int maxB, int max_nnz) {
     return 0;
 }
 
-struct TrainOpts { float* c2w = nullptr; float rank_thres = 0.f; };
+struct TrainOpts { float* c2w = nullptr; float rank_thres = 0.f; int dropout = 0; unsigned long long seed = 0; };
 static std::map<hsg_ctx*, TrainOpts> g_opts;
 
 extern "C" int hsg_train_options(hsg_ctx* c, const float* cell2weight_host, float rank_thres) {
@@ -694,6 +706,14 @@ extern "C" int hsg_train_options(hsg_ctx* c, const float* cell2weight_host, floa
         if (!o.c2w) HSG_CUDA(cudaMalloc(&o.c2w, (size_t)c->n_cells * sizeof(float)));
         HSG_CUDA(cudaMemcpy(o.c2w, cell2weight_host, (size_t)c->n_cells * sizeof(float), cudaMemcpyHostToDevice));
     }
+    return 0;
+}
+
+// training-mode dropout (Hyper_SAGNN: 0.3 after fc1 / fc2, Modules.py:685,1088-1089; 0.4 inside pff_n1, Modules.py:686,876).
+// enabled = 0 gives the eval-mode semantics the parity tests use; `seed` should change every step.
+extern "C" int hsg_train_set_dropout(hsg_ctx* c, int enabled, uint64_t seed) {
+    HSG_CHECK(c && c->d > 0, "context not initialised");
+    g_opts[c].dropout = enabled; g_opts[c].seed = seed;
     return 0;
 }
 
@@ -788,10 +808,17 @@ extern "C" int hsg_score_fwd(hsg_ctx* c, int stage, int chrom, const int64_t* x_
     attn_fwd_kernel<<<nblk(B * 8, 128), 128, 0, s>>>(w->Q, w->K, w->V, B, w->ctx, w->P); TR_CHECK_LAUNCH(c);
     if (LIN_FWD(R, d, HSG_HD, w->ctx, HSG_HD, PARAM(HSG_W_FC1), HSG_HD, w->yv, d, 0.f)) return 1;
     if (LIN_FWD(R, d, HSG_HD, w->V, HSG_HD, PARAM(HSG_W_FC2), HSG_HD, w->sp, d, 0.f)) return 1;
+    const TrainOpts& opt = g_opts[c];
+    w->dropout = opt.dropout; w->seed = opt.seed;
+    if (opt.dropout) {
+        dropout_kernel<<<nblk((int64_t)R * d), 256, 0, s>>>(w->yv, (int64_t)R * d, 0.3f, opt.seed, 1); TR_CHECK_LAUNCH(c);
+        dropout_kernel<<<nblk((int64_t)R * d), 256, 0, s>>>(w->sp, (int64_t)R * d, 0.3f, opt.seed, 2); TR_CHECK_LAUNCH(c);
+    }
     // 4. pff_n1: LN -> W0 -> swish -> W1 -> + residual                                    (Modules.py:865-889)
     if (ln_fwd(c, s, w->yv, R, PARAM(HSG_W_PFF_LN_G), PARAM(HSG_W_PFF_LN_B), w->xn, w->mu_y, w->rs_y)) return 1;
     if (LIN_FWD(R, d, d, w->xn, d, PARAM(HSG_W_PFF_W0), d, w->h, d, 0.f)) return 1;
     bias_act_kernel<<<nblk((int64_t)R * d), 256, 0, s>>>(w->h, PARAM(HSG_W_PFF_B0), (int64_t)R * d, d, 1, w->hpre); TR_CHECK_LAUNCH(c);
+    if (opt.dropout) { dropout_kernel<<<nblk((int64_t)R * d), 256, 0, s>>>(w->h, (int64_t)R * d, 0.4f, opt.seed, 3); TR_CHECK_LAUNCH(c); }
     HSG_CUDA(cudaMemcpyAsync(w->z, w->yv, (size_t)R * d * sizeof(float), cudaMemcpyDeviceToDevice, s));
     if (LIN_FWD(R, d, d, w->h, d, PARAM(HSG_W_PFF_W1), d, w->z, d, 1.f)) return 1;
     bias_act_kernel<<<nblk((int64_t)R * d), 256, 0, s>>>(w->z, PARAM(HSG_W_PFF_B1), (int64_t)R * d, d, 0, nullptr); TR_CHECK_LAUNCH(c);
@@ -898,13 +925,18 @@ extern "C" int hsg_score_bwd(hsg_ctx* c, void* stream) {
     colsum_kernel<<<dim3((d + 63) / 64, 32), 64, 0, s>>>(w->dz, R, d, GRAD(HSG_W_PFF_B1)); TR_CHECK_LAUNCH(c);
     if (LIN_DW(R, d, d, w->dz, d, w->h, d, GRAD(HSG_W_PFF_W1), d)) return 1;
     if (LIN_DX(R, d, d, w->dz, d, PARAM(HSG_W_PFF_W1), d, w->dh, d, 0.f)) return 1;
+    if (w->dropout) { dropout_kernel<<<nblk(nRd), 256, 0, s>>>(w->dh, nRd, 0.4f, w->seed, 3); TR_CHECK_LAUNCH(c); }
     dswish_kernel<<<nblk(nRd), 256, 0, s>>>(w->dh, w->hpre, nRd); TR_CHECK_LAUNCH(c);
     colsum_kernel<<<dim3((d + 63) / 64, 32), 64, 0, s>>>(w->dh, R, d, GRAD(HSG_W_PFF_B0)); TR_CHECK_LAUNCH(c);
     if (LIN_DW(R, d, d, w->dh, d, w->xn, d, GRAD(HSG_W_PFF_W0), d)) return 1;
     if (LIN_DX(R, d, d, w->dh, d, PARAM(HSG_W_PFF_W0), d, w->dxn, d, 0.f)) return 1;
     HSG_CUDA(cudaMemcpyAsync(w->dy, w->dz, nRd * sizeof(float), cudaMemcpyDeviceToDevice, s));      // residual branch
     if (ln_bwd(c, s, w->dxn, w->yv, R, PARAM(HSG_W_PFF_LN_G), w->mu_y, w->rs_y, w->dy, 1, GRAD(HSG_W_PFF_LN_G), GRAD(HSG_W_PFF_LN_B))) return 1;
-    // attention outputs:  y = fc1 ctx ; sp = fc2 V
+    // attention outputs:  y = fc1 ctx ; sp = fc2 V   (each followed by dropout 0.3 in training mode)
+    if (w->dropout) {
+        dropout_kernel<<<nblk(nRd), 256, 0, s>>>(w->dy, nRd, 0.3f, w->seed, 1); TR_CHECK_LAUNCH(c);
+        dropout_kernel<<<nblk(nRd), 256, 0, s>>>(w->dsp, nRd, 0.3f, w->seed, 2); TR_CHECK_LAUNCH(c);
+    }
     if (LIN_DW(R, d, HSG_HD, w->dy, d, w->ctx, HSG_HD, GRAD(HSG_W_FC1), HSG_HD)) return 1;
     if (LIN_DX(R, d, HSG_HD, w->dy, d, PARAM(HSG_W_FC1), HSG_HD, w->dctx, HSG_HD, 0.f)) return 1;
     if (LIN_DW(R, d, HSG_HD, w->dsp, d, w->V, HSG_HD, GRAD(HSG_W_FC2), HSG_HD)) return 1;

@@ -111,7 +111,7 @@ class DataParallelTrainer:
         for i, n in enumerate(self.names):
             if ".wstack." in n:
                 b = int(n.split(".wstack.")[1].split(".")[0])
-                on = (b == chrom + 1) or (b == 0 and stage == 1 and False)
+                on = (b == chrom + 1) or (b == 0 and stage == 1 and self.eng.cell_on_hook)
             else:
                 on = not (n.startswith("pff_classifier_var") or n.startswith("pff_classifier_proba") or
                           n.startswith("extra_proba.") or n.startswith("extra_proba3") or
@@ -119,10 +119,28 @@ class DataParallelTrainer:
             if on:
                 self.presence[i] = 1.0
 
-    def step(self, x, chrom, to_neighs, y, w, stage=2, loss_mode=0):
+    def step(self, x, chrom, to_neighs, y, w, stage=2, loss_mode=0, train_mode=True, alpha=1.0, beta=1e-2,
+             median_sparsity=0.0, contractive_weight=0.0):
+        """One update.  stage 1 reproduces train_epoch's three backward passes (Higashi_wrapper.py:970-1006):
+        gradient of the main loss, gradient of the reconstruction loss, ratio1 = max(beta*|g_main|/|g_recon|,
+        100*median_sparsity - 3), total = alpha*main + ratio1*recon + contractive."""
+        self.n_steps = getattr(self, "n_steps", 0) + 1
+        self.eng.set_dropout(train_mode, seed=0x5EED0000 + self.n_steps)
         self.eng.zero_grad()
         _, loss = self.eng.forward(x, chrom, to_neighs, y=y, w=w, stage=stage, loss_mode=loss_mode)
         self.eng.backward()
+        if alpha != 1.0:
+            self.eng.grads.mul_(alpha)
+        if stage == 1 and self.eng.cell_on_hook:
+            pfx = self.eng.embed_prefix
+            w0 = "%s.wstack.0.weight_list.0" % pfx
+            main_norm = float(self.eng.named_grads()[w0].norm(2))
+            self.recon_loss, recon_norm = self.eng.recon_loss()
+            ratio1 = max(beta * main_norm / max(recon_norm, 1e-30), 100.0 * median_sparsity - 3.0)
+            self.eng.recon_apply(ratio1)
+            if contractive_weight > 0:
+                for name in (w0, "%s.wstack.0.reverse_weight_list.0" % pfx):
+                    self.eng.named_grads()[name].add_(self.eng.named_params()[name], alpha=2.0 * contractive_weight)
         self._local_presence(chrom, stage)
         reduce_gradients(self.eng.grads, self.presence)
         pres = self.presence.cpu().numpy()

@@ -162,6 +162,10 @@ class TrainEngine:
         self.ctx._check(self.ctx.lib.hsg_train_options(self.ctx.h, None if cw is None else cw.ctypes.data_as(C.POINTER(C.c_float)),
                                                        C.c_float(rank_thres)))
 
+    def set_dropout(self, enabled: bool, seed: int = 0):
+        """model.train() / model.eval() for the dropout layers (Modules.py:685-686)."""
+        self.ctx._check(self.ctx.lib.hsg_train_set_dropout(self.ctx.h, 1 if enabled else 0, C.c_uint64(int(seed) & (2 ** 64 - 1))))
+
     def heads(self, B: int, zinb: bool = False):
         """(mean, var, proba, pred) of the last forward batch; var / proba / pred only after a zinb forward."""
         fp = lambda a: a.ctypes.data_as(C.POINTER(C.c_float))

@@ -158,6 +158,9 @@ int  hsg_score_fwd(hsg_ctx* ctx, int stage, int chrom, const int64_t* x_host, in
 /* per-run constants of the loss heads: cell2weight [n_cells] (Higashi_wrapper.py:722,898 `cell_feats1`, zinb mode) and the
  * rank threshold (config `rank_thres`, Higashi_wrapper.py:884).  cell2weight may be NULL.                              */
 int  hsg_train_options(hsg_ctx* ctx, const float* cell2weight_host, float rank_thres);
+/* training-mode dropout (0.3 after fc1/fc2, 0.4 inside pff_n1: Modules.py:685-686); masks are counter-based on `seed`,
+ * identical in hsg_score_fwd and hsg_score_bwd; change the seed every step.  enabled = 0: eval-mode semantics.          */
+int  hsg_train_set_dropout(hsg_ctx* ctx, int enabled, uint64_t seed);
 /* the three heads of the last forward batch (var / proba are produced by loss_mode 2 = zinb only) and, in zinb mode, the
  * clamped mean `pred` that forward_batch_hyperedge returns; host float [B] each, any may be NULL                       */
 int  hsg_score_heads(hsg_ctx* ctx, float* mean_host, float* var_host, float* proba_host, float* pred_host, void* stream);

@@ -179,3 +179,49 @@ def test_stage1_cell_branch_and_reconstruction():
         ref = g["s1/grad_recon/" + name]
         assert float(np.abs(gr[name] - ref).max()) <= 2e-5 * max(1.0, float(np.abs(ref).max()) / 1e-2) + 1e-6, name
     eng.close()
+
+
+def test_dropout_gradient_is_consistent():
+    """Training-mode dropout: with a fixed seed the masks of forward and backward coincide, so the analytic gradient
+    matches a central finite difference of the (dropped-out) loss along a random direction."""
+    g = load("grads_d64.npz")
+    ds = FixtureDataset(g)
+    eng, _ = _train_engine(g, "sd/", ds)
+    tn = (g["indices"], g["values"], g["unique"])
+    eng.set_dropout(True, seed=1234)
+    _, l_drop = eng.forward(g["x"], 0, tn, y=g["y"], w=g["w"], stage=2)
+    eng.set_dropout(False)
+    _, l_eval = eng.forward(g["x"], 0, tn, y=g["y"], w=g["w"], stage=2)
+    assert abs(l_drop - l_eval) > 1e-4                      # dropout really changes the forward
+    eng.set_dropout(True, seed=1234)
+    eng.forward(g["x"], 0, tn, y=g["y"], w=g["w"], stage=2)
+    eng.zero_grad(); eng.backward(); torch.cuda.synchronize()
+    gen = torch.Generator(device="cuda").manual_seed(0)
+    v = torch.randn(eng.total, device="cuda", generator=gen)
+    v /= v.norm()
+    analytic = float((eng.grads.double() * v.double()).sum())
+    eps = 2e-2
+    base = eng.params.clone()
+    eng.params.copy_(base + eps * v); _, lp = eng.forward(g["x"], 0, tn, y=g["y"], w=g["w"], stage=2)
+    eng.params.copy_(base - eps * v); _, lm = eng.forward(g["x"], 0, tn, y=g["y"], w=g["w"], stage=2)
+    eng.params.copy_(base)
+    numeric = (lp - lm) / (2 * eps)
+    assert abs(numeric - analytic) < 0.05 * max(abs(analytic), 1e-3) + 2e-4, (numeric, analytic)
+    eng.close()
+
+
+def test_stage1_trainer_step_runs_and_learns():
+    from higashi_b200 import parallel
+    from higashi_b200.train_engine import TrainEngine
+    g = load("losses_d64.npz")
+    ds = FixtureDataset(g)
+    sd = {k[len("s1/sd/"):]: v for k, v in g.items() if k.startswith("s1/sd/")}
+    eng = TrainEngine(sd, ds.num, ds.feats, ds.cell_feats, device=0, cell_on_hook=True)
+    tr = parallel.DataParallelTrainer(eng, lr=1e-3)
+    losses, recon = [], []
+    for _ in range(8):
+        losses.append(tr.step(g["s1/x"], 0, None, g["s1/y"], g["s1/w"], stage=1, train_mode=False, beta=1e-2,
+                              median_sparsity=0.02, contractive_weight=1e-3))
+        recon.append(tr.recon_loss)
+    assert losses[-1] < losses[0] and recon[-1] < recon[0], (losses, recon)
+    eng.close()
