@@ -7,22 +7,42 @@ columns, normalised weights), so no COO / unique-node relabelling is needed."""
 import numpy as np
 
 
-def neighbor_csr(csr, x, chrom, num_list, training=False, rng=None):
+def _rows_of(csr, cells, chrom, bins):
+    rows = cells * csr.n_bins + int(csr.bin_off[chrom]) + bins
+    lo, hi = csr.row_ptr[rows], csr.row_ptr[rows + 1]
+    cnt = (hi - lo).astype(np.int64)
+    seg = np.repeat(np.arange(len(rows)), cnt)
+    idx = np.arange(int(cnt.sum()), dtype=np.int64) - np.repeat(np.cumsum(cnt) - cnt, cnt) + np.repeat(lo, cnt)
+    return seg, csr.col[idx].astype(np.int64), csr.val[idx].astype(np.float32)
+
+
+def neighbor_csr(csr, x, chrom, num_list, training=False, rng=None, nbr=None, nbr_w=None):
+    """nbr / nbr_w: kNN cell graph ([n_cells, k+1] 1-based ids self first, weights): the token's row is the weighted sum of
+    the neighbour cells' rows with duplicate columns merged (sum_duplicates, Higashi_wrapper.py:224-233, 281-293)."""
     x = np.asarray(x, dtype=np.int64)
     B = len(x)
-    n_bins = csr.n_bins
     base = int(num_list[chrom]) + 1
     cells = np.repeat(x[:, 0] - 1, 2)
     bins = x[:, 1:3].reshape(-1) - base
     partner = x[:, [2, 1]].reshape(-1) - base
-    rows = cells * n_bins + int(csr.bin_off[chrom]) + bins
-    lo, hi = csr.row_ptr[rows], csr.row_ptr[rows + 1]
-    cnt = (hi - lo).astype(np.int64)
-    tot = int(cnt.sum())
-    seg = np.repeat(np.arange(2 * B), cnt)
-    idx = np.arange(tot, dtype=np.int64) - np.repeat(np.cumsum(cnt) - cnt, cnt) + np.repeat(lo, cnt)
-    cols = csr.col[idx].astype(np.int32)
-    vals = csr.val[idx].astype(np.float32)
+    if nbr is None:
+        seg, cols, vals = _rows_of(csr, cells, chrom, bins)
+    else:
+        n = int(csr.bins[chrom])
+        segs, colss, valss = [], [], []
+        for q in range(nbr.shape[1]):
+            sg, cl, vl = _rows_of(csr, nbr[cells, q] - 1, chrom, bins)
+            segs.append(sg); colss.append(cl); valss.append(vl * nbr_w[cells, q][sg])
+        seg, cols, vals = np.concatenate(segs), np.concatenate(colss), np.concatenate(valss)
+        key = seg * n + cols
+        order = np.argsort(key, kind="stable")
+        key, vals = key[order], vals[order]
+        first = np.append(True, key[1:] != key[:-1])
+        vals = np.add.reduceat(vals, np.flatnonzero(first)).astype(np.float32) if len(key) else vals
+        key = key[first]
+        seg, cols = key // n, key % n
+    cnt = np.bincount(seg, minlength=2 * B).astype(np.int64)
+    cols = cols.astype(np.int32)
     if training:
         rng = rng or np.random.default_rng()
         drop_row = (rng.random(2 * B) >= 0.6) & (cnt > 1)

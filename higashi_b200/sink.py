@@ -49,3 +49,20 @@ def read_num(temp_dir):
             return np.asarray(f["num"])
     with np.load(os.path.join(temp_dir, "node_feats.npz")) as f:
         return np.asarray(f["num"])
+
+
+def read_node_feats(temp_dir):
+    """All datasets of `node_feats.hdf5` (Process.py:627,773,781-858) as a flat dict; groups are flattened with '/'
+    (e.g. 'cell/0').  `.npz` twin with the same keys when h5py is unavailable."""
+    p = os.path.join(temp_dir, "node_feats.hdf5")
+    if h5py is not None and os.path.exists(p):
+        out = {}
+
+        def visit(name, obj):
+            if hasattr(obj, "shape"):
+                out[name] = np.asarray(obj)
+        with h5py.File(p, "r") as f:
+            f.visititems(visit)
+        return out
+    with np.load(os.path.join(temp_dir, "node_feats.npz"), allow_pickle=True) as f:
+        return {k: f[k] for k in f.files}

@@ -319,3 +319,54 @@ def random_state_dict(ds: "SynthDataset", d: int, seed: int = 0):
         sd["encode1.static_nn.wstack.%d.weight_list.0" % i] = U(d, f.shape[1], fan_in=f.shape[1])
         sd["encode1.static_nn.wstack.%d.bias_list.0" % i] = U(d, fan_in=f.shape[1])
     return sd, feats
+
+
+def write_temp_dir(ds: "SynthDataset", temp_dir: str, chrom_names=None, test_frac: float = 0.1, seed: int = 0):
+    """Write the files the reference's Process.py leaves in `temp_dir` (its output = the hot path's input contract):
+    node_feats (num, train/test hyperedges + weights per chromosome, sparsity, start_end_dict, extra_cell_feats, cell2weight,
+    bin features "{c}", cell features "cell/{c}"; Process.py:627,773,781-858) as `.npz` (h5py is absent here),
+    `chrom_start_end.npy` and `sparse_nondiag_adj_nbr_1.npy` (object array [C][n_cells] of scipy CSR, Process.py:783-784)."""
+    import os
+    rng = np.random.Generator(np.random.PCG64(seed))
+    os.makedirs(temp_dir, exist_ok=True)
+    C = len(ds.bins)
+    chrom_names = chrom_names or ["chr%d" % (j + 1) for j in range(C)]
+    out = {"num": ds.num}
+    csr, nl = ds.csr, ds.num_list
+    start_end = np.zeros((int(nl[-1]), 2), dtype=np.int64)
+    start_end[:ds.n_cells] = (0, ds.n_cells)
+    reads = np.zeros((ds.n_cells, C))
+    off, cse = 0, []
+    for j, name in enumerate(chrom_names):
+        n = ds.bins[j]
+        start_end[nl[j]:nl[j + 1]] = (nl[j], nl[j + 1])
+        cse.append((off, off + n)); off += n
+        trip, wts = [], []
+        for c in range(ds.n_cells):
+            m = csr.matrix(j, c).tocoo()
+            up = (m.col - m.row) >= 1
+            reads[c, j] = m.data[up].sum()
+            if up.any():
+                trip.append(np.stack([np.full(up.sum(), c + 1), nl[j] + m.row[up] + 1, nl[j] + m.col[up] + 1], axis=-1))
+                wts.append(np.maximum(1.0, np.round(m.data[up])))
+        trip = np.concatenate(trip).astype(np.int64); wts = np.concatenate(wts).astype(np.float32)
+        perm = rng.permutation(len(trip))
+        n_test = max(1, int(test_frac * len(trip)))
+        for tag, idx in (("test", perm[:n_test]), ("train", perm[n_test:])):
+            out["%s_data_%s" % (tag, name)] = trip[idx]
+            out["%s_weight_%s" % (tag, name)] = wts[idx]
+            out["%s_chrom_%s" % (tag, name)] = np.full(len(idx), j, dtype=np.int8)
+        out["%d" % j] = ds.bin_feats[j][:, :-C] if ds.bin_feats else np.eye(n, dtype=np.float32)
+        F = ds.cell_embed_feats.shape[1]
+        w = max(1, F // C)
+        out["cell/%d" % j] = ds.cell_embed_feats[:, j * w:(j + 1) * w if j < C - 1 else F]
+    out["sparsity"] = np.array([(csr.row_ptr[(c + 1) * csr.n_bins] - csr.row_ptr[c * csr.n_bins]) / float(sum(b * b for b in ds.bins))
+                                for c in range(ds.n_cells)])
+    out["start_end_dict"] = start_end
+    out["extra_cell_feats"] = reads
+    out["cell2weight"] = (reads.sum(-1) / max(1e-9, reads.sum(-1).mean())).astype(np.float32)
+    out["distance2weight"] = np.ones(10, dtype=np.float32)
+    np.savez(os.path.join(temp_dir, "node_feats.npz"), **out)
+    np.save(os.path.join(temp_dir, "chrom_start_end.npy"), np.array(cse, dtype=np.int64))
+    np.save(os.path.join(temp_dir, "sparse_nondiag_adj_nbr_1.npy"), csr.to_object_array(), allow_pickle=True)
+    return chrom_names

@@ -1,0 +1,44 @@
+"""End-to-end run of the mirrored `Higashi` orchestrator on a tiny synthetic temp_dir: all three training stages (shortened)
+and both imputations, through the same method names a reference user calls (Higashi_wrapper.py:1643-1652)."""
+import json
+import os
+
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+
+def test_full_pipeline_tiny(tmp_path):
+    from higashi_b200 import sink, synthetic as S
+    from higashi_b200.Higashi_wrapper import Higashi
+    ds = S.make_dataset("C1", n_cells=40, bins=[60, 44], seed=17, density=0.06)
+    chroms = S.write_temp_dir(ds, str(tmp_path))
+    cfg = dict(temp_dir=str(tmp_path), data_dir=str(tmp_path), chrom_list=chroms, impute_list=chroms, resolution=1000000,
+               dimensions=64, neighbor_num=3, loss_mode="zinb", rank_thres=1, embedding_name="emb", gpu_num=1, cpu_num=1,
+               local_transfer_range=1, minimum_distance=1000000, maximum_distance=-1, embedding_epoch=2, no_nbr_epoch=2,
+               with_nbr_epoch=1, impute_verbose=0)
+    cfg_path = str(tmp_path / "config.json")
+    json.dump(cfg, open(cfg_path, "w"))
+    h = Higashi(cfg_path)
+    h.prep_model()
+    h.update_num_per_training_epoch, h.update_num_per_eval_epoch = 12, 2
+    assert h.neg_num == 5 and h.batch_size == 256 * 6
+    h.train_for_embeddings()
+    emb0 = h.fetch_cell_embeddings()
+    assert emb0.shape == (40, 64) and np.isfinite(emb0).all()
+    h.train_for_imputation_nbr_0()
+    h.impute_no_nbr()
+    h.train_for_imputation_with_nbr()
+    h.impute_with_nbr()
+    assert os.path.exists(tmp_path / "weighted_info.npy")
+    for k in (0, 3):
+        for chrom, n in zip(chroms, ds.bins):
+            f = sink.read_container(str(tmp_path), chrom, "emb_nbr_%d_impute" % k)
+            P = n * (n - 1) // 2
+            assert f["coordinates"].shape == (P, 2) and f["coordinates"].dtype == np.int64
+            for cell in (0, 39):
+                v = f["cell_%d" % cell]
+                assert v.shape == (P,) and v.dtype == np.float32 and np.isfinite(v).all() and (v >= 0).all()    # softplus head
+    raw, m0, m3 = h.fetch_map(chroms[0], 5)
+    assert raw.shape == (60, 60) and m0.shape == (60, 60) and abs(m3 - m3.T).max() < 1e-6
