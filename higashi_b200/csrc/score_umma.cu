@@ -51,7 +51,8 @@
 #define CST_COUNT 264
 #define SM_BAR (SM_CONST + CST_COUNT * 4)       // 8 mbarriers
 #define SM_TMEM (SM_BAR + 64)
-#define SM_TOTAL (SM_TMEM + 16)
+#define SM_PAIRS (SM_TMEM + 16)                 // int2 [UM_WG * 128]: (bin_i, bin_j) of every row of the current tiles
+#define SM_TOTAL (SM_PAIRS + UM_WG * 128 * 8)
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
@@ -152,13 +153,76 @@ struct UmmaParams {
     float* out;
 };
 
-// masked 3-token softmax row (Modules.py:948-953) with the diagonal logit forced to 0
+__device__ __forceinline__ float ex2_approx(float x) { float y; asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
+__device__ __forceinline__ float rcp_approx(float x) { float y; asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
+// masked 3-token softmax row (Modules.py:948-953) with the diagonal logit forced to 0:
+// w_a = p_a / (p_a + p_b + 1e-13), p = softmax([0, la, lb])  ==  e_a / (e_a + e_b + 1e-13 (e_0 + e_a + e_b))
 __device__ __forceinline__ void masked_row_fast(float la, float lb, float& wa, float& wb) {
+    const float L2E = 1.4426950408889634f;
     float mx = fmaxf(0.f, fmaxf(la, lb));
-    float e0 = __expf(-mx), ea = __expf(la - mx), eb = __expf(lb - mx);
-    float den = (ea + eb) + 1e-13f * (e0 + ea + eb);
-    float inv = __frcp_rn(den);
+    float e0 = ex2_approx(-mx * L2E), ea = ex2_approx((la - mx) * L2E), eb = ex2_approx((lb - mx) * L2E);
+    float den = fmaf(1e-13f, e0 + ea + eb, ea + eb);
+    float inv = rcp_approx(den);
     wa = ea * inv; wb = eb * inv;
+}
+
+struct UmmaParams;
+// Attention of one token row-tile (fast variant), T = token position (0 cell, 1 bin_i, 2 bin_j): row T attends to the two
+// other tokens.  Lane mapping: lane = (row-in-group rho = lane>>3, head h = lane&7); a warp walks its own 32 rows four at a
+// time, so the 8 lanes of a row read one contiguous 256-byte table row (coalesced).  Each lane owns the two 16-byte chunks
+// of head h; lanes with h >= 4 handle them in swapped order so that the 8 lanes of a quarter-warp hit 8 distinct swizzle
+// slots when storing (no 2-way bank conflict).  s_pr: the (bin_i, bin_j) pairs of this warp's 32 rows in shared memory.
+template <int T>
+__device__ __forceinline__ void attention_fast(const __half* __restrict__ QK16, const float* __restrict__ XS,
+                                               const __half* __restrict__ binV16, const __half* __restrict__ cellV16,
+                                               const int2* s_pr, int lane, int warp_in_wg, uint32_t a_base, uint32_t tokbase, int cell) {
+    const int h = lane & 7, rsub = lane >> 3;
+    const int cA = h * 2 + (h >> 2), cB = h * 2 + 1 - (h >> 2);
+    const uint4* QKh = reinterpret_cast<const uint4*>(QK16) + h * 2;
+    const uint4* BVa = reinterpret_cast<const uint4*>(binV16) + cA;
+    const uint4* BVb = reinterpret_cast<const uint4*>(binV16) + cB;
+    const float* XSh = XS + h + (T == 0 ? 0 : 8);
+    uint4 vc0 = make_uint4(0, 0, 0, 0), vc1 = vc0;
+    if (T != 0) {
+        const uint4* vc = reinterpret_cast<const uint4*>(cellV16) + (uint32_t)cell * 16u;
+        vc0 = __ldg(vc + cA); vc1 = __ldg(vc + cB);
+    }
+#pragma unroll 2
+    for (int it = 0; it < 8; ++it) {
+        const int rw = it * 4 + rsub;
+        const int2 pr = s_pr[rw];
+        const uint32_t ti = tokbase + (uint32_t)pr.x, tj = tokbase + (uint32_t)pr.y;
+        float la, lb;
+        uint4 a0, a1, b0, b1;
+        if (T == 0) {
+            la = __ldg(XSh + ti * 16u); lb = __ldg(XSh + tj * 16u);
+            a0 = __ldg(BVa + (uint32_t)pr.x * 16u); a1 = __ldg(BVb + (uint32_t)pr.x * 16u);
+            b0 = __ldg(BVa + (uint32_t)pr.y * 16u); b1 = __ldg(BVb + (uint32_t)pr.y * 16u);
+        } else {
+            const uint32_t tq = (T == 1) ? ti : tj, tk = (T == 1) ? tj : ti, bv = (uint32_t)((T == 1) ? pr.y : pr.x);
+            la = __ldg(XSh + tq * 16u);
+            const uint4 q0 = __ldg(QKh + tq * 32u), q1 = __ldg(QKh + tq * 32u + 1);
+            const uint4 k0 = __ldg(QKh + tk * 32u + 16), k1 = __ldg(QKh + tk * 32u + 17);
+            b0 = __ldg(BVa + bv * 16u); b1 = __ldg(BVb + bv * 16u);
+            a0 = vc0; a1 = vc1;
+            __half2 acc = __hmul2(u2h(q0.x), u2h(k0.x)), acc2 = __hmul2(u2h(q1.x), u2h(k1.x));
+            acc = __hfma2(u2h(q0.y), u2h(k0.y), acc); acc2 = __hfma2(u2h(q1.y), u2h(k1.y), acc2);
+            acc = __hfma2(u2h(q0.z), u2h(k0.z), acc); acc2 = __hfma2(u2h(q1.z), u2h(k1.z), acc2);
+            acc = __hfma2(u2h(q0.w), u2h(k0.w), acc); acc2 = __hfma2(u2h(q1.w), u2h(k1.w), acc2);
+            float2 f = __half22float2(__hadd2(acc, acc2));
+            lb = (f.x + f.y) * 0.25f;
+        }
+        float wa, wb;
+        masked_row_fast(la, lb, wa, wb);
+        const __half2 wa2 = __float2half2_rn(wa), wb2 = __float2half2_rn(wb);
+        const int arow = warp_in_wg * 32 + rw;
+        sts128(a_chunk_addr(a_base, arow, cA),
+               h2u(__hfma2(wb2, u2h(b0.x), __hmul2(wa2, u2h(a0.x)))), h2u(__hfma2(wb2, u2h(b0.y), __hmul2(wa2, u2h(a0.y)))),
+               h2u(__hfma2(wb2, u2h(b0.z), __hmul2(wa2, u2h(a0.z)))), h2u(__hfma2(wb2, u2h(b0.w), __hmul2(wa2, u2h(a0.w)))));
+        sts128(a_chunk_addr(a_base, arow, cB),
+               h2u(__hfma2(wb2, u2h(b1.x), __hmul2(wa2, u2h(a1.x)))), h2u(__hfma2(wb2, u2h(b1.y), __hmul2(wa2, u2h(a1.y)))),
+               h2u(__hfma2(wb2, u2h(b1.z), __hmul2(wa2, u2h(a1.z)))), h2u(__hfma2(wb2, u2h(b1.w), __hmul2(wa2, u2h(a1.w)))));
+    }
 }
 
 // NK k-steps of one [128 x N] += A[128 x 16NK] . B[N x 16NK]^T ; A / B tiles in K-major SWIZZLE_128B
@@ -228,6 +292,10 @@ __global__ void __launch_bounds__(UM_THREADS, 1) score_umma_kernel(UmmaParams p)
         const bool valid = pi < p.P;
         const int2 pr = p.pairs[valid ? pi : (p.P - 1)];
         const float bias = valid ? p.pair_bias[pi] : 0.f;
+        int2* s_pr = reinterpret_cast<int2*>(smem + SM_PAIRS) + wg * 128 + warp_in_wg * 32;    // this warp's 32 rows
+        __syncwarp();
+        s_pr[lane] = pr;
+        __syncwarp();
         const int cell = p.cell_start + cb;
         float osum = 0.f;
 
@@ -287,83 +355,11 @@ __global__ void __launch_bounds__(UM_THREADS, 1) score_umma_kernel(UmmaParams p)
                     sts128(a_chunk_addr(a_base, arow, cA), sw ? pk[4] : pk[0], sw ? pk[5] : pk[1], sw ? pk[6] : pk[2], sw ? pk[7] : pk[3]);
                     sts128(a_chunk_addr(a_base, arow, cB), sw ? pk[0] : pk[4], sw ? pk[1] : pk[5], sw ? pk[2] : pk[6], sw ? pk[3] : pk[7]);
                 }
-            } else
-            {
-                const int h = lane & 7, rsub = lane >> 3;
-                // each lane owns the two 16-byte chunks of head h; lanes with h >= 4 handle them in swapped order so that
-                // the 8 lanes of a quarter-warp hit 8 distinct swizzle slots when storing (no 2-way bank conflict)
-                const int cA = h * 2 + (h >> 2), cB = h * 2 + 1 - (h >> 2);
-                const uint4* QK4 = reinterpret_cast<const uint4*>(p.QK16);
-                const uint4* BV4 = reinterpret_cast<const uint4*>(p.binV16);
+            } else {
                 const uint32_t tokbase = (uint32_t)cb * (uint32_t)p.n_bins;
-                uint4 vc0 = make_uint4(0, 0, 0, 0), vc1 = vc0;        // V of the cell token, head h (t = 1, 2)
-                if (t != 0) {
-                    const uint4* vc = reinterpret_cast<const uint4*>(p.cellV16) + (uint32_t)cell * 16u + h * 2;
-                    vc0 = __ldg(vc + (cA - h * 2)); vc1 = __ldg(vc + (cB - h * 2));
-                }
-                struct AttLoad { uint4 q0, q1, k0, k1, a0, a1, b0, b1; float la, lb; };
-                AttLoad L[2];
-                auto issue_loads = [&](int it, AttLoad& X) {
-                    const int rw = it * 4 + rsub;
-                    const uint32_t bi_r = (uint32_t)__shfl_sync(0xffffffffu, pr.x, rw), bj_r = (uint32_t)__shfl_sync(0xffffffffu, pr.y, rw);
-                    const uint32_t ti = tokbase + bi_r, tj = tokbase + bj_r;
-                    if (t == 0) {
-                        X.la = __ldg(p.XS + ti * 16u + h);
-                        X.lb = __ldg(p.XS + tj * 16u + h);
-                        X.a0 = __ldg(BV4 + bi_r * 16u + cA); X.a1 = __ldg(BV4 + bi_r * 16u + cB);
-                        X.b0 = __ldg(BV4 + bj_r * 16u + cA); X.b1 = __ldg(BV4 + bj_r * 16u + cB);
-                    } else {
-                        const uint32_t tq = (t == 1) ? ti : tj, tk = (t == 1) ? tj : ti, bv = (t == 1) ? bj_r : bi_r;
-                        X.la = __ldg(p.XS + tq * 16u + 8 + h);
-                        X.q0 = __ldg(QK4 + tq * 32u + h * 2); X.q1 = __ldg(QK4 + tq * 32u + h * 2 + 1);
-                        X.k0 = __ldg(QK4 + tk * 32u + 16 + h * 2); X.k1 = __ldg(QK4 + tk * 32u + 16 + h * 2 + 1);
-                        X.b0 = __ldg(BV4 + bv * 16u + cA); X.b1 = __ldg(BV4 + bv * 16u + cB);
-                    }
-                };
-                auto compute = [&](int it, const AttLoad& X) {
-                    float lb = X.lb;
-                    uint4 a0 = X.a0, a1 = X.a1;
-                    if (t != 0) {
-                        __half2 acc = __hmul2(u2h(X.q0.x), u2h(X.k0.x)), acc2 = __hmul2(u2h(X.q1.x), u2h(X.k1.x));
-                        acc = __hfma2(u2h(X.q0.y), u2h(X.k0.y), acc); acc2 = __hfma2(u2h(X.q1.y), u2h(X.k1.y), acc2);
-                        acc = __hfma2(u2h(X.q0.z), u2h(X.k0.z), acc); acc2 = __hfma2(u2h(X.q1.z), u2h(X.k1.z), acc2);
-                        acc = __hfma2(u2h(X.q0.w), u2h(X.k0.w), acc); acc2 = __hfma2(u2h(X.q1.w), u2h(X.k1.w), acc2);
-                        float2 f = __half22float2(acc), f2_ = __half22float2(acc2);
-                        lb = ((f.x + f.y) + (f2_.x + f2_.y)) * 0.25f;
-                        a0 = vc0; a1 = vc1;
-                    }
-                    float wa, wb;
-                    masked_row_fast(X.la, lb, wa, wb);
-                    const __half2 wa2 = __float2half2_rn(wa), wb2 = __float2half2_rn(wb);
-                    const int arow = warp_in_wg * 32 + it * 4 + rsub;
-                    uint32_t c0 = h2u(__hfma2(wb2, u2h(X.b0.x), __hmul2(wa2, u2h(a0.x))));
-                    uint32_t c1 = h2u(__hfma2(wb2, u2h(X.b0.y), __hmul2(wa2, u2h(a0.y))));
-                    uint32_t c2 = h2u(__hfma2(wb2, u2h(X.b0.z), __hmul2(wa2, u2h(a0.z))));
-                    uint32_t c3 = h2u(__hfma2(wb2, u2h(X.b0.w), __hmul2(wa2, u2h(a0.w))));
-                    sts128(a_chunk_addr(a_base, arow, cA), c0, c1, c2, c3);
-                    c0 = h2u(__hfma2(wb2, u2h(X.b1.x), __hmul2(wa2, u2h(a1.x))));
-                    c1 = h2u(__hfma2(wb2, u2h(X.b1.y), __hmul2(wa2, u2h(a1.y))));
-                    c2 = h2u(__hfma2(wb2, u2h(X.b1.z), __hmul2(wa2, u2h(a1.z))));
-                    c3 = h2u(__hfma2(wb2, u2h(X.b1.w), __hmul2(wa2, u2h(a1.w))));
-                    sts128(a_chunk_addr(a_base, arow, cB), c0, c1, c2, c3);
-                };
-                // software pipeline, two rows-groups per trip: the next group's loads are in flight while one computes
-#if UM_ATT_PREFETCH
-                issue_loads(0, L[0]);
-#pragma unroll 1
-                for (int it = 0; it < 8; it += 2) {
-                    issue_loads(it + 1, L[1]);
-                    compute(it, L[0]);
-                    if (it + 2 < 8) issue_loads(it + 2, L[0]);
-                    compute(it + 1, L[1]);
-                }
-#else
-#pragma unroll 2
-                for (int it = 0; it < 8; ++it) {
-                    issue_loads(it, L[0]);
-                    compute(it, L[0]);
-                }
-#endif
+                if (t == 0) attention_fast<0>(p.QK16, p.XS, p.binV16, p.cellV16, s_pr, lane, warp_in_wg, a_base, tokbase, cell);
+                else if (t == 1) attention_fast<1>(p.QK16, p.XS, p.binV16, p.cellV16, s_pr, lane, warp_in_wg, a_base, tokbase, cell);
+                else attention_fast<2>(p.QK16, p.XS, p.binV16, p.cellV16, s_pr, lane, warp_in_wg, a_base, tokbase, cell);
             }
             if constexpr (HI) {
                 ISSUE_BEGIN()
