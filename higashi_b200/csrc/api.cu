@@ -1,6 +1,7 @@
 // api.cu -- the C ABI of libhsg.so (declared in include/hsg.h): context, uploads, preparation and the
 // imputation driver that strings K1a -> K1b -> K2 over batches of cells.
 #include <algorithm>
+#include <cstdlib>
 #include <cstring>
 #include <cub/cub.cuh>
 

@@ -17,236 +17,7 @@
 //     kernel is the 4-byte score per triplet, token tables are read through L1/L2.
 // Operands are fp16, not bf16: with bf16 operands the measured score error is 1.5e-3..2e-3 (above the 1e-3
 // parity bar), with fp16 it is 2.4e-4 at identical tensor throughput (scripts/bf16_emulation.py).
-#include <cuda_fp16.h>
-
-#include <cstring>
-#include <vector>
-
-#include "common.cuh"
-
-#define UM_WG 4
-#define UM_THREADS (UM_WG * 128)
-#define UM_D 64
-#ifndef UM_ATT_PREFETCH
-#define UM_ATT_PREFETCH 0
-#endif
-
-// shared memory map (bytes)
-#define SM_B_FC1 0            // [64 x 128] fp16, 2 K-atoms of 8 KB
-#define SM_B_W0 16384         // [64 x 64]
-#define SM_B_W1 24576         // [64 x 64]
-#define SM_B_C0 32768         // [32 x 64]
-#define SM_B_FC1_LO 36864      // low halves (w - fp16(w)) of fc1 and C0 for the high-accuracy variant
-#define SM_B_C0_LO 53248
-#define SM_WIMG_BYTES 57344
-#define SM_A0 57344           // 4 x 32 KB A buffers (one per warpgroup)
-#define SM_A_BYTES 32768
-#define SM_CONST (SM_A0 + UM_WG * SM_A_BYTES)   // fp32 constants
-#define CST_B0F 0
-#define CST_B1 64
-#define CST_G1 128
-#define CST_CB0 192
-#define CST_CW1 224
-#define CST_CB1 256
-#define CST_COUNT 264
-#define SM_BAR (SM_CONST + CST_COUNT * 4)       // 8 mbarriers
-#define SM_TMEM (SM_BAR + 64)
-#define SM_PAIRS (SM_TMEM + 16)                 // int2 [UM_WG * 128]: (bin_i, bin_j) of every row of the current tiles
-#define SM_TOTAL (SM_PAIRS + UM_WG * 128 * 8)
-
-__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
-
-__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
-    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
-}
-__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
-    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
-    uint32_t ok;
-    do {
-        asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\tselp.u32 %0, 1, 0, p;\n\t}"
-                     : "=r"(ok) : "r"(bar), "r"(parity), "r"(0x989680u) : "memory");
-    } while (!ok);
-}
-__device__ __forceinline__ void tma_bulk_g2s(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
-    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
-                 ::"r"(dst), "l"(src), "r"(bytes), "r"(bar) : "memory");
-}
-__device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
-__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
-__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
-__device__ __forceinline__ void wg_bar(int wg) { asm volatile("bar.sync %0, 128;" ::"r"(wg + 1) : "memory"); }
-
-// K-major, SWIZZLE_128B shared-memory matrix descriptor (cute::UMMA::SmemDescriptor bit layout):
-// start>>4 [0,14) | LBO>>4 [16,30) (unused for swizzled K-major, 1) | SBO>>4 [32,46) = 1024 B between
-// 8-row groups | version=1 [46,48) | layout_type=2 (SWIZZLE_128B) [61,64)
-__device__ __forceinline__ uint64_t umma_desc(uint32_t saddr) {
-    return (uint64_t)((saddr >> 4) & 0x3FFF) | (1ull << 16) | ((uint64_t)(1024 >> 4) << 32) | (1ull << 46) | (2ull << 61);
-}
-// instruction descriptor kind::f16: D=f32 (1<<4), A=B=f16 (0<<7, 0<<10), K-major both, N>>3 at 17, M>>4 at 24
-__host__ __device__ constexpr uint32_t umma_idesc_f16(int M, int N) {
-    return (1u << 4) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
-}
-__device__ __forceinline__ void umma_f16(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accum) {
-    asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\ttcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
-                 ::"r"(d_tmem), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accum) : "memory");
-}
-__device__ __forceinline__ void umma_commit(uint32_t bar) {
-    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
-}
-
-#define TMEM_LD_ARGS16(r, o) "=r"(r[o + 0]), "=r"(r[o + 1]), "=r"(r[o + 2]), "=r"(r[o + 3]), "=r"(r[o + 4]), "=r"(r[o + 5]),   \
-    "=r"(r[o + 6]), "=r"(r[o + 7]), "=r"(r[o + 8]), "=r"(r[o + 9]), "=r"(r[o + 10]), "=r"(r[o + 11]), "=r"(r[o + 12]),         \
-    "=r"(r[o + 13]), "=r"(r[o + 14]), "=r"(r[o + 15])
-
-// 32 lanes x 32 columns -> 32 registers per thread
-__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
-    asm volatile(
-        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
-        "{%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,%29,%30,%31}, [%32];"
-        : TMEM_LD_ARGS16(r, 0), TMEM_LD_ARGS16(r, 16) : "r"(taddr) : "memory");
-}
-__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
-
-__device__ __forceinline__ float fast_tanh(float x) {
-    float y;
-    asm("tanh.approx.f32 %0, %1;" : "=f"(y) : "f"(x));
-    return y;
-}
-// swish(x) = x * sigmoid(x) = x * (0.5 + 0.5 tanh(x/2)).  The GEMMs that feed a swish carry the factor 1/2 in
-// their (pre-scaled) weights and biases, so the epilogue sees w = x/2 and swish(x) = w + w tanh(w): MUFU + FFMA.
-__device__ __forceinline__ float swish_half(float w) { return fmaf(w, fast_tanh(w), w); }
-
-// row r of a [128 x K] fp16 A tile, 16-byte chunk `c` (8 halves), K-major SWIZZLE_128B
-__device__ __forceinline__ uint32_t a_chunk_addr(uint32_t a_base, int r, int c) {
-    return a_base + (uint32_t)(c >> 3) * 16384u + (uint32_t)(r >> 3) * 1024u + (uint32_t)(r & 7) * 128u +
-           (uint32_t)(((c & 7) ^ (r & 7)) << 4);
-}
-__device__ __forceinline__ void sts128(uint32_t addr, uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
-    asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(a), "r"(b), "r"(c), "r"(d) : "memory");
-}
-__device__ __forceinline__ uint32_t pack_h2(float a, float b) {
-    __half2 h = __floats2half2_rn(a, b);
-    return *reinterpret_cast<uint32_t*>(&h);
-}
-__device__ __forceinline__ float2 f2(uint32_t a, uint32_t b) { return make_float2(__uint_as_float(a), __uint_as_float(b)); }
-__device__ __forceinline__ __half2 u2h(uint32_t u) { return *reinterpret_cast<__half2*>(&u); }
-__device__ __forceinline__ uint32_t h2u(__half2 h) { return *reinterpret_cast<uint32_t*>(&h); }
-
-struct UmmaParams {
-    // 16-bit token tables
-    const __half* QK16;      // [slot][n_bins][256]  Q then K
-    const float* XS;         // [slot][n_bins][16]   qcK[8] = Q_cell.K_b/4, kcQ[8] = Q_b.K_cell/4 per head
-    const __half* binV16;    // [n_bins][128]
-    const float* binSb;      // [64][n_bins]   feature-major: layer_norm2(fc2 V) - beta(layer_norm1)
-    const __half* cellV16;   // [n_cells][128]
-    // high-accuracy variant: fp32 token tables (Q/K per (cell, bin), V per bin / cell)
-    const float* QK32;       // [slot][n_bins][2][128]
-    const float* binV32;     // [n_bins][128]
-    const float* cellV32;    // [n_cells][128]
-    const float* cellSb;     // [64][n_cells]  feature-major
-    const unsigned char* wimg;   // SM_WIMG_BYTES pre-swizzled fp16 weight images
-    float cst[CST_COUNT];        // fp32 constants, by value: they become constant-bank operands of the epilogue math
-    const int2* pairs; const float* pair_bias; long long P;
-    int n_bins, n_cells, cell_start, n_batch, tiles_per_cell, act;
-    float* out;
-};
-
-__device__ __forceinline__ float ex2_approx(float x) { float y; asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
-__device__ __forceinline__ float rcp_approx(float x) { float y; asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
-// masked 3-token softmax row (Modules.py:948-953) with the diagonal logit forced to 0:
-// w_a = p_a / (p_a + p_b + 1e-13), p = softmax([0, la, lb])  ==  e_a / (e_a + e_b + 1e-13 (e_0 + e_a + e_b))
-__device__ __forceinline__ void masked_row_fast(float la, float lb, float& wa, float& wb) {
-    const float L2E = 1.4426950408889634f;
-    float mx = fmaxf(0.f, fmaxf(la, lb));
-    float e0 = ex2_approx(-mx * L2E), ea = ex2_approx((la - mx) * L2E), eb = ex2_approx((lb - mx) * L2E);
-    float den = fmaf(1e-13f, e0 + ea + eb, ea + eb);
-    float inv = rcp_approx(den);
-    wa = ea * inv; wb = eb * inv;
-}
-
-struct UmmaParams;
-// Attention of one token row-tile (fast variant), T = token position (0 cell, 1 bin_i, 2 bin_j): row T attends to the two
-// other tokens.  Lane mapping: lane = (row-in-group rho = lane>>3, head h = lane&7); a warp walks its own 32 rows four at a
-// time, so the 8 lanes of a row read one contiguous 256-byte table row (coalesced).  Each lane owns the two 16-byte chunks
-// of head h; lanes with h >= 4 handle them in swapped order so that the 8 lanes of a quarter-warp hit 8 distinct swizzle
-// slots when storing (no 2-way bank conflict).  s_pr: the (bin_i, bin_j) pairs of this warp's 32 rows in shared memory.
-template <int T>
-__device__ __forceinline__ void attention_fast(const __half* __restrict__ QK16, const float* __restrict__ XS,
-                                               const __half* __restrict__ binV16, const __half* __restrict__ cellV16,
-                                               const int2* s_pr, int lane, int warp_in_wg, uint32_t a_base, uint32_t tokbase, int cell) {
-    const int h = lane & 7, rsub = lane >> 3;
-    const int cA = h * 2 + (h >> 2), cB = h * 2 + 1 - (h >> 2);
-    const uint4* QKh = reinterpret_cast<const uint4*>(QK16) + h * 2;
-    const uint4* BVa = reinterpret_cast<const uint4*>(binV16) + cA;
-    const uint4* BVb = reinterpret_cast<const uint4*>(binV16) + cB;
-    const float* XSh = XS + h + (T == 0 ? 0 : 8);
-    uint4 vc0 = make_uint4(0, 0, 0, 0), vc1 = vc0;
-    if (T != 0) {
-        const uint4* vc = reinterpret_cast<const uint4*>(cellV16) + (uint32_t)cell * 16u;
-        vc0 = __ldg(vc + cA); vc1 = __ldg(vc + cB);
-    }
-#pragma unroll 2
-    for (int it = 0; it < 8; ++it) {
-        const int rw = it * 4 + rsub;
-        const int2 pr = s_pr[rw];
-        const uint32_t ti = tokbase + (uint32_t)pr.x, tj = tokbase + (uint32_t)pr.y;
-        float la, lb;
-        uint4 a0, a1, b0, b1;
-        if (T == 0) {
-            la = __ldg(XSh + ti * 16u); lb = __ldg(XSh + tj * 16u);
-            a0 = __ldg(BVa + (uint32_t)pr.x * 16u); a1 = __ldg(BVb + (uint32_t)pr.x * 16u);
-            b0 = __ldg(BVa + (uint32_t)pr.y * 16u); b1 = __ldg(BVb + (uint32_t)pr.y * 16u);
-        } else {
-            const uint32_t tq = (T == 1) ? ti : tj, tk = (T == 1) ? tj : ti, bv = (uint32_t)((T == 1) ? pr.y : pr.x);
-            la = __ldg(XSh + tq * 16u);
-            const uint4 q0 = __ldg(QKh + tq * 32u), q1 = __ldg(QKh + tq * 32u + 1);
-            const uint4 k0 = __ldg(QKh + tk * 32u + 16), k1 = __ldg(QKh + tk * 32u + 17);
-            b0 = __ldg(BVa + bv * 16u); b1 = __ldg(BVb + bv * 16u);
-            a0 = vc0; a1 = vc1;
-            __half2 acc = __hmul2(u2h(q0.x), u2h(k0.x)), acc2 = __hmul2(u2h(q1.x), u2h(k1.x));
-            acc = __hfma2(u2h(q0.y), u2h(k0.y), acc); acc2 = __hfma2(u2h(q1.y), u2h(k1.y), acc2);
-            acc = __hfma2(u2h(q0.z), u2h(k0.z), acc); acc2 = __hfma2(u2h(q1.z), u2h(k1.z), acc2);
-            acc = __hfma2(u2h(q0.w), u2h(k0.w), acc); acc2 = __hfma2(u2h(q1.w), u2h(k1.w), acc2);
-            float2 f = __half22float2(__hadd2(acc, acc2));
-            lb = (f.x + f.y) * 0.25f;
-        }
-        float wa, wb;
-        masked_row_fast(la, lb, wa, wb);
-        const __half2 wa2 = __float2half2_rn(wa), wb2 = __float2half2_rn(wb);
-        const int arow = warp_in_wg * 32 + rw;
-        sts128(a_chunk_addr(a_base, arow, cA),
-               h2u(__hfma2(wb2, u2h(b0.x), __hmul2(wa2, u2h(a0.x)))), h2u(__hfma2(wb2, u2h(b0.y), __hmul2(wa2, u2h(a0.y)))),
-               h2u(__hfma2(wb2, u2h(b0.z), __hmul2(wa2, u2h(a0.z)))), h2u(__hfma2(wb2, u2h(b0.w), __hmul2(wa2, u2h(a0.w)))));
-        sts128(a_chunk_addr(a_base, arow, cB),
-               h2u(__hfma2(wb2, u2h(b1.x), __hmul2(wa2, u2h(a1.x)))), h2u(__hfma2(wb2, u2h(b1.y), __hmul2(wa2, u2h(a1.y)))),
-               h2u(__hfma2(wb2, u2h(b1.z), __hmul2(wa2, u2h(a1.z)))), h2u(__hfma2(wb2, u2h(b1.w), __hmul2(wa2, u2h(a1.w)))));
-    }
-}
-
-// NK k-steps of one [128 x N] += A[128 x 16NK] . B[N x 16NK]^T ; A / B tiles in K-major SWIZZLE_128B
-template <int NK, int N>
-__device__ __forceinline__ void mma_group(uint32_t a_base, uint32_t b_base, int b_rows, uint32_t d_tmem, uint32_t accum_first) {
-    constexpr uint32_t idesc = umma_idesc_f16(128, N);
-#pragma unroll
-    for (int k = 0; k < NK; ++k) {
-        uint32_t aoff = (uint32_t)(k >> 2) * 16384u + (uint32_t)(k & 3) * 32u;
-        uint32_t boff = (uint32_t)(k >> 2) * (uint32_t)(b_rows * 128) + (uint32_t)(k & 3) * 32u;
-        umma_f16(d_tmem, umma_desc(a_base + aoff), umma_desc(b_base + boff), idesc, (k > 0) ? 1u : accum_first);
-    }
-}
-// one MMA round trip for a warpgroup: the A tile is complete in shared memory.  Generic-proxy writes of the A tile are
-// made visible to the tensor core (async proxy), the warpgroup syncs, one thread issues and commits to the mbarrier.
-#define ISSUE_BEGIN() fence_async_smem(); tc_fence_before(); wg_bar(wg); if (wtid == 0) { tc_fence_after();
-#define ISSUE_END() umma_commit(bar_mma); }
-template <int NK, int N>
-__device__ __forceinline__ void issue_gemm(int wg, int wtid, uint32_t a_base, uint32_t b_base, int b_rows, uint32_t d_tmem,
-                                           uint32_t accum_first, uint32_t bar_mma) {
-    ISSUE_BEGIN()
-    mma_group<NK, N>(a_base, b_base, b_rows, d_tmem, accum_first);
-    ISSUE_END()
-}
+#include "umma_common.cuh"
 
 template <bool HI>
 __global__ void __launch_bounds__(UM_THREADS, 1) score_umma_kernel(UmmaParams p) {
@@ -292,9 +63,9 @@ __global__ void __launch_bounds__(UM_THREADS, 1) score_umma_kernel(UmmaParams p)
         const bool valid = pi < p.P;
         const int2 pr = p.pairs[valid ? pi : (p.P - 1)];
         const float bias = valid ? p.pair_bias[pi] : 0.f;
-        int2* s_pr = reinterpret_cast<int2*>(smem + SM_PAIRS) + wg * 128 + warp_in_wg * 32;    // this warp's 32 rows
+        int2* s_pr_wg = reinterpret_cast<int2*>(smem + SM_PAIRS) + wg * 128;    // rows of this warpgroup's tile
         __syncwarp();
-        s_pr[lane] = pr;
+        s_pr_wg[wtid] = pr;                                                      // a warp only reads its own 32 rows
         __syncwarp();
         const int cell = p.cell_start + cb;
         float osum = 0.f;
@@ -357,9 +128,9 @@ __global__ void __launch_bounds__(UM_THREADS, 1) score_umma_kernel(UmmaParams p)
                 }
             } else {
                 const uint32_t tokbase = (uint32_t)cb * (uint32_t)p.n_bins;
-                if (t == 0) attention_fast<0>(p.QK16, p.XS, p.binV16, p.cellV16, s_pr, lane, warp_in_wg, a_base, tokbase, cell);
-                else if (t == 1) attention_fast<1>(p.QK16, p.XS, p.binV16, p.cellV16, s_pr, lane, warp_in_wg, a_base, tokbase, cell);
-                else attention_fast<2>(p.QK16, p.XS, p.binV16, p.cellV16, s_pr, lane, warp_in_wg, a_base, tokbase, cell);
+                if (t == 0) attention_fast<0, 8>(p.QK16, p.XS, p.binV16, p.cellV16, s_pr_wg, lane, warp_in_wg * 32, a_base, tokbase, cell);
+                else if (t == 1) attention_fast<1, 8>(p.QK16, p.XS, p.binV16, p.cellV16, s_pr_wg, lane, warp_in_wg * 32, a_base, tokbase, cell);
+                else attention_fast<2, 8>(p.QK16, p.XS, p.binV16, p.cellV16, s_pr_wg, lane, warp_in_wg * 32, a_base, tokbase, cell);
             }
             if constexpr (HI) {
                 ISSUE_BEGIN()

@@ -1,0 +1,241 @@
+// umma_common.cuh -- tcgen05 / TMEM / mbarrier helpers, shared-memory map and parameter block shared by the tensor-core
+// scorer kernels (score_umma.cu: one thread per row; score_umma2.cu: two threads per row).
+#pragma once
+#include <cuda_fp16.h>
+
+#include <cstring>
+#include <vector>
+
+#include "common.cuh"
+
+#define UM_WG 4
+#define UM_THREADS (UM_WG * 128)
+#define UM_D 64
+#ifndef UM_ATT_PREFETCH
+#define UM_ATT_PREFETCH 0
+#endif
+
+// shared memory map (bytes)
+#define SM_B_FC1 0            // [64 x 128] fp16, 2 K-atoms of 8 KB
+#define SM_B_W0 16384         // [64 x 64]
+#define SM_B_W1 24576         // [64 x 64]
+#define SM_B_C0 32768         // [32 x 64]
+#define SM_B_FC1_LO 36864      // low halves (w - fp16(w)) of fc1 and C0 for the high-accuracy variant
+#define SM_B_C0_LO 53248
+#define SM_WIMG_BYTES 57344
+#define SM_A0 57344           // 4 x 32 KB A buffers (one per warpgroup)
+#define SM_A_BYTES 32768
+#define SM_CONST (SM_A0 + UM_WG * SM_A_BYTES)   // fp32 constants
+#define CST_B0F 0
+#define CST_B1 64
+#define CST_G1 128
+#define CST_CB0 192
+#define CST_CW1 224
+#define CST_CB1 256
+#define CST_COUNT 264
+#define SM_BAR (SM_CONST + CST_COUNT * 4)       // 8 mbarriers
+#define SM_TMEM (SM_BAR + 64)
+#define SM_PAIRS (SM_TMEM + 16)                 // int2 [UM_WG * 128]: (bin_i, bin_j) of every row of the current tiles
+#define SM_TOTAL (SM_PAIRS + UM_WG * 128 * 8)
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+    uint32_t ok;
+    do {
+        asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+                     : "=r"(ok) : "r"(bar), "r"(parity), "r"(0x989680u) : "memory");
+    } while (!ok);
+}
+__device__ __forceinline__ void tma_bulk_g2s(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(dst), "l"(src), "r"(bytes), "r"(bar) : "memory");
+}
+__device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void wg_bar(int wg) { asm volatile("bar.sync %0, 128;" ::"r"(wg + 1) : "memory"); }
+
+// K-major, SWIZZLE_128B shared-memory matrix descriptor (cute::UMMA::SmemDescriptor bit layout):
+// start>>4 [0,14) | LBO>>4 [16,30) (unused for swizzled K-major, 1) | SBO>>4 [32,46) = 1024 B between
+// 8-row groups | version=1 [46,48) | layout_type=2 (SWIZZLE_128B) [61,64)
+__device__ __forceinline__ uint64_t umma_desc(uint32_t saddr) {
+    return (uint64_t)((saddr >> 4) & 0x3FFF) | (1ull << 16) | ((uint64_t)(1024 >> 4) << 32) | (1ull << 46) | (2ull << 61);
+}
+// instruction descriptor kind::f16: D=f32 (1<<4), A=B=f16 (0<<7, 0<<10), K-major both, N>>3 at 17, M>>4 at 24
+__host__ __device__ constexpr uint32_t umma_idesc_f16(int M, int N) {
+    return (1u << 4) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
+}
+__device__ __forceinline__ void umma_f16(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accum) {
+    asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\ttcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+                 ::"r"(d_tmem), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accum) : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint32_t bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+
+#define TMEM_LD_ARGS16(r, o) "=r"(r[o + 0]), "=r"(r[o + 1]), "=r"(r[o + 2]), "=r"(r[o + 3]), "=r"(r[o + 4]), "=r"(r[o + 5]),   \
+    "=r"(r[o + 6]), "=r"(r[o + 7]), "=r"(r[o + 8]), "=r"(r[o + 9]), "=r"(r[o + 10]), "=r"(r[o + 11]), "=r"(r[o + 12]),         \
+    "=r"(r[o + 13]), "=r"(r[o + 14]), "=r"(r[o + 15])
+
+// 32 lanes x 32 columns -> 32 registers per thread
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+        "{%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,%29,%30,%31}, [%32];"
+        : TMEM_LD_ARGS16(r, 0), TMEM_LD_ARGS16(r, 16) : "r"(taddr) : "memory");
+}
+__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+
+__device__ __forceinline__ float fast_tanh(float x) {
+    float y;
+    asm("tanh.approx.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
+}
+// swish(x) = x * sigmoid(x) = x * (0.5 + 0.5 tanh(x/2)).  The GEMMs that feed a swish carry the factor 1/2 in
+// their (pre-scaled) weights and biases, so the epilogue sees w = x/2 and swish(x) = w + w tanh(w): MUFU + FFMA.
+__device__ __forceinline__ float swish_half(float w) { return fmaf(w, fast_tanh(w), w); }
+
+// row r of a [128 x K] fp16 A tile, 16-byte chunk `c` (8 halves), K-major SWIZZLE_128B
+__device__ __forceinline__ uint32_t a_chunk_addr(uint32_t a_base, int r, int c) {
+    return a_base + (uint32_t)(c >> 3) * 16384u + (uint32_t)(r >> 3) * 1024u + (uint32_t)(r & 7) * 128u +
+           (uint32_t)(((c & 7) ^ (r & 7)) << 4);
+}
+__device__ __forceinline__ void sts128(uint32_t addr, uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
+    asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(a), "r"(b), "r"(c), "r"(d) : "memory");
+}
+__device__ __forceinline__ uint32_t pack_h2(float a, float b) {
+    __half2 h = __floats2half2_rn(a, b);
+    return *reinterpret_cast<uint32_t*>(&h);
+}
+__device__ __forceinline__ float2 f2(uint32_t a, uint32_t b) { return make_float2(__uint_as_float(a), __uint_as_float(b)); }
+__device__ __forceinline__ __half2 u2h(uint32_t u) { return *reinterpret_cast<__half2*>(&u); }
+__device__ __forceinline__ uint32_t h2u(__half2 h) { return *reinterpret_cast<uint32_t*>(&h); }
+
+struct UmmaParams {
+    // 16-bit token tables
+    const __half* QK16;      // [slot][n_bins][256]  Q then K
+    const float* XS;         // [slot][n_bins][16]   qcK[8] = Q_cell.K_b/4, kcQ[8] = Q_b.K_cell/4 per head
+    const __half* binV16;    // [n_bins][128]
+    const float* binSb;      // [64][n_bins]   feature-major: layer_norm2(fc2 V) - beta(layer_norm1)
+    const __half* cellV16;   // [n_cells][128]
+    // high-accuracy variant: fp32 token tables (Q/K per (cell, bin), V per bin / cell)
+    const float* QK32;       // [slot][n_bins][2][128]
+    const float* binV32;     // [n_bins][128]
+    const float* cellV32;    // [n_cells][128]
+    const float* cellSb;     // [64][n_cells]  feature-major
+    const unsigned char* wimg;   // SM_WIMG_BYTES pre-swizzled fp16 weight images
+    float cst[CST_COUNT];        // fp32 constants, by value: they become constant-bank operands of the epilogue math
+    const int2* pairs; const float* pair_bias; long long P;
+    int n_bins, n_cells, cell_start, n_batch, tiles_per_cell, act;
+    float* out;
+};
+
+__device__ __forceinline__ float ex2_approx(float x) { float y; asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
+__device__ __forceinline__ float rcp_approx(float x) { float y; asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
+// masked 3-token softmax row (Modules.py:948-953) with the diagonal logit forced to 0:
+// w_a = p_a / (p_a + p_b + 1e-13), p = softmax([0, la, lb])  ==  e_a / (e_a + e_b + 1e-13 (e_0 + e_a + e_b))
+__device__ __forceinline__ void masked_row_fast(float la, float lb, float& wa, float& wb) {
+    const float L2E = 1.4426950408889634f;
+    float mx = fmaxf(0.f, fmaxf(la, lb));
+    float e0 = ex2_approx(-mx * L2E), ea = ex2_approx((la - mx) * L2E), eb = ex2_approx((lb - mx) * L2E);
+    float den = fmaf(1e-13f, e0 + ea + eb, ea + eb);
+    float inv = rcp_approx(den);
+    wa = ea * inv; wb = eb * inv;
+}
+
+struct UmmaParams;
+// Attention of one token row-tile (fast variant), T = token position (0 cell, 1 bin_i, 2 bin_j): row T attends to the two
+// other tokens.  Lane mapping: lane = (row-in-group rho = lane>>3, head h = lane&7); a warp walks its own 32 rows four at a
+// time, so the 8 lanes of a row read one contiguous 256-byte table row (coalesced).  Each lane owns the two 16-byte chunks
+// of head h; lanes with h >= 4 handle them in swapped order so that the 8 lanes of a quarter-warp hit 8 distinct swizzle
+// slots when storing (no 2-way bank conflict).  s_pr: the (bin_i, bin_j) pairs of the warpgroup's 128 rows in shared memory;
+// the calling warp handles rows row0 .. row0 + 4 NIT - 1.
+template <int T, int NIT>
+__device__ __forceinline__ void attention_fast(const __half* __restrict__ QK16, const float* __restrict__ XS,
+                                               const __half* __restrict__ binV16, const __half* __restrict__ cellV16,
+                                               const int2* s_pr, int lane, int row0, uint32_t a_base, uint32_t tokbase, int cell) {
+    // Lane j = lane & 7 of a row owns the 16-byte chunks j and 8 + j of the 256-byte Q / K / V rows, i.e. one half of head
+    // hA = j >> 1 and one half of head hB = 4 + (j >> 1): every warp-level 128-bit load then covers four fully used 128-byte
+    // lines (the shared-memory / L1 data pipe is what bounds this kernel).  The two lanes that share a head add their partial
+    // dot products with one shuffle.
+    const int j = lane & 7, rsub = lane >> 3, hA = j >> 1, hB = 4 + (j >> 1);
+    const uint4* QKj = reinterpret_cast<const uint4*>(QK16) + j;
+    const uint4* BVj = reinterpret_cast<const uint4*>(binV16) + j;
+    const float* XSa = XS + hA + (T == 0 ? 0 : 8);
+    uint4 vcA = make_uint4(0, 0, 0, 0), vcB = vcA;
+    if (T != 0) {
+        const uint4* vc = reinterpret_cast<const uint4*>(cellV16) + (uint32_t)cell * 16u + j;
+        vcA = __ldg(vc); vcB = __ldg(vc + 8);
+    }
+#pragma unroll 2
+    for (int it = 0; it < NIT; ++it) {
+        const int rw = row0 + it * 4 + rsub;          // row of the 128-row tile handled by this lane in this step
+        const int2 pr = s_pr[rw];
+        const uint32_t ti = tokbase + (uint32_t)pr.x, tj = tokbase + (uint32_t)pr.y;
+        float laA, laB, lbA, lbB;
+        uint4 aA, aB, bA, bB;
+        if (T == 0) {
+            laA = __ldg(XSa + ti * 16u); laB = __ldg(XSa + ti * 16u + 4);
+            lbA = __ldg(XSa + tj * 16u); lbB = __ldg(XSa + tj * 16u + 4);
+            aA = __ldg(BVj + (uint32_t)pr.x * 16u); aB = __ldg(BVj + (uint32_t)pr.x * 16u + 8);
+            bA = __ldg(BVj + (uint32_t)pr.y * 16u); bB = __ldg(BVj + (uint32_t)pr.y * 16u + 8);
+        } else {
+            const uint32_t tq = (T == 1) ? ti : tj, tk = (T == 1) ? tj : ti, bv = (uint32_t)((T == 1) ? pr.y : pr.x);
+            laA = __ldg(XSa + tq * 16u); laB = __ldg(XSa + tq * 16u + 4);
+            const uint4 qA = __ldg(QKj + tq * 32u), qB = __ldg(QKj + tq * 32u + 8);
+            const uint4 kA = __ldg(QKj + tk * 32u + 16), kB = __ldg(QKj + tk * 32u + 24);
+            bA = __ldg(BVj + bv * 16u); bB = __ldg(BVj + bv * 16u + 8);
+            aA = vcA; aB = vcB;
+            __half2 accA = __hmul2(u2h(qA.x), u2h(kA.x)), accB = __hmul2(u2h(qB.x), u2h(kB.x));
+            accA = __hfma2(u2h(qA.y), u2h(kA.y), accA); accB = __hfma2(u2h(qB.y), u2h(kB.y), accB);
+            accA = __hfma2(u2h(qA.z), u2h(kA.z), accA); accB = __hfma2(u2h(qB.z), u2h(kB.z), accB);
+            accA = __hfma2(u2h(qA.w), u2h(kA.w), accA); accB = __hfma2(u2h(qB.w), u2h(kB.w), accB);
+            float2 fA = __half22float2(accA), fB = __half22float2(accB);
+            float pA = fA.x + fA.y, pB = fB.x + fB.y;
+            pA += __shfl_xor_sync(0xffffffffu, pA, 1); pB += __shfl_xor_sync(0xffffffffu, pB, 1);
+            lbA = pA * 0.25f; lbB = pB * 0.25f;
+        }
+        float waA, wbA, waB, wbB;
+        masked_row_fast(laA, lbA, waA, wbA);
+        masked_row_fast(laB, lbB, waB, wbB);
+        const __half2 wa2 = __float2half2_rn(waA), wb2 = __float2half2_rn(wbA);
+        sts128(a_chunk_addr(a_base, rw, j),
+               h2u(__hfma2(wb2, u2h(bA.x), __hmul2(wa2, u2h(aA.x)))), h2u(__hfma2(wb2, u2h(bA.y), __hmul2(wa2, u2h(aA.y)))),
+               h2u(__hfma2(wb2, u2h(bA.z), __hmul2(wa2, u2h(aA.z)))), h2u(__hfma2(wb2, u2h(bA.w), __hmul2(wa2, u2h(aA.w)))));
+        const __half2 wc2 = __float2half2_rn(waB), wd2 = __float2half2_rn(wbB);
+        sts128(a_chunk_addr(a_base, rw, 8 + j),
+               h2u(__hfma2(wd2, u2h(bB.x), __hmul2(wc2, u2h(aB.x)))), h2u(__hfma2(wd2, u2h(bB.y), __hmul2(wc2, u2h(aB.y)))),
+               h2u(__hfma2(wd2, u2h(bB.z), __hmul2(wc2, u2h(aB.z)))), h2u(__hfma2(wd2, u2h(bB.w), __hmul2(wc2, u2h(aB.w)))));
+        (void)hB;
+    }
+}
+
+// NK k-steps of one [128 x N] += A[128 x 16NK] . B[N x 16NK]^T ; A / B tiles in K-major SWIZZLE_128B
+template <int NK, int N>
+__device__ __forceinline__ void mma_group(uint32_t a_base, uint32_t b_base, int b_rows, uint32_t d_tmem, uint32_t accum_first) {
+    constexpr uint32_t idesc = umma_idesc_f16(128, N);
+#pragma unroll
+    for (int k = 0; k < NK; ++k) {
+        uint32_t aoff = (uint32_t)(k >> 2) * 16384u + (uint32_t)(k & 3) * 32u;
+        uint32_t boff = (uint32_t)(k >> 2) * (uint32_t)(b_rows * 128) + (uint32_t)(k & 3) * 32u;
+        umma_f16(d_tmem, umma_desc(a_base + aoff), umma_desc(b_base + boff), idesc, (k > 0) ? 1u : accum_first);
+    }
+}
+// one MMA round trip for a warpgroup: the A tile is complete in shared memory.  Generic-proxy writes of the A tile are
+// made visible to the tensor core (async proxy), the warpgroup syncs, one thread issues and commits to the mbarrier.
+#define ISSUE_BEGIN() fence_async_smem(); tc_fence_before(); wg_bar(wg); if (wtid == 0) { tc_fence_after();
+#define ISSUE_END() umma_commit(bar_mma); }
+template <int NK, int N>
+__device__ __forceinline__ void issue_gemm(int wg, int wtid, uint32_t a_base, uint32_t b_base, int b_rows, uint32_t d_tmem,
+                                           uint32_t accum_first, uint32_t bar_mma) {
+    ISSUE_BEGIN()
+    mma_group<NK, N>(a_base, b_base, b_rows, d_tmem, accum_first);
+    ISSUE_END()
+}
