@@ -41,7 +41,9 @@ def parse():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="C2")
-    ap.add_argument("--cells-per-step", type=int, default=256)
+    ap.add_argument("--cells-per-step", type=int, default=1000)
+    ap.add_argument("--mode", default="impute", choices=["impute", "train"],
+                    help="impute (default, the BASELINE headline) or train (hyperedges/s of the data-parallel training step)")
     ap.add_argument("--precision", default=os.environ.get("HSG_PRECISION", "auto"))
     ap.add_argument("--n-cells", type=int, default=0, help="shrink the dataset (debug only; marks the run invalid)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
@@ -210,10 +212,67 @@ def cpu_baseline(args, ds_shape):
 
 
 # ------------------------------------------------------------------------------------------ our arm
+def run_train(args):
+    """Secondary metric of BASELINE.json: training hyperedges/s (positives + negatives through forward + backward + gradient
+    allreduce + Adam), stage-2 model, C4-shaped synthetic data (mm10 @ 500 kb, 4935 bins; --n-cells cells, default 300 because
+    the step cost does not depend on the number of cells), batch 3072 hyperedges per rank (Higashi_wrapper.py:728,759).
+    Batches (negatives + neighbour lists) are pre-materialised on the host, so the timed region is the scorer, as in the
+    reference's own GPU-side timing."""
+    import torch
+    import torch.distributed as dist
+    from higashi_b200 import batches, parallel, synthetic as S
+    from higashi_b200.train_engine import TrainEngine
+    rank, world, local = int(os.environ.get("RANK", "0")), int(os.environ.get("WORLD_SIZE", "1")), int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    ds = S.make_dataset("C4", n_cells=args.n_cells or 300, seed=4000, density=0.02)
+    sd, feats = S.random_state_dict(ds, ds.d, seed=0)
+    eng = TrainEngine(sd, ds.num, feats, ds.cell_feats, device=local)
+    tr = parallel.DataParallelTrainer(eng, lr=1e-3)
+    rng = np.random.default_rng(10 + rank)
+    n_pos, neg = 512, 5
+    pool = []
+    for i in range(8):
+        chrom = int(rng.integers(0, len(ds.bins)))
+        x, y, w = batches.synthetic_batch(ds.csr, chrom, ds.num_list, n_pos, neg, rng)
+        pool.append((x, chrom, batches.neighbor_csr(ds.csr, x, chrom, ds.num_list, training=True, rng=rng), y, w))
+    B = len(pool[0][0])
+
+    def step(i):
+        x, chrom, nb, y, w = pool[i % len(pool)]
+        tr.step(x, chrom, nb, y, w, stage=2, loss_mode=0, train_mode=True)
+    for i in range(args.warmup):
+        step(i)
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    l0 = eng.ctx.launch_count()
+    t0 = time.perf_counter()
+    for i in range(args.steps):
+        step(args.warmup + i)
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    dt = parallel.max_over_ranks(time.perf_counter() - t0)
+    if rank == 0:
+        print(json.dumps({"metric": "train hyperedges/s", "value": world * args.steps * B / dt, "unit": "hyperedges/s", "n_gpus": world,
+                          "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps, "higher_is_better": True,
+                          "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+                          "config": {"workload": "C4-shaped: %d cells x %d bins (mm10 @ 500 kb), stage-2 (GraphSAGE) training step, %d hyperedges "
+                                                 "per rank per step, d_model=%d, dropout on, Adam, 1 NCCL allreduce/step" % (ds.n_cells, sum(ds.bins), B, ds.d)},
+                          "gpu_launches": int(eng.ctx.launch_count() - l0)}), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
 def main():
     args = parse()
     if args.impl == "reference":
         run_reference(args)
+        return
+    if args.mode == "train":
+        run_train(args)
         return
     import torch
     import torch.distributed as dist
@@ -295,8 +354,16 @@ def main():
         pass
     peak_tf = float(peaks.get("bf16_tflops_sustained", 1400.0))
     achieved_tf = FLOP_PER_TRIPLET_TENSOR * cps * P / (k2_ms_per_step * 1e-3) / 1e12 * (ds.d / 64.0) ** 2 if k2_ms_per_step > 0 else 0.0
+    traffic = None
+    try:        # DRAM bytes per launch of the dominant kernel from the committed ncu capture, scaled to this run's launch size
+        tj = json.load(open(os.path.join(ROOT, "profiles", "r01_k2_traffic.json")))
+        per_triplet = (tj["dram_bytes_read"] + tj["dram_bytes_write"]) / tj["triplets_per_launch"]
+        traffic = per_triplet * min(cps, 40) * P
+    except Exception:
+        pass
     roofline = {"kernel": "K2 fused scorer", "bound": "tensor", "achieved": achieved_tf, "peak": peak_tf, "unit": "TFLOP/s",
-                "frac": achieved_tf / peak_tf, "traffic": None,
+                "frac": achieved_tf / peak_tf, "traffic": traffic,
+                "traffic_note": "DRAM bytes per K2 launch (one batch of <= 40 cells) from profiles/r01_k2_traffic.json (ncu); algorithmic bytes = 4 B/triplet",
                 "peak_source": "MEASURED_PEAKS.json bf16_tflops_sustained" if peaks else "fallback 1.4 PFLOP/s sustained",
                 "stage_ms_per_step": {"gather_K1a": stage[0] / nprof, "project_K1b": stage[1] / nprof, "scorer_K2": k2_ms_per_step},
                 "k2_share_of_step": float(stage[2] / max(stage[3], 1e-9))}
