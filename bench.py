@@ -241,7 +241,7 @@ def run_train(args):
 
     def step(i):
         x, chrom, nb, y, w = pool[i % len(pool)]
-        tr.step(x, chrom, nb, y, w, stage=2, loss_mode=0, train_mode=True)
+        tr.step(x, chrom, nb, y, w, stage=2, loss_mode=0, train_mode=True, want_loss=(i % 10 == 0))
     for i in range(args.warmup):
         step(i)
     torch.cuda.synchronize()

@@ -11,6 +11,7 @@
 // reference's to_neighs row order.
 #include <cstring>
 
+#include <algorithm>
 #include "common.cuh"
 
 #define TR_CHECK_LAUNCH(c) do { (c)->launches++; HSG_CUDA(cudaGetLastError()); } while (0)
@@ -25,7 +26,11 @@ __global__ void __launch_bounds__(256) sgemm_kernel(int M, int N, int K, const f
     const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;
     const int m0 = blockIdx.y * 64, n0 = blockIdx.x * 64;
     float acc[4][4] = {};
-    for (int k0 = 0; k0 < K; k0 += 16) {
+    // split-K: gridDim.z slices of the reduction, combined with atomics (only launched with beta == 1)
+    const int kchunk = ((K + (int)gridDim.z - 1) / (int)gridDim.z + 15) & ~15;
+    const int kbeg = blockIdx.z * kchunk;
+    K = min(K, kbeg + kchunk);
+    for (int k0 = kbeg; k0 < K; k0 += 16) {
         for (int i = threadIdx.x; i < 16 * 64; i += 256) {
             int kk = i & 15, mm = i >> 4;
             if (TA) { kk = i >> 6; mm = i & 63; }
@@ -58,7 +63,8 @@ __global__ void __launch_bounds__(256) sgemm_kernel(int M, int N, int K, const f
             int m = m0 + ty * 4 + i, n = n0 + tx * 4 + j;
             if (m < M && n < N) {
                 float* p = C + (size_t)m * ldc + n;
-                *p = (beta != 0.f) ? fmaf(beta, *p, acc[i][j]) : acc[i][j];
+                if (gridDim.z > 1) atomicAdd(p, acc[i][j]);
+                else *p = (beta != 0.f) ? fmaf(beta, *p, acc[i][j]) : acc[i][j];
             }
         }
 }
@@ -67,6 +73,11 @@ static int gemm(hsg_ctx* c, cudaStream_t s, bool ta, bool tb, int M, int N, int 
                 int ldb, float* C, int ldc, float beta) {
     if (M <= 0 || N <= 0) return 0;
     dim3 grid((N + 63) / 64, (M + 63) / 64);
+    // weight-gradient shapes (tiny M x N, long K): slice the reduction so the grid covers the SMs
+    if (beta == 1.0f && K >= 512 && grid.x * grid.y < 148) {
+        int want = (2 * 148 + grid.x * grid.y - 1) / (grid.x * grid.y);
+        grid.z = (unsigned)std::max(1, std::min(want, K / 128));
+    }
     if (!ta && tb) sgemm_kernel<false, true><<<grid, 256, 0, s>>>(M, N, K, A, lda, B, ldb, C, ldc, beta);
     else if (!ta && !tb) sgemm_kernel<false, false><<<grid, 256, 0, s>>>(M, N, K, A, lda, B, ldb, C, ldc, beta);
     else if (ta && !tb) sgemm_kernel<true, false><<<grid, 256, 0, s>>>(M, N, K, A, lda, B, ldb, C, ldc, beta);

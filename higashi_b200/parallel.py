@@ -105,29 +105,45 @@ class DataParallelTrainer:
         self.grad_views = list(engine.named_grads().values())
         self.opt = torch.optim.Adam(self.params, lr=lr)
         self.presence = torch.zeros(len(self.names), dtype=torch.float32, device=engine.grads.device)
+        self._patterns = {}
+        self.loss_mode_cached = 0
+        self.world = 1
+        try:
+            import torch.distributed as dist
+            if dist.is_available() and dist.is_initialized():
+                self.world = dist.get_world_size()
+        except Exception:
+            pass
 
-    def _local_presence(self, chrom, stage):
-        self.presence.zero_()
-        for i, n in enumerate(self.names):
-            if ".wstack." in n:
-                b = int(n.split(".wstack.")[1].split(".")[0])
-                on = (b == chrom + 1) or (b == 0 and stage == 1 and self.eng.cell_on_hook)
-            else:
-                on = not (n.startswith("pff_classifier_var") or n.startswith("pff_classifier_proba") or
-                          n.startswith("extra_proba.") or n.startswith("extra_proba3") or
-                          (stage == 1 and n.startswith("encode1.dynamic_nn.nn")))
-            if on:
-                self.presence[i] = 1.0
+    def _presence_pattern(self, chrom, stage):
+        """Which parameter tensors receive a gradient for a batch of chromosome `chrom` (host list, cached)."""
+        key = (chrom, stage, self.loss_mode_cached)
+        if key not in self._patterns:
+            zinb = self.loss_mode_cached == 2
+            pat = []
+            for n in self.names:
+                if ".wstack." in n:
+                    b = int(n.split(".wstack.")[1].split(".")[0])
+                    on = (b == chrom + 1) or (b == 0 and stage == 1 and self.eng.cell_on_hook)
+                else:
+                    unused_head = (n.startswith("pff_classifier_var") or n.startswith("pff_classifier_proba") or
+                                   n.startswith("extra_proba.") or n.startswith("extra_proba3"))
+                    on = not ((unused_head and not zinb) or (stage == 1 and n.startswith("encode1.dynamic_nn.nn")))
+                pat.append(bool(on))
+            import torch
+            self._patterns[key] = (pat, torch.tensor([1.0 if v else 0.0 for v in pat], dtype=torch.float32, device=self.presence.device))
+        return self._patterns[key]
 
     def step(self, x, chrom, to_neighs, y, w, stage=2, loss_mode=0, train_mode=True, alpha=1.0, beta=1e-2,
-             median_sparsity=0.0, contractive_weight=0.0):
+             median_sparsity=0.0, contractive_weight=0.0, want_loss=True):
         """One update.  stage 1 reproduces train_epoch's three backward passes (Higashi_wrapper.py:970-1006):
         gradient of the main loss, gradient of the reconstruction loss, ratio1 = max(beta*|g_main|/|g_recon|,
         100*median_sparsity - 3), total = alpha*main + ratio1*recon + contractive."""
         self.n_steps = getattr(self, "n_steps", 0) + 1
         self.eng.set_dropout(train_mode, seed=0x5EED0000 + self.n_steps)
         self.eng.zero_grad()
-        _, loss = self.eng.forward(x, chrom, to_neighs, y=y, w=w, stage=stage, loss_mode=loss_mode)
+        _, loss = self.eng.forward(x, chrom, to_neighs, y=y, w=w, stage=stage, loss_mode=loss_mode, want_outputs=want_loss,
+                                   want_mean=False)
         self.eng.backward()
         if alpha != 1.0:
             self.eng.grads.mul_(alpha)
@@ -141,10 +157,13 @@ class DataParallelTrainer:
             if contractive_weight > 0:
                 for name in (w0, "%s.wstack.0.reverse_weight_list.0" % pfx):
                     self.eng.named_grads()[name].add_(self.eng.named_params()[name], alpha=2.0 * contractive_weight)
-        self._local_presence(chrom, stage)
-        reduce_gradients(self.eng.grads, self.presence)
-        pres = self.presence.cpu().numpy()
-        for p, g, on in zip(self.params, self.grad_views, pres):
-            p.grad = g if on > 0 else None
+        self.loss_mode_cached = loss_mode
+        pat, pat_dev = self._presence_pattern(chrom, stage)
+        if self.world > 1:
+            self.presence.copy_(pat_dev)
+            reduce_gradients(self.eng.grads, self.presence)
+            pat = (self.presence > 0).tolist()            # OR over the ranks (they may have drawn different chromosomes)
+        for p, g, on in zip(self.params, self.grad_views, pat):
+            p.grad = g if on else None
         self.opt.step()
         return loss

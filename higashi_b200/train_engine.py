@@ -130,7 +130,7 @@ class TrainEngine:
         self.grads.zero_()
 
     def forward(self, x, chrom: int, to_neighs=None, y=None, w=None, stage: int = 2, loss_mode: int = LOSS_CLASSIFICATION,
-                only_model: bool = False, want_outputs: bool = True):
+                only_model: bool = False, want_outputs: bool = True, want_mean: bool = True):
         """One minibatch of ONE chromosome (DataGenerator.next_iter draws one chromosome per batch, Modules.py:1205).
         Returns (mean float32 [B] or None, loss float or None)."""
         x = np.ascontiguousarray(_np(x), dtype=np.int64)
@@ -147,7 +147,7 @@ class TrainEngine:
             nnz = int(len(cols))
         yv = None if y is None else np.ascontiguousarray(_np(y), dtype=np.float32).reshape(-1)
         wv = None if w is None else np.ascontiguousarray(_np(w), dtype=np.float32).reshape(-1)
-        mean = np.empty(B, dtype=np.float32) if want_outputs else None
+        mean = np.empty(B, dtype=np.float32) if (want_outputs and want_mean) else None
         loss = np.zeros(1, dtype=np.float32) if (want_outputs and y is not None) else None
         stream = torch.cuda.current_stream(self.device).cuda_stream
         self.ctx._check(self.ctx.lib.hsg_score_fwd(self.ctx.h, int(stage), int(chrom), p(x, C.c_int64), B, p(indptr, C.c_int32),
