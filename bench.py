@@ -180,6 +180,63 @@ def run_reference(args):
     print(json.dumps(line), flush=True)
 
 
+def run_reference_train(args):
+    """Reference arm of --mode train: the oracle's torch-CPU restatement of the stage-2 training step (forward_stage2 + BCE +
+    autograd + Adam; Higashi_wrapper.py:728-759, 1006-1010), all host threads, on batches of the same shape."""
+    import torch
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    from oracle import scorer as OS
+    from higashi_b200 import batches, synthetic as S
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    ds = S.make_dataset("C4", n_cells=args.n_cells or 300, seed=4000, density=0.02)
+    sd, feats = S.random_state_dict(ds, ds.d, seed=0)
+    tsd = {k: torch.from_numpy(np.array(v, dtype=np.float32, copy=True)) for k, v in sd.items()}
+    with torch.no_grad():
+        cell_table = OS.encoder_branch(torch.as_tensor(feats[0]), tsd, "encode1.static_nn", 0)
+    tables = [cell_table] + [None] * len(ds.bins)
+    params = [t.requires_grad_(True) for k, t in tsd.items() if t.dtype == torch.float32 and "attribute_dict" not in k]
+    opt = torch.optim.Adam(params, lr=1e-3)
+    rng = np.random.default_rng(10)
+    pool = []
+    for i in range(4):
+        chrom = int(rng.integers(0, len(ds.bins)))
+        x, y, w = batches.synthetic_batch(ds.csr, chrom, ds.num_list, 512, 5, rng)
+        indptr, cols, vals = batches.neighbor_csr(ds.csr, x, chrom, ds.num_list, training=True, rng=rng)
+        rows = np.repeat(np.arange(len(indptr) - 1), np.diff(indptr))
+        base = int(ds.num_list[chrom]) + 1
+        nb = (np.stack([rows, cols]).astype(np.int64), vals, np.arange(base, base + ds.bins[chrom], dtype=np.int64))
+        pool.append((x, nb, torch.from_numpy(y.astype(np.float32)), torch.from_numpy(w.astype(np.float32))))
+    B = len(pool[0][0])
+    times = []
+    for it in range(args.warmup + args.steps):
+        x, nb, y, w = pool[it % len(pool)]
+        t0 = time.perf_counter()
+        opt.zero_grad()
+        out = OS.forward_stage2(x, nb, ds.num_list, tsd, feats, ds.cell_feats, tables)
+        mean = out[0] if isinstance(out, (tuple, list)) else out
+        loss = torch.nn.functional.binary_cross_entropy_with_logits(mean.reshape(-1), y.reshape(-1), weight=w.reshape(-1))
+        loss.backward()
+        opt.step()
+        dt = time.perf_counter() - t0
+        if it >= args.warmup:
+            times.append(dt)
+    total = sum(times)
+    val = args.steps * B / total
+    print(json.dumps({"impl": "reference", "metric": "train hyperedges/s", "value": val, "unit": "hyperedges/s", "n_gpus": args.gpus,
+                      "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * total / args.steps, "higher_is_better": True,
+                      "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+                      "config": {"workload": "C4-shaped: %d cells x %d bins, stage-2 training step, %d hyperedges per step, d_model=%d"
+                                             % (ds.n_cells, sum(ds.bins), B, ds.d)},
+                      "cpu_baseline": {"value": val, "unit": "hyperedges/s", "cores": cores, "kind": "port",
+                                       "sample": "%d steps of %d hyperedges (oracle/ forward_stage2 + torch autograd + Adam, no dropout)"
+                                                 % (args.steps, B)},
+                      "e2e": {"value": val, "unit": "hyperedges/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+                      "gpu_launches": 0}), flush=True)
+
+
 def cpu_baseline(args, ds_shape):
     """Bounded CPU sample (oracle port) for the `cpu_baseline` object of the main line."""
     import torch
@@ -269,7 +326,7 @@ def run_train(args):
 def main():
     args = parse()
     if args.impl == "reference":
-        run_reference(args)
+        (run_reference_train if args.mode == "train" else run_reference)(args)
         return
     if args.mode == "train":
         run_train(args)

@@ -45,8 +45,8 @@ __global__ void __launch_bounds__(UM_THREADS, 1) score_umma_kernel(UmmaParams p)
     __syncthreads();
     tc_fence_after();
     if (tid == 0) {
-        mbar_expect_tx(bar_w, SM_WIMG_BYTES);
-        tma_bulk_g2s(sbase + SM_B_FC1, p.wimg, SM_WIMG_BYTES, bar_w);
+        mbar_expect_tx(bar_w, HI ? SM_WIMG_BYTES : SMF_WIMG_BYTES);
+        tma_bulk_g2s(sbase, HI ? p.wimg : p.wimg + SM_WIMG_BYTES, HI ? SM_WIMG_BYTES : SMF_WIMG_BYTES, bar_w);
     }
     const uint32_t tmem_base = *tmem_slot;
     const uint32_t t_lane = ((uint32_t)(warp_in_wg * 32)) << 16;
@@ -133,79 +133,123 @@ __global__ void __launch_bounds__(UM_THREADS, 1) score_umma_kernel(UmmaParams p)
                 else attention_fast<2, 8>(p.QK16, p.XS, p.binV16, p.cellV16, s_pr_wg, lane, warp_in_wg * 32, a_base, tokbase, cell);
             }
             if constexpr (HI) {
-                ISSUE_BEGIN()
-                mma_group<8, 64>(a_base, sbase + SM_B_FC1, 64, t_y, 0u);
-                mma_group<8, 64>(a_base, sbase + SM_B_FC1_LO, 64, t_y, 1u);        // + ctx . (fc1 - fp16(fc1))^T
-                ISSUE_END()
-            } else {
-                issue_gemm<8, 64>(wg, wtid, a_base, sbase + SM_B_FC1, 64, t_y, 0u, bar_mma);
-            }
-            mbar_wait(bar_mma, phase); phase ^= 1;
-            tc_fence_after();
+                if constexpr (HI) {
+                    ISSUE_BEGIN()
+                    mma_group<8, 64>(a_base, sbase + SM_B_FC1, 64, t_y, 0u);
+                    mma_group<8, 64>(a_base, sbase + SM_B_FC1_LO, 64, t_y, 1u);        // + ctx . (fc1 - fp16(fc1))^T
+                    ISSUE_END()
+                }
+                mbar_wait(bar_mma, phase); phase ^= 1;
+                tc_fence_after();
 
-            // The row-wise epilogues below use the packed fp32x2 instructions of sm_100 (FADD2/FMUL2/FFMA2 via
-            // __fadd2_rn/__fmul2_rn/__ffma2_rn): two columns per issue slot.
-            // ------------------------------------------------------------------ y -> LN_pff(y) (A tile, K = 64)
-            {
-                uint32_t r0[32], r1[32];
-                tmem_ld32(t_y + t_lane, r0);
-                tmem_ld32(t_y + t_lane + 32, r1);
-                tmem_ld_wait();
-                float2 x[32];
-#pragma unroll
-                for (int i = 0; i < 16; ++i) { x[i] = f2(r0[2 * i], r0[2 * i + 1]); x[16 + i] = f2(r1[2 * i], r1[2 * i + 1]); }
-                float2 sA = x[0], sB = x[1], sC = x[2], sD = x[3];        // 4 independent chains (ILP)
-#pragma unroll
-                for (int i = 4; i < 32; i += 4) {
-                    sA = __fadd2_rn(sA, x[i]); sB = __fadd2_rn(sB, x[i + 1]); sC = __fadd2_rn(sC, x[i + 2]); sD = __fadd2_rn(sD, x[i + 3]);
-                }
-                sA = __fadd2_rn(__fadd2_rn(sA, sB), __fadd2_rn(sC, sD));
-                const float mean = (sA.x + sA.y) * (1.0f / 64.0f);
-                const float2 nm = make_float2(-mean, -mean);
-                float2 vA = make_float2(0.f, 0.f), vB = vA, vC = vA, vD = vA;
-#pragma unroll
-                for (int i = 0; i < 32; i += 4) {
-                    x[i] = __fadd2_rn(x[i], nm); x[i + 1] = __fadd2_rn(x[i + 1], nm);
-                    x[i + 2] = __fadd2_rn(x[i + 2], nm); x[i + 3] = __fadd2_rn(x[i + 3], nm);
-                    vA = __ffma2_rn(x[i], x[i], vA); vB = __ffma2_rn(x[i + 1], x[i + 1], vB);
-                    vC = __ffma2_rn(x[i + 2], x[i + 2], vC); vD = __ffma2_rn(x[i + 3], x[i + 3], vD);
-                }
-                vA = __fadd2_rn(__fadd2_rn(vA, vB), __fadd2_rn(vC, vD));
-                const float rstd = rsqrtf((vA.x + vA.y) * (1.0f / 64.0f) + HSG_LN_EPS);
-                const float2 rs = make_float2(rstd, rstd);
-#pragma unroll
-                for (int c = 0; c < 8; ++c) {
-                    float2 a0 = __fmul2_rn(x[c * 4 + 0], rs), a1 = __fmul2_rn(x[c * 4 + 1], rs);
-                    float2 a2 = __fmul2_rn(x[c * 4 + 2], rs), a3 = __fmul2_rn(x[c * 4 + 3], rs);
-                    sts128(a_chunk_addr(a_base, wtid, c), pack_h2(a0.x, a0.y), pack_h2(a1.x, a1.y), pack_h2(a2.x, a2.y), pack_h2(a3.x, a3.y));
-                }
-            }
-            issue_gemm<4, 64>(wg, wtid, a_base, sbase + SM_B_W0, 64, t_h, 0u, bar_mma);
-            mbar_wait(bar_mma, phase); phase ^= 1;
-            tc_fence_after();
-
-            // ------------------------------------------------------------------ h = swish(. + b0') (A tile, K = 64)
-#pragma unroll
-            for (int half = 0; half < 2; ++half) {
-                uint32_t r[32];
-                tmem_ld32(t_h + t_lane + half * 32, r);
-                tmem_ld_wait();
-#pragma unroll
-                for (int c = 0; c < 4; ++c) {
-                    const float* bq = cst + CST_B0F + half * 32 + c * 8;
-                    uint32_t pk[4];
-#pragma unroll
-                    for (int q = 0; q < 4; ++q) {
-                        float2 w = __fadd2_rn(f2(r[c * 8 + 2 * q], r[c * 8 + 2 * q + 1]), make_float2(bq[2 * q], bq[2 * q + 1]));
-                        float2 th = make_float2(fast_tanh(w.x), fast_tanh(w.y));
-                        float2 hh = __ffma2_rn(w, th, w);
-                        pk[q] = pack_h2(hh.x, hh.y);
+                // The row-wise epilogues below use the packed fp32x2 instructions of sm_100 (FADD2/FMUL2/FFMA2 via
+                // __fadd2_rn/__fmul2_rn/__ffma2_rn): two columns per issue slot.
+                // ------------------------------------------------------------------ y -> LN_pff(y) (A tile, K = 64)
+                {
+                    uint32_t r0[32], r1[32];
+                    tmem_ld32(t_y + t_lane, r0);
+                    tmem_ld32(t_y + t_lane + 32, r1);
+                    tmem_ld_wait();
+                    float2 x[32];
+    #pragma unroll
+                    for (int i = 0; i < 16; ++i) { x[i] = f2(r0[2 * i], r0[2 * i + 1]); x[16 + i] = f2(r1[2 * i], r1[2 * i + 1]); }
+                    float2 sA = x[0], sB = x[1], sC = x[2], sD = x[3];        // 4 independent chains (ILP)
+    #pragma unroll
+                    for (int i = 4; i < 32; i += 4) {
+                        sA = __fadd2_rn(sA, x[i]); sB = __fadd2_rn(sB, x[i + 1]); sC = __fadd2_rn(sC, x[i + 2]); sD = __fadd2_rn(sD, x[i + 3]);
                     }
-                    sts128(a_chunk_addr(a_base, wtid, half * 4 + c), pk[0], pk[1], pk[2], pk[3]);
+                    sA = __fadd2_rn(__fadd2_rn(sA, sB), __fadd2_rn(sC, sD));
+                    const float mean = (sA.x + sA.y) * (1.0f / 64.0f);
+                    const float2 nm = make_float2(-mean, -mean);
+                    float2 vA = make_float2(0.f, 0.f), vB = vA, vC = vA, vD = vA;
+    #pragma unroll
+                    for (int i = 0; i < 32; i += 4) {
+                        x[i] = __fadd2_rn(x[i], nm); x[i + 1] = __fadd2_rn(x[i + 1], nm);
+                        x[i + 2] = __fadd2_rn(x[i + 2], nm); x[i + 3] = __fadd2_rn(x[i + 3], nm);
+                        vA = __ffma2_rn(x[i], x[i], vA); vB = __ffma2_rn(x[i + 1], x[i + 1], vB);
+                        vC = __ffma2_rn(x[i + 2], x[i + 2], vC); vD = __ffma2_rn(x[i + 3], x[i + 3], vD);
+                    }
+                    vA = __fadd2_rn(__fadd2_rn(vA, vB), __fadd2_rn(vC, vD));
+                    const float rstd = rsqrtf((vA.x + vA.y) * (1.0f / 64.0f) + HSG_LN_EPS);
+                    const float2 rs = make_float2(rstd, rstd);
+    #pragma unroll
+                    for (int c = 0; c < 8; ++c) {
+                        float2 a0 = __fmul2_rn(x[c * 4 + 0], rs), a1 = __fmul2_rn(x[c * 4 + 1], rs);
+                        float2 a2 = __fmul2_rn(x[c * 4 + 2], rs), a3 = __fmul2_rn(x[c * 4 + 3], rs);
+                        sts128(a_chunk_addr(a_base, wtid, c), pack_h2(a0.x, a0.y), pack_h2(a1.x, a1.y), pack_h2(a2.x, a2.y), pack_h2(a3.x, a3.y));
+                    }
+                }
+                issue_gemm<4, 64>(wg, wtid, a_base, sbase + SM_B_W0, 64, t_h, 0u, bar_mma);
+                mbar_wait(bar_mma, phase); phase ^= 1;
+                tc_fence_after();
+
+                // ------------------------------------------------------------------ h = swish(. + b0') (A tile, K = 64)
+    #pragma unroll
+                for (int half = 0; half < 2; ++half) {
+                    uint32_t r[32];
+                    tmem_ld32(t_h + t_lane + half * 32, r);
+                    tmem_ld_wait();
+    #pragma unroll
+                    for (int c = 0; c < 4; ++c) {
+                        const float* bq = cst + CST_B0F + half * 32 + c * 8;
+                        uint32_t pk[4];
+    #pragma unroll
+                        for (int q = 0; q < 4; ++q) {
+                            float2 w = __fadd2_rn(f2(r[c * 8 + 2 * q], r[c * 8 + 2 * q + 1]), make_float2(bq[2 * q], bq[2 * q + 1]));
+                            float2 th = make_float2(fast_tanh(w.x), fast_tanh(w.y));
+                            float2 hh = __ffma2_rn(w, th, w);
+                            pk[q] = pack_h2(hh.x, hh.y);
+                        }
+                        sts128(a_chunk_addr(a_base, wtid, half * 4 + c), pk[0], pk[1], pk[2], pk[3]);
+                    }
+                }
+            } else {
+                // ONE N=128 GEMM gives y_c = ctx . fc1c^T (columns 0..63: y with its row mean already removed, because the
+                // mean over the outputs was subtracted from fc1 on the host) and g = ctx . (W0' fc1c)^T (columns 64..127).
+                // LayerNorm(y) . W0'^T = rstd(y_c) * g, so the LN -> fp16 -> shared memory -> MMA round trip of the
+                // feed-forward input disappears: the epilogue only needs the row variance of y_c.
+                issue_gemm<8, 128>(wg, wtid, a_base, sbase + SMF_B_FC1, 128, t_y, 0u, bar_mma);
+                mbar_wait(bar_mma, phase); phase ^= 1;
+                tc_fence_after();
+                float2 rs;
+                {
+                    uint32_t r0[32], r1[32];
+                    tmem_ld32(t_y + t_lane, r0);
+                    tmem_ld32(t_y + t_lane + 32, r1);
+                    tmem_ld_wait();
+                    float2 vA = make_float2(0.f, 0.f), vB = vA, vC = vA, vD = vA;
+#pragma unroll
+                    for (int i = 0; i < 16; i += 2) {
+                        float2 a = f2(r0[2 * i], r0[2 * i + 1]), b = f2(r0[2 * i + 2], r0[2 * i + 3]);
+                        float2 c2 = f2(r1[2 * i], r1[2 * i + 1]), d2 = f2(r1[2 * i + 2], r1[2 * i + 3]);
+                        vA = __ffma2_rn(a, a, vA); vB = __ffma2_rn(b, b, vB); vC = __ffma2_rn(c2, c2, vC); vD = __ffma2_rn(d2, d2, vD);
+                    }
+                    vA = __fadd2_rn(__fadd2_rn(vA, vB), __fadd2_rn(vC, vD));
+                    const float rstd = rsqrtf((vA.x + vA.y) * (1.0f / 64.0f) + HSG_LN_EPS);
+                    rs = make_float2(rstd, rstd);
+                }
+#pragma unroll
+                for (int half = 0; half < 2; ++half) {
+                    uint32_t r[32];
+                    tmem_ld32(t_h + t_lane + half * 32, r);
+                    tmem_ld_wait();
+#pragma unroll
+                    for (int c = 0; c < 4; ++c) {
+                        const float* bq = cst + CST_B0F + half * 32 + c * 8;
+                        uint32_t pk[4];
+#pragma unroll
+                        for (int q = 0; q < 4; ++q) {
+                            float2 w = __ffma2_rn(f2(r[c * 8 + 2 * q], r[c * 8 + 2 * q + 1]), rs, make_float2(bq[2 * q], bq[2 * q + 1]));
+                            float2 th = make_float2(fast_tanh(w.x), fast_tanh(w.y));
+                            float2 hh = __ffma2_rn(w, th, w);
+                            pk[q] = pack_h2(hh.x, hh.y);
+                        }
+                        sts128(a_chunk_addr(a_base, wtid, half * 4 + c), pk[0], pk[1], pk[2], pk[3]);
+                    }
                 }
             }
             // z = y + h . W1^T : accumulate onto y (still in TMEM) -- the residual is free
-            issue_gemm<4, 64>(wg, wtid, a_base, sbase + SM_B_W1, 64, t_y, 1u, bar_mma);
+            issue_gemm<4, 64>(wg, wtid, a_base, sbase + (HI ? SM_B_W1 : SMF_B_W1), 64, t_y, 1u, bar_mma);
             mbar_wait(bar_mma, phase); phase ^= 1;
             tc_fence_after();
 
@@ -219,21 +263,26 @@ __global__ void __launch_bounds__(UM_THREADS, 1) score_umma_kernel(UmmaParams p)
                 float2 sA = make_float2(0.f, 0.f), sB = sA;
 #pragma unroll
                 for (int i = 0; i < 16; i += 2) {
-                    const float* bq = cst + CST_B1 + 2 * i;
+                    const float* bq = cst + (HI ? CST_B1 : CST_B1C) + 2 * i;
                     x[i] = __fadd2_rn(f2(r0[2 * i], r0[2 * i + 1]), make_float2(bq[0], bq[1]));
                     x[i + 1] = __fadd2_rn(f2(r0[2 * i + 2], r0[2 * i + 3]), make_float2(bq[2], bq[3]));
                     x[16 + i] = __fadd2_rn(f2(r1[2 * i], r1[2 * i + 1]), make_float2(bq[32], bq[33]));
                     x[17 + i] = __fadd2_rn(f2(r1[2 * i + 2], r1[2 * i + 3]), make_float2(bq[34], bq[35]));
-                    sA = __fadd2_rn(sA, __fadd2_rn(x[i], x[16 + i]));
-                    sB = __fadd2_rn(sB, __fadd2_rn(x[i + 1], x[17 + i]));
+                    if constexpr (HI) {
+                        sA = __fadd2_rn(sA, __fadd2_rn(x[i], x[16 + i]));
+                        sB = __fadd2_rn(sB, __fadd2_rn(x[i + 1], x[17 + i]));
+                    }
                 }
-                const float mean = ((sA.x + sA.y) + (sB.x + sB.y)) * (1.0f / 64.0f);
-                const float2 nm = make_float2(-mean, -mean);
                 float2 vA = make_float2(0.f, 0.f), vB = vA, vC = vA, vD = vA;
+                if constexpr (HI) {
+                    const float mean = ((sA.x + sA.y) + (sB.x + sB.y)) * (1.0f / 64.0f);
+                    const float2 nm = make_float2(-mean, -mean);
+#pragma unroll
+                    for (int i = 0; i < 32; ++i) x[i] = __fadd2_rn(x[i], nm);
+                }
+                // fast variant: z arrives centred (y_c + h . W1c^T + b1c has zero row mean by construction)
 #pragma unroll
                 for (int i = 0; i < 32; i += 4) {
-                    x[i] = __fadd2_rn(x[i], nm); x[i + 1] = __fadd2_rn(x[i + 1], nm);
-                    x[i + 2] = __fadd2_rn(x[i + 2], nm); x[i + 3] = __fadd2_rn(x[i + 3], nm);
                     vA = __ffma2_rn(x[i], x[i], vA); vB = __ffma2_rn(x[i + 1], x[i + 1], vB);
                     vC = __ffma2_rn(x[i + 2], x[i + 2], vC); vD = __ffma2_rn(x[i + 3], x[i + 3], vD);
                 }
@@ -272,7 +321,7 @@ __global__ void __launch_bounds__(UM_THREADS, 1) score_umma_kernel(UmmaParams p)
                 mma_group<4, 32>(a_base, sbase + SM_B_C0_LO, 32, t_h, 1u);               // u_hi . C0_lo
                 ISSUE_END()
             } else {
-                issue_gemm<4, 32>(wg, wtid, a_base, sbase + SM_B_C0, 32, t_h, 0u, bar_mma);
+                issue_gemm<4, 32>(wg, wtid, a_base, sbase + SMF_B_C0, 32, t_h, 0u, bar_mma);
             }
             mbar_wait(bar_mma, phase); phase ^= 1;
             tc_fence_after();
@@ -345,7 +394,7 @@ int umma_build_weights(const float* fc1, const float* w0, const float* b0, const
         }
         cst_host[CST_B0F + n] = (float)(0.5 * acc);
     }
-    memset(wimg_host, 0, SM_WIMG_BYTES);
+    memset(wimg_host, 0, SM_WIMG_BYTES + SMF_WIMG_BYTES);
     swizzle_image(fc1, d, HSG_HD, reinterpret_cast<__half*>(wimg_host + SM_B_FC1));
     swizzle_image(w0f.data(), d, d, reinterpret_cast<__half*>(wimg_host + SM_B_W0));
     swizzle_image(w1, d, d, reinterpret_cast<__half*>(wimg_host + SM_B_W1));
@@ -361,10 +410,43 @@ int umma_build_weights(const float* fc1, const float* w0, const float* b0, const
     for (int i = 0; i < d; ++i) { cst_host[CST_B1 + i] = b1[i]; cst_host[CST_G1 + i] = ln1_g[i]; }
     for (int i = 0; i < d / 2; ++i) { cst_host[CST_CB0 + i] = 0.5f * cb0[i]; cst_host[CST_CW1 + i] = cw1[i]; }
     cst_host[CST_CB1] = cb1[0];
+    // ---- fast-variant image (appended): every LayerNorm input is produced centred, and LN_pff . W0' is folded into fc1
+    {
+        unsigned char* img = wimg_host + SM_WIMG_BYTES;
+        std::vector<double> fc1c((size_t)d * HSG_HD);
+        for (int k = 0; k < HSG_HD; ++k) {
+            double m = 0;
+            for (int n = 0; n < d; ++n) m += fc1[(size_t)n * HSG_HD + k];
+            m /= d;
+            for (int n = 0; n < d; ++n) fc1c[(size_t)n * HSG_HD + k] = fc1[(size_t)n * HSG_HD + k] - m;
+        }
+        std::vector<float> comb((size_t)2 * d * HSG_HD);
+        for (int n = 0; n < d; ++n)
+            for (int k = 0; k < HSG_HD; ++k) {
+                comb[(size_t)n * HSG_HD + k] = (float)fc1c[(size_t)n * HSG_HD + k];
+                double acc = 0;
+                for (int j = 0; j < d; ++j) acc += (double)w0f[(size_t)n * d + j] * fc1c[(size_t)j * HSG_HD + k];
+                comb[(size_t)(d + n) * HSG_HD + k] = (float)acc;
+            }
+        swizzle_image(comb.data(), 2 * d, HSG_HD, reinterpret_cast<__half*>(img + SMF_B_FC1));
+        std::vector<float> w1c((size_t)d * d);
+        for (int k = 0; k < d; ++k) {
+            double m = 0;
+            for (int n = 0; n < d; ++n) m += w1[(size_t)n * d + k];
+            m /= d;
+            for (int n = 0; n < d; ++n) w1c[(size_t)n * d + k] = (float)(w1[(size_t)n * d + k] - m);
+        }
+        swizzle_image(w1c.data(), d, d, reinterpret_cast<__half*>(img + SMF_B_W1));
+        swizzle_image(c0h.data(), d / 2, d, reinterpret_cast<__half*>(img + SMF_B_C0));
+        double mb = 0;
+        for (int i = 0; i < d; ++i) mb += b1[i];
+        mb /= d;
+        for (int i = 0; i < d; ++i) cst_host[CST_B1C + i] = (float)(b1[i] - mb);
+    }
     return 0;
 }
 
-int umma_wimg_bytes() { return SM_WIMG_BYTES; }
+int umma_wimg_bytes() { return SM_WIMG_BYTES + SMF_WIMG_BYTES; }
 int umma_cst_count() { return CST_COUNT; }
 
 // fp32 static tables -> 16-bit / offset copies used by the tensor-core kernel

@@ -23,6 +23,11 @@
 #define SM_B_FC1_LO 36864      // low halves (w - fp16(w)) of fc1 and C0 for the high-accuracy variant
 #define SM_B_C0_LO 53248
 #define SM_WIMG_BYTES 57344
+// fast variant: [y_c | g] = ctx . [fc1c ; W0' fc1c]^T in ONE N=128 GEMM (see score_umma.cu), then W1c and C0
+#define SMF_B_FC1 0           // [128 x 128] fp16, 2 K-atoms of 16 KB: rows 0..63 fc1c, rows 64..127 W0' fc1c
+#define SMF_B_W1 32768        // [64 x 64]  W1 with its output mean removed
+#define SMF_B_C0 40960        // [32 x 64]
+#define SMF_WIMG_BYTES 45056
 #define SM_A0 57344           // 4 x 32 KB A buffers (one per warpgroup)
 #define SM_A_BYTES 32768
 #define SM_CONST (SM_A0 + UM_WG * SM_A_BYTES)   // fp32 constants
@@ -32,7 +37,8 @@
 #define CST_CB0 192
 #define CST_CW1 224
 #define CST_CB1 256
-#define CST_COUNT 264
+#define CST_B1C 264           // b1 - mean(b1) (fast variant: every LayerNorm input is produced already centred)
+#define CST_COUNT 328
 #define SM_BAR (SM_CONST + CST_COUNT * 4)       // 8 mbarriers
 #define SM_TMEM (SM_BAR + 64)
 #define SM_PAIRS (SM_TMEM + 16)                 // int2 [UM_WG * 128]: (bin_i, bin_j) of every row of the current tiles
