@@ -289,17 +289,19 @@ __global__ void __launch_bounds__(UM_THREADS, 1) score_umma_kernel(UmmaParams p)
                 vA = __fadd2_rn(__fadd2_rn(vA, vB), __fadd2_rn(vC, vD));
                 const float rstd = rsqrtf((vA.x + vA.y) * (1.0f / 64.0f) + HSG_LN_EPS);
                 const float2 rs = make_float2(rstd, rstd);
-                // S tables are stored feature-major ([64][n_tokens]) so that consecutive rows (consecutive bins)
-                // read consecutive addresses: 64 coalesced 4-byte loads instead of 16 row-scattered 16-byte loads
-                const float* Scol = (t == 0) ? p.cellSb + cell : p.binSb + (t == 1 ? pr.x : pr.y);
+                // S tables are stored in feature blocks ([16][n_tokens][4]) so that consecutive rows (consecutive bins) read
+                // consecutive 16-byte quads: 16 coalesced 128-bit loads per row instead of 16 row-scattered ones
+                const float4* Scol = reinterpret_cast<const float4*>((t == 0) ? p.cellSb : p.binSb) + ((t == 0) ? cell : (t == 1 ? pr.x : pr.y));
                 const long long sstr = (t == 0) ? p.n_cells : p.n_bins;
 #pragma unroll
                 for (int c = 0; c < 8; ++c) {
                     const float* gq = cst + CST_G1 + c * 8;
                     uint32_t pk[4], pl[4];
+                    const float4 s0 = __ldg(Scol + (2 * c) * sstr), s1 = __ldg(Scol + (2 * c + 1) * sstr);
+                    const float svv[8] = {s0.x, s0.y, s0.z, s0.w, s1.x, s1.y, s1.z, s1.w};
 #pragma unroll
                     for (int q = 0; q < 4; ++q) {
-                        float2 sv = make_float2(-__ldg(Scol + (c * 8 + 2 * q) * sstr), -__ldg(Scol + (c * 8 + 2 * q + 1) * sstr));
+                        float2 sv = make_float2(svv[2 * q], svv[2 * q + 1]);       // the table holds beta - S
                         float2 tz = __fmul2_rn(x[c * 4 + q], rs);
                         float2 u = __ffma2_rn(tz, make_float2(gq[2 * q], gq[2 * q + 1]), sv);
                         u = __fmul2_rn(u, u);
@@ -454,7 +456,7 @@ __global__ void convert_static_kernel(const float* __restrict__ V, const float* 
                                       long long rows, int d, __half* __restrict__ V16, float* __restrict__ Sb) {
     long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (i < rows * HSG_HD) V16[i] = __float2half_rn(V[i]);
-    if (i < rows * d) { long long r = i / d; int f = (int)(i - r * d); Sb[(long long)f * rows + r] = S[i] - ln1_b[f]; }
+    if (i < rows * d) { long long r = i / d; int f = (int)(i - r * d); Sb[((long long)(f >> 2) * rows + r) * 4 + (f & 3)] = ln1_b[f] - S[i]; }
 }
 
 int launch_convert_static(hsg_ctx* c, const float* V, const float* S, long long rows, void* V16, float* Sb, cudaStream_t s) {

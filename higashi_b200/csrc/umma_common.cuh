@@ -129,13 +129,13 @@ struct UmmaParams {
     const __half* QK16;      // [slot][n_bins][256]  Q then K
     const float* XS;         // [slot][n_bins][16]   qcK[8] = Q_cell.K_b/4, kcQ[8] = Q_b.K_cell/4 per head
     const __half* binV16;    // [n_bins][128]
-    const float* binSb;      // [64][n_bins]   feature-major: layer_norm2(fc2 V) - beta(layer_norm1)
+    const float* binSb;      // [16][n_bins][4] feature blocks: beta(layer_norm1) - layer_norm2(fc2 V)
     const __half* cellV16;   // [n_cells][128]
     // high-accuracy variant: fp32 token tables (Q/K per (cell, bin), V per bin / cell)
     const float* QK32;       // [slot][n_bins][2][128]
     const float* binV32;     // [n_bins][128]
     const float* cellV32;    // [n_cells][128]
-    const float* cellSb;     // [64][n_cells]  feature-major
+    const float* cellSb;     // [16][n_cells][4]
     const unsigned char* wimg;   // SM_WIMG_BYTES pre-swizzled fp16 weight images
     float cst[CST_COUNT];        // fp32 constants, by value: they become constant-bank operands of the epilogue math
     const int2* pairs; const float* pair_bias; long long P;
