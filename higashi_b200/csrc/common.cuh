@@ -12,6 +12,7 @@
 #define HSG_DK 16
 #define HSG_HD 128                 // n_head * d_k = n_head * d_v   (Higashi_wrapper.py:834-845)
 #define HSG_LN_EPS 1e-5f
+#define HSG_L2E_QUARTER 0.36067376022224085f      // log2(e) / 4: attention logits of the tensor-core scorer are kept in log2 units
 #define HSG_PDF0 0.3989422804014327f   // scipy.stats.norm.pdf(0)   (Impute.py:19)
 
 void hsg_set_error(const std::string& msg);

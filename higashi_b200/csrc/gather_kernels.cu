@@ -324,8 +324,9 @@ __global__ void __launch_bounds__(256) token_project_kernel(
             int64_t tok = tok0 + tk;
             if (tok >= n_tok) continue;
             const float* src = qkT + (ch * 8) * TP_LDA + tk;
-            __half2 h0 = __floats2half2_rn(src[0], src[TP_LDA]), h1 = __floats2half2_rn(src[2 * TP_LDA], src[3 * TP_LDA]);
-            __half2 h2 = __floats2half2_rn(src[4 * TP_LDA], src[5 * TP_LDA]), h3 = __floats2half2_rn(src[6 * TP_LDA], src[7 * TP_LDA]);
+            const float sc = (ch < 16) ? HSG_L2E_QUARTER : 1.0f;        // Q rows carry log2(e)/4: the scorer's logits are in log2 units
+            __half2 h0 = __floats2half2_rn(sc * src[0], sc * src[TP_LDA]), h1 = __floats2half2_rn(sc * src[2 * TP_LDA], sc * src[3 * TP_LDA]);
+            __half2 h2 = __floats2half2_rn(sc * src[4 * TP_LDA], sc * src[5 * TP_LDA]), h3 = __floats2half2_rn(sc * src[6 * TP_LDA], sc * src[7 * TP_LDA]);
             uint4 pk;
             pk.x = *reinterpret_cast<uint32_t*>(&h0); pk.y = *reinterpret_cast<uint32_t*>(&h1);
             pk.z = *reinterpret_cast<uint32_t*>(&h2); pk.w = *reinterpret_cast<uint32_t*>(&h3);
@@ -345,8 +346,8 @@ __global__ void __launch_bounds__(256) token_project_kernel(
                     a = fmaf(__ldg(qc + e), qkT[(HSG_HD + h * 16 + e) * TP_LDA + tk], a);
                     b = fmaf(qkT[(h * 16 + e) * TP_LDA + tk], __ldg(kc + e), b);
                 }
-                XS[tok * 16 + h] = a * 0.25f;
-                XS[tok * 16 + 8 + h] = b * 0.25f;
+                XS[tok * 16 + h] = a * HSG_L2E_QUARTER;
+                XS[tok * 16 + 8 + h] = b * HSG_L2E_QUARTER;
             }
         }
     }

@@ -57,11 +57,15 @@ __global__ void __launch_bounds__(UM_THREADS, 1) score_umma_kernel(UmmaParams p)
 
     uint32_t phase = 0;
     const long long n_tiles = (long long)p.n_batch * p.tiles_per_cell;
-    for (long long tile = (long long)blockIdx.x * UM_WG + wg; tile < n_tiles; tile += (long long)gridDim.x * UM_WG) {
+    // The loop bound depends on the block only (not on the warpgroup), so the whole body is warp-uniform control flow for the
+    // compiler; a warpgroup whose tile index runs past the end recomputes the last tile with its stores masked.
+    for (long long tile0 = (long long)blockIdx.x * UM_WG; tile0 < n_tiles; tile0 += (long long)gridDim.x * UM_WG) {
+        const bool tile_ok = tile0 + wg < n_tiles;
+        const long long tile = tile_ok ? tile0 + wg : n_tiles - 1;
         const int cb = (int)(tile / p.tiles_per_cell), pt = (int)(tile - (long long)cb * p.tiles_per_cell);
         const long long pi = (long long)pt * 128 + wtid;
-        const bool valid = pi < p.P;
-        const int2 pr = p.pairs[valid ? pi : (p.P - 1)];
+        const bool valid = tile_ok && pi < p.P;
+        const int2 pr = p.pairs[pi < p.P ? pi : (p.P - 1)];
         const float bias = valid ? p.pair_bias[pi] : 0.f;
         int2* s_pr_wg = reinterpret_cast<int2*>(smem + SM_PAIRS) + wg * 128;    // rows of this warpgroup's tile
         __syncwarp();
@@ -106,7 +110,7 @@ __global__ void __launch_bounds__(UM_THREADS, 1) score_umma_kernel(UmmaParams p)
                             acc = __ffma2_rn(make_float2(qv.x, qv.y), make_float2(kv.x, kv.y), acc);
                             acc2 = __ffma2_rn(make_float2(qv.z, qv.w), make_float2(kv.z, kv.w), acc2);
                         }
-                        lb = ((acc.x + acc.y) + (acc2.x + acc2.y)) * 0.25f;
+                        lb = ((acc.x + acc.y) + (acc2.x + acc2.y)) * HSG_L2E_QUARTER;
                         va = CV4; vb = BV4 + ((t == 1) ? bj_r : bi_r) * 32u + h * 4;
                     }
                     float wa, wb;

@@ -146,14 +146,30 @@ struct UmmaParams {
 __device__ __forceinline__ float ex2_approx(float x) { float y; asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
 __device__ __forceinline__ float rcp_approx(float x) { float y; asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
 // masked 3-token softmax row (Modules.py:948-953) with the diagonal logit forced to 0:
-// w_a = p_a / (p_a + p_b + 1e-13), p = softmax([0, la, lb])  ==  e_a / (e_a + e_b + 1e-13 (e_0 + e_a + e_b))
-__device__ __forceinline__ void masked_row_fast(float la, float lb, float& wa, float& wb) {
-    const float L2E = 1.4426950408889634f;
+// w_a = p_a / (p_a + p_b + 1e-13), p = softmax([0, la, lb])  ==  e_a / (e_a + e_b + 1e-13 (e_0 + e_a + e_b)).
+// The logits arrive in log2 units (K1b folds log2(e)/4 into the Q rows and the cell cross terms).
+__device__ __forceinline__ void masked_row_exact(float la, float lb, float& wa, float& wb) {
     float mx = fmaxf(0.f, fmaxf(la, lb));
-    float e0 = ex2_approx(-mx * L2E), ea = ex2_approx((la - mx) * L2E), eb = ex2_approx((lb - mx) * L2E);
+    float e0 = ex2_approx(-mx), ea = ex2_approx(la - mx), eb = ex2_approx(lb - mx);
     float den = fmaf(1e-13f, e0 + ea + eb, ea + eb);
     float inv = rcp_approx(den);
     wa = ea * inv; wb = eb * inv;
+}
+// The 1e-13 term changes the result by less than 1e-7 relative unless both logits are below -20 (2^-20 ~ 1e-6 >> 1e-13), so the
+// common case is a two-way softmax: w_a = 1 / (1 + 2^(lb - la)), w_b = 1 - w_a  (2 MUFU instead of 4).
+__device__ __forceinline__ void masked_row_fast(float la, float lb, float& wa, float& wb) {
+    wa = rcp_approx(1.0f + ex2_approx(lb - la));
+    wb = 1.0f - wa;
+    if (fmaxf(la, lb) < -20.f) masked_row_exact(la, lb, wa, wb);
+}
+__device__ __forceinline__ void masked_row_fast2(float laA, float lbA, float laB, float lbB, float& waA, float& wbA, float& waB,
+                                                 float& wbB) {
+    waA = rcp_approx(1.0f + ex2_approx(lbA - laA)); wbA = 1.0f - waA;
+    waB = rcp_approx(1.0f + ex2_approx(lbB - laB)); wbB = 1.0f - waB;
+    if (fminf(fmaxf(laA, lbA), fmaxf(laB, lbB)) < -20.f) {
+        masked_row_exact(laA, lbA, waA, wbA);
+        masked_row_exact(laB, lbB, waB, wbB);
+    }
 }
 
 struct UmmaParams;
@@ -206,11 +222,10 @@ __device__ __forceinline__ void attention_fast(const __half* __restrict__ QK16, 
             float2 fA = __half22float2(accA), fB = __half22float2(accB);
             float pA = fA.x + fA.y, pB = fB.x + fB.y;
             pA += __shfl_xor_sync(0xffffffffu, pA, 1); pB += __shfl_xor_sync(0xffffffffu, pB, 1);
-            lbA = pA * 0.25f; lbB = pB * 0.25f;
+            lbA = pA; lbB = pB;                      // the Q rows carry log2(e) / 4
         }
         float waA, wbA, waB, wbB;
-        masked_row_fast(laA, lbA, waA, wbA);
-        masked_row_fast(laB, lbB, waB, wbB);
+        masked_row_fast2(laA, lbA, laB, lbB, waA, wbA, waB, wbB);
         const __half2 wa2 = __float2half2_rn(waA), wb2 = __float2half2_rn(wbA);
         sts128(a_chunk_addr(a_base, rw, j),
                h2u(__hfma2(wb2, u2h(bA.x), __hmul2(wa2, u2h(aA.x)))), h2u(__hfma2(wb2, u2h(bA.y), __hmul2(wa2, u2h(aA.y)))),
