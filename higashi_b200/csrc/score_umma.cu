@@ -254,70 +254,130 @@ __global__ void __launch_bounds__(UM_THREADS, 1) score_umma_kernel(UmmaParams p)
             }
             // z = y + h . W1^T : accumulate onto y (still in TMEM) -- the residual is free
             issue_gemm<4, 64>(wg, wtid, a_base, sbase + (HI ? SM_B_W1 : SMF_B_W1), 64, t_y, 1u, bar_mma);
-            mbar_wait(bar_mma, phase); phase ^= 1;
-            tc_fence_after();
-
-            // ------------------------------------------------------------------ u = (LN1(z + b1) - S)^2 (A tile, K = 64)
-            {
-                uint32_t r0[32], r1[32];
-                tmem_ld32(t_y + t_lane, r0);
-                tmem_ld32(t_y + t_lane + 32, r1);
-                tmem_ld_wait();
-                float2 x[32];
-                float2 sA = make_float2(0.f, 0.f), sB = sA;
-#pragma unroll
-                for (int i = 0; i < 16; i += 2) {
-                    const float* bq = cst + (HI ? CST_B1 : CST_B1C) + 2 * i;
-                    x[i] = __fadd2_rn(f2(r0[2 * i], r0[2 * i + 1]), make_float2(bq[0], bq[1]));
-                    x[i + 1] = __fadd2_rn(f2(r0[2 * i + 2], r0[2 * i + 3]), make_float2(bq[2], bq[3]));
-                    x[16 + i] = __fadd2_rn(f2(r1[2 * i], r1[2 * i + 1]), make_float2(bq[32], bq[33]));
-                    x[17 + i] = __fadd2_rn(f2(r1[2 * i + 2], r1[2 * i + 3]), make_float2(bq[34], bq[35]));
-                    if constexpr (HI) {
-                        sA = __fadd2_rn(sA, __fadd2_rn(x[i], x[16 + i]));
-                        sB = __fadd2_rn(sB, __fadd2_rn(x[i + 1], x[17 + i]));
-                    }
-                }
-                float2 vA = make_float2(0.f, 0.f), vB = vA, vC = vA, vD = vA;
-                if constexpr (HI) {
-                    const float mean = ((sA.x + sA.y) + (sB.x + sB.y)) * (1.0f / 64.0f);
-                    const float2 nm = make_float2(-mean, -mean);
-#pragma unroll
-                    for (int i = 0; i < 32; ++i) x[i] = __fadd2_rn(x[i], nm);
-                }
-                // fast variant: z arrives centred (y_c + h . W1c^T + b1c has zero row mean by construction)
-#pragma unroll
-                for (int i = 0; i < 32; i += 4) {
-                    vA = __ffma2_rn(x[i], x[i], vA); vB = __ffma2_rn(x[i + 1], x[i + 1], vB);
-                    vC = __ffma2_rn(x[i + 2], x[i + 2], vC); vD = __ffma2_rn(x[i + 3], x[i + 3], vD);
-                }
-                vA = __fadd2_rn(__fadd2_rn(vA, vB), __fadd2_rn(vC, vD));
-                const float rstd = rsqrtf((vA.x + vA.y) * (1.0f / 64.0f) + HSG_LN_EPS);
-                const float2 rs = make_float2(rstd, rstd);
-                // S tables are stored in feature blocks ([16][n_tokens][4]) so that consecutive rows (consecutive bins) read
-                // consecutive 16-byte quads: 16 coalesced 128-bit loads per row instead of 16 row-scattered ones
+            // S rows of this token (feature blocks of 4): requested BEFORE waiting for the MMA so that their L2 latency hides
+            // behind the tensor-core round trip (volatile loads: the compiler must not sink them below the wait)
+            float4 sreg[16];
+            if constexpr (!HI) {
                 const float4* Scol = reinterpret_cast<const float4*>((t == 0) ? p.cellSb : p.binSb) + ((t == 0) ? cell : (t == 1 ? pr.x : pr.y));
                 const long long sstr = (t == 0) ? p.n_cells : p.n_bins;
 #pragma unroll
-                for (int c = 0; c < 8; ++c) {
-                    const float* gq = cst + CST_G1 + c * 8;
-                    uint32_t pk[4], pl[4];
-                    const float4 s0 = __ldg(Scol + (2 * c) * sstr), s1 = __ldg(Scol + (2 * c + 1) * sstr);
-                    const float svv[8] = {s0.x, s0.y, s0.z, s0.w, s1.x, s1.y, s1.z, s1.w};
+                for (int c = 0; c < 16; ++c) sreg[c] = ldg_nc_v4_volatile(Scol + c * sstr);
+            }
+            mbar_wait(bar_mma, phase); phase ^= 1;
+            tc_fence_after();
+
+            if constexpr (!HI) {
+                // ---------------------------------------------------------------- u = (LN1(z + b1c) - S)^2 (A tile, K = 64)
+                // z arrives centred (y_c + h . W1c^T + b1c has zero row mean by construction).  Two passes over TMEM keep the
+                // register footprint at 32 columns + the 64 prefetched S values: pass 1 = row variance, pass 2 = u.
+                float2 rs;
+                {
+                    float2 vA = make_float2(0.f, 0.f), vB = vA, vC = vA, vD = vA;
 #pragma unroll
-                    for (int q = 0; q < 4; ++q) {
-                        float2 sv = make_float2(svv[2 * q], svv[2 * q + 1]);       // the table holds beta - S
-                        float2 tz = __fmul2_rn(x[c * 4 + q], rs);
-                        float2 u = __ffma2_rn(tz, make_float2(gq[2 * q], gq[2 * q + 1]), sv);
-                        u = __fmul2_rn(u, u);
-                        pk[q] = pack_h2(u.x, u.y);
-                        if constexpr (HI) {             // u = hi + lo, both fp16: the classifier GEMM sees ~22 bits of u
-                            float2 hf = __half22float2(u2h(pk[q]));
-                            float2 lo = __fadd2_rn(u, make_float2(-hf.x, -hf.y));
-                            pl[q] = pack_h2(lo.x, lo.y);
+                    for (int half = 0; half < 2; ++half) {
+                        uint32_t r[32];
+                        tmem_ld32(t_y + t_lane + half * 32, r);
+                        tmem_ld_wait();
+#pragma unroll
+                        for (int i = 0; i < 16; i += 4) {
+                            const float* bq = cst + CST_B1C + half * 32 + 2 * i;
+                            float2 a = __fadd2_rn(f2(r[2 * i], r[2 * i + 1]), make_float2(bq[0], bq[1]));
+                            float2 b = __fadd2_rn(f2(r[2 * i + 2], r[2 * i + 3]), make_float2(bq[2], bq[3]));
+                            float2 c2 = __fadd2_rn(f2(r[2 * i + 4], r[2 * i + 5]), make_float2(bq[4], bq[5]));
+                            float2 d2 = __fadd2_rn(f2(r[2 * i + 6], r[2 * i + 7]), make_float2(bq[6], bq[7]));
+                            vA = __ffma2_rn(a, a, vA); vB = __ffma2_rn(b, b, vB); vC = __ffma2_rn(c2, c2, vC); vD = __ffma2_rn(d2, d2, vD);
                         }
                     }
-                    sts128(a_chunk_addr(a_base, wtid, c), pk[0], pk[1], pk[2], pk[3]);
-                    if constexpr (HI) sts128(a_chunk_addr(a_base + 16384u, wtid, c), pl[0], pl[1], pl[2], pl[3]);
+                    vA = __fadd2_rn(__fadd2_rn(vA, vB), __fadd2_rn(vC, vD));
+                    const float rstd = rsqrtf((vA.x + vA.y) * (1.0f / 64.0f) + HSG_LN_EPS);
+                    rs = make_float2(rstd, rstd);
+                }
+#pragma unroll
+                for (int half = 0; half < 2; ++half) {
+                    uint32_t r[32];
+                    tmem_ld32(t_y + t_lane + half * 32, r);
+                    tmem_ld_wait();
+#pragma unroll
+                    for (int c = 0; c < 4; ++c) {
+                        const float* bq = cst + CST_B1C + half * 32 + c * 8;
+                        const float* gq = cst + CST_G1 + half * 32 + c * 8;
+                        const float4 s0 = sreg[half * 8 + 2 * c], s1 = sreg[half * 8 + 2 * c + 1];
+                        const float svv[8] = {s0.x, s0.y, s0.z, s0.w, s1.x, s1.y, s1.z, s1.w};
+                        uint32_t pk[4];
+#pragma unroll
+                        for (int q = 0; q < 4; ++q) {
+                            float2 x = __fadd2_rn(f2(r[c * 8 + 2 * q], r[c * 8 + 2 * q + 1]), make_float2(bq[2 * q], bq[2 * q + 1]));
+                            float2 tz = __fmul2_rn(x, rs);
+                            float2 u = __ffma2_rn(tz, make_float2(gq[2 * q], gq[2 * q + 1]), make_float2(svv[2 * q], svv[2 * q + 1]));
+                            u = __fmul2_rn(u, u);
+                            pk[q] = pack_h2(u.x, u.y);
+                        }
+                        sts128(a_chunk_addr(a_base, wtid, half * 4 + c), pk[0], pk[1], pk[2], pk[3]);
+                    }
+                }
+            } else {
+                // ------------------------------------------------------------------ u = (LN1(z + b1) - S)^2 (A tile, K = 64)
+                {
+                    uint32_t r0[32], r1[32];
+                    tmem_ld32(t_y + t_lane, r0);
+                    tmem_ld32(t_y + t_lane + 32, r1);
+                    tmem_ld_wait();
+                    float2 x[32];
+                    float2 sA = make_float2(0.f, 0.f), sB = sA;
+    #pragma unroll
+                    for (int i = 0; i < 16; i += 2) {
+                        const float* bq = cst + (HI ? CST_B1 : CST_B1C) + 2 * i;
+                        x[i] = __fadd2_rn(f2(r0[2 * i], r0[2 * i + 1]), make_float2(bq[0], bq[1]));
+                        x[i + 1] = __fadd2_rn(f2(r0[2 * i + 2], r0[2 * i + 3]), make_float2(bq[2], bq[3]));
+                        x[16 + i] = __fadd2_rn(f2(r1[2 * i], r1[2 * i + 1]), make_float2(bq[32], bq[33]));
+                        x[17 + i] = __fadd2_rn(f2(r1[2 * i + 2], r1[2 * i + 3]), make_float2(bq[34], bq[35]));
+                        if constexpr (HI) {
+                            sA = __fadd2_rn(sA, __fadd2_rn(x[i], x[16 + i]));
+                            sB = __fadd2_rn(sB, __fadd2_rn(x[i + 1], x[17 + i]));
+                        }
+                    }
+                    float2 vA = make_float2(0.f, 0.f), vB = vA, vC = vA, vD = vA;
+                    if constexpr (HI) {
+                        const float mean = ((sA.x + sA.y) + (sB.x + sB.y)) * (1.0f / 64.0f);
+                        const float2 nm = make_float2(-mean, -mean);
+    #pragma unroll
+                        for (int i = 0; i < 32; ++i) x[i] = __fadd2_rn(x[i], nm);
+                    }
+                    // fast variant: z arrives centred (y_c + h . W1c^T + b1c has zero row mean by construction)
+    #pragma unroll
+                    for (int i = 0; i < 32; i += 4) {
+                        vA = __ffma2_rn(x[i], x[i], vA); vB = __ffma2_rn(x[i + 1], x[i + 1], vB);
+                        vC = __ffma2_rn(x[i + 2], x[i + 2], vC); vD = __ffma2_rn(x[i + 3], x[i + 3], vD);
+                    }
+                    vA = __fadd2_rn(__fadd2_rn(vA, vB), __fadd2_rn(vC, vD));
+                    const float rstd = rsqrtf((vA.x + vA.y) * (1.0f / 64.0f) + HSG_LN_EPS);
+                    const float2 rs = make_float2(rstd, rstd);
+                    // S tables are stored in feature blocks ([16][n_tokens][4]) so that consecutive rows (consecutive bins) read
+                    // consecutive 16-byte quads: 16 coalesced 128-bit loads per row instead of 16 row-scattered ones
+                    const float4* Scol = reinterpret_cast<const float4*>((t == 0) ? p.cellSb : p.binSb) + ((t == 0) ? cell : (t == 1 ? pr.x : pr.y));
+                    const long long sstr = (t == 0) ? p.n_cells : p.n_bins;
+    #pragma unroll
+                    for (int c = 0; c < 8; ++c) {
+                        const float* gq = cst + CST_G1 + c * 8;
+                        uint32_t pk[4], pl[4];
+                        const float4 s0 = __ldg(Scol + (2 * c) * sstr), s1 = __ldg(Scol + (2 * c + 1) * sstr);
+                        const float svv[8] = {s0.x, s0.y, s0.z, s0.w, s1.x, s1.y, s1.z, s1.w};
+    #pragma unroll
+                        for (int q = 0; q < 4; ++q) {
+                            float2 sv = make_float2(svv[2 * q], svv[2 * q + 1]);       // the table holds beta - S
+                            float2 tz = __fmul2_rn(x[c * 4 + q], rs);
+                            float2 u = __ffma2_rn(tz, make_float2(gq[2 * q], gq[2 * q + 1]), sv);
+                            u = __fmul2_rn(u, u);
+                            pk[q] = pack_h2(u.x, u.y);
+                            if constexpr (HI) {             // u = hi + lo, both fp16: the classifier GEMM sees ~22 bits of u
+                                float2 hf = __half22float2(u2h(pk[q]));
+                                float2 lo = __fadd2_rn(u, make_float2(-hf.x, -hf.y));
+                                pl[q] = pack_h2(lo.x, lo.y);
+                            }
+                        }
+                        sts128(a_chunk_addr(a_base, wtid, c), pk[0], pk[1], pk[2], pk[3]);
+                        if constexpr (HI) sts128(a_chunk_addr(a_base + 16384u, wtid, c), pl[0], pl[1], pl[2], pl[3]);
+                    }
                 }
             }
             if constexpr (HI) {
