@@ -185,15 +185,81 @@ struct UmmaParams;
 // of head h; lanes with h >= 4 handle them in swapped order so that the 8 lanes of a quarter-warp hit 8 distinct swizzle
 // slots when storing (no 2-way bank conflict).  s_pr: the (bin_i, bin_j) pairs of the warpgroup's 128 rows in shared memory;
 // the calling warp handles rows row0 .. row0 + 4 NIT - 1.
+__device__ __forceinline__ uint4 ldg_nc_u4_volatile(const uint4* p) {
+    uint4 v;
+    asm volatile("ld.global.nc.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(p));
+    return v;
+}
+__device__ __forceinline__ float ldg_nc_f32_volatile(const float* p) {
+    float v;
+    asm volatile("ld.global.nc.f32 %0, [%1];" : "=f"(v) : "l"(p));
+    return v;
+}
+// everything one lane needs from the token tables for one row of one token position
+struct AttRow {
+    uint4 qA, qB, kA, kB;     // T != 0: this lane's chunks of Q[tq] and K[tk] ;  T == 0: V[bi] in qA/qB
+    uint4 bA, bB;             // V of the "b" token
+    float laA, laB, lbA, lbB; // logits that come from the cross-term table
+    int rw;
+};
+template <int T>
+__device__ __forceinline__ void att_load(AttRow& r, int rw, const int2* s_pr, const uint4* QKj, const float* XSa, const uint4* BVj,
+                                         uint32_t tokbase) {
+    const int2 pr = s_pr[rw];
+    const uint32_t ti = tokbase + (uint32_t)pr.x, tj = tokbase + (uint32_t)pr.y;
+    r.rw = rw;
+    if (T == 0) {
+        r.laA = ldg_nc_f32_volatile(XSa + ti * 16u); r.laB = ldg_nc_f32_volatile(XSa + ti * 16u + 4);
+        r.lbA = ldg_nc_f32_volatile(XSa + tj * 16u); r.lbB = ldg_nc_f32_volatile(XSa + tj * 16u + 4);
+        r.qA = ldg_nc_u4_volatile(BVj + (uint32_t)pr.x * 16u); r.qB = ldg_nc_u4_volatile(BVj + (uint32_t)pr.x * 16u + 8);
+        r.bA = ldg_nc_u4_volatile(BVj + (uint32_t)pr.y * 16u); r.bB = ldg_nc_u4_volatile(BVj + (uint32_t)pr.y * 16u + 8);
+    } else {
+        const uint32_t tq = (T == 1) ? ti : tj, tk = (T == 1) ? tj : ti, bv = (uint32_t)((T == 1) ? pr.y : pr.x);
+        r.laA = ldg_nc_f32_volatile(XSa + tq * 16u); r.laB = ldg_nc_f32_volatile(XSa + tq * 16u + 4);
+        r.qA = ldg_nc_u4_volatile(QKj + tq * 32u); r.qB = ldg_nc_u4_volatile(QKj + tq * 32u + 8);
+        r.kA = ldg_nc_u4_volatile(QKj + tk * 32u + 16); r.kB = ldg_nc_u4_volatile(QKj + tk * 32u + 24);
+        r.bA = ldg_nc_u4_volatile(BVj + bv * 16u); r.bB = ldg_nc_u4_volatile(BVj + bv * 16u + 8);
+    }
+}
+template <int T>
+__device__ __forceinline__ void att_compute(const AttRow& r, uint4 vcA, uint4 vcB, uint32_t a_base, int j) {
+    float laA = r.laA, laB = r.laB, lbA, lbB;
+    uint4 aA, aB;
+    if (T == 0) {
+        lbA = r.lbA; lbB = r.lbB; aA = r.qA; aB = r.qB;
+    } else {
+        aA = vcA; aB = vcB;
+        __half2 accA = __hmul2(u2h(r.qA.x), u2h(r.kA.x)), accB = __hmul2(u2h(r.qB.x), u2h(r.kB.x));
+        accA = __hfma2(u2h(r.qA.y), u2h(r.kA.y), accA); accB = __hfma2(u2h(r.qB.y), u2h(r.kB.y), accB);
+        accA = __hfma2(u2h(r.qA.z), u2h(r.kA.z), accA); accB = __hfma2(u2h(r.qB.z), u2h(r.kB.z), accB);
+        accA = __hfma2(u2h(r.qA.w), u2h(r.kA.w), accA); accB = __hfma2(u2h(r.qB.w), u2h(r.kB.w), accB);
+        float2 fA = __half22float2(accA), fB = __half22float2(accB);
+        float pA = fA.x + fA.y, pB = fB.x + fB.y;
+        pA += __shfl_xor_sync(0xffffffffu, pA, 1); pB += __shfl_xor_sync(0xffffffffu, pB, 1);
+        lbA = pA; lbB = pB;                      // the Q rows carry log2(e) / 4
+    }
+    float waA, wbA, waB, wbB;
+    masked_row_fast2(laA, lbA, laB, lbB, waA, wbA, waB, wbB);
+    const uint4 bA = r.bA, bB = r.bB;
+    const __half2 wa2 = __float2half2_rn(waA), wb2 = __float2half2_rn(wbA);
+    sts128(a_chunk_addr(a_base, r.rw, j),
+           h2u(__hfma2(wb2, u2h(bA.x), __hmul2(wa2, u2h(aA.x)))), h2u(__hfma2(wb2, u2h(bA.y), __hmul2(wa2, u2h(aA.y)))),
+           h2u(__hfma2(wb2, u2h(bA.z), __hmul2(wa2, u2h(aA.z)))), h2u(__hfma2(wb2, u2h(bA.w), __hmul2(wa2, u2h(aA.w)))));
+    const __half2 wc2 = __float2half2_rn(waB), wd2 = __float2half2_rn(wbB);
+    sts128(a_chunk_addr(a_base, r.rw, 8 + j),
+           h2u(__hfma2(wd2, u2h(bB.x), __hmul2(wc2, u2h(aB.x)))), h2u(__hfma2(wd2, u2h(bB.y), __hmul2(wc2, u2h(aB.y)))),
+           h2u(__hfma2(wd2, u2h(bB.z), __hmul2(wc2, u2h(aB.z)))), h2u(__hfma2(wd2, u2h(bB.w), __hmul2(wc2, u2h(aB.w)))));
+}
+// Software-pipelined: the table rows of row group it + 1 are requested (volatile loads, the compiler keeps the order) before the
+// math of row group it, so one L2 round trip overlaps one group's compute instead of stalling every loop trip.
 template <int T, int NIT>
 __device__ __forceinline__ void attention_fast(const __half* __restrict__ QK16, const float* __restrict__ XS,
                                                const __half* __restrict__ binV16, const __half* __restrict__ cellV16,
                                                const int2* s_pr, int lane, int row0, uint32_t a_base, uint32_t tokbase, int cell) {
     // Lane j = lane & 7 of a row owns the 16-byte chunks j and 8 + j of the 256-byte Q / K / V rows, i.e. one half of head
     // hA = j >> 1 and one half of head hB = 4 + (j >> 1): every warp-level 128-bit load then covers four fully used 128-byte
-    // lines (the shared-memory / L1 data pipe is what bounds this kernel).  The two lanes that share a head add their partial
-    // dot products with one shuffle.
-    const int j = lane & 7, rsub = lane >> 3, hA = j >> 1, hB = 4 + (j >> 1);
+    // lines.  The two lanes that share a head add their partial dot products with one shuffle.
+    const int j = lane & 7, rsub = lane >> 3, hA = j >> 1;
     const uint4* QKj = reinterpret_cast<const uint4*>(QK16) + j;
     const uint4* BVj = reinterpret_cast<const uint4*>(binV16) + j;
     const float* XSa = XS + hA + (T == 0 ? 0 : 8);
@@ -202,45 +268,14 @@ __device__ __forceinline__ void attention_fast(const __half* __restrict__ QK16, 
         const uint4* vc = reinterpret_cast<const uint4*>(cellV16) + (uint32_t)cell * 16u + j;
         vcA = __ldg(vc); vcB = __ldg(vc + 8);
     }
-#pragma unroll 2
-    for (int it = 0; it < NIT; ++it) {
-        const int rw = row0 + it * 4 + rsub;          // row of the 128-row tile handled by this lane in this step
-        const int2 pr = s_pr[rw];
-        const uint32_t ti = tokbase + (uint32_t)pr.x, tj = tokbase + (uint32_t)pr.y;
-        float laA, laB, lbA, lbB;
-        uint4 aA, aB, bA, bB;
-        if (T == 0) {
-            laA = __ldg(XSa + ti * 16u); laB = __ldg(XSa + ti * 16u + 4);
-            lbA = __ldg(XSa + tj * 16u); lbB = __ldg(XSa + tj * 16u + 4);
-            aA = __ldg(BVj + (uint32_t)pr.x * 16u); aB = __ldg(BVj + (uint32_t)pr.x * 16u + 8);
-            bA = __ldg(BVj + (uint32_t)pr.y * 16u); bB = __ldg(BVj + (uint32_t)pr.y * 16u + 8);
-        } else {
-            const uint32_t tq = (T == 1) ? ti : tj, tk = (T == 1) ? tj : ti, bv = (uint32_t)((T == 1) ? pr.y : pr.x);
-            laA = __ldg(XSa + tq * 16u); laB = __ldg(XSa + tq * 16u + 4);
-            const uint4 qA = __ldg(QKj + tq * 32u), qB = __ldg(QKj + tq * 32u + 8);
-            const uint4 kA = __ldg(QKj + tk * 32u + 16), kB = __ldg(QKj + tk * 32u + 24);
-            bA = __ldg(BVj + bv * 16u); bB = __ldg(BVj + bv * 16u + 8);
-            aA = vcA; aB = vcB;
-            __half2 accA = __hmul2(u2h(qA.x), u2h(kA.x)), accB = __hmul2(u2h(qB.x), u2h(kB.x));
-            accA = __hfma2(u2h(qA.y), u2h(kA.y), accA); accB = __hfma2(u2h(qB.y), u2h(kB.y), accB);
-            accA = __hfma2(u2h(qA.z), u2h(kA.z), accA); accB = __hfma2(u2h(qB.z), u2h(kB.z), accB);
-            accA = __hfma2(u2h(qA.w), u2h(kA.w), accA); accB = __hfma2(u2h(qB.w), u2h(kB.w), accB);
-            float2 fA = __half22float2(accA), fB = __half22float2(accB);
-            float pA = fA.x + fA.y, pB = fB.x + fB.y;
-            pA += __shfl_xor_sync(0xffffffffu, pA, 1); pB += __shfl_xor_sync(0xffffffffu, pB, 1);
-            lbA = pA; lbB = pB;                      // the Q rows carry log2(e) / 4
-        }
-        float waA, wbA, waB, wbB;
-        masked_row_fast2(laA, lbA, laB, lbB, waA, wbA, waB, wbB);
-        const __half2 wa2 = __float2half2_rn(waA), wb2 = __float2half2_rn(wbA);
-        sts128(a_chunk_addr(a_base, rw, j),
-               h2u(__hfma2(wb2, u2h(bA.x), __hmul2(wa2, u2h(aA.x)))), h2u(__hfma2(wb2, u2h(bA.y), __hmul2(wa2, u2h(aA.y)))),
-               h2u(__hfma2(wb2, u2h(bA.z), __hmul2(wa2, u2h(aA.z)))), h2u(__hfma2(wb2, u2h(bA.w), __hmul2(wa2, u2h(aA.w)))));
-        const __half2 wc2 = __float2half2_rn(waB), wd2 = __float2half2_rn(wbB);
-        sts128(a_chunk_addr(a_base, rw, 8 + j),
-               h2u(__hfma2(wd2, u2h(bB.x), __hmul2(wc2, u2h(aB.x)))), h2u(__hfma2(wd2, u2h(bB.y), __hmul2(wc2, u2h(aB.y)))),
-               h2u(__hfma2(wd2, u2h(bB.z), __hmul2(wc2, u2h(aB.z)))), h2u(__hfma2(wd2, u2h(bB.w), __hmul2(wc2, u2h(aB.w)))));
-        (void)hB;
+    AttRow A, B;
+    att_load<T>(A, row0 + rsub, s_pr, QKj, XSa, BVj, tokbase);
+#pragma unroll 1
+    for (int it = 0; it < NIT; it += 2) {
+        att_load<T>(B, row0 + (it + 1) * 4 + rsub, s_pr, QKj, XSa, BVj, tokbase);
+        att_compute<T>(A, vcA, vcB, a_base, j);
+        if (it + 2 < NIT) att_load<T>(A, row0 + (it + 2) * 4 + rsub, s_pr, QKj, XSa, BVj, tokbase);
+        att_compute<T>(B, vcA, vcB, a_base, j);
     }
 }
 
