@@ -215,10 +215,24 @@ extern "C" int hsg_set_contacts(hsg_ctx* c, const int64_t* row_ptr, const int32_
     HSG_CHECK(row_ptr && (nnz == 0 || (col && val)), "null contact arrays");
     HSG_CHECK(n_rows == (int64_t)c->n_cells * c->n_bins, "contacts: n_rows must be n_cells * n_bins");
     HSG_CHECK(row_ptr[0] == 0 && row_ptr[n_rows] == nnz, "contacts: row_ptr does not span nnz");
-    if (dev_alloc(&c->row_ptr, (size_t)n_rows + 1) || dev_alloc(&c->col, (size_t)nnz) || dev_alloc(&c->val, (size_t)nnz)) return 1;
-    HSG_CUDA(cudaMemcpy(c->row_ptr, row_ptr, (size_t)(n_rows + 1) * sizeof(int64_t), cudaMemcpyHostToDevice));
-    HSG_CUDA(cudaMemcpy(c->col, col, (size_t)nnz * sizeof(int32_t), cudaMemcpyHostToDevice));
-    HSG_CUDA(cudaMemcpy(c->val, val, (size_t)nnz * sizeof(float), cudaMemcpyHostToDevice));
+    // a re-upload of a same-sized (or smaller) matrix reuses the device buffers: no cudaFree / cudaMalloc round trip
+    if (c->col != nullptr) HSG_CUDA(cudaDeviceSynchronize());      // work queued on any stream may still read the old contents
+    if (n_rows + 1 > c->cap_rows) {
+        if (dev_alloc(&c->row_ptr, (size_t)n_rows + 1)) return 1;
+        c->cap_rows = n_rows + 1;
+    }
+    if (nnz > c->cap_nnz || c->col == nullptr) {
+        if (dev_alloc(&c->col, (size_t)nnz) || dev_alloc(&c->val, (size_t)nnz)) return 1;
+        c->cap_nnz = nnz;
+    }
+    // three back-to-back DMA transfers on the context stream (truly asynchronous from pinned memory), one wait at the end:
+    // the caller may reuse its arrays as soon as this returns
+    HSG_CUDA(cudaMemcpyAsync(c->row_ptr, row_ptr, (size_t)(n_rows + 1) * sizeof(int64_t), cudaMemcpyHostToDevice, c->stream));
+    if (nnz > 0) {
+        HSG_CUDA(cudaMemcpyAsync(c->col, col, (size_t)nnz * sizeof(int32_t), cudaMemcpyHostToDevice, c->stream));
+        HSG_CUDA(cudaMemcpyAsync(c->val, val, (size_t)nnz * sizeof(float), cudaMemcpyHostToDevice, c->stream));
+    }
+    HSG_CUDA(cudaStreamSynchronize(c->stream));
     c->n_rows = n_rows; c->nnz = nnz;
     return 0;
 }
@@ -230,9 +244,12 @@ extern "C" int hsg_set_neighbors(hsg_ctx* c, const int32_t* nbr, const float* w,
     HSG_CHECK(w != nullptr && k1 >= 1, "bad neighbour arguments");
     for (int64_t i = 0; i < (int64_t)c->n_cells * k1; ++i)
         HSG_CHECK(nbr[i] >= 0 && nbr[i] < c->n_cells, "neighbour id out of range");
-    if (dev_alloc(&c->nbr, (size_t)c->n_cells * k1) || dev_alloc(&c->nbr_w, (size_t)c->n_cells * k1)) return 1;
-    HSG_CUDA(cudaMemcpy(c->nbr, nbr, (size_t)c->n_cells * k1 * sizeof(int32_t), cudaMemcpyHostToDevice));
-    HSG_CUDA(cudaMemcpy(c->nbr_w, w, (size_t)c->n_cells * k1 * sizeof(float), cudaMemcpyHostToDevice));
+    if (c->nbr == nullptr || k1 != c->k1 || !c->weighted) {
+        if (dev_alloc(&c->nbr, (size_t)c->n_cells * k1) || dev_alloc(&c->nbr_w, (size_t)c->n_cells * k1)) return 1;
+    }
+    HSG_CUDA(cudaMemcpyAsync(c->nbr, nbr, (size_t)c->n_cells * k1 * sizeof(int32_t), cudaMemcpyHostToDevice, c->stream));
+    HSG_CUDA(cudaMemcpyAsync(c->nbr_w, w, (size_t)c->n_cells * k1 * sizeof(float), cudaMemcpyHostToDevice, c->stream));
+    HSG_CUDA(cudaStreamSynchronize(c->stream));
     c->k1 = k1; c->weighted = true;
     return 0;
 }

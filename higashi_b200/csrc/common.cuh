@@ -65,6 +65,7 @@ struct hsg_ctx {
     // contacts: packed CSR
     int64_t* row_ptr = nullptr; int32_t* col = nullptr; float* val = nullptr;
     int64_t n_rows = 0, nnz = 0;
+    int64_t cap_rows = 0, cap_nnz = 0;          // allocated capacity of the contact arrays (re-uploads reuse the buffers)
     // neighbours
     int32_t* nbr = nullptr; float* nbr_w = nullptr; int k1 = 1; bool weighted = false;
 
