@@ -74,7 +74,7 @@ static void free_derived(hsg_ctx* c) {
     { __half* p = (__half*)c->QK16; dev_free(p); c->QK16 = nullptr; }
     { __half* p = (__half*)c->binV16; dev_free(p); c->binV16 = nullptr; }
     { __half* p = (__half*)c->cellV16; dev_free(p); c->cellV16 = nullptr; }
-    dev_free(c->XS); dev_free(c->binSb); dev_free(c->cellSb); dev_free(c->wimg); dev_free(c->cst);
+    dev_free(c->XS); dev_free(c->binSb); dev_free(c->cellSb); dev_free(c->wimg); dev_free(c->cst); dev_free(c->pj_wimg);
     c->use_umma = false;
     dev_free(c->stage_out[0]); dev_free(c->stage_out[1]); c->stage_bytes = 0;
     c->prepared = false;
@@ -455,6 +455,7 @@ extern "C" int hsg_prepare(hsg_ctx* c, int precision, int local_transfer_range, 
     if (launch_pair_bias(c, c->stream)) return 1;
     // Tensor-core mode exists for d_model = 64; d_model = 128 keeps the (more precise) fp32 kernels for now.
     c->use_umma = (precision != HSG_PREC_FP32 && d == 64);
+    c->use_proj_umma = false;
     // softplus / raw heads pass the logit error through with slope ~1: they get the high-accuracy variant
     c->umma_hi = c->use_umma && (precision == HSG_PREC_TC16_HI || activation != HSG_ACT_SIGMOID);
     size_t per_cell;
@@ -471,6 +472,18 @@ extern "C" int hsg_prepare(hsg_ctx* c, int precision, int local_transfer_range, 
         HSG_CUDA(cudaMemcpy(c->cst, cst.data(), cst.size() * sizeof(float), cudaMemcpyHostToDevice));
         HSG_CHECK(cst.size() <= 512, "constant block too large");
         memcpy(c->h_cst, cst.data(), cst.size() * sizeof(float));
+        // K1b on the tensor cores (fast variant only; a 128-token tile may touch at most 4 cells)
+        c->use_proj_umma = !c->umma_hi && c->n_bins >= proj_min_bins();
+        if (c->use_proj_umma) {
+            std::vector<unsigned char> pimg(proj_wimg_bytes());
+            std::vector<float> pcst(proj_cst_count(), 0.f);
+            proj_build_weights(h->v[HSG_W_SAGE_W].data(), h->v[HSG_W_SAGE_B].data(), h->v[HSG_W_QS].data(), h->v[HSG_W_KS].data(),
+                               h->v[HSG_W_ALN1_G].data(), h->v[HSG_W_ALN1_B].data(), h->v[HSG_W_ALN2_G].data(),
+                               h->v[HSG_W_ALN2_B].data(), pimg.data(), pcst.data());
+            if (dev_alloc(&c->pj_wimg, pimg.size())) return 1;
+            HSG_CUDA(cudaMemcpy(c->pj_wimg, pimg.data(), pimg.size(), cudaMemcpyHostToDevice));
+            memcpy(c->h_pj_cst, pcst.data(), pcst.size() * sizeof(float));
+        }
         __half *bv = nullptr, *cv = nullptr;
         if (dev_alloc(&bv, (size_t)c->n_bins * HSG_HD) || dev_alloc(&cv, (size_t)c->n_cells * HSG_HD) ||
             dev_alloc(&c->binSb, (size_t)c->n_bins * d) || dev_alloc(&c->cellSb, (size_t)c->n_cells * d)) return 1;
@@ -504,7 +517,8 @@ static int run_batch(hsg_ctx* c, int cell0, int nb, float* out, cudaStream_t s, 
     if (prof) HSG_CUDA(cudaEventRecord(c->ev[0], s));
     if (launch_gather(c, nullptr, cell0, nb, s)) return 1;
     if (prof) HSG_CUDA(cudaEventRecord(c->ev[1], s));
-    if (launch_token_project(c, cell0, nb, c->use_umma ? (c->umma_hi ? 2 : 1) : 0, s)) return 1;
+    if (c->use_umma && c->use_proj_umma) { if (launch_token_project_umma(c, cell0, nb, s)) return 1; }
+    else if (launch_token_project(c, cell0, nb, c->use_umma ? (c->umma_hi ? 2 : 1) : 0, s)) return 1;
     if (prof) HSG_CUDA(cudaEventRecord(c->ev[2], s));
     if (c->use_umma) { if (launch_score_pairs_umma(c, cell0, nb, out, s)) return 1; }
     else if (launch_score_pairs_f32(c, cell0, nb, out, s)) return 1;

@@ -93,6 +93,7 @@ struct hsg_ctx {
     float* XS = nullptr;                     // [batch, n_bins, 16] cross terms with the cell token
     void* binV16 = nullptr; float* binSb = nullptr; void* cellV16 = nullptr; float* cellSb = nullptr;
     unsigned char* wimg = nullptr; float* cst = nullptr; float h_cst[512] = {0};
+    unsigned char* pj_wimg = nullptr; float h_pj_cst[320] = {0}; bool use_proj_umma = false;   // tensor-core K1b (project_umma.cu)
     bool use_umma = false;
     bool umma_hi = false;                    // high-accuracy tensor-core variant (fp32 tables, hi/lo operand splits)
     int n_sm = 148;
@@ -121,6 +122,12 @@ int umma_build_weights(const float* fc1, const float* w0, const float* b0, const
                        const float* w1, const float* b1, const float* ln1_g, const float* c0, const float* cb0,
                        const float* cw1, const float* cb1, unsigned char* wimg_host, float* cst_host);
 int umma_wimg_bytes();
+int proj_wimg_bytes();
+int proj_cst_count();
+int proj_min_bins();
+int proj_build_weights(const float* sage_w, const float* sage_b, const float* wq, const float* wk, const float* g1, const float* b1,
+                       const float* g2, const float* b2, unsigned char* wimg_host, float* cst_host);
+int launch_token_project_umma(hsg_ctx* c, int cell_start, int n_cells_batch, cudaStream_t s);
 int umma_cst_count();
 int launch_score_pairs_f32(hsg_ctx* c, int cell_start, int n_cells_batch, float* out, cudaStream_t s);
 int launch_score_triplets_f32(hsg_ctx* c, const int64_t* x, int64_t B, float* out, cudaStream_t s);

@@ -1,0 +1,271 @@
+// project_umma.cu -- K1b (tensor-core mode): per-(cell, bin) token projection on tcgen05 / TMEM (sm_100a).
+//
+//   dyn = swish(nn([neigh | E_self]))                         (GraphSageEncoder_with_weights, Modules.py:1480)
+//   Q   = w_qs . layer_norm1(dyn),  K = w_ks . layer_norm2(dyn)   (MultiHeadAttention, Modules.py:1035-1044)
+//   qcK = Q_cell,h . K_b,h / 4,  kcQ = Q_b,h . K_cell,h / 4       (the cell-token logits, hoisted out of the scorer)
+//
+// One CTA (128 threads, thread r <-> token r <-> TMEM lane r) per tile of 128 consecutive tokens, two CTAs per SM:
+//   * A1 = [neigh | E_self] is converted to fp16 and written by the CTA itself into the canonical K-major SWIZZLE_128B
+//     layout (coalesced 8-lanes-per-row reads); the weights arrive once per CTA with one TMA bulk copy;
+//   * GEMM1  D1[128 x 64]  = A1 . G^T            (K = 128)  -> epilogue: + bias, swish, ONE set of LayerNorm statistics
+//   * GEMM2  D2[128 x 256] = xhat . [Wq' ; Wk']^T (K = 64)  with the two LayerNorm gains folded into the weights and the
+//     LayerNorm biases folded into the output bias: Q|K come out of a single N = 256 MMA;
+//   * epilogue 2 adds the bias, accumulates the cell cross terms against the cell's K / Q vectors (staged in shared memory),
+//     rounds to fp16 (Q pre-scaled by log2(e)/4, see score_umma.cu) into a swizzled staging tile and the CTA copies the tile
+//     out with fully coalesced 128-bit stores (a tile's Q|K rows are one contiguous 64 KB block of the table).
+// fp16 operands / fp32 accumulation: measured effect on the final score 1.9e-4 -> 2.0e-4 (scripts/bf16_emulation.py).
+#include "umma_common.cuh"
+
+#define PJ_B_G 0                 // [64 x 128] fp16, 2 K-atoms of 8 KB
+#define PJ_B_QK 16384            // [256 x 64] fp16, 1 K-atom of 32 KB
+#define PJ_WIMG_BYTES 49152
+#define PJ_A 49152               // A1 (32 KB: 2 atoms); A2 = atom 0; output staging (32 KB) reuses the region
+#define PJ_CELL 81920            // PJ_SLOTS x 256 floats: [cell K (128) | cell Q (128)] of the cells this tile touches
+#define PJ_SLOTS 4
+#define PJ_BAR (PJ_CELL + PJ_SLOTS * 1024)
+#define PJ_TMEM (PJ_BAR + 16)
+#define PJ_TOTAL (PJ_TMEM + 16)
+#define PJC_GB 0                 // constants: sage bias [64], Q bias [128], K bias [128]
+#define PJC_BQ 64
+#define PJC_BK 192
+#define PJC_COUNT 320
+
+struct ProjParams {
+    const float* neigh; const float* E_bin; const float* cellQ; const float* cellK;
+    const unsigned char* wimg;
+    float cst[PJC_COUNT];
+    __half* QK16; float* XS;
+    long long n_tok;
+    int n_bins, cell_start, n_tiles;
+};
+
+__global__ void __launch_bounds__(128, 2) project_umma_kernel(ProjParams p) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const uint32_t sraw = smem_u32(smem_raw);
+    const uint32_t sbase = (sraw + 1023u) & ~1023u;
+    unsigned char* smem = smem_raw + (sbase - sraw);
+    const float* cst = p.cst;
+    const uint32_t bar_w = sbase + PJ_BAR, bar_mma = sbase + PJ_BAR + 8;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + PJ_TMEM);
+    float* s_cell = reinterpret_cast<float*>(smem + PJ_CELL);
+
+    if (tid == 0) {
+        mbar_init(bar_w, 1);
+        mbar_init(bar_mma, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (tid < 32) {     // 256 TMEM columns per CTA (two CTAs per SM)
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(256) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    if (tid == 0) {
+        mbar_expect_tx(bar_w, PJ_WIMG_BYTES);
+        tma_bulk_g2s(sbase, p.wimg, PJ_WIMG_BYTES, bar_w);
+    }
+    const uint32_t t0 = *tmem_slot;
+    const uint32_t t_lane = ((uint32_t)(warp * 32)) << 16;
+    const uint32_t a_base = sbase + PJ_A;
+    mbar_wait(bar_w, 0);
+
+    uint32_t phase = 0;
+    const int j = lane & 7, rsub = lane >> 3;
+    for (int tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x) {
+        const long long tok0 = (long long)tile * 128;
+        const int cb0 = (int)(tok0 / p.n_bins);
+        const int g0 = (int)(tok0 - (long long)cb0 * p.n_bins);
+        {   // the K / Q vectors of the cells this tile touches
+            const long long last = (tok0 + 127 < p.n_tok ? tok0 + 127 : p.n_tok - 1);
+            const int nslots = (int)(last / p.n_bins) - cb0 + 1;
+            for (int i = tid; i < nslots * 256; i += 128) {
+                const int slot = i >> 8, e = i & 255;
+                const long long cell = (long long)p.cell_start + cb0 + slot;
+                s_cell[i] = (e < 128) ? __ldg(p.cellK + cell * 128 + e) : __ldg(p.cellQ + cell * 128 + (e - 128));
+            }
+        }
+        // ---------------------------------------------------------------- A1 = [neigh | E_self] -> fp16, swizzled
+#pragma unroll 2
+        for (int it = 0; it < 8; ++it) {
+            const int rw = warp * 32 + it * 4 + rsub;
+            long long tok = tok0 + rw;
+            if (tok >= p.n_tok) tok = p.n_tok - 1;
+            int g = g0 + (int)(tok - tok0);
+            while (g >= p.n_bins) g -= p.n_bins;
+            const float4* sn = reinterpret_cast<const float4*>(p.neigh + tok * 64 + j * 8);
+            const float4* se = reinterpret_cast<const float4*>(p.E_bin + (long long)g * 64 + j * 8);
+            const float4 n0 = __ldg(sn), n1 = __ldg(sn + 1), e0 = __ldg(se), e1 = __ldg(se + 1);
+            sts128(a_chunk_addr(a_base, rw, j), pack_h2(n0.x, n0.y), pack_h2(n0.z, n0.w), pack_h2(n1.x, n1.y), pack_h2(n1.z, n1.w));
+            sts128(a_chunk_addr(a_base, rw, 8 + j), pack_h2(e0.x, e0.y), pack_h2(e0.z, e0.w), pack_h2(e1.x, e1.y), pack_h2(e1.z, e1.w));
+        }
+        fence_async_smem();
+        tc_fence_before();
+        __syncthreads();
+        if (tid == 0) {
+            tc_fence_after();
+            mma_group<8, 64>(a_base, sbase + PJ_B_G, 64, t0, 0u);
+            umma_commit(bar_mma);
+        }
+        mbar_wait(bar_mma, phase); phase ^= 1;
+        tc_fence_after();
+
+        // ---------------------------------------------------------------- dyn = swish(. + b) ; xhat = LayerNorm statistics only
+        {
+            uint32_t r0[32], r1[32];
+            tmem_ld32(t0 + t_lane, r0);
+            tmem_ld32(t0 + t_lane + 32, r1);
+            tmem_ld_wait();
+            float x[64];
+            float s = 0.f;
+#pragma unroll
+            for (int i = 0; i < 64; ++i) {
+                const float v = __uint_as_float(i < 32 ? r0[i] : r1[i - 32]) + cst[PJC_GB + i];
+                const float d = v * rcp_approx(1.0f + ex2_approx(v * -1.4426950408889634f));      // v * sigmoid(v)
+                x[i] = d;
+                s += d;
+            }
+            const float mean = s * (1.0f / 64.0f);
+            float vs = 0.f;
+#pragma unroll
+            for (int i = 0; i < 64; ++i) { x[i] -= mean; vs = fmaf(x[i], x[i], vs); }
+            const float rstd = rsqrtf(vs * (1.0f / 64.0f) + HSG_LN_EPS);
+#pragma unroll
+            for (int c = 0; c < 8; ++c)
+                sts128(a_chunk_addr(a_base, tid, c), pack_h2(x[c * 8] * rstd, x[c * 8 + 1] * rstd), pack_h2(x[c * 8 + 2] * rstd, x[c * 8 + 3] * rstd),
+                       pack_h2(x[c * 8 + 4] * rstd, x[c * 8 + 5] * rstd), pack_h2(x[c * 8 + 6] * rstd, x[c * 8 + 7] * rstd));
+        }
+        fence_async_smem();
+        tc_fence_before();
+        __syncthreads();
+        if (tid == 0) {
+            tc_fence_after();
+            mma_group<4, 256>(a_base, sbase + PJ_B_QK, 256, t0, 0u);
+            umma_commit(bar_mma);
+        }
+        mbar_wait(bar_mma, phase); phase ^= 1;
+        tc_fence_after();
+
+        // ---------------------------------------------------------------- Q | K: bias, cross terms, fp16, coalesced copy-out
+        const long long tokr = tok0 + tid;
+        int slot_r = 0;
+        {
+            int g = g0 + tid;
+            while (g >= p.n_bins) { g -= p.n_bins; ++slot_r; }
+            if (slot_r >= PJ_SLOTS) slot_r = PJ_SLOTS - 1;         // rows past n_tok only (never stored)
+        }
+        float xs[16];
+#pragma unroll
+        for (int half = 0; half < 2; ++half) {
+            const float* cv = s_cell + slot_r * 256 + half * 128;          // Q half pairs with the cell's K, K half with its Q
+            const float* bias = cst + (half == 0 ? PJC_BQ : PJC_BK);
+            const float qs = (half == 0) ? HSG_L2E_QUARTER : 1.0f;
+#pragma unroll
+            for (int cc = 0; cc < 4; ++cc) {
+                uint32_t r[32];
+                tmem_ld32(t0 + t_lane + half * 128 + cc * 32, r);
+                tmem_ld_wait();
+                float crA = 0.f, crB = 0.f;
+#pragma unroll
+                for (int c8 = 0; c8 < 4; ++c8) {
+                    const float4 k0 = *reinterpret_cast<const float4*>(cv + cc * 32 + c8 * 8);
+                    const float4 k1 = *reinterpret_cast<const float4*>(cv + cc * 32 + c8 * 8 + 4);
+                    const float kk[8] = {k0.x, k0.y, k0.z, k0.w, k1.x, k1.y, k1.z, k1.w};
+                    float v[8];
+                    float cr = 0.f;
+#pragma unroll
+                    for (int q = 0; q < 8; ++q) {
+                        v[q] = __uint_as_float(r[c8 * 8 + q]) + bias[cc * 32 + c8 * 8 + q];
+                        cr = fmaf(v[q], kk[q], cr);
+                    }
+                    if (c8 < 2) crA += cr; else crB += cr;
+                    sts128(a_chunk_addr(a_base, tid, cc * 4 + c8), pack_h2(v[0] * qs, v[1] * qs), pack_h2(v[2] * qs, v[3] * qs),
+                           pack_h2(v[4] * qs, v[5] * qs), pack_h2(v[6] * qs, v[7] * qs));
+                }
+                // half 0: kcQ = Q_b . K_cell -> XS[8 + h] ; half 1: qcK = Q_cell . K_b -> XS[h]
+                xs[(half == 0 ? 8 : 0) + cc * 2] = crA * HSG_L2E_QUARTER;
+                xs[(half == 0 ? 8 : 0) + cc * 2 + 1] = crB * HSG_L2E_QUARTER;
+            }
+            __syncthreads();
+            // copy-out: lane j of a row group moves chunks j and 8 + j (8 lanes = one contiguous 128-byte line)
+#pragma unroll 2
+            for (int it = 0; it < 8; ++it) {
+                const int rw = warp * 32 + it * 4 + rsub;
+                const long long tok = tok0 + rw;
+                if (tok < p.n_tok) {
+                    uint4 a, b;
+                    asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(a.x), "=r"(a.y), "=r"(a.z), "=r"(a.w) : "r"(a_chunk_addr(a_base, rw, j)));
+                    asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(b.x), "=r"(b.y), "=r"(b.z), "=r"(b.w) : "r"(a_chunk_addr(a_base, rw, 8 + j)));
+                    uint4* dst = reinterpret_cast<uint4*>(p.QK16 + tok * 256 + half * 128);
+                    dst[j] = a;
+                    dst[8 + j] = b;
+                }
+            }
+            __syncthreads();
+        }
+        if (tokr < p.n_tok) {
+            float4* xd = reinterpret_cast<float4*>(p.XS + tokr * 16);
+            xd[0] = make_float4(xs[0], xs[1], xs[2], xs[3]); xd[1] = make_float4(xs[4], xs[5], xs[6], xs[7]);
+            xd[2] = make_float4(xs[8], xs[9], xs[10], xs[11]); xd[3] = make_float4(xs[12], xs[13], xs[14], xs[15]);
+        }
+        tc_fence_before();      // TMEM reads done before the next tile's MMA overwrites the columns (ordered by its __syncthreads)
+    }
+
+    tc_fence_before();
+    __syncthreads();
+    if (tid < 32) {
+        tc_fence_after();
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(t0), "r"(256) : "memory");
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// host side
+// ---------------------------------------------------------------------------------------------
+int proj_wimg_bytes() { return PJ_WIMG_BYTES; }
+int proj_cst_count() { return PJC_COUNT; }
+int proj_min_bins() { return (127 + PJ_SLOTS - 2) / (PJ_SLOTS - 1); }        // a 128-token tile must touch at most PJ_SLOTS cells
+
+// sage [64][128], wq / wk [128][64], LayerNorm gains / biases [64]
+int proj_build_weights(const float* sage_w, const float* sage_b, const float* wq, const float* wk, const float* g1, const float* b1,
+                       const float* g2, const float* b2, unsigned char* wimg_host, float* cst_host) {
+    const int d = UM_D;
+    memset(wimg_host, 0, PJ_WIMG_BYTES);
+    swizzle_image(sage_w, d, 2 * d, reinterpret_cast<__half*>(wimg_host + PJ_B_G));
+    std::vector<float> qk((size_t)2 * HSG_HD * d);
+    for (int n = 0; n < HSG_HD; ++n) {
+        double bq = 0, bk = 0;
+        for (int k = 0; k < d; ++k) {
+            qk[(size_t)n * d + k] = wq[(size_t)n * d + k] * g1[k];
+            qk[(size_t)(HSG_HD + n) * d + k] = wk[(size_t)n * d + k] * g2[k];
+            bq += (double)wq[(size_t)n * d + k] * b1[k];
+            bk += (double)wk[(size_t)n * d + k] * b2[k];
+        }
+        cst_host[PJC_BQ + n] = (float)bq;
+        cst_host[PJC_BK + n] = (float)bk;
+    }
+    swizzle_image(qk.data(), 2 * HSG_HD, d, reinterpret_cast<__half*>(wimg_host + PJ_B_QK));
+    for (int i = 0; i < d; ++i) cst_host[PJC_GB + i] = sage_b[i];
+    return 0;
+}
+
+int launch_token_project_umma(hsg_ctx* c, int cell_start, int n_batch, cudaStream_t s) {
+    const long long n_tok = (long long)n_batch * c->n_bins;
+    if (n_tok == 0) return 0;
+    ProjParams p;
+    p.neigh = c->neigh; p.E_bin = c->E_bin; p.cellQ = c->cellQ; p.cellK = c->cellK; p.wimg = c->pj_wimg;
+    memcpy(p.cst, c->h_pj_cst, sizeof(p.cst));
+    p.QK16 = (__half*)c->QK16; p.XS = c->XS; p.n_tok = n_tok; p.n_bins = c->n_bins; p.cell_start = cell_start;
+    p.n_tiles = (int)((n_tok + 127) / 128);
+    static bool attr_set = false;
+    if (!attr_set) {
+        HSG_CUDA(cudaFuncSetAttribute(project_umma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, PJ_TOTAL + 1024));
+        attr_set = true;
+    }
+    int grid = p.n_tiles < 2 * c->n_sm ? p.n_tiles : 2 * c->n_sm;
+    project_umma_kernel<<<grid, 128, PJ_TOTAL + 1024, s>>>(p);
+    c->launches++;
+    HSG_CUDA(cudaGetLastError());
+    return 0;
+}

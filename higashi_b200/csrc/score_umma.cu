@@ -436,17 +436,6 @@ struct UmmaTables {
     unsigned char* wimg; float* cst;
 };
 
-// W [N][K] row-major fp32 -> K-major SWIZZLE_128B fp16 image (64 halves = 128 B per swizzle row)
-static void swizzle_image(const float* W, int N, int K, __half* img) {
-    for (int n = 0; n < N; ++n)
-        for (int k = 0; k < K; ++k) {
-            int atom = k / 64, kk = k % 64, chunk = kk / 8;
-            size_t byte = (size_t)atom * N * 128 + (size_t)(n / 8) * 1024 + (size_t)(n % 8) * 128 + (size_t)((chunk ^ (n % 8)) * 16) +
-                          (size_t)(kk % 8) * 2;
-            img[byte / 2] = __float2half_rn(W[(size_t)n * K + k]);
-        }
-}
-
 int umma_build_weights(const float* fc1, const float* w0, const float* b0, const float* pff_g, const float* pff_b,
                        const float* w1, const float* b1, const float* ln1_g, const float* c0, const float* cb0,
                        const float* cw1, const float* cb1, unsigned char* wimg_host, float* cst_host) {

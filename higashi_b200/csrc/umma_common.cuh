@@ -301,3 +301,15 @@ __device__ __forceinline__ void issue_gemm(int wg, int wtid, uint32_t a_base, ui
     mma_group<NK, N>(a_base, b_base, b_rows, d_tmem, accum_first);
     ISSUE_END()
 }
+
+// W [N][K] row-major fp32 -> K-major SWIZZLE_128B fp16 image (64 halves = 128 B per swizzle row)
+static inline void swizzle_image(const float* W, int N, int K, __half* img) {
+    for (int n = 0; n < N; ++n)
+        for (int k = 0; k < K; ++k) {
+            int atom = k / 64, kk = k % 64, chunk = kk / 8;
+            size_t byte = (size_t)atom * N * 128 + (size_t)(n / 8) * 1024 + (size_t)(n % 8) * 128 + (size_t)((chunk ^ (n % 8)) * 16) +
+                          (size_t)(kk % 8) * 2;
+            img[byte / 2] = __float2half_rn(W[(size_t)n * K + k]);
+        }
+}
+
