@@ -163,12 +163,23 @@ def _random_state(ds, d, seed):
                                           (4, 0, 64, "tc16"), (0, 1, 64, "tc16")])
 def test_synthetic_vs_oracle(k, ltr, d, prec):
     """Seeded synthetic data (two chr1-sized chromosomes): CUDA vs oracle on a handful of cells."""
+    _synthetic_case(k, ltr, d, prec, [250, 97], [0, 17, 39])
+
+
+@pytest.mark.parametrize("bins", [[30, 20], [25, 10], [43], [128], [129, 127]])
+def test_small_genomes_tensor_core(bins):
+    """Token tiles of the tensor-core projection kernel (128 consecutive (cell, bin) tokens) straddle up to four cells when the
+    genome is small; below 43 bins the engine must fall back to the fp32 projection.  Same 1e-3 bar."""
+    _synthetic_case(4, 0, 64, "tc16", bins, [0, 1, 2, 3, 20, 39])
+
+
+def _synthetic_case(k, ltr, d, prec, bins, cells):
     from higashi_b200 import engine as E
     from higashi_b200 import synthetic as S
     from oracle import impute as OI
     from oracle import prep as OP
     from oracle import scorer as OS
-    ds = S.make_dataset("C1", n_cells=40, bins=[250, 97], seed=5)
+    ds = S.make_dataset("C1", n_cells=40, bins=bins, seed=5)
     ds.d = d
     sd, feats = _random_state(ds, d, seed=42 + d)
     nbr = nbr_w = None
@@ -180,11 +191,10 @@ def test_synthetic_vs_oracle(k, ltr, d, prec):
     eng.load_model(sd, ds.num, feats=feats, cell_feats=ds.cell_feats)
     eng.set_contacts(ds.csr)
     eng.set_neighbors(nbr, nbr_w)
-    chroms = [0, 1]
+    chroms = list(range(len(bins)))
     eng.set_pairs(chroms, 1, -1)
     eng.prepare(E.PREC_FP32 if prec == "fp32" else E.PREC_TC16, ltr, E.ACT_SIGMOID)
     tol = TOL_FP32 if prec == "fp32" else TOL_BF16
-    cells = [0, 17, 39]
     got_all = eng.impute_to_host(0, ds.n_cells)
     # oracle
     tsd = {k_: torch.from_numpy(np.asarray(v)) for k_, v in sd.items()}
