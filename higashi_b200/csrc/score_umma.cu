@@ -237,23 +237,31 @@ __global__ void __launch_bounds__(UM_THREADS, 1) score_umma_kernel(UmmaParams p)
                     uint32_t r[32];
                     tmem_ld32(t_h + t_lane + half * 32, r);
                     tmem_ld_wait();
+                    uint32_t hp[16];
 #pragma unroll
                     for (int c = 0; c < 4; ++c) {
                         const float* bq = cst + CST_B0F + half * 32 + c * 8;
-                        uint32_t pk[4];
 #pragma unroll
                         for (int q = 0; q < 4; ++q) {
                             float2 w = __ffma2_rn(f2(r[c * 8 + 2 * q], r[c * 8 + 2 * q + 1]), rs, make_float2(bq[2 * q], bq[2 * q + 1]));
                             float2 th = make_float2(fast_tanh(w.x), fast_tanh(w.y));
                             float2 hh = __ffma2_rn(w, th, w);
-                            pk[q] = pack_h2(hh.x, hh.y);
+                            hp[c * 4 + q] = pack_h2(hh.x, hh.y);
                         }
-                        sts128(a_chunk_addr(a_base, wtid, half * 4 + c), pk[0], pk[1], pk[2], pk[3]);
                     }
+                    // h goes back to TMEM as the fp16 A operand of the next MMA (two K elements per column): it overwrites the
+                    // g columns this thread has just consumed -- no shared-memory round trip, no proxy fence
+                    tmem_st16(t_h + t_lane + half * 16, hp);
                 }
             }
             // z = y + h . W1^T : accumulate onto y (still in TMEM) -- the residual is free
-            issue_gemm<4, 64>(wg, wtid, a_base, sbase + (HI ? SM_B_W1 : SMF_B_W1), 64, t_y, 1u, bar_mma);
+            if constexpr (HI) {
+                issue_gemm<4, 64>(wg, wtid, a_base, sbase + SM_B_W1, 64, t_y, 1u, bar_mma);
+            } else {
+                ISSUE_BEGIN_TS()
+                mma_group_ts<4, 64>(t_h, sbase + SMF_B_W1, 64, t_y, 1u);
+                ISSUE_END()
+            }
             // S rows of this token (feature blocks of 4): requested BEFORE waiting for the MMA so that their L2 latency hides
             // behind the tensor-core round trip (volatile loads: the compiler must not sink them below the wait)
             float4 sreg[16];
@@ -293,27 +301,26 @@ __global__ void __launch_bounds__(UM_THREADS, 1) score_umma_kernel(UmmaParams p)
                     rs = make_float2(rstd, rstd);
                 }
 #pragma unroll
-                for (int half = 0; half < 2; ++half) {
-                    uint32_t r[32];
-                    tmem_ld32(t_y + t_lane + half * 32, r);
+                for (int qt = 0; qt < 4; ++qt) {                 // 16 columns at a time: 16 + 8 live registers next to the 64 S values
+                    uint32_t r[16], up[8];
+                    tmem_ld16(t_y + t_lane + qt * 16, r);
                     tmem_ld_wait();
 #pragma unroll
-                    for (int c = 0; c < 4; ++c) {
-                        const float* bq = cst + CST_B1C + half * 32 + c * 8;
-                        const float* gq = cst + CST_G1 + half * 32 + c * 8;
-                        const float4 s0 = sreg[half * 8 + 2 * c], s1 = sreg[half * 8 + 2 * c + 1];
+                    for (int c = 0; c < 2; ++c) {
+                        const float* bq = cst + CST_B1C + qt * 16 + c * 8;
+                        const float* gq = cst + CST_G1 + qt * 16 + c * 8;
+                        const float4 s0 = sreg[qt * 4 + 2 * c], s1 = sreg[qt * 4 + 2 * c + 1];
                         const float svv[8] = {s0.x, s0.y, s0.z, s0.w, s1.x, s1.y, s1.z, s1.w};
-                        uint32_t pk[4];
 #pragma unroll
                         for (int q = 0; q < 4; ++q) {
                             float2 x = __fadd2_rn(f2(r[c * 8 + 2 * q], r[c * 8 + 2 * q + 1]), make_float2(bq[2 * q], bq[2 * q + 1]));
                             float2 tz = __fmul2_rn(x, rs);
                             float2 u = __ffma2_rn(tz, make_float2(gq[2 * q], gq[2 * q + 1]), make_float2(svv[2 * q], svv[2 * q + 1]));
                             u = __fmul2_rn(u, u);
-                            pk[q] = pack_h2(u.x, u.y);
+                            up[c * 4 + q] = pack_h2(u.x, u.y);
                         }
-                        sts128(a_chunk_addr(a_base, wtid, half * 4 + c), pk[0], pk[1], pk[2], pk[3]);
                     }
+                    tmem_st8(t_h + t_lane + qt * 8, up);         // u as the fp16 A operand of the classifier GEMM (h is consumed)
                 }
             } else {
                 // ------------------------------------------------------------------ u = (LN1(z + b1) - S)^2 (A tile, K = 64)
@@ -387,7 +394,10 @@ __global__ void __launch_bounds__(UM_THREADS, 1) score_umma_kernel(UmmaParams p)
                 mma_group<4, 32>(a_base, sbase + SM_B_C0_LO, 32, t_h, 1u);               // u_hi . C0_lo
                 ISSUE_END()
             } else {
-                issue_gemm<4, 32>(wg, wtid, a_base, sbase + SMF_B_C0, 32, t_h, 0u, bar_mma);
+                // c = u . C0^T lands on the first 32 columns of the (consumed) z block
+                ISSUE_BEGIN_TS()
+                mma_group_ts<4, 32>(t_h, sbase + SMF_B_C0, 32, t_y, 0u);
+                ISSUE_END()
             }
             mbar_wait(bar_mma, phase); phase ^= 1;
             tc_fence_after();
@@ -395,7 +405,7 @@ __global__ void __launch_bounds__(UM_THREADS, 1) score_umma_kernel(UmmaParams p)
             // ------------------------------------------------------------------ o_t = c1 . swish(c + cb0) + cb1
             {
                 uint32_t r[32];
-                tmem_ld32(t_h + t_lane, r);
+                tmem_ld32((HI ? t_h : t_y) + t_lane, r);
                 tmem_ld_wait();
                 float2 oA = make_float2(0.f, 0.f), oB = oA;
 #pragma unroll

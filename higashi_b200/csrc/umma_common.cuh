@@ -82,6 +82,11 @@ __device__ __forceinline__ void umma_f16(uint32_t d_tmem, uint64_t adesc, uint64
     asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\ttcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
                  ::"r"(d_tmem), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accum) : "memory");
 }
+// A operand from TMEM (fp16, lane = row, two K elements per 32-bit column), B from shared memory
+__device__ __forceinline__ void umma_f16_ts(uint32_t d_tmem, uint32_t a_tmem, uint64_t bdesc, uint32_t idesc, uint32_t accum) {
+    asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\ttcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n\t}"
+                 ::"r"(d_tmem), "r"(a_tmem), "l"(bdesc), "r"(idesc), "r"(accum) : "memory");
+}
 __device__ __forceinline__ void umma_commit(uint32_t bar) {
     asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
 }
@@ -97,6 +102,23 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
         "{%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,%29,%30,%31}, [%32];"
         : TMEM_LD_ARGS16(r, 0), TMEM_LD_ARGS16(r, 16) : "r"(taddr) : "memory");
 }
+// 32 lanes x 16 columns
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&r)[16]) {
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
+                 : TMEM_LD_ARGS16(r, 0) : "r"(taddr) : "memory");
+}
+// registers -> TMEM (thread r writes lane r): 16 / 8 consecutive 32-bit columns.  Used to hand an fp16 A operand (two K
+// elements per column, K-major) to the tensor core without the shared-memory round trip.
+__device__ __forceinline__ void tmem_st16(uint32_t taddr, const uint32_t (&r)[16]) {
+    asm volatile("tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16};"
+                 ::"r"(taddr), "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]), "r"(r[8]), "r"(r[9]),
+                   "r"(r[10]), "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15]) : "memory");
+}
+__device__ __forceinline__ void tmem_st8(uint32_t taddr, const uint32_t (&r)[8]) {
+    asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};"
+                 ::"r"(taddr), "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]) : "memory");
+}
+__device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 
 __device__ __forceinline__ float fast_tanh(float x) {
@@ -290,10 +312,22 @@ __device__ __forceinline__ void mma_group(uint32_t a_base, uint32_t b_base, int 
         umma_f16(d_tmem, umma_desc(a_base + aoff), umma_desc(b_base + boff), idesc, (k > 0) ? 1u : accum_first);
     }
 }
+// same with the A tile in TMEM: k-step k reads the 8 columns [8k, 8k + 8)
+template <int NK, int N>
+__device__ __forceinline__ void mma_group_ts(uint32_t a_tmem, uint32_t b_base, int b_rows, uint32_t d_tmem, uint32_t accum_first) {
+    constexpr uint32_t idesc = umma_idesc_f16(128, N);
+#pragma unroll
+    for (int k = 0; k < NK; ++k) {
+        uint32_t boff = (uint32_t)(k >> 2) * (uint32_t)(b_rows * 128) + (uint32_t)(k & 3) * 32u;
+        umma_f16_ts(d_tmem, a_tmem + (uint32_t)k * 8u, umma_desc(b_base + boff), idesc, (k > 0) ? 1u : accum_first);
+    }
+}
 // one MMA round trip for a warpgroup: the A tile is complete in shared memory.  Generic-proxy writes of the A tile are
 // made visible to the tensor core (async proxy), the warpgroup syncs, one thread issues and commits to the mbarrier.
 #define ISSUE_BEGIN() fence_async_smem(); tc_fence_before(); wg_bar(wg); if (wtid == 0) { tc_fence_after();
 #define ISSUE_END() umma_commit(bar_mma); }
+// A operand written to TMEM by the warpgroup's own tcgen05.st: no shared-memory proxy fence needed
+#define ISSUE_BEGIN_TS() tmem_st_wait(); tc_fence_before(); wg_bar(wg); if (wtid == 0) { tc_fence_after();
 template <int NK, int N>
 __device__ __forceinline__ void issue_gemm(int wg, int wtid, uint32_t a_base, uint32_t b_base, int b_rows, uint32_t d_tmem,
                                            uint32_t accum_first, uint32_t bar_mma) {
