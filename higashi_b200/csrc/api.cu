@@ -57,6 +57,7 @@ extern "C" int hsg_create(hsg_ctx** out, int device_ordinal) {
     hsg_ctx* c = new hsg_ctx();
     c->device = device_ordinal;
     c->n_sm = prop.multiProcessorCount;
+    if (const char* e = getenv("HSG_GATHER_SPARSE")) c->gather_sparse = (e[0] != '0');
     HSG_CUDA(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
     HSG_CUDA(cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking));
     for (int i = 0; i < 8; ++i) HSG_CUDA(cudaEventCreate(&c->ev[i]));
@@ -74,7 +75,7 @@ static void free_derived(hsg_ctx* c) {
     { __half* p = (__half*)c->QK16; dev_free(p); c->QK16 = nullptr; }
     { __half* p = (__half*)c->binV16; dev_free(p); c->binV16 = nullptr; }
     { __half* p = (__half*)c->cellV16; dev_free(p); c->cellV16 = nullptr; }
-    dev_free(c->XS); dev_free(c->binSb); dev_free(c->cellSb); dev_free(c->wimg); dev_free(c->cst); dev_free(c->pj_wimg);
+    dev_free(c->XS); dev_free(c->binSb); dev_free(c->cellSb); dev_free(c->wimg); dev_free(c->cst); dev_free(c->pj_wimg); dev_free(c->ovf_list);
     c->use_umma = false;
     dev_free(c->stage_out[0]); dev_free(c->stage_out[1]); c->stage_bytes = 0;
     c->prepared = false;

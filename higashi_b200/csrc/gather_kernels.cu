@@ -7,6 +7,8 @@
 //                              K = w_ks.LN2(dyn)                   (Modules.py:1035-1044)
 #include <cuda_fp16.h>
 
+#include <algorithm>
+
 #include "common.cuh"
 
 // ---------------------------------------------------------------------------------------------
@@ -58,7 +60,8 @@ __global__ void neigh_gather_kernel(const int64_t* __restrict__ row_ptr, const i
                                     const float* __restrict__ nbr_w, int k1, int weighted,
                                     const float* __restrict__ E_bin, const int* __restrict__ bin_chrom,
                                     const int* __restrict__ bin_off, int n_bins, int cell_start,
-                                    int n_batch_cells, int ltr, int max_nc, float* __restrict__ neigh) {
+                                    int n_batch_cells, int ltr, int max_nc, float* __restrict__ neigh,
+                                    const int* __restrict__ tok_list, const int* __restrict__ tok_count) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, wpb = blockDim.x >> 5;
     const size_t wbytes = gather_warp_bytes(max_nc, ltr);
@@ -77,8 +80,10 @@ __global__ void neigh_gather_kernel(const int64_t* __restrict__ row_ptr, const i
     for (int i = lane; i < words; i += 32) { S.amask[i] = 0u; if (ltr > 0) S.tmask[i] = 0u; }
     __syncwarp();
 
-    const int64_t n_tok = (int64_t)n_batch_cells * n_bins;
-    for (int64_t tok = (int64_t)blockIdx.x * wpb + warp; tok < n_tok; tok += (int64_t)gridDim.x * wpb) {
+    // list mode: only the tokens the sub-warp kernel could not hold in registers (tok_list / tok_count written by it)
+    const int64_t n_tok = tok_list ? (int64_t)*tok_count : (int64_t)n_batch_cells * n_bins;
+    for (int64_t ti = (int64_t)blockIdx.x * wpb + warp; ti < n_tok; ti += (int64_t)gridDim.x * wpb) {
+        const int64_t tok = tok_list ? (int64_t)tok_list[ti] : ti;
         const int cb = (int)(tok / n_bins), g = (int)(tok - (int64_t)cb * n_bins);
         const int cell = cell_start + cb;
         const int c = bin_chrom[g], off = bin_off[c], nc = bin_off[c + 1] - off, l = g - off;
@@ -172,6 +177,152 @@ __global__ void neigh_gather_kernel(const int64_t* __restrict__ row_ptr, const i
     }
 }
 
+
+// ---------------------------------------------------------------------------------------------
+// K1a, sparse rows (the scHi-C regime: a handful of contacts per row).  EIGHT lanes per (cell, bin) token, four tokens per
+// warp, everything in registers:
+//   * lanes 0..k1-1 of a group fetch the k+1 neighbour rows' extents together (one dependent round trip instead of k+1),
+//     then push their entries, already scaled by the neighbour weight, into a 32-entry staging strip in row order;
+//   * duplicates across neighbour rows are merged with an all-pairs compare over shuffles, every sum taken in row order
+//     (same order as the reference's sequential sparse adds, deterministic);
+//   * x pdf(0), log1p, L1 normalisation and the gather of the E rows (each lane owns 8 of the 64 output columns: two 128-bit
+//     loads per entry, one contiguous 256-byte row per group).
+// Tokens with more than GS_CAP merged candidates go to an overflow list that the generic warp-per-token kernel finishes.
+// ---------------------------------------------------------------------------------------------
+#define GS_CAP 32
+#define GS_SLOTS (GS_CAP / 8)
+#define GS_WPB 8
+
+template <int S>
+__device__ __forceinline__ void gs_dedup(const int (&col)[GS_SLOTS], const float (&val)[GS_SLOTS], int gl, float (&sum)[GS_SLOTS],
+                                         bool (&dup)[GS_SLOTS]) {
+#pragma unroll
+    for (int s = 0; s < GS_SLOTS; ++s) { sum[s] = 0.f; dup[s] = false; }
+#pragma unroll
+    for (int s2 = 0; s2 < S; ++s2) {
+#pragma unroll
+        for (int l2 = 0; l2 < 8; ++l2) {
+            const int c2 = __shfl_sync(0xffffffffu, col[s2], l2, 8);
+            const float v2 = __shfl_sync(0xffffffffu, val[s2], l2, 8);
+            const int e2 = s2 * 8 + l2;
+#pragma unroll
+            for (int s = 0; s < S; ++s) {
+                const int e = s * 8 + gl;
+                const bool same = (c2 == col[s]);
+                if (same && e2 >= e) sum[s] = __fadd_rn(sum[s], v2);     // owner accumulates in row order (itself first)
+                if (same && e2 < e) dup[s] = true;
+            }
+        }
+    }
+}
+
+__global__ void __launch_bounds__(GS_WPB * 32) neigh_gather_sparse_kernel(
+    const int64_t* __restrict__ row_ptr, const int32_t* __restrict__ col, const float* __restrict__ val,
+    const int32_t* __restrict__ nbr, const float* __restrict__ nbr_w, int k1, int weighted, const float* __restrict__ E_bin,
+    const int* __restrict__ bin_chrom, const int* __restrict__ bin_off, int n_bins, int cell_start, int n_tok,
+    float* __restrict__ neigh, int* __restrict__ tok_list, int* __restrict__ tok_count) {
+    __shared__ int s_col[GS_WPB][4][GS_CAP];
+    __shared__ float s_val[GS_WPB][4][GS_CAP];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, gl = lane & 7, grp = lane >> 3;
+    const int n_quads = (n_tok + 3) >> 2;
+    for (int quad = blockIdx.x * GS_WPB + warp; quad < n_quads; quad += gridDim.x * GS_WPB) {
+        const int tok = quad * 4 + grp;
+        const bool tvalid = tok < n_tok;
+        const int tk = tvalid ? tok : n_tok - 1;
+        const int cb = tk / n_bins, g = tk - cb * n_bins;
+        const int cell = cell_start + cb;
+        const int off = bin_off[bin_chrom[g]];
+        // ---- extents of the k1 neighbour rows (lane gl < k1 owns row gl)
+        int64_t lo = 0;
+        int len = 0;
+        float w = 1.0f;
+        if (gl < k1) {
+            int src = cell;
+            if (weighted) { src = __ldg(nbr + (int64_t)cell * k1 + gl); w = __ldg(nbr_w + (int64_t)cell * k1 + gl); }
+            const int64_t row = (int64_t)src * n_bins + g;
+            lo = __ldg(row_ptr + row);
+            len = (int)(__ldg(row_ptr + row + 1) - lo);
+        }
+        int start = len;                         // inclusive prefix over the 8 lanes of the group
+#pragma unroll
+        for (int o = 1; o < 8; o <<= 1) {
+            int t = __shfl_up_sync(0xffffffffu, start, o, 8);
+            if (gl >= o) start += t;
+        }
+        const int n = __shfl_sync(0xffffffffu, start, 7, 8);
+        start -= len;
+        const bool over = n > GS_CAP;
+        if (over && gl == 0 && tvalid) tok_list[atomicAdd(tok_count, 1)] = tok;
+        // ---- push the (weighted) entries into the staging strip in row order
+        if (!over) {
+            for (int i = 0; i < len; ++i) {
+                const float v = __ldg(val + lo + i);
+                s_col[warp][grp][start + i] = __ldg(col + lo + i);
+                s_val[warp][grp][start + i] = weighted ? __fmul_rn(w, v) : v;
+            }
+        }
+        __syncwarp();
+        const int n_eff = over ? 0 : n;
+        int nmax = n_eff;
+        nmax = max(nmax, __shfl_xor_sync(0xffffffffu, nmax, 8));
+        nmax = max(nmax, __shfl_xor_sync(0xffffffffu, nmax, 16));
+        int ec[GS_SLOTS];
+        float ev[GS_SLOTS];
+#pragma unroll
+        for (int s = 0; s < GS_SLOTS; ++s) {
+            const int e = s * 8 + gl;
+            const bool ok = e < n_eff;
+            ec[s] = ok ? s_col[warp][grp][e] : -1 - e;           // distinct negative keys: never equal to a real column
+            ev[s] = ok ? s_val[warp][grp][e] : 0.f;
+        }
+        __syncwarp();
+        float sum[GS_SLOTS];
+        bool dup[GS_SLOTS];
+        if (nmax <= 8) gs_dedup<1>(ec, ev, gl, sum, dup);
+        else if (nmax <= 16) gs_dedup<2>(ec, ev, gl, sum, dup);
+        else if (nmax <= 24) gs_dedup<3>(ec, ev, gl, sum, dup);
+        else gs_dedup<4>(ec, ev, gl, sum, dup);
+        // ---- x pdf(0), log1p, L1 normalisation (Impute.py:19, 91-92)
+        float part = 0.f;
+#pragma unroll
+        for (int s = 0; s < GS_SLOTS; ++s) {
+            const bool own = (s * 8 + gl < n_eff) && !dup[s];
+            const float v = own ? log1pf(__fmul_rn(sum[s], HSG_PDF0)) : 0.f;
+            sum[s] = v;
+            part += fabsf(v);
+        }
+        part += __shfl_xor_sync(0xffffffffu, part, 1, 8);
+        part += __shfl_xor_sync(0xffffffffu, part, 2, 8);
+        part += __shfl_xor_sync(0xffffffffu, part, 4, 8);
+        if (part > 0.f) {
+#pragma unroll
+            for (int s = 0; s < GS_SLOTS; ++s) sum[s] = __fdiv_rn(sum[s], part);
+        }
+        // ---- neigh = sum_t A_hat[b,t] * E_bin[t,:] : lane gl owns columns [8 gl, 8 gl + 8)
+        float4 o0 = make_float4(0.f, 0.f, 0.f, 0.f), o1 = o0;
+        const float4* Eg = reinterpret_cast<const float4*>(E_bin + (int64_t)off * 64) + gl * 2;
+#pragma unroll
+        for (int s = 0; s < GS_SLOTS; ++s) {
+            if (s * 8 < nmax) {
+#pragma unroll
+                for (int l2 = 0; l2 < 8; ++l2) {
+                    const float a = __shfl_sync(0xffffffffu, sum[s], l2, 8);
+                    const int c = __shfl_sync(0xffffffffu, ec[s], l2, 8);
+                    if (a != 0.f) {
+                        const float4 x0 = __ldg(Eg + (int64_t)c * 16), x1 = __ldg(Eg + (int64_t)c * 16 + 1);
+                        o0.x = fmaf(a, x0.x, o0.x); o0.y = fmaf(a, x0.y, o0.y); o0.z = fmaf(a, x0.z, o0.z); o0.w = fmaf(a, x0.w, o0.w);
+                        o1.x = fmaf(a, x1.x, o1.x); o1.y = fmaf(a, x1.y, o1.y); o1.z = fmaf(a, x1.z, o1.z); o1.w = fmaf(a, x1.w, o1.w);
+                    }
+                }
+            }
+        }
+        if (tvalid && !over) {
+            float4* dst = reinterpret_cast<float4*>(neigh + (int64_t)tok * 64) + gl * 2;
+            dst[0] = o0; dst[1] = o1;
+        }
+    }
+}
+
 int launch_gather(hsg_ctx* c, const int*, int cell_start, int n_batch, cudaStream_t s) {
     int max_nc = 0;
     for (int b : c->bins) max_nc = b > max_nc ? b : max_nc;
@@ -185,16 +336,39 @@ int launch_gather(hsg_ctx* c, const int*, int cell_start, int n_batch, cudaStrea
     int64_t blocks = (n_tok + wpb - 1) / wpb;
     int64_t cap = 148LL * 8;
     unsigned grid = (unsigned)(blocks < cap ? blocks : cap);
+    const int* list = nullptr;
+    const int* count = nullptr;
+    // sparse-row fast path (d = 64, no row-shift smoothing, at most 8 neighbour rows): the generic kernel then only finishes the
+    // tokens on the overflow list
+    if (c->d == 64 && c->ltr == 0 && c->k1 <= 8 && n_tok < (1LL << 31) && c->gather_sparse) {
+        if (c->ovf_cap < n_tok + 1) {
+            if (c->ovf_list) cudaFree(c->ovf_list);
+            HSG_CUDA(cudaMalloc((void**)&c->ovf_list, (size_t)(n_tok + 1) * sizeof(int)));
+            c->ovf_cap = n_tok + 1;
+        }
+        int* cnt = c->ovf_list + n_tok;
+        HSG_CUDA(cudaMemsetAsync(cnt, 0, sizeof(int), s));
+        int64_t quads = (n_tok + 3) / 4;
+        int64_t gb = (quads + GS_WPB - 1) / GS_WPB;
+        int64_t gcap = (int64_t)c->n_sm * 8;
+        neigh_gather_sparse_kernel<<<(unsigned)(gb < gcap ? gb : gcap), GS_WPB * 32, 0, s>>>(
+            c->row_ptr, c->col, c->val, c->nbr, c->nbr_w, c->k1, c->weighted ? 1 : 0, c->E_bin, c->d_bin_chrom, c->d_bin_off,
+            c->n_bins, cell_start, (int)n_tok, c->neigh, c->ovf_list, cnt);
+        c->launches++;
+        HSG_CUDA(cudaGetLastError());
+        list = c->ovf_list; count = cnt;
+        grid = (unsigned)std::min<int64_t>(grid, (int64_t)c->n_sm * 2);
+    }
     if (c->d == 64) {
         HSG_CUDA(cudaFuncSetAttribute(neigh_gather_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         neigh_gather_kernel<64><<<grid, wpb * 32, smem, s>>>(c->row_ptr, c->col, c->val, c->nbr, c->nbr_w, c->k1,
                                                              c->weighted ? 1 : 0, c->E_bin, c->d_bin_chrom, c->d_bin_off,
-                                                             c->n_bins, cell_start, n_batch, c->ltr, max_nc, c->neigh);
+                                                             c->n_bins, cell_start, n_batch, c->ltr, max_nc, c->neigh, list, count);
     } else {
         HSG_CUDA(cudaFuncSetAttribute(neigh_gather_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         neigh_gather_kernel<128><<<grid, wpb * 32, smem, s>>>(c->row_ptr, c->col, c->val, c->nbr, c->nbr_w, c->k1,
                                                               c->weighted ? 1 : 0, c->E_bin, c->d_bin_chrom, c->d_bin_off,
-                                                              c->n_bins, cell_start, n_batch, c->ltr, max_nc, c->neigh);
+                                                              c->n_bins, cell_start, n_batch, c->ltr, max_nc, c->neigh, list, count);
     }
     c->launches++;
     HSG_CUDA(cudaGetLastError());
