@@ -173,13 +173,20 @@ def test_small_genomes_tensor_core(bins):
     _synthetic_case(4, 0, 64, "tc16", bins, [0, 1, 2, 3, 20, 39])
 
 
-def _synthetic_case(k, ltr, d, prec, bins, cells):
+@pytest.mark.parametrize("density,k", [(0.3, 4), (0.08, 4), (0.02, 9), (0.02, 7), (0.0, 4)])
+def test_gather_paths(density, k):
+    """K1a has a sparse-row fast path (<= 32 merged candidates per token, <= 8 neighbour rows) and a generic kernel that
+    finishes the overflow list: dense rows (every token overflows), mixed, k+1 > 8 (generic only), k+1 = 8, empty contacts."""
+    _synthetic_case(k, 0, 64, "fp32", [120, 40], [0, 5, 39], density=density)
+
+
+def _synthetic_case(k, ltr, d, prec, bins, cells, density=None):
     from higashi_b200 import engine as E
     from higashi_b200 import synthetic as S
     from oracle import impute as OI
     from oracle import prep as OP
     from oracle import scorer as OS
-    ds = S.make_dataset("C1", n_cells=40, bins=bins, seed=5)
+    ds = S.make_dataset("C1", n_cells=40, bins=bins, seed=5, **({} if density is None else {"density": density}))
     ds.d = d
     sd, feats = _random_state(ds, d, seed=42 + d)
     nbr = nbr_w = None
