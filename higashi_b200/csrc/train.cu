@@ -112,12 +112,18 @@ __global__ void dswish_kernel(float* __restrict__ dy, const float* __restrict__ 
     if (i < n) dy[i] *= dswish(pre[i]);
 }
 // db[col] += sum_rows dy[row, col]
+// block = 64 columns x 4 row lanes; gridDim.y row slices (COLSUM_SLICES) so that the grid covers the SMs
+#define COLSUM_SLICES 128
 __global__ void colsum_kernel(const float* __restrict__ dy, int rows, int cols, float* __restrict__ db) {
-    int col = blockIdx.x * blockDim.x + threadIdx.x;
-    if (col >= cols) return;
+    __shared__ float part[4][64];
+    const int cl = threadIdx.x & 63, rl = threadIdx.x >> 6;
+    const int col = blockIdx.x * 64 + cl;
     float s = 0.f;
-    for (int r = blockIdx.y; r < rows; r += gridDim.y) s += dy[(size_t)r * cols + col];
-    atomicAdd(db + col, s);
+    if (col < cols)
+        for (int r = blockIdx.y * 4 + rl; r < rows; r += gridDim.y * 4) s += dy[(size_t)r * cols + col];
+    part[rl][cl] = s;
+    __syncthreads();
+    if (rl == 0 && col < cols) atomicAdd(db + col, (part[0][cl] + part[1][cl]) + (part[2][cl] + part[3][cl]));
 }
 // inverted dropout with a counter-based mask (same (seed, tag, index) -> same mask in forward and backward)
 __device__ __forceinline__ float keep_scale(unsigned long long seed, unsigned tag, unsigned long long i, float p) {
@@ -455,20 +461,35 @@ __global__ void xp_bwd_kernel(const int64_t* __restrict__ x, int B, int A, int c
                               const float* __restrict__ cellf, int only_model, const float* __restrict__ w1, const float* __restrict__ hpre,
                               const float* __restrict__ dout, float* __restrict__ dw0, float* __restrict__ db0, float* __restrict__ dw1,
                               float* __restrict__ db1) {
+    // block-level accumulation in shared memory ([4 * in_w] dw0, [4] db0, [4] dw1, [1] db1), one global atomic per value per block
+    extern __shared__ float acc[];
+    const int in_w = 2 * A + cf, n_acc = 4 * in_w + 9;
+    for (int i = threadIdx.x; i < n_acc; i += blockDim.x) acc[i] = 0.f;
+    __syncthreads();
+    float* a_b0 = acc + 4 * in_w; float* a_w1 = a_b0 + 4; float* a_b1 = a_w1 + 4;
     int r = blockIdx.x * blockDim.x + threadIdx.x;
-    if (r >= B) return;
-    const int in_w = 2 * A + cf;
-    const float g = dout[r];
-    const float* ai = attr + (size_t)x[r * 3 + 1] * A; const float* aj = attr + (size_t)x[r * 3 + 2] * A;
-    const float* cfp = cellf + (size_t)x[r * 3] * cf;
-    atomicAdd(db1, g);
-    for (int u = 0; u < 4; ++u) {
-        float pre = hpre[r * 4 + u];
-        atomicAdd(dw1 + u, g * swish_acc(pre));
-        float dh = g * w1[u] * dswish(pre);
-        atomicAdd(db0 + u, dh);
-        for (int t = 0; t < A; ++t) { atomicAdd(dw0 + u * in_w + t, dh * ai[t]); atomicAdd(dw0 + u * in_w + A + t, dh * aj[t]); }
-        if (!only_model) for (int t = 0; t < cf; ++t) atomicAdd(dw0 + u * in_w + 2 * A + t, dh * cfp[t]);
+    if (r < B) {
+        const float g = dout[r];
+        const float* ai = attr + (size_t)x[r * 3 + 1] * A; const float* aj = attr + (size_t)x[r * 3 + 2] * A;
+        const float* cfp = cellf + (size_t)x[r * 3] * cf;
+        atomicAdd(a_b1, g);
+        for (int u = 0; u < 4; ++u) {
+            float pre = hpre[r * 4 + u];
+            atomicAdd(a_w1 + u, g * swish_acc(pre));
+            float dh = g * w1[u] * dswish(pre);
+            atomicAdd(a_b0 + u, dh);
+            for (int t = 0; t < A; ++t) { atomicAdd(acc + u * in_w + t, dh * ai[t]); atomicAdd(acc + u * in_w + A + t, dh * aj[t]); }
+            if (!only_model) for (int t = 0; t < cf; ++t) atomicAdd(acc + u * in_w + 2 * A + t, dh * cfp[t]);
+        }
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < n_acc; i += blockDim.x) {
+        float v = acc[i];
+        if (v == 0.f) continue;
+        if (i < 4 * in_w) atomicAdd(dw0 + i, v);
+        else if (i < 4 * in_w + 4) atomicAdd(db0 + (i - 4 * in_w), v);
+        else if (i < 4 * in_w + 8) atomicAdd(dw1 + (i - 4 * in_w - 4), v);
+        else atomicAdd(db1, v);
     }
 }
 // head = mean over the 3 tokens + side channel
@@ -896,7 +917,7 @@ extern "C" int hsg_score_bwd(hsg_ctx* c, void* stream) {
     const int bin_base = c->n_cells + 1 + c->bin_off[chrom];
     const int64_t nRd = (int64_t)R * d;
     // heads
-    xp_bwd_kernel<<<nblk(B), 256, 0, s>>>(w->x, B, c->n_chrom + 1, c->cf, c->w[HSG_W_ATTR], c->w[HSG_W_CELL_FEATS], w->only_model,
+    xp_bwd_kernel<<<nblk(B), 256, (4 * (2 * (c->n_chrom + 1) + c->cf) + 9) * sizeof(float), s>>>(w->x, B, c->n_chrom + 1, c->cf, c->w[HSG_W_ATTR], c->w[HSG_W_CELL_FEATS], w->only_model,
                                           PARAM(HSG_W_XP2_W1), w->hp2, w->dmean, GRAD(HSG_W_XP2_W0), GRAD(HSG_W_XP2_B0),
                                           GRAD(HSG_W_XP2_W1), GRAD(HSG_W_XP2_B1));
     TR_CHECK_LAUNCH(c);
@@ -904,16 +925,16 @@ extern "C" int hsg_score_bwd(hsg_ctx* c, void* stream) {
                                                                    GRAD(HSG_W_CLS_B1));
     TR_CHECK_LAUNCH(c);
     dswish_kernel<<<nblk((int64_t)R * hd), 256, 0, s>>>(w->dc, w->cpre, (int64_t)R * hd); TR_CHECK_LAUNCH(c);
-    colsum_kernel<<<dim3((hd + 63) / 64, 32), 64, 0, s>>>(w->dc, R, hd, GRAD(HSG_W_CLS_B0)); TR_CHECK_LAUNCH(c);
+    colsum_kernel<<<dim3((hd + 63) / 64, COLSUM_SLICES), 256, 0, s>>>(w->dc, R, hd, GRAD(HSG_W_CLS_B0)); TR_CHECK_LAUNCH(c);
     if (LIN_DW(R, hd, d, w->dc, hd, w->u, d, GRAD(HSG_W_CLS_W0), d)) return 1;
     if (LIN_DX(R, hd, d, w->dc, hd, PARAM(HSG_W_CLS_W0), d, w->du, d, 0.f)) return 1;
     HSG_CUDA(cudaMemsetAsync(w->dS, 0, nRd * sizeof(float), s));
     if (w->mode == 2) {        // zinb: the var and proba heads read the normalised static branch
-        xp_bwd_kernel<<<nblk(B), 256, 0, s>>>(w->x, B, c->n_chrom + 1, c->cf, c->w[HSG_W_ATTR], c->w[HSG_W_CELL_FEATS], w->only_model,
+        xp_bwd_kernel<<<nblk(B), 256, (4 * (2 * (c->n_chrom + 1) + c->cf) + 9) * sizeof(float), s>>>(w->x, B, c->n_chrom + 1, c->cf, c->w[HSG_W_ATTR], c->w[HSG_W_CELL_FEATS], w->only_model,
                                               PARAM(HSG_W_XP3_W1), w->hp3, w->dvar, GRAD(HSG_W_XP3_W0), GRAD(HSG_W_XP3_B0),
                                               GRAD(HSG_W_XP3_W1), GRAD(HSG_W_XP3_B1));
         TR_CHECK_LAUNCH(c);
-        xp_bwd_kernel<<<nblk(B), 256, 0, s>>>(w->x, B, c->n_chrom + 1, c->cf, c->w[HSG_W_ATTR], c->w[HSG_W_CELL_FEATS], w->only_model,
+        xp_bwd_kernel<<<nblk(B), 256, (4 * (2 * (c->n_chrom + 1) + c->cf) + 9) * sizeof(float), s>>>(w->x, B, c->n_chrom + 1, c->cf, c->w[HSG_W_ATTR], c->w[HSG_W_CELL_FEATS], w->only_model,
                                               PARAM(HSG_W_XP_W1), w->hp1, w->dproba, GRAD(HSG_W_XP_W0), GRAD(HSG_W_XP_B0),
                                               GRAD(HSG_W_XP_W1), GRAD(HSG_W_XP_B1));
         TR_CHECK_LAUNCH(c);
@@ -924,7 +945,7 @@ extern "C" int hsg_score_bwd(hsg_ctx* c, void* stream) {
                                                                            GRAD(slots[q][3]));
             TR_CHECK_LAUNCH(c);
             dswish_kernel<<<nblk((int64_t)R * hd), 256, 0, s>>>(w->dc, pre[q], (int64_t)R * hd); TR_CHECK_LAUNCH(c);
-            colsum_kernel<<<dim3((hd + 63) / 64, 32), 64, 0, s>>>(w->dc, R, hd, GRAD(slots[q][1])); TR_CHECK_LAUNCH(c);
+            colsum_kernel<<<dim3((hd + 63) / 64, COLSUM_SLICES), 256, 0, s>>>(w->dc, R, hd, GRAD(slots[q][1])); TR_CHECK_LAUNCH(c);
             if (LIN_DW(R, hd, d, w->dc, hd, w->Sn, d, GRAD(slots[q][0]), d)) return 1;
             if (LIN_DX(R, hd, d, w->dc, hd, PARAM(slots[q][0]), d, w->dS, d, 1.f)) return 1;
         }
@@ -933,12 +954,12 @@ extern "C" int hsg_score_bwd(hsg_ctx* c, void* stream) {
     if (ln_bwd(c, s, w->dD, w->z, R, PARAM(HSG_W_LN1_G), w->mu_z, w->rs_z, w->dz, 0, GRAD(HSG_W_LN1_G), GRAD(HSG_W_LN1_B))) return 1;
     if (ln_bwd(c, s, w->dS, w->sp, R, PARAM(HSG_W_LN2_G), w->mu_p, w->rs_p, w->dsp, 0, GRAD(HSG_W_LN2_G), GRAD(HSG_W_LN2_B))) return 1;
     // pff_n1:  z = y + W1 h + b1 ; h = swish(W0 xn + b0) ; xn = LN(y)
-    colsum_kernel<<<dim3((d + 63) / 64, 32), 64, 0, s>>>(w->dz, R, d, GRAD(HSG_W_PFF_B1)); TR_CHECK_LAUNCH(c);
+    colsum_kernel<<<dim3((d + 63) / 64, COLSUM_SLICES), 256, 0, s>>>(w->dz, R, d, GRAD(HSG_W_PFF_B1)); TR_CHECK_LAUNCH(c);
     if (LIN_DW(R, d, d, w->dz, d, w->h, d, GRAD(HSG_W_PFF_W1), d)) return 1;
     if (LIN_DX(R, d, d, w->dz, d, PARAM(HSG_W_PFF_W1), d, w->dh, d, 0.f)) return 1;
     if (w->dropout) { dropout_kernel<<<nblk(nRd), 256, 0, s>>>(w->dh, nRd, 0.4f, w->seed, 3); TR_CHECK_LAUNCH(c); }
     dswish_kernel<<<nblk(nRd), 256, 0, s>>>(w->dh, w->hpre, nRd); TR_CHECK_LAUNCH(c);
-    colsum_kernel<<<dim3((d + 63) / 64, 32), 64, 0, s>>>(w->dh, R, d, GRAD(HSG_W_PFF_B0)); TR_CHECK_LAUNCH(c);
+    colsum_kernel<<<dim3((d + 63) / 64, COLSUM_SLICES), 256, 0, s>>>(w->dh, R, d, GRAD(HSG_W_PFF_B0)); TR_CHECK_LAUNCH(c);
     if (LIN_DW(R, d, d, w->dh, d, w->xn, d, GRAD(HSG_W_PFF_W0), d)) return 1;
     if (LIN_DX(R, d, d, w->dh, d, PARAM(HSG_W_PFF_W0), d, w->dxn, d, 0.f)) return 1;
     HSG_CUDA(cudaMemcpyAsync(w->dy, w->dz, nRd * sizeof(float), cudaMemcpyDeviceToDevice, s));      // residual branch
@@ -969,7 +990,7 @@ extern "C" int hsg_score_bwd(hsg_ctx* c, void* stream) {
     if (w->stage == 2) {
         const int64_t nNd = (int64_t)NB * d;
         dswish_kernel<<<nblk(nNd), 256, 0, s>>>(w->dcomb, w->combpre, nNd); TR_CHECK_LAUNCH(c);
-        colsum_kernel<<<dim3((d + 63) / 64, 32), 64, 0, s>>>(w->dcomb, NB, d, GRAD(HSG_W_SAGE_B)); TR_CHECK_LAUNCH(c);
+        colsum_kernel<<<dim3((d + 63) / 64, COLSUM_SLICES), 256, 0, s>>>(w->dcomb, NB, d, GRAD(HSG_W_SAGE_B)); TR_CHECK_LAUNCH(c);
         float* dG = GRAD(HSG_W_SAGE_W); const float* G = PARAM(HSG_W_SAGE_W);
         if (LIN_DW(NB, d, d, w->dcomb, d, w->neigh, d, dG, 2 * d)) return 1;
         if (LIN_DW(NB, d, d, w->dcomb, d, w->selfb, d, dG + d, 2 * d)) return 1;
@@ -983,12 +1004,12 @@ extern "C" int hsg_score_bwd(hsg_ctx* c, void* stream) {
     if (w->stage == 1 && w->cell_on_hook) {
         const int F = b->in_dim[0];
         cell_grad_rows_kernel<<<nblk((int64_t)B * d), 256, 0, s>>>(w->ddyn, w->dsta, B, d, w->dcell); TR_CHECK_LAUNCH(c);
-        colsum_kernel<<<dim3((d + 63) / 64, 32), 64, 0, s>>>(w->dcell, B, d, b->grads + b->off_pb[0]); TR_CHECK_LAUNCH(c);
+        colsum_kernel<<<dim3((d + 63) / 64, COLSUM_SLICES), 256, 0, s>>>(w->dcell, B, d, b->grads + b->off_pb[0]); TR_CHECK_LAUNCH(c);
         if (LIN_DW(B, d, F, w->dcell, d, w->Xg, F, b->grads + b->off_pw[0], F)) return 1;
     }
     // E = swish(X W^T + b)
     dswish_kernel<<<nblk((int64_t)nc * d), 256, 0, s>>>(w->dEall, w->Epre, (int64_t)nc * d); TR_CHECK_LAUNCH(c);
-    colsum_kernel<<<dim3((d + 63) / 64, 32), 64, 0, s>>>(w->dEall, nc, d, b->grads + b->off_pb[chrom + 1]); TR_CHECK_LAUNCH(c);
+    colsum_kernel<<<dim3((d + 63) / 64, COLSUM_SLICES), 256, 0, s>>>(w->dEall, nc, d, b->grads + b->off_pb[chrom + 1]); TR_CHECK_LAUNCH(c);
     if (LIN_DW(nc, d, in_c, w->dEall, d, b->feat[chrom + 1], in_c, b->grads + b->off_pw[chrom + 1], in_c)) return 1;
     return 0;
 }
@@ -1033,11 +1054,11 @@ extern "C" int hsg_recon_loss(hsg_ctx* c, float* loss_host, float* gnorm_w0_host
     if (gemm(c, s, false, false, n, F, d, a2, d, Rw, F, rec, F, 0.f)) return 1;
     recon_mse_kernel<<<nblk((int64_t)n * F), 256, 0, s>>>(rec, rb, b->feat[0], (int64_t)n * F, F, misc); TR_CHECK_LAUNCH(c);
     // backward: rec now holds d(loss)/d(recon)
-    colsum_kernel<<<dim3((F + 63) / 64, 32), 64, 0, s>>>(rec, n, F, grb); TR_CHECK_LAUNCH(c);
+    colsum_kernel<<<dim3((F + 63) / 64, COLSUM_SLICES), 256, 0, s>>>(rec, n, F, grb); TR_CHECK_LAUNCH(c);
     if (gemm(c, s, true, false, d, F, n, a2, d, rec, F, gR, F, 1.f)) return 1;              // dR = a2^T drecon
     if (gemm(c, s, false, true, n, d, F, rec, F, Rw, F, a2, d, 0.f)) return 1;              // da2 = drecon R^T (reuse a2)
     swish2_bwd_kernel<<<nblk((int64_t)n * d), 256, 0, s>>>(a2, enc, a1, (int64_t)n * d); TR_CHECK_LAUNCH(c);
-    colsum_kernel<<<dim3((d + 63) / 64, 32), 64, 0, s>>>(a2, n, d, gb); TR_CHECK_LAUNCH(c);
+    colsum_kernel<<<dim3((d + 63) / 64, COLSUM_SLICES), 256, 0, s>>>(a2, n, d, gb); TR_CHECK_LAUNCH(c);
     if (LIN_DW(n, d, F, a2, d, b->feat[0], F, gW, F)) return 1;
     sumsq_kernel<<<nblk((int64_t)d * F), 256, 0, s>>>(gW, (int64_t)d * F, misc + 1); TR_CHECK_LAUNCH(c);
     float h[2] = {0, 0};
