@@ -18,22 +18,24 @@
 
 // ------------------------------------------------------------------------------------------------ sgemm
 // C[M,N] = sum_k a(m,k) b(k,n) (+ beta*C);  a(m,k) = TA ? A[k*lda+m] : A[m*lda+k];  b(k,n) = TB ? B[n*ldb+k] : B[k*ldb+n]
-template <bool TA, bool TB>
+// BM = 64 or 32 rows per block (32 doubles the grid for the tall-skinny activations: 9216 x 64 would otherwise be 144 blocks)
+template <bool TA, bool TB, int BM>
 __global__ void __launch_bounds__(256) sgemm_kernel(int M, int N, int K, const float* __restrict__ A, int lda,
                                                     const float* __restrict__ B, int ldb, float* __restrict__ C, int ldc,
                                                     float beta) {
-    __shared__ float sA[16][65], sB[16][65];
+    constexpr int RM = BM / 16;                  // rows per thread
+    __shared__ __align__(16) float sA[16][BM + 4], sB[16][68];
     const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;
-    const int m0 = blockIdx.y * 64, n0 = blockIdx.x * 64;
-    float acc[4][4] = {};
+    const int m0 = blockIdx.y * BM, n0 = blockIdx.x * 64;
+    float acc[RM][4] = {};
     // split-K: gridDim.z slices of the reduction, combined with atomics (only launched with beta == 1)
     const int kchunk = ((K + (int)gridDim.z - 1) / (int)gridDim.z + 15) & ~15;
     const int kbeg = blockIdx.z * kchunk;
     K = min(K, kbeg + kchunk);
     for (int k0 = kbeg; k0 < K; k0 += 16) {
-        for (int i = threadIdx.x; i < 16 * 64; i += 256) {
+        for (int i = threadIdx.x; i < 16 * BM; i += 256) {
             int kk = i & 15, mm = i >> 4;
-            if (TA) { kk = i >> 6; mm = i & 63; }
+            if (TA) { kk = i / BM; mm = i % BM; }
             int m = m0 + mm, k = k0 + kk;
             sA[kk][mm] = (m < M && k < K) ? (TA ? A[(size_t)k * lda + m] : A[(size_t)m * lda + k]) : 0.f;
         }
@@ -46,27 +48,38 @@ __global__ void __launch_bounds__(256) sgemm_kernel(int M, int N, int K, const f
         __syncthreads();
 #pragma unroll
         for (int kk = 0; kk < 16; ++kk) {
-            float a[4], b[4];
+            float a[RM];
+            if (RM == 4) { float4 av = *reinterpret_cast<const float4*>(&sA[kk][ty * 4]); a[0] = av.x; a[1] = av.y; a[2 % RM] = av.z; a[3 % RM] = av.w; }
+            else { float2 av = *reinterpret_cast<const float2*>(&sA[kk][ty * 2]); a[0] = av.x; a[1] = av.y; }
+            const float4 bv = *reinterpret_cast<const float4*>(&sB[kk][tx * 4]);
 #pragma unroll
-            for (int i = 0; i < 4; ++i) { a[i] = sA[kk][ty * 4 + i]; b[i] = sB[kk][tx * 4 + i]; }
-#pragma unroll
-            for (int i = 0; i < 4; ++i)
-#pragma unroll
-                for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(a[i], b[j], acc[i][j]);
+            for (int i = 0; i < RM; ++i) {
+                acc[i][0] = fmaf(a[i], bv.x, acc[i][0]); acc[i][1] = fmaf(a[i], bv.y, acc[i][1]);
+                acc[i][2] = fmaf(a[i], bv.z, acc[i][2]); acc[i][3] = fmaf(a[i], bv.w, acc[i][3]);
+            }
         }
         __syncthreads();
     }
 #pragma unroll
-    for (int i = 0; i < 4; ++i)
+    for (int i = 0; i < RM; ++i)
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
-            int m = m0 + ty * 4 + i, n = n0 + tx * 4 + j;
+            int m = m0 + ty * RM + i, n = n0 + tx * 4 + j;
             if (m < M && n < N) {
                 float* p = C + (size_t)m * ldc + n;
                 if (gridDim.z > 1) atomicAdd(p, acc[i][j]);
                 else *p = (beta != 0.f) ? fmaf(beta, *p, acc[i][j]) : acc[i][j];
             }
         }
+}
+
+template <int BM>
+static void gemm_launch(cudaStream_t s, dim3 grid, bool ta, bool tb, int M, int N, int K, const float* A, int lda, const float* B, int ldb,
+                        float* C, int ldc, float beta) {
+    if (!ta && tb) sgemm_kernel<false, true, BM><<<grid, 256, 0, s>>>(M, N, K, A, lda, B, ldb, C, ldc, beta);
+    else if (!ta && !tb) sgemm_kernel<false, false, BM><<<grid, 256, 0, s>>>(M, N, K, A, lda, B, ldb, C, ldc, beta);
+    else if (ta && !tb) sgemm_kernel<true, false, BM><<<grid, 256, 0, s>>>(M, N, K, A, lda, B, ldb, C, ldc, beta);
+    else sgemm_kernel<true, true, BM><<<grid, 256, 0, s>>>(M, N, K, A, lda, B, ldb, C, ldc, beta);
 }
 
 static int gemm(hsg_ctx* c, cudaStream_t s, bool ta, bool tb, int M, int N, int K, const float* A, int lda, const float* B,
@@ -78,10 +91,12 @@ static int gemm(hsg_ctx* c, cudaStream_t s, bool ta, bool tb, int M, int N, int 
         int want = (2 * 148 + grid.x * grid.y - 1) / (grid.x * grid.y);
         grid.z = (unsigned)std::max(1, std::min(want, K / 128));
     }
-    if (!ta && tb) sgemm_kernel<false, true><<<grid, 256, 0, s>>>(M, N, K, A, lda, B, ldb, C, ldc, beta);
-    else if (!ta && !tb) sgemm_kernel<false, false><<<grid, 256, 0, s>>>(M, N, K, A, lda, B, ldb, C, ldc, beta);
-    else if (ta && !tb) sgemm_kernel<true, false><<<grid, 256, 0, s>>>(M, N, K, A, lda, B, ldb, C, ldc, beta);
-    else sgemm_kernel<true, true><<<grid, 256, 0, s>>>(M, N, K, A, lda, B, ldb, C, ldc, beta);
+    if (grid.z == 1 && grid.x * grid.y < 2 * 148 && M > 64) {       // tall-skinny activations: 32-row tiles, twice the blocks
+        grid.y = (M + 31) / 32;
+        gemm_launch<32>(s, grid, ta, tb, M, N, K, A, lda, B, ldb, C, ldc, beta);
+    } else {
+        gemm_launch<64>(s, grid, ta, tb, M, N, K, A, lda, B, ldb, C, ldc, beta);
+    }
     TR_CHECK_LAUNCH(c);
     return 0;
 }
@@ -457,39 +472,52 @@ __global__ void xp_fwd_kernel(const int64_t* __restrict__ x, int B, int A, int c
     }
     out[r] = o;
 }
-__global__ void xp_bwd_kernel(const int64_t* __restrict__ x, int B, int A, int cf, const float* __restrict__ attr,
+// One block per 256 hyperedges: dh / ids staged in shared memory, then ONE thread per output element (4 x in_w weights, 4 + 4 + 1
+// biases / output weights) walks the block's rows -- no contended atomics, one global atomic per output per block.
+__global__ void __launch_bounds__(256) xp_bwd_kernel(const int64_t* __restrict__ x, int B, int A, int cf, const float* __restrict__ attr,
                               const float* __restrict__ cellf, int only_model, const float* __restrict__ w1, const float* __restrict__ hpre,
                               const float* __restrict__ dout, float* __restrict__ dw0, float* __restrict__ db0, float* __restrict__ dw1,
                               float* __restrict__ db1) {
-    // block-level accumulation in shared memory ([4 * in_w] dw0, [4] db0, [4] dw1, [1] db1), one global atomic per value per block
-    extern __shared__ float acc[];
-    const int in_w = 2 * A + cf, n_acc = 4 * in_w + 9;
-    for (int i = threadIdx.x; i < n_acc; i += blockDim.x) acc[i] = 0.f;
-    __syncthreads();
-    float* a_b0 = acc + 4 * in_w; float* a_w1 = a_b0 + 4; float* a_b1 = a_w1 + 4;
-    int r = blockIdx.x * blockDim.x + threadIdx.x;
-    if (r < B) {
-        const float g = dout[r];
-        const float* ai = attr + (size_t)x[r * 3 + 1] * A; const float* aj = attr + (size_t)x[r * 3 + 2] * A;
-        const float* cfp = cellf + (size_t)x[r * 3] * cf;
-        atomicAdd(a_b1, g);
+    __shared__ float s_dh[256][4], s_gs[256][4], s_g[256];
+    __shared__ int s_x[256][3];
+    const int in_w = 2 * A + cf;
+    const int r0 = blockIdx.x * 256, nr = min(256, B - r0);
+    {
+        const int r = r0 + threadIdx.x;
+        const bool ok = threadIdx.x < nr;
+        const float g = ok ? dout[r] : 0.f;
+        s_g[threadIdx.x] = g;
+#pragma unroll
         for (int u = 0; u < 4; ++u) {
-            float pre = hpre[r * 4 + u];
-            atomicAdd(a_w1 + u, g * swish_acc(pre));
-            float dh = g * w1[u] * dswish(pre);
-            atomicAdd(a_b0 + u, dh);
-            for (int t = 0; t < A; ++t) { atomicAdd(acc + u * in_w + t, dh * ai[t]); atomicAdd(acc + u * in_w + A + t, dh * aj[t]); }
-            if (!only_model) for (int t = 0; t < cf; ++t) atomicAdd(acc + u * in_w + 2 * A + t, dh * cfp[t]);
+            const float pre = ok ? hpre[r * 4 + u] : 0.f;
+            s_gs[threadIdx.x][u] = g * swish_acc(pre);
+            s_dh[threadIdx.x][u] = g * w1[u] * dswish(pre);
         }
+#pragma unroll
+        for (int q = 0; q < 3; ++q) s_x[threadIdx.x][q] = ok ? (int)x[r * 3 + q] : 0;
     }
     __syncthreads();
-    for (int i = threadIdx.x; i < n_acc; i += blockDim.x) {
-        float v = acc[i];
-        if (v == 0.f) continue;
-        if (i < 4 * in_w) atomicAdd(dw0 + i, v);
-        else if (i < 4 * in_w + 4) atomicAdd(db0 + (i - 4 * in_w), v);
-        else if (i < 4 * in_w + 8) atomicAdd(dw1 + (i - 4 * in_w - 4), v);
-        else atomicAdd(db1, v);
+    for (int o = threadIdx.x; o < 4 * in_w + 9; o += 256) {
+        float acc = 0.f;
+        if (o < 4 * in_w) {
+            const int u = o / in_w, t = o - u * in_w;
+            if (t >= 2 * A && only_model) continue;
+            const float* base = (t < 2 * A) ? attr + (t < A ? t : t - A) : cellf + (t - 2 * A);
+            const int which = (t < A) ? 1 : (t < 2 * A ? 2 : 0), stride = (t < 2 * A) ? A : cf;
+            for (int r = 0; r < nr; ++r) acc = fmaf(s_dh[r][u], __ldg(base + (size_t)s_x[r][which] * stride), acc);
+            atomicAdd(dw0 + o, acc);
+        } else if (o < 4 * in_w + 4) {
+            const int u = o - 4 * in_w;
+            for (int r = 0; r < nr; ++r) acc += s_dh[r][u];
+            atomicAdd(db0 + u, acc);
+        } else if (o < 4 * in_w + 8) {
+            const int u = o - 4 * in_w - 4;
+            for (int r = 0; r < nr; ++r) acc += s_gs[r][u];
+            atomicAdd(dw1 + u, acc);
+        } else {
+            for (int r = 0; r < nr; ++r) acc += s_g[r];
+            atomicAdd(db1, acc);
+        }
     }
 }
 // head = mean over the 3 tokens + side channel
@@ -917,7 +945,7 @@ extern "C" int hsg_score_bwd(hsg_ctx* c, void* stream) {
     const int bin_base = c->n_cells + 1 + c->bin_off[chrom];
     const int64_t nRd = (int64_t)R * d;
     // heads
-    xp_bwd_kernel<<<nblk(B), 256, (4 * (2 * (c->n_chrom + 1) + c->cf) + 9) * sizeof(float), s>>>(w->x, B, c->n_chrom + 1, c->cf, c->w[HSG_W_ATTR], c->w[HSG_W_CELL_FEATS], w->only_model,
+    xp_bwd_kernel<<<nblk(B), 256, 0, s>>>(w->x, B, c->n_chrom + 1, c->cf, c->w[HSG_W_ATTR], c->w[HSG_W_CELL_FEATS], w->only_model,
                                           PARAM(HSG_W_XP2_W1), w->hp2, w->dmean, GRAD(HSG_W_XP2_W0), GRAD(HSG_W_XP2_B0),
                                           GRAD(HSG_W_XP2_W1), GRAD(HSG_W_XP2_B1));
     TR_CHECK_LAUNCH(c);
@@ -930,11 +958,11 @@ extern "C" int hsg_score_bwd(hsg_ctx* c, void* stream) {
     if (LIN_DX(R, hd, d, w->dc, hd, PARAM(HSG_W_CLS_W0), d, w->du, d, 0.f)) return 1;
     HSG_CUDA(cudaMemsetAsync(w->dS, 0, nRd * sizeof(float), s));
     if (w->mode == 2) {        // zinb: the var and proba heads read the normalised static branch
-        xp_bwd_kernel<<<nblk(B), 256, (4 * (2 * (c->n_chrom + 1) + c->cf) + 9) * sizeof(float), s>>>(w->x, B, c->n_chrom + 1, c->cf, c->w[HSG_W_ATTR], c->w[HSG_W_CELL_FEATS], w->only_model,
+        xp_bwd_kernel<<<nblk(B), 256, 0, s>>>(w->x, B, c->n_chrom + 1, c->cf, c->w[HSG_W_ATTR], c->w[HSG_W_CELL_FEATS], w->only_model,
                                               PARAM(HSG_W_XP3_W1), w->hp3, w->dvar, GRAD(HSG_W_XP3_W0), GRAD(HSG_W_XP3_B0),
                                               GRAD(HSG_W_XP3_W1), GRAD(HSG_W_XP3_B1));
         TR_CHECK_LAUNCH(c);
-        xp_bwd_kernel<<<nblk(B), 256, (4 * (2 * (c->n_chrom + 1) + c->cf) + 9) * sizeof(float), s>>>(w->x, B, c->n_chrom + 1, c->cf, c->w[HSG_W_ATTR], c->w[HSG_W_CELL_FEATS], w->only_model,
+        xp_bwd_kernel<<<nblk(B), 256, 0, s>>>(w->x, B, c->n_chrom + 1, c->cf, c->w[HSG_W_ATTR], c->w[HSG_W_CELL_FEATS], w->only_model,
                                               PARAM(HSG_W_XP_W1), w->hp1, w->dproba, GRAD(HSG_W_XP_W0), GRAD(HSG_W_XP_B0),
                                               GRAD(HSG_W_XP_W1), GRAD(HSG_W_XP_B1));
         TR_CHECK_LAUNCH(c);
