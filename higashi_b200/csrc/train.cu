@@ -557,21 +557,29 @@ __global__ void mse_kernel(const float* __restrict__ pred, const float* __restri
 // do[row] = dmean[row/3] / 3 ; dc[row, j] = do[row] * w1[j] ; dw1[j] += do * c ; db1 += do
 __global__ void head_bwd_kernel(const float* __restrict__ dmean, const float* __restrict__ cact, int rows, int hd,
                                 const float* __restrict__ w1, float* __restrict__ dc, float* __restrict__ dw1, float* __restrict__ db1) {
-    extern __shared__ float sh[];                 // hd + 1 partial sums
-    for (int i = threadIdx.x; i <= hd; i += blockDim.x) sh[i] = 0.f;
-    __syncthreads();
-    int row = blockIdx.x * blockDim.x + threadIdx.x;
-    if (row < rows) {
-        float g = dmean[row / 3] / 3.0f;
-        atomicAdd(&sh[hd], g);
-        for (int j = 0; j < hd; ++j) {
-            dc[(size_t)row * hd + j] = g * w1[j];
-            atomicAdd(&sh[j], g * cact[(size_t)row * hd + j]);
+    // 256 rows per block; thread (j = tid % hd, lane group = tid / hd) walks rows so that a warp reads contiguous cact columns:
+    // per-thread partial sums, shared-memory combine, one global atomic per output column per block
+    extern __shared__ float sh[];                 // [groups][hd + 1]
+    const int groups = blockDim.x / hd, j = threadIdx.x % hd, grp = threadIdx.x / hd;
+    const int r0 = blockIdx.x * 256, r1 = min(rows, r0 + 256);
+    float sw = 0.f, sb = 0.f;
+    if (grp < groups) {
+        const float wj = w1[j];
+        for (int row = r0 + grp; row < r1; row += groups) {
+            const float g = dmean[row / 3] / 3.0f;
+            dc[(size_t)row * hd + j] = g * wj;
+            sw = fmaf(g, cact[(size_t)row * hd + j], sw);
+            sb += g;
         }
+        sh[grp * (hd + 1) + j] = sw;
+        if (j == 0) sh[grp * (hd + 1) + hd] = sb;
     }
     __syncthreads();
-    for (int i = threadIdx.x; i < hd; i += blockDim.x) atomicAdd(dw1 + i, sh[i]);
-    if (threadIdx.x == 0) atomicAdd(db1, sh[hd]);
+    if (threadIdx.x <= hd) {
+        float v = 0.f;
+        for (int gq = 0; gq < groups; ++gq) v += sh[gq * (hd + 1) + threadIdx.x];
+        atomicAdd(threadIdx.x < hd ? dw1 + threadIdx.x : db1, v);
+    }
 }
 
 
@@ -949,7 +957,7 @@ extern "C" int hsg_score_bwd(hsg_ctx* c, void* stream) {
                                           PARAM(HSG_W_XP2_W1), w->hp2, w->dmean, GRAD(HSG_W_XP2_W0), GRAD(HSG_W_XP2_B0),
                                           GRAD(HSG_W_XP2_W1), GRAD(HSG_W_XP2_B1));
     TR_CHECK_LAUNCH(c);
-    head_bwd_kernel<<<nblk(R), 256, (hd + 1) * sizeof(float), s>>>(w->dmean, w->cact, R, hd, PARAM(HSG_W_CLS_W1), w->dc, GRAD(HSG_W_CLS_W1),
+    head_bwd_kernel<<<nblk(R), 256, (256 / hd) * (hd + 1) * sizeof(float), s>>>(w->dmean, w->cact, R, hd, PARAM(HSG_W_CLS_W1), w->dc, GRAD(HSG_W_CLS_W1),
                                                                    GRAD(HSG_W_CLS_B1));
     TR_CHECK_LAUNCH(c);
     dswish_kernel<<<nblk((int64_t)R * hd), 256, 0, s>>>(w->dc, w->cpre, (int64_t)R * hd); TR_CHECK_LAUNCH(c);
@@ -969,7 +977,7 @@ extern "C" int hsg_score_bwd(hsg_ctx* c, void* stream) {
         const int slots[2][4] = {{HSG_W_VAR_W0, HSG_W_VAR_B0, HSG_W_VAR_W1, HSG_W_VAR_B1}, {HSG_W_PRB_W0, HSG_W_PRB_B0, HSG_W_PRB_W1, HSG_W_PRB_B1}};
         float* dh[2] = {w->dvar, w->dproba}; float* act[2] = {w->vact, w->pact}; float* pre[2] = {w->vpre, w->ppre};
         for (int q = 0; q < 2; ++q) {
-            head_bwd_kernel<<<nblk(R), 256, (hd + 1) * sizeof(float), s>>>(dh[q], act[q], R, hd, PARAM(slots[q][2]), w->dc, GRAD(slots[q][2]),
+            head_bwd_kernel<<<nblk(R), 256, (256 / hd) * (hd + 1) * sizeof(float), s>>>(dh[q], act[q], R, hd, PARAM(slots[q][2]), w->dc, GRAD(slots[q][2]),
                                                                            GRAD(slots[q][3]));
             TR_CHECK_LAUNCH(c);
             dswish_kernel<<<nblk((int64_t)R * hd), 256, 0, s>>>(w->dc, pre[q], (int64_t)R * hd); TR_CHECK_LAUNCH(c);
