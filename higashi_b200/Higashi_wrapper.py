@@ -238,18 +238,26 @@ class Higashi:
 
     def train(self, stage, epochs, dynamic_pair_ratio=False, pair_ratio=0.5, beta=1e-2, save_embed=False, save_name=""):
         eng = self._engine(stage)
+        # training batches are produced on the device (negatives, labels, neighbour lists: hsg_sample_batch); the host
+        # restatement (NegativeSampler + batches.neighbor_csr) stays for validation batches and as the tests' cross-check
+        eng.set_graph(self.csr, self.nbr, self.nbr_w)
         tr = parallel.DataParallelTrainer(eng, lr=1e-3)
         mode = LOSS_MODES[self.mode]
         best, no_improve = 1000.0, 0
+        n_batches = 0
         for epoch_i in range(epochs):
             t0, tot = time.time(), 0.0
             for _ in range(self.update_num_per_training_epoch):
-                x, y, w, chrom = self._batch(self.training_data_generator, pair_ratio, True)
-                nb = None
-                if stage >= 2:
-                    nb = batches.neighbor_csr(self.csr, x, chrom, self.num_list, training=True, nbr=self.nbr, nbr_w=self.nbr_w)
-                tot += tr.step(x, chrom, nb, y, w, stage=min(stage, 2), loss_mode=mode, train_mode=True, beta=beta,
-                               median_sparsity=self.median_total_sparsity_cell, contractive_weight=self.contractive_loss_weight if stage == 1 else 0.0)
+                e, _, w, chroms = self.training_data_generator.next_iter()
+                chrom = int(chroms[0])
+                n_batches += 1
+                e = np.asarray(e, dtype=np.int64)
+                e[:, 1:] = np.sort(e[:, 1:], axis=1)
+                B, nnz = eng.sample_batch(e, chrom, self.neg_num, pair_ratio, self.max_bin, pos_w=np.asarray(w).reshape(-1), training=True,
+                                          classification=(self.mode == "classification"), seed=(int(self.config.get("random_seed", 0)) << 20) + n_batches)
+                tot += tr.step(None, chrom, None, None, None, stage=min(stage, 2), loss_mode=mode, train_mode=True, beta=beta,
+                               median_sparsity=self.median_total_sparsity_cell, contractive_weight=self.contractive_loss_weight if stage == 1 else 0.0,
+                               sampled=(B, nnz))
             bce = tot / self.update_num_per_training_epoch
             vt = 0.0
             eng.set_dropout(False)

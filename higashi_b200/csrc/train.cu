@@ -230,13 +230,14 @@ static int ln_bwd(hsg_ctx* c, cudaStream_t s, const float* dy, const float* x, i
 // ------------------------------------------------------------------------------------------------ node embedding
 // CSR SpMM over the bin-token rows: neigh[row] = sum_e val[e] * E[col[e]]        (Modules.py:1356-1360)
 template <int D>
-__global__ void spmm_fwd_kernel(const int* __restrict__ indptr, const int* __restrict__ cols, const float* __restrict__ vals,
-                                const float* __restrict__ E, int rows, float* __restrict__ out) {
+__global__ void spmm_fwd_kernel(const int* __restrict__ indptr, const int* __restrict__ rowcnt, const int* __restrict__ cols,
+                                const float* __restrict__ vals, const float* __restrict__ E, int rows, float* __restrict__ out) {
     int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5), lane = threadIdx.x & 31;
     if (row >= rows) return;
     constexpr int V = D / 32;
     float acc[V] = {};
-    for (int e = indptr[row]; e < indptr[row + 1]; ++e) {
+    const int e_end = rowcnt ? indptr[row] + rowcnt[row] : indptr[row + 1];
+    for (int e = indptr[row]; e < e_end; ++e) {
         float w = vals[e];
         const float* er = E + (size_t)cols[e] * D;
 #pragma unroll
@@ -246,15 +247,16 @@ __global__ void spmm_fwd_kernel(const int* __restrict__ indptr, const int* __res
     for (int q = 0; q < V; ++q) out[(size_t)row * D + q * 32 + lane] = acc[q];
 }
 template <int D>
-__global__ void spmm_bwd_kernel(const int* __restrict__ indptr, const int* __restrict__ cols, const float* __restrict__ vals,
-                                const float* __restrict__ dout, int rows, float* __restrict__ dE) {
+__global__ void spmm_bwd_kernel(const int* __restrict__ indptr, const int* __restrict__ rowcnt, const int* __restrict__ cols,
+                                const float* __restrict__ vals, const float* __restrict__ dout, int rows, float* __restrict__ dE) {
     int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5), lane = threadIdx.x & 31;
     if (row >= rows) return;
     constexpr int V = D / 32;
     float d[V];
 #pragma unroll
     for (int q = 0; q < V; ++q) d[q] = dout[(size_t)row * D + q * 32 + lane];
-    for (int e = indptr[row]; e < indptr[row + 1]; ++e) {
+    const int e_end = rowcnt ? indptr[row] + rowcnt[row] : indptr[row + 1];
+    for (int e = indptr[row]; e < e_end; ++e) {
         float w = vals[e];
         float* er = dE + (size_t)cols[e] * D;
 #pragma unroll
@@ -661,6 +663,7 @@ struct TrainWs {
     int maxB = 0, max_nnz = 0, max_nc = 0;
     float* buf = nullptr; size_t floats = 0;
     int* indptr = nullptr; int* cols = nullptr; float* vals = nullptr;
+    int* rowcnt = nullptr; bool sampled = false;       // batch left by hsg_sample_batch: row r = [indptr[r], indptr[r] + rowcnt[r])
     int64_t* x = nullptr; float* y = nullptr; float* w = nullptr;
     // forward activations (all [rows, *] row-major)
     float *Epre, *Eall, *neigh, *selfb, *combpre, *comb, *dyn, *sta, *mu_d, *rs_d, *mu_s, *rs_s, *qin, *kin, *vin, *Q, *K, *V, *P,
@@ -724,7 +727,7 @@ static int ws_cell_alloc(hsg_ctx* c, TrainWs* w, int B, int F) {
 static int ws_alloc(hsg_ctx* c, int maxB, int max_nnz) {
     TrainWs*& w = g_ws[c];
     if (w && w->maxB >= maxB && w->max_nnz >= max_nnz) return 0;
-    if (w) { cudaFree(w->buf); cudaFree(w->indptr); cudaFree(w->cols); cudaFree(w->vals); cudaFree(w->x); delete w; }
+    if (w) { cudaFree(w->buf); cudaFree(w->indptr); cudaFree(w->rowcnt); cudaFree(w->cols); cudaFree(w->vals); cudaFree(w->x); delete w; }
     w = new TrainWs();
     w->maxB = maxB; w->max_nnz = max_nnz;
     int max_nc = 0; for (int v : c->bins) max_nc = std::max(max_nc, v);
@@ -754,6 +757,7 @@ static int ws_alloc(hsg_ctx* c, int maxB, int max_nnz) {
     for (size_t i = 0; i < plan.size(); ++i) *plan[i].first = w->buf + offs[i];
     w->floats = total;
     HSG_CUDA(cudaMalloc(&w->indptr, (NB + 1) * sizeof(int)));
+    HSG_CUDA(cudaMalloc(&w->rowcnt, (NB + 1) * sizeof(int)));
     HSG_CUDA(cudaMalloc(&w->cols, (size_t)std::max(1, max_nnz) * sizeof(int)));
     HSG_CUDA(cudaMalloc(&w->vals, (size_t)std::max(1, max_nnz) * sizeof(float)));
     HSG_CUDA(cudaMalloc(&w->x, ((size_t)maxB * 3) * sizeof(int64_t) + (size_t)maxB * 2 * sizeof(float)));
@@ -761,6 +765,8 @@ static int ws_alloc(hsg_ctx* c, int maxB, int max_nnz) {
     w->w = w->y + maxB;
     return 0;
 }
+
+#include "sampler.cuh"
 
 struct TrainOpts { float* c2w = nullptr; float rank_thres = 0.f; int dropout = 0; unsigned long long seed = 0; };
 static std::map<hsg_ctx*, TrainOpts> g_opts;
@@ -810,9 +816,15 @@ extern "C" int hsg_score_fwd(hsg_ctx* c, int stage, int chrom, const int64_t* x_
     HSG_CHECK(c && c->d > 0, "context not initialised");
     HSG_CUDA(cudaSetDevice(c->device));
     HSG_CHECK(stage == 1 || stage == 2, "stage must be 1 (MultipleEmbedding) or 2 (GraphSAGE on-hook)");
-    HSG_CHECK(chrom >= 0 && chrom < c->n_chrom && B > 0 && x_host, "bad batch");
+    HSG_CHECK(chrom >= 0 && chrom < c->n_chrom && B > 0, "bad batch");
+    // x_host == NULL: run on the batch hsg_sample_batch left in the workspace (B / nnz must be the values it returned)
+    const bool dev_batch = (x_host == nullptr);
+    if (dev_batch) {
+        auto it = g_ws.find(c);
+        HSG_CHECK(it != g_ws.end() && it->second && it->second->sampled && it->second->chrom == chrom, "x_host is NULL but there is no sampled batch for this chromosome");
+    }
     HSG_CHECK(loss_mode >= 0 && loss_mode <= 3, "loss_mode must be 0..3");
-    HSG_CHECK(stage == 1 || (indptr_host && (nnz == 0 || (cols_local_host && vals_host))), "stage 2 needs the neighbour CSR");
+    HSG_CHECK(stage == 1 || dev_batch || (indptr_host && (nnz == 0 || (cols_local_host && vals_host))), "stage 2 needs the neighbour CSR");
     TrainBind* b = bind_of(c);
     HSG_CHECK(b->params != nullptr, "call hsg_train_bind first");
     HSG_CHECK((int)b->feat.size() > chrom + 1 && b->feat[chrom + 1] != nullptr, "call hsg_train_set_features for this chromosome");
@@ -826,10 +838,14 @@ extern "C" int hsg_score_fwd(hsg_ctx* c, int stage, int chrom, const int64_t* x_
     const int d = c->d, hd = d / 2, R = 3 * B, NB = 2 * B, nc = c->bins[chrom], in_c = b->in_dim[chrom + 1];
     const int bin_base = c->n_cells + 1 + c->bin_off[chrom];
     w->B = B; w->chrom = chrom; w->nnz = nnz; w->stage = stage; w->only_model = only_model; w->mode = loss_mode;
-    HSG_CUDA(cudaMemcpyAsync(w->x, x_host, (size_t)B * 3 * sizeof(int64_t), cudaMemcpyHostToDevice, s));
-    if (y_host) HSG_CUDA(cudaMemcpyAsync(w->y, y_host, B * sizeof(float), cudaMemcpyHostToDevice, s));
-    if (w_host) HSG_CUDA(cudaMemcpyAsync(w->w, w_host, B * sizeof(float), cudaMemcpyHostToDevice, s));
-    if (stage == 2) {
+    if (!dev_batch) {
+        w->sampled = false;
+        HSG_CUDA(cudaMemcpyAsync(w->x, x_host, (size_t)B * 3 * sizeof(int64_t), cudaMemcpyHostToDevice, s));
+        if (y_host) HSG_CUDA(cudaMemcpyAsync(w->y, y_host, B * sizeof(float), cudaMemcpyHostToDevice, s));
+        if (w_host) HSG_CUDA(cudaMemcpyAsync(w->w, w_host, B * sizeof(float), cudaMemcpyHostToDevice, s));
+    }
+    const bool have_y = dev_batch || y_host != nullptr, have_w = dev_batch || w_host != nullptr;
+    if (stage == 2 && !dev_batch) {
         HSG_CUDA(cudaMemcpyAsync(w->indptr, indptr_host, (NB + 1) * sizeof(int), cudaMemcpyHostToDevice, s));
         if (nnz) {
             HSG_CUDA(cudaMemcpyAsync(w->cols, cols_local_host, nnz * sizeof(int), cudaMemcpyHostToDevice, s));
@@ -844,8 +860,8 @@ extern "C" int hsg_score_fwd(hsg_ctx* c, int stage, int chrom, const int64_t* x_
     if (stage == 2) {
         assemble_kernel<<<nblk((int64_t)R * d), 256, 0, s>>>(w->x, B, d, c->n_cells, bin_base, c->E_cell, w->Eall, nullptr, w->dyn, w->sta, w->selfb);
         TR_CHECK_LAUNCH(c);
-        if (d == 64) spmm_fwd_kernel<64><<<(NB + 7) / 8, 256, 0, s>>>(w->indptr, w->cols, w->vals, w->Eall, NB, w->neigh);
-        else spmm_fwd_kernel<128><<<(NB + 7) / 8, 256, 0, s>>>(w->indptr, w->cols, w->vals, w->Eall, NB, w->neigh);
+        if (d == 64) spmm_fwd_kernel<64><<<(NB + 7) / 8, 256, 0, s>>>(w->indptr, w->sampled ? w->rowcnt : nullptr, w->cols, w->vals, w->Eall, NB, w->neigh);
+        else spmm_fwd_kernel<128><<<(NB + 7) / 8, 256, 0, s>>>(w->indptr, w->sampled ? w->rowcnt : nullptr, w->cols, w->vals, w->Eall, NB, w->neigh);
         TR_CHECK_LAUNCH(c);
         const float* G = PARAM(HSG_W_SAGE_W);
         if (LIN_FWD(NB, d, d, w->neigh, d, G, 2 * d, w->comb, d, 0.f)) return 1;
@@ -923,7 +939,7 @@ extern "C" int hsg_score_fwd(hsg_ctx* c, int stage, int chrom, const int64_t* x_
     }
     // 6. loss: 0 classification (weighted BCE with logits), 1 regression (MSE against w), 2 zinb, 3 rank
     HSG_CUDA(cudaMemsetAsync(w->loss, 0, 4 * sizeof(float), s));
-    if (w_host && (y_host || loss_mode != 0)) {
+    if (have_w && (have_y || loss_mode != 0)) {
         if (loss_mode == 0) bce_kernel<<<nblk(B), 256, 0, s>>>(w->mean, w->y, w->w, B, w->loss, w->dmean);
         else if (loss_mode == 1) mse_kernel<<<nblk(B), 256, 0, s>>>(w->mean, w->w, B, w->loss, w->dmean);
         else if (loss_mode == 2)
@@ -1033,8 +1049,8 @@ extern "C" int hsg_score_bwd(hsg_ctx* c, void* stream) {
         if (LIN_DX(NB, d, d, w->dcomb, d, G, 2 * d, w->dneigh, d, 0.f)) return 1;
         if (LIN_DX(NB, d, d, w->dcomb, d, G + d, 2 * d, w->dself, d, 0.f)) return 1;
         scatter_rows_kernel<<<nblk(nNd), 256, 0, s>>>(w->x, B, d, bin_base, w->dself, w->dEall); TR_CHECK_LAUNCH(c);
-        if (d == 64) spmm_bwd_kernel<64><<<(NB + 7) / 8, 256, 0, s>>>(w->indptr, w->cols, w->vals, w->dneigh, NB, w->dEall);
-        else spmm_bwd_kernel<128><<<(NB + 7) / 8, 256, 0, s>>>(w->indptr, w->cols, w->vals, w->dneigh, NB, w->dEall);
+        if (d == 64) spmm_bwd_kernel<64><<<(NB + 7) / 8, 256, 0, s>>>(w->indptr, w->sampled ? w->rowcnt : nullptr, w->cols, w->vals, w->dneigh, NB, w->dEall);
+        else spmm_bwd_kernel<128><<<(NB + 7) / 8, 256, 0, s>>>(w->indptr, w->sampled ? w->rowcnt : nullptr, w->cols, w->vals, w->dneigh, NB, w->dEall);
         TR_CHECK_LAUNCH(c);
     }
     if (w->stage == 1 && w->cell_on_hook) {

@@ -135,7 +135,7 @@ class DataParallelTrainer:
         return self._patterns[key]
 
     def step(self, x, chrom, to_neighs, y, w, stage=2, loss_mode=0, train_mode=True, alpha=1.0, beta=1e-2,
-             median_sparsity=0.0, contractive_weight=0.0, want_loss=True):
+             median_sparsity=0.0, contractive_weight=0.0, want_loss=True, sampled=None):
         """One update.  stage 1 reproduces train_epoch's three backward passes (Higashi_wrapper.py:970-1006):
         gradient of the main loss, gradient of the reconstruction loss, ratio1 = max(beta*|g_main|/|g_recon|,
         100*median_sparsity - 3), total = alpha*main + ratio1*recon + contractive."""
@@ -143,7 +143,7 @@ class DataParallelTrainer:
         self.eng.set_dropout(train_mode, seed=0x5EED0000 + self.n_steps)
         self.eng.zero_grad()
         _, loss = self.eng.forward(x, chrom, to_neighs, y=y, w=w, stage=stage, loss_mode=loss_mode, want_outputs=want_loss,
-                                   want_mean=False)
+                                   want_mean=False, sampled=sampled)
         self.eng.backward()
         if alpha != 1.0:
             self.eng.grads.mul_(alpha)

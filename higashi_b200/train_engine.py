@@ -129,10 +129,52 @@ class TrainEngine:
     def zero_grad(self):
         self.grads.zero_()
 
+    # ---- device batch producer (generate_negative_cpu + one_thread_generate_neg, Higashi_wrapper.py:95-333) ------------------
+    def set_graph(self, csr, nbr=None, nbr_w=None):
+        """Contacts (PackedCSR) and optional kNN cell graph (1-based ids, self first) the batch producer samples against."""
+        self.ctx.set_contacts(csr.row_ptr, csr.col, csr.val)
+        if nbr is not None:
+            self.ctx.set_neighbors(np.ascontiguousarray(np.asarray(nbr) - 1, dtype=np.int32), np.ascontiguousarray(nbr_w, dtype=np.float32))
+
+    def sample_batch(self, pos, chrom: int, neg_num: int, pair_ratio: float, max_bin: int, pos_w=None, training: bool = True,
+                     classification: bool = True, wide_check: bool = True, seed: int = 0):
+        """Builds [positives ; negatives], labels, weights and the neighbour CSR on the device; returns (B, nnz) for
+        forward(None, chrom, sampled=(B, nnz))."""
+        pos = np.ascontiguousarray(_np(pos), dtype=np.int64)
+        pw = None if pos_w is None else np.ascontiguousarray(_np(pos_w), dtype=np.float32).reshape(-1)
+        B, nnz = C.c_int32(0), C.c_int64(0)
+        stream = torch.cuda.current_stream(self.device).cuda_stream
+        self.ctx._check(self.ctx.lib.hsg_sample_batch(
+            self.ctx.h, pos.ctypes.data_as(C.POINTER(C.c_int64)), None if pw is None else pw.ctypes.data_as(C.POINTER(C.c_float)),
+            pos.shape[0], int(chrom), int(neg_num), C.c_float(pair_ratio), int(max_bin), 1 if wide_check else 0, 1 if training else 0,
+            C.c_float(1.0 if classification else 0.0), C.c_uint64(int(seed) & (2 ** 64 - 1)), C.byref(B), C.byref(nnz), C.c_void_p(stream)))
+        return int(B.value), int(nnz.value)
+
+    def fetch_sampled(self, B: int, nnz: int):
+        """(x, y, w, indptr, rowcnt, cols, vals) of the batch the producer left on the device (tests / debugging)."""
+        x = np.empty((B, 3), np.int64); y = np.empty(B, np.float32); w = np.empty(B, np.float32)
+        indptr = np.empty(2 * B + 1, np.int32); rowcnt = np.empty(2 * B, np.int32)
+        cols = np.empty(max(nnz, 1), np.int32); vals = np.empty(max(nnz, 1), np.float32)
+        stream = torch.cuda.current_stream(self.device).cuda_stream
+        pt = lambda a, t: a.ctypes.data_as(C.POINTER(t))
+        self.ctx._check(self.ctx.lib.hsg_sampled_fetch(self.ctx.h, pt(x, C.c_int64), pt(y, C.c_float), pt(w, C.c_float), pt(indptr, C.c_int32),
+                                                       pt(rowcnt, C.c_int32), pt(cols, C.c_int32), pt(vals, C.c_float), C.c_void_p(stream)))
+        return x, y, w, indptr, rowcnt, cols[:nnz], vals[:nnz]
+
     def forward(self, x, chrom: int, to_neighs=None, y=None, w=None, stage: int = 2, loss_mode: int = LOSS_CLASSIFICATION,
-                only_model: bool = False, want_outputs: bool = True, want_mean: bool = True):
+                only_model: bool = False, want_outputs: bool = True, want_mean: bool = True, sampled=None):
         """One minibatch of ONE chromosome (DataGenerator.next_iter draws one chromosome per batch, Modules.py:1205).
-        Returns (mean float32 [B] or None, loss float or None)."""
+        Returns (mean float32 [B] or None, loss float or None).  x = None with sampled = (B, nnz): the batch sample_batch left
+        on the device."""
+        if x is None:
+            B, nnz = sampled
+            mean = np.empty(B, dtype=np.float32) if (want_outputs and want_mean) else None
+            loss = np.zeros(1, dtype=np.float32) if want_outputs else None
+            stream = torch.cuda.current_stream(self.device).cuda_stream
+            fp = lambda a: None if a is None else a.ctypes.data_as(C.POINTER(C.c_float))
+            self.ctx._check(self.ctx.lib.hsg_score_fwd(self.ctx.h, int(stage), int(chrom), None, B, None, None, None, int(nnz), None, None,
+                                                       int(loss_mode), 1 if only_model else 0, fp(mean), fp(loss), C.c_void_p(stream)))
+            return mean, (None if loss is None else float(loss[0]))
         x = np.ascontiguousarray(_np(x), dtype=np.int64)
         B = x.shape[0]
         bin_base = int(self.num_list[chrom]) + 1

@@ -151,7 +151,8 @@ int  hsg_train_set_features(hsg_ctx* ctx, int branch, const float* x_host, int64
  * of the chromosome, vals = normalised weights).  x host int64 [B,3] node ids; y, w host float [B] (NULL = no loss).
  * loss_mode 0 = classification (weighted BCE with logits), 1 = regression (MSE against w), 2 = zinb (-log_zinb_positive,
  * Modules.py:30-80, needs hsg_train_options), 3 = rank (pairwise BCE, Higashi_wrapper.py:880-888).  Eval-mode semantics
- * (dropout off).  mean_out / loss_out: host outputs (may be NULL).                                                  */
+ * (dropout off).  mean_out / loss_out: host outputs (may be NULL).  x_host = NULL: run on the batch hsg_sample_batch
+ * left on the device (B and nnz as it returned them; the neighbour / label pointers are ignored).                         */
 int  hsg_score_fwd(hsg_ctx* ctx, int stage, int chrom, const int64_t* x_host, int B, const int32_t* indptr_host,
                    const int32_t* cols_local_host, const float* vals_host, int nnz, const float* y_host, const float* w_host,
                    int loss_mode, int only_model, float* mean_out_host, float* loss_out_host, void* stream);
@@ -164,6 +165,23 @@ int  hsg_train_set_dropout(hsg_ctx* ctx, int enabled, uint64_t seed);
 /* the three heads of the last forward batch (var / proba are produced by loss_mode 2 = zinb only) and, in zinb mode, the
  * clamped mean `pred` that forward_batch_hyperedge returns; host float [B] each, any may be NULL                       */
 int  hsg_score_heads(hsg_ctx* ctx, float* mean_host, float* var_host, float* proba_host, float* pred_host, void* stream);
+/* ---- training batch producer on the device ------------------------------
+ * replaces: generate_negative_cpu + check_nonzero (Higashi_wrapper.py:71-168), the label / weight assembly and the neighbour-
+ * list builder of one_thread_generate_neg (:236-333) and to_neighs_to_mask (:171-221) for ONE minibatch of ONE chromosome.
+ * pos host int64 [Bp,3] (cell id, bin_i < bin_j global ids), pos_w host float [Bp] edge weights (NULL = 1); neg_num
+ * negatives per positive by rejection sampling (<= 50 trials, hard negatives with probability pair_ratio, 1 < |bj-bi| <
+ * max_bin, candidate rejected while it touches a stored contact: 3x3 neighbourhood if wide_check else the entry itself);
+ * neg_weight = weight of a negative (1 classification, 0 otherwise); training != 0 enables the 40 % partner removal.
+ * Uses the contacts (hsg_set_contacts) and, if set, the kNN graph (hsg_set_neighbors).  The batch [positives ; accepted
+ * negatives] with labels, weights and the neighbour CSR stays on the device: call hsg_score_fwd with x_host = NULL,
+ * B = *B_out, nnz = *nnz_out.  Counter-based random numbers: same (seed, inputs) -> same batch.                          */
+int  hsg_sample_batch(hsg_ctx* ctx, const int64_t* pos_host, const float* pos_w_host, int Bp, int chrom, int neg_num,
+                      float pair_ratio, int max_bin, int wide_check, int training, float neg_weight, uint64_t seed,
+                      int* B_out, int64_t* nnz_out, void* stream);
+/* copies the produced batch to the host (tests / debugging); row r of the neighbour CSR = [indptr[r], indptr[r] + rowcnt[r]);
+ * any pointer may be NULL                                                                                               */
+int  hsg_sampled_fetch(hsg_ctx* ctx, int64_t* x_host, float* y_host, float* w_host, int32_t* indptr_host, int32_t* rowcnt_host,
+                       int32_t* cols_host, float* vals_host, void* stream);
 /* replaces: loss.backward() (Higashi_wrapper.py:1006) for the batch of the last hsg_score_fwd: ACCUMULATES into grads */
 int  hsg_score_bwd(hsg_ctx* ctx, void* stream);
 
