@@ -301,11 +301,17 @@ def run_train(args):
     max_bin = int(max(ds.bins))
     sizes = []
 
-    def step(i):
+    def begin(i):
         x, chrom, pw = pool[i % len(pool)]
-        B, nnz = eng.sample_batch(x, chrom, neg, 0.5, max_bin, pos_w=pw, training=True, classification=True, seed=1000 * rank + i)
+        eng.sample_batch_begin(x, chrom, neg, 0.5, max_bin, pos_w=pw, training=True, classification=True, seed=1000 * rank + i)
+
+    def step(i):
+        # batch i was started one step ago; batch i+1 is produced (own stream) while the step on batch i runs
+        B, nnz = eng.sample_batch_end()
+        begin(i + 1)
         sizes.append(B)
-        tr.step(None, chrom, None, None, None, stage=2, loss_mode=0, train_mode=True, want_loss=(i % 10 == 0), sampled=(B, nnz))
+        tr.step(None, pool[i % len(pool)][1], None, None, None, stage=2, loss_mode=0, train_mode=True, want_loss=(i % 10 == 0), sampled=(B, nnz))
+    begin(0)
     for i in range(args.warmup):
         step(i)
     torch.cuda.synchronize()

@@ -85,6 +85,7 @@ extern "C" int hsg_destroy(hsg_ctx* c) {
     if (!c) return 0;
     cudaSetDevice(c->device);
     cudaDeviceSynchronize();
+    train_release(c);
     free_derived(c);
     for (int i = 0; i < HSG_W_COUNT; ++i) dev_free(c->w[i]);
     dev_free(c->E_cell); dev_free(c->E_bin); dev_free(c->d_bin_off); dev_free(c->d_bin_chrom);

@@ -18,6 +18,10 @@ struct SamplerWs {
     int* s_col = nullptr; float* s_val = nullptr; float* s_sum = nullptr; int* s_first = nullptr; int64_t cap_cand = 0;
     int* counts = nullptr;          // device: [0] = hyperedges in the batch, [1] = neighbour candidates
     int B = 0; int64_t nnz = 0; bool ready = false;
+    // asynchronous production: begin() runs on `side`, sizes land in pinned memory, end() finishes on the caller's stream
+    cudaStream_t side = nullptr; cudaEvent_t sized = nullptr, consumed = nullptr; int* h_counts = nullptr;
+    bool pending = false, consumed_valid = false;
+    int p_Bp = 0, p_chrom = 0, p_training = 0; unsigned long long p_seed = 0;
 };
 static std::map<hsg_ctx*, SamplerWs*> g_sampler;
 
@@ -246,23 +250,36 @@ static int grow(T** p, size_t n) {
     return 0;
 }
 
-extern "C" int hsg_sample_batch(hsg_ctx* c, const int64_t* pos_host, const float* pos_w_host, int Bp, int chrom, int neg_num,
-                                float pair_ratio, int max_bin, int wide_check, int training, float neg_weight, uint64_t seed,
-                                int* B_out, int64_t* nnz_out, void* stream) {
+// Phase 1 (asynchronous, on the producer's own stream): negatives, labels / weights, candidate counts; the two sizes the host
+// needs (hyperedges in the batch, neighbour candidates) are copied to pinned memory and an event is recorded.
+extern "C" int hsg_sample_batch_begin(hsg_ctx* c, const int64_t* pos_host, const float* pos_w_host, int Bp, int chrom, int neg_num,
+                                      float pair_ratio, int max_bin, int wide_check, int training, float neg_weight, uint64_t seed) {
     HSG_CHECK(c && c->d > 0, "context not initialised");
     HSG_CUDA(cudaSetDevice(c->device));
     HSG_CHECK(c->row_ptr != nullptr, "hsg_sample_batch: contacts not set (hsg_set_contacts)");
-    HSG_CHECK(pos_host && Bp > 0 && chrom >= 0 && chrom < c->n_chrom && neg_num >= 0 && B_out && nnz_out, "bad arguments");
+    HSG_CHECK(pos_host && Bp > 0 && chrom >= 0 && chrom < c->n_chrom && neg_num >= 0, "bad arguments");
     HSG_CHECK(!c->weighted || c->nbr != nullptr, "neighbour graph flagged but missing");
-    cudaStream_t s = (cudaStream_t)stream;
     SamplerWs*& sw = g_sampler[c];
-    if (!sw) { sw = new SamplerWs(); HSG_CUDA(cudaMalloc((void**)&sw->counts, 2 * sizeof(int))); }
+    if (!sw) {
+        sw = new SamplerWs();
+        HSG_CUDA(cudaMalloc((void**)&sw->counts, 2 * sizeof(int)));
+        HSG_CUDA(cudaStreamCreateWithFlags(&sw->side, cudaStreamNonBlocking));
+        HSG_CUDA(cudaEventCreateWithFlags(&sw->sized, cudaEventDisableTiming));
+        HSG_CUDA(cudaEventCreateWithFlags(&sw->consumed, cudaEventDisableTiming));
+        HSG_CUDA(cudaHostAlloc((void**)&sw->h_counts, 2 * sizeof(int), cudaHostAllocDefault));
+    }
+    HSG_CHECK(!sw->pending, "hsg_sample_batch_begin: the previous batch has not been finished (hsg_sample_batch_end)");
+    cudaStream_t s = sw->side;
+    // the scratch of the previous batch may still be read by work queued on the consumer's stream
+    if (sw->consumed_valid) HSG_CUDA(cudaStreamWaitEvent(s, sw->consumed, 0));
     const int n = c->bins[chrom], bin_base = c->n_cells + 1 + c->bin_off[chrom], n_neg = Bp * neg_num, Bmax = Bp + n_neg;
     for (int i = 0; i < Bp; ++i) {
         HSG_CHECK(pos_host[i * 3] >= 1 && pos_host[i * 3] <= c->n_cells, "positive: cell id out of range");
         HSG_CHECK(pos_host[i * 3 + 1] >= bin_base && pos_host[i * 3 + 2] < bin_base + n && pos_host[i * 3 + 1] <= pos_host[i * 3 + 2],
                   "positive: bins must be sorted ids of the batch chromosome");
     }
+    const bool regrow = sw->cap_pos < Bp || sw->cap_neg < n_neg || sw->cap_all < Bmax || sw->cap_rows < 2 * Bmax;
+    if (regrow) HSG_CUDA(cudaDeviceSynchronize());          // buffers are about to be replaced
     if (sw->cap_pos < Bp) { if (grow(&sw->pos, (size_t)Bp * 3) || grow(&sw->pos_w, (size_t)Bp)) return 1; sw->cap_pos = Bp; }
     if (sw->cap_neg < n_neg) {
         if (grow(&sw->neg, (size_t)n_neg * 3) || grow(&sw->flag, (size_t)n_neg) || grow(&sw->scan, (size_t)n_neg)) return 1;
@@ -276,6 +293,7 @@ extern "C" int hsg_sample_batch(hsg_ctx* c, const int64_t* pos_host, const float
         if (grow(&sw->cand_cnt, (size_t)2 * Bmax) || grow(&sw->cand_off, (size_t)2 * Bmax)) return 1;
         sw->cap_rows = 2 * Bmax;
     }
+    // pageable sources: the copies return once the data is staged, the caller may reuse its arrays
     HSG_CUDA(cudaMemcpyAsync(sw->pos, pos_host, (size_t)Bp * 3 * sizeof(int64_t), cudaMemcpyHostToDevice, s));
     if (pos_w_host) HSG_CUDA(cudaMemcpyAsync(sw->pos_w, pos_w_host, (size_t)Bp * sizeof(float), cudaMemcpyHostToDevice, s));
     if (n_neg > 0) {
@@ -284,7 +302,8 @@ extern "C" int hsg_sample_batch(hsg_ctx* c, const int64_t* pos_host, const float
         TR_CHECK_LAUNCH(c);
         block_scan_kernel<<<1, 1024, 0, s>>>(sw->flag, n_neg, sw->scan, sw->counts, Bp); TR_CHECK_LAUNCH(c);
     } else {
-        HSG_CUDA(cudaMemcpyAsync(sw->counts, &Bp, sizeof(int), cudaMemcpyHostToDevice, s));
+        sw->h_counts[0] = Bp;
+        HSG_CUDA(cudaMemcpyAsync(sw->counts, sw->h_counts, sizeof(int), cudaMemcpyHostToDevice, s));
     }
     build_batch_kernel<<<nblk(Bmax), 256, 0, s>>>(sw->pos, pos_w_host ? sw->pos_w : nullptr, Bp, sw->neg, sw->flag, sw->scan, n_neg,
                                                   neg_weight, sw->x_all, sw->y_all, sw->w_all);
@@ -293,29 +312,63 @@ extern "C" int hsg_sample_batch(hsg_ctx* c, const int64_t* pos_host, const float
                                                      c->n_bins, c->bin_off[chrom], bin_base, sw->cand_cnt);
     TR_CHECK_LAUNCH(c);
     block_scan_kernel<<<1, 1024, 0, s>>>(sw->cand_cnt, 2 * Bmax, sw->cand_off, sw->counts + 1, 0); TR_CHECK_LAUNCH(c);
-    int h_counts[2] = {0, 0};
-    HSG_CUDA(cudaMemcpyAsync(h_counts, sw->counts, 2 * sizeof(int), cudaMemcpyDeviceToHost, s));
-    HSG_CUDA(cudaStreamSynchronize(s));                 // the one host round trip of the producer: sizes of the batch
-    const int B = h_counts[0];
-    const int64_t n_cand = h_counts[1];
+    HSG_CUDA(cudaMemcpyAsync(sw->h_counts, sw->counts, 2 * sizeof(int), cudaMemcpyDeviceToHost, s));
+    HSG_CUDA(cudaEventRecord(sw->sized, s));
+    sw->pending = true; sw->ready = false;
+    sw->p_Bp = Bp; sw->p_chrom = chrom; sw->p_training = training; sw->p_seed = seed;
+    return 0;
+}
+
+// Phase 2 (on the consumer's stream): waits for the sizes (normally long since there), sizes the training workspace, moves the
+// batch in and builds the neighbour CSR.  Nothing here waits for work queued on `stream` itself.
+extern "C" int hsg_sample_batch_end(hsg_ctx* c, int* B_out, int64_t* nnz_out, void* stream) {
+    HSG_CHECK(c && B_out && nnz_out, "bad arguments");
+    HSG_CUDA(cudaSetDevice(c->device));
+    auto it = g_sampler.find(c);
+    HSG_CHECK(it != g_sampler.end() && it->second->pending, "hsg_sample_batch_end without hsg_sample_batch_begin");
+    SamplerWs* sw = it->second;
+    cudaStream_t s = (cudaStream_t)stream;
+    HSG_CUDA(cudaEventSynchronize(sw->sized));
+    sw->pending = false;
+    const int B = sw->h_counts[0];
+    const int64_t n_cand = sw->h_counts[1];
+    const int chrom = sw->p_chrom, bin_base = c->n_cells + 1 + c->bin_off[chrom];
     if (sw->cap_cand < n_cand) {
+        HSG_CUDA(cudaDeviceSynchronize());
         if (grow(&sw->s_col, (size_t)n_cand) || grow(&sw->s_val, (size_t)n_cand) || grow(&sw->s_sum, (size_t)n_cand) ||
             grow(&sw->s_first, (size_t)n_cand)) return 1;
         sw->cap_cand = n_cand;
     }
-    if (ws_alloc(c, B, (int)n_cand)) return 1;
+    {
+        auto wit = g_ws.find(c);
+        const bool realloc_ws = wit == g_ws.end() || !wit->second || wit->second->maxB < B || wit->second->max_nnz < (int)n_cand;
+        if (realloc_ws) HSG_CUDA(cudaDeviceSynchronize());   // the workspace is about to be replaced: let queued steps finish
+        // grow with head-room so that the next slightly larger batch does not reallocate again
+        if (realloc_ws && ws_alloc(c, B + B / 8, (int)(n_cand + n_cand / 4))) return 1;
+    }
     TrainWs* w = g_ws[c];
+    HSG_CUDA(cudaStreamWaitEvent(s, sw->sized, 0));
     HSG_CUDA(cudaMemcpyAsync(w->x, sw->x_all, (size_t)B * 3 * sizeof(int64_t), cudaMemcpyDeviceToDevice, s));
     HSG_CUDA(cudaMemcpyAsync(w->y, sw->y_all, (size_t)B * sizeof(float), cudaMemcpyDeviceToDevice, s));
     HSG_CUDA(cudaMemcpyAsync(w->w, sw->w_all, (size_t)B * sizeof(float), cudaMemcpyDeviceToDevice, s));
     neigh_rows_kernel<<<(2 * B + 7) / 8, 256, 0, s>>>(w->x, B, c->row_ptr, c->col, c->val, c->nbr, c->nbr_w, c->k1, c->weighted ? 1 : 0,
-                                                      c->n_bins, c->bin_off[chrom], bin_base, training ? 1 : 0, seed, sw->cand_off, sw->s_col,
-                                                      sw->s_val, sw->s_sum, sw->s_first, w->indptr, w->rowcnt, w->cols, w->vals);
+                                                      c->n_bins, c->bin_off[chrom], bin_base, sw->p_training ? 1 : 0, sw->p_seed, sw->cand_off,
+                                                      sw->s_col, sw->s_val, sw->s_sum, sw->s_first, w->indptr, w->rowcnt, w->cols, w->vals);
     TR_CHECK_LAUNCH(c);
+    HSG_CUDA(cudaEventRecord(sw->consumed, s));
+    sw->consumed_valid = true;
     sw->B = B; sw->nnz = n_cand; sw->ready = true;
     w->sampled = true; w->chrom = chrom;
     *B_out = B; *nnz_out = n_cand;
     return 0;
+}
+
+extern "C" int hsg_sample_batch(hsg_ctx* c, const int64_t* pos_host, const float* pos_w_host, int Bp, int chrom, int neg_num,
+                                float pair_ratio, int max_bin, int wide_check, int training, float neg_weight, uint64_t seed,
+                                int* B_out, int64_t* nnz_out, void* stream) {
+    if (hsg_sample_batch_begin(c, pos_host, pos_w_host, Bp, chrom, neg_num, pair_ratio, max_bin, wide_check, training, neg_weight, seed))
+        return 1;
+    return hsg_sample_batch_end(c, B_out, nnz_out, stream);
 }
 
 // debug / test access to the batch the producer left on the device (any pointer may be NULL)

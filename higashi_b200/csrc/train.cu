@@ -727,7 +727,7 @@ static int ws_cell_alloc(hsg_ctx* c, TrainWs* w, int B, int F) {
 static int ws_alloc(hsg_ctx* c, int maxB, int max_nnz) {
     TrainWs*& w = g_ws[c];
     if (w && w->maxB >= maxB && w->max_nnz >= max_nnz) return 0;
-    if (w) { cudaFree(w->buf); cudaFree(w->indptr); cudaFree(w->rowcnt); cudaFree(w->cols); cudaFree(w->vals); cudaFree(w->x); delete w; }
+    if (w) { cudaFree(w->buf); cudaFree(w->indptr); cudaFree(w->rowcnt); cudaFree(w->cols); cudaFree(w->vals); cudaFree(w->x); if (w->Xg) cudaFree(w->Xg); delete w; }
     w = new TrainWs();
     w->maxB = maxB; w->max_nnz = max_nnz;
     int max_nc = 0; for (int v : c->bins) max_nc = std::max(max_nc, v);
@@ -1133,4 +1133,44 @@ extern "C" int hsg_recon_apply(hsg_ctx* c, float scale, void* stream) {
     axpy_scaled_kernel<<<nblk(d), 256, 0, s>>>(b->grads + b->off_pb[0], gb, scale, d); TR_CHECK_LAUNCH(c);
     axpy_scaled_kernel<<<nblk(F), 256, 0, s>>>(b->grads + rs.off_rb, grb, scale, F); TR_CHECK_LAUNCH(c);
     return 0;
+}
+
+// ------------------------------------------------------------------------------------------------ teardown
+// Called by hsg_destroy: all per-context training state is keyed by the context pointer, and a later context may be given the
+// same address -- stale entries would hand it buffers sized for another model.
+void train_release(hsg_ctx* c) {
+    auto w = g_ws.find(c);
+    if (w != g_ws.end()) {
+        if (w->second) {
+            cudaFree(w->second->buf); cudaFree(w->second->indptr); cudaFree(w->second->rowcnt); cudaFree(w->second->cols);
+            cudaFree(w->second->vals); cudaFree(w->second->x);
+            if (w->second->Xg) cudaFree(w->second->Xg);
+            delete w->second;
+        }
+        g_ws.erase(w);
+    }
+    auto b = g_bind.find(c);
+    if (b != g_bind.end()) {
+        if (b->second) { for (float* f : b->second->feat) if (f) cudaFree(f); delete b->second; }
+        g_bind.erase(b);
+    }
+    auto o = g_opts.find(c);
+    if (o != g_opts.end()) { if (o->second.c2w) cudaFree(o->second.c2w); g_opts.erase(o); }
+    auto r = g_recon.find(c);
+    if (r != g_recon.end()) { if (r->second.scratch) cudaFree(r->second.scratch); if (r->second.act) cudaFree(r->second.act); g_recon.erase(r); }
+    auto s = g_sampler.find(c);
+    if (s != g_sampler.end()) {
+        SamplerWs* sw = s->second;
+        if (sw) {
+            cudaFree(sw->pos); cudaFree(sw->pos_w); cudaFree(sw->neg); cudaFree(sw->flag); cudaFree(sw->scan); cudaFree(sw->x_all);
+            cudaFree(sw->y_all); cudaFree(sw->w_all); cudaFree(sw->cand_cnt); cudaFree(sw->cand_off); cudaFree(sw->s_col);
+            cudaFree(sw->s_val); cudaFree(sw->s_sum); cudaFree(sw->s_first); cudaFree(sw->counts);
+            if (sw->h_counts) cudaFreeHost(sw->h_counts);
+            if (sw->sized) cudaEventDestroy(sw->sized);
+            if (sw->consumed) cudaEventDestroy(sw->consumed);
+            if (sw->side) cudaStreamDestroy(sw->side);
+            delete sw;
+        }
+        g_sampler.erase(s);
+    }
 }

@@ -150,6 +150,23 @@ class TrainEngine:
             C.c_float(1.0 if classification else 0.0), C.c_uint64(int(seed) & (2 ** 64 - 1)), C.byref(B), C.byref(nnz), C.c_void_p(stream)))
         return int(B.value), int(nnz.value)
 
+    def sample_batch_begin(self, pos, chrom: int, neg_num: int, pair_ratio: float, max_bin: int, pos_w=None, training: bool = True,
+                           classification: bool = True, wide_check: bool = True, seed: int = 0):
+        """Asynchronous first half of sample_batch (own stream): call it for batch i+1 before stepping on batch i."""
+        pos = np.ascontiguousarray(_np(pos), dtype=np.int64)
+        pw = None if pos_w is None else np.ascontiguousarray(_np(pos_w), dtype=np.float32).reshape(-1)
+        self.ctx._check(self.ctx.lib.hsg_sample_batch_begin(
+            self.ctx.h, pos.ctypes.data_as(C.POINTER(C.c_int64)), None if pw is None else pw.ctypes.data_as(C.POINTER(C.c_float)),
+            pos.shape[0], int(chrom), int(neg_num), C.c_float(pair_ratio), int(max_bin), 1 if wide_check else 0, 1 if training else 0,
+            C.c_float(1.0 if classification else 0.0), C.c_uint64(int(seed) & (2 ** 64 - 1))))
+
+    def sample_batch_end(self):
+        """Second half: returns (B, nnz); the batch is then in the training workspace."""
+        B, nnz = C.c_int32(0), C.c_int64(0)
+        stream = torch.cuda.current_stream(self.device).cuda_stream
+        self.ctx._check(self.ctx.lib.hsg_sample_batch_end(self.ctx.h, C.byref(B), C.byref(nnz), C.c_void_p(stream)))
+        return int(B.value), int(nnz.value)
+
     def fetch_sampled(self, B: int, nnz: int):
         """(x, y, w, indptr, rowcnt, cols, vals) of the batch the producer left on the device (tests / debugging)."""
         x = np.empty((B, 3), np.int64); y = np.empty(B, np.float32); w = np.empty(B, np.float32)

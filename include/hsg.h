@@ -178,6 +178,12 @@ int  hsg_score_heads(hsg_ctx* ctx, float* mean_host, float* var_host, float* pro
 int  hsg_sample_batch(hsg_ctx* ctx, const int64_t* pos_host, const float* pos_w_host, int Bp, int chrom, int neg_num,
                       float pair_ratio, int max_bin, int wide_check, int training, float neg_weight, uint64_t seed,
                       int* B_out, int64_t* nnz_out, void* stream);
+/* the same in two phases, so that producing batch i+1 overlaps the training step on batch i: _begin runs asynchronously on
+ * the producer's own stream (it may be called while a step is in flight), _end finishes on `stream` without waiting for the
+ * work already queued there.  hsg_sample_batch = _begin + _end.                                                         */
+int  hsg_sample_batch_begin(hsg_ctx* ctx, const int64_t* pos_host, const float* pos_w_host, int Bp, int chrom, int neg_num,
+                            float pair_ratio, int max_bin, int wide_check, int training, float neg_weight, uint64_t seed);
+int  hsg_sample_batch_end(hsg_ctx* ctx, int* B_out, int64_t* nnz_out, void* stream);
 /* copies the produced batch to the host (tests / debugging); row r of the neighbour CSR = [indptr[r], indptr[r] + rowcnt[r]);
  * any pointer may be NULL                                                                                               */
 int  hsg_sampled_fetch(hsg_ctx* ctx, int64_t* x_host, float* y_host, float* w_host, int32_t* indptr_host, int32_t* rowcnt_host,
