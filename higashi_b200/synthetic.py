@@ -113,6 +113,43 @@ class PackedCSR:
         val = np.concatenate(vals) if vals else np.zeros(0, np.float32)
         return PackedCSR(n_cells, bins, bin_off, row_ptr, col, val)
 
+    # ---- stable binary layout: replaces unpickling sparse_nondiag_adj_nbr_1.npy on every launch -------------
+    # header: magic "HSGCSR01", int64 n_cells, C, n_rows, nnz ; then bins int32[C] (padded to 8 bytes), row_ptr int64[n_rows+1],
+    # col int32[nnz] (padded to 8 bytes), val float32[nnz].  All little-endian, every array 8-byte aligned, so the file can be
+    # np.memmap'ed and handed to hsg_set_contacts without a copy on the host.
+    MAGIC = b"HSGCSR01"
+
+    def save_blob(self, path: str):
+        n_rows, nnz, C = len(self.row_ptr) - 1, len(self.col), len(self.bins)
+        pad = lambda n_bytes: (-n_bytes) % 8
+        with open(path, "wb") as f:
+            f.write(self.MAGIC)
+            f.write(np.array([self.n_cells, C, n_rows, nnz], dtype="<i8").tobytes())
+            f.write(np.ascontiguousarray(self.bins, dtype="<i4").tobytes()); f.write(b"\0" * pad(4 * C))
+            f.write(np.ascontiguousarray(self.row_ptr, dtype="<i8").tobytes())
+            f.write(np.ascontiguousarray(self.col, dtype="<i4").tobytes()); f.write(b"\0" * pad(4 * nnz))
+            f.write(np.ascontiguousarray(self.val, dtype="<f4").tobytes())
+
+    @staticmethod
+    def load_blob(path: str, mmap: bool = True) -> "PackedCSR":
+        with open(path, "rb") as f:
+            head = f.read(8 + 32)
+        if head[:8] != PackedCSR.MAGIC:
+            raise ValueError("%s is not a packed contact blob (bad magic)" % path)
+        n_cells, C, n_rows, nnz = (int(v) for v in np.frombuffer(head[8:], dtype="<i8"))
+        pad = lambda n_bytes: (-n_bytes) % 8
+        off = 40
+        take = (lambda dt, n, o: np.memmap(path, dtype=dt, mode="r", offset=o, shape=(n,))) if mmap else \
+            (lambda dt, n, o: np.fromfile(path, dtype=dt, count=n, offset=o))
+        bins = np.array(take("<i4", C, off)); off += 4 * C + pad(4 * C)
+        row_ptr = take("<i8", n_rows + 1, off); off += 8 * (n_rows + 1)
+        col = take("<i4", nnz, off) if nnz else np.zeros(0, np.int32); off += 4 * nnz + pad(4 * nnz)
+        val = take("<f4", nnz, off) if nnz else np.zeros(0, np.float32)
+        if int(bins.sum()) * n_cells != n_rows or int(row_ptr[0]) != 0 or int(row_ptr[-1]) != nnz:
+            raise ValueError("%s: inconsistent header / row_ptr" % path)
+        bin_off = np.concatenate([[0], np.cumsum(bins)]).astype(np.int64)
+        return PackedCSR(n_cells, bins.astype(np.int32), bin_off, row_ptr, col, val)
+
 
 @dataclass
 class SynthDataset:

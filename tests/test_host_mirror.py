@@ -162,3 +162,25 @@ def test_predict_api_like_reference():
         out = model.predict(x, np.zeros(len(x), dtype=int), verbose=False, batch_size=int(1e5), activation=torch.sigmoid)
         assert out.shape == (len(x), 1) and out.dtype == np.float32
         np.testing.assert_allclose(out.reshape(-1), g["impute/sigmoid"][n], atol=1e-5, rtol=0)
+
+
+def test_packed_contact_blob_round_trip(tmp_path):
+    """Stable binary layout of the packed contact CSR (8f rank 3): save -> memmap load -> identical arrays, and the object-array
+    route of the reference (sparse_nondiag_adj_nbr_1.npy) packs to the same blob."""
+    from higashi_b200 import synthetic as S
+    ds = S.make_dataset("C1", n_cells=7, bins=[31, 12], seed=2)
+    path = str(tmp_path / "contacts.hsgcsr")
+    ds.csr.save_blob(path)
+    for mm in (True, False):
+        got = S.PackedCSR.load_blob(path, mmap=mm)
+        assert got.n_cells == ds.csr.n_cells and np.array_equal(got.bins, ds.csr.bins) and np.array_equal(got.bin_off, ds.csr.bin_off)
+        assert np.array_equal(got.row_ptr, ds.csr.row_ptr) and np.array_equal(got.col, ds.csr.col) and np.array_equal(got.val, ds.csr.val)
+    again = S.PackedCSR.from_object_array(ds.csr.to_object_array())
+    path2 = str(tmp_path / "contacts2.hsgcsr")
+    again.save_blob(path2)
+    assert open(path, "rb").read() == open(path2, "rb").read()
+    with open(path, "r+b") as f:
+        f.write(b"XXXX")
+    import pytest
+    with pytest.raises(ValueError):
+        S.PackedCSR.load_blob(path)
