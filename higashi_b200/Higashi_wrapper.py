@@ -201,8 +201,8 @@ class Higashi:
             train_weight, test_weight = [w + 1 for w in train_weight], [w + 1 for w in test_weight]
         embeddings, attr, targets = self.generate_attributes(nf)
         self.feats = embeddings
-        sparse = np.load(os.path.join(self.temp_dir, "sparse_nondiag_adj_nbr_1.npy"), allow_pickle=True)
-        self.csr = PackedCSR.from_object_array(sparse)
+        # packed binary blob next to the pickled object array: unpickling thousands of scipy matrices happens once, not per launch
+        self.csr = PackedCSR.from_npy_cached(os.path.join(self.temp_dir, "sparse_nondiag_adj_nbr_1.npy"))
         self.node_embedding_init = M.MultipleEmbedding(embeddings, self.dimensions, False, self.num_list, targets)
         self.higashi_model = M.Hyper_SAGNN(n_head=8, d_model=self.dimensions, d_k=16, d_v=16, diag_mask=True,
                                            bottle_neck=self.dimensions, attribute_dict=attr, cell_feats=self.cell_feats,

@@ -54,8 +54,7 @@ def impute_process(config_path, model, name, mode, cell_start, cell_end, sparse_
 
     num = S.read_num(temp_dir)
     n_cells = int(num[0])
-    sparse_chrom_list = np.load(sparse_path, allow_pickle=True)
-    csr = PackedCSR.from_object_array(sparse_chrom_list)
+    csr = PackedCSR.from_npy_cached(sparse_path)            # packed blob cache next to the pickled object array
     nbr = nbr_w = None
     if weighted_info is not None:
         nbr, nbr_w = _neighbor_arrays(np.load(weighted_info, allow_pickle=True), n_cells)

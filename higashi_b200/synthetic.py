@@ -131,6 +131,24 @@ class PackedCSR:
             f.write(np.ascontiguousarray(self.val, dtype="<f4").tobytes())
 
     @staticmethod
+    def from_npy_cached(npy_path: str) -> "PackedCSR":
+        """Loads `<npy_path>.hsgcsr` if it is at least as new as the pickled object array, else packs the array once and writes
+        the blob next to it (falls back silently to no caching on a read-only directory)."""
+        import os
+        blob = npy_path + ".hsgcsr"
+        try:
+            if os.path.exists(blob) and os.path.getmtime(blob) >= os.path.getmtime(npy_path):
+                return PackedCSR.load_blob(blob)
+        except (OSError, ValueError):
+            pass
+        csr = PackedCSR.from_object_array(np.load(npy_path, allow_pickle=True))
+        try:
+            csr.save_blob(blob)
+        except OSError:
+            pass
+        return csr
+
+    @staticmethod
     def load_blob(path: str, mmap: bool = True) -> "PackedCSR":
         with open(path, "rb") as f:
             head = f.read(8 + 32)
