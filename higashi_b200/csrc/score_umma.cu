@@ -45,8 +45,8 @@ __global__ void __launch_bounds__(UM_THREADS, 1) score_umma_kernel(UmmaParams p)
     __syncthreads();
     tc_fence_after();
     if (tid == 0) {
-        mbar_expect_tx(bar_w, HI ? SM_WIMG_BYTES : SMF_WIMG_BYTES);
-        tma_bulk_g2s(sbase, HI ? p.wimg : p.wimg + SM_WIMG_BYTES, HI ? SM_WIMG_BYTES : SMF_WIMG_BYTES, bar_w);
+        mbar_expect_tx(bar_w, HI ? SMH_WIMG_BYTES : SMF_WIMG_BYTES);
+        tma_bulk_g2s(sbase, p.wimg, HI ? SMH_WIMG_BYTES : SMF_WIMG_BYTES, bar_w);
     }
     const uint32_t tmem_base = *tmem_slot;
     const uint32_t t_lane = ((uint32_t)(warp_in_wg * 32)) << 16;
@@ -136,136 +136,67 @@ __global__ void __launch_bounds__(UM_THREADS, 1) score_umma_kernel(UmmaParams p)
                 else if (t == 1) attention_fast<1, 8>(p.QK16, p.XS, p.binV16, p.cellV16, s_pr_wg, lane, warp_in_wg * 32, a_base, tokbase, cell);
                 else attention_fast<2, 8>(p.QK16, p.XS, p.binV16, p.cellV16, s_pr_wg, lane, warp_in_wg * 32, a_base, tokbase, cell);
             }
-            if constexpr (HI) {
-                if constexpr (HI) {
-                    ISSUE_BEGIN()
-                    mma_group<8, 64>(a_base, sbase + SM_B_FC1, 64, t_y, 0u);
-                    mma_group<8, 64>(a_base, sbase + SM_B_FC1_LO, 64, t_y, 1u);        // + ctx . (fc1 - fp16(fc1))^T
-                    ISSUE_END()
-                }
-                mbar_wait(bar_mma, phase); phase ^= 1;
-                tc_fence_after();
+            // ------------------------------------------------------------------ MMA 1: [y_c | g] = ctx . [fc1c ; W0' fc1c]^T
+            // ONE N=128 GEMM gives y_c = ctx . fc1c^T (columns 0..63: y with its row mean already removed, because the mean over
+            // the outputs was subtracted from fc1 on the host) and g = ctx . (W0' fc1c)^T (columns 64..127).
+            // LayerNorm(y) . W0'^T = rstd(y_c) * g, so the LN -> fp16 -> shared memory -> MMA round trip of the feed-forward
+            // input disappears: the epilogue only needs the row variance of y_c.  High-accuracy variant: the weight image is
+            // split into fp16 hi + lo parts, the lo part is one more accumulating MMA group.
+            ISSUE_BEGIN()
+            mma_group<8, 128>(a_base, sbase + SMF_B_FC1, 128, t_y, 0u);
+            if constexpr (HI) mma_group<8, 128>(a_base, sbase + SMH_B_FC1_LO, 128, t_y, 1u);
+            ISSUE_END()
+            mbar_wait(bar_mma, phase); phase ^= 1;
+            tc_fence_after();
 
-                // The row-wise epilogues below use the packed fp32x2 instructions of sm_100 (FADD2/FMUL2/FFMA2 via
-                // __fadd2_rn/__fmul2_rn/__ffma2_rn): two columns per issue slot.
-                // ------------------------------------------------------------------ y -> LN_pff(y) (A tile, K = 64)
-                {
-                    uint32_t r0[32], r1[32];
-                    tmem_ld32(t_y + t_lane, r0);
-                    tmem_ld32(t_y + t_lane + 32, r1);
-                    tmem_ld_wait();
-                    float2 x[32];
-    #pragma unroll
-                    for (int i = 0; i < 16; ++i) { x[i] = f2(r0[2 * i], r0[2 * i + 1]); x[16 + i] = f2(r1[2 * i], r1[2 * i + 1]); }
-                    float2 sA = x[0], sB = x[1], sC = x[2], sD = x[3];        // 4 independent chains (ILP)
-    #pragma unroll
-                    for (int i = 4; i < 32; i += 4) {
-                        sA = __fadd2_rn(sA, x[i]); sB = __fadd2_rn(sB, x[i + 1]); sC = __fadd2_rn(sC, x[i + 2]); sD = __fadd2_rn(sD, x[i + 3]);
-                    }
-                    sA = __fadd2_rn(__fadd2_rn(sA, sB), __fadd2_rn(sC, sD));
-                    const float mean = (sA.x + sA.y) * (1.0f / 64.0f);
-                    const float2 nm = make_float2(-mean, -mean);
-                    float2 vA = make_float2(0.f, 0.f), vB = vA, vC = vA, vD = vA;
-    #pragma unroll
-                    for (int i = 0; i < 32; i += 4) {
-                        x[i] = __fadd2_rn(x[i], nm); x[i + 1] = __fadd2_rn(x[i + 1], nm);
-                        x[i + 2] = __fadd2_rn(x[i + 2], nm); x[i + 3] = __fadd2_rn(x[i + 3], nm);
-                        vA = __ffma2_rn(x[i], x[i], vA); vB = __ffma2_rn(x[i + 1], x[i + 1], vB);
-                        vC = __ffma2_rn(x[i + 2], x[i + 2], vC); vD = __ffma2_rn(x[i + 3], x[i + 3], vD);
-                    }
-                    vA = __fadd2_rn(__fadd2_rn(vA, vB), __fadd2_rn(vC, vD));
-                    const float rstd = rsqrtf((vA.x + vA.y) * (1.0f / 64.0f) + HSG_LN_EPS);
-                    const float2 rs = make_float2(rstd, rstd);
-    #pragma unroll
-                    for (int c = 0; c < 8; ++c) {
-                        float2 a0 = __fmul2_rn(x[c * 4 + 0], rs), a1 = __fmul2_rn(x[c * 4 + 1], rs);
-                        float2 a2 = __fmul2_rn(x[c * 4 + 2], rs), a3 = __fmul2_rn(x[c * 4 + 3], rs);
-                        sts128(a_chunk_addr(a_base, wtid, c), pack_h2(a0.x, a0.y), pack_h2(a1.x, a1.y), pack_h2(a2.x, a2.y), pack_h2(a3.x, a3.y));
-                    }
-                }
-                issue_gemm<4, 64>(wg, wtid, a_base, sbase + SM_B_W0, 64, t_h, 0u, bar_mma);
-                mbar_wait(bar_mma, phase); phase ^= 1;
-                tc_fence_after();
-
-                // ------------------------------------------------------------------ h = swish(. + b0') (A tile, K = 64)
-    #pragma unroll
-                for (int half = 0; half < 2; ++half) {
-                    uint32_t r[32];
-                    tmem_ld32(t_h + t_lane + half * 32, r);
-                    tmem_ld_wait();
-    #pragma unroll
-                    for (int c = 0; c < 4; ++c) {
-                        const float* bq = cst + CST_B0F + half * 32 + c * 8;
-                        uint32_t pk[4];
-    #pragma unroll
-                        for (int q = 0; q < 4; ++q) {
-                            float2 w = __fadd2_rn(f2(r[c * 8 + 2 * q], r[c * 8 + 2 * q + 1]), make_float2(bq[2 * q], bq[2 * q + 1]));
-                            float2 th = make_float2(fast_tanh(w.x), fast_tanh(w.y));
-                            float2 hh = __ffma2_rn(w, th, w);
-                            pk[q] = pack_h2(hh.x, hh.y);
-                        }
-                        sts128(a_chunk_addr(a_base, wtid, half * 4 + c), pk[0], pk[1], pk[2], pk[3]);
-                    }
-                }
-            } else {
-                // ONE N=128 GEMM gives y_c = ctx . fc1c^T (columns 0..63: y with its row mean already removed, because the
-                // mean over the outputs was subtracted from fc1 on the host) and g = ctx . (W0' fc1c)^T (columns 64..127).
-                // LayerNorm(y) . W0'^T = rstd(y_c) * g, so the LN -> fp16 -> shared memory -> MMA round trip of the
-                // feed-forward input disappears: the epilogue only needs the row variance of y_c.
-                issue_gemm<8, 128>(wg, wtid, a_base, sbase + SMF_B_FC1, 128, t_y, 0u, bar_mma);
-                mbar_wait(bar_mma, phase); phase ^= 1;
-                tc_fence_after();
-                float2 rs;
-                {
-                    uint32_t r0[32], r1[32];
-                    tmem_ld32(t_y + t_lane, r0);
-                    tmem_ld32(t_y + t_lane + 32, r1);
-                    tmem_ld_wait();
-                    float2 vA = make_float2(0.f, 0.f), vB = vA, vC = vA, vD = vA;
+            // The row-wise epilogues use the packed fp32x2 instructions of sm_100 (FADD2/FMUL2/FFMA2): two columns per issue slot.
+            float2 rs;
+            {
+                uint32_t r0[32], r1[32];
+                tmem_ld32(t_y + t_lane, r0);
+                tmem_ld32(t_y + t_lane + 32, r1);
+                tmem_ld_wait();
+                float2 vA = make_float2(0.f, 0.f), vB = vA, vC = vA, vD = vA;
 #pragma unroll
-                    for (int i = 0; i < 16; i += 2) {
-                        float2 a = f2(r0[2 * i], r0[2 * i + 1]), b = f2(r0[2 * i + 2], r0[2 * i + 3]);
-                        float2 c2 = f2(r1[2 * i], r1[2 * i + 1]), d2 = f2(r1[2 * i + 2], r1[2 * i + 3]);
-                        vA = __ffma2_rn(a, a, vA); vB = __ffma2_rn(b, b, vB); vC = __ffma2_rn(c2, c2, vC); vD = __ffma2_rn(d2, d2, vD);
-                    }
-                    vA = __fadd2_rn(__fadd2_rn(vA, vB), __fadd2_rn(vC, vD));
-                    const float rstd = rsqrtf((vA.x + vA.y) * (1.0f / 64.0f) + HSG_LN_EPS);
-                    rs = make_float2(rstd, rstd);
+                for (int i = 0; i < 16; i += 2) {
+                    float2 a = f2(r0[2 * i], r0[2 * i + 1]), b = f2(r0[2 * i + 2], r0[2 * i + 3]);
+                    float2 c2 = f2(r1[2 * i], r1[2 * i + 1]), d2 = f2(r1[2 * i + 2], r1[2 * i + 3]);
+                    vA = __ffma2_rn(a, a, vA); vB = __ffma2_rn(b, b, vB); vC = __ffma2_rn(c2, c2, vC); vD = __ffma2_rn(d2, d2, vD);
                 }
-#pragma unroll
-                for (int half = 0; half < 2; ++half) {
-                    uint32_t r[32];
-                    tmem_ld32(t_h + t_lane + half * 32, r);
-                    tmem_ld_wait();
-                    uint32_t hp[16];
-#pragma unroll
-                    for (int c = 0; c < 4; ++c) {
-                        const float* bq = cst + CST_B0F + half * 32 + c * 8;
-#pragma unroll
-                        for (int q = 0; q < 4; ++q) {
-                            float2 w = __ffma2_rn(f2(r[c * 8 + 2 * q], r[c * 8 + 2 * q + 1]), rs, make_float2(bq[2 * q], bq[2 * q + 1]));
-                            float2 th = make_float2(fast_tanh(w.x), fast_tanh(w.y));
-                            float2 hh = __ffma2_rn(w, th, w);
-                            hp[c * 4 + q] = pack_h2(hh.x, hh.y);
-                        }
-                    }
-                    // h goes back to TMEM as the fp16 A operand of the next MMA (two K elements per column): it overwrites the
-                    // g columns this thread has just consumed -- no shared-memory round trip, no proxy fence
-                    tmem_st16(t_h + t_lane + half * 16, hp);
-                }
+                vA = __fadd2_rn(__fadd2_rn(vA, vB), __fadd2_rn(vC, vD));
+                const float rstd = rsqrtf((vA.x + vA.y) * (1.0f / 64.0f) + HSG_LN_EPS);
+                rs = make_float2(rstd, rstd);
             }
-            // z = y + h . W1^T : accumulate onto y (still in TMEM) -- the residual is free
-            if constexpr (HI) {
-                issue_gemm<4, 64>(wg, wtid, a_base, sbase + SM_B_W1, 64, t_y, 1u, bar_mma);
-            } else {
-                ISSUE_BEGIN_TS()
-                mma_group_ts<4, 64>(t_h, sbase + SMF_B_W1, 64, t_y, 1u);
-                ISSUE_END()
+            // ------------------------------------------------------------------ h = swish(rstd * g + b0')  -> TMEM A operand
+#pragma unroll
+            for (int half = 0; half < 2; ++half) {
+                uint32_t r[32];
+                tmem_ld32(t_h + t_lane + half * 32, r);
+                tmem_ld_wait();
+                uint32_t hp[16];
+#pragma unroll
+                for (int c = 0; c < 4; ++c) {
+                    const float* bq = cst + CST_B0F + half * 32 + c * 8;
+#pragma unroll
+                    for (int q = 0; q < 4; ++q) {
+                        float2 w = __ffma2_rn(f2(r[c * 8 + 2 * q], r[c * 8 + 2 * q + 1]), rs, make_float2(bq[2 * q], bq[2 * q + 1]));
+                        float2 th = make_float2(fast_tanh(w.x), fast_tanh(w.y));
+                        float2 hh = __ffma2_rn(w, th, w);
+                        hp[c * 4 + q] = pack_h2(hh.x, hh.y);
+                    }
+                }
+                // h goes back to TMEM as the fp16 A operand of the next MMA (two K elements per column): it overwrites the g
+                // columns this thread has just consumed -- no shared-memory round trip, no proxy fence
+                tmem_st16(t_h + t_lane + half * 16, hp);
             }
+            // ------------------------------------------------------------------ MMA 2: z_c = y_c + h . W1c^T (residual for free)
+            ISSUE_BEGIN_TS()
+            mma_group_ts<4, 64>(t_h, sbase + SMF_B_W1, 64, t_y, 1u);
+            ISSUE_END()
             // S rows of this token (feature blocks of 4): requested BEFORE waiting for the MMA so that their L2 latency hides
             // behind the tensor-core round trip (volatile loads: the compiler must not sink them below the wait)
             float4 sreg[16];
-            if constexpr (!HI) {
+            {
                 const float4* Scol = reinterpret_cast<const float4*>((t == 0) ? p.cellSb : p.binSb) + ((t == 0) ? cell : (t == 1 ? pr.x : pr.y));
                 const long long sstr = (t == 0) ? p.n_cells : p.n_bins;
 #pragma unroll
@@ -274,138 +205,73 @@ __global__ void __launch_bounds__(UM_THREADS, 1) score_umma_kernel(UmmaParams p)
             mbar_wait(bar_mma, phase); phase ^= 1;
             tc_fence_after();
 
-            if constexpr (!HI) {
-                // ---------------------------------------------------------------- u = (LN1(z + b1c) - S)^2 (A tile, K = 64)
-                // z arrives centred (y_c + h . W1c^T + b1c has zero row mean by construction).  Two passes over TMEM keep the
-                // register footprint at 32 columns + the 64 prefetched S values: pass 1 = row variance, pass 2 = u.
-                float2 rs;
-                {
-                    float2 vA = make_float2(0.f, 0.f), vB = vA, vC = vA, vD = vA;
+            // ------------------------------------------------------------------ u = (LN1(z + b1c) - S)^2  -> TMEM A operand
+            // z arrives centred (y_c + h . W1c^T + b1c has zero row mean by construction).  Two passes over TMEM keep the register
+            // footprint at 16 columns + the 64 prefetched S values: pass 1 = row variance, pass 2 = u.
+            {
+                float2 vA = make_float2(0.f, 0.f), vB = vA, vC = vA, vD = vA;
 #pragma unroll
-                    for (int half = 0; half < 2; ++half) {
-                        uint32_t r[32];
-                        tmem_ld32(t_y + t_lane + half * 32, r);
-                        tmem_ld_wait();
-#pragma unroll
-                        for (int i = 0; i < 16; i += 4) {
-                            const float* bq = cst + CST_B1C + half * 32 + 2 * i;
-                            float2 a = __fadd2_rn(f2(r[2 * i], r[2 * i + 1]), make_float2(bq[0], bq[1]));
-                            float2 b = __fadd2_rn(f2(r[2 * i + 2], r[2 * i + 3]), make_float2(bq[2], bq[3]));
-                            float2 c2 = __fadd2_rn(f2(r[2 * i + 4], r[2 * i + 5]), make_float2(bq[4], bq[5]));
-                            float2 d2 = __fadd2_rn(f2(r[2 * i + 6], r[2 * i + 7]), make_float2(bq[6], bq[7]));
-                            vA = __ffma2_rn(a, a, vA); vB = __ffma2_rn(b, b, vB); vC = __ffma2_rn(c2, c2, vC); vD = __ffma2_rn(d2, d2, vD);
-                        }
-                    }
-                    vA = __fadd2_rn(__fadd2_rn(vA, vB), __fadd2_rn(vC, vD));
-                    const float rstd = rsqrtf((vA.x + vA.y) * (1.0f / 64.0f) + HSG_LN_EPS);
-                    rs = make_float2(rstd, rstd);
-                }
-#pragma unroll
-                for (int qt = 0; qt < 4; ++qt) {                 // 16 columns at a time: 16 + 8 live registers next to the 64 S values
-                    uint32_t r[16], up[8];
-                    tmem_ld16(t_y + t_lane + qt * 16, r);
+                for (int half = 0; half < 2; ++half) {
+                    uint32_t r[32];
+                    tmem_ld32(t_y + t_lane + half * 32, r);
                     tmem_ld_wait();
 #pragma unroll
-                    for (int c = 0; c < 2; ++c) {
-                        const float* bq = cst + CST_B1C + qt * 16 + c * 8;
-                        const float* gq = cst + CST_G1 + qt * 16 + c * 8;
-                        const float4 s0 = sreg[qt * 4 + 2 * c], s1 = sreg[qt * 4 + 2 * c + 1];
-                        const float svv[8] = {s0.x, s0.y, s0.z, s0.w, s1.x, s1.y, s1.z, s1.w};
-#pragma unroll
-                        for (int q = 0; q < 4; ++q) {
-                            float2 x = __fadd2_rn(f2(r[c * 8 + 2 * q], r[c * 8 + 2 * q + 1]), make_float2(bq[2 * q], bq[2 * q + 1]));
-                            float2 tz = __fmul2_rn(x, rs);
-                            float2 u = __ffma2_rn(tz, make_float2(gq[2 * q], gq[2 * q + 1]), make_float2(svv[2 * q], svv[2 * q + 1]));
-                            u = __fmul2_rn(u, u);
-                            up[c * 4 + q] = pack_h2(u.x, u.y);
-                        }
-                    }
-                    tmem_st8(t_h + t_lane + qt * 8, up);         // u as the fp16 A operand of the classifier GEMM (h is consumed)
-                }
-            } else {
-                // ------------------------------------------------------------------ u = (LN1(z + b1) - S)^2 (A tile, K = 64)
-                {
-                    uint32_t r0[32], r1[32];
-                    tmem_ld32(t_y + t_lane, r0);
-                    tmem_ld32(t_y + t_lane + 32, r1);
-                    tmem_ld_wait();
-                    float2 x[32];
-                    float2 sA = make_float2(0.f, 0.f), sB = sA;
-    #pragma unroll
-                    for (int i = 0; i < 16; i += 2) {
-                        const float* bq = cst + (HI ? CST_B1 : CST_B1C) + 2 * i;
-                        x[i] = __fadd2_rn(f2(r0[2 * i], r0[2 * i + 1]), make_float2(bq[0], bq[1]));
-                        x[i + 1] = __fadd2_rn(f2(r0[2 * i + 2], r0[2 * i + 3]), make_float2(bq[2], bq[3]));
-                        x[16 + i] = __fadd2_rn(f2(r1[2 * i], r1[2 * i + 1]), make_float2(bq[32], bq[33]));
-                        x[17 + i] = __fadd2_rn(f2(r1[2 * i + 2], r1[2 * i + 3]), make_float2(bq[34], bq[35]));
-                        if constexpr (HI) {
-                            sA = __fadd2_rn(sA, __fadd2_rn(x[i], x[16 + i]));
-                            sB = __fadd2_rn(sB, __fadd2_rn(x[i + 1], x[17 + i]));
-                        }
-                    }
-                    float2 vA = make_float2(0.f, 0.f), vB = vA, vC = vA, vD = vA;
-                    if constexpr (HI) {
-                        const float mean = ((sA.x + sA.y) + (sB.x + sB.y)) * (1.0f / 64.0f);
-                        const float2 nm = make_float2(-mean, -mean);
-    #pragma unroll
-                        for (int i = 0; i < 32; ++i) x[i] = __fadd2_rn(x[i], nm);
-                    }
-                    // fast variant: z arrives centred (y_c + h . W1c^T + b1c has zero row mean by construction)
-    #pragma unroll
-                    for (int i = 0; i < 32; i += 4) {
-                        vA = __ffma2_rn(x[i], x[i], vA); vB = __ffma2_rn(x[i + 1], x[i + 1], vB);
-                        vC = __ffma2_rn(x[i + 2], x[i + 2], vC); vD = __ffma2_rn(x[i + 3], x[i + 3], vD);
-                    }
-                    vA = __fadd2_rn(__fadd2_rn(vA, vB), __fadd2_rn(vC, vD));
-                    const float rstd = rsqrtf((vA.x + vA.y) * (1.0f / 64.0f) + HSG_LN_EPS);
-                    const float2 rs = make_float2(rstd, rstd);
-                    // S tables are stored in feature blocks ([16][n_tokens][4]) so that consecutive rows (consecutive bins) read
-                    // consecutive 16-byte quads: 16 coalesced 128-bit loads per row instead of 16 row-scattered ones
-                    const float4* Scol = reinterpret_cast<const float4*>((t == 0) ? p.cellSb : p.binSb) + ((t == 0) ? cell : (t == 1 ? pr.x : pr.y));
-                    const long long sstr = (t == 0) ? p.n_cells : p.n_bins;
-    #pragma unroll
-                    for (int c = 0; c < 8; ++c) {
-                        const float* gq = cst + CST_G1 + c * 8;
-                        uint32_t pk[4], pl[4];
-                        const float4 s0 = __ldg(Scol + (2 * c) * sstr), s1 = __ldg(Scol + (2 * c + 1) * sstr);
-                        const float svv[8] = {s0.x, s0.y, s0.z, s0.w, s1.x, s1.y, s1.z, s1.w};
-    #pragma unroll
-                        for (int q = 0; q < 4; ++q) {
-                            float2 sv = make_float2(svv[2 * q], svv[2 * q + 1]);       // the table holds beta - S
-                            float2 tz = __fmul2_rn(x[c * 4 + q], rs);
-                            float2 u = __ffma2_rn(tz, make_float2(gq[2 * q], gq[2 * q + 1]), sv);
-                            u = __fmul2_rn(u, u);
-                            pk[q] = pack_h2(u.x, u.y);
-                            if constexpr (HI) {             // u = hi + lo, both fp16: the classifier GEMM sees ~22 bits of u
-                                float2 hf = __half22float2(u2h(pk[q]));
-                                float2 lo = __fadd2_rn(u, make_float2(-hf.x, -hf.y));
-                                pl[q] = pack_h2(lo.x, lo.y);
-                            }
-                        }
-                        sts128(a_chunk_addr(a_base, wtid, c), pk[0], pk[1], pk[2], pk[3]);
-                        if constexpr (HI) sts128(a_chunk_addr(a_base + 16384u, wtid, c), pl[0], pl[1], pl[2], pl[3]);
+                    for (int i = 0; i < 16; i += 4) {
+                        const float* bq = cst + CST_B1C + half * 32 + 2 * i;
+                        float2 a = __fadd2_rn(f2(r[2 * i], r[2 * i + 1]), make_float2(bq[0], bq[1]));
+                        float2 b = __fadd2_rn(f2(r[2 * i + 2], r[2 * i + 3]), make_float2(bq[2], bq[3]));
+                        float2 c2 = __fadd2_rn(f2(r[2 * i + 4], r[2 * i + 5]), make_float2(bq[4], bq[5]));
+                        float2 d2 = __fadd2_rn(f2(r[2 * i + 6], r[2 * i + 7]), make_float2(bq[6], bq[7]));
+                        vA = __ffma2_rn(a, a, vA); vB = __ffma2_rn(b, b, vB); vC = __ffma2_rn(c2, c2, vC); vD = __ffma2_rn(d2, d2, vD);
                     }
                 }
+                vA = __fadd2_rn(__fadd2_rn(vA, vB), __fadd2_rn(vC, vD));
+                const float rstd = rsqrtf((vA.x + vA.y) * (1.0f / 64.0f) + HSG_LN_EPS);
+                rs = make_float2(rstd, rstd);
             }
+#pragma unroll
+            for (int qt = 0; qt < 4; ++qt) {                 // 16 columns at a time next to the 64 S values
+                uint32_t r[16], up[8], ul[8];
+                tmem_ld16(t_y + t_lane + qt * 16, r);
+                tmem_ld_wait();
+#pragma unroll
+                for (int c = 0; c < 2; ++c) {
+                    const float* bq = cst + CST_B1C + qt * 16 + c * 8;
+                    const float* gq = cst + CST_G1 + qt * 16 + c * 8;
+                    const float4 s0 = sreg[qt * 4 + 2 * c], s1 = sreg[qt * 4 + 2 * c + 1];
+                    const float svv[8] = {s0.x, s0.y, s0.z, s0.w, s1.x, s1.y, s1.z, s1.w};
+#pragma unroll
+                    for (int q = 0; q < 4; ++q) {
+                        float2 x = __fadd2_rn(f2(r[c * 8 + 2 * q], r[c * 8 + 2 * q + 1]), make_float2(bq[2 * q], bq[2 * q + 1]));
+                        float2 tz = __fmul2_rn(x, rs);
+                        float2 u = __ffma2_rn(tz, make_float2(gq[2 * q], gq[2 * q + 1]), make_float2(svv[2 * q], svv[2 * q + 1]));
+                        u = __fmul2_rn(u, u);
+                        up[c * 4 + q] = pack_h2(u.x, u.y);
+                        if constexpr (HI) {             // u = hi + lo, both fp16: the classifier GEMM sees ~22 bits of u
+                            float2 hf = __half22float2(u2h(up[c * 4 + q]));
+                            float2 lo = __fadd2_rn(u, make_float2(-hf.x, -hf.y));
+                            ul[c * 4 + q] = pack_h2(lo.x, lo.y);
+                        }
+                    }
+                }
+                tmem_st8(t_h + t_lane + qt * 8, up);         // u as the fp16 A operand of the classifier GEMM (h is consumed)
+                if constexpr (HI) tmem_st8(t_h + t_lane + 32 + qt * 8, ul);
+            }
+            // ------------------------------------------------------------------ MMA 3: c = u . C0^T  (first 32 columns of the consumed z)
+            ISSUE_BEGIN_TS()
+            mma_group_ts<4, 32>(t_h, sbase + SMF_B_C0, 32, t_y, 0u);                                 // u_hi . C0_hi
             if constexpr (HI) {
-                ISSUE_BEGIN()
-                mma_group<4, 32>(a_base, sbase + SM_B_C0, 32, t_h, 0u);                  // u_hi . C0_hi
-                mma_group<4, 32>(a_base + 16384u, sbase + SM_B_C0, 32, t_h, 1u);         // u_lo . C0_hi
-                mma_group<4, 32>(a_base, sbase + SM_B_C0_LO, 32, t_h, 1u);               // u_hi . C0_lo
-                ISSUE_END()
-            } else {
-                // c = u . C0^T lands on the first 32 columns of the (consumed) z block
-                ISSUE_BEGIN_TS()
-                mma_group_ts<4, 32>(t_h, sbase + SMF_B_C0, 32, t_y, 0u);
-                ISSUE_END()
+                mma_group_ts<4, 32>(t_h + 32, sbase + SMF_B_C0, 32, t_y, 1u);                        // u_lo . C0_hi
+                mma_group_ts<4, 32>(t_h, sbase + SMH_B_C0_LO, 32, t_y, 1u);                          // u_hi . C0_lo
             }
+            ISSUE_END()
             mbar_wait(bar_mma, phase); phase ^= 1;
             tc_fence_after();
 
             // ------------------------------------------------------------------ o_t = c1 . swish(c + cb0) + cb1
             {
                 uint32_t r[32];
-                tmem_ld32((HI ? t_h : t_y) + t_lane, r);
+                tmem_ld32(t_y + t_lane, r);
                 tmem_ld_wait();
                 float2 oA = make_float2(0.f, 0.f), oB = oA;
 #pragma unroll
@@ -459,59 +325,50 @@ int umma_build_weights(const float* fc1, const float* w0, const float* b0, const
         }
         cst_host[CST_B0F + n] = (float)(0.5 * acc);
     }
-    memset(wimg_host, 0, SM_WIMG_BYTES + SMF_WIMG_BYTES);
-    swizzle_image(fc1, d, HSG_HD, reinterpret_cast<__half*>(wimg_host + SM_B_FC1));
-    swizzle_image(w0f.data(), d, d, reinterpret_cast<__half*>(wimg_host + SM_B_W0));
-    swizzle_image(w1, d, d, reinterpret_cast<__half*>(wimg_host + SM_B_W1));
-    std::vector<float> c0h((size_t)(d / 2) * d);
-    for (size_t i = 0; i < c0h.size(); ++i) c0h[i] = 0.5f * c0[i];
-    swizzle_image(c0h.data(), d / 2, d, reinterpret_cast<__half*>(wimg_host + SM_B_C0));
-    // low halves for the high-accuracy variant: w_lo = w - fp16(w)
-    std::vector<float> lo((size_t)d * HSG_HD);
-    for (size_t i = 0; i < lo.size(); ++i) lo[i] = fc1[i] - __half2float(__float2half_rn(fc1[i]));
-    swizzle_image(lo.data(), d, HSG_HD, reinterpret_cast<__half*>(wimg_host + SM_B_FC1_LO));
-    for (size_t i = 0; i < c0h.size(); ++i) lo[i] = c0h[i] - __half2float(__float2half_rn(c0h[i]));
-    swizzle_image(lo.data(), d / 2, d, reinterpret_cast<__half*>(wimg_host + SM_B_C0_LO));
-    for (int i = 0; i < d; ++i) { cst_host[CST_B1 + i] = b1[i]; cst_host[CST_G1 + i] = ln1_g[i]; }
+    memset(wimg_host, 0, SMH_WIMG_BYTES);
+    for (int i = 0; i < d; ++i) cst_host[CST_G1 + i] = ln1_g[i];
     for (int i = 0; i < d / 2; ++i) { cst_host[CST_CB0 + i] = 0.5f * cb0[i]; cst_host[CST_CW1 + i] = cw1[i]; }
     cst_host[CST_CB1] = cb1[0];
-    // ---- fast-variant image (appended): every LayerNorm input is produced centred, and LN_pff . W0' is folded into fc1
-    {
-        unsigned char* img = wimg_host + SM_WIMG_BYTES;
-        std::vector<double> fc1c((size_t)d * HSG_HD);
-        for (int k = 0; k < HSG_HD; ++k) {
-            double m = 0;
-            for (int n = 0; n < d; ++n) m += fc1[(size_t)n * HSG_HD + k];
-            m /= d;
-            for (int n = 0; n < d; ++n) fc1c[(size_t)n * HSG_HD + k] = fc1[(size_t)n * HSG_HD + k] - m;
-        }
-        std::vector<float> comb((size_t)2 * d * HSG_HD);
-        for (int n = 0; n < d; ++n)
-            for (int k = 0; k < HSG_HD; ++k) {
-                comb[(size_t)n * HSG_HD + k] = (float)fc1c[(size_t)n * HSG_HD + k];
-                double acc = 0;
-                for (int j = 0; j < d; ++j) acc += (double)w0f[(size_t)n * d + j] * fc1c[(size_t)j * HSG_HD + k];
-                comb[(size_t)(d + n) * HSG_HD + k] = (float)acc;
-            }
-        swizzle_image(comb.data(), 2 * d, HSG_HD, reinterpret_cast<__half*>(img + SMF_B_FC1));
-        std::vector<float> w1c((size_t)d * d);
-        for (int k = 0; k < d; ++k) {
-            double m = 0;
-            for (int n = 0; n < d; ++n) m += w1[(size_t)n * d + k];
-            m /= d;
-            for (int n = 0; n < d; ++n) w1c[(size_t)n * d + k] = (float)(w1[(size_t)n * d + k] - m);
-        }
-        swizzle_image(w1c.data(), d, d, reinterpret_cast<__half*>(img + SMF_B_W1));
-        swizzle_image(c0h.data(), d / 2, d, reinterpret_cast<__half*>(img + SMF_B_C0));
-        double mb = 0;
-        for (int i = 0; i < d; ++i) mb += b1[i];
-        mb /= d;
-        for (int i = 0; i < d; ++i) cst_host[CST_B1C + i] = (float)(b1[i] - mb);
+    // every LayerNorm input is produced centred, and LN_pff . W0' is folded into fc1
+    std::vector<double> fc1c((size_t)d * HSG_HD);
+    for (int k = 0; k < HSG_HD; ++k) {
+        double m = 0;
+        for (int n = 0; n < d; ++n) m += fc1[(size_t)n * HSG_HD + k];
+        m /= d;
+        for (int n = 0; n < d; ++n) fc1c[(size_t)n * HSG_HD + k] = fc1[(size_t)n * HSG_HD + k] - m;
     }
+    std::vector<float> comb((size_t)2 * d * HSG_HD), lo((size_t)2 * d * HSG_HD);
+    for (int n = 0; n < d; ++n)
+        for (int k = 0; k < HSG_HD; ++k) {
+            comb[(size_t)n * HSG_HD + k] = (float)fc1c[(size_t)n * HSG_HD + k];
+            double acc = 0;
+            for (int j = 0; j < d; ++j) acc += (double)w0f[(size_t)n * d + j] * fc1c[(size_t)j * HSG_HD + k];
+            comb[(size_t)(d + n) * HSG_HD + k] = (float)acc;
+        }
+    swizzle_image(comb.data(), 2 * d, HSG_HD, reinterpret_cast<__half*>(wimg_host + SMF_B_FC1));
+    for (size_t i = 0; i < comb.size(); ++i) lo[i] = comb[i] - __half2float(__float2half_rn(comb[i]));
+    swizzle_image(lo.data(), 2 * d, HSG_HD, reinterpret_cast<__half*>(wimg_host + SMH_B_FC1_LO));
+    std::vector<float> w1c((size_t)d * d);
+    for (int k = 0; k < d; ++k) {
+        double m = 0;
+        for (int n = 0; n < d; ++n) m += w1[(size_t)n * d + k];
+        m /= d;
+        for (int n = 0; n < d; ++n) w1c[(size_t)n * d + k] = (float)(w1[(size_t)n * d + k] - m);
+    }
+    swizzle_image(w1c.data(), d, d, reinterpret_cast<__half*>(wimg_host + SMF_B_W1));
+    std::vector<float> c0h((size_t)(d / 2) * d);
+    for (size_t i = 0; i < c0h.size(); ++i) c0h[i] = 0.5f * c0[i];
+    swizzle_image(c0h.data(), d / 2, d, reinterpret_cast<__half*>(wimg_host + SMF_B_C0));
+    for (size_t i = 0; i < c0h.size(); ++i) lo[i] = c0h[i] - __half2float(__float2half_rn(c0h[i]));
+    swizzle_image(lo.data(), d / 2, d, reinterpret_cast<__half*>(wimg_host + SMH_B_C0_LO));
+    double mb = 0;
+    for (int i = 0; i < d; ++i) mb += b1[i];
+    mb /= d;
+    for (int i = 0; i < d; ++i) cst_host[CST_B1C + i] = (float)(b1[i] - mb);
     return 0;
 }
 
-int umma_wimg_bytes() { return SM_WIMG_BYTES + SMF_WIMG_BYTES; }
+int umma_wimg_bytes() { return SMH_WIMG_BYTES; }
 int umma_cst_count() { return CST_COUNT; }
 
 // fp32 static tables -> 16-bit / offset copies used by the tensor-core kernel

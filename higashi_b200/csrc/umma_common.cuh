@@ -15,29 +15,25 @@
 #define UM_ATT_PREFETCH 0
 #endif
 
-// shared memory map (bytes)
-#define SM_B_FC1 0            // [64 x 128] fp16, 2 K-atoms of 8 KB
-#define SM_B_W0 16384         // [64 x 64]
-#define SM_B_W1 24576         // [64 x 64]
-#define SM_B_C0 32768         // [32 x 64]
-#define SM_B_FC1_LO 36864      // low halves (w - fp16(w)) of fc1 and C0 for the high-accuracy variant
-#define SM_B_C0_LO 53248
-#define SM_WIMG_BYTES 57344
-// fast variant: [y_c | g] = ctx . [fc1c ; W0' fc1c]^T in ONE N=128 GEMM (see score_umma.cu), then W1c and C0
-#define SMF_B_FC1 0           // [128 x 128] fp16, 2 K-atoms of 16 KB: rows 0..63 fc1c, rows 64..127 W0' fc1c
+// shared memory map (bytes).  Weight images (fp16, K-major SWIZZLE_128B, built on the host):
+//   [y_c | g] = ctx . [fc1c ; W0' fc1c]^T in ONE N=128 GEMM (see score_umma.cu), then W1c and C0; the high-accuracy variant
+//   appends the low halves (w - fp16(w)) of the first and the last image.
+#define SMF_B_FC1 0           // [128 x 128], 2 K-atoms of 16 KB: rows 0..63 fc1c, rows 64..127 W0' fc1c
 #define SMF_B_W1 32768        // [64 x 64]  W1 with its output mean removed
-#define SMF_B_C0 40960        // [32 x 64]
+#define SMF_B_C0 40960        // [32 x 64]  C0 / 2
 #define SMF_WIMG_BYTES 45056
-#define SM_A0 57344           // 4 x 32 KB A buffers (one per warpgroup)
+#define SMH_B_FC1_LO 45056    // [128 x 128] low halves
+#define SMH_B_C0_LO 77824     // [32 x 64]   low halves
+#define SMH_WIMG_BYTES 81920
+#define SM_A0 81920           // 4 x 32 KB ctx tiles (one per warpgroup)
 #define SM_A_BYTES 32768
 #define SM_CONST (SM_A0 + UM_WG * SM_A_BYTES)   // fp32 constants
 #define CST_B0F 0
-#define CST_B1 64
 #define CST_G1 128
 #define CST_CB0 192
 #define CST_CW1 224
 #define CST_CB1 256
-#define CST_B1C 264           // b1 - mean(b1) (fast variant: every LayerNorm input is produced already centred)
+#define CST_B1C 264           // b1 - mean(b1): every LayerNorm input is produced already centred
 #define CST_COUNT 328
 #define SM_BAR (SM_CONST + CST_COUNT * 4)       // 8 mbarriers
 #define SM_TMEM (SM_BAR + 64)
