@@ -12,6 +12,9 @@
 #define HSG_DK 16
 #define HSG_HD 128                 // n_head * d_k = n_head * d_v   (Higashi_wrapper.py:834-845)
 #define HSG_LN_EPS 1e-5f
+// cell cross-term table XS [token][16]: floats 0..7 = qcK, 8..15 = kcQ, each group stored as 4 (head i, head i+4) pairs so
+// that the scorer lane that owns halves of heads i and i+4 reads both with one 64-bit load
+#define HSG_XS_POS(h) ((((h) & 3) << 1) | ((h) >> 2))
 #define HSG_L2E_QUARTER 0.36067376022224085f      // log2(e) / 4: attention logits of the tensor-core scorer are kept in log2 units
 #define HSG_PDF0 0.3989422804014327f   // scipy.stats.norm.pdf(0)   (Impute.py:19)
 

@@ -520,8 +520,8 @@ __global__ void __launch_bounds__(256) token_project_kernel(
                     a = fmaf(__ldg(qc + e), qkT[(HSG_HD + h * 16 + e) * TP_LDA + tk], a);
                     b = fmaf(qkT[(h * 16 + e) * TP_LDA + tk], __ldg(kc + e), b);
                 }
-                XS[tok * 16 + h] = a * HSG_L2E_QUARTER;
-                XS[tok * 16 + 8 + h] = b * HSG_L2E_QUARTER;
+                XS[tok * 16 + HSG_XS_POS(h)] = a * HSG_L2E_QUARTER;
+                XS[tok * 16 + 8 + HSG_XS_POS(h)] = b * HSG_L2E_QUARTER;
             }
         }
     }

@@ -184,8 +184,8 @@ __global__ void __launch_bounds__(128, 2) project_umma_kernel(ProjParams p) {
                            pack_h2(v[4] * qs, v[5] * qs), pack_h2(v[6] * qs, v[7] * qs));
                 }
                 // half 0: kcQ = Q_b . K_cell -> XS[8 + h] ; half 1: qcK = Q_cell . K_b -> XS[h]
-                xs[(half == 0 ? 8 : 0) + cc * 2] = crA * HSG_L2E_QUARTER;
-                xs[(half == 0 ? 8 : 0) + cc * 2 + 1] = crB * HSG_L2E_QUARTER;
+                xs[(half == 0 ? 8 : 0) + HSG_XS_POS(cc * 2)] = crA * HSG_L2E_QUARTER;          // heads 2 cc and 2 cc + 1 of this 32-column chunk
+                xs[(half == 0 ? 8 : 0) + HSG_XS_POS(cc * 2 + 1)] = crB * HSG_L2E_QUARTER;
             }
             __syncthreads();
             // copy-out: lane j of a row group moves chunks j and 8 + j (8 lanes = one contiguous 128-byte line)

@@ -97,11 +97,11 @@ __global__ void __launch_bounds__(UM_THREADS, 1) score_umma_kernel(UmmaParams p)
                     float la, lb;
                     const float4 *va, *vb;
                     if (t == 0) {
-                        la = __ldg(p.XS + ti * 16u + h); lb = __ldg(p.XS + tj * 16u + h);
+                        la = __ldg(p.XS + ti * 16u + HSG_XS_POS(h)); lb = __ldg(p.XS + tj * 16u + HSG_XS_POS(h));
                         va = BV4 + bi_r * 32u + h * 4; vb = BV4 + bj_r * 32u + h * 4;
                     } else {
                         const uint32_t tq = (t == 1) ? ti : tj, tk = (t == 1) ? tj : ti;
-                        la = __ldg(p.XS + tq * 16u + 8 + h);
+                        la = __ldg(p.XS + tq * 16u + 8 + HSG_XS_POS(h));
                         const float4* q = QK4 + tq * 64u + h * 4; const float4* k = QK4 + tk * 64u + 32 + h * 4;
                         float2 acc = make_float2(0.f, 0.f), acc2 = acc;
 #pragma unroll

@@ -151,7 +151,7 @@ __device__ __forceinline__ uint32_t h2u(__half2 h) { return *reinterpret_cast<ui
 struct UmmaParams {
     // 16-bit token tables
     const __half* QK16;      // [slot][n_bins][256]  Q then K
-    const float* XS;         // [slot][n_bins][16]   qcK[8] = Q_cell.K_b/4, kcQ[8] = Q_b.K_cell/4 per head
+    const float* XS;         // [slot][n_bins][16]   qcK[8] = Q_cell.K_b, kcQ[8] = Q_b.K_cell (x log2(e)/4), pair order HSG_XS_POS
     const __half* binV16;    // [n_bins][128]
     const float* binSb;      // [16][n_bins][4] feature blocks: beta(layer_norm1) - layer_norm2(fc2 V)
     const __half* cellV16;   // [n_cells][128]
@@ -208,9 +208,9 @@ __device__ __forceinline__ uint4 ldg_nc_u4_volatile(const uint4* p) {
     asm volatile("ld.global.nc.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(p));
     return v;
 }
-__device__ __forceinline__ float ldg_nc_f32_volatile(const float* p) {
-    float v;
-    asm volatile("ld.global.nc.f32 %0, [%1];" : "=f"(v) : "l"(p));
+__device__ __forceinline__ float2 ldg_nc_f32x2_volatile(const float* p) {
+    float2 v;
+    asm volatile("ld.global.nc.v2.f32 {%0, %1}, [%2];" : "=f"(v.x), "=f"(v.y) : "l"(p));
     return v;
 }
 // everything one lane needs from the token tables for one row of one token position
@@ -227,13 +227,14 @@ __device__ __forceinline__ void att_load(AttRow& r, int rw, const int2* s_pr, co
     const uint32_t ti = tokbase + (uint32_t)pr.x, tj = tokbase + (uint32_t)pr.y;
     r.rw = rw;
     if (T == 0) {
-        r.laA = ldg_nc_f32_volatile(XSa + ti * 16u); r.laB = ldg_nc_f32_volatile(XSa + ti * 16u + 4);
-        r.lbA = ldg_nc_f32_volatile(XSa + tj * 16u); r.lbB = ldg_nc_f32_volatile(XSa + tj * 16u + 4);
+        const float2 la = ldg_nc_f32x2_volatile(XSa + ti * 16u), lb = ldg_nc_f32x2_volatile(XSa + tj * 16u);   // (head hA, head 4 + hA)
+        r.laA = la.x; r.laB = la.y; r.lbA = lb.x; r.lbB = lb.y;
         r.qA = ldg_nc_u4_volatile(BVj + (uint32_t)pr.x * 16u); r.qB = ldg_nc_u4_volatile(BVj + (uint32_t)pr.x * 16u + 8);
         r.bA = ldg_nc_u4_volatile(BVj + (uint32_t)pr.y * 16u); r.bB = ldg_nc_u4_volatile(BVj + (uint32_t)pr.y * 16u + 8);
     } else {
         const uint32_t tq = (T == 1) ? ti : tj, tk = (T == 1) ? tj : ti, bv = (uint32_t)((T == 1) ? pr.y : pr.x);
-        r.laA = ldg_nc_f32_volatile(XSa + tq * 16u); r.laB = ldg_nc_f32_volatile(XSa + tq * 16u + 4);
+        const float2 la = ldg_nc_f32x2_volatile(XSa + tq * 16u);
+        r.laA = la.x; r.laB = la.y;
         r.qA = ldg_nc_u4_volatile(QKj + tq * 32u); r.qB = ldg_nc_u4_volatile(QKj + tq * 32u + 8);
         r.kA = ldg_nc_u4_volatile(QKj + tk * 32u + 16); r.kB = ldg_nc_u4_volatile(QKj + tk * 32u + 24);
         r.bA = ldg_nc_u4_volatile(BVj + bv * 16u); r.bB = ldg_nc_u4_volatile(BVj + bv * 16u + 8);
@@ -280,7 +281,7 @@ __device__ __forceinline__ void attention_fast(const __half* __restrict__ QK16, 
     const int j = lane & 7, rsub = lane >> 3, hA = j >> 1;
     const uint4* QKj = reinterpret_cast<const uint4*>(QK16) + j;
     const uint4* BVj = reinterpret_cast<const uint4*>(binV16) + j;
-    const float* XSa = XS + hA + (T == 0 ? 0 : 8);
+    const float* XSa = XS + 2 * hA + (T == 0 ? 0 : 8);        // pair (head hA, head 4 + hA), see HSG_XS_POS
     uint4 vcA = make_uint4(0, 0, 0, 0), vcB = vcA;
     if (T != 0) {
         const uint4* vc = reinterpret_cast<const uint4*>(cellV16) + (uint32_t)cell * 16u + j;
