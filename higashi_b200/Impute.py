@@ -81,20 +81,28 @@ def impute_process(config_path, model, name, mode, cell_start, cell_end, sparse_
         offs.append(offs[-1] + eng.sel_P[slot])
 
     start = time.time()
-    buf = torch.empty((min(cells_per_call, max(1, cell_end - cell_start)), max(1, eng.P)), dtype=torch.float32).pin_memory()
-    count = 0
-    for c0 in range(cell_start, cell_end, cells_per_call):
-        c1 = min(cell_end, c0 + cells_per_call)
-        out = buf.numpy()[: c1 - c0]
-        eng.ctx.impute_cells_host_ptr(c0, c1, buf.data_ptr())
+    # two pinned blocks: the writer thread drains block k into the sinks (copy + gzip) while the GPU fills block k + 1
+    rows = min(cells_per_call, max(1, cell_end - cell_start))
+    bufs = [torch.empty((rows, max(1, eng.P)), dtype=torch.float32).pin_memory() for _ in range(2)]
+    drain = S.AsyncDrain(depth=1)
+
+    def write_block(out, c0, c1):
         for i in range(c0, c1):
             for slot in range(len(impute_list)):
                 sinks[slot].create_dataset("cell_%d" % i, out[i - c0, offs[slot]:offs[slot + 1]].copy(), compress=True)
+
+    count = 0
+    for k, c0 in enumerate(range(cell_start, cell_end, cells_per_call)):
+        c1 = min(cell_end, c0 + cells_per_call)
+        buf = bufs[k % 2]
+        eng.ctx.impute_cells_host_ptr(c0, c1, buf.data_ptr())            # block k - 1 is being written meanwhile
+        drain.submit(lambda out=buf.numpy()[: c1 - c0], a=c0, b=c1: write_block(out, a, b))   # waits for block k - 1 first
         count += c1 - c0
         if impute_verbose > 0:
             el = time.time() - start
             print("Imputing %s: %d of %d, takes %.2f s estimate %.2f s to finish" %
                   (name, count, cell_end - cell_start, el, el / count * (cell_end - cell_start - count)))
+    drain.close()
     print("finish imputing, used %.2f s" % (time.time() - start))
     for sk in sinks:
         sk.close()

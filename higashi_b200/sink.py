@@ -32,6 +32,53 @@ class ChromSink:
             np.savez(self.base + ".npz", **self.data)
 
 
+class AsyncDrain:
+    """One background thread that drains finished score blocks into the sinks while the GPU computes the next block
+    (SURVEY 8f rank 2).  submit(job) hands over a callable; at most `depth` jobs are in flight, so with depth + 1 pinned host
+    buffers the producer never overwrites a block that is still being written.  Exceptions of the writer are re-raised in the
+    caller by the next submit() / close()."""
+
+    def __init__(self, depth: int = 1):
+        import queue
+        import threading
+        self._q = queue.Queue(maxsize=depth)
+        self._err = None
+        self._t = threading.Thread(target=self._run, daemon=True)
+        self._t.start()
+
+    def _run(self):
+        while True:
+            job = self._q.get()
+            try:
+                if job is None:
+                    return
+                if self._err is None:
+                    job()
+            except BaseException as e:      # noqa: BLE001 - handed to the caller
+                self._err = e
+            finally:
+                self._q.task_done()
+
+    def _raise(self):
+        if self._err is not None:
+            err, self._err = self._err, None
+            raise err
+
+    def submit(self, job):
+        self._raise()
+        self._q.put(job)                    # blocks while `depth` jobs are pending
+
+    def wait(self):
+        self._q.join()
+        self._raise()
+
+    def close(self):
+        self._q.join()
+        self._q.put(None)
+        self._t.join()
+        self._raise()
+
+
 def read_container(temp_dir, chrom, name):
     base = os.path.join(temp_dir, "%s_%s" % (chrom, name))
     if h5py is not None and os.path.exists(base + ".hdf5"):

@@ -184,3 +184,21 @@ def test_packed_contact_blob_round_trip(tmp_path):
     import pytest
     with pytest.raises(ValueError):
         S.PackedCSR.load_blob(path)
+
+
+def test_async_drain_orders_jobs_and_propagates_errors():
+    """The background writer of the output sink (8f rank 2): jobs run in submission order, at most depth jobs are pending, and an
+    exception raised by a job surfaces in the producer."""
+    import time
+    import pytest
+    from higashi_b200.sink import AsyncDrain
+    seen = []
+    d = AsyncDrain(depth=1)
+    for i in range(6):
+        d.submit(lambda i=i: (time.sleep(0.01), seen.append(i)))
+    d.close()
+    assert seen == list(range(6))
+    d = AsyncDrain(depth=1)
+    d.submit(lambda: (_ for _ in ()).throw(ValueError("disk full")))
+    with pytest.raises(ValueError):
+        d.close()
