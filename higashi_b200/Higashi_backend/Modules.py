@@ -321,6 +321,38 @@ class GraphSageEncoder_with_weights(nn.Module):
 
 
 # ----------------------------------------------------------------------------- the scorer
+class _HyperedgeScoreFn(torch.autograd.Function):
+    """Hyper_SAGNN.forward as one autograd node: forward = hsg_score_fwd (no loss), backward = hsg_score_set_head_grads +
+    hsg_score_bwd; parameter gradients are written to the module's parameters as a side effect of backward."""
+
+    @staticmethod
+    def forward(ctx, anchor, model, x, chrom, to_neighs, stage):
+        eng = model._train_engine(stage)
+        model._push_params(eng)
+        model._tseed += 1
+        eng.set_dropout(bool(model.training), seed=0x51ED0000 + model._tseed)
+        xx = np.ascontiguousarray(np.asarray(x.detach().cpu() if hasattr(x, "detach") else x), dtype=np.int64)
+        eng.forward(xx, chrom, to_neighs, stage=stage, loss_mode=2, only_model=bool(model.only_model), want_outputs=False)
+        mean, var, proba, _ = eng.heads(len(xx), zinb=True)
+        ctx.set_materialize_grads(False)
+        ctx.model, ctx.eng, ctx.chrom, ctx.stage = model, eng, chrom, stage
+        dev = eng.device
+        return tuple(torch.from_numpy(a).to(dev).view(-1, 1) for a in (mean, var, proba))
+
+    @staticmethod
+    def backward(ctx, gmean, gvar, gproba):
+        eng, model = ctx.eng, ctx.model
+        if gmean is None:
+            gmean = torch.zeros_like(gvar if gvar is not None else gproba)
+        eng.zero_grad()
+        zinb = gvar is not None or gproba is not None
+        eng.set_head_grads(gmean, gvar, gproba)
+        eng.backward()
+        torch.cuda.current_stream(eng.device).synchronize()
+        model._pull_grads(eng, ctx.chrom, ctx.stage, zinb)
+        return None, None, None, None, None, None
+
+
 class Hyper_SAGNN(nn.Module):
     """Reference: Modules.py:657-827.  Same constructor and attributes; `predict` runs the fused CUDA scorer."""
 
@@ -378,12 +410,73 @@ class Hyper_SAGNN(nn.Module):
 
     def __getstate__(self):
         st = self.__dict__.copy()
-        st["_engine"] = None            # the CUDA context is not part of the pickle (torch.save(model))
+        st["_engine"] = None            # the CUDA contexts are not part of the pickle (torch.save(model))
+        for k in ("_teng", "_teng_key", "_tmap", "_tflat", "_tversion", "_tseed"):
+            st.pop(k, None)
         return st
 
+    # -- training forward (three heads) under torch autograd ------------------------------------------------------------
+    def _train_engine(self, stage: int):
+        """TrainEngine bound to this module's parameters (created lazily, rebuilt when the hook state changes)."""
+        from ..train_engine import TrainEngine
+        _require_cuda("Hyper_SAGNN.forward")
+        emb = self.encode1.static_nn
+        cell_on = 0 in emb.on_hook_set
+        cell_table = None if cell_on else emb.off_hook_embedding[0].embedding
+        key = (stage, cell_on, None if cell_table is None else cell_table.data_ptr(), torch.cuda.current_device())
+        if getattr(self, "_teng", None) is not None and self._teng_key == key:
+            return self._teng
+        if getattr(self, "_teng", None) is not None:
+            self._teng.close()
+        num = [int(emb.num_list[i + 1] - emb.num_list[i]) for i in range(len(emb.wstack))]
+        feats = [e.embedding.detach().cpu().numpy().astype(np.float32) for e in emb.embeddings]
+        eng = TrainEngine(self.state_dict(), num, feats, self.cell_feats, device=torch.cuda.current_device(), cell_table=cell_table,
+                          cell_on_hook=(cell_on and stage == 1))
+        named = dict(self.named_parameters(remove_duplicate=False))
+        self._tmap = [(name, named[name], o, int(np.prod(shape))) for name, (o, shape) in eng.layout.items() if name in named]
+        self._tflat = torch.zeros(eng.total, dtype=torch.float32).pin_memory()
+        self._tversion = None
+        self._teng, self._teng_key, self._tseed = eng, key, 0
+        return eng
+
+    def _push_params(self, eng):
+        version = tuple(p._version for _, p, _, _ in self._tmap)
+        if version == self._tversion:
+            return
+        for _, prm, o, n in self._tmap:
+            self._tflat[o:o + n].copy_(prm.detach().reshape(-1))
+        eng.params.copy_(self._tflat, non_blocking=False)
+        self._tversion = version
+
+    def _pull_grads(self, eng, chrom, stage, zinb):
+        from ..train_engine import grad_presence
+        flat = eng.grads.detach().cpu()
+        names = [t[0] for t in self._tmap]
+        for (name, prm, o, n), on in zip(self._tmap, grad_presence(names, chrom, stage, zinb, eng.cell_on_hook)):
+            if not on or not prm.requires_grad:
+                continue
+            g = flat[o:o + n].view(prm.shape).to(prm.device)
+            prm.grad = g.clone() if prm.grad is None else prm.grad + g
+
     def forward(self, x, x_chrom, mask=None, chroms_in_batch=None):
-        raise RuntimeError("Hyper_SAGNN.forward (three-head training forward) belongs to the training kernels "
-                           "(DESIGN.md section 9); use predict() for the imputation path")
+        """Modules.py:726-783: (mean, var, proba) heads [B,1] of a minibatch of ONE chromosome, differentiable: the forward and
+        backward passes run in the CUDA training kernels (hsg_score_fwd / hsg_score_bwd); loss.backward() leaves the gradients
+        in the .grad of this module's parameters, so the reference's train_epoch body works unchanged.  `x_chrom` is either the
+        chromosome array or the (chromosome array, to_neighs) pair that forward_batch_hyperedge passes (Higashi_wrapper.py:867)."""
+        to_neighs = None
+        if isinstance(x_chrom, (tuple, list)) and len(x_chrom) == 2 and not np.isscalar(x_chrom[0]):
+            x_chrom, to_neighs = x_chrom
+        chroms = np.asarray(x_chrom.detach().cpu() if hasattr(x_chrom, "detach") else x_chrom).reshape(-1)
+        if len(chroms) == 0 or np.any(chroms != chroms[0]):
+            raise ValueError("one chromosome per minibatch (DataGenerator.next_iter with k=1, Modules.py:1205)")
+        stage = 2 if isinstance(self.encode1.dynamic_nn, GraphSageEncoder_with_weights) else 1
+        if stage == 2:
+            if isinstance(to_neighs, list) and len(to_neighs) == 1:
+                to_neighs = to_neighs[0]
+            if to_neighs is None:
+                raise ValueError("the GraphSAGE encoder needs the to_neighs_to_mask tuple: model(x, (chrom, to_neighs))")
+        anchor = torch.zeros((), dtype=torch.float32, requires_grad=torch.is_grad_enabled())
+        return _HyperedgeScoreFn.apply(anchor, self, x, int(chroms[0]), to_neighs, stage)
 
     def predict(self, input, input_chrom, verbose=False, batch_size=96, activation=None, extra_info=None):
         """Modules.py:786-827: scores of explicit triplets [N,3] (cell+1, bin_i, bin_j) for the cell fixed by

@@ -74,7 +74,7 @@ EXPORTS = [
     "hsg_fix_cell", "hsg_score_triplets", "hsg_launch_count", "hsg_last_timing", "hsg_set_profiling",
     "hsg_train_bind", "hsg_train_set_features", "hsg_score_fwd", "hsg_score_bwd", "hsg_train_options", "hsg_score_heads",
     "hsg_train_bind_recon", "hsg_recon_loss", "hsg_recon_apply", "hsg_train_set_dropout",
-    "hsg_sample_batch", "hsg_sample_batch_begin", "hsg_sample_batch_end", "hsg_sampled_fetch",
+    "hsg_score_set_head_grads", "hsg_sample_batch", "hsg_sample_batch_begin", "hsg_sample_batch_end", "hsg_sampled_fetch",
 ]
 
 
@@ -121,6 +121,7 @@ def load():
     lib.hsg_train_bind.argtypes = [p, p, p, i64, i64p, i64p, i64p]
     lib.hsg_train_set_features.argtypes = [p, i32, f32p, i64, i32]
     lib.hsg_score_fwd.argtypes = [p, i32, i32, i64p, i32, i32p, i32p, f32p, i32, f32p, f32p, i32, i32, f32p, f32p, p]
+    lib.hsg_score_set_head_grads.argtypes = [p, p, p, p, p]
     lib.hsg_sample_batch.argtypes = [p, i64p, f32p, i32, i32, i32, C.c_float, i32, i32, i32, C.c_float, C.c_uint64, i32p, i64p, p]
     lib.hsg_sample_batch_begin.argtypes = [p, i64p, f32p, i32, i32, i32, C.c_float, i32, i32, i32, C.c_float, C.c_uint64]
     lib.hsg_sample_batch_end.argtypes = [p, i32p, i64p, p]

@@ -921,7 +921,7 @@ extern "C" int hsg_score_fwd(hsg_ctx* c, int stage, int chrom, const int64_t* x_
     if (loss_mode == 2) {
         HSG_CHECK(b->off_slot[HSG_W_VAR_W0] >= 0 && b->off_slot[HSG_W_PRB_W0] >= 0 && b->off_slot[HSG_W_XP_W0] >= 0 &&
                   b->off_slot[HSG_W_XP3_W0] >= 0, "zinb mode needs the var / proba heads bound");
-        HSG_CHECK(g_opts[c].c2w != nullptr, "zinb mode needs hsg_train_options(cell2weight)");
+        HSG_CHECK(g_opts[c].c2w != nullptr || !(have_w), "zinb loss needs hsg_train_options(cell2weight)");
         if (LIN_FWD(R, hd, d, w->Sn, d, PARAM(HSG_W_VAR_W0), d, w->vact, hd, 0.f)) return 1;
         bias_act_kernel<<<nblk((int64_t)R * hd), 256, 0, s>>>(w->vact, PARAM(HSG_W_VAR_B0), (int64_t)R * hd, hd, 1, w->vpre); TR_CHECK_LAUNCH(c);
         head_out_kernel<<<nblk(R), 256, 0, s>>>(w->vact, R, hd, PARAM(HSG_W_VAR_W1), PARAM(HSG_W_VAR_B1), w->ov); TR_CHECK_LAUNCH(c);
@@ -959,6 +959,30 @@ extern "C" int hsg_score_fwd(hsg_ctx* c, int stage, int chrom, const int64_t* x_
 }
 
 // backward of the last hsg_score_fwd batch: accumulates into the bound flat gradient buffer (the caller zeroes it)
+// Upstream gradients of the three heads from an external loss (Hyper_SAGNN.forward used under torch autograd): replaces the
+// gradients the built-in loss kernels would have written.  Device pointers, [B] each; dvar / dproba may be NULL (those heads then
+// receive no gradient and the backward pass skips them).
+extern "C" int hsg_score_set_head_grads(hsg_ctx* c, const float* dmean_dev, const float* dvar_dev, const float* dproba_dev, void* stream) {
+    HSG_CHECK(c && dmean_dev, "bad arguments");
+    HSG_CUDA(cudaSetDevice(c->device));
+    auto it = g_ws.find(c);
+    HSG_CHECK(it != g_ws.end() && it->second && it->second->B > 0, "hsg_score_set_head_grads: no forward batch");
+    TrainWs* w = it->second;
+    cudaStream_t s = (cudaStream_t)stream;
+    const size_t nb = (size_t)w->B * sizeof(float);
+    HSG_CUDA(cudaMemcpyAsync(w->dmean, dmean_dev, nb, cudaMemcpyDeviceToDevice, s));
+    if (dvar_dev || dproba_dev) {
+        HSG_CHECK(w->mode == 2, "var / proba gradients need a forward pass that produced those heads (loss_mode 2)");
+        if (dvar_dev) HSG_CUDA(cudaMemcpyAsync(w->dvar, dvar_dev, nb, cudaMemcpyDeviceToDevice, s));
+        else HSG_CUDA(cudaMemsetAsync(w->dvar, 0, nb, s));
+        if (dproba_dev) HSG_CUDA(cudaMemcpyAsync(w->dproba, dproba_dev, nb, cudaMemcpyDeviceToDevice, s));
+        else HSG_CUDA(cudaMemsetAsync(w->dproba, 0, nb, s));
+    } else if (w->mode == 2) {
+        w->mode = 0;                 // the main head only: the backward of the var / proba heads is skipped
+    }
+    return 0;
+}
+
 extern "C" int hsg_score_bwd(hsg_ctx* c, void* stream) {
     HSG_CHECK(c && g_ws.count(c) && g_ws[c]->B > 0, "no forward batch to differentiate");
     HSG_CUDA(cudaSetDevice(c->device));

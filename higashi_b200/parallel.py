@@ -119,17 +119,8 @@ class DataParallelTrainer:
         """Which parameter tensors receive a gradient for a batch of chromosome `chrom` (host list, cached)."""
         key = (chrom, stage, self.loss_mode_cached)
         if key not in self._patterns:
-            zinb = self.loss_mode_cached == 2
-            pat = []
-            for n in self.names:
-                if ".wstack." in n:
-                    b = int(n.split(".wstack.")[1].split(".")[0])
-                    on = (b == chrom + 1) or (b == 0 and stage == 1 and self.eng.cell_on_hook)
-                else:
-                    unused_head = (n.startswith("pff_classifier_var") or n.startswith("pff_classifier_proba") or
-                                   n.startswith("extra_proba.") or n.startswith("extra_proba3"))
-                    on = not ((unused_head and not zinb) or (stage == 1 and n.startswith("encode1.dynamic_nn.nn")))
-                pat.append(bool(on))
+            from .train_engine import grad_presence
+            pat = grad_presence(self.names, chrom, stage, self.loss_mode_cached == 2, self.eng.cell_on_hook)
             import torch
             self._patterns[key] = (pat, torch.tensor([1.0 if v else 0.0 for v in pat], dtype=torch.float32, device=self.presence.device))
         return self._patterns[key]

@@ -38,6 +38,22 @@ def neighbors_to_csr(to_neighs, n_rows: int, bin_base: int):
     return indptr, np.ascontiguousarray(cols), np.ascontiguousarray(val, dtype=np.float32)
 
 
+def grad_presence(names, chrom: int, stage: int, zinb: bool, cell_on_hook: bool):
+    """Which parameter tensors receive a gradient for a batch of chromosome `chrom` (the others keep grad = None, so Adam skips
+    them exactly as in the reference, where untouched branches have no .grad)."""
+    pat = []
+    for n in names:
+        if ".wstack." in n:
+            b = int(n.split(".wstack.")[1].split(".")[0])
+            on = (b == chrom + 1) or (b == 0 and stage == 1 and cell_on_hook)
+        else:
+            unused_head = (n.startswith("pff_classifier_var") or n.startswith("pff_classifier_proba") or
+                           n.startswith("extra_proba.") or n.startswith("extra_proba3"))
+            on = not ((unused_head and not zinb) or (stage == 1 and n.startswith("encode1.dynamic_nn.nn")))
+        pat.append(bool(on))
+    return pat
+
+
 class TrainEngine:
     def __init__(self, sd: Dict[str, object], num: Sequence[int], feats: list, cell_feats, device: int = 0,
                  cell_table=None, embed_prefix: str = "encode1.static_nn", cell_on_hook: bool = False):
@@ -237,6 +253,14 @@ class TrainEngine:
                                                      None if proba is None else fp(proba), None if pred is None else fp(pred),
                                                      C.c_void_p(stream)))
         return mean, var, proba, pred
+
+    def set_head_grads(self, dmean, dvar=None, dproba=None):
+        """Upstream gradients (CUDA float32 tensors [B]) of the heads of the last forward, from an external loss."""
+        keep = [None if t is None else t.detach().to(self.device, torch.float32).contiguous().reshape(-1) for t in (dmean, dvar, dproba)]
+        ptr = lambda t: None if t is None else C.c_void_p(t.data_ptr())
+        stream = torch.cuda.current_stream(self.device).cuda_stream
+        self.ctx._check(self.ctx.lib.hsg_score_set_head_grads(self.ctx.h, ptr(keep[0]), ptr(keep[1]), ptr(keep[2]), C.c_void_p(stream)))
+        torch.cuda.current_stream(self.device).synchronize()        # `keep` may be freed once the copies are done
 
     def backward(self):
         stream = torch.cuda.current_stream(self.device).cuda_stream

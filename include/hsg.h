@@ -188,6 +188,9 @@ int  hsg_sample_batch_end(hsg_ctx* ctx, int* B_out, int64_t* nnz_out, void* stre
  * any pointer may be NULL                                                                                               */
 int  hsg_sampled_fetch(hsg_ctx* ctx, int64_t* x_host, float* y_host, float* w_host, int32_t* indptr_host, int32_t* rowcnt_host,
                        int32_t* cols_host, float* vals_host, void* stream);
+/* upstream gradients of the heads from an EXTERNAL loss (Hyper_SAGNN.forward under torch autograd, Modules.py:726-783):
+ * device float [B] each, dvar / dproba may be NULL; call between hsg_score_fwd (run without y / w) and hsg_score_bwd        */
+int  hsg_score_set_head_grads(hsg_ctx* ctx, const float* dmean_dev, const float* dvar_dev, const float* dproba_dev, void* stream);
 /* replaces: loss.backward() (Higashi_wrapper.py:1006) for the batch of the last hsg_score_fwd: ACCUMULATES into grads */
 int  hsg_score_bwd(hsg_ctx* ctx, void* stream);
 

@@ -225,3 +225,50 @@ def test_stage1_trainer_step_runs_and_learns():
         recon.append(tr.recon_loss)
     assert losses[-1] < losses[0] and recon[-1] < recon[0], (losses, recon)
     eng.close()
+
+
+def test_module_forward_is_differentiable_like_the_reference():
+    """Hyper_SAGNN.forward of the mirror under torch autograd (the reference's train_epoch body: model(x, (chrom, to_neighs)),
+    F.binary_cross_entropy_with_logits, loss.backward()): heads, loss and every parameter gradient against the reference's
+    autograd on the golden batch (grads_d64.npz, eval mode)."""
+    import torch.nn.functional as F
+    from tests.test_host_mirror import build_mirror_model
+    g = load("grads_d64.npz")
+    ds = FixtureDataset(g)
+    sd = {k[3:]: v for k, v in g.items() if k.startswith("sd/")}
+    model = build_mirror_model(ds, 64, sd)
+    model.eval()
+    model.encode1.static_nn.off_hook([0])                      # stage >= 2: frozen cell table (Higashi_wrapper.py:1384)
+    x = torch.from_numpy(np.asarray(g["x"]))
+    tn = (g["indices"], g["values"], g["unique"])
+    mean, var, proba = model(x, (np.zeros(len(x), dtype=np.int8), tn), chroms_in_batch=np.array([1]))
+    assert mean.shape == (len(x), 1) and var.shape == mean.shape and proba.shape == mean.shape and mean.requires_grad
+    heads = torch.cat([mean, var, proba], dim=1).detach().cpu().numpy()          # the reference returns the same three heads
+    np.testing.assert_allclose(heads, g["out"], atol=1e-5, rtol=0)
+    y = torch.from_numpy(np.asarray(g["y"], dtype=np.float32)).view(-1, 1).to(mean.device)
+    w = torch.from_numpy(np.asarray(g["w"], dtype=np.float32)).view(-1, 1).to(mean.device)
+    loss = F.binary_cross_entropy_with_logits(mean, y, weight=w)
+    assert abs(float(loss.detach()) - float(g["loss"])) < 1e-5
+    loss.backward()
+    named = dict(model.named_parameters(remove_duplicate=False))
+    checked = 0
+    for k in g:
+        if not k.startswith("grad/"):
+            continue
+        name = k[len("grad/"):]
+        got = named[name].grad
+        assert got is not None, name
+        ref = g[k].reshape(tuple(got.shape))
+        scale = max(1e-3, float(np.abs(ref).max()))
+        err = float(np.abs(got.cpu().numpy() - ref).max())
+        assert err <= 2e-5 * max(1.0, scale / 1e-2) + 1e-6, (name, err, scale)
+        checked += 1
+    assert checked >= 33
+    assert named["encode1.static_nn.wstack.2.weight_list.0"].grad is None          # the other chromosome's branch: untouched
+    assert named["pff_classifier_var.w_stack.0.weight"].grad is None               # heads that did not feed the loss
+    # a second call after an optimizer step sees the updated parameters
+    opt = torch.optim.SGD([p for p in model.parameters() if p.grad is not None], lr=1e-2)
+    opt.step()
+    mean2, _, _ = model(x, (np.zeros(len(x), dtype=np.int8), tn))
+    loss2 = F.binary_cross_entropy_with_logits(mean2, y, weight=w)
+    assert float(loss2.detach()) < float(loss.detach())
