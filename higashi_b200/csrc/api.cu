@@ -75,7 +75,7 @@ static void free_derived(hsg_ctx* c) {
     { __half* p = (__half*)c->QK16; dev_free(p); c->QK16 = nullptr; }
     { __half* p = (__half*)c->binV16; dev_free(p); c->binV16 = nullptr; }
     { __half* p = (__half*)c->cellV16; dev_free(p); c->cellV16 = nullptr; }
-    dev_free(c->XS); dev_free(c->binSb); dev_free(c->cellSb); dev_free(c->wimg); dev_free(c->cst); dev_free(c->pj_wimg); dev_free(c->ovf_list);
+    dev_free(c->XS); dev_free(c->binSb); dev_free(c->cellSb); dev_free(c->binV32p); dev_free(c->cellV32p); dev_free(c->wimg); dev_free(c->cst); dev_free(c->pj_wimg); dev_free(c->ovf_list);
     c->use_umma = false;
     dev_free(c->stage_out[0]); dev_free(c->stage_out[1]); c->stage_bytes = 0;
     c->prepared = false;
@@ -490,8 +490,9 @@ extern "C" int hsg_prepare(hsg_ctx* c, int precision, int local_transfer_range, 
         if (dev_alloc(&bv, (size_t)c->n_bins * HSG_HD) || dev_alloc(&cv, (size_t)c->n_cells * HSG_HD) ||
             dev_alloc(&c->binSb, (size_t)c->n_bins * d) || dev_alloc(&c->cellSb, (size_t)c->n_cells * d)) return 1;
         c->binV16 = bv; c->cellV16 = cv;
-        if (launch_convert_static(c, c->binV, c->binS, c->n_bins, c->binV16, c->binSb, c->stream)) return 1;
-        if (launch_convert_static(c, c->cellV, c->cellS, c->n_cells, c->cellV16, c->cellSb, c->stream)) return 1;
+        if (c->umma_hi && (dev_alloc(&c->binV32p, (size_t)c->n_bins * HSG_HD) || dev_alloc(&c->cellV32p, (size_t)c->n_cells * HSG_HD))) return 1;
+        if (launch_convert_static(c, c->binV, c->binS, c->n_bins, c->binV16, c->binSb, c->umma_hi ? c->binV32p : nullptr, c->stream)) return 1;
+        if (launch_convert_static(c, c->cellV, c->cellS, c->n_cells, c->cellV16, c->cellSb, c->umma_hi ? c->cellV32p : nullptr, c->stream)) return 1;
         per_cell = (size_t)c->n_bins * ((c->umma_hi ? 2 * HSG_HD * sizeof(float) : 2 * HSG_HD * sizeof(__half)) + 16 * sizeof(float) + d * sizeof(float));
     } else {
         per_cell = (size_t)c->n_bins * (2 * HSG_HD + d) * sizeof(float);

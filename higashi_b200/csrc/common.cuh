@@ -15,6 +15,9 @@
 // cell cross-term table XS [token][16]: floats 0..7 = qcK, 8..15 = kcQ, each group stored as 4 (head i, head i+4) pairs so
 // that the scorer lane that owns halves of heads i and i+4 reads both with one 64-bit load
 #define HSG_XS_POS(h) ((((h) & 3) << 1) | ((h) >> 2))
+// high-accuracy scorer tables: a 128-float Q / K / V row is stored as [4 quads][8 heads][4 floats], so that the 8 lanes of a row
+// (lane = head) read one contiguous 128-byte line per 128-bit load.  Column c = 16 h + 4 e + r  ->  32 e + 4 h + r
+#define HSG_HI_POS(c) ((((c) >> 2) & 3) * 32 + ((c) >> 4) * 4 + ((c) & 3))
 #define HSG_L2E_QUARTER 0.36067376022224085f      // log2(e) / 4: attention logits of the tensor-core scorer are kept in log2 units
 #define HSG_PDF0 0.3989422804014327f   // scipy.stats.norm.pdf(0)   (Impute.py:19)
 
@@ -97,6 +100,7 @@ struct hsg_ctx {
     void* QK16 = nullptr;                    // half [batch, n_bins, 256]
     float* XS = nullptr;                     // [batch, n_bins, 16] cross terms with the cell token
     void* binV16 = nullptr; float* binSb = nullptr; void* cellV16 = nullptr; float* cellSb = nullptr;
+    float* binV32p = nullptr; float* cellV32p = nullptr;   // high-accuracy variant: fp32 V rows in (quad e, head h) order (HSG_HI_POS)
     unsigned char* wimg = nullptr; float* cst = nullptr; float h_cst[512] = {0};
     unsigned char* pj_wimg = nullptr; float h_pj_cst[320] = {0}; bool use_proj_umma = false;   // tensor-core K1b (project_umma.cu)
     bool use_umma = false;
@@ -122,7 +126,7 @@ int launch_pair_bias(hsg_ctx* c, cudaStream_t s);
 int launch_gather(hsg_ctx* c, const int* cells_dev_unused, int cell_start, int n_cells_batch, cudaStream_t s);
 int launch_token_project(hsg_ctx* c, int cell_start, int n_cells_batch, int mode, cudaStream_t s);   // mode 0: fp32 QK, 1: fp16 QK + XS, 2: fp32 QK + XS
 int launch_score_pairs_umma(hsg_ctx* c, int cell_start, int n_cells_batch, float* out, cudaStream_t s);
-int launch_convert_static(hsg_ctx* c, const float* V, const float* S, long long rows, void* V16, float* Sb, cudaStream_t s);
+int launch_convert_static(hsg_ctx* c, const float* V, const float* S, long long rows, void* V16, float* Sb, float* V32p, cudaStream_t s);
 int umma_build_weights(const float* fc1, const float* w0, const float* b0, const float* pff_g, const float* pff_b,
                        const float* w1, const float* b1, const float* ln1_g, const float* c0, const float* cb0,
                        const float* cw1, const float* cb1, unsigned char* wimg_host, float* cst_host);

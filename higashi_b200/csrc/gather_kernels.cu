@@ -484,8 +484,10 @@ __global__ void __launch_bounds__(256) token_project_kernel(
 #pragma unroll
             for (int r = 0; r < 4; ++r) {
                 int64_t tok = tok0 + rg * 4 + r;
+                // MODE 2 (high-accuracy scorer): quads in (quad e, head h) order, see HSG_HI_POS
+                const int qpos = (MODE == 2) ? ((cg & 3) * 8 + (cg >> 2)) * 4 : cg * 4;
                 if (tok < n_tok)
-                    *reinterpret_cast<float4*>(QK + (tok * 2 + which) * HSG_HD + cg * 4) =
+                    *reinterpret_cast<float4*>(QK + (tok * 2 + which) * HSG_HD + qpos) =
                         make_float4(acc[r][0], acc[r][1], acc[r][2], acc[r][3]);
             }
         }

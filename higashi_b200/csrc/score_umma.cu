@@ -87,7 +87,13 @@ __global__ void __launch_bounds__(UM_THREADS, 1) score_umma_kernel(UmmaParams p)
                 const int cA = h * 2 + (h >> 2), cB = h * 2 + 1 - (h >> 2);
                 const float4* QK4 = reinterpret_cast<const float4*>(p.QK32);
                 const float4* BV4 = reinterpret_cast<const float4*>(p.binV32);
-                const float4* CV4 = reinterpret_cast<const float4*>(p.cellV32) + (uint32_t)cell * 32u + h * 4;
+                // rows are stored [quad e][head h][4 floats] (HSG_HI_POS): the 8 lanes of a row read 128 contiguous bytes per load
+                const float4* CV4 = reinterpret_cast<const float4*>(p.cellV32) + (uint32_t)cell * 32u + h;
+                float4 cv[4];
+                if (t != 0) {
+#pragma unroll
+                    for (int e = 0; e < 4; ++e) cv[e] = __ldg(CV4 + e * 8);
+                }
                 const uint32_t tokbase = (uint32_t)cb * (uint32_t)p.n_bins;
 #pragma unroll 1
                 for (int it = 0; it < 8; ++it) {
@@ -98,20 +104,20 @@ __global__ void __launch_bounds__(UM_THREADS, 1) score_umma_kernel(UmmaParams p)
                     const float4 *va, *vb;
                     if (t == 0) {
                         la = __ldg(p.XS + ti * 16u + HSG_XS_POS(h)); lb = __ldg(p.XS + tj * 16u + HSG_XS_POS(h));
-                        va = BV4 + bi_r * 32u + h * 4; vb = BV4 + bj_r * 32u + h * 4;
+                        va = BV4 + bi_r * 32u + h; vb = BV4 + bj_r * 32u + h;
                     } else {
                         const uint32_t tq = (t == 1) ? ti : tj, tk = (t == 1) ? tj : ti;
                         la = __ldg(p.XS + tq * 16u + 8 + HSG_XS_POS(h));
-                        const float4* q = QK4 + tq * 64u + h * 4; const float4* k = QK4 + tk * 64u + 32 + h * 4;
+                        const float4* q = QK4 + tq * 64u + h; const float4* k = QK4 + tk * 64u + 32 + h;
                         float2 acc = make_float2(0.f, 0.f), acc2 = acc;
 #pragma unroll
                         for (int e = 0; e < 4; ++e) {
-                            float4 qv = __ldg(q + e), kv = __ldg(k + e);
+                            float4 qv = __ldg(q + e * 8), kv = __ldg(k + e * 8);
                             acc = __ffma2_rn(make_float2(qv.x, qv.y), make_float2(kv.x, kv.y), acc);
                             acc2 = __ffma2_rn(make_float2(qv.z, qv.w), make_float2(kv.z, kv.w), acc2);
                         }
                         lb = ((acc.x + acc.y) + (acc2.x + acc2.y)) * HSG_L2E_QUARTER;
-                        va = CV4; vb = BV4 + ((t == 1) ? bj_r : bi_r) * 32u + h * 4;
+                        va = nullptr; vb = BV4 + ((t == 1) ? bj_r : bi_r) * 32u + h;
                     }
                     float wa, wb;
                     masked_row_fast(la, lb, wa, wb);
@@ -120,7 +126,7 @@ __global__ void __launch_bounds__(UM_THREADS, 1) score_umma_kernel(UmmaParams p)
                     uint32_t pk[8];
 #pragma unroll
                     for (int e = 0; e < 4; ++e) {
-                        float4 av = __ldg(va + e), bv = __ldg(vb + e);
+                        float4 av = (t == 0) ? __ldg(va + e * 8) : cv[e], bv = __ldg(vb + e * 8);
                         float2 c0 = __ffma2_rn(wb2, make_float2(bv.x, bv.y), __fmul2_rn(wa2, make_float2(av.x, av.y)));
                         float2 c1 = __ffma2_rn(wb2, make_float2(bv.z, bv.w), __fmul2_rn(wa2, make_float2(av.z, av.w)));
                         pk[e * 2] = pack_h2(c0.x, c0.y); pk[e * 2 + 1] = pack_h2(c1.x, c1.y);
@@ -373,15 +379,18 @@ int umma_cst_count() { return CST_COUNT; }
 
 // fp32 static tables -> 16-bit / offset copies used by the tensor-core kernel
 __global__ void convert_static_kernel(const float* __restrict__ V, const float* __restrict__ S, const float* __restrict__ ln1_b,
-                                      long long rows, int d, __half* __restrict__ V16, float* __restrict__ Sb) {
+                                      long long rows, int d, __half* __restrict__ V16, float* __restrict__ Sb, float* __restrict__ V32p) {
     long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i < rows * HSG_HD) V16[i] = __float2half_rn(V[i]);
+    if (i < rows * HSG_HD) {
+        V16[i] = __float2half_rn(V[i]);
+        if (V32p) { const int cc = (int)(i & (HSG_HD - 1)); V32p[i - cc + HSG_HI_POS(cc)] = V[i]; }
+    }
     if (i < rows * d) { long long r = i / d; int f = (int)(i - r * d); Sb[((long long)(f >> 2) * rows + r) * 4 + (f & 3)] = ln1_b[f] - S[i]; }
 }
 
-int launch_convert_static(hsg_ctx* c, const float* V, const float* S, long long rows, void* V16, float* Sb, cudaStream_t s) {
+int launch_convert_static(hsg_ctx* c, const float* V, const float* S, long long rows, void* V16, float* Sb, float* V32p, cudaStream_t s) {
     long long n = rows * HSG_HD;
-    convert_static_kernel<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(V, S, c->w[HSG_W_LN1_B], rows, c->d, (__half*)V16, Sb);
+    convert_static_kernel<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(V, S, c->w[HSG_W_LN1_B], rows, c->d, (__half*)V16, Sb, V32p);
     c->launches++;
     HSG_CUDA(cudaGetLastError());
     return 0;
@@ -392,7 +401,7 @@ int launch_score_pairs_umma(hsg_ctx* c, int cell_start, int n_batch, float* out,
     UmmaParams p;
     p.QK16 = (const __half*)c->QK16; p.XS = c->XS; p.binV16 = (const __half*)c->binV16; p.binSb = c->binSb;
     p.cellV16 = (const __half*)c->cellV16; p.cellSb = c->cellSb; p.wimg = c->wimg;
-    p.QK32 = c->QK; p.binV32 = c->binV; p.cellV32 = c->cellV;
+    p.QK32 = c->QK; p.binV32 = c->binV32p; p.cellV32 = c->cellV32p;
     memcpy(p.cst, c->h_cst, sizeof(p.cst));
     p.pairs = c->pairs; p.pair_bias = c->pair_bias; p.P = c->P;
     p.n_bins = c->n_bins; p.n_cells = c->n_cells; p.cell_start = cell_start; p.n_batch = n_batch;
