@@ -95,7 +95,7 @@ __global__ void __launch_bounds__(UM_THREADS, 1) score_umma_kernel(UmmaParams p)
                     for (int e = 0; e < 4; ++e) cv[e] = __ldg(CV4 + e * 8);
                 }
                 const uint32_t tokbase = (uint32_t)cb * (uint32_t)p.n_bins;
-#pragma unroll 1
+#pragma unroll 2
                 for (int it = 0; it < 8; ++it) {
                     const int rw = it * 4 + rsub;
                     const uint32_t bi_r = (uint32_t)__shfl_sync(0xffffffffu, pr.x, rw), bj_r = (uint32_t)__shfl_sync(0xffffffffu, pr.y, rw);
