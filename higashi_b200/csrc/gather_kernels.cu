@@ -187,17 +187,17 @@ __global__ void neigh_gather_kernel(const int64_t* __restrict__ row_ptr, const i
 //     (same order as the reference's sequential sparse adds, deterministic);
 //   * x pdf(0), log1p, L1 normalisation and the gather of the E rows (each lane owns 8 of the 64 output columns: two 128-bit
 //     loads per entry, one contiguous 256-byte row per group).
-// Tokens with more than GS_CAP merged candidates go to an overflow list that the generic warp-per-token kernel finishes.
+// Tokens with more than 8 SLOTS merged candidates go to an overflow list that the generic warp-per-token kernel finishes.
 // ---------------------------------------------------------------------------------------------
-#define GS_CAP 32
-#define GS_SLOTS (GS_CAP / 8)
+// SLOTS x 8 candidates per token are held in registers (SLOTS slots per lane): 4 (32 candidates) for the sparsest data, 8 / 12
+// (64 / 96) when the merged rows are longer -- the all-pairs dedup costs SLOTS^2, so the launcher picks the smallest that fits
 #define GS_WPB 8
 
-template <int S>
-__device__ __forceinline__ void gs_dedup(const int (&col)[GS_SLOTS], const float (&val)[GS_SLOTS], int gl, float (&sum)[GS_SLOTS],
-                                         bool (&dup)[GS_SLOTS]) {
+template <int SLOTS, int S>
+__device__ __forceinline__ void gs_dedup(const int (&col)[SLOTS], const float (&val)[SLOTS], int gl, float (&sum)[SLOTS],
+                                         bool (&dup)[SLOTS]) {
 #pragma unroll
-    for (int s = 0; s < GS_SLOTS; ++s) { sum[s] = 0.f; dup[s] = false; }
+    for (int s = 0; s < SLOTS; ++s) { sum[s] = 0.f; dup[s] = false; }
 #pragma unroll
     for (int s2 = 0; s2 < S; ++s2) {
 #pragma unroll
@@ -216,11 +216,26 @@ __device__ __forceinline__ void gs_dedup(const int (&col)[GS_SLOTS], const float
     }
 }
 
+// compile-time dispatch on the number of slots actually in use by this warp's four tokens
+template <int SLOTS, int S>
+__device__ __forceinline__ void gs_dedup_dispatch(int nmax, const int (&col)[SLOTS], const float (&val)[SLOTS], int gl,
+                                                  float (&sum)[SLOTS], bool (&dup)[SLOTS]) {
+    if constexpr (S >= SLOTS) {
+        gs_dedup<SLOTS, SLOTS>(col, val, gl, sum, dup);
+    } else {
+        if (nmax <= S * 8) gs_dedup<SLOTS, S>(col, val, gl, sum, dup);
+        else gs_dedup_dispatch<SLOTS, S + 1>(nmax, col, val, gl, sum, dup);
+    }
+}
+
+template <int SLOTS>
 __global__ void __launch_bounds__(GS_WPB * 32) neigh_gather_sparse_kernel(
     const int64_t* __restrict__ row_ptr, const int32_t* __restrict__ col, const float* __restrict__ val,
     const int32_t* __restrict__ nbr, const float* __restrict__ nbr_w, int k1, int weighted, const float* __restrict__ E_bin,
     const int* __restrict__ bin_chrom, const int* __restrict__ bin_off, int n_bins, int cell_start, int n_tok,
     float* __restrict__ neigh, int* __restrict__ tok_list, int* __restrict__ tok_count) {
+    constexpr int GS_CAP = SLOTS * 8;
+    constexpr int GS_SLOTS = SLOTS;
     __shared__ int s_col[GS_WPB][4][GS_CAP];
     __shared__ float s_val[GS_WPB][4][GS_CAP];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, gl = lane & 7, grp = lane >> 3;
@@ -278,10 +293,7 @@ __global__ void __launch_bounds__(GS_WPB * 32) neigh_gather_sparse_kernel(
         __syncwarp();
         float sum[GS_SLOTS];
         bool dup[GS_SLOTS];
-        if (nmax <= 8) gs_dedup<1>(ec, ev, gl, sum, dup);
-        else if (nmax <= 16) gs_dedup<2>(ec, ev, gl, sum, dup);
-        else if (nmax <= 24) gs_dedup<3>(ec, ev, gl, sum, dup);
-        else gs_dedup<4>(ec, ev, gl, sum, dup);
+        gs_dedup_dispatch<SLOTS, 1>(nmax, ec, ev, gl, sum, dup);
         // ---- x pdf(0), log1p, L1 normalisation (Impute.py:19, 91-92)
         float part = 0.f;
 #pragma unroll
@@ -340,7 +352,12 @@ int launch_gather(hsg_ctx* c, const int*, int cell_start, int n_batch, cudaStrea
     const int* count = nullptr;
     // sparse-row fast path (d = 64, no row-shift smoothing, at most 8 neighbour rows): the generic kernel then only finishes the
     // tokens on the overflow list
-    if (c->d == 64 && c->ltr == 0 && c->k1 <= 8 && n_tok < (1LL << 31) && c->gather_sparse) {
+    // Which kernel: the register kernel wins for sparse rows (<= 16 merged candidates on average).  For longer rows its
+    // all-pairs dedup (SLOTS^2) loses to the generic kernel's dense accumulator -- unless the chromosomes are so long that the
+    // accumulator (4 B x max_nc per warp) leaves the generic kernel with a handful of warps per SM (measured, C3 / C4 / C5 shapes).
+    const double avg_cand = (double)c->k1 * (double)c->nnz / (double)std::max<int64_t>(c->n_rows, 1);
+    const bool sparse_ok = c->d == 64 && c->ltr == 0 && c->k1 <= 8 && n_tok < (1LL << 31) && c->gather_sparse;
+    if (sparse_ok && (avg_cand <= 16.0 || max_nc > 1536)) {
         if (c->ovf_cap < n_tok + 1) {
             if (c->ovf_list) cudaFree(c->ovf_list);
             HSG_CUDA(cudaMalloc((void**)&c->ovf_list, (size_t)(n_tok + 1) * sizeof(int)));
@@ -351,9 +368,16 @@ int launch_gather(hsg_ctx* c, const int*, int cell_start, int n_batch, cudaStrea
         int64_t quads = (n_tok + 3) / 4;
         int64_t gb = (quads + GS_WPB - 1) / GS_WPB;
         int64_t gcap = (int64_t)c->n_sm * 8;
-        neigh_gather_sparse_kernel<<<(unsigned)(gb < gcap ? gb : gcap), GS_WPB * 32, 0, s>>>(
-            c->row_ptr, c->col, c->val, c->nbr, c->nbr_w, c->k1, c->weighted ? 1 : 0, c->E_bin, c->d_bin_chrom, c->d_bin_off,
-            c->n_bins, cell_start, (int)n_tok, c->neigh, c->ovf_list, cnt);
+        // register capacity from the average number of merged candidates per token (k+1 rows of nnz / n_rows entries each)
+        const double avg = avg_cand;
+        const unsigned g = (unsigned)(gb < gcap ? gb : gcap);
+#define GS_LAUNCH(SL) neigh_gather_sparse_kernel<SL><<<g, GS_WPB * 32, 0, s>>>(                                                    \
+            c->row_ptr, c->col, c->val, c->nbr, c->nbr_w, c->k1, c->weighted ? 1 : 0, c->E_bin, c->d_bin_chrom, c->d_bin_off,      \
+            c->n_bins, cell_start, (int)n_tok, c->neigh, c->ovf_list, cnt)
+        if (avg <= 16.0) GS_LAUNCH(4);
+        else if (avg <= 36.0) GS_LAUNCH(8);
+        else GS_LAUNCH(12);
+#undef GS_LAUNCH
         c->launches++;
         HSG_CUDA(cudaGetLastError());
         list = c->ovf_list; count = cnt;
