@@ -180,13 +180,20 @@ def test_gather_paths(density, k):
     _synthetic_case(k, 0, 64, "fp32", [120, 40], [0, 5, 39], density=density)
 
 
-def _synthetic_case(k, ltr, d, prec, bins, cells, density=None):
+@pytest.mark.parametrize("density", [0.004, 0.009])
+def test_gather_long_chromosome(density):
+    """Chromosomes longer than 1536 bins with medium-dense rows take the 64- / 96-candidate register kernels (plus the overflow
+    list); banded pairs keep the oracle fast."""
+    _synthetic_case(4, 0, 64, "fp32", [1600], [0, 7, 23], density=density, band=40, n_cells=24)
+
+
+def _synthetic_case(k, ltr, d, prec, bins, cells, density=None, band=-1, n_cells=40):
     from higashi_b200 import engine as E
     from higashi_b200 import synthetic as S
     from oracle import impute as OI
     from oracle import prep as OP
     from oracle import scorer as OS
-    ds = S.make_dataset("C1", n_cells=40, bins=bins, seed=5, **({} if density is None else {"density": density}))
+    ds = S.make_dataset("C1", n_cells=n_cells, bins=bins, seed=5, **({} if density is None else {"density": density}))
     ds.d = d
     sd, feats = _random_state(ds, d, seed=42 + d)
     nbr = nbr_w = None
@@ -199,7 +206,7 @@ def _synthetic_case(k, ltr, d, prec, bins, cells, density=None):
     eng.set_contacts(ds.csr)
     eng.set_neighbors(nbr, nbr_w)
     chroms = list(range(len(bins)))
-    eng.set_pairs(chroms, 1, -1)
+    eng.set_pairs(chroms, 1, band)
     eng.prepare(E.PREC_FP32 if prec == "fp32" else E.PREC_TC16, ltr, E.ACT_SIGMOID)
     tol = TOL_FP32 if prec == "fp32" else TOL_BF16
     got_all = eng.impute_to_host(0, ds.n_cells)
@@ -207,7 +214,7 @@ def _synthetic_case(k, ltr, d, prec, bins, cells, density=None):
     tsd = {k_: torch.from_numpy(np.asarray(v)) for k_, v in sd.items()}
     with torch.no_grad():
         tables = OS.embed_tables(tsd, feats)
-    big, big_chrom, slices, coords = OI.enumerate_pairs(ds.num_list, chroms, 1, int(1e5))
+    big, big_chrom, slices, coords = OI.enumerate_pairs(ds.num_list, chroms, 1, int(1e5) if band < 0 else band)
     ref = OI.impute_cells(tsd, tables, ds.cell_feats, ds.num_list, lambda c, cell: ds.csr.matrix(c, cell - 1), cells,
                           chroms, big, ltr, nbr, nbr_w, "sigmoid")
     assert eng.P == len(big)
