@@ -4,19 +4,20 @@
 // Blackwell:
 //   * one CTA per SM (persistent), 4 warpgroups of 128 threads; a warpgroup owns a tile of 128 triplets,
 //     thread r <-> triplet r <-> TMEM lane r, and walks the 3 tokens of its triplets one after the other;
-//   * per token row-tile the four dense contractions run on the 5th-gen tensor cores
-//       y  = ctx . fc1^T          (M128 N64 K128)      h = LN(y) . W0'^T       (M128 N64 K64)
-//       z  = y + h . W1^T         (accumulated onto y in TMEM, K64)
-//       c  = u . C0^T             (M128 N32 K64),  u = (LN1(z) - S)^2
-//     issued by one elected thread of the warpgroup (tcgen05.mma, fp16 operands, fp32 accumulation in
-//     TMEM), completion tracked with tcgen05.commit -> mbarrier, accumulators read back with tcgen05.ld;
-//   * A operands are produced by the warpgroup itself (attention / LayerNorm / swish epilogues) straight
-//     into the canonical K-major SWIZZLE_128B shared-memory layout; the B operands (weights, pre-swizzled
-//     on the host) are staged once per CTA with one TMA bulk copy (cp.async.bulk + mbarrier);
-//   * the 3-token masked attention stays in registers (packed half2 math); the only HBM traffic of the
-//     kernel is the 4-byte score per triplet, token tables are read through L1/L2.
+//   * per token row-tile the dense contractions run on the 5th-gen tensor cores in THREE MMA round trips
+//       [y_c | g] = ctx . [fc1c ; W0' fc1c]^T   (M128 N128 K128; centred fc1, LayerNorm . W0 folded in: see the body)
+//       z_c       = y_c + h . W1c^T             (M128 N64 K64, accumulated onto y_c in TMEM; A operand h in TMEM)
+//       c         = u . C0^T                    (M128 N32 K64; A operand u = (LN1(z) - S)^2 in TMEM)
+//     issued by one elected thread of the warpgroup (tcgen05.mma, fp16 operands, fp32 accumulation in TMEM), completion
+//     tracked with tcgen05.commit -> mbarrier, accumulators read back with tcgen05.ld;
+//   * the ctx operand is written by the warpgroup itself straight into the canonical K-major SWIZZLE_128B shared-memory
+//     layout; h and u go back to TMEM with tcgen05.st and are consumed as TMEM A operands (no shared-memory round trip);
+//     the B operands (weights, pre-swizzled on the host) are staged once per CTA with one TMA bulk copy (cp.async.bulk);
+//   * the 3-token masked attention stays in registers (packed half2 math, software-pipelined table loads); the only HBM
+//     traffic of the kernel is the 4-byte score per triplet, token tables are read through L1/L2;
+//   * template flag HI: high-accuracy variant (fp32 tables and attention, hi + lo weight / operand splits) for softplus heads.
 // Operands are fp16, not bf16: with bf16 operands the measured score error is 1.5e-3..2e-3 (above the 1e-3
-// parity bar), with fp16 it is 2.4e-4 at identical tensor throughput (scripts/bf16_emulation.py).
+// parity bar), with fp16 it is <= 5e-4 at identical tensor throughput (scripts/bf16_emulation.py, scripts/tail_error.py).
 #include "umma_common.cuh"
 
 template <bool HI>
@@ -313,10 +314,6 @@ __global__ void __launch_bounds__(UM_THREADS, 1) score_umma_kernel(UmmaParams p)
 // ---------------------------------------------------------------------------------------------
 // host side
 // ---------------------------------------------------------------------------------------------
-struct UmmaTables {
-    __half* QK16; float* XS; __half* binV16; float* binSb; __half* cellV16; float* cellSb;
-    unsigned char* wimg; float* cst;
-};
 
 int umma_build_weights(const float* fc1, const float* w0, const float* b0, const float* pff_g, const float* pff_b,
                        const float* w1, const float* b1, const float* ln1_g, const float* c0, const float* cb0,

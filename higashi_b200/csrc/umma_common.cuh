@@ -1,5 +1,5 @@
 // umma_common.cuh -- tcgen05 / TMEM / mbarrier helpers, shared-memory map and parameter block shared by the tensor-core
-// scorer kernels (score_umma.cu: one thread per row; score_umma2.cu: two threads per row).
+// kernels (score_umma.cu: the fused scorer; project_umma.cu: the token projection).
 #pragma once
 #include <cuda_fp16.h>
 
@@ -11,9 +11,6 @@
 #define UM_WG 4
 #define UM_THREADS (UM_WG * 128)
 #define UM_D 64
-#ifndef UM_ATT_PREFETCH
-#define UM_ATT_PREFETCH 0
-#endif
 
 // shared memory map (bytes).  Weight images (fp16, K-major SWIZZLE_128B, built on the host):
 //   [y_c | g] = ctx . [fc1c ; W0' fc1c]^T in ONE N=128 GEMM (see score_umma.cu), then W1c and C0; the high-accuracy variant
