@@ -447,17 +447,29 @@ def main():
         nbr0 = None if nbr is None else np.ascontiguousarray(nbr - 1, dtype=np.int32)
 
         def e2e_step(i):
+            # every step uploads its inputs (the packed contact CSR + kNN lists) from pinned host memory and reads its scores back.
+            # The upload of step i+1 is staged on its own stream while step i computes (hsg_stage_contacts / hsg_commit_contacts:
+            # the streaming pattern of a dataset that does not fit on the device), so its cost overlaps instead of adding up.
             c0 = (i % n_ranges) * cps
-            eng.ctx.set_contacts(h_rowptr.numpy(), h_col.numpy(), h_val.numpy())      # H2D of the step's inputs
+            if eng.ctx_staged:
+                eng.ctx.commit_contacts()                                                  # the H2D issued during the previous step
+            else:
+                eng.ctx.set_contacts(h_rowptr.numpy(), h_col.numpy(), h_val.numpy())      # first step: nothing to overlap with
             if nbr0 is not None:
-                eng.ctx.set_neighbors(nbr0, w)
+                eng.ctx.set_neighbors(nbr0, w)                                             # small: before the big copy occupies the H2D engine
+            eng.ctx.stage_contacts(h_rowptr.numpy(), h_col.numpy(), h_val.numpy())        # H2D of the NEXT step's inputs
+            eng.ctx_staged = True
             eng.ctx.impute_cells_host_ptr(c0, c0 + cps, h_out.data_ptr())             # compute + D2H of the result
+        eng.ctx_staged = False
         for i in range(min(args.warmup, 2)):
             e2e_step(i)
         barrier()
         t0 = time.perf_counter()
         for i in range(args.steps):
             e2e_step(args.warmup + i)
+        if eng.ctx_staged:
+            eng.ctx.commit_contacts()          # drain the last staged upload inside the timed region
+            eng.ctx_staged = False
         barrier()
         dt = time.perf_counter() - t0
         tt = torch.tensor([dt], device="cuda")

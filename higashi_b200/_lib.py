@@ -69,7 +69,7 @@ ACT_NONE, ACT_SIGMOID, ACT_SOFTPLUS = 0, 1, 2
 # every symbol include/hsg.h declares (tests check that the library exports all of them)
 EXPORTS = [
     "hsg_abi_version", "hsg_last_error", "hsg_create", "hsg_destroy", "hsg_set_dims", "hsg_set_weight",
-    "hsg_embed_table", "hsg_set_table", "hsg_set_contacts", "hsg_set_neighbors", "hsg_build_neighbors",
+    "hsg_embed_table", "hsg_set_table", "hsg_set_contacts", "hsg_stage_contacts", "hsg_commit_contacts", "hsg_set_neighbors", "hsg_build_neighbors",
     "hsg_set_pairs", "hsg_get_coordinates", "hsg_prepare", "hsg_impute_cells", "hsg_impute_cells_host",
     "hsg_fix_cell", "hsg_score_triplets", "hsg_launch_count", "hsg_last_timing", "hsg_set_profiling",
     "hsg_train_bind", "hsg_train_set_features", "hsg_score_fwd", "hsg_score_bwd", "hsg_train_options", "hsg_score_heads",
@@ -105,6 +105,8 @@ def load():
     lib.hsg_embed_table.argtypes = [p, i32, f32p, i64, i32, f32p, f32p, f32p]
     lib.hsg_set_table.argtypes = [p, i32, f32p, i64]
     lib.hsg_set_contacts.argtypes = [p, i64p, i32p, f32p, i64, i64]
+    lib.hsg_stage_contacts.argtypes = [p, i64p, i32p, f32p, i64, i64]
+    lib.hsg_commit_contacts.argtypes = [p]
     lib.hsg_set_neighbors.argtypes = [p, i32p, f32p, i32]
     lib.hsg_build_neighbors.argtypes = [p, f32p, i32, i32, i32p, f32p]
     lib.hsg_set_pairs.argtypes = [p, i32, i32p, i32, i32, i32p, i32, i64p, i64p]
@@ -205,6 +207,17 @@ class Context:
     def set_contacts(self, row_ptr, col, val):
         r, rp = _i64(row_ptr); c, cp = _i32(col); v, vp = _f32(val)
         self._check(self.lib.hsg_set_contacts(self.h, rp, cp, vp, r.size - 1, c.size))
+
+    def stage_contacts(self, row_ptr, col, val):
+        """Asynchronous upload of the NEXT contact matrix (own stream, second buffer set); the arrays must stay alive and
+        unchanged until commit_contacts()."""
+        r, rp = _i64(row_ptr); c, cp = _i32(col); v, vp = _f32(val)
+        self._staged_keep = (r, c, v)
+        self._check(self.lib.hsg_stage_contacts(self.h, rp, cp, vp, r.size - 1, c.size))
+
+    def commit_contacts(self):
+        self._check(self.lib.hsg_commit_contacts(self.h))
+        self._staged_keep = None
 
     def set_neighbors(self, nbr0, w):
         if nbr0 is None:

@@ -90,6 +90,9 @@ extern "C" int hsg_destroy(hsg_ctx* c) {
     for (int i = 0; i < HSG_W_COUNT; ++i) dev_free(c->w[i]);
     dev_free(c->E_cell); dev_free(c->E_bin); dev_free(c->d_bin_off); dev_free(c->d_bin_chrom);
     dev_free(c->row_ptr); dev_free(c->col); dev_free(c->val); dev_free(c->nbr); dev_free(c->nbr_w); dev_free(c->pairs);
+    dev_free(c->row_ptr2); dev_free(c->col2); dev_free(c->val2);
+    if (c->h2d_stream) cudaStreamDestroy(c->h2d_stream);
+    if (c->staged_ev) cudaEventDestroy(c->staged_ev);
     for (int i = 0; i < 8; ++i) if (c->ev[i]) cudaEventDestroy(c->ev[i]);
     for (int i = 0; i < 2; ++i) if (c->stage_ev[i]) cudaEventDestroy(c->stage_ev[i]);
     if (c->stream) cudaStreamDestroy(c->stream);
@@ -236,6 +239,47 @@ extern "C" int hsg_set_contacts(hsg_ctx* c, const int64_t* row_ptr, const int32_
     }
     HSG_CUDA(cudaStreamSynchronize(c->stream));
     c->n_rows = n_rows; c->nnz = nnz;
+    return 0;
+}
+
+extern "C" int hsg_stage_contacts(hsg_ctx* c, const int64_t* row_ptr, const int32_t* col, const float* val, int64_t n_rows,
+                                  int64_t nnz) {
+    CTX_GUARD(c);
+    HSG_CHECK(c->d > 0, "call hsg_set_dims first");
+    HSG_CHECK(row_ptr && (nnz == 0 || (col && val)), "null contact arrays");
+    HSG_CHECK(n_rows == (int64_t)c->n_cells * c->n_bins, "contacts: n_rows must be n_cells * n_bins");
+    HSG_CHECK(row_ptr[0] == 0 && row_ptr[n_rows] == nnz, "contacts: row_ptr does not span nnz");
+    HSG_CHECK(!c->staged, "hsg_stage_contacts: the previous staged matrix has not been committed");
+    if (!c->h2d_stream) {
+        HSG_CUDA(cudaStreamCreateWithFlags(&c->h2d_stream, cudaStreamNonBlocking));
+        HSG_CUDA(cudaEventCreateWithFlags(&c->staged_ev, cudaEventDisableTiming));
+    }
+    if (n_rows + 1 > c->cap_rows2) {
+        if (dev_alloc(&c->row_ptr2, (size_t)n_rows + 1)) return 1;
+        c->cap_rows2 = n_rows + 1;
+    }
+    if (nnz > c->cap_nnz2 || c->col2 == nullptr) {
+        if (dev_alloc(&c->col2, (size_t)nnz) || dev_alloc(&c->val2, (size_t)nnz)) return 1;
+        c->cap_nnz2 = nnz;
+    }
+    HSG_CUDA(cudaMemcpyAsync(c->row_ptr2, row_ptr, (size_t)(n_rows + 1) * sizeof(int64_t), cudaMemcpyHostToDevice, c->h2d_stream));
+    if (nnz > 0) {
+        HSG_CUDA(cudaMemcpyAsync(c->col2, col, (size_t)nnz * sizeof(int32_t), cudaMemcpyHostToDevice, c->h2d_stream));
+        HSG_CUDA(cudaMemcpyAsync(c->val2, val, (size_t)nnz * sizeof(float), cudaMemcpyHostToDevice, c->h2d_stream));
+    }
+    HSG_CUDA(cudaEventRecord(c->staged_ev, c->h2d_stream));
+    c->staged_rows = n_rows; c->staged_nnz = nnz; c->staged = true;
+    return 0;
+}
+
+extern "C" int hsg_commit_contacts(hsg_ctx* c) {
+    CTX_GUARD(c);
+    HSG_CHECK(c->staged, "hsg_commit_contacts without hsg_stage_contacts");
+    HSG_CUDA(cudaEventSynchronize(c->staged_ev));       // the staged copy has landed
+    HSG_CUDA(cudaDeviceSynchronize());                  // nothing queued may still read the current matrix
+    std::swap(c->row_ptr, c->row_ptr2); std::swap(c->col, c->col2); std::swap(c->val, c->val2);
+    std::swap(c->cap_rows, c->cap_rows2); std::swap(c->cap_nnz, c->cap_nnz2);
+    c->n_rows = c->staged_rows; c->nnz = c->staged_nnz; c->staged = false;
     return 0;
 }
 

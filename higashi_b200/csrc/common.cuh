@@ -72,6 +72,11 @@ struct hsg_ctx {
     int64_t* row_ptr = nullptr; int32_t* col = nullptr; float* val = nullptr;
     int64_t n_rows = 0, nnz = 0;
     int64_t cap_rows = 0, cap_nnz = 0;          // allocated capacity of the contact arrays (re-uploads reuse the buffers)
+    // second set of contact buffers: hsg_stage_contacts fills it on its own stream while the current set is in use,
+    // hsg_commit_contacts swaps the two (streaming datasets: the upload of the next block overlaps the imputation of this one)
+    int64_t* row_ptr2 = nullptr; int32_t* col2 = nullptr; float* val2 = nullptr;
+    int64_t cap_rows2 = 0, cap_nnz2 = 0, staged_rows = 0, staged_nnz = 0;
+    cudaStream_t h2d_stream = nullptr; cudaEvent_t staged_ev = nullptr; bool staged = false;
     // neighbours
     int32_t* nbr = nullptr; float* nbr_w = nullptr; int k1 = 1; bool weighted = false;
 

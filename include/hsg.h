@@ -101,6 +101,12 @@ int  hsg_set_table(hsg_ctx* ctx, int branch, const float* table, int64_t rows);
  * matrices as one CSR: row (cell, chrom j, local bin b) = cell*n_bins + bin_off[j] + b, columns local. */
 int  hsg_set_contacts(hsg_ctx* ctx, const int64_t* row_ptr, const int32_t* col, const float* val,
                       int64_t n_rows, int64_t nnz);
+/* streaming variant: hsg_stage_contacts copies the NEXT matrix into a second set of device buffers on its own stream and
+ * returns at once (the host arrays must stay untouched -- pinned memory makes the copy truly asynchronous -- until the
+ * commit); hsg_commit_contacts waits for that copy and swaps the two sets.  Imputation calls issued in between keep using
+ * the current matrix, so the upload of block i+1 overlaps the imputation of block i.                                    */
+int  hsg_stage_contacts(hsg_ctx* ctx, const int64_t* row_ptr, const int32_t* col, const float* val, int64_t n_rows, int64_t nnz);
+int  hsg_commit_contacts(hsg_ctx* ctx);
 /* replaces: weighted_info.npy = (cell_neighbor_list, weight_dict) (Higashi_wrapper.py:1520-1545, Impute.py:245)
  * nbr [n_cells,k1] 0-based cell ids (self first), w [n_cells,k1].  nbr == NULL => no neighbours (k1 = 1).   */
 int  hsg_set_neighbors(hsg_ctx* ctx, const int32_t* nbr, const float* w, int k1);
