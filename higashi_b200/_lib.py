@@ -75,6 +75,7 @@ EXPORTS = [
     "hsg_train_bind", "hsg_train_set_features", "hsg_score_fwd", "hsg_score_bwd", "hsg_train_options", "hsg_score_heads",
     "hsg_train_bind_recon", "hsg_recon_loss", "hsg_recon_apply", "hsg_train_set_dropout",
     "hsg_score_set_head_grads", "hsg_sample_batch", "hsg_sample_batch_begin", "hsg_sample_batch_end", "hsg_sampled_fetch",
+    "hsg_insulation",
 ]
 
 
@@ -135,6 +136,7 @@ def load():
     lib.hsg_recon_loss.argtypes = [p, f32p, f32p, p]
     lib.hsg_recon_apply.argtypes = [p, C.c_float, p]
     lib.hsg_train_set_dropout.argtypes = [p, i32, C.c_uint64]
+    lib.hsg_insulation.argtypes = [p, i32, p, i32, i32, i32, p, p, f32p, p, p]
     for name in EXPORTS:
         if name not in ("hsg_last_error", "hsg_launch_count", "hsg_abi_version"):
             getattr(lib, name).restype = i32
@@ -270,6 +272,24 @@ class Context:
 
     def score_triplets(self, x_dev_ptr, B, out_dev_ptr, stream=0):
         self._check(self.lib.hsg_score_triplets(self.h, C.c_void_p(x_dev_ptr), int(B), C.c_void_p(out_dev_ptr), C.c_void_p(stream)))
+
+    def insulation(self, sel_slot, scores_dev_ptr, n_batch, n, window_bins, tad_order, keep=None, discard=None, stream=0):
+        """scores on the DEVICE ([n_batch, P_total] block of impute_cells) -> (score float32 [n_batch, n], border uint8 [n_batch, n])."""
+        score = np.empty((n_batch, n), dtype=np.float32)
+        border = np.empty((n_batch, n), dtype=np.uint8)
+        kp = dp = None
+        if keep is not None:
+            keep = np.ascontiguousarray(keep, dtype=np.uint8)
+            assert keep.shape == (n,)
+            kp = keep.ctypes.data_as(C.c_void_p)
+        if discard is not None:
+            discard = np.ascontiguousarray(discard, dtype=np.uint8)
+            assert discard.shape == (n,)
+            dp = discard.ctypes.data_as(C.c_void_p)
+        self._check(self.lib.hsg_insulation(self.h, int(sel_slot), C.c_void_p(scores_dev_ptr), int(n_batch), int(window_bins),
+                                            int(tad_order), kp, dp, score.ctypes.data_as(C.POINTER(C.c_float)),
+                                            border.ctypes.data_as(C.c_void_p), C.c_void_p(stream)))
+        return score, border
 
     # ---- introspection
     def launch_count(self):

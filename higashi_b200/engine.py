@@ -109,3 +109,15 @@ class ScorerEngine:
         assert x_tensor.is_cuda and x_tensor.is_contiguous() and out_tensor.is_cuda
         self.ctx.score_triplets(x_tensor.data_ptr(), x_tensor.shape[0], out_tensor.data_ptr(), stream_ptr)
         return out_tensor
+
+    def insulation(self, slot, scores_tensor, window_bins, tad_order, keep=None, discard_rows=None, stream_ptr: int = 0):
+        """Single-cell insulation scores + TAD boundary flags of one chromosome from the score block on the device
+        (scTAD.py:91-104 without the n x n maps).  scores_tensor: CUDA float32 [n_batch, P]; discard_rows: bin indices."""
+        assert scores_tensor.is_cuda and scores_tensor.is_contiguous() and scores_tensor.shape[1] == self.P
+        n = int(self.num[1 + self.chroms[slot]])
+        disc = None
+        if discard_rows is not None:
+            disc = np.zeros(n, dtype=np.uint8)
+            disc[np.asarray(discard_rows, dtype=np.int64)] = 1
+        return self.ctx.insulation(slot, scores_tensor.data_ptr(), scores_tensor.shape[0], n, window_bins, tad_order, keep, disc,
+                                   stream_ptr)

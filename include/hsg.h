@@ -210,6 +210,19 @@ int  hsg_train_bind_recon(hsg_ctx* ctx, int64_t off_reverse_w, int64_t off_recon
 int  hsg_recon_loss(hsg_ctx* ctx, float* loss_host, float* gnorm_w0_host, void* stream);
 int  hsg_recon_apply(hsg_ctx* ctx, float scale, void* stream);
 
+/* ---- first consumer on the device ----------------------------------------
+ * replaces: the per-cell body of scTAD.gen_tad (scTAD.py:91-104) for the cells of one score block:
+ *   m[x, y] += proba ; m = m + m^T ; m *= mask ; sqrt_norm (Higashi_analysis.py:581-588) ;
+ *   insulation_score (Higashi_TAD.py:7-19) ; score[discard_rows] = 1 ; call_tads (Higashi_TAD.py:22-27).
+ * scores_dev: DEVICE float [n_batch, P_total], the block hsg_impute_cells wrote (row = cell, leading dimension = the total
+ * pair count of hsg_set_pairs); sel_slot picks the chromosome.  window_bins = int(window_ins / res), tad_order =
+ * int(window_tad / res / 2).  keep_host uint8 [n] (1 = bin kept, i.e. the diagonal of scTAD's `mask`; NULL = all kept),
+ * discard_host uint8 [n] (1 = row of discard_rows; NULL = none).  Outputs (host): score float [n_batch, n],
+ * border uint8 [n_batch, n] (1 where call_tads reports a boundary).  The n x n maps are never materialised.           */
+int  hsg_insulation(hsg_ctx* ctx, int sel_slot, const float* scores_dev, int n_batch, int window_bins, int tad_order,
+                    const unsigned char* keep_host, const unsigned char* discard_host, float* score_out_host,
+                    unsigned char* border_out_host, void* stream);
+
 /* ---- introspection ------------------------------------------------------------------------ */
 /* number of kernels this library launched since the context was created (bench.py gpu_launches) */
 int64_t hsg_launch_count(hsg_ctx* ctx);

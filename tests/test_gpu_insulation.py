@@ -1,0 +1,71 @@
+"""GPU parity of the on-device insulation score / TAD boundary reduction (hsg_insulation) against the golden
+vectors minted from the reference's own functions and against the CPU oracle on imputed scores."""
+import numpy as np
+import pytest
+import torch
+
+from tests._util import FixtureDataset, load
+
+pytestmark = pytest.mark.gpu
+
+TOL = 2e-6      # scores are stored as float32; the reduction itself runs in fp64
+
+
+@pytest.mark.parametrize("tag", ["a", "b", "c"])
+def test_insulation_golden(tag):
+    from higashi_b200.engine import ScorerEngine
+    g = load("insulation.npz")
+    n, w_ins, w_tad = [int(v) for v in g["%s/cfg" % tag]]
+    coords, proba = g["%s/coords" % tag], g["%s/proba" % tag]
+    band = int((coords[:, 1] - coords[:, 0]).max())
+    eng = ScorerEngine(0)
+    eng.ctx.set_dims(64, proba.shape[0], [11, n], 1)
+    eng.num = [proba.shape[0], 11, n]
+    P = eng.set_pairs([1], 1, band + 1)
+    assert P == len(coords) and np.array_equal(eng.coordinates(0), coords)
+    scores = torch.from_numpy(proba).cuda().contiguous()
+    score, border = eng.insulation(0, scores, w_ins, w_tad, g["%s/keep" % tag], g["%s/discard" % tag])
+    np.testing.assert_allclose(score, g["%s/score" % tag], atol=TOL, rtol=0)
+    assert np.array_equal(border, g["%s/border" % tag])
+    # no mask / no discarded rows
+    from oracle import insulation as OX
+    score, border = eng.insulation(0, scores, w_ins, w_tad)
+    for c in range(proba.shape[0]):
+        s_ref, b_ref = OX.cell_profile(coords, proba[c], n, np.ones(n), [], w_ins, w_tad)
+        np.testing.assert_allclose(score[c], s_ref, atol=TOL, rtol=0)
+        assert np.array_equal(border[c], b_ref)
+    eng.close()
+
+
+def test_insulation_after_imputation():
+    """impute -> insulation without the scores leaving the device, against the oracle run on a host copy of the same scores."""
+    from higashi_b200 import engine as E
+    from higashi_b200.scTAD import gen_tad_scores
+    from oracle import insulation as OX
+    g = load("impute_k4_r0.npz")
+    ds = FixtureDataset(g)
+    sd = {k[3:]: v for k, v in g.items() if k.startswith("sd/")}
+    eng = E.ScorerEngine(0)
+    eng.load_model(sd, ds.num, feats=ds.feats, cell_feats=ds.cell_feats)
+    eng.set_contacts(ds.csr)
+    eng.set_neighbors(g["knn/nbr"], g["knn/w"])
+    chroms = list(range(len(ds.bins)))
+    eng.set_pairs(chroms, 1, 12)
+    eng.prepare(E.PREC_FP32, 0, E.ACT_SIGMOID)
+    host = eng.impute_to_host(0, ds.n_cells)
+    off = 0
+    for slot, j in enumerate(chroms):
+        n = ds.bins[j]
+        keep = np.ones(n, dtype=np.uint8)
+        keep[n // 3] = 0
+        discard = np.array([1, n - 2])
+        score, border, bulk = gen_tad_scores(eng, slot, 0, ds.n_cells, 6.0, 8.0, 1.0, keep, discard, cells_per_call=3)
+        coords = eng.coordinates(slot)
+        P = len(coords)
+        np.testing.assert_allclose(bulk, host[:, off:off + P].astype(np.float64).sum(0), rtol=1e-6)
+        for c in range(ds.n_cells):
+            s_ref, b_ref = OX.cell_profile(coords, host[c, off:off + P], n, keep, discard, 6, 4)
+            np.testing.assert_allclose(score[c], s_ref, atol=TOL, rtol=0)
+            assert np.array_equal(border[c], b_ref)
+        off += P
+    eng.close()
