@@ -9,8 +9,17 @@
 //
 // The matrix is never built: a pair (a < b) with normalised value v contributes v to the numerator of the bins
 // i in [max(a+1, b-w), min(a+w, b-1)] (b <= n-2, the reference's column bound) and 2v to the denominator of the bins
-// i in [b-w, a+w] -- two range updates on per-cell difference arrays (fp64 atomics), then one prefix sum per cell.
+// i in [b-w, a+w] -- two range updates on per-cell difference arrays, then one prefix sum per cell.
+//
+// The difference arrays hold 64-bit FIXED-POINT integers (v * 2^40, v <= 1 after sqrt_norm): integer atomics make the result
+// independent of the order the atomics land in, and -- what the boundary calls need -- sums that are mathematically zero or
+// mathematically equal come out exactly zero / exactly equal (the reference's last two bins have an empty numerator block and
+// score exactly 0, which `score > 0` then rejects; a floating-point prefix sum would leave a 1e-17 residue there).
+// Wrap-around arithmetic is exact as long as every window sum fits: (2w+1)^2 * 2 * 2^40 < 2^63  <=>  w <= 1000.
 #include "common.cuh"
+
+#define INS_FIX_SCALE 1099511627776.0      // 2^40
+__device__ __forceinline__ void fix_add(unsigned long long* p, long long q) { atomicAdd(p, (unsigned long long)q); }
 
 // rowsum[cell][a] += v, rowsum[cell][b] += v   (symmetric matrix, masked rows / columns dropped)
 __global__ void ins_rowsum_kernel(const float* __restrict__ scores, int64_t ld, int64_t off, const int2* __restrict__ pairs, int64_t P,
@@ -30,7 +39,7 @@ __global__ void ins_rowsum_kernel(const float* __restrict__ scores, int64_t ld, 
 // range updates of the difference arrays: diff[cell][0][.] numerator, diff[cell][1][.] denominator (n + 1 entries each)
 __global__ void ins_diff_kernel(const float* __restrict__ scores, int64_t ld, int64_t off, const int2* __restrict__ pairs, int64_t P,
                                 int goff, int n, int n_cells, int w, const unsigned char* __restrict__ keep,
-                                const double* __restrict__ rowsum, double* __restrict__ diff) {
+                                const double* __restrict__ rowsum, unsigned long long* __restrict__ diff) {
     const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     const int cell = blockIdx.y;
     if (i >= P || cell >= n_cells) return;
@@ -43,36 +52,38 @@ __global__ void ins_diff_kernel(const float* __restrict__ scores, int64_t ld, in
     if (raw == 0.0 || !(ra > 0.0) || !(rb > 0.0)) return;          // sqrt_norm: division by a zero coverage -> 0
     const double v = raw / sqrt(ra) / sqrt(rb);
     if (!isfinite(v)) return;
-    double* num = diff + (int64_t)cell * 2 * (n + 1);
-    double* den = num + (n + 1);
+    const long long q = llrint(v * INS_FIX_SCALE);
+    if (q == 0) return;
+    unsigned long long* num = diff + (int64_t)cell * 2 * (n + 1);
+    unsigned long long* den = num + (n + 1);
     if (a == b) {                                                    // a diagonal entry counts once, in the denominator only
         const int lo = max(0, a - w), hi = min(n - 1, a + w);
-        atomicAdd(den + lo, 2.0 * v); atomicAdd(den + hi + 1, -2.0 * v);      // m + m^T doubles the diagonal
+        fix_add(den + lo, 2 * q); fix_add(den + hi + 1, -2 * q);     // m + m^T doubles the diagonal
         return;
     }
     {   // denominator: both (a, b) and (b, a) lie inside the window of bin i  <=>  b - w <= i <= a + w
         const int lo = max(0, b - w), hi = min(n - 1, a + w);
-        if (lo <= hi) { atomicAdd(den + lo, 2.0 * v); atomicAdd(den + hi + 1, -2.0 * v); }
+        if (lo <= hi) { fix_add(den + lo, 2 * q); fix_add(den + hi + 1, -2 * q); }
     }
     if (b <= n - 2) {   // numerator: a in [i - w, i), b in [i + 1, min(n - 1, i + w + 1))
         const int lo = max(a + 1, b - w), hi = min(a + w, b - 1);
-        if (lo <= hi) { atomicAdd(num + lo, v); atomicAdd(num + hi + 1, -v); }
+        if (lo <= hi) { fix_add(num + lo, q); fix_add(num + hi + 1, -q); }
     }
 }
 
 // one block per cell: prefix sums, ratio, discarded rows, boundary calls
-__global__ void ins_finish_kernel(const double* __restrict__ diff, int n, int order, const unsigned char* __restrict__ discard,
+__global__ void ins_finish_kernel(const unsigned long long* __restrict__ diff, int n, int order, const unsigned char* __restrict__ discard,
                                   float* __restrict__ score_out, unsigned char* __restrict__ border_out, double* __restrict__ score64) {
     const int cell = blockIdx.x;
-    const double* num = diff + (int64_t)cell * 2 * (n + 1);
-    const double* den = num + (n + 1);
+    const unsigned long long* num = diff + (int64_t)cell * 2 * (n + 1);
+    const unsigned long long* den = num + (n + 1);
     double* sc = score64 + (int64_t)cell * n;
-    if (threadIdx.x == 0) {                       // n is a few thousand: a serial fp64 scan keeps the summation order fixed
-        double sn = 0.0, sd = 0.0;
+    if (threadIdx.x == 0) {                       // n is a few thousand: one serial (exact, integer) scan per cell
+        unsigned long long sn = 0, sd = 0;
         for (int i = 0; i < n; ++i) {
             sn += num[i]; sd += den[i];
-            double v = sn / sd;
-            if (isnan(v) || sd == 0.0) v = 1.0;   // 0 / 0 -> nan -> 1 (the numerator is a subset of the denominator)
+            double v = (double)(long long)sn / (double)(long long)sd;
+            if (isnan(v) || sd == 0) v = 1.0;     // 0 / 0 -> nan -> 1 (the numerator is a subset of the denominator)
             if (discard && discard[i]) v = 1.0;
             sc[i] = v;
         }
@@ -97,10 +108,12 @@ extern "C" int hsg_insulation(hsg_ctx* c, int sel_slot, const float* scores_dev,
     HSG_CUDA(cudaSetDevice(c->device));
     HSG_CHECK(sel_slot >= 0 && sel_slot < (int)c->sel_chroms.size(), "bad chromosome slot (hsg_set_pairs first)");
     HSG_CHECK(scores_dev && n_batch > 0 && window_bins > 0 && tad_order >= 0 && score_out_host && border_out_host, "bad arguments");
+    HSG_CHECK(window_bins <= 1000, "insulation window above 1000 bins");
     cudaStream_t s = (cudaStream_t)stream;
     const int chrom = c->sel_chroms[sel_slot], n = c->bins[chrom], goff = c->bin_off[chrom];
     const int64_t off = c->sel_off[sel_slot], P = c->sel_P[sel_slot];
-    double *rowsum = nullptr, *diff = nullptr, *sc64 = nullptr;
+    double *rowsum = nullptr, *sc64 = nullptr;
+    unsigned long long* diff = nullptr;
     float* d_score = nullptr;
     unsigned char *d_border = nullptr, *d_keep = nullptr, *d_discard = nullptr;
     auto cleanup = [&]() {
@@ -109,12 +122,12 @@ extern "C" int hsg_insulation(hsg_ctx* c, int sel_slot, const float* scores_dev,
     const size_t nb = (size_t)n_batch;
 #define INS_CUDA(x) do { cudaError_t e_ = (x); if (e_ != cudaSuccess) { cleanup(); hsg_set_error(std::string("CUDA error: ") + cudaGetErrorString(e_)); return 1; } } while (0)
     INS_CUDA(cudaMalloc((void**)&rowsum, nb * n * sizeof(double)));
-    INS_CUDA(cudaMalloc((void**)&diff, nb * 2 * (n + 1) * sizeof(double)));
+    INS_CUDA(cudaMalloc((void**)&diff, nb * 2 * (n + 1) * sizeof(unsigned long long)));
     INS_CUDA(cudaMalloc((void**)&sc64, nb * n * sizeof(double)));
     INS_CUDA(cudaMalloc((void**)&d_score, nb * n * sizeof(float)));
     INS_CUDA(cudaMalloc((void**)&d_border, nb * n));
     INS_CUDA(cudaMemsetAsync(rowsum, 0, nb * n * sizeof(double), s));
-    INS_CUDA(cudaMemsetAsync(diff, 0, nb * 2 * (n + 1) * sizeof(double), s));
+    INS_CUDA(cudaMemsetAsync(diff, 0, nb * 2 * (n + 1) * sizeof(unsigned long long), s));
     if (keep_host) {
         INS_CUDA(cudaMalloc((void**)&d_keep, n));
         INS_CUDA(cudaMemcpyAsync(d_keep, keep_host, n, cudaMemcpyHostToDevice, s));
