@@ -12,9 +12,15 @@
 #define HSG_DK 16
 #define HSG_HD 128                 // n_head * d_k = n_head * d_v   (Higashi_wrapper.py:834-845)
 #define HSG_LN_EPS 1e-5f
-// cell cross-term table XS [token][16]: floats 0..7 = qcK, 8..15 = kcQ, each group stored as 4 (head i, head i+4) pairs so
-// that the scorer lane that owns halves of heads i and i+4 reads both with one 64-bit load
-#define HSG_XS_POS(h) ((((h) & 3) << 1) | ((h) >> 2))
+// cell cross-term table XS [token][16]: floats 0..7 = qcK[head], 8..15 = kcQ[head]
+#define HSG_XS_POS(h) (h)
+// 16-bit Q / K / V rows (128 halves = 16 chunks of 16 bytes; head h = logical chunks 2h, 2h + 1) are stored with the chunks
+// permuted: position h holds the first and position 8 + h the second half of head h.  Scorer lane j of a row reads positions j
+// and 8 + j: the 8 lanes of a row still cover two fully used 128-byte lines per load, and every lane owns ONE complete head
+// (no cross-lane reduction of the logits, one softmax per lane).  The ctx A tile keeps the permuted order; the K columns of
+// the fc1 weight image are permuted to match (umma_build_weights).
+#define HSG_CHUNK_POS(c) ((((c) >> 1)) + (((c) & 1) << 3))
+#define HSG_COL_POS(col) (HSG_CHUNK_POS((col) >> 3) * 8 + ((col) & 7))
 // high-accuracy scorer tables: a 128-float Q / K / V row is stored as [4 quads][8 heads][4 floats], so that the 8 lanes of a row
 // (lane = head) read one contiguous 128-byte line per 128-bit load.  Column c = 16 h + 4 e + r  ->  32 e + 4 h + r
 #define HSG_HI_POS(c) ((((c) >> 2) & 3) * 32 + ((c) >> 4) * 4 + ((c) & 3))

@@ -530,7 +530,7 @@ __global__ void __launch_bounds__(256) token_project_kernel(
             uint4 pk;
             pk.x = *reinterpret_cast<uint32_t*>(&h0); pk.y = *reinterpret_cast<uint32_t*>(&h1);
             pk.z = *reinterpret_cast<uint32_t*>(&h2); pk.w = *reinterpret_cast<uint32_t*>(&h3);
-            *reinterpret_cast<uint4*>(QK16 + tok * 256 + ch * 8) = pk;
+            *reinterpret_cast<uint4*>(QK16 + tok * 256 + (ch & 16) * 8 + HSG_CHUNK_POS(ch & 15) * 8) = pk;      // head-per-lane chunk order
         }
         // cross terms with the cell token: qcK[h] = Q_cell,h . K_b,h / 4 ; kcQ[h] = Q_b,h . K_cell,h / 4
         {

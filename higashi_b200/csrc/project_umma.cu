@@ -11,7 +11,7 @@
 //   * GEMM2  D2[128 x 256] = xhat . [Wq' ; Wk']^T (K = 64)  with the two LayerNorm gains folded into the weights and the
 //     LayerNorm biases folded into the output bias: Q|K come out of a single N = 256 MMA;
 //   * epilogue 2 adds the bias, accumulates the cell cross terms against the cell's K / Q vectors (staged in shared memory),
-//     rounds to fp16 (Q pre-scaled by log2(e)/4, see score_umma.cu) into a swizzled staging tile and the CTA copies the tile
+//     rounds to fp16 (Q pre-scaled by log2(e)/4, chunks in HSG_CHUNK_POS order, see score_umma.cu) into a swizzled staging tile and the CTA copies the tile
 //     out with fully coalesced 128-bit stores (a tile's Q|K rows are one contiguous 64 KB block of the table).
 // fp16 operands / fp32 accumulation: measured effect on the final score 1.9e-4 -> 2.0e-4 (scripts/bf16_emulation.py).
 #include "umma_common.cuh"
@@ -180,7 +180,7 @@ __global__ void __launch_bounds__(128, 2) project_umma_kernel(ProjParams p) {
                         cr = fmaf(v[q], kk[q], cr);
                     }
                     if (c8 < 2) crA += cr; else crB += cr;
-                    sts128(a_chunk_addr(a_base, tid, cc * 4 + c8), pack_h2(v[0] * qs, v[1] * qs), pack_h2(v[2] * qs, v[3] * qs),
+                    sts128(a_chunk_addr(a_base, tid, HSG_CHUNK_POS(cc * 4 + c8)), pack_h2(v[0] * qs, v[1] * qs), pack_h2(v[2] * qs, v[3] * qs),
                            pack_h2(v[4] * qs, v[5] * qs), pack_h2(v[6] * qs, v[7] * qs));
                 }
                 // half 0: kcQ = Q_b . K_cell -> XS[8 + h] ; half 1: qcK = Q_cell . K_b -> XS[h]

@@ -85,7 +85,6 @@ __global__ void __launch_bounds__(UM_THREADS, 1) score_umma_kernel(UmmaParams p)
             if constexpr (HI) {
                 // high-accuracy variant: fp32 Q/K/V tables, fp32 dot products and ctx, one fp16 rounding of ctx
                 const int h = lane & 7, rsub = lane >> 3;
-                const int cA = h * 2 + (h >> 2), cB = h * 2 + 1 - (h >> 2);
                 const float4* QK4 = reinterpret_cast<const float4*>(p.QK32);
                 const float4* BV4 = reinterpret_cast<const float4*>(p.binV32);
                 // rows are stored [quad e][head h][4 floats] (HSG_HI_POS): the 8 lanes of a row read 128 contiguous bytes per load
@@ -132,10 +131,9 @@ __global__ void __launch_bounds__(UM_THREADS, 1) score_umma_kernel(UmmaParams p)
                         float2 c1 = __ffma2_rn(wb2, make_float2(bv.z, bv.w), __fmul2_rn(wa2, make_float2(av.z, av.w)));
                         pk[e * 2] = pack_h2(c0.x, c0.y); pk[e * 2 + 1] = pack_h2(c1.x, c1.y);
                     }
-                    // chunk order swapped for h >= 4 (bank-conflict-free stores, see the fast variant)
-                    const bool sw = (h & 4) != 0;         // selects, not a branch: all lanes store together
-                    sts128(a_chunk_addr(a_base, arow, cA), sw ? pk[4] : pk[0], sw ? pk[5] : pk[1], sw ? pk[6] : pk[2], sw ? pk[7] : pk[3]);
-                    sts128(a_chunk_addr(a_base, arow, cB), sw ? pk[0] : pk[4], sw ? pk[1] : pk[5], sw ? pk[2] : pk[6], sw ? pk[3] : pk[7]);
+                    // head h = chunk positions h and 8 + h (HSG_CHUNK_POS): the 8 lanes of a row hit 8 distinct swizzle slots
+                    sts128(a_chunk_addr(a_base, arow, h), pk[0], pk[1], pk[2], pk[3]);
+                    sts128(a_chunk_addr(a_base, arow, 8 + h), pk[4], pk[5], pk[6], pk[7]);
                 }
             } else {
                 const uint32_t tokbase = (uint32_t)cb * (uint32_t)p.n_bins;
@@ -348,6 +346,12 @@ int umma_build_weights(const float* fc1, const float* w0, const float* b0, const
             for (int j = 0; j < d; ++j) acc += (double)w0f[(size_t)n * d + j] * fc1c[(size_t)j * HSG_HD + k];
             comb[(size_t)(d + n) * HSG_HD + k] = (float)acc;
         }
+    {   // the ctx A tile arrives with its 16-byte chunks in HSG_CHUNK_POS order: permute the K columns of the image to match
+        std::vector<float> perm(comb.size());
+        for (int n = 0; n < 2 * d; ++n)
+            for (int k = 0; k < HSG_HD; ++k) perm[(size_t)n * HSG_HD + HSG_COL_POS(k)] = comb[(size_t)n * HSG_HD + k];
+        comb.swap(perm);
+    }
     swizzle_image(comb.data(), 2 * d, HSG_HD, reinterpret_cast<__half*>(wimg_host + SMF_B_FC1));
     for (size_t i = 0; i < comb.size(); ++i) lo[i] = comb[i] - __half2float(__float2half_rn(comb[i]));
     swizzle_image(lo.data(), 2 * d, HSG_HD, reinterpret_cast<__half*>(wimg_host + SMH_B_FC1_LO));
@@ -379,7 +383,7 @@ __global__ void convert_static_kernel(const float* __restrict__ V, const float* 
                                       long long rows, int d, __half* __restrict__ V16, float* __restrict__ Sb, float* __restrict__ V32p) {
     long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (i < rows * HSG_HD) {
-        V16[i] = __float2half_rn(V[i]);
+        { const int cc = (int)(i & (HSG_HD - 1)); V16[i - cc + HSG_COL_POS(cc)] = __float2half_rn(V[i]); }     // head-per-lane chunk order
         if (V32p) { const int cc = (int)(i & (HSG_HD - 1)); V32p[i - cc + HSG_HI_POS(cc)] = V[i]; }
     }
     if (i < rows * d) { long long r = i / d; int f = (int)(i - r * d); Sb[((long long)(f >> 2) * rows + r) * 4 + (f & 3)] = ln1_b[f] - S[i]; }

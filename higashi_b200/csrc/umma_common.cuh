@@ -183,88 +183,75 @@ __device__ __forceinline__ void masked_row_fast(float la, float lb, float& wa, f
     wb = 1.0f - wa;
     if (fmaxf(la, lb) < -20.f) masked_row_exact(la, lb, wa, wb);
 }
-__device__ __forceinline__ void masked_row_fast2(float laA, float lbA, float laB, float lbB, float& waA, float& wbA, float& waB,
-                                                 float& wbB) {
-    waA = rcp_approx(1.0f + ex2_approx(lbA - laA)); wbA = 1.0f - waA;
-    waB = rcp_approx(1.0f + ex2_approx(lbB - laB)); wbB = 1.0f - waB;
-    if (fminf(fmaxf(laA, lbA), fmaxf(laB, lbB)) < -20.f) {
-        masked_row_exact(laA, lbA, waA, wbA);
-        masked_row_exact(laB, lbB, waB, wbB);
-    }
-}
 
 struct UmmaParams;
 // Attention of one token row-tile (fast variant), T = token position (0 cell, 1 bin_i, 2 bin_j): row T attends to the two
-// other tokens.  Lane mapping: lane = (row-in-group rho = lane>>3, head h = lane&7); a warp walks its own 32 rows four at a
-// time, so the 8 lanes of a row read one contiguous 256-byte table row (coalesced).  Each lane owns the two 16-byte chunks
-// of head h; lanes with h >= 4 handle them in swapped order so that the 8 lanes of a quarter-warp hit 8 distinct swizzle
-// slots when storing (no 2-way bank conflict).  s_pr: the (bin_i, bin_j) pairs of the warpgroup's 128 rows in shared memory;
-// the calling warp handles rows row0 .. row0 + 4 NIT - 1.
+// other tokens.  Lane mapping: lane = (row-in-group rho = lane>>3, head j = lane&7); a warp walks its own 32 rows four at a
+// time.  The 16-bit Q / K / V rows are stored with their 16-byte chunks in HSG_CHUNK_POS order (position j = first half,
+// position 8 + j = second half of head j), so lane j reads positions j and 8 + j: the 8 lanes of a row cover two fully used
+// 128-byte lines per load AND every lane owns one complete head -- its logit needs no cross-lane reduction and the softmax
+// is computed once per (row, head).  The ctx chunks go to the same positions of the A tile (8 lanes of a row = 8 distinct
+// swizzle slots, conflict-free); fc1's K columns are permuted to match.  s_pr: the (bin_i, bin_j) pairs of the warpgroup's
+// 128 rows in shared memory; the calling warp handles rows row0 .. row0 + 4 NIT - 1.
 __device__ __forceinline__ uint4 ldg_nc_u4_volatile(const uint4* p) {
     uint4 v;
     asm volatile("ld.global.nc.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(p));
     return v;
 }
-__device__ __forceinline__ float2 ldg_nc_f32x2_volatile(const float* p) {
-    float2 v;
-    asm volatile("ld.global.nc.v2.f32 {%0, %1}, [%2];" : "=f"(v.x), "=f"(v.y) : "l"(p));
+__device__ __forceinline__ float ldg_nc_f32_volatile(const float* p) {
+    float v;
+    asm volatile("ld.global.nc.f32 %0, [%1];" : "=f"(v) : "l"(p));
     return v;
 }
 // everything one lane needs from the token tables for one row of one token position
 struct AttRow {
-    uint4 qA, qB, kA, kB;     // T != 0: this lane's chunks of Q[tq] and K[tk] ;  T == 0: V[bi] in qA/qB
+    uint4 qA, qB, kA, kB;     // T != 0: this lane's head of Q[tq] and K[tk] ;  T == 0: V[bi] in qA/qB
     uint4 bA, bB;             // V of the "b" token
-    float laA, laB, lbA, lbB; // logits that come from the cross-term table
-    int rw;
+    float la, lb;             // logits that come from the cross-term table
 };
 template <int T>
-__device__ __forceinline__ void att_load(AttRow& r, int rw, const int2* s_pr, const uint4* QKj, const float* XSa, const uint4* BVj,
+__device__ __forceinline__ void att_load(AttRow& r, int rw, const int2* s_pr, const uint4* QKj, const float* XSj, const uint4* BVj,
                                          uint32_t tokbase) {
     const int2 pr = s_pr[rw];
     const uint32_t ti = tokbase + (uint32_t)pr.x, tj = tokbase + (uint32_t)pr.y;
-    r.rw = rw;
     if (T == 0) {
-        const float2 la = ldg_nc_f32x2_volatile(XSa + ti * 16u), lb = ldg_nc_f32x2_volatile(XSa + tj * 16u);   // (head hA, head 4 + hA)
-        r.laA = la.x; r.laB = la.y; r.lbA = lb.x; r.lbB = lb.y;
+        r.la = ldg_nc_f32_volatile(XSj + ti * 16u); r.lb = ldg_nc_f32_volatile(XSj + tj * 16u);
         r.qA = ldg_nc_u4_volatile(BVj + (uint32_t)pr.x * 16u); r.qB = ldg_nc_u4_volatile(BVj + (uint32_t)pr.x * 16u + 8);
         r.bA = ldg_nc_u4_volatile(BVj + (uint32_t)pr.y * 16u); r.bB = ldg_nc_u4_volatile(BVj + (uint32_t)pr.y * 16u + 8);
     } else {
         const uint32_t tq = (T == 1) ? ti : tj, tk = (T == 1) ? tj : ti, bv = (uint32_t)((T == 1) ? pr.y : pr.x);
-        const float2 la = ldg_nc_f32x2_volatile(XSa + tq * 16u);
-        r.laA = la.x; r.laB = la.y;
+        r.la = ldg_nc_f32_volatile(XSj + tq * 16u);
         r.qA = ldg_nc_u4_volatile(QKj + tq * 32u); r.qB = ldg_nc_u4_volatile(QKj + tq * 32u + 8);
         r.kA = ldg_nc_u4_volatile(QKj + tk * 32u + 16); r.kB = ldg_nc_u4_volatile(QKj + tk * 32u + 24);
         r.bA = ldg_nc_u4_volatile(BVj + bv * 16u); r.bB = ldg_nc_u4_volatile(BVj + bv * 16u + 8);
     }
 }
+// st_addr: shared-memory address of chunk position j of this row in the A tile; position 8 + j is one K atom (16 KB) further
 template <int T>
-__device__ __forceinline__ void att_compute(const AttRow& r, uint4 vcA, uint4 vcB, uint32_t a_base, int j) {
-    float laA = r.laA, laB = r.laB, lbA, lbB;
+__device__ __forceinline__ void att_compute(const AttRow& r, uint4 vcA, uint4 vcB, uint32_t st_addr) {
+    float la = r.la, lb;
     uint4 aA, aB;
     if (T == 0) {
-        lbA = r.lbA; lbB = r.lbB; aA = r.qA; aB = r.qB;
+        lb = r.lb; aA = r.qA; aB = r.qB;
     } else {
         aA = vcA; aB = vcB;
         __half2 accA = __hmul2(u2h(r.qA.x), u2h(r.kA.x)), accB = __hmul2(u2h(r.qB.x), u2h(r.kB.x));
         accA = __hfma2(u2h(r.qA.y), u2h(r.kA.y), accA); accB = __hfma2(u2h(r.qB.y), u2h(r.kB.y), accB);
         accA = __hfma2(u2h(r.qA.z), u2h(r.kA.z), accA); accB = __hfma2(u2h(r.qB.z), u2h(r.kB.z), accB);
         accA = __hfma2(u2h(r.qA.w), u2h(r.kA.w), accA); accB = __hfma2(u2h(r.qB.w), u2h(r.kB.w), accB);
-        float2 fA = __half22float2(accA), fB = __half22float2(accB);
-        float pA = fA.x + fA.y, pB = fB.x + fB.y;
-        pA += __shfl_xor_sync(0xffffffffu, pA, 1); pB += __shfl_xor_sync(0xffffffffu, pB, 1);
-        lbA = pA; lbB = pB;                      // the Q rows carry log2(e) / 4
+        const float2 fA = __half22float2(accA), fB = __half22float2(accB);
+        lb = (fA.x + fA.y) + (fB.x + fB.y);      // the Q rows carry log2(e) / 4
     }
-    float waA, wbA, waB, wbB;
-    masked_row_fast2(laA, lbA, laB, lbB, waA, wbA, waB, wbB);
+    float wa, wb;
+    masked_row_fast(la, lb, wa, wb);
     const uint4 bA = r.bA, bB = r.bB;
-    const __half2 wa2 = __float2half2_rn(waA), wb2 = __float2half2_rn(wbA);
-    sts128(a_chunk_addr(a_base, r.rw, j),
+    const __half2 wa2 = __float2half2_rn(wa), wb2 = __float2half2_rn(wb);
+    sts128(st_addr,
            h2u(__hfma2(wb2, u2h(bA.x), __hmul2(wa2, u2h(aA.x)))), h2u(__hfma2(wb2, u2h(bA.y), __hmul2(wa2, u2h(aA.y)))),
            h2u(__hfma2(wb2, u2h(bA.z), __hmul2(wa2, u2h(aA.z)))), h2u(__hfma2(wb2, u2h(bA.w), __hmul2(wa2, u2h(aA.w)))));
-    const __half2 wc2 = __float2half2_rn(waB), wd2 = __float2half2_rn(wbB);
-    sts128(a_chunk_addr(a_base, r.rw, 8 + j),
-           h2u(__hfma2(wd2, u2h(bB.x), __hmul2(wc2, u2h(aB.x)))), h2u(__hfma2(wd2, u2h(bB.y), __hmul2(wc2, u2h(aB.y)))),
-           h2u(__hfma2(wd2, u2h(bB.z), __hmul2(wc2, u2h(aB.z)))), h2u(__hfma2(wd2, u2h(bB.w), __hmul2(wc2, u2h(aB.w)))));
+    sts128(st_addr + 16384u,
+           h2u(__hfma2(wb2, u2h(bB.x), __hmul2(wa2, u2h(aB.x)))), h2u(__hfma2(wb2, u2h(bB.y), __hmul2(wa2, u2h(aB.y)))),
+           h2u(__hfma2(wb2, u2h(bB.z), __hmul2(wa2, u2h(aB.z)))), h2u(__hfma2(wb2, u2h(bB.w), __hmul2(wa2, u2h(aB.w)))));
 }
 // Software-pipelined: the table rows of row group it + 1 are requested (volatile loads, the compiler keeps the order) before the
 // math of row group it, so one L2 round trip overlaps one group's compute instead of stalling every loop trip.
@@ -272,26 +259,28 @@ template <int T, int NIT>
 __device__ __forceinline__ void attention_fast(const __half* __restrict__ QK16, const float* __restrict__ XS,
                                                const __half* __restrict__ binV16, const __half* __restrict__ cellV16,
                                                const int2* s_pr, int lane, int row0, uint32_t a_base, uint32_t tokbase, int cell) {
-    // Lane j = lane & 7 of a row owns the 16-byte chunks j and 8 + j of the 256-byte Q / K / V rows, i.e. one half of head
-    // hA = j >> 1 and one half of head hB = 4 + (j >> 1): every warp-level 128-bit load then covers four fully used 128-byte
-    // lines.  The two lanes that share a head add their partial dot products with one shuffle.
-    const int j = lane & 7, rsub = lane >> 3, hA = j >> 1;
+    const int j = lane & 7, rsub = lane >> 3;
     const uint4* QKj = reinterpret_cast<const uint4*>(QK16) + j;
     const uint4* BVj = reinterpret_cast<const uint4*>(binV16) + j;
-    const float* XSa = XS + 2 * hA + (T == 0 ? 0 : 8);        // pair (head hA, head 4 + hA), see HSG_XS_POS
+    const float* XSj = XS + j + (T == 0 ? 0 : 8);
     uint4 vcA = make_uint4(0, 0, 0, 0), vcB = vcA;
     if (T != 0) {
         const uint4* vc = reinterpret_cast<const uint4*>(cellV16) + (uint32_t)cell * 16u + j;
         vcA = __ldg(vc); vcB = __ldg(vc + 8);
     }
+    // row0 is a multiple of 32 and the rows of an even / odd group are rsub / rsub + 4 (mod 8): the swizzled store address is a
+    // per-lane constant plus 1024 bytes per pair of groups
+    uint32_t stA = a_chunk_addr(a_base, row0 + rsub, j), stB = a_chunk_addr(a_base, row0 + 4 + rsub, j);
+    const int2* prA = s_pr + row0 + rsub;
     AttRow A, B;
-    att_load<T>(A, row0 + rsub, s_pr, QKj, XSa, BVj, tokbase);
+    att_load<T>(A, 0, prA, QKj, XSj, BVj, tokbase);
 #pragma unroll 1
     for (int it = 0; it < NIT; it += 2) {
-        att_load<T>(B, row0 + (it + 1) * 4 + rsub, s_pr, QKj, XSa, BVj, tokbase);
-        att_compute<T>(A, vcA, vcB, a_base, j);
-        if (it + 2 < NIT) att_load<T>(A, row0 + (it + 2) * 4 + rsub, s_pr, QKj, XSa, BVj, tokbase);
-        att_compute<T>(B, vcA, vcB, a_base, j);
+        att_load<T>(B, 4, prA, QKj, XSj, BVj, tokbase);
+        att_compute<T>(A, vcA, vcB, stA);
+        if (it + 2 < NIT) att_load<T>(A, 8, prA, QKj, XSj, BVj, tokbase);
+        att_compute<T>(B, vcA, vcB, stB);
+        prA += 8; stA += 1024u; stB += 1024u;
     }
 }
 
