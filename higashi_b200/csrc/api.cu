@@ -503,7 +503,9 @@ extern "C" int hsg_prepare(hsg_ctx* c, int precision, int local_transfer_range, 
     c->use_umma = (precision != HSG_PREC_FP32 && d == 64);
     c->use_proj_umma = false;
     // softplus / raw heads pass the logit error through with slope ~1: they get the high-accuracy variant
-    c->umma_hi = c->use_umma && (precision == HSG_PREC_TC16_HI || activation != HSG_ACT_SIGMOID);
+    // (so does a layer_norm1 gain too close to zero for the fast variant's gain folding)
+    c->umma_hi = c->use_umma && (precision == HSG_PREC_TC16_HI || activation != HSG_ACT_SIGMOID ||
+                                 !umma_gain_foldable(h->v[HSG_W_LN1_G].data()));
     size_t per_cell;
     if (c->use_umma) {
         std::vector<unsigned char> wimg(umma_wimg_bytes());
@@ -511,7 +513,7 @@ extern "C" int hsg_prepare(hsg_ctx* c, int precision, int local_transfer_range, 
         umma_build_weights(h->v[HSG_W_FC1].data(), h->v[HSG_W_PFF_W0].data(), h->v[HSG_W_PFF_B0].data(),
                            h->v[HSG_W_PFF_LN_G].data(), h->v[HSG_W_PFF_LN_B].data(), h->v[HSG_W_PFF_W1].data(),
                            h->v[HSG_W_PFF_B1].data(), h->v[HSG_W_LN1_G].data(), h->v[HSG_W_CLS_W0].data(),
-                           h->v[HSG_W_CLS_B0].data(), h->v[HSG_W_CLS_W1].data(), h->v[HSG_W_CLS_B1].data(), wimg.data(),
+                           h->v[HSG_W_CLS_B0].data(), h->v[HSG_W_CLS_W1].data(), h->v[HSG_W_CLS_B1].data(), c->umma_hi ? 1 : 0, wimg.data(),
                            cst.data());
         if (dev_alloc(&c->wimg, wimg.size()) || dev_alloc(&c->cst, cst.size())) return 1;
         HSG_CUDA(cudaMemcpy(c->wimg, wimg.data(), wimg.size(), cudaMemcpyHostToDevice));

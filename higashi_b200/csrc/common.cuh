@@ -140,7 +140,8 @@ int launch_score_pairs_umma(hsg_ctx* c, int cell_start, int n_cells_batch, float
 int launch_convert_static(hsg_ctx* c, const float* V, const float* S, long long rows, void* V16, float* Sb, float* V32p, cudaStream_t s);
 int umma_build_weights(const float* fc1, const float* w0, const float* b0, const float* pff_g, const float* pff_b,
                        const float* w1, const float* b1, const float* ln1_g, const float* c0, const float* cb0,
-                       const float* cw1, const float* cb1, unsigned char* wimg_host, float* cst_host);
+                       const float* cw1, const float* cb1, int hi, unsigned char* wimg_host, float* cst_host);
+int umma_gain_foldable(const float* ln1_g);
 void train_release(hsg_ctx* c);     // train.cu: frees every per-context training / sampler buffer (called by hsg_destroy)
 int umma_wimg_bytes();
 int proj_wimg_bytes();

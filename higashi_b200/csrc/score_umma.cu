@@ -135,11 +135,11 @@ __global__ void __launch_bounds__(UM_THREADS, 1) score_umma_kernel(UmmaParams p)
                     sts128(a_chunk_addr(a_base, arow, h), pk[0], pk[1], pk[2], pk[3]);
                     sts128(a_chunk_addr(a_base, arow, 8 + h), pk[4], pk[5], pk[6], pk[7]);
                 }
-            } else {
-                const uint32_t tokbase = (uint32_t)cb * (uint32_t)p.n_bins;
-                if (t == 0) attention_fast<0, 8>(p.QK16, p.XS, p.binV16, p.cellV16, s_pr_wg, lane, warp_in_wg * 32, a_base, tokbase, cell);
-                else if (t == 1) attention_fast<1, 8>(p.QK16, p.XS, p.binV16, p.cellV16, s_pr_wg, lane, warp_in_wg * 32, a_base, tokbase, cell);
-                else attention_fast<2, 8>(p.QK16, p.XS, p.binV16, p.cellV16, s_pr_wg, lane, warp_in_wg * 32, a_base, tokbase, cell);
+            } else if (t == 0) {
+                // fast variant: only the first token's attention runs here; the ctx tile of token t + 1 is built while MMA 3 of
+                // token t is in flight (the A tile is free as soon as MMA 1 of token t has completed), see below
+                attention_fast<0, 8>(p.QK16, p.XS, p.binV16, p.cellV16, s_pr_wg, lane, warp_in_wg * 32, a_base,
+                                     (uint32_t)cb * (uint32_t)p.n_bins, cell);
             }
             // ------------------------------------------------------------------ MMA 1: [y_c | g] = ctx . [fc1c ; W0' fc1c]^T
             // ONE N=128 GEMM gives y_c = ctx . fc1c^T (columns 0..63: y with its row mean already removed, because the mean over
@@ -194,9 +194,16 @@ __global__ void __launch_bounds__(UM_THREADS, 1) score_umma_kernel(UmmaParams p)
                 // columns this thread has just consumed -- no shared-memory round trip, no proxy fence
                 tmem_st16(t_h + t_lane + half * 16, hp);
             }
+            if constexpr (!HI) {
+                // K columns 64 / 65 of the A operand = 1 (the bias columns of the W1 / C0 images); g is consumed, MMA 1 of the
+                // next token overwrites them again
+                const uint32_t one[8] = {0x3C003C00u, 0u, 0u, 0u, 0u, 0u, 0u, 0u};
+                tmem_st8(t_h + t_lane + 32, one);
+            }
             // ------------------------------------------------------------------ MMA 2: z_c = y_c + h . W1c^T (residual for free)
             ISSUE_BEGIN_TS()
             mma_group_ts<4, 64>(t_h, sbase + SMF_B_W1, 64, t_y, 1u);
+            if constexpr (!HI) umma_f16_ts(t_y, t_h + 32, umma_desc(sbase + SMF_X_W1B), umma_idesc_f16(128, 64), 1u);     // + b1c
             ISSUE_END()
             // S rows of this token (feature blocks of 4): requested BEFORE waiting for the MMA so that their L2 latency hides
             // behind the tensor-core round trip (volatile loads: the compiler must not sink them below the wait)
@@ -210,9 +217,11 @@ __global__ void __launch_bounds__(UM_THREADS, 1) score_umma_kernel(UmmaParams p)
             mbar_wait(bar_mma, phase); phase ^= 1;
             tc_fence_after();
 
-            // ------------------------------------------------------------------ u = (LN1(z + b1c) - S)^2  -> TMEM A operand
+            // ------------------------------------------------------------------ u = (LN1(z) - S)^2  -> TMEM A operand
             // z arrives centred (y_c + h . W1c^T + b1c has zero row mean by construction).  Two passes over TMEM keep the register
             // footprint at 16 columns + the 64 prefetched S values: pass 1 = row variance, pass 2 = u.
+            // Fast variant: b1c was added by the tensor core (bias K columns) and the LayerNorm gain is folded away
+            // (S table = (beta - S) / gamma, gamma^2 in the columns of C0): u' = (z rstd + S')^2 -- FFMA2 + FMUL2 + pack per pair.
             {
                 float2 vA = make_float2(0.f, 0.f), vB = vA, vC = vA, vD = vA;
 #pragma unroll
@@ -222,11 +231,13 @@ __global__ void __launch_bounds__(UM_THREADS, 1) score_umma_kernel(UmmaParams p)
                     tmem_ld_wait();
 #pragma unroll
                     for (int i = 0; i < 16; i += 4) {
-                        const float* bq = cst + CST_B1C + half * 32 + 2 * i;
-                        float2 a = __fadd2_rn(f2(r[2 * i], r[2 * i + 1]), make_float2(bq[0], bq[1]));
-                        float2 b = __fadd2_rn(f2(r[2 * i + 2], r[2 * i + 3]), make_float2(bq[2], bq[3]));
-                        float2 c2 = __fadd2_rn(f2(r[2 * i + 4], r[2 * i + 5]), make_float2(bq[4], bq[5]));
-                        float2 d2 = __fadd2_rn(f2(r[2 * i + 6], r[2 * i + 7]), make_float2(bq[6], bq[7]));
+                        float2 a = f2(r[2 * i], r[2 * i + 1]), b = f2(r[2 * i + 2], r[2 * i + 3]);
+                        float2 c2 = f2(r[2 * i + 4], r[2 * i + 5]), d2 = f2(r[2 * i + 6], r[2 * i + 7]);
+                        if constexpr (HI) {
+                            const float* bq = cst + CST_B1C + half * 32 + 2 * i;
+                            a = __fadd2_rn(a, make_float2(bq[0], bq[1])); b = __fadd2_rn(b, make_float2(bq[2], bq[3]));
+                            c2 = __fadd2_rn(c2, make_float2(bq[4], bq[5])); d2 = __fadd2_rn(d2, make_float2(bq[6], bq[7]));
+                        }
                         vA = __ffma2_rn(a, a, vA); vB = __ffma2_rn(b, b, vB); vC = __ffma2_rn(c2, c2, vC); vD = __ffma2_rn(d2, d2, vD);
                     }
                 }
@@ -247,9 +258,14 @@ __global__ void __launch_bounds__(UM_THREADS, 1) score_umma_kernel(UmmaParams p)
                     const float svv[8] = {s0.x, s0.y, s0.z, s0.w, s1.x, s1.y, s1.z, s1.w};
 #pragma unroll
                     for (int q = 0; q < 4; ++q) {
-                        float2 x = __fadd2_rn(f2(r[c * 8 + 2 * q], r[c * 8 + 2 * q + 1]), make_float2(bq[2 * q], bq[2 * q + 1]));
-                        float2 tz = __fmul2_rn(x, rs);
-                        float2 u = __ffma2_rn(tz, make_float2(gq[2 * q], gq[2 * q + 1]), make_float2(svv[2 * q], svv[2 * q + 1]));
+                        float2 u;
+                        if constexpr (HI) {
+                            float2 x = __fadd2_rn(f2(r[c * 8 + 2 * q], r[c * 8 + 2 * q + 1]), make_float2(bq[2 * q], bq[2 * q + 1]));
+                            float2 tz = __fmul2_rn(x, rs);
+                            u = __ffma2_rn(tz, make_float2(gq[2 * q], gq[2 * q + 1]), make_float2(svv[2 * q], svv[2 * q + 1]));
+                        } else {
+                            u = __ffma2_rn(f2(r[c * 8 + 2 * q], r[c * 8 + 2 * q + 1]), rs, make_float2(svv[2 * q], svv[2 * q + 1]));
+                        }
                         u = __fmul2_rn(u, u);
                         up[c * 4 + q] = pack_h2(u.x, u.y);
                         if constexpr (HI) {             // u = hi + lo, both fp16: the classifier GEMM sees ~22 bits of u
@@ -268,8 +284,15 @@ __global__ void __launch_bounds__(UM_THREADS, 1) score_umma_kernel(UmmaParams p)
             if constexpr (HI) {
                 mma_group_ts<4, 32>(t_h + 32, sbase + SMF_B_C0, 32, t_y, 1u);                        // u_lo . C0_hi
                 mma_group_ts<4, 32>(t_h, sbase + SMH_B_C0_LO, 32, t_y, 1u);                          // u_hi . C0_lo
+            } else {
+                umma_f16_ts(t_y, t_h + 32, umma_desc(sbase + SMF_X_C0B), umma_idesc_f16(128, 32), 1u);  // + cb0 / 2
             }
             ISSUE_END()
+            if constexpr (!HI) {        // next token's attention overlaps the classifier MMA round trip
+                const uint32_t tokbase = (uint32_t)cb * (uint32_t)p.n_bins;
+                if (t == 0) attention_fast<1, 8>(p.QK16, p.XS, p.binV16, p.cellV16, s_pr_wg, lane, warp_in_wg * 32, a_base, tokbase, cell);
+                else if (t == 1) attention_fast<2, 8>(p.QK16, p.XS, p.binV16, p.cellV16, s_pr_wg, lane, warp_in_wg * 32, a_base, tokbase, cell);
+            }
             mbar_wait(bar_mma, phase); phase ^= 1;
             tc_fence_after();
 
@@ -282,8 +305,8 @@ __global__ void __launch_bounds__(UM_THREADS, 1) score_umma_kernel(UmmaParams p)
 #pragma unroll
                 for (int i = 0; i < 16; i += 2) {
                     const float* bq = cst + CST_CB0 + 2 * i; const float* wq = cst + CST_CW1 + 2 * i;
-                    float2 w0 = __fadd2_rn(f2(r[2 * i], r[2 * i + 1]), make_float2(bq[0], bq[1]));
-                    float2 w1 = __fadd2_rn(f2(r[2 * i + 2], r[2 * i + 3]), make_float2(bq[2], bq[3]));
+                    float2 w0 = f2(r[2 * i], r[2 * i + 1]), w1 = f2(r[2 * i + 2], r[2 * i + 3]);
+                    if constexpr (HI) { w0 = __fadd2_rn(w0, make_float2(bq[0], bq[1])); w1 = __fadd2_rn(w1, make_float2(bq[2], bq[3])); }
                     float2 h0 = __ffma2_rn(w0, make_float2(fast_tanh(w0.x), fast_tanh(w0.y)), w0);
                     float2 h1 = __ffma2_rn(w1, make_float2(fast_tanh(w1.x), fast_tanh(w1.y)), w1);
                     oA = __ffma2_rn(h0, make_float2(wq[0], wq[1]), oA);
@@ -315,7 +338,7 @@ __global__ void __launch_bounds__(UM_THREADS, 1) score_umma_kernel(UmmaParams p)
 
 int umma_build_weights(const float* fc1, const float* w0, const float* b0, const float* pff_g, const float* pff_b,
                        const float* w1, const float* b1, const float* ln1_g, const float* c0, const float* cb0,
-                       const float* cw1, const float* cb1, unsigned char* wimg_host, float* cst_host) {
+                       const float* cw1, const float* cb1, int hi, unsigned char* wimg_host, float* cst_host) {
     const int d = UM_D;
     std::vector<float> w0f((size_t)d * d);
     for (int n = 0; n < d; ++n) {
@@ -353,8 +376,7 @@ int umma_build_weights(const float* fc1, const float* w0, const float* b0, const
         comb.swap(perm);
     }
     swizzle_image(comb.data(), 2 * d, HSG_HD, reinterpret_cast<__half*>(wimg_host + SMF_B_FC1));
-    for (size_t i = 0; i < comb.size(); ++i) lo[i] = comb[i] - __half2float(__float2half_rn(comb[i]));
-    swizzle_image(lo.data(), 2 * d, HSG_HD, reinterpret_cast<__half*>(wimg_host + SMH_B_FC1_LO));
+    for (size_t i = 0; i < comb.size(); ++i) lo[i] = comb[i] - __half2float(__float2half_rn(comb[i]));      // written below (hi only)
     std::vector<float> w1c((size_t)d * d);
     for (int k = 0; k < d; ++k) {
         double m = 0;
@@ -363,35 +385,62 @@ int umma_build_weights(const float* fc1, const float* w0, const float* b0, const
         for (int n = 0; n < d; ++n) w1c[(size_t)n * d + k] = (float)(w1[(size_t)n * d + k] - m);
     }
     swizzle_image(w1c.data(), d, d, reinterpret_cast<__half*>(wimg_host + SMF_B_W1));
-    std::vector<float> c0h((size_t)(d / 2) * d);
-    for (size_t i = 0; i < c0h.size(); ++i) c0h[i] = 0.5f * c0[i];
-    swizzle_image(c0h.data(), d / 2, d, reinterpret_cast<__half*>(wimg_host + SMF_B_C0));
-    for (size_t i = 0; i < c0h.size(); ++i) lo[i] = c0h[i] - __half2float(__float2half_rn(c0h[i]));
-    swizzle_image(lo.data(), d / 2, d, reinterpret_cast<__half*>(wimg_host + SMH_B_C0_LO));
     double mb = 0;
     for (int i = 0; i < d; ++i) mb += b1[i];
     mb /= d;
     for (int i = 0; i < d; ++i) cst_host[CST_B1C + i] = (float)(b1[i] - mb);
+    // fast variant: u' = u / gamma^2 (the S table is divided by gamma, convert_static_kernel), so gamma^2 goes into C0's columns
+    std::vector<float> c0h((size_t)(d / 2) * d);
+    for (int n = 0; n < d / 2; ++n)
+        for (int k = 0; k < d; ++k) c0h[(size_t)n * d + k] = 0.5f * c0[(size_t)n * d + k] * (hi ? 1.0f : ln1_g[k] * ln1_g[k]);
+    swizzle_image(c0h.data(), d / 2, d, reinterpret_cast<__half*>(wimg_host + SMF_B_C0));
+    if (hi) {
+        swizzle_image(lo.data(), 2 * d, HSG_HD, reinterpret_cast<__half*>(wimg_host + SMH_B_FC1_LO));
+        for (size_t i = 0; i < c0h.size(); ++i) lo[i] = c0h[i] - __half2float(__float2half_rn(c0h[i]));
+        swizzle_image(lo.data(), d / 2, d, reinterpret_cast<__half*>(wimg_host + SMH_B_C0_LO));
+    } else {
+        // bias atoms: K column 0 = fp16(b), column 1 = fp16(b - fp16(b)); the A operand carries (1, 1, 0, ...) in these columns
+        std::vector<float> wb((size_t)d * d, 0.f), cb((size_t)(d / 2) * d, 0.f);
+        for (int n = 0; n < d; ++n) {
+            const float b = cst_host[CST_B1C + n], bh = __half2float(__float2half_rn(b));
+            wb[(size_t)n * d] = bh; wb[(size_t)n * d + 1] = b - bh;
+        }
+        for (int n = 0; n < d / 2; ++n) {
+            const float b = 0.5f * cb0[n], bh = __half2float(__float2half_rn(b));
+            cb[(size_t)n * d] = bh; cb[(size_t)n * d + 1] = b - bh;
+        }
+        swizzle_image(wb.data(), d, d, reinterpret_cast<__half*>(wimg_host + SMF_X_W1B));
+        swizzle_image(cb.data(), d / 2, d, reinterpret_cast<__half*>(wimg_host + SMF_X_C0B));
+    }
     return 0;
+}
+
+// the fast variant folds the layer_norm1 gain into the S table and C0: it needs |gamma| bounded away from 0
+int umma_gain_foldable(const float* ln1_g) {
+    for (int i = 0; i < UM_D; ++i) if (!(fabsf(ln1_g[i]) >= 0.05f)) return 0;
+    return 1;
 }
 
 int umma_wimg_bytes() { return SMH_WIMG_BYTES; }
 int umma_cst_count() { return CST_COUNT; }
 
 // fp32 static tables -> 16-bit / offset copies used by the tensor-core kernel
+// Sb = beta(layer_norm1) - S, divided by gamma(layer_norm1) when ln1_g is given (fast variant, see umma_build_weights)
 __global__ void convert_static_kernel(const float* __restrict__ V, const float* __restrict__ S, const float* __restrict__ ln1_b,
-                                      long long rows, int d, __half* __restrict__ V16, float* __restrict__ Sb, float* __restrict__ V32p) {
+                                      const float* __restrict__ ln1_g, long long rows, int d, __half* __restrict__ V16,
+                                      float* __restrict__ Sb, float* __restrict__ V32p) {
     long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (i < rows * HSG_HD) {
         { const int cc = (int)(i & (HSG_HD - 1)); V16[i - cc + HSG_COL_POS(cc)] = __float2half_rn(V[i]); }     // head-per-lane chunk order
         if (V32p) { const int cc = (int)(i & (HSG_HD - 1)); V32p[i - cc + HSG_HI_POS(cc)] = V[i]; }
     }
-    if (i < rows * d) { long long r = i / d; int f = (int)(i - r * d); Sb[((long long)(f >> 2) * rows + r) * 4 + (f & 3)] = ln1_b[f] - S[i]; }
+    if (i < rows * d) { long long r = i / d; int f = (int)(i - r * d); Sb[((long long)(f >> 2) * rows + r) * 4 + (f & 3)] = ln1_g ? (ln1_b[f] - S[i]) / ln1_g[f] : ln1_b[f] - S[i]; }
 }
 
 int launch_convert_static(hsg_ctx* c, const float* V, const float* S, long long rows, void* V16, float* Sb, float* V32p, cudaStream_t s) {
     long long n = rows * HSG_HD;
-    convert_static_kernel<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(V, S, c->w[HSG_W_LN1_B], rows, c->d, (__half*)V16, Sb, V32p);
+    convert_static_kernel<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(V, S, c->w[HSG_W_LN1_B], c->umma_hi ? nullptr : c->w[HSG_W_LN1_G], rows, c->d,
+                                                                       (__half*)V16, Sb, V32p);
     c->launches++;
     HSG_CUDA(cudaGetLastError());
     return 0;

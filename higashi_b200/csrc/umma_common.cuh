@@ -18,7 +18,11 @@
 #define SMF_B_FC1 0           // [128 x 128], 2 K-atoms of 16 KB: rows 0..63 fc1c, rows 64..127 W0' fc1c
 #define SMF_B_W1 32768        // [64 x 64]  W1 with its output mean removed
 #define SMF_B_C0 40960        // [32 x 64]  C0 / 2
-#define SMF_WIMG_BYTES 45056
+// fast variant only: one more K atom each for W1 and C0 whose first two K columns hold the bias (fp16 hi + lo); the A operand
+// supplies the matching constant columns (1, 1, 0, ...), so z_c and c leave the tensor core with their biases added
+#define SMF_X_W1B 45056       // [64 x 64]  column 0 / 1 = hi / lo of b1 - mean(b1)
+#define SMF_X_C0B 53248       // [32 x 64]  column 0 / 1 = hi / lo of cb0 / 2
+#define SMF_WIMG_BYTES 57344
 #define SMH_B_FC1_LO 45056    // [128 x 128] low halves
 #define SMH_B_C0_LO 77824     // [32 x 64]   low halves
 #define SMH_WIMG_BYTES 81920
