@@ -312,6 +312,8 @@ def run_train(args):
         sizes.append(B)
         tr.step(None, pool[i % len(pool)][1], None, None, None, stage=2, loss_mode=0, train_mode=True, want_loss=(i % 10 == 0), sampled=(B, nnz))
     begin(0)
+    # untimed: at least one pass over every pooled batch shape (workspaces grow to their final size on first use)
+    args.warmup = max(args.warmup, len(pool) + 2)
     for i in range(args.warmup):
         step(i)
     torch.cuda.synchronize()

@@ -18,85 +18,142 @@
 
 // ------------------------------------------------------------------------------------------------ sgemm
 // C[M,N] = sum_k a(m,k) b(k,n) (+ beta*C);  a(m,k) = TA ? A[k*lda+m] : A[m*lda+k];  b(k,n) = TB ? B[n*ldb+k] : B[k*ldb+n]
-// BM = 64 or 32 rows per block (32 doubles the grid for the tall-skinny activations: 9216 x 64 would otherwise be 144 blocks)
-template <bool TA, bool TB, int BM>
+//
+// Every GEMM of the training step is tall and skinny (M = 3B rows of activations, N and K in {32, 64, 128}, or the transposed
+// weight-gradient shape with the long dimension as the reduction), so one launch is a few MFLOP and a handful of dependent
+// global-load latencies.  64 x 64 output tile per block of 256 threads, 4 x 4 outputs per thread, K in steps of 32:
+//   * both operand tiles live in shared memory k-major ([k][m], [k][n]) so that a thread reads its 4 rows / 4 columns with one
+//     128-bit load each per k (the A read is a broadcast: 3 wavefronts per 16 FMAs);
+//   * operands that are m-/n-major in global memory are transposed on the way in; the 4-float groups of a row are XOR-swizzled
+//     with k/4, which makes the transposing scalar stores conflict-free without padding (padding would break the 128-bit reads);
+//   * global loads are 128-bit and fully coalesced whenever the leading dimensions / base pointers allow it, guarded scalar
+//     loads otherwise (ragged feature widths);
+//   * the next k tile is fetched into registers before the current one is multiplied (one __syncthreads per tile);
+//   * weight-gradient shapes slice the reduction over gridDim.z and combine with atomics (only launched with beta == 1).
+#define SG_BM 64
+#define SG_BN 64
+#define SG_BK 32
+
+// tile element (kk, x) with x the m / n index inside the tile -> shared-memory offset (floats)
+__device__ __forceinline__ int sg_off(int kk, int x) { return kk * 64 + ((((x >> 2) ^ (kk >> 2)) & 15) << 2) + (x & 3); }
+
+// Fetch one [SG_BK x 64] operand tile into registers (8 floats per thread).  XMAJOR: element (k, x) at P[k*ld + x] (x contiguous),
+// else at P[x*ld + k] (k contiguous).  Thread mapping: XMAJOR  idx -> kk = idx/16, x4 = idx%16 ; else idx -> x = idx/8, k4 = idx%8.
+template <bool XMAJOR>
+__device__ __forceinline__ void sg_fetch(float (&r)[8], const float* __restrict__ P, int ld, int x0, int X, int k0, int K, bool vec) {
+#pragma unroll
+    for (int t = 0; t < 2; ++t) {
+        const int idx = threadIdx.x + t * 256;
+        int kk, xx;
+        if (XMAJOR) { kk = idx >> 4; xx = (idx & 15) << 2; } else { xx = idx >> 3; kk = (idx & 7) << 2; }
+        const int k = k0 + kk, x = x0 + xx;
+        float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (XMAJOR) {
+            if (k < K) {
+                const float* q = P + (size_t)k * ld + x;
+                if (vec && x + 3 < X) v = __ldg(reinterpret_cast<const float4*>(q));
+                else { if (x < X) v.x = __ldg(q); if (x + 1 < X) v.y = __ldg(q + 1); if (x + 2 < X) v.z = __ldg(q + 2); if (x + 3 < X) v.w = __ldg(q + 3); }
+            }
+        } else {
+            if (x < X) {
+                const float* q = P + (size_t)x * ld + k;
+                if (vec && k + 3 < K) v = __ldg(reinterpret_cast<const float4*>(q));
+                else { if (k < K) v.x = __ldg(q); if (k + 1 < K) v.y = __ldg(q + 1); if (k + 2 < K) v.z = __ldg(q + 2); if (k + 3 < K) v.w = __ldg(q + 3); }
+            }
+        }
+        r[t * 4] = v.x; r[t * 4 + 1] = v.y; r[t * 4 + 2] = v.z; r[t * 4 + 3] = v.w;
+    }
+}
+template <bool XMAJOR>
+__device__ __forceinline__ void sg_stash(const float (&r)[8], float* __restrict__ S) {
+#pragma unroll
+    for (int t = 0; t < 2; ++t) {
+        const int idx = threadIdx.x + t * 256;
+        if (XMAJOR) {
+            const int kk = idx >> 4, xx = (idx & 15) << 2;
+            *reinterpret_cast<float4*>(S + sg_off(kk, xx)) = make_float4(r[t * 4], r[t * 4 + 1], r[t * 4 + 2], r[t * 4 + 3]);
+        } else {
+            const int xx = idx >> 3, kk = (idx & 7) << 2;          // the 4 values are 4 consecutive k of one row / column
+#pragma unroll
+            for (int j = 0; j < 4; ++j) S[sg_off(kk + j, xx)] = r[t * 4 + j];
+        }
+    }
+}
+
+template <bool TA, bool TB>
 __global__ void __launch_bounds__(256) sgemm_kernel(int M, int N, int K, const float* __restrict__ A, int lda,
                                                     const float* __restrict__ B, int ldb, float* __restrict__ C, int ldc,
-                                                    float beta) {
-    constexpr int RM = BM / 16;                  // rows per thread
-    __shared__ __align__(16) float sA[16][BM + 4], sB[16][68];
+                                                    float beta, int vecA, int vecB) {
+    __shared__ __align__(16) float sA[2][SG_BK * SG_BM], sB[2][SG_BK * SG_BN];
     const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;
-    const int m0 = blockIdx.y * BM, n0 = blockIdx.x * 64;
-    float acc[RM][4] = {};
-    // split-K: gridDim.z slices of the reduction, combined with atomics (only launched with beta == 1)
-    const int kchunk = ((K + (int)gridDim.z - 1) / (int)gridDim.z + 15) & ~15;
+    const int m0 = blockIdx.y * SG_BM, n0 = blockIdx.x * SG_BN;
+    // split-K: gridDim.z slices of the reduction, combined with atomics
+    const int kchunk = ((K + (int)gridDim.z - 1) / (int)gridDim.z + SG_BK - 1) & ~(SG_BK - 1);
     const int kbeg = blockIdx.z * kchunk;
     K = min(K, kbeg + kchunk);
-    for (int k0 = kbeg; k0 < K; k0 += 16) {
-        for (int i = threadIdx.x; i < 16 * BM; i += 256) {
-            int kk = i & 15, mm = i >> 4;
-            if (TA) { kk = i / BM; mm = i % BM; }
-            int m = m0 + mm, k = k0 + kk;
-            sA[kk][mm] = (m < M && k < K) ? (TA ? A[(size_t)k * lda + m] : A[(size_t)m * lda + k]) : 0.f;
-        }
-        for (int i = threadIdx.x; i < 16 * 64; i += 256) {
-            int kk = i & 15, nn = i >> 4;
-            if (!TB) { kk = i >> 6; nn = i & 63; }
-            int n = n0 + nn, k = k0 + kk;
-            sB[kk][nn] = (n < N && k < K) ? (TB ? B[(size_t)n * ldb + k] : B[(size_t)k * ldb + n]) : 0.f;
-        }
+    float acc[4][4] = {};
+    float ra[8], rb[8];
+    if (kbeg < K) {
+        sg_fetch<TA>(ra, A, lda, m0, M, kbeg, K, vecA != 0);
+        sg_fetch<!TB>(rb, B, ldb, n0, N, kbeg, K, vecB != 0);
+    }
+    int buf = 0;
+    for (int k0 = kbeg; k0 < K; k0 += SG_BK) {
+        sg_stash<TA>(ra, sA[buf]);
+        sg_stash<!TB>(rb, sB[buf]);
         __syncthreads();
+        if (k0 + SG_BK < K) {                     // next tile in flight while this one is multiplied
+            sg_fetch<TA>(ra, A, lda, m0, M, k0 + SG_BK, K, vecA != 0);
+            sg_fetch<!TB>(rb, B, ldb, n0, N, k0 + SG_BK, K, vecB != 0);
+        }
+        const float* a_s = sA[buf];
+        const float* b_s = sB[buf];
 #pragma unroll
-        for (int kk = 0; kk < 16; ++kk) {
-            float a[RM];
-            if (RM == 4) { float4 av = *reinterpret_cast<const float4*>(&sA[kk][ty * 4]); a[0] = av.x; a[1] = av.y; a[2 % RM] = av.z; a[3 % RM] = av.w; }
-            else { float2 av = *reinterpret_cast<const float2*>(&sA[kk][ty * 2]); a[0] = av.x; a[1] = av.y; }
-            const float4 bv = *reinterpret_cast<const float4*>(&sB[kk][tx * 4]);
+        for (int kk = 0; kk < SG_BK; ++kk) {
+            const float4 av = *reinterpret_cast<const float4*>(a_s + kk * 64 + ((ty ^ (kk >> 2)) << 2));
+            const float4 bv = *reinterpret_cast<const float4*>(b_s + kk * 64 + ((tx ^ (kk >> 2)) << 2));
+            const float a[4] = {av.x, av.y, av.z, av.w};
 #pragma unroll
-            for (int i = 0; i < RM; ++i) {
+            for (int i = 0; i < 4; ++i) {
                 acc[i][0] = fmaf(a[i], bv.x, acc[i][0]); acc[i][1] = fmaf(a[i], bv.y, acc[i][1]);
                 acc[i][2] = fmaf(a[i], bv.z, acc[i][2]); acc[i][3] = fmaf(a[i], bv.w, acc[i][3]);
             }
         }
-        __syncthreads();
+        buf ^= 1;                                 // the other buffer was last read two tiles ago: one barrier per tile suffices
     }
+    if (kbeg >= K && gridDim.z > 1) return;
 #pragma unroll
-    for (int i = 0; i < RM; ++i)
+    for (int i = 0; i < 4; ++i) {
+        const int m = m0 + ty * 4 + i;
+        if (m >= M) continue;
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
-            int m = m0 + ty * RM + i, n = n0 + tx * 4 + j;
-            if (m < M && n < N) {
+            const int n = n0 + tx * 4 + j;
+            if (n < N) {
                 float* p = C + (size_t)m * ldc + n;
                 if (gridDim.z > 1) atomicAdd(p, acc[i][j]);
                 else *p = (beta != 0.f) ? fmaf(beta, *p, acc[i][j]) : acc[i][j];
             }
         }
+    }
 }
 
-template <int BM>
-static void gemm_launch(cudaStream_t s, dim3 grid, bool ta, bool tb, int M, int N, int K, const float* A, int lda, const float* B, int ldb,
-                        float* C, int ldc, float beta) {
-    if (!ta && tb) sgemm_kernel<false, true, BM><<<grid, 256, 0, s>>>(M, N, K, A, lda, B, ldb, C, ldc, beta);
-    else if (!ta && !tb) sgemm_kernel<false, false, BM><<<grid, 256, 0, s>>>(M, N, K, A, lda, B, ldb, C, ldc, beta);
-    else if (ta && !tb) sgemm_kernel<true, false, BM><<<grid, 256, 0, s>>>(M, N, K, A, lda, B, ldb, C, ldc, beta);
-    else sgemm_kernel<true, true, BM><<<grid, 256, 0, s>>>(M, N, K, A, lda, B, ldb, C, ldc, beta);
-}
+static inline bool sg_vec_ok(const float* P, int ld) { return (((uintptr_t)P) & 15) == 0 && (ld & 3) == 0; }
 
 static int gemm(hsg_ctx* c, cudaStream_t s, bool ta, bool tb, int M, int N, int K, const float* A, int lda, const float* B,
                 int ldb, float* C, int ldc, float beta) {
     if (M <= 0 || N <= 0) return 0;
-    dim3 grid((N + 63) / 64, (M + 63) / 64);
+    dim3 grid((N + SG_BN - 1) / SG_BN, (M + SG_BM - 1) / SG_BM);
     // weight-gradient shapes (tiny M x N, long K): slice the reduction so the grid covers the SMs
     if (beta == 1.0f && K >= 512 && grid.x * grid.y < 148) {
         int want = (2 * 148 + grid.x * grid.y - 1) / (grid.x * grid.y);
         grid.z = (unsigned)std::max(1, std::min(want, K / 128));
     }
-    if (grid.z == 1 && grid.x * grid.y < 2 * 148 && M > 64) {       // tall-skinny activations: 32-row tiles, twice the blocks
-        grid.y = (M + 31) / 32;
-        gemm_launch<32>(s, grid, ta, tb, M, N, K, A, lda, B, ldb, C, ldc, beta);
-    } else {
-        gemm_launch<64>(s, grid, ta, tb, M, N, K, A, lda, B, ldb, C, ldc, beta);
-    }
+    const int va = sg_vec_ok(A, lda) ? 1 : 0, vb = sg_vec_ok(B, ldb) ? 1 : 0;
+    if (!ta && tb) sgemm_kernel<false, true><<<grid, 256, 0, s>>>(M, N, K, A, lda, B, ldb, C, ldc, beta, va, vb);
+    else if (!ta && !tb) sgemm_kernel<false, false><<<grid, 256, 0, s>>>(M, N, K, A, lda, B, ldb, C, ldc, beta, va, vb);
+    else if (ta && !tb) sgemm_kernel<true, false><<<grid, 256, 0, s>>>(M, N, K, A, lda, B, ldb, C, ldc, beta, va, vb);
+    else sgemm_kernel<true, true><<<grid, 256, 0, s>>>(M, N, K, A, lda, B, ldb, C, ldc, beta, va, vb);
     TR_CHECK_LAUNCH(c);
     return 0;
 }

@@ -103,7 +103,8 @@ class DataParallelTrainer:
         self.names = list(engine.layout.keys())
         self.params = [torch.nn.Parameter(v) for v in engine.named_params().values()]
         self.grad_views = list(engine.named_grads().values())
-        self.opt = torch.optim.Adam(self.params, lr=lr)
+        # one fused update kernel over all parameter tensors instead of torch's default foreach implementation (7 launches / step)
+        self.opt = torch.optim.Adam(self.params, lr=lr, fused=bool(self.params and self.params[0].is_cuda))
         self.presence = torch.zeros(len(self.names), dtype=torch.float32, device=engine.grads.device)
         self._patterns = {}
         self.loss_mode_cached = 0
