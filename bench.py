@@ -31,6 +31,26 @@ import numpy as np
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
+# The contract is ONE JSON line on stdout.  Libraries (NCCL's version banner, torch warnings) may write to file descriptor 1
+# behind Python's back, so fd 1 is pointed at stderr for the whole run and the result line goes to a private copy of the
+# original stdout.
+_RESULT_OUT = None
+
+
+def _claim_stdout():
+    global _RESULT_OUT
+    if _RESULT_OUT is None:
+        sys.stdout.flush()
+        _RESULT_OUT = os.fdopen(os.dup(1), "w")
+        os.dup2(2, 1)
+
+
+def emit(obj):
+    _claim_stdout()
+    _RESULT_OUT.write(json.dumps(obj) + "\n")
+    _RESULT_OUT.flush()
+
+
 FLOP_PER_TRIPLET_TENSOR = 110592.0      # fc1 + pff_n1 + classifier layer 1 at d = 64
 
 
@@ -177,7 +197,7 @@ def run_reference(args):
                                        % (cells_per_step, args.steps, args.workload)},
             "e2e": {"value": val, "unit": "triplets/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
-    print(json.dumps(line), flush=True)
+    emit(line)
 
 
 def run_reference_train(args):
@@ -223,8 +243,9 @@ def run_reference_train(args):
         if it >= args.warmup:
             times.append(dt)
     total = sum(times)
+    B = float(np.mean([len(pool[it % len(pool)][0]) for it in range(args.warmup, args.warmup + args.steps)]))
     val = args.steps * B / total
-    print(json.dumps({"impl": "reference", "metric": "train hyperedges/s", "value": val, "unit": "hyperedges/s", "n_gpus": args.gpus,
+    emit(({"impl": "reference", "metric": "train hyperedges/s", "value": val, "unit": "hyperedges/s", "n_gpus": args.gpus,
                       "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * total / args.steps, "higher_is_better": True,
                       "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
                       "config": {"workload": "C4-shaped: %d cells x %d bins, stage-2 training step, %d hyperedges per step, d_model=%d"
@@ -233,7 +254,7 @@ def run_reference_train(args):
                                        "sample": "%d steps of %d hyperedges (oracle/ forward_stage2 + torch autograd + Adam, no dropout)"
                                                  % (args.steps, B)},
                       "e2e": {"value": val, "unit": "hyperedges/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
-                      "gpu_launches": 0}), flush=True)
+                      "gpu_launches": 0}))
 
 
 def cpu_baseline(args, ds_shape):
@@ -293,8 +314,9 @@ def run_train(args):
     nbr, nbr_w = knn_lists(ds, ds.k, 99 + rank)
     eng.set_graph(ds.csr, nbr, nbr_w)
     pool = []
+    chrom_rng = np.random.default_rng(10)      # shared chromosome schedule: every rank trains the same chromosome in a given step
     for i in range(8):
-        chrom = int(rng.integers(0, len(ds.bins)))
+        chrom = int(chrom_rng.integers(0, len(ds.bins)))
         x, _, _ = batches.synthetic_batch(ds.csr, chrom, ds.num_list, 2 * n_pos, 0, rng)
         x = x[(x[:, 2] - x[:, 1] > 1)][:n_pos]
         pool.append((np.ascontiguousarray(x), chrom, rng.uniform(0.5, 2.0, size=len(x)).astype(np.float32)))
@@ -310,7 +332,8 @@ def run_train(args):
         B, nnz = eng.sample_batch_end()
         begin(i + 1)
         sizes.append(B)
-        tr.step(None, pool[i % len(pool)][1], None, None, None, stage=2, loss_mode=0, train_mode=True, want_loss=(i % 10 == 0), sampled=(B, nnz))
+        tr.step(None, pool[i % len(pool)][1], None, None, None, stage=2, loss_mode=0, train_mode=True, want_loss=(i % 10 == 0), sampled=(B, nnz),
+                uniform_batches=True)
     begin(0)
     # untimed: at least one pass over every pooled batch shape (workspaces grow to their final size on first use)
     args.warmup = max(args.warmup, len(pool) + 2)
@@ -329,19 +352,20 @@ def run_train(args):
     dt = parallel.max_over_ranks(time.perf_counter() - t0)
     if rank == 0:
         B = float(np.mean(sizes[-args.steps:]))
-        print(json.dumps({"metric": "train hyperedges/s", "value": world * args.steps * B / dt, "unit": "hyperedges/s", "n_gpus": world,
+        emit(({"metric": "train hyperedges/s", "value": world * args.steps * B / dt, "unit": "hyperedges/s", "n_gpus": world,
                           "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps, "higher_is_better": True,
                           "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
                           "config": {"workload": "C4-shaped: %d cells x %d bins (mm10 @ 500 kb), stage-2 (GraphSAGE) training step, %d hyperedges "
                                                  "per rank per step (512 positives + 5 negatives each; negatives and neighbour lists produced on the device "
                                                  "inside the timed region), d_model=%d, dropout on, Adam, 1 NCCL allreduce/step" % (ds.n_cells, sum(ds.bins), B, ds.d)},
-                          "gpu_launches": int(eng.ctx.launch_count() - l0)}), flush=True)
+                          "gpu_launches": int(eng.ctx.launch_count() - l0)}))
     if world > 1:
         dist.destroy_process_group()
 
 
 def main():
     args = parse()
+    _claim_stdout()
     if args.impl == "reference":
         (run_reference_train if args.mode == "train" else run_reference)(args)
         return
@@ -497,7 +521,7 @@ def main():
                 "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches), "roofline": roofline, "cpu_baseline": cpu}
         if args.n_cells:
             line["invalid"] = "dataset shrunk with --n-cells (debug run)"
-        print(json.dumps(line), flush=True)
+        emit(line)
     if world > 1:
         dist.destroy_process_group()
 

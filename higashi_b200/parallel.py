@@ -80,15 +80,29 @@ def reduce_gradients(flat_grads, presence):
     flat_grads: 1-D tensor (fixed layout, zeros where a rank produced no gradient); presence: 1-D tensor with one entry
     per parameter tensor (1 = this rank produced a gradient).  Every rank gets the MEAN gradient over the ranks and the
     OR of the presence flags -- parameters no rank touched keep `grad = None`, exactly like the reference's single-GPU
-    run where e.g. only the batch chromosome's projection receives a gradient (torch Adam skips grad=None)."""
+    run where e.g. only the batch chromosome's projection receives a gradient (torch Adam skips grad=None).
+
+    ONE collective: when `presence` is the tail of the storage `flat_grads` starts (TrainEngine allocates them that way) the
+    two are summed in a single all_reduce; otherwise they are packed into one buffer first."""
     import torch
     import torch.distributed as dist
     if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size() == 1:
         return flat_grads, presence
     world = dist.get_world_size()
-    dist.all_reduce(flat_grads, op=dist.ReduceOp.SUM)            # NCCL over NVLink on the GPUs, gloo in the CPU tests
+    n, m = flat_grads.numel(), presence.numel()
+    contiguous_pair = (flat_grads.dtype == presence.dtype and flat_grads.is_contiguous() and presence.is_contiguous() and
+                       presence.data_ptr() == flat_grads.data_ptr() + n * flat_grads.element_size() and
+                       flat_grads.untyped_storage().data_ptr() == presence.untyped_storage().data_ptr())
+    if contiguous_pair:
+        both = torch.as_strided(flat_grads, (n + m,), (1,))
+        dist.all_reduce(both, op=dist.ReduceOp.SUM)              # NCCL over NVLink on the GPUs, gloo in the CPU tests
+    else:
+        both = torch.cat([flat_grads, presence.to(flat_grads.dtype)])
+        dist.all_reduce(both, op=dist.ReduceOp.SUM)
+        flat_grads.copy_(both[:n])
+        presence.copy_(both[n:])
     flat_grads.div_(world)
-    dist.all_reduce(presence, op=dist.ReduceOp.MAX)
+    presence.clamp_(max=1.0)                                     # sum of 0/1 flags -> OR
     return flat_grads, presence
 
 
@@ -105,7 +119,9 @@ class DataParallelTrainer:
         self.grad_views = list(engine.named_grads().values())
         # one fused update kernel over all parameter tensors instead of torch's default foreach implementation (7 launches / step)
         self.opt = torch.optim.Adam(self.params, lr=lr, fused=bool(self.params and self.params[0].is_cuda))
-        self.presence = torch.zeros(len(self.names), dtype=torch.float32, device=engine.grads.device)
+        # presence flags live right behind the flat gradient (same storage): gradients + flags travel in ONE all_reduce
+        self.presence = engine.presence if getattr(engine, "presence", None) is not None else \
+            torch.zeros(len(self.names), dtype=torch.float32, device=engine.grads.device)
         self._patterns = {}
         self.loss_mode_cached = 0
         self.world = 1
@@ -127,10 +143,13 @@ class DataParallelTrainer:
         return self._patterns[key]
 
     def step(self, x, chrom, to_neighs, y, w, stage=2, loss_mode=0, train_mode=True, alpha=1.0, beta=1e-2,
-             median_sparsity=0.0, contractive_weight=0.0, want_loss=True, sampled=None):
+             median_sparsity=0.0, contractive_weight=0.0, want_loss=True, sampled=None, uniform_batches=False):
         """One update.  stage 1 reproduces train_epoch's three backward passes (Higashi_wrapper.py:970-1006):
         gradient of the main loss, gradient of the reconstruction loss, ratio1 = max(beta*|g_main|/|g_recon|,
-        100*median_sparsity - 3), total = alpha*main + ratio1*recon + contractive."""
+        100*median_sparsity - 3), total = alpha*main + ratio1*recon + contractive.
+        uniform_batches=True: the caller guarantees that every rank runs the same (chrom, stage, loss_mode) this step (e.g. a
+        shared chromosome schedule), so the set of parameters with a gradient is known locally and the step needs no
+        device-to-host read of the reduced presence flags."""
         self.n_steps = getattr(self, "n_steps", 0) + 1
         self.eng.set_dropout(train_mode, seed=0x5EED0000 + self.n_steps)
         self.eng.zero_grad()
@@ -154,7 +173,8 @@ class DataParallelTrainer:
         if self.world > 1:
             self.presence.copy_(pat_dev)
             reduce_gradients(self.eng.grads, self.presence)
-            pat = (self.presence > 0).tolist()            # OR over the ranks (they may have drawn different chromosomes)
+            if not uniform_batches:
+                pat = (self.presence > 0).tolist()        # OR over the ranks (they may have drawn different chromosomes)
         for p, g, on in zip(self.params, self.grad_views, pat):
             p.grad = g if on else None
         self.opt.step()

@@ -104,7 +104,10 @@ class TrainEngine:
                 off += (int(np.prod(shape)) + 3) & ~3
         self.total = off
         self.params = torch.zeros(self.total, dtype=torch.float32, device=self.device)
-        self.grads = torch.zeros(self.total, dtype=torch.float32, device=self.device)
+        # gradient buffer + one presence flag per parameter tensor behind it (one storage: one all_reduce moves both)
+        self._gbuf = torch.zeros(self.total + len(self.layout), dtype=torch.float32, device=self.device)
+        self.grads = self._gbuf[:self.total]
+        self.presence = self._gbuf[self.total:]
         for key, (o, shape) in self.layout.items():
             n = int(np.prod(shape))
             self.params[o:o + n] = torch.from_numpy(_np(sd[key]).astype(np.float32).reshape(-1)).to(self.device)

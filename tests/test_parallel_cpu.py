@@ -64,8 +64,21 @@ def _grad_worker(rank, world, port, ret):
     else:
         flat[0:4] = 3.0; pres[0] = 1
     parallel.reduce_gradients(flat, pres)
+    # the layout TrainEngine uses: presence flags right behind the gradients in ONE storage -> a single all_reduce
+    buf = torch.zeros(12 + 3)
+    flat2, pres2 = buf[:12], buf[12:]
+    if rank == 0:
+        flat2[0:4] = 1.0; flat2[4:8] = 2.0; pres2[0] = 1; pres2[1] = 1
+    else:
+        flat2[0:4] = 3.0; pres2[0] = 1
+    calls = []
+    real = dist.all_reduce
+    dist.all_reduce = lambda t, *a, **k: (calls.append(t.numel()), real(t, *a, **k))[1]
+    parallel.reduce_gradients(flat2, pres2)
+    dist.all_reduce = real
     if rank == 0:
         ret["flat"] = flat.tolist(); ret["pres"] = pres.tolist()
+        ret["flat2"] = flat2.tolist(); ret["pres2"] = pres2.tolist(); ret["calls"] = calls
     dist.destroy_process_group()
 
 
@@ -76,3 +89,5 @@ def test_two_rank_gradient_exchange():
     mp.spawn(_grad_worker, args=(world, port, ret), nprocs=world, join=True)
     assert ret["flat"] == [2.0] * 4 + [1.0] * 4 + [0.0] * 4         # mean over ranks, zeros where absent
     assert ret["pres"] == [1.0, 1.0, 0.0]                            # tensor 2: no rank had a gradient -> grad stays None
+    assert ret["flat2"] == ret["flat"] and ret["pres2"] == ret["pres"]
+    assert ret["calls"] == [15]                                      # gradients + flags in ONE collective
