@@ -335,6 +335,187 @@ __global__ void __launch_bounds__(GS_WPB * 32) neigh_gather_sparse_kernel(
     }
 }
 
+// ---------------------------------------------------------------------------------------------
+// K1a, dense short-chromosome regime (C3 / C4 shapes: tens of merged candidates per row, chromosomes of a few hundred bins).
+// The generic kernel above spends its time on the E-row gather: ~60 candidates x 256 B per token out of L2 (22 GB of L2
+// traffic per 250 cells of C3) with one warp iteration per candidate.  Here a block works on ONE chromosome:
+//   * the chromosome's E table [n_c x 64] fp32 (<= 128 KB) is staged in shared memory once per block, the gather reads it from there;
+//   * the k+1 row extents of a token are fetched together (lanes 0..k) one token ahead, and the first 32 entries of every
+//     neighbour row are requested before any of them is accumulated: one exposed round trip per token (col / val) instead of
+//     2 (k+1) dependent ones;
+//   * the gather runs 4 candidates at a time: 8 lanes per candidate, 8 columns per lane (two 128-bit shared-memory loads per
+//     8 FMAs), the 4 partial sums are combined with shuffles at the end.
+// The merge itself is the generic kernel's (row by row in neighbour order, fp32, bit-identical A_hat values); only the order of
+// the 64-column dot-product sum changes (4 interleaved partial sums), well inside the fp32-mode tolerance.
+// Blocks are assigned to chromosomes in proportion to n_c (n_c + 400) (rows x (fixed per-token cost + candidates per row)).
+// ---------------------------------------------------------------------------------------------
+#define GC_WARPS 24
+#define GC_MAX_CHROM 64
+struct GatherChromParams {
+    const int64_t* row_ptr; const int32_t* col; const float* val; const int32_t* nbr; const float* nbr_w;
+    const float* E_bin; const int* bin_off; float* neigh;
+    int k1, weighted, n_bins, cell_start, n_batch, max_nc, n_chrom;
+    int blk_first[GC_MAX_CHROM + 1];       // blocks [blk_first[c], blk_first[c + 1]) work on chromosome c
+};
+
+__global__ void __launch_bounds__(GC_WARPS * 32, 1) neigh_gather_chrom_kernel(GatherChromParams p) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    int c = 0;
+    while (c + 1 < p.n_chrom && (int)blockIdx.x >= p.blk_first[c + 1]) ++c;
+    const int jb = blockIdx.x - p.blk_first[c], nb_c = p.blk_first[c + 1] - p.blk_first[c];
+    const int off = p.bin_off[c], nc = p.bin_off[c + 1] - off;
+    // shared memory: E_c [max_nc][64] fp32, then the per-warp merge scratch
+    float* Es = reinterpret_cast<float*>(smem_raw);
+    const size_t wbytes = gather_warp_bytes(p.max_nc, 0);
+    unsigned char* base = smem_raw + (size_t)p.max_nc * 64 * sizeof(float) + (size_t)warp * wbytes;
+    const int words = (p.max_nc + 31) / 32;
+    float* acc = (float*)base;
+    unsigned* amask = (unsigned*)(base + (size_t)p.max_nc * 4);
+    unsigned short* alist = (unsigned short*)(base + (size_t)p.max_nc * 4 + (size_t)words * 4);
+    {
+        const float4* src = reinterpret_cast<const float4*>(p.E_bin + (int64_t)off * 64);
+        float4* dst = reinterpret_cast<float4*>(Es);
+        for (int i = threadIdx.x; i < nc * 16; i += blockDim.x) dst[i] = __ldg(src + i);
+    }
+    for (int i = lane; i < p.max_nc; i += 32) acc[i] = 0.f;
+    for (int i = lane; i < words; i += 32) amask[i] = 0u;
+    __syncthreads();
+
+    const int grp = lane >> 3, gl = lane & 7;
+    const int64_t n_tok = (int64_t)p.n_batch * nc;
+    // lanes 0..k: neighbour id, weight and row extent of a token, all in flight together; the extents of the warp's NEXT token
+    // are requested at the top of the current token's work, so only the col / val round trip is exposed per token
+    auto fetch_extents = [&](int64_t t, int64_t& lo, int64_t& hi, float& w) {
+        lo = 0; hi = 0; w = 1.0f;
+        if (lane < p.k1 && t < n_tok) {
+            const int cb = (int)(t / nc), l = (int)(t - (int64_t)cb * nc);
+            const int cell = p.cell_start + cb;
+            const int src = p.weighted ? __ldg(p.nbr + (int64_t)cell * p.k1 + lane) : cell;
+            if (p.weighted) w = __ldg(p.nbr_w + (int64_t)cell * p.k1 + lane);
+            const int64_t row = (int64_t)src * p.n_bins + off + l;
+            lo = __ldg(p.row_ptr + row); hi = __ldg(p.row_ptr + row + 1);
+        }
+    };
+    const int64_t t_first = (int64_t)jb * GC_WARPS + warp, t_step = (int64_t)nb_c * GC_WARPS;
+    int64_t lo_n, hi_n;
+    float w_n;
+    fetch_extents(t_first, lo_n, hi_n, w_n);
+    for (int64_t t = t_first; t < n_tok; t += t_step) {
+        const int cb = (int)(t / nc), l = (int)(t - (int64_t)cb * nc);
+        const int64_t lo_l = lo_n, hi_l = hi_n;
+        const float w_l = w_n;
+        fetch_extents(t + t_step, lo_n, hi_n, w_n);
+        // first 32 entries of every neighbour row requested before any accumulation (k+1 <= 8 rows per pass)
+        int acount = 0;
+        for (int nb0 = 0; nb0 < p.k1; nb0 += 8) {
+            int cc[8]; float vv[8];
+#pragma unroll
+            for (int q = 0; q < 8; ++q) {
+                const int64_t lo = __shfl_sync(0xffffffffu, lo_l, (nb0 + q) & 31), hi = __shfl_sync(0xffffffffu, hi_l, (nb0 + q) & 31);
+                cc[q] = -1; vv[q] = 0.f;
+                if (nb0 + q < p.k1 && lo + lane < hi) { cc[q] = __ldg(p.col + lo + lane); vv[q] = __ldg(p.val + lo + lane); }
+            }
+#pragma unroll
+            for (int q = 0; q < 8; ++q) {
+                if (nb0 + q >= p.k1) break;                       // warp-uniform
+                const float w = __shfl_sync(0xffffffffu, w_l, nb0 + q);
+                const int64_t lo = __shfl_sync(0xffffffffu, lo_l, nb0 + q), hi = __shfl_sync(0xffffffffu, hi_l, nb0 + q);
+                bool is_new = false;
+                const int cidx = cc[q];
+                if (cidx >= 0) {
+                    const float prod = p.weighted ? __fmul_rn(w, vv[q]) : vv[q];
+                    acc[cidx] = __fadd_rn(acc[cidx], prod);
+                    const unsigned bit = 1u << (cidx & 31);
+                    const unsigned old = atomicOr(&amask[cidx >> 5], bit);
+                    is_new = !(old & bit);
+                }
+                const unsigned b = __ballot_sync(0xffffffffu, is_new);
+                if (is_new) alist[acount + __popc(b & ((1u << lane) - 1u))] = (unsigned short)cidx;
+                acount += __popc(b);
+                __syncwarp();
+                if (hi - lo > 32) merge_row(p.col, p.val, lo + 32, hi, w, p.weighted != 0, acc, amask, alist, acount, lane);   // long row: the rest
+            }
+        }
+        // x pdf(0), log1p, L1 norm (Impute.py:19, 91-92)
+        float part = 0.f;
+        for (int i = lane; i < acount; i += 32) {
+            const int ci = alist[i];
+            const float v = log1pf(__fmul_rn(acc[ci], HSG_PDF0));
+            acc[ci] = v;
+            part += fabsf(v);
+        }
+        const float total = warp_sum(part);
+        const float inv_total = (total > 0.f) ? __frcp_rn(total) : 1.0f;      // one reciprocal per row (1 ulp from the division)
+        __syncwarp();
+        // gather from shared memory: group g takes candidates g, g + 4, ...; lane gl of a group owns columns 8 gl .. 8 gl + 7
+        float4 o0 = make_float4(0.f, 0.f, 0.f, 0.f), o1 = o0;
+#pragma unroll 2
+        for (int i = grp; i < acount; i += 4) {
+            const int ci = alist[i];
+            const float a = acc[ci] * inv_total;
+            const float4* er = reinterpret_cast<const float4*>(Es + ci * 64 + gl * 8);
+            const float4 x0 = er[0], x1 = er[1];
+            o0.x = fmaf(a, x0.x, o0.x); o0.y = fmaf(a, x0.y, o0.y); o0.z = fmaf(a, x0.z, o0.z); o0.w = fmaf(a, x0.w, o0.w);
+            o1.x = fmaf(a, x1.x, o1.x); o1.y = fmaf(a, x1.y, o1.y); o1.z = fmaf(a, x1.z, o1.z); o1.w = fmaf(a, x1.w, o1.w);
+        }
+#pragma unroll
+        for (int sh = 8; sh <= 16; sh <<= 1) {
+            o0.x += __shfl_xor_sync(0xffffffffu, o0.x, sh); o0.y += __shfl_xor_sync(0xffffffffu, o0.y, sh);
+            o0.z += __shfl_xor_sync(0xffffffffu, o0.z, sh); o0.w += __shfl_xor_sync(0xffffffffu, o0.w, sh);
+            o1.x += __shfl_xor_sync(0xffffffffu, o1.x, sh); o1.y += __shfl_xor_sync(0xffffffffu, o1.y, sh);
+            o1.z += __shfl_xor_sync(0xffffffffu, o1.z, sh); o1.w += __shfl_xor_sync(0xffffffffu, o1.w, sh);
+        }
+        if (grp == 0) {
+            float4* dst = reinterpret_cast<float4*>(p.neigh + ((int64_t)cb * p.n_bins + off + l) * 64 + gl * 8);
+            dst[0] = o0; dst[1] = o1;
+        }
+        __syncwarp();
+        for (int i = lane; i < acount; i += 32) {            // reset scratch for the next token
+            const int ci = alist[i];
+            acc[ci] = 0.f;
+            amask[ci >> 5] = 0u;
+        }
+        __syncwarp();
+    }
+}
+
+// returns 1 if the chromosome-block kernel was launched (it then covers every token of the batch)
+static int try_launch_gather_chrom(hsg_ctx* c, int cell_start, int n_batch, int max_nc, cudaStream_t s, bool* done) {
+    *done = false;
+    const size_t smem = (size_t)max_nc * 64 * sizeof(float) + (size_t)GC_WARPS * gather_warp_bytes(max_nc, 0);
+    if (c->d != 64 || c->ltr != 0 || c->n_chrom > GC_MAX_CHROM || smem > 220 * 1024 || c->k1 > 32) return 0;
+    GatherChromParams p;
+    p.row_ptr = c->row_ptr; p.col = c->col; p.val = c->val; p.nbr = c->nbr; p.nbr_w = c->nbr_w; p.E_bin = c->E_bin;
+    p.bin_off = c->d_bin_off; p.neigh = c->neigh; p.k1 = c->k1; p.weighted = c->weighted ? 1 : 0; p.n_bins = c->n_bins;
+    p.cell_start = cell_start; p.n_batch = n_batch; p.max_nc = max_nc; p.n_chrom = c->n_chrom;
+    // blocks per chromosome in proportion to n_c (n_c + 400): rows x (fixed cost of a token -- three dependent global round
+    // trips -- plus the candidates of a row, which grow with n_c), at least one, about 2 waves in total
+    auto weight = [](int b) { return (double)b * ((double)b + 400.0); };
+    double tot = 0;
+    for (int b : c->bins) tot += weight(b);
+    const int target = 2 * c->n_sm;
+    int first = 0;
+    for (int j = 0; j < c->n_chrom; ++j) {
+        p.blk_first[j] = first;
+        const int64_t toks = (int64_t)n_batch * c->bins[j];
+        int nb = (int)(target * weight(c->bins[j]) / tot + 0.5);
+        nb = (int)std::max<int64_t>(1, std::min<int64_t>(nb, (toks + GC_WARPS - 1) / GC_WARPS));
+        first += nb;
+    }
+    p.blk_first[c->n_chrom] = first;
+    static bool attr_set = false;
+    if (!attr_set) {
+        HSG_CUDA(cudaFuncSetAttribute(neigh_gather_chrom_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024));
+        attr_set = true;
+    }
+    neigh_gather_chrom_kernel<<<first, GC_WARPS * 32, smem, s>>>(p);
+    c->launches++;
+    HSG_CUDA(cudaGetLastError());
+    *done = true;
+    return 0;
+}
+
 int launch_gather(hsg_ctx* c, const int*, int cell_start, int n_batch, cudaStream_t s) {
     int max_nc = 0;
     for (int b : c->bins) max_nc = b > max_nc ? b : max_nc;
@@ -357,7 +538,13 @@ int launch_gather(hsg_ctx* c, const int*, int cell_start, int n_batch, cudaStrea
     // accumulator (4 B x max_nc per warp) leaves the generic kernel with a handful of warps per SM (measured, C3 / C4 / C5 shapes).
     const double avg_cand = (double)c->k1 * (double)c->nnz / (double)std::max<int64_t>(c->n_rows, 1);
     const bool sparse_ok = c->d == 64 && c->ltr == 0 && c->k1 <= 8 && n_tok < (1LL << 31) && c->gather_sparse;
-    if (sparse_ok && (avg_cand <= 16.0 || max_nc > 1536)) {
+    const bool to_sparse = sparse_ok && (avg_cand <= 16.0 || max_nc > 1536);
+    if (!to_sparse && c->gather_chrom) {        // dense rows, short chromosomes: one chromosome per block, E_c in shared memory
+        bool done = false;
+        if (try_launch_gather_chrom(c, cell_start, n_batch, max_nc, s, &done)) return 1;
+        if (done) return 0;
+    }
+    if (to_sparse) {
         if (c->ovf_cap < n_tok + 1) {
             if (c->ovf_list) cudaFree(c->ovf_list);
             HSG_CUDA(cudaMalloc((void**)&c->ovf_list, (size_t)(n_tok + 1) * sizeof(int)));

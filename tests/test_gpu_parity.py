@@ -180,6 +180,14 @@ def test_gather_paths(density, k):
     _synthetic_case(k, 0, 64, "fp32", [120, 40], [0, 5, 39], density=density)
 
 
+@pytest.mark.parametrize("density,k", [(0.3, 4), (0.02, 9)])
+def test_gather_generic_kernel(density, k, monkeypatch):
+    """Dense rows on short chromosomes normally take the chromosome-block kernel (E table of the chromosome in shared memory);
+    with it switched off the generic warp-per-token kernel must give the same answer."""
+    monkeypatch.setenv("HSG_GATHER_CHROM", "0")
+    _synthetic_case(k, 0, 64, "fp32", [120, 40], [0, 5, 39], density=density)
+
+
 @pytest.mark.parametrize("density", [0.004, 0.009])
 def test_gather_long_chromosome(density):
     """Chromosomes longer than 1536 bins with medium-dense rows take the 64- / 96-candidate register kernels (plus the overflow
