@@ -20,6 +20,14 @@
 // parity bar), with fp16 it is <= 5e-4 at identical tensor throughput (scripts/bf16_emulation.py, scripts/tail_error.py).
 #include "umma_common.cuh"
 
+// 1: build the ctx tile of token t + 1 between the issue and the wait of token t's classifier MMA.  Measured on the B200
+// (C2, 12 steps): 54.3-54.7 ms against 53.76 ms without -- the four warpgroups already fill each other's MMA waits -- so it
+// stays off.  Also measured and dropped: MMA 1 as two N = 64 halves with separate commits (variance pass under the g half):
+// 56.2 ms against 53.6 ms.
+#ifndef K2_OVERLAP_ATT
+#define K2_OVERLAP_ATT 0
+#endif
+
 template <bool HI>
 __global__ void __launch_bounds__(UM_THREADS, 1) score_umma_kernel(UmmaParams p) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -29,13 +37,13 @@ __global__ void __launch_bounds__(UM_THREADS, 1) score_umma_kernel(UmmaParams p)
     const uint32_t sbase = (sraw + 1023u) & ~1023u;
     unsigned char* smem = smem_raw + (sbase - sraw);
     const float* cst = p.cst;
-    const uint32_t bar_w = sbase + SM_BAR;                 // weights landed
-    const uint32_t bar_mma = sbase + SM_BAR + 8 + wg * 8;  // this warpgroup's MMA completion
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + SM_TMEM);
+    const uint32_t bar_w = sbase + SM_BAR_OF(HI);                 // weights landed
+    const uint32_t bar_mma = sbase + SM_BAR_OF(HI) + 8 + wg * 8;  // this warpgroup's MMA completion
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + SM_TMEM_OF(HI));
 
     if (tid == 0) {
         mbar_init(bar_w, 1);
-        for (int i = 0; i < UM_WG; ++i) mbar_init(sbase + SM_BAR + 8 + i * 8, 1);
+        for (int i = 0; i < UM_WG; ++i) mbar_init(sbase + SM_BAR_OF(HI) + 8 + i * 8, 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (tid < 32) {     // warp 0 allocates all 512 TMEM columns (one CTA per SM)
@@ -53,7 +61,7 @@ __global__ void __launch_bounds__(UM_THREADS, 1) score_umma_kernel(UmmaParams p)
     const uint32_t t_lane = ((uint32_t)(warp_in_wg * 32)) << 16;
     const uint32_t t_y = tmem_base + (uint32_t)(wg * 128);          // columns [0,64) of this warpgroup: y, then z
     const uint32_t t_h = t_y + 64;                                  // columns [64,128): h, then c
-    const uint32_t a_base = sbase + SM_A0 + wg * SM_A_BYTES;
+    const uint32_t a_base = sbase + SM_A0_OF(HI) + wg * SM_A_BYTES;
     mbar_wait(bar_w, 0);
 
     uint32_t phase = 0;
@@ -68,7 +76,7 @@ __global__ void __launch_bounds__(UM_THREADS, 1) score_umma_kernel(UmmaParams p)
         const bool valid = tile_ok && pi < p.P;
         const int2 pr = p.pairs[pi < p.P ? pi : (p.P - 1)];
         const float bias = valid ? p.pair_bias[pi] : 0.f;
-        int2* s_pr_wg = reinterpret_cast<int2*>(smem + SM_PAIRS) + wg * 128;    // rows of this warpgroup's tile
+        int2* s_pr_wg = reinterpret_cast<int2*>(smem + SM_PAIRS_OF(HI)) + wg * 128;    // rows of this warpgroup's tile
         __syncwarp();
         s_pr_wg[wtid] = pr;                                                      // a warp only reads its own 32 rows
         __syncwarp();
@@ -135,11 +143,13 @@ __global__ void __launch_bounds__(UM_THREADS, 1) score_umma_kernel(UmmaParams p)
                     sts128(a_chunk_addr(a_base, arow, h), pk[0], pk[1], pk[2], pk[3]);
                     sts128(a_chunk_addr(a_base, arow, 8 + h), pk[4], pk[5], pk[6], pk[7]);
                 }
-            } else if (t == 0) {
-                // fast variant: only the first token's attention runs here; the ctx tile of token t + 1 is built while MMA 3 of
-                // token t is in flight (the A tile is free as soon as MMA 1 of token t has completed), see below
-                attention_fast<0, 8>(p.QK16, p.XS, p.binV16, p.cellV16, s_pr_wg, lane, warp_in_wg * 32, a_base,
-                                     (uint32_t)cb * (uint32_t)p.n_bins, cell);
+            } else if (!K2_OVERLAP_ATT || t == 0) {
+                // with K2_OVERLAP_ATT only the first token's attention runs here; the ctx tile of token t + 1 is then built while
+                // MMA 3 of token t is in flight (the A tile is free as soon as MMA 1 of token t has completed), see below
+                const uint32_t tokbase = (uint32_t)cb * (uint32_t)p.n_bins;
+                if (t == 0) attention_fast<0, 8>(p.QK16, p.XS, p.binV16, p.cellV16, s_pr_wg, lane, warp_in_wg * 32, a_base, tokbase, cell);
+                else if (t == 1) attention_fast<1, 8>(p.QK16, p.XS, p.binV16, p.cellV16, s_pr_wg, lane, warp_in_wg * 32, a_base, tokbase, cell);
+                else attention_fast<2, 8>(p.QK16, p.XS, p.binV16, p.cellV16, s_pr_wg, lane, warp_in_wg * 32, a_base, tokbase, cell);
             }
             // ------------------------------------------------------------------ MMA 1: [y_c | g] = ctx . [fc1c ; W0' fc1c]^T
             // ONE N=128 GEMM gives y_c = ctx . fc1c^T (columns 0..63: y with its row mean already removed, because the mean over
@@ -288,7 +298,7 @@ __global__ void __launch_bounds__(UM_THREADS, 1) score_umma_kernel(UmmaParams p)
                 umma_f16_ts(t_y, t_h + 32, umma_desc(sbase + SMF_X_C0B), umma_idesc_f16(128, 32), 1u);  // + cb0 / 2
             }
             ISSUE_END()
-            if constexpr (!HI) {        // next token's attention overlaps the classifier MMA round trip
+            if constexpr (!HI && K2_OVERLAP_ATT) {        // next token's attention overlaps the classifier MMA round trip
                 const uint32_t tokbase = (uint32_t)cb * (uint32_t)p.n_bins;
                 if (t == 0) attention_fast<1, 8>(p.QK16, p.XS, p.binV16, p.cellV16, s_pr_wg, lane, warp_in_wg * 32, a_base, tokbase, cell);
                 else if (t == 1) attention_fast<2, 8>(p.QK16, p.XS, p.binV16, p.cellV16, s_pr_wg, lane, warp_in_wg * 32, a_base, tokbase, cell);
@@ -461,12 +471,12 @@ int launch_score_pairs_umma(hsg_ctx* c, int cell_start, int n_batch, float* out,
     int grid = (int)(quads < c->n_sm ? quads : c->n_sm);
     static bool attr_set = false;
     if (!attr_set) {
-        HSG_CUDA(cudaFuncSetAttribute(score_umma_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, SM_TOTAL + 1024));
-        HSG_CUDA(cudaFuncSetAttribute(score_umma_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, SM_TOTAL + 1024));
+        HSG_CUDA(cudaFuncSetAttribute(score_umma_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, SM_TOTAL_OF(0) + 1024));
+        HSG_CUDA(cudaFuncSetAttribute(score_umma_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, SM_TOTAL_OF(1) + 1024));
         attr_set = true;
     }
-    if (c->umma_hi) score_umma_kernel<true><<<grid, UM_THREADS, SM_TOTAL + 1024, s>>>(p);
-    else score_umma_kernel<false><<<grid, UM_THREADS, SM_TOTAL + 1024, s>>>(p);
+    if (c->umma_hi) score_umma_kernel<true><<<grid, UM_THREADS, SM_TOTAL_OF(1) + 1024, s>>>(p);
+    else score_umma_kernel<false><<<grid, UM_THREADS, SM_TOTAL_OF(0) + 1024, s>>>(p);
     c->launches++;
     HSG_CUDA(cudaGetLastError());
     return 0;

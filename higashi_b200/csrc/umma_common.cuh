@@ -26,9 +26,10 @@
 #define SMH_B_FC1_LO 45056    // [128 x 128] low halves
 #define SMH_B_C0_LO 77824     // [32 x 64]   low halves
 #define SMH_WIMG_BYTES 81920
-#define SM_A0 81920           // 4 x 32 KB ctx tiles (one per warpgroup)
+// everything behind the weight images is placed relative to the end of the variant's images (HI = 1: high-accuracy variant), so
+// the fast variant asks for ~190 KB instead of ~214 KB and the SM keeps a 60 KB L1 (196 KB carve-out) instead of 28 KB
+#define SM_A0_OF(HI) ((HI) ? SMH_WIMG_BYTES : SMF_WIMG_BYTES)       // 4 x 32 KB ctx tiles (one per warpgroup)
 #define SM_A_BYTES 32768
-#define SM_CONST (SM_A0 + UM_WG * SM_A_BYTES)   // fp32 constants
 #define CST_B0F 0
 #define CST_G1 128
 #define CST_CB0 192
@@ -36,10 +37,11 @@
 #define CST_CB1 256
 #define CST_B1C 264           // b1 - mean(b1): every LayerNorm input is produced already centred
 #define CST_COUNT 328
-#define SM_BAR (SM_CONST + CST_COUNT * 4)       // 8 mbarriers
-#define SM_TMEM (SM_BAR + 64)
-#define SM_PAIRS (SM_TMEM + 16)                 // int2 [UM_WG * 128]: (bin_i, bin_j) of every row of the current tiles
-#define SM_TOTAL (SM_PAIRS + UM_WG * 128 * 8)
+#define SM_CONST_OF(HI) (SM_A0_OF(HI) + UM_WG * SM_A_BYTES)         // fp32 constants (reserved)
+#define SM_BAR_OF(HI) (SM_CONST_OF(HI) + CST_COUNT * 4)            // 8 mbarriers
+#define SM_TMEM_OF(HI) (SM_BAR_OF(HI) + 64)
+#define SM_PAIRS_OF(HI) (SM_TMEM_OF(HI) + 16)                      // int2 [UM_WG * 128]: (bin_i, bin_j) of every row of the current tiles
+#define SM_TOTAL_OF(HI) (SM_PAIRS_OF(HI) + UM_WG * 128 * 8)
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
