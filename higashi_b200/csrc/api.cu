@@ -92,6 +92,7 @@ extern "C" int hsg_destroy(hsg_ctx* c) {
     dev_free(c->E_cell); dev_free(c->E_bin); dev_free(c->d_bin_off); dev_free(c->d_bin_chrom);
     dev_free(c->row_ptr); dev_free(c->col); dev_free(c->val); dev_free(c->nbr); dev_free(c->nbr_w); dev_free(c->pairs);
     dev_free(c->row_ptr2); dev_free(c->col2); dev_free(c->val2);
+    if (c->ins_ws) cudaFree(c->ins_ws);
     if (c->h2d_stream) cudaStreamDestroy(c->h2d_stream);
     if (c->staged_ev) cudaEventDestroy(c->staged_ev);
     for (int i = 0; i < 8; ++i) if (c->ev[i]) cudaEventDestroy(c->ev[i]);

@@ -128,6 +128,7 @@ struct hsg_ctx {
     bool profiling = false;
     float last_ms[4] = {0, 0, 0, 0};
     int64_t launches = 0;
+    void* ins_ws = nullptr; size_t ins_ws_bytes = 0;      // hsg_insulation workspace (grow-only)
 };
 
 // ---- kernel launchers (definitions in the .cu files) ---------------------------------------

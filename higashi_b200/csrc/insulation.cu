@@ -21,36 +21,85 @@
 #define INS_FIX_SCALE 1099511627776.0      // 2^40
 __device__ __forceinline__ void fix_add(unsigned long long* p, long long q) { atomicAdd(p, (unsigned long long)q); }
 
-// rowsum[cell][a] += v, rowsum[cell][b] += v   (symmetric matrix, masked rows / columns dropped)
-__global__ void ins_rowsum_kernel(const float* __restrict__ scores, int64_t ld, int64_t off, const int2* __restrict__ pairs, int64_t P,
-                                  int goff, int n, int n_cells, const unsigned char* __restrict__ keep, double* __restrict__ rowsum) {
+// rowsum[cell][a] += v, rowsum[cell][b] += v   (symmetric matrix, masked rows / columns dropped), in 64-bit fixed point
+// (v * 2^30; |score| < 1e5 keeps a row of 8192 bins inside 63 bits) so that shared-memory and global integer atomics can be mixed
+// and the sums do not depend on their order.
+// A block owns INS_CHUNK consecutive pairs.  Pairs are stored row-major (a fixed, b ascending), so a chunk touches the bins of a
+// narrow window behind its first row: both contributions go to a shared-memory window first (out-of-window bins straight to
+// global memory) and the window is flushed with one global atomic per touched bin -- ~8x fewer global atomics than one per pair.
+// The lanes of a warp mostly share `a`: their contributions to rowsum[a] are summed with a segmented shuffle scan and the last
+// lane of each run issues ONE atomic; the b's of a run are consecutive bins (no contention inside the warp).
+#define INS_CHUNK 4096
+#define INS_WIN 1024
+#define INS_ROW_SCALE 1073741824.0          // 2^30
+__global__ void __launch_bounds__(256) ins_rowsum_kernel(const float* __restrict__ scores, int64_t ld, int64_t off,
+                                                         const int2* __restrict__ pairs, int64_t P, int goff, int n, int n_cells,
+                                                         const unsigned char* __restrict__ keep, unsigned long long* __restrict__ rowsum) {
+    __shared__ unsigned long long win[INS_WIN];
+    const int cell = blockIdx.y, lane = threadIdx.x & 31;
+    const int64_t chunk0 = (int64_t)blockIdx.x * INS_CHUNK;
+    for (int j = threadIdx.x; j < INS_WIN; j += 256) win[j] = 0ull;
+    const int base = pairs[off + chunk0].x - goff;          // chunk0 < P by construction of the grid
+    __syncthreads();
+    unsigned long long* rs = rowsum + (int64_t)cell * n;
+    for (int k = 0; k < INS_CHUNK / 256; ++k) {
+        const int64_t i = chunk0 + (int64_t)k * 256 + threadIdx.x;
+        int a = -1, b = -1;
+        long long q = 0;
+        if (i < P) {
+            const int2 pr = pairs[off + i];
+            a = pr.x - goff; b = pr.y - goff;
+            if (!keep || (keep[a] && keep[b])) q = llrint((double)scores[(int64_t)cell * ld + off + i] * INS_ROW_SCALE);
+        }
+        if (q != 0) {                                       // a diagonal pair (a == b) counts twice: once here, once below
+            const unsigned ib = (unsigned)(b - base);
+            if (ib < INS_WIN) atomicAdd(&win[ib], (unsigned long long)q); else atomicAdd(rs + b, (unsigned long long)q);
+        }
+        // segmented inclusive scan over runs of equal a (lanes are in pair order): the LAST lane of a run holds its sum
+        long long sum = q;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+            const long long up = __shfl_up_sync(0xffffffffu, sum, d);
+            const int au = __shfl_up_sync(0xffffffffu, a, d);
+            if (lane >= d && au == a) sum += up;
+        }
+        const int an = __shfl_down_sync(0xffffffffu, a, 1);
+        if (a >= 0 && (lane == 31 || an != a) && sum != 0) {
+            const unsigned ia = (unsigned)(a - base);
+            if (ia < INS_WIN) atomicAdd(&win[ia], (unsigned long long)sum); else atomicAdd(rs + a, (unsigned long long)sum);
+        }
+    }
+    __syncthreads();
+    for (int j = threadIdx.x; j < INS_WIN; j += 256) {
+        const unsigned long long v = win[j];
+        if (v != 0ull && base + j < n) atomicAdd(rs + base + j, v);
+    }
+}
+
+// inv[cell][a] = 1 / sqrt(rowsum[cell][a])  (0 where the coverage is not positive: sqrt_norm maps those rows to 0)
+__global__ void ins_invsqrt_kernel(const unsigned long long* __restrict__ rowsum, int64_t total, double* __restrict__ inv) {
     const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    const int cell = blockIdx.y;
-    if (i >= P || cell >= n_cells) return;
-    const int2 pr = pairs[off + i];
-    const int a = pr.x - goff, b = pr.y - goff;
-    if (keep && (!keep[a] || !keep[b])) return;
-    const double v = (double)scores[(int64_t)cell * ld + off + i];
-    if (v == 0.0) return;
-    atomicAdd(rowsum + (int64_t)cell * n + a, v);
-    if (b != a) atomicAdd(rowsum + (int64_t)cell * n + b, v); else atomicAdd(rowsum + (int64_t)cell * n + a, v);
+    if (i >= total) return;
+    const double r = (double)(long long)rowsum[i] * (1.0 / INS_ROW_SCALE);
+    inv[i] = (r > 0.0) ? 1.0 / sqrt(r) : 0.0;
 }
 
 // range updates of the difference arrays: diff[cell][0][.] numerator, diff[cell][1][.] denominator (n + 1 entries each)
 __global__ void ins_diff_kernel(const float* __restrict__ scores, int64_t ld, int64_t off, const int2* __restrict__ pairs, int64_t P,
                                 int goff, int n, int n_cells, int w, const unsigned char* __restrict__ keep,
-                                const double* __restrict__ rowsum, unsigned long long* __restrict__ diff) {
+                                const double* __restrict__ inv, unsigned long long* __restrict__ diff) {
     const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     const int cell = blockIdx.y;
     if (i >= P || cell >= n_cells) return;
     const int2 pr = pairs[off + i];
     int a = pr.x - goff, b = pr.y - goff;
-    if (keep && (!keep[a] || !keep[b])) return;
     if (a > b) { int t = a; a = b; b = t; }
+    if (b - a > 2 * w) return;                                       // outside every window: no numerator, no denominator range
+    if (keep && (!keep[a] || !keep[b])) return;
     const double raw = (double)scores[(int64_t)cell * ld + off + i];
-    const double ra = rowsum[(int64_t)cell * n + a], rb = rowsum[(int64_t)cell * n + b];
-    if (raw == 0.0 || !(ra > 0.0) || !(rb > 0.0)) return;          // sqrt_norm: division by a zero coverage -> 0
-    const double v = raw / sqrt(ra) / sqrt(rb);
+    const double ia = inv[(int64_t)cell * n + a], ib = inv[(int64_t)cell * n + b];
+    if (raw == 0.0 || ia == 0.0 || ib == 0.0) return;               // sqrt_norm: division by a zero coverage -> 0
+    const double v = raw * ia * ib;
     if (!isfinite(v)) return;
     const long long q = llrint(v * INS_FIX_SCALE);
     if (q == 0) return;
@@ -78,15 +127,26 @@ __global__ void ins_finish_kernel(const unsigned long long* __restrict__ diff, i
     const unsigned long long* num = diff + (int64_t)cell * 2 * (n + 1);
     const unsigned long long* den = num + (n + 1);
     double* sc = score64 + (int64_t)cell * n;
-    if (threadIdx.x == 0) {                       // n is a few thousand: one serial (exact, integer) scan per cell
-        unsigned long long sn = 0, sd = 0;
-        for (int i = 0; i < n; ++i) {
-            sn += num[i]; sd += den[i];
-            double v = (double)(long long)sn / (double)(long long)sd;
-            if (isnan(v) || sd == 0) v = 1.0;     // 0 / 0 -> nan -> 1 (the numerator is a subset of the denominator)
-            if (discard && discard[i]) v = 1.0;
-            sc[i] = v;
-        }
+    // exact (integer, wrap-around) prefix sums of both difference arrays: every thread scans a contiguous segment, the 256 segment
+    // totals are scanned through shared memory, then every thread finishes its segment
+    __shared__ unsigned long long tot_n[256], tot_d[256];
+    const int seg = (n + 255) / 256, i0 = min(n, (int)threadIdx.x * seg), i1 = min(n, i0 + seg);
+    unsigned long long sn = 0, sd = 0;
+    for (int i = i0; i < i1; ++i) { sn += num[i]; sd += den[i]; }
+    tot_n[threadIdx.x] = sn; tot_d[threadIdx.x] = sd;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        unsigned long long an = 0, ad = 0;
+        for (int t = 0; t < 256; ++t) { const unsigned long long xn = tot_n[t], xd = tot_d[t]; tot_n[t] = an; tot_d[t] = ad; an += xn; ad += xd; }
+    }
+    __syncthreads();
+    sn = tot_n[threadIdx.x]; sd = tot_d[threadIdx.x];
+    for (int i = i0; i < i1; ++i) {
+        sn += num[i]; sd += den[i];
+        double v = (double)(long long)sn / (double)(long long)sd;
+        if (isnan(v) || sd == 0) v = 1.0;         // 0 / 0 -> nan -> 1 (the numerator is a subset of the denominator)
+        if (discard && discard[i]) v = 1.0;
+        sc[i] = v;
     }
     __syncthreads();
     for (int i = threadIdx.x; i < n; i += blockDim.x) {
@@ -112,46 +172,46 @@ extern "C" int hsg_insulation(hsg_ctx* c, int sel_slot, const float* scores_dev,
     cudaStream_t s = (cudaStream_t)stream;
     const int chrom = c->sel_chroms[sel_slot], n = c->bins[chrom], goff = c->bin_off[chrom];
     const int64_t off = c->sel_off[sel_slot], P = c->sel_P[sel_slot];
-    double *rowsum = nullptr, *sc64 = nullptr;
-    unsigned long long* diff = nullptr;
-    float* d_score = nullptr;
-    unsigned char *d_border = nullptr, *d_keep = nullptr, *d_discard = nullptr;
-    auto cleanup = [&]() {
-        cudaFree(rowsum); cudaFree(diff); cudaFree(sc64); cudaFree(d_score); cudaFree(d_border); cudaFree(d_keep); cudaFree(d_discard);
-    };
-    const size_t nb = (size_t)n_batch;
-#define INS_CUDA(x) do { cudaError_t e_ = (x); if (e_ != cudaSuccess) { cleanup(); hsg_set_error(std::string("CUDA error: ") + cudaGetErrorString(e_)); return 1; } } while (0)
-    INS_CUDA(cudaMalloc((void**)&rowsum, nb * n * sizeof(double)));
-    INS_CUDA(cudaMalloc((void**)&diff, nb * 2 * (n + 1) * sizeof(unsigned long long)));
-    INS_CUDA(cudaMalloc((void**)&sc64, nb * n * sizeof(double)));
-    INS_CUDA(cudaMalloc((void**)&d_score, nb * n * sizeof(float)));
-    INS_CUDA(cudaMalloc((void**)&d_border, nb * n));
-    INS_CUDA(cudaMemsetAsync(rowsum, 0, nb * n * sizeof(double), s));
-    INS_CUDA(cudaMemsetAsync(diff, 0, nb * 2 * (n + 1) * sizeof(unsigned long long), s));
-    if (keep_host) {
-        INS_CUDA(cudaMalloc((void**)&d_keep, n));
-        INS_CUDA(cudaMemcpyAsync(d_keep, keep_host, n, cudaMemcpyHostToDevice, s));
+    // one grow-only workspace per context: [rowsum | diff] (zeroed per call) | inv | score64 | score | border | keep | discard
+    const size_t nb = (size_t)n_batch, cells_n = nb * n;
+    auto up = [](size_t b) { return (b + 255) & ~(size_t)255; };
+    const size_t o_rowsum = 0, o_diff = o_rowsum + up(cells_n * 8), o_inv = o_diff + up(nb * 2 * (n + 1) * 8),
+                 o_sc64 = o_inv + up(cells_n * 8), o_score = o_sc64 + up(cells_n * 8), o_border = o_score + up(cells_n * 4),
+                 o_keep = o_border + up(cells_n), o_disc = o_keep + up(n), total = o_disc + up(n);
+    if (c->ins_ws_bytes < total) {
+        if (c->ins_ws) { HSG_CUDA(cudaStreamSynchronize(s)); cudaFree(c->ins_ws); c->ins_ws = nullptr; c->ins_ws_bytes = 0; }
+        HSG_CUDA(cudaMalloc(&c->ins_ws, total));
+        c->ins_ws_bytes = total;
     }
-    if (discard_host) {
-        INS_CUDA(cudaMalloc((void**)&d_discard, n));
-        INS_CUDA(cudaMemcpyAsync(d_discard, discard_host, n, cudaMemcpyHostToDevice, s));
-    }
+    unsigned char* ws = (unsigned char*)c->ins_ws;
+    unsigned long long* rowsum = (unsigned long long*)(ws + o_rowsum);
+    unsigned long long* diff = (unsigned long long*)(ws + o_diff);
+    double* inv = (double*)(ws + o_inv);
+    double* sc64 = (double*)(ws + o_sc64);
+    float* d_score = (float*)(ws + o_score);
+    unsigned char* d_border = ws + o_border;
+    unsigned char* d_keep = keep_host ? ws + o_keep : nullptr;
+    unsigned char* d_discard = discard_host ? ws + o_disc : nullptr;
+    HSG_CUDA(cudaMemsetAsync(ws, 0, o_inv, s));
+    if (keep_host) HSG_CUDA(cudaMemcpyAsync(d_keep, keep_host, n, cudaMemcpyHostToDevice, s));
+    if (discard_host) HSG_CUDA(cudaMemcpyAsync(d_discard, discard_host, n, cudaMemcpyHostToDevice, s));
     if (P > 0) {
-        dim3 grid((unsigned)((P + 255) / 256), (unsigned)n_batch);
-        ins_rowsum_kernel<<<grid, 256, 0, s>>>(scores_dev, c->P, off, c->pairs, P, goff, n, n_batch, d_keep, rowsum);
+        dim3 grid((unsigned)((P + 255) / 256), (unsigned)n_batch), grid_rs((unsigned)((P + INS_CHUNK - 1) / INS_CHUNK), (unsigned)n_batch);
+        ins_rowsum_kernel<<<grid_rs, 256, 0, s>>>(scores_dev, c->P, off, c->pairs, P, goff, n, n_batch, d_keep, rowsum);
         c->launches++;
-        INS_CUDA(cudaGetLastError());
-        ins_diff_kernel<<<grid, 256, 0, s>>>(scores_dev, c->P, off, c->pairs, P, goff, n, n_batch, window_bins, d_keep, rowsum, diff);
+        HSG_CUDA(cudaGetLastError());
+        ins_invsqrt_kernel<<<(unsigned)((cells_n + 255) / 256), 256, 0, s>>>(rowsum, (int64_t)cells_n, inv);
         c->launches++;
-        INS_CUDA(cudaGetLastError());
+        HSG_CUDA(cudaGetLastError());
+        ins_diff_kernel<<<grid, 256, 0, s>>>(scores_dev, c->P, off, c->pairs, P, goff, n, n_batch, window_bins, d_keep, inv, diff);
+        c->launches++;
+        HSG_CUDA(cudaGetLastError());
     }
     ins_finish_kernel<<<n_batch, 256, 0, s>>>(diff, n, tad_order, d_discard, d_score, d_border, sc64);
     c->launches++;
-    INS_CUDA(cudaGetLastError());
-    INS_CUDA(cudaMemcpyAsync(score_out_host, d_score, nb * n * sizeof(float), cudaMemcpyDeviceToHost, s));
-    INS_CUDA(cudaMemcpyAsync(border_out_host, d_border, nb * n, cudaMemcpyDeviceToHost, s));
-    INS_CUDA(cudaStreamSynchronize(s));
-#undef INS_CUDA
-    cleanup();
+    HSG_CUDA(cudaGetLastError());
+    HSG_CUDA(cudaMemcpyAsync(score_out_host, d_score, cells_n * sizeof(float), cudaMemcpyDeviceToHost, s));
+    HSG_CUDA(cudaMemcpyAsync(border_out_host, d_border, cells_n, cudaMemcpyDeviceToHost, s));
+    HSG_CUDA(cudaStreamSynchronize(s));
     return 0;
 }
