@@ -466,6 +466,24 @@ def main():
                 "stage_ms_per_step": {"gather_K1a": stage[0] / nprof, "project_K1b": stage[1] / nprof, "scorer_K2": k2_ms_per_step},
                 "k2_share_of_step": float(stage[2] / max(stage[3], 1e-9))}
 
+    # secondary roofline: the gather (K1a) against the measured HBM copy bandwidth.  Algorithmic bytes per cell:
+    # the CSR rows of the cell and its k neighbours (8 B per stored entry + the row extents) + the [n_bins, d] fp32 rows it writes.
+    try:
+        rp = ds.csr.row_ptr
+        rows_per_cell = int(sum(ds.bins))
+        nnz_cell = np.diff(rp[::rows_per_cell]).astype(np.float64)            # stored entries per cell
+        k1 = 1 if nbr is None else int(np.asarray(nbr).shape[1])
+        cells_prof = np.concatenate([np.arange((i % n_ranges) * cps, (i % n_ranges) * cps + cps) for i in range(nprof)])
+        src = cells_prof[:, None] if nbr is None else (np.asarray(nbr)[cells_prof] - 1)
+        bytes_k1a = float((8.0 * nnz_cell[src].sum() + 16.0 * rows_per_cell * k1 * len(cells_prof) + 4.0 * ds.d * rows_per_cell * len(cells_prof)))
+        hbm_peak = float(peaks.get("hbm_gbs", 6650.0))
+        gbs = bytes_k1a / max(stage[0] * 1e-3, 1e-12) / 1e9
+        roofline["gather_K1a"] = {"bound": "hbm", "achieved": gbs, "peak": hbm_peak, "unit": "GB/s", "frac": gbs / hbm_peak,
+                                  "note": "algorithmic bytes (k+1 CSR rows per token: 8 B per entry + extents, + the fp32 row written) / K1a device "
+                                          "time; the kernel is bound by its per-candidate instruction count, not by HBM (DESIGN.md section 5)"}
+    except Exception as e:                                                     # never lose the headline line over the secondary figure
+        roofline["gather_K1a"] = {"error": str(e)}
+
     # ---- e2e: host buffers in, host buffers out, through the C ABI
     e2e = None
     if not args.no_e2e:

@@ -69,3 +69,28 @@ def test_insulation_after_imputation():
             assert np.array_equal(border[c], b_ref)
         off += P
     eng.close()
+
+
+@pytest.mark.parametrize("n,min_bin,band,w_ins,order", [(70, 0, 15, 4, 2), (40, 1, 39, 60, 3), (33, 2, 9, 3, 1)])
+def test_insulation_edge_cases(n, min_bin, band, w_ins, order):
+    """Diagonal pairs in the list (min_bin = 0: m + m^T doubles them), a window wider than the chromosome, pairs starting at distance 2
+    (a one-bin window over such a list makes every score exactly 1/2 in exact arithmetic -- the reference's boundary calls are then
+    decided by its rounding noise, so that degenerate case is not compared); exact zeros in the scores."""
+    from higashi_b200.engine import ScorerEngine
+    from oracle import insulation as OX
+    rng = np.random.Generator(np.random.PCG64(n))
+    eng = ScorerEngine(0)
+    eng.ctx.set_dims(64, 6, [n, 13], 1)
+    eng.num = [6, n, 13]
+    P = eng.set_pairs([0], min_bin, band + 1)
+    coords = eng.coordinates(0)
+    proba = rng.random((6, P)).astype(np.float32)
+    proba[proba < 0.2] = 0.0
+    proba[5] = 0.0
+    keep = np.ones(n, dtype=np.uint8); keep[[2, n - 3]] = 0
+    score, border = eng.insulation(0, torch.from_numpy(proba).cuda(), w_ins, order, keep, np.array([0]))
+    for c in range(6):
+        s_ref, b_ref = OX.cell_profile(coords, proba[c], n, keep, [0], w_ins, order)
+        np.testing.assert_allclose(score[c], s_ref, atol=TOL, rtol=0)
+        assert np.array_equal(border[c], b_ref)
+    eng.close()

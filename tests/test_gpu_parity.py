@@ -195,7 +195,17 @@ def test_gather_long_chromosome(density):
     _synthetic_case(4, 0, 64, "fp32", [1600], [0, 7, 23], density=density, band=40, n_cells=24)
 
 
-def _synthetic_case(k, ltr, d, prec, bins, cells, density=None, band=-1, n_cells=40):
+def test_tiny_layernorm_gain_takes_high_accuracy_variant():
+    """The fast tensor-core variant folds layer_norm1.weight into the S table and the classifier weights (S / gamma, gamma^2): a
+    gain close to zero must route the model to the high-accuracy variant instead, same 1e-3 bar."""
+    def shrink(sd):
+        g = np.array(sd["layer_norm1.weight"], copy=True)
+        g[3] = 1e-3; g[17] = -2e-3
+        sd["layer_norm1.weight"] = g
+    _synthetic_case(4, 0, 64, "tc16", [120, 40], [0, 5, 39], mutate=shrink)
+
+
+def _synthetic_case(k, ltr, d, prec, bins, cells, density=None, band=-1, n_cells=40, mutate=None):
     from higashi_b200 import engine as E
     from higashi_b200 import synthetic as S
     from oracle import impute as OI
@@ -204,6 +214,8 @@ def _synthetic_case(k, ltr, d, prec, bins, cells, density=None, band=-1, n_cells
     ds = S.make_dataset("C1", n_cells=n_cells, bins=bins, seed=5, **({} if density is None else {"density": density}))
     ds.d = d
     sd, feats = _random_state(ds, d, seed=42 + d)
+    if mutate is not None:
+        mutate(sd)
     nbr = nbr_w = None
     if k > 0:
         rng = np.random.Generator(np.random.PCG64(9))
