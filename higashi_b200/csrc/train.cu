@@ -178,11 +178,6 @@ __global__ void bias_act_kernel(float* __restrict__ x, const float* __restrict__
     if (pre) pre[i] = v;
     x[i] = act ? swish_acc(v) : v;
 }
-// dpre = dy * swish'(pre)   (in place on dy)
-__global__ void dswish_kernel(float* __restrict__ dy, const float* __restrict__ pre, int64_t n) {
-    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i < n) dy[i] *= dswish(pre[i]);
-}
 // db[col] += sum_rows dy[row, col]
 // block = 64 columns x 4 row lanes; gridDim.y row slices (COLSUM_SLICES) so that the grid covers the SMs
 #define COLSUM_SLICES 128
@@ -207,6 +202,37 @@ __device__ __forceinline__ float keep_scale(unsigned long long seed, unsigned ta
 __global__ void dropout_kernel(float* __restrict__ x, int64_t n, float p, unsigned long long seed, unsigned tag) {
     int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i < n) x[i] *= keep_scale(seed, tag, (unsigned long long)i, p);
+}
+// dpre = [dropout mask *] dy * swish'(pre) in place, and db[col] += sum_rows dpre[row, col] in the same pass (the bias gradient of
+// the layer whose activation this is).  Same tiling as colsum_kernel; p_drop > 0 applies the forward pass's dropout mask first.
+__global__ void dswish_colsum_kernel(float* __restrict__ dy, const float* __restrict__ pre, int rows, int cols, float* __restrict__ db,
+                                     float p_drop, unsigned long long seed, unsigned tag) {
+    __shared__ float part[4][64];
+    const int cl = threadIdx.x & 63, rl = threadIdx.x >> 6;
+    const int col = blockIdx.x * 64 + cl;
+    float s = 0.f;
+    if (col < cols)
+        for (int r = blockIdx.y * 4 + rl; r < rows; r += gridDim.y * 4) {
+            const size_t i = (size_t)r * cols + col;
+            float g = dy[i];
+            if (p_drop > 0.f) g *= keep_scale(seed, tag, (unsigned long long)i, p_drop);
+            g *= dswish(pre[i]);
+            dy[i] = g;
+            s += g;
+        }
+    part[rl][cl] = s;
+    __syncthreads();
+    if (rl == 0 && col < cols) atomicAdd(db + col, (part[0][cl] + part[1][cl]) + (part[2][cl] + part[3][cl]));
+}
+// y = dropout(act(x + bias[col])) in one pass (the forward of pff_n1's hidden layer); keeps the pre-activation
+__global__ void bias_act_dropout_kernel(float* __restrict__ x, const float* __restrict__ bias, int64_t n, int cols, int act,
+                                        float* __restrict__ pre, float p_drop, unsigned long long seed, unsigned tag) {
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    float v = x[i] + (bias ? bias[i % cols] : 0.f);
+    if (pre) pre[i] = v;
+    v = act ? swish_acc(v) : v;
+    x[i] = v * keep_scale(seed, tag, (unsigned long long)i, p_drop);
 }
 __global__ void axpy_kernel(float* __restrict__ y, const float* __restrict__ x, int64_t n) {
     int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -452,41 +478,56 @@ __global__ void attn_fwd_kernel(const float* __restrict__ Q, const float* __rest
         for (int e = 0; e < 16; ++e) o[e] = fmaf(w[t][b], v[b][e], w[t][a] * v[a][e]);
     }
 }
+// 4 lanes per (hyperedge, head), 4 of the 16 head dimensions per lane: the 32 lanes of a warp cover one full 128-float row per
+// token (512 contiguous bytes per load), 36 accumulators per thread instead of 144, 4x the threads of the forward kernel; the
+// two 16-element dot products of a row are finished with two shuffles.
+__device__ __forceinline__ float dot4(const float4 a, const float4 b) { return fmaf(a.x, b.x, fmaf(a.y, b.y, fmaf(a.z, b.z, a.w * b.w))); }
+__device__ __forceinline__ void axpy4(float4& y, float s, const float4 x) {
+    y.x = fmaf(s, x.x, y.x); y.y = fmaf(s, x.y, y.y); y.z = fmaf(s, x.z, y.z); y.w = fmaf(s, x.w, y.w);
+}
 __global__ void attn_bwd_kernel(const float* __restrict__ Q, const float* __restrict__ K, const float* __restrict__ V,
                                 const float* __restrict__ P, const float* __restrict__ dctx, int B, float* __restrict__ dQ,
                                 float* __restrict__ dK, float* __restrict__ dV) {
-    int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= B * 8) return;
-    int r = i >> 3, h = i & 7;
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    const bool valid = i < B * 32;
+    const int ii = valid ? i : B * 32 - 1;               // every lane takes part in the shuffles
+    const int r = ii >> 5, h = (ii >> 2) & 7, e4 = ii & 3;
     size_t base[3];
-    for (int t = 0; t < 3; ++t) base[t] = ((size_t)r * 3 + t) * HSG_HD + h * 16;
-    float dq[3][16] = {}, dk[3][16] = {}, dv[3][16] = {};
-    const float* ps = P + (size_t)i * 6;
+    float4 q[3], k[3], v[3], dc[3];
+#pragma unroll
     for (int t = 0; t < 3; ++t) {
-        int a = (t == 0) ? 1 : 0, b = (t == 2) ? 1 : 2;
-        float pa = ps[t * 2], pb = ps[t * 2 + 1];
-        float den = (pa + pb) + 1e-13f;
-        float wa = pa / den, wb = pb / den;
-        float dwa = 0.f, dwb = 0.f;
-        for (int e = 0; e < 16; ++e) {
-            float dc = dctx[base[t] + e];
-            dwa = fmaf(dc, V[base[a] + e], dwa); dwb = fmaf(dc, V[base[b] + e], dwb);
-            dv[a][e] = fmaf(wa, dc, dv[a][e]); dv[b][e] = fmaf(wb, dc, dv[b][e]);
-        }
-        // w = p / (pa + pb + eps)
-        float common = (dwa * wa + dwb * wb) / den;
-        float dpa = dwa / den - common, dpb = dwb / den - common;
-        // p = softmax([0, la, lb])  (the diagonal logit is the constant 0)
-        float dot = pa * dpa + pb * dpb;
-        float dla = pa * (dpa - dot) * 0.25f, dlb = pb * (dpb - dot) * 0.25f;
-        for (int e = 0; e < 16; ++e) {
-            dq[t][e] = fmaf(dla, K[base[a] + e], fmaf(dlb, K[base[b] + e], dq[t][e]));
-            dk[a][e] = fmaf(dla, Q[base[t] + e], dk[a][e]);
-            dk[b][e] = fmaf(dlb, Q[base[t] + e], dk[b][e]);
-        }
+        base[t] = ((size_t)r * 3 + t) * HSG_HD + h * 16 + e4 * 4;
+        q[t] = *reinterpret_cast<const float4*>(Q + base[t]); k[t] = *reinterpret_cast<const float4*>(K + base[t]);
+        v[t] = *reinterpret_cast<const float4*>(V + base[t]); dc[t] = *reinterpret_cast<const float4*>(dctx + base[t]);
     }
-    for (int t = 0; t < 3; ++t)
-        for (int e = 0; e < 16; ++e) { dQ[base[t] + e] = dq[t][e]; dK[base[t] + e] = dk[t][e]; dV[base[t] + e] = dv[t][e]; }
+    const float4 z4 = make_float4(0.f, 0.f, 0.f, 0.f);
+    float4 dq[3] = {z4, z4, z4}, dk[3] = {z4, z4, z4}, dv[3] = {z4, z4, z4};
+    const float* ps = P + ((size_t)r * 8 + h) * 6;
+#pragma unroll
+    for (int t = 0; t < 3; ++t) {
+        const int a = (t == 0) ? 1 : 0, b = (t == 2) ? 1 : 2;
+        const float pa = ps[t * 2], pb = ps[t * 2 + 1];
+        const float den = (pa + pb) + 1e-13f;
+        const float wa = pa / den, wb = pb / den;
+        float dwa = dot4(dc[t], v[a]), dwb = dot4(dc[t], v[b]);
+        dwa += __shfl_xor_sync(0xffffffffu, dwa, 1); dwb += __shfl_xor_sync(0xffffffffu, dwb, 1);
+        dwa += __shfl_xor_sync(0xffffffffu, dwa, 2); dwb += __shfl_xor_sync(0xffffffffu, dwb, 2);
+        axpy4(dv[a], wa, dc[t]); axpy4(dv[b], wb, dc[t]);
+        // w = p / (pa + pb + eps)
+        const float common = (dwa * wa + dwb * wb) / den;
+        const float dpa = dwa / den - common, dpb = dwb / den - common;
+        // p = softmax([0, la, lb])  (the diagonal logit is the constant 0)
+        const float dot = pa * dpa + pb * dpb;
+        const float dla = pa * (dpa - dot) * 0.25f, dlb = pb * (dpb - dot) * 0.25f;
+        axpy4(dq[t], dla, k[a]); axpy4(dq[t], dlb, k[b]);
+        axpy4(dk[a], dla, q[t]); axpy4(dk[b], dlb, q[t]);
+    }
+    if (!valid) return;
+#pragma unroll
+    for (int t = 0; t < 3; ++t) {
+        *reinterpret_cast<float4*>(dQ + base[t]) = dq[t]; *reinterpret_cast<float4*>(dK + base[t]) = dk[t];
+        *reinterpret_cast<float4*>(dV + base[t]) = dv[t];
+    }
 }
 
 // ------------------------------------------------------------------------------------------------ heads and loss
@@ -958,8 +999,9 @@ extern "C" int hsg_score_fwd(hsg_ctx* c, int stage, int chrom, const int64_t* x_
     // 4. pff_n1: LN -> W0 -> swish -> W1 -> + residual                                    (Modules.py:865-889)
     if (ln_fwd(c, s, w->yv, R, PARAM(HSG_W_PFF_LN_G), PARAM(HSG_W_PFF_LN_B), w->xn, w->mu_y, w->rs_y)) return 1;
     if (LIN_FWD(R, d, d, w->xn, d, PARAM(HSG_W_PFF_W0), d, w->h, d, 0.f)) return 1;
-    bias_act_kernel<<<nblk((int64_t)R * d), 256, 0, s>>>(w->h, PARAM(HSG_W_PFF_B0), (int64_t)R * d, d, 1, w->hpre); TR_CHECK_LAUNCH(c);
-    if (opt.dropout) { dropout_kernel<<<nblk((int64_t)R * d), 256, 0, s>>>(w->h, (int64_t)R * d, 0.4f, opt.seed, 3); TR_CHECK_LAUNCH(c); }
+    if (opt.dropout) bias_act_dropout_kernel<<<nblk((int64_t)R * d), 256, 0, s>>>(w->h, PARAM(HSG_W_PFF_B0), (int64_t)R * d, d, 1, w->hpre, 0.4f, opt.seed, 3);
+    else bias_act_kernel<<<nblk((int64_t)R * d), 256, 0, s>>>(w->h, PARAM(HSG_W_PFF_B0), (int64_t)R * d, d, 1, w->hpre);
+    TR_CHECK_LAUNCH(c);
     HSG_CUDA(cudaMemcpyAsync(w->z, w->yv, (size_t)R * d * sizeof(float), cudaMemcpyDeviceToDevice, s));
     if (LIN_FWD(R, d, d, w->h, d, PARAM(HSG_W_PFF_W1), d, w->z, d, 1.f)) return 1;
     bias_act_kernel<<<nblk((int64_t)R * d), 256, 0, s>>>(w->z, PARAM(HSG_W_PFF_B1), (int64_t)R * d, d, 0, nullptr); TR_CHECK_LAUNCH(c);
@@ -1057,8 +1099,7 @@ extern "C" int hsg_score_bwd(hsg_ctx* c, void* stream) {
     head_bwd_kernel<<<nblk(R), 256, (256 / hd) * (hd + 1) * sizeof(float), s>>>(w->dmean, w->cact, R, hd, PARAM(HSG_W_CLS_W1), w->dc, GRAD(HSG_W_CLS_W1),
                                                                    GRAD(HSG_W_CLS_B1));
     TR_CHECK_LAUNCH(c);
-    dswish_kernel<<<nblk((int64_t)R * hd), 256, 0, s>>>(w->dc, w->cpre, (int64_t)R * hd); TR_CHECK_LAUNCH(c);
-    colsum_kernel<<<dim3((hd + 63) / 64, COLSUM_SLICES), 256, 0, s>>>(w->dc, R, hd, GRAD(HSG_W_CLS_B0)); TR_CHECK_LAUNCH(c);
+    dswish_colsum_kernel<<<dim3((hd + 63) / 64, COLSUM_SLICES), 256, 0, s>>>(w->dc, w->cpre, R, hd, GRAD(HSG_W_CLS_B0), 0.f, 0ull, 0u); TR_CHECK_LAUNCH(c);
     if (LIN_DW(R, hd, d, w->dc, hd, w->u, d, GRAD(HSG_W_CLS_W0), d)) return 1;
     if (LIN_DX(R, hd, d, w->dc, hd, PARAM(HSG_W_CLS_W0), d, w->du, d, 0.f)) return 1;
     HSG_CUDA(cudaMemsetAsync(w->dS, 0, nRd * sizeof(float), s));
@@ -1077,8 +1118,7 @@ extern "C" int hsg_score_bwd(hsg_ctx* c, void* stream) {
             head_bwd_kernel<<<nblk(R), 256, (256 / hd) * (hd + 1) * sizeof(float), s>>>(dh[q], act[q], R, hd, PARAM(slots[q][2]), w->dc, GRAD(slots[q][2]),
                                                                            GRAD(slots[q][3]));
             TR_CHECK_LAUNCH(c);
-            dswish_kernel<<<nblk((int64_t)R * hd), 256, 0, s>>>(w->dc, pre[q], (int64_t)R * hd); TR_CHECK_LAUNCH(c);
-            colsum_kernel<<<dim3((hd + 63) / 64, COLSUM_SLICES), 256, 0, s>>>(w->dc, R, hd, GRAD(slots[q][1])); TR_CHECK_LAUNCH(c);
+            dswish_colsum_kernel<<<dim3((hd + 63) / 64, COLSUM_SLICES), 256, 0, s>>>(w->dc, pre[q], R, hd, GRAD(slots[q][1]), 0.f, 0ull, 0u); TR_CHECK_LAUNCH(c);
             if (LIN_DW(R, hd, d, w->dc, hd, w->Sn, d, GRAD(slots[q][0]), d)) return 1;
             if (LIN_DX(R, hd, d, w->dc, hd, PARAM(slots[q][0]), d, w->dS, d, 1.f)) return 1;
         }
@@ -1090,9 +1130,8 @@ extern "C" int hsg_score_bwd(hsg_ctx* c, void* stream) {
     colsum_kernel<<<dim3((d + 63) / 64, COLSUM_SLICES), 256, 0, s>>>(w->dz, R, d, GRAD(HSG_W_PFF_B1)); TR_CHECK_LAUNCH(c);
     if (LIN_DW(R, d, d, w->dz, d, w->h, d, GRAD(HSG_W_PFF_W1), d)) return 1;
     if (LIN_DX(R, d, d, w->dz, d, PARAM(HSG_W_PFF_W1), d, w->dh, d, 0.f)) return 1;
-    if (w->dropout) { dropout_kernel<<<nblk(nRd), 256, 0, s>>>(w->dh, nRd, 0.4f, w->seed, 3); TR_CHECK_LAUNCH(c); }
-    dswish_kernel<<<nblk(nRd), 256, 0, s>>>(w->dh, w->hpre, nRd); TR_CHECK_LAUNCH(c);
-    colsum_kernel<<<dim3((d + 63) / 64, COLSUM_SLICES), 256, 0, s>>>(w->dh, R, d, GRAD(HSG_W_PFF_B0)); TR_CHECK_LAUNCH(c);
+    dswish_colsum_kernel<<<dim3((d + 63) / 64, COLSUM_SLICES), 256, 0, s>>>(w->dh, w->hpre, R, d, GRAD(HSG_W_PFF_B0), w->dropout ? 0.4f : 0.f, w->seed, 3u);
+    TR_CHECK_LAUNCH(c);
     if (LIN_DW(R, d, d, w->dh, d, w->xn, d, GRAD(HSG_W_PFF_W0), d)) return 1;
     if (LIN_DX(R, d, d, w->dh, d, PARAM(HSG_W_PFF_W0), d, w->dxn, d, 0.f)) return 1;
     HSG_CUDA(cudaMemcpyAsync(w->dy, w->dz, nRd * sizeof(float), cudaMemcpyDeviceToDevice, s));      // residual branch
@@ -1105,7 +1144,7 @@ extern "C" int hsg_score_bwd(hsg_ctx* c, void* stream) {
     if (LIN_DW(R, d, HSG_HD, w->dy, d, w->ctx, HSG_HD, GRAD(HSG_W_FC1), HSG_HD)) return 1;
     if (LIN_DX(R, d, HSG_HD, w->dy, d, PARAM(HSG_W_FC1), HSG_HD, w->dctx, HSG_HD, 0.f)) return 1;
     if (LIN_DW(R, d, HSG_HD, w->dsp, d, w->V, HSG_HD, GRAD(HSG_W_FC2), HSG_HD)) return 1;
-    attn_bwd_kernel<<<nblk(B * 8, 128), 128, 0, s>>>(w->Q, w->K, w->V, w->P, w->dctx, B, w->dQ, w->dK, w->dV); TR_CHECK_LAUNCH(c);
+    attn_bwd_kernel<<<nblk((int64_t)B * 32, 128), 128, 0, s>>>(w->Q, w->K, w->V, w->P, w->dctx, B, w->dQ, w->dK, w->dV); TR_CHECK_LAUNCH(c);
     if (LIN_DX(R, d, HSG_HD, w->dsp, d, PARAM(HSG_W_FC2), HSG_HD, w->dV, HSG_HD, 1.f)) return 1;
     if (LIN_DW(R, HSG_HD, d, w->dQ, HSG_HD, w->qin, d, GRAD(HSG_W_QS), d)) return 1;
     if (LIN_DW(R, HSG_HD, d, w->dK, HSG_HD, w->kin, d, GRAD(HSG_W_KS), d)) return 1;
@@ -1122,8 +1161,7 @@ extern "C" int hsg_score_bwd(hsg_ctx* c, void* stream) {
     TR_CHECK_LAUNCH(c);
     if (w->stage == 2) {
         const int64_t nNd = (int64_t)NB * d;
-        dswish_kernel<<<nblk(nNd), 256, 0, s>>>(w->dcomb, w->combpre, nNd); TR_CHECK_LAUNCH(c);
-        colsum_kernel<<<dim3((d + 63) / 64, COLSUM_SLICES), 256, 0, s>>>(w->dcomb, NB, d, GRAD(HSG_W_SAGE_B)); TR_CHECK_LAUNCH(c);
+        dswish_colsum_kernel<<<dim3((d + 63) / 64, COLSUM_SLICES), 256, 0, s>>>(w->dcomb, w->combpre, NB, d, GRAD(HSG_W_SAGE_B), 0.f, 0ull, 0u); TR_CHECK_LAUNCH(c);
         float* dG = GRAD(HSG_W_SAGE_W); const float* G = PARAM(HSG_W_SAGE_W);
         if (LIN_DW(NB, d, d, w->dcomb, d, w->neigh, d, dG, 2 * d)) return 1;
         if (LIN_DW(NB, d, d, w->dcomb, d, w->selfb, d, dG + d, 2 * d)) return 1;
@@ -1141,8 +1179,7 @@ extern "C" int hsg_score_bwd(hsg_ctx* c, void* stream) {
         if (LIN_DW(B, d, F, w->dcell, d, w->Xg, F, b->grads + b->off_pw[0], F)) return 1;
     }
     // E = swish(X W^T + b)
-    dswish_kernel<<<nblk((int64_t)nc * d), 256, 0, s>>>(w->dEall, w->Epre, (int64_t)nc * d); TR_CHECK_LAUNCH(c);
-    colsum_kernel<<<dim3((d + 63) / 64, COLSUM_SLICES), 256, 0, s>>>(w->dEall, nc, d, b->grads + b->off_pb[chrom + 1]); TR_CHECK_LAUNCH(c);
+    dswish_colsum_kernel<<<dim3((d + 63) / 64, COLSUM_SLICES), 256, 0, s>>>(w->dEall, w->Epre, nc, d, b->grads + b->off_pb[chrom + 1], 0.f, 0ull, 0u); TR_CHECK_LAUNCH(c);
     if (LIN_DW(nc, d, in_c, w->dEall, d, b->feat[chrom + 1], in_c, b->grads + b->off_pw[chrom + 1], in_c)) return 1;
     return 0;
 }
