@@ -77,6 +77,7 @@ static void free_derived(hsg_ctx* c) {
     { __half* p = (__half*)c->binV16; dev_free(p); c->binV16 = nullptr; }
     { __half* p = (__half*)c->cellV16; dev_free(p); c->cellV16 = nullptr; }
     dev_free(c->XS); dev_free(c->binSb); dev_free(c->cellSb); dev_free(c->binV32p); dev_free(c->cellV32p); dev_free(c->wimg); dev_free(c->cst); dev_free(c->pj_wimg); dev_free(c->ovf_list);
+    c->ovf_cap = 0;                          // the overflow list is gone: the next gather must allocate it again
     c->use_umma = false;
     dev_free(c->stage_out[0]); dev_free(c->stage_out[1]); c->stage_bytes = 0;
     c->prepared = false;

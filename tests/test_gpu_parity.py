@@ -195,6 +195,27 @@ def test_gather_long_chromosome(density):
     _synthetic_case(4, 0, 64, "fp32", [1600], [0, 7, 23], density=density, band=40, n_cells=24)
 
 
+def test_prepare_twice_on_one_engine():
+    """hsg_prepare may be called again on a live context (another precision / activation): every derived buffer, including the
+    sparse gather's overflow list, must be rebuilt (regression: a stale capacity left the list pointer null)."""
+    from higashi_b200 import engine as E
+    from higashi_b200 import synthetic as S
+    ds = S.make_dataset("C1", n_cells=30, bins=[120, 40], seed=5, density=0.02)
+    sd, feats = _random_state(ds, 64, seed=7)
+    eng = _engine()
+    eng.load_model(sd, ds.num, feats=feats, cell_feats=ds.cell_feats)
+    eng.set_contacts(ds.csr)
+    eng.set_pairs([0, 1], 1, -1)
+    outs = []
+    for prec in (E.PREC_TC16, E.PREC_TC16_HI, E.PREC_FP32, E.PREC_TC16):
+        eng.prepare(prec, 0, E.ACT_SIGMOID)
+        outs.append(eng.impute_to_host(3, 12))
+    for o in outs[:2] + outs[3:]:
+        np.testing.assert_allclose(o, outs[2], atol=TOL_BF16, rtol=0)
+    assert np.array_equal(outs[0], outs[3])
+    eng.close()
+
+
 def test_tiny_layernorm_gain_takes_high_accuracy_variant():
     """The fast tensor-core variant folds layer_norm1.weight into the S table and the classifier weights (S / gamma, gamma^2): a
     gain close to zero must route the model to the high-accuracy variant instead, same 1e-3 bar."""
