@@ -218,7 +218,8 @@ int  hsg_recon_apply(hsg_ctx* ctx, float scale, void* stream);
  * pair count of hsg_set_pairs); sel_slot picks the chromosome.  window_bins = int(window_ins / res), tad_order =
  * int(window_tad / res / 2).  keep_host uint8 [n] (1 = bin kept, i.e. the diagonal of scTAD's `mask`; NULL = all kept),
  * discard_host uint8 [n] (1 = row of discard_rows; NULL = none).  Outputs (host): score float [n_batch, n],
- * border uint8 [n_batch, n] (1 where call_tads reports a boundary).  The n x n maps are never materialised.           */
+ * border uint8 [n_batch, n] (1 where call_tads reports a boundary).  The n x n maps are never materialised.  Sums run in
+ * 64-bit fixed point (order-independent, exact ties): scores must be finite with |score| < 1e5, window_bins <= 1000.       */
 int  hsg_insulation(hsg_ctx* ctx, int sel_slot, const float* scores_dev, int n_batch, int window_bins, int tad_order,
                     const unsigned char* keep_host, const unsigned char* discard_host, float* score_out_host,
                     unsigned char* border_out_host, void* stream);
