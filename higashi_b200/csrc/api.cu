@@ -59,6 +59,7 @@ extern "C" int hsg_create(hsg_ctx** out, int device_ordinal) {
     c->n_sm = prop.multiProcessorCount;
     if (const char* e = getenv("HSG_GATHER_SPARSE")) c->gather_sparse = (e[0] != '0');
     if (const char* e = getenv("HSG_GATHER_CHROM")) c->gather_chrom = (e[0] != '0');
+    if (const char* e = getenv("HSG_GATHER_HASH")) c->gather_hash = (e[0] != '0');
     HSG_CUDA(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
     HSG_CUDA(cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking));
     for (int i = 0; i < 8; ++i) HSG_CUDA(cudaEventCreate(&c->ev[i]));

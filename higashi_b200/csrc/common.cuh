@@ -106,6 +106,7 @@ struct hsg_ctx {
     float* neigh = nullptr;                  // [batch, n_bins, d]
     int* ovf_list = nullptr; int64_t ovf_cap = 0;   // K1a overflow tokens (+ counter in the last element)
     bool gather_sparse = true;               // sparse-row K1a fast path enabled (HSG_GATHER_SPARSE=0 disables it)
+    bool gather_hash = true;                 // hash-merge K1a for long chromosomes enabled (HSG_GATHER_HASH=0 disables it)
     bool gather_chrom = true;                // chromosome-block K1a for dense rows enabled (HSG_GATHER_CHROM=0 disables it)
     float* QK = nullptr;                     // fp32 [qk_cells, n_bins, 2, 128] (fp32 mode: batch; tensor-core mode: 1 cell for hsg_fix_cell)
     // tensor-core mode (HSG_PREC_TC16): 16-bit token tables + pre-swizzled weight images

@@ -8,6 +8,7 @@
 #include <cuda_fp16.h>
 
 #include <algorithm>
+#include <cstdlib>
 
 #include "common.cuh"
 
@@ -516,6 +517,147 @@ static int try_launch_gather_chrom(hsg_ctx* c, int cell_start, int n_batch, int 
     return 0;
 }
 
+// ---------------------------------------------------------------------------------------------
+// K1a, long chromosomes with medium-dense rows (C5: 4864 bins at 50 kb, ~70 merged candidates per token).  The chromosome's E
+// table (1.2 MB) does not fit in shared memory and a dense per-warp accumulator (19 KB) leaves the generic kernel ~10 warps per
+// SM; the register kernel pays SLOTS^2 shuffles for its all-pairs dedup.  Here a warp merges the k+1 rows of its token into a
+// 256-slot HASH table in shared memory (3.5 KB per warp): one atomicCAS on the key claims / finds the slot of a column, the value
+// is added in row order (columns are unique inside a row, rows are processed one after the other -> the same fp32 sums as the
+// generic kernel), then the table is compacted, x pdf(0), log1p, L1 norm, and the E rows are gathered from L2 four candidates at
+// a time (8 lanes x 8 columns, two 128-bit loads per 8 FMAs).  Row extents are fetched one token ahead, the first 32 entries of
+// all rows are requested before any is inserted.  Tokens whose probe sequence exceeds GH_PROBES (table nearly full) go to the
+// overflow list that the generic kernel finishes.
+// ---------------------------------------------------------------------------------------------
+#define GH_WARPS 8
+#define GH_SLOTS 256
+#define GH_PROBES 48
+struct GatherHashParams {
+    const int64_t* row_ptr; const int32_t* col; const float* val; const int32_t* nbr; const float* nbr_w;
+    const float* E_bin; const int* bin_chrom; const int* bin_off; float* neigh; int* tok_list; int* tok_count;
+    int k1, weighted, n_bins, cell_start;
+    int64_t n_tok;
+};
+
+__global__ void __launch_bounds__(GH_WARPS * 32) neigh_gather_hash_kernel(GatherHashParams p) {
+    __shared__ int s_key[GH_WARPS][GH_SLOTS];
+    __shared__ float s_val[GH_WARPS][GH_SLOTS];
+    __shared__ float s_cval[GH_WARPS][GH_SLOTS];
+    __shared__ unsigned short s_ccol[GH_WARPS][GH_SLOTS];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    int* key = s_key[warp]; float* hv = s_val[warp]; float* cval = s_cval[warp]; unsigned short* ccol = s_ccol[warp];
+    for (int i = lane; i < GH_SLOTS; i += 32) { key[i] = -1; hv[i] = 0.f; }
+    __syncwarp();
+    const int grp = lane >> 3, gl = lane & 7;
+
+    auto fetch_extents = [&](int64_t t, int64_t& lo, int64_t& hi, float& w) {
+        lo = 0; hi = 0; w = 1.0f;
+        if (lane < p.k1 && t < p.n_tok) {
+            const int cb = (int)(t / p.n_bins), g = (int)(t - (int64_t)cb * p.n_bins);
+            const int cell = p.cell_start + cb;
+            const int src = p.weighted ? __ldg(p.nbr + (int64_t)cell * p.k1 + lane) : cell;
+            if (p.weighted) w = __ldg(p.nbr_w + (int64_t)cell * p.k1 + lane);
+            const int64_t row = (int64_t)src * p.n_bins + g;
+            lo = __ldg(p.row_ptr + row); hi = __ldg(p.row_ptr + row + 1);
+        }
+    };
+    // insert one (column, weighted value) of the current row; false = probe limit hit
+    auto insert = [&](int cidx, float prod) -> bool {
+        unsigned h = ((unsigned)cidx * 0x9E3779B1u) >> 24;
+        for (int pr = 0; pr < GH_PROBES; ++pr) {
+            const int slot = (int)((h + pr) & (GH_SLOTS - 1));
+            const int old = atomicCAS(&key[slot], -1, cidx);
+            if (old == -1 || old == cidx) { hv[slot] = __fadd_rn(hv[slot], prod); return true; }
+        }
+        return false;
+    };
+
+    const int64_t t_first = (int64_t)blockIdx.x * GH_WARPS + warp, t_step = (int64_t)gridDim.x * GH_WARPS;
+    int64_t lo_n, hi_n;
+    float w_n;
+    fetch_extents(t_first, lo_n, hi_n, w_n);
+    for (int64_t t = t_first; t < p.n_tok; t += t_step) {
+        const int g = (int)(t % p.n_bins);
+        const int off = p.bin_off[p.bin_chrom[g]];
+        const int64_t lo_l = lo_n, hi_l = hi_n;
+        const float w_l = w_n;
+        fetch_extents(t + t_step, lo_n, hi_n, w_n);
+        bool fail = false;
+        for (int nb0 = 0; nb0 < p.k1; nb0 += 8) {
+            int cc[8]; float vv[8];
+#pragma unroll
+            for (int q = 0; q < 8; ++q) {
+                const int64_t lo = __shfl_sync(0xffffffffu, lo_l, (nb0 + q) & 31), hi = __shfl_sync(0xffffffffu, hi_l, (nb0 + q) & 31);
+                cc[q] = -1; vv[q] = 0.f;
+                if (nb0 + q < p.k1 && lo + lane < hi) { cc[q] = __ldg(p.col + lo + lane); vv[q] = __ldg(p.val + lo + lane); }
+            }
+#pragma unroll
+            for (int q = 0; q < 8; ++q) {
+                if (nb0 + q >= p.k1) break;                       // warp-uniform
+                const float w = __shfl_sync(0xffffffffu, w_l, nb0 + q);
+                const int64_t lo = __shfl_sync(0xffffffffu, lo_l, nb0 + q), hi = __shfl_sync(0xffffffffu, hi_l, nb0 + q);
+                if (cc[q] >= 0 && !insert(cc[q], p.weighted ? __fmul_rn(w, vv[q]) : vv[q])) fail = true;
+                __syncwarp();
+                for (int64_t e0 = lo + 32; e0 < hi; e0 += 32) {   // long row: the rest, 32 entries at a time
+                    const int64_t e = e0 + lane;
+                    if (e < hi) {
+                        const float v = __ldg(p.val + e);
+                        if (!insert(__ldg(p.col + e), p.weighted ? __fmul_rn(w, v) : v)) fail = true;
+                    }
+                    __syncwarp();
+                }
+            }
+        }
+        fail = __any_sync(0xffffffffu, fail);
+        // compact the table (and reset it for the next token)
+        int acount = 0;
+        float part = 0.f;
+#pragma unroll
+        for (int s0 = 0; s0 < GH_SLOTS; s0 += 32) {
+            const int sidx = s0 + lane;
+            const int kcol = key[sidx];
+            const bool used = kcol >= 0;
+            const unsigned b = __ballot_sync(0xffffffffu, used);
+            if (used) {
+                const float v = log1pf(__fmul_rn(hv[sidx], HSG_PDF0));       // x pdf(0), log1p (Impute.py:19, 91)
+                const int pos = acount + __popc(b & ((1u << lane) - 1u));
+                ccol[pos] = (unsigned short)kcol; cval[pos] = v;
+                part += fabsf(v);
+                key[sidx] = -1; hv[sidx] = 0.f;
+            }
+            acount += __popc(b);
+        }
+        const float total = warp_sum(part);
+        __syncwarp();
+        if (fail) {                                             // table (nearly) full: the generic kernel finishes this token
+            if (lane == 0) p.tok_list[atomicAdd(p.tok_count, 1)] = (int)t;
+            continue;
+        }
+        const float inv_total = (total > 0.f) ? __frcp_rn(total) : 1.0f;
+        const float4* Ec = reinterpret_cast<const float4*>(p.E_bin + (int64_t)off * 64) + gl * 2;
+        float4 o0 = make_float4(0.f, 0.f, 0.f, 0.f), o1 = o0;
+#pragma unroll 2
+        for (int i = grp; i < acount; i += 4) {
+            const int ci = ccol[i];
+            const float a = cval[i] * inv_total;
+            const float4 x0 = __ldg(Ec + (int64_t)ci * 16), x1 = __ldg(Ec + (int64_t)ci * 16 + 1);
+            o0.x = fmaf(a, x0.x, o0.x); o0.y = fmaf(a, x0.y, o0.y); o0.z = fmaf(a, x0.z, o0.z); o0.w = fmaf(a, x0.w, o0.w);
+            o1.x = fmaf(a, x1.x, o1.x); o1.y = fmaf(a, x1.y, o1.y); o1.z = fmaf(a, x1.z, o1.z); o1.w = fmaf(a, x1.w, o1.w);
+        }
+#pragma unroll
+        for (int sh = 8; sh <= 16; sh <<= 1) {
+            o0.x += __shfl_xor_sync(0xffffffffu, o0.x, sh); o0.y += __shfl_xor_sync(0xffffffffu, o0.y, sh);
+            o0.z += __shfl_xor_sync(0xffffffffu, o0.z, sh); o0.w += __shfl_xor_sync(0xffffffffu, o0.w, sh);
+            o1.x += __shfl_xor_sync(0xffffffffu, o1.x, sh); o1.y += __shfl_xor_sync(0xffffffffu, o1.y, sh);
+            o1.z += __shfl_xor_sync(0xffffffffu, o1.z, sh); o1.w += __shfl_xor_sync(0xffffffffu, o1.w, sh);
+        }
+        if (grp == 0) {
+            float4* dst = reinterpret_cast<float4*>(p.neigh + t * 64 + gl * 8);
+            dst[0] = o0; dst[1] = o1;
+        }
+        __syncwarp();
+    }
+}
+
 int launch_gather(hsg_ctx* c, const int*, int cell_start, int n_batch, cudaStream_t s) {
     int max_nc = 0;
     for (int b : c->bins) max_nc = b > max_nc ? b : max_nc;
@@ -538,7 +680,8 @@ int launch_gather(hsg_ctx* c, const int*, int cell_start, int n_batch, cudaStrea
     // accumulator (4 B x max_nc per warp) leaves the generic kernel with a handful of warps per SM (measured, C3 / C4 / C5 shapes).
     const double avg_cand = (double)c->k1 * (double)c->nnz / (double)std::max<int64_t>(c->n_rows, 1);
     const bool sparse_ok = c->d == 64 && c->ltr == 0 && c->k1 <= 8 && n_tok < (1LL << 31) && c->gather_sparse;
-    const bool to_sparse = sparse_ok && (avg_cand <= 16.0 || max_nc > 1536);
+    static const bool hash_everywhere = []() { const char* e = getenv("HSG_GATHER_HASH"); return e && e[0] == '2'; }();   // A/B switch
+    const bool to_sparse = sparse_ok && (avg_cand <= 16.0 || max_nc > 1536 || (hash_everywhere && c->gather_hash));
     if (!to_sparse && c->gather_chrom) {        // dense rows, short chromosomes: one chromosome per block, E_c in shared memory
         bool done = false;
         if (try_launch_gather_chrom(c, cell_start, n_batch, max_nc, s, &done)) return 1;
@@ -561,7 +704,16 @@ int launch_gather(hsg_ctx* c, const int*, int cell_start, int n_batch, cudaStrea
 #define GS_LAUNCH(SL) neigh_gather_sparse_kernel<SL><<<g, GS_WPB * 32, 0, s>>>(                                                    \
             c->row_ptr, c->col, c->val, c->nbr, c->nbr_w, c->k1, c->weighted ? 1 : 0, c->E_bin, c->d_bin_chrom, c->d_bin_off,      \
             c->n_bins, cell_start, (int)n_tok, c->neigh, c->ovf_list, cnt)
-        if (avg <= 16.0) GS_LAUNCH(4);
+        if (avg > 16.0 && c->gather_hash && max_nc < 65536) {
+            // long chromosome, tens of candidates per token: shared-memory hash merge instead of the SLOTS^2 register dedup
+            GatherHashParams hp;
+            hp.row_ptr = c->row_ptr; hp.col = c->col; hp.val = c->val; hp.nbr = c->nbr; hp.nbr_w = c->nbr_w; hp.E_bin = c->E_bin;
+            hp.bin_chrom = c->d_bin_chrom; hp.bin_off = c->d_bin_off; hp.neigh = c->neigh; hp.tok_list = c->ovf_list; hp.tok_count = cnt;
+            hp.k1 = c->k1; hp.weighted = c->weighted ? 1 : 0; hp.n_bins = c->n_bins; hp.cell_start = cell_start; hp.n_tok = n_tok;
+            const int64_t hb = (n_tok + GH_WARPS - 1) / GH_WARPS;
+            neigh_gather_hash_kernel<<<(unsigned)std::min<int64_t>(hb, (int64_t)c->n_sm * 6), GH_WARPS * 32, 0, s>>>(hp);
+        }
+        else if (avg <= 16.0) GS_LAUNCH(4);
         else if (avg <= 36.0) GS_LAUNCH(8);
         else GS_LAUNCH(12);
 #undef GS_LAUNCH
