@@ -518,7 +518,7 @@ static int try_launch_gather_chrom(hsg_ctx* c, int cell_start, int n_batch, int 
 }
 
 // ---------------------------------------------------------------------------------------------
-// K1a, long chromosomes with medium-dense rows (C5: 4864 bins at 50 kb, ~70 merged candidates per token).  The chromosome's E
+// K1a, rows with tens of merged candidates (C3, C4, C5).  For long chromosomes (C5: 4864 bins at 50 kb) the chromosome's E
 // table (1.2 MB) does not fit in shared memory and a dense per-warp accumulator (19 KB) leaves the generic kernel ~10 warps per
 // SM; the register kernel pays SLOTS^2 shuffles for its all-pairs dedup.  Here a warp merges the k+1 rows of its token into a
 // 256-slot HASH table in shared memory (3.5 KB per warp): one atomicCAS on the key claims / finds the slot of a column, the value
@@ -680,8 +680,10 @@ int launch_gather(hsg_ctx* c, const int*, int cell_start, int n_batch, cudaStrea
     // accumulator (4 B x max_nc per warp) leaves the generic kernel with a handful of warps per SM (measured, C3 / C4 / C5 shapes).
     const double avg_cand = (double)c->k1 * (double)c->nnz / (double)std::max<int64_t>(c->n_rows, 1);
     const bool sparse_ok = c->d == 64 && c->ltr == 0 && c->k1 <= 8 && n_tok < (1LL << 31) && c->gather_sparse;
-    static const bool hash_everywhere = []() { const char* e = getenv("HSG_GATHER_HASH"); return e && e[0] == '2'; }();   // A/B switch
-    const bool to_sparse = sparse_ok && (avg_cand <= 16.0 || max_nc > 1536 || (hash_everywhere && c->gather_hash));
+    // long rows (> 16 merged candidates): the hash-merge kernel wherever the fast path applies (measured: C5 7.28 -> 2.54 ms against
+    // the 96-candidate register kernel, C3 3.53 -> 3.38 ms against the chromosome-block kernel); with it switched off the old rule
+    // stands (register kernel only for chromosomes too long for a dense per-warp accumulator)
+    const bool to_sparse = sparse_ok && (avg_cand <= 16.0 || max_nc > 1536 || c->gather_hash);
     if (!to_sparse && c->gather_chrom) {        // dense rows, short chromosomes: one chromosome per block, E_c in shared memory
         bool done = false;
         if (try_launch_gather_chrom(c, cell_start, n_batch, max_nc, s, &done)) return 1;

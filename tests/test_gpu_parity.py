@@ -180,11 +180,21 @@ def test_gather_paths(density, k):
     _synthetic_case(k, 0, 64, "fp32", [120, 40], [0, 5, 39], density=density)
 
 
+@pytest.mark.parametrize("density,k,bins,band,n_cells", [(0.3, 4, [120, 40], -1, 40), (0.08, 4, [120, 40], -1, 40),
+                                                         (0.009, 4, [1600], 40, 24)])
+def test_gather_without_hash_kernel(density, k, bins, band, n_cells, monkeypatch):
+    """Rows with more than 16 merged candidates normally take the hash-merge kernel; with it switched off dense rows on short
+    chromosomes take the chromosome-block kernel and long chromosomes the 64 / 96-candidate register kernels."""
+    monkeypatch.setenv("HSG_GATHER_HASH", "0")
+    _synthetic_case(k, 0, 64, "fp32", bins, [0, 5, 23], density=density, band=band, n_cells=n_cells)
+
+
 @pytest.mark.parametrize("density,k", [(0.3, 4), (0.02, 9)])
 def test_gather_generic_kernel(density, k, monkeypatch):
     """Dense rows on short chromosomes normally take the chromosome-block kernel (E table of the chromosome in shared memory);
     with it switched off the generic warp-per-token kernel must give the same answer."""
     monkeypatch.setenv("HSG_GATHER_CHROM", "0")
+    monkeypatch.setenv("HSG_GATHER_HASH", "0")
     _synthetic_case(k, 0, 64, "fp32", [120, 40], [0, 5, 39], density=density)
 
 
