@@ -68,6 +68,17 @@ def test_insulation_after_imputation():
             np.testing.assert_allclose(score[c], s_ref, atol=TOL, rtol=0)
             assert np.array_equal(border[c], b_ref)
         off += P
+    # the full return tuple of the reference's gen_tad (single-cell part from the device, pseudo-bulk on the host)
+    from higashi_b200.scTAD import gen_tad
+    chrom, sc_score, sc_border, sc_idx, bulk_score, bulk_tad_b = gen_tad(eng, 0, "chr1", 0, ds.n_cells, 6.0, 8.0, 1.0, cells_per_call=7)
+    n0 = ds.bins[chroms[0]]
+    assert chrom == "chr1" and sc_score.shape == (ds.n_cells, n0) and sc_border.shape == (ds.n_cells, n0) and len(sc_idx) == ds.n_cells
+    assert all(np.array_equal(np.flatnonzero(sc_border[i]), sc_idx[i]) for i in range(ds.n_cells))
+    P0 = len(eng.coordinates(0))
+    m = np.zeros((n0, n0)); np.add.at(m, (eng.coordinates(0)[:, 0], eng.coordinates(0)[:, 1]), host[:, :P0].astype(np.float64).sum(0))
+    ref = OX.insulation_score(OX.sqrt_norm(m), 6)
+    np.testing.assert_allclose(bulk_score, ref, rtol=1e-6, atol=1e-9)
+    assert np.array_equal(bulk_tad_b, OX.call_tads(ref, 4))
     eng.close()
 
 

@@ -57,3 +57,25 @@ def test_fixed_point_range_update_algorithm_matches_reference_vectors():
             np.testing.assert_allclose(score, g["%s/score" % tag][c], atol=1e-7, rtol=0)
             assert np.array_equal(border, g["%s/border" % tag][c])
             assert score[n - 1] in (0.0, 1.0) and score[n - 2] in (0.0, 1.0)          # exact, not 1e-17
+
+
+def test_bulk_profile_matches_reference_functions_on_upper_triangular_bulk():
+    """scTAD.gen_tad's pseudo-bulk (scTAD.py:113-119): the summed vector goes into the UPPER triangle only, then the same three
+    functions.  The host mirror's prefix-sum implementation against the oracle's direct restatement of those functions."""
+    from higashi_b200.scTAD import bulk_profile
+    from oracle import insulation as OX
+    rng = np.random.Generator(np.random.PCG64(3))
+    for n, band, w, order in ((90, 30, 7, 4), (41, 40, 12, 2), (64, 9, 3, 1)):
+        xs, ys = np.where(np.triu(np.ones((n, n)), 1) - np.triu(np.ones((n, n)), band + 1) > 0)
+        coords = np.stack([xs, ys], axis=1)
+        blk = 11
+        bulk = (0.1 + 3.0 * ((xs // blk) == (ys // blk)) * rng.uniform(0.5, 1.0, len(xs)) + 0.2 * rng.random(len(xs)))
+        keep = np.ones(n, dtype=np.uint8); keep[rng.choice(n, 3, replace=False)] = 0
+        discard = np.sort(rng.choice(n, 2, replace=False))
+        score, borders = bulk_profile(coords, bulk, n, w * 10.0, order * 20.0, 10.0, keep, discard)
+        m = np.zeros((n, n)); m[xs, ys] += bulk
+        m *= np.outer(keep, keep)
+        ref = OX.insulation_score(OX.sqrt_norm(m), w)
+        ref[discard] = 1.0
+        np.testing.assert_allclose(score, ref, rtol=1e-9, atol=1e-12)
+        assert np.array_equal(borders, OX.call_tads(ref, order))
