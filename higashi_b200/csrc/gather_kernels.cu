@@ -505,10 +505,10 @@ static int try_launch_gather_chrom(hsg_ctx* c, int cell_start, int n_batch, int 
         first += nb;
     }
     p.blk_first[c->n_chrom] = first;
-    static bool attr_set = false;
-    if (!attr_set) {
+    static bool attr_set[64] = {};               // per device: the attribute belongs to the device's function instance
+    if (!attr_set[c->device & 63]) {
         HSG_CUDA(cudaFuncSetAttribute(neigh_gather_chrom_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024));
-        attr_set = true;
+        attr_set[c->device & 63] = true;
     }
     neigh_gather_chrom_kernel<<<first, GC_WARPS * 32, smem, s>>>(p);
     c->launches++;

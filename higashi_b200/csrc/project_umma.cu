@@ -258,10 +258,10 @@ int launch_token_project_umma(hsg_ctx* c, int cell_start, int n_batch, cudaStrea
     memcpy(p.cst, c->h_pj_cst, sizeof(p.cst));
     p.QK16 = (__half*)c->QK16; p.XS = c->XS; p.n_tok = n_tok; p.n_bins = c->n_bins; p.cell_start = cell_start;
     p.n_tiles = (int)((n_tok + 127) / 128);
-    static bool attr_set = false;
-    if (!attr_set) {
+    static bool attr_set[64] = {};               // per device: the attribute belongs to the device's function instance
+    if (!attr_set[c->device & 63]) {
         HSG_CUDA(cudaFuncSetAttribute(project_umma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, PJ_TOTAL + 1024));
-        attr_set = true;
+        attr_set[c->device & 63] = true;
     }
     int grid = p.n_tiles < 2 * c->n_sm ? p.n_tiles : 2 * c->n_sm;
     project_umma_kernel<<<grid, 128, PJ_TOTAL + 1024, s>>>(p);

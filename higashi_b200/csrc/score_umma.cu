@@ -469,11 +469,11 @@ int launch_score_pairs_umma(hsg_ctx* c, int cell_start, int n_batch, float* out,
     long long n_tiles = (long long)n_batch * p.tiles_per_cell;
     long long quads = (n_tiles + UM_WG - 1) / UM_WG;
     int grid = (int)(quads < c->n_sm ? quads : c->n_sm);
-    static bool attr_set = false;
-    if (!attr_set) {
+    static bool attr_set[64] = {};               // per device: the attribute belongs to the device's function instance
+    if (!attr_set[c->device & 63]) {
         HSG_CUDA(cudaFuncSetAttribute(score_umma_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, SM_TOTAL_OF(0) + 1024));
         HSG_CUDA(cudaFuncSetAttribute(score_umma_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, SM_TOTAL_OF(1) + 1024));
-        attr_set = true;
+        attr_set[c->device & 63] = true;
     }
     if (c->umma_hi) score_umma_kernel<true><<<grid, UM_THREADS, SM_TOTAL_OF(1) + 1024, s>>>(p);
     else score_umma_kernel<false><<<grid, UM_THREADS, SM_TOTAL_OF(0) + 1024, s>>>(p);
