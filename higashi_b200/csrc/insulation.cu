@@ -169,6 +169,7 @@ extern "C" int hsg_insulation(hsg_ctx* c, int sel_slot, const float* scores_dev,
     HSG_CHECK(sel_slot >= 0 && sel_slot < (int)c->sel_chroms.size(), "bad chromosome slot (hsg_set_pairs first)");
     HSG_CHECK(scores_dev && n_batch > 0 && window_bins > 0 && tad_order >= 0 && score_out_host && border_out_host, "bad arguments");
     HSG_CHECK(window_bins <= 1000, "insulation window above 1000 bins");
+    HSG_CHECK(n_batch <= 65535, "at most 65535 cells per hsg_insulation call");
     cudaStream_t s = (cudaStream_t)stream;
     const int chrom = c->sel_chroms[sel_slot], n = c->bins[chrom], goff = c->bin_off[chrom];
     const int64_t off = c->sel_off[sel_slot], P = c->sel_P[sel_slot];
