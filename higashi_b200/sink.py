@@ -13,23 +13,37 @@ except Exception:                       # noqa: BLE001
 
 
 class ChromSink:
+    """One output container.  With h5py: `{chrom}_{name}.hdf5`, datasets written as they arrive (gzip-6 when asked, as
+    Impute.py:277).  Without: `{chrom}_{name}.npz` -- a zip archive of `.npy` members that is ALSO written as the datasets arrive
+    (deflate level 6 when asked), so a run never holds more than the block in flight in host memory; `numpy.load` reads it."""
+
     def __init__(self, temp_dir, chrom, name):
         self.base = os.path.join(temp_dir, "%s_%s" % (chrom, name))
         self.h5 = h5py.File(self.base + ".hdf5", "w") if h5py is not None else None
-        self.data = {}
+        self.zf = None
+        if self.h5 is None:
+            import zipfile
+            self.zf = zipfile.ZipFile(self.base + ".npz", "w", allowZip64=True)
 
     def create_dataset(self, key, data, compress=False):
         if self.h5 is not None:
             kw = dict(compression="gzip", compression_opts=6) if compress else {}
             self.h5.create_dataset(key, data=data, **kw)
         else:
-            self.data[key] = np.asarray(data)
+            import zipfile
+            info = zipfile.ZipInfo(key + ".npy")
+            info.compress_type = zipfile.ZIP_DEFLATED if compress else zipfile.ZIP_STORED
+            if compress:
+                info._compresslevel = 6
+            with self.zf.open(info, "w", force_zip64=True) as f:
+                np.lib.format.write_array(f, np.ascontiguousarray(data), allow_pickle=False)
 
     def close(self):
         if self.h5 is not None:
             self.h5.close()
-        else:
-            np.savez(self.base + ".npz", **self.data)
+        elif self.zf is not None:
+            self.zf.close()
+            self.zf = None
 
 
 class AsyncDrain:
