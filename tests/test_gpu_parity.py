@@ -173,7 +173,7 @@ def test_small_genomes_tensor_core(bins):
     _synthetic_case(4, 0, 64, "tc16", bins, [0, 1, 2, 3, 20, 39])
 
 
-@pytest.mark.parametrize("density,k", [(0.3, 4), (0.08, 4), (0.02, 9), (0.02, 7), (0.0, 4)])
+@pytest.mark.parametrize("density,k", [(0.3, 4), (0.3, 0), (0.08, 4), (0.02, 9), (0.02, 7), (0.0, 4)])
 def test_gather_paths(density, k):
     """K1a has a sparse-row fast path (<= 32 merged candidates per token, <= 8 neighbour rows) and a generic kernel that
     finishes the overflow list: dense rows (every token overflows), mixed, k+1 > 8 (generic only), k+1 = 8, empty contacts."""
