@@ -81,22 +81,30 @@ def impute_process(config_path, model, name, mode, cell_start, cell_end, sparse_
         offs.append(offs[-1] + eng.sel_P[slot])
 
     start = time.time()
-    # two pinned blocks: the writer thread drains block k into the sinks (copy + gzip) while the GPU fills block k + 1
+    # Two pinned blocks: the writer thread drains block k into the sinks (widen + copy + gzip) while the GPU fills block k + 1.
+    # Block k + 2 reuses the buffer of block k, so it first waits for the TICKET of block k's write job (the queue bound of the
+    # drain does not cover the job the writer is still running).  `impute_score_dtype: "float16"` in the config moves the scores
+    # to the host as fp16 (half the D2H bytes, hsg_impute_cells_host_f16) and widens them here; the datasets stay float32.
+    half = str(config.get("impute_score_dtype", "float32")) in ("float16", "fp16", "half") and eng.scorer_variant() == E.PREC_TC16
     rows = min(cells_per_call, max(1, cell_end - cell_start))
-    bufs = [torch.empty((rows, max(1, eng.P)), dtype=torch.float32).pin_memory() for _ in range(2)]
+    bufs = [torch.empty((rows, max(1, eng.P)), dtype=torch.float16 if half else torch.float32).pin_memory() for _ in range(2)]
+    tickets = [None, None]
     drain = S.AsyncDrain(depth=1)
 
     def write_block(out, c0, c1):
         for i in range(c0, c1):
             for slot in range(len(impute_list)):
-                sinks[slot].create_dataset("cell_%d" % i, out[i - c0, offs[slot]:offs[slot + 1]].copy(), compress=True)
+                sinks[slot].create_dataset("cell_%d" % i, out[i - c0, offs[slot]:offs[slot + 1]].astype(np.float32), compress=True)
 
     count = 0
     for k, c0 in enumerate(range(cell_start, cell_end, cells_per_call)):
         c1 = min(cell_end, c0 + cells_per_call)
         buf = bufs[k % 2]
-        eng.ctx.impute_cells_host_ptr(c0, c1, buf.data_ptr())            # block k - 1 is being written meanwhile
-        drain.submit(lambda out=buf.numpy()[: c1 - c0], a=c0, b=c1: write_block(out, a, b))   # waits for block k - 1 first
+        if tickets[k % 2] is not None:
+            tickets[k % 2].wait()                                        # block k - 2 has left this buffer
+            drain._raise()
+        eng.ctx.impute_cells_host_ptr(c0, c1, buf.data_ptr(), half=half)     # block k - 1 is being written meanwhile
+        tickets[k % 2] = drain.submit(lambda out=buf.numpy()[: c1 - c0], a=c0, b=c1: write_block(out, a, b))
         count += c1 - c0
         if impute_verbose > 0:
             el = time.time() - start

@@ -75,7 +75,7 @@ EXPORTS = [
     "hsg_train_bind", "hsg_train_set_features", "hsg_score_fwd", "hsg_score_bwd", "hsg_train_options", "hsg_score_heads",
     "hsg_train_bind_recon", "hsg_recon_loss", "hsg_recon_apply", "hsg_train_set_dropout",
     "hsg_score_set_head_grads", "hsg_sample_batch", "hsg_sample_batch_begin", "hsg_sample_batch_end", "hsg_sampled_fetch",
-    "hsg_insulation",
+    "hsg_insulation", "hsg_impute_cells_f16", "hsg_impute_cells_host_f16", "hsg_refresh_contacts", "hsg_scorer_variant", "hsg_sample_set_removal_draws",
 ]
 
 
@@ -115,6 +115,11 @@ def load():
     lib.hsg_prepare.argtypes = [p, i32, i32, i32]
     lib.hsg_impute_cells.argtypes = [p, i32, i32, p, p]
     lib.hsg_impute_cells_host.argtypes = [p, i32, i32, p]
+    lib.hsg_impute_cells_f16.argtypes = [p, i32, i32, p, p]
+    lib.hsg_impute_cells_host_f16.argtypes = [p, i32, i32, p]
+    lib.hsg_refresh_contacts.argtypes = [p, i32, i32, p, p, i64]
+    lib.hsg_scorer_variant.argtypes = [p, i32p]
+    lib.hsg_sample_set_removal_draws.argtypes = [p, f32p, i32]
     lib.hsg_fix_cell.argtypes = [p, i32, p]
     lib.hsg_score_triplets.argtypes = [p, p, i64, p, p]
     lib.hsg_launch_count.argtypes = [p]
@@ -264,8 +269,25 @@ class Context:
         assert out_host.dtype == np.float32 and out_host.flags["C_CONTIGUOUS"]
         self._check(self.lib.hsg_impute_cells_host(self.h, int(cell_start), int(cell_end), C.c_void_p(out_host.ctypes.data)))
 
-    def impute_cells_host_ptr(self, cell_start, cell_end, host_ptr):
-        self._check(self.lib.hsg_impute_cells_host(self.h, int(cell_start), int(cell_end), C.c_void_p(host_ptr)))
+    def impute_cells_host_ptr(self, cell_start, cell_end, host_ptr, half=False):
+        f = self.lib.hsg_impute_cells_host_f16 if half else self.lib.hsg_impute_cells_host
+        self._check(f(self.h, int(cell_start), int(cell_end), C.c_void_p(host_ptr)))
+
+    def impute_cells_f16(self, cell_start, cell_end, out_dev_ptr, stream=0):
+        self._check(self.lib.hsg_impute_cells_f16(self.h, int(cell_start), int(cell_end), C.c_void_p(out_dev_ptr), C.c_void_p(stream)))
+
+    def impute_cells_host_f16(self, cell_start, cell_end, out_host: np.ndarray):
+        assert out_host.dtype == np.float16 and out_host.flags["C_CONTIGUOUS"]
+        self._check(self.lib.hsg_impute_cells_host_f16(self.h, int(cell_start), int(cell_end), C.c_void_p(out_host.ctypes.data)))
+
+    def refresh_contacts_ptr(self, cell_start, cell_end, col_ptr, val_ptr, nnz_range):
+        """Asynchronous re-upload of the stored entries of the rows of cells [cell_start, cell_end) (host pointers)."""
+        self._check(self.lib.hsg_refresh_contacts(self.h, int(cell_start), int(cell_end), C.c_void_p(col_ptr), C.c_void_p(val_ptr), int(nnz_range)))
+
+    def scorer_variant(self):
+        v = C.c_int32(0)
+        self._check(self.lib.hsg_scorer_variant(self.h, C.byref(v)))
+        return int(v.value)
 
     def fix_cell(self, cell_1based, stream=0):
         self._check(self.lib.hsg_fix_cell(self.h, int(cell_1based), C.c_void_p(stream)))

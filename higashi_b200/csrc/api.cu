@@ -64,6 +64,8 @@ extern "C" int hsg_create(hsg_ctx** out, int device_ordinal) {
     HSG_CUDA(cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking));
     for (int i = 0; i < 8; ++i) HSG_CUDA(cudaEventCreate(&c->ev[i]));
     for (int i = 0; i < 2; ++i) HSG_CUDA(cudaEventCreateWithFlags(&c->stage_ev[i], cudaEventDisableTiming));
+    HSG_CUDA(cudaEventCreateWithFlags(&c->work_ev, cudaEventDisableTiming));
+    HSG_CUDA(cudaEventCreateWithFlags(&c->refresh_ev, cudaEventDisableTiming));
     g_extra[c] = new CtxExtra();
     *out = c;
     return 0;
@@ -97,6 +99,8 @@ extern "C" int hsg_destroy(hsg_ctx* c) {
     if (c->ins_ws) cudaFree(c->ins_ws);
     if (c->h2d_stream) cudaStreamDestroy(c->h2d_stream);
     if (c->staged_ev) cudaEventDestroy(c->staged_ev);
+    if (c->work_ev) cudaEventDestroy(c->work_ev);
+    if (c->refresh_ev) cudaEventDestroy(c->refresh_ev);
     for (int i = 0; i < 8; ++i) if (c->ev[i]) cudaEventDestroy(c->ev[i]);
     for (int i = 0; i < 2; ++i) if (c->stage_ev[i]) cudaEventDestroy(c->stage_ev[i]);
     if (c->stream) cudaStreamDestroy(c->stream);
@@ -243,6 +247,8 @@ extern "C" int hsg_set_contacts(hsg_ctx* c, const int64_t* row_ptr, const int32_
     }
     HSG_CUDA(cudaStreamSynchronize(c->stream));
     c->n_rows = n_rows; c->nnz = nnz;
+    c->h_cell_ptr.resize((size_t)c->n_cells + 1);
+    for (int i = 0; i <= c->n_cells; ++i) c->h_cell_ptr[i] = row_ptr[(int64_t)i * c->n_bins];
     return 0;
 }
 
@@ -272,6 +278,8 @@ extern "C" int hsg_stage_contacts(hsg_ctx* c, const int64_t* row_ptr, const int3
         HSG_CUDA(cudaMemcpyAsync(c->val2, val, (size_t)nnz * sizeof(float), cudaMemcpyHostToDevice, c->h2d_stream));
     }
     HSG_CUDA(cudaEventRecord(c->staged_ev, c->h2d_stream));
+    c->h_cell_ptr2.resize((size_t)c->n_cells + 1);
+    for (int i = 0; i <= c->n_cells; ++i) c->h_cell_ptr2[i] = row_ptr[(int64_t)i * c->n_bins];
     c->staged_rows = n_rows; c->staged_nnz = nnz; c->staged = true;
     return 0;
 }
@@ -280,7 +288,9 @@ extern "C" int hsg_commit_contacts(hsg_ctx* c) {
     CTX_GUARD(c);
     HSG_CHECK(c->staged, "hsg_commit_contacts without hsg_stage_contacts");
     HSG_CUDA(cudaEventSynchronize(c->staged_ev));       // the staged copy has landed
-    HSG_CUDA(cudaDeviceSynchronize());                  // nothing queued may still read the current matrix
+    // nothing queued may still read the current matrix: wait for the last imputation call's event (not for the whole device)
+    if (c->work_pending) { HSG_CUDA(cudaEventSynchronize(c->work_ev)); c->work_pending = false; }
+    c->h_cell_ptr.swap(c->h_cell_ptr2);
     std::swap(c->row_ptr, c->row_ptr2); std::swap(c->col, c->col2); std::swap(c->val, c->val2);
     std::swap(c->cap_rows, c->cap_rows2); std::swap(c->cap_nnz, c->cap_nnz2);
     c->n_rows = c->staged_rows; c->nnz = c->staged_nnz; c->staged = false;
@@ -510,6 +520,26 @@ extern "C" int hsg_prepare(hsg_ctx* c, int precision, int local_transfer_range, 
     // (so does a layer_norm1 gain too close to zero for the fast variant's gain folding)
     c->umma_hi = c->use_umma && (precision == HSG_PREC_TC16_HI || activation != HSG_ACT_SIGMOID ||
                                  !umma_gain_foldable(h->v[HSG_W_LN1_G].data()));
+    if (c->use_umma) {
+        // fp16 RANGE guard: the 16-bit operands (Q / K / V rows, ctx, h, the squared difference u) top out at 65504.  Bound every one
+        // of them from the weights and from the S tables of THIS model; a model outside the fast variant's range takes the
+        // high-accuracy variant (fp32 tables and attention, unfolded layer_norm1), one outside that range the fp32 kernels.
+        HSG_CUDA(cudaStreamSynchronize(c->stream));
+        std::vector<float> hS((size_t)(c->n_bins + c->n_cells) * d);
+        HSG_CUDA(cudaMemcpy(hS.data(), c->binS, (size_t)c->n_bins * d * sizeof(float), cudaMemcpyDeviceToHost));
+        HSG_CUDA(cudaMemcpy(hS.data() + (size_t)c->n_bins * d, c->cellS, (size_t)c->n_cells * d * sizeof(float), cudaMemcpyDeviceToHost));
+        const int lvl = umma_range_level(h->v[HSG_W_QS].data(), h->v[HSG_W_KS].data(), h->v[HSG_W_VS].data(), h->v[HSG_W_ALN1_G].data(),
+                                         h->v[HSG_W_ALN1_B].data(), h->v[HSG_W_ALN2_G].data(), h->v[HSG_W_ALN2_B].data(),
+                                         h->v[HSG_W_ALN3_G].data(), h->v[HSG_W_ALN3_B].data(), h->v[HSG_W_PFF_W0].data(),
+                                         h->v[HSG_W_PFF_B0].data(), h->v[HSG_W_PFF_LN_G].data(), h->v[HSG_W_PFF_LN_B].data(),
+                                         h->v[HSG_W_LN1_G].data(), h->v[HSG_W_LN1_B].data(), hS.data(), (long long)(c->n_bins + c->n_cells), d);
+        if (lvl >= 1) c->umma_hi = true;
+        if (lvl >= 2) { c->use_umma = false; c->umma_hi = false; }
+    }
+    {
+        const char* v1 = getenv("HSG_K2V1");
+        c->k2v2 = c->use_umma && !c->umma_hi && !(v1 && v1[0] == '1');
+    }
     size_t per_cell;
     if (c->use_umma) {
         std::vector<unsigned char> wimg(umma_wimg_bytes());
@@ -517,8 +547,8 @@ extern "C" int hsg_prepare(hsg_ctx* c, int precision, int local_transfer_range, 
         umma_build_weights(h->v[HSG_W_FC1].data(), h->v[HSG_W_PFF_W0].data(), h->v[HSG_W_PFF_B0].data(),
                            h->v[HSG_W_PFF_LN_G].data(), h->v[HSG_W_PFF_LN_B].data(), h->v[HSG_W_PFF_W1].data(),
                            h->v[HSG_W_PFF_B1].data(), h->v[HSG_W_LN1_G].data(), h->v[HSG_W_CLS_W0].data(),
-                           h->v[HSG_W_CLS_B0].data(), h->v[HSG_W_CLS_W1].data(), h->v[HSG_W_CLS_B1].data(), c->umma_hi ? 1 : 0, wimg.data(),
-                           cst.data());
+                           h->v[HSG_W_CLS_B0].data(), h->v[HSG_W_CLS_W1].data(), h->v[HSG_W_CLS_B1].data(), c->umma_hi ? 1 : 0, c->k2v2 ? 1 : 0,
+                           wimg.data(), cst.data());
         if (dev_alloc(&c->wimg, wimg.size()) || dev_alloc(&c->cst, cst.size())) return 1;
         HSG_CUDA(cudaMemcpy(c->wimg, wimg.data(), wimg.size(), cudaMemcpyHostToDevice));
         HSG_CUDA(cudaMemcpy(c->cst, cst.data(), cst.size() * sizeof(float), cudaMemcpyHostToDevice));
@@ -537,12 +567,20 @@ extern "C" int hsg_prepare(hsg_ctx* c, int precision, int local_transfer_range, 
             memcpy(c->h_pj_cst, pcst.data(), pcst.size() * sizeof(float));
         }
         __half *bv = nullptr, *cv = nullptr;
-        if (dev_alloc(&bv, (size_t)c->n_bins * HSG_HD) || dev_alloc(&cv, (size_t)c->n_cells * HSG_HD) ||
-            dev_alloc(&c->binSb, (size_t)c->n_bins * d) || dev_alloc(&c->cellSb, (size_t)c->n_cells * d)) return 1;
+        const size_t bins_pad = (size_t)((c->n_bins + HSG_GRP - 1) / HSG_GRP) * HSG_GRP;     // score_umma2.cu tables hold whole groups of 32 bins
+        if (dev_alloc(&bv, bins_pad * HSG_HD) || dev_alloc(&cv, (size_t)c->n_cells * HSG_HD) ||
+            dev_alloc(&c->binSb, bins_pad * d) || dev_alloc(&c->cellSb, (size_t)c->n_cells * d)) return 1;
+        HSG_CUDA(cudaMemsetAsync(bv, 0, bins_pad * HSG_HD * sizeof(__half), c->stream));
+        HSG_CUDA(cudaMemsetAsync(c->binSb, 0, bins_pad * d * sizeof(float), c->stream));
         c->binV16 = bv; c->cellV16 = cv;
         if (c->umma_hi && (dev_alloc(&c->binV32p, (size_t)c->n_bins * HSG_HD) || dev_alloc(&c->cellV32p, (size_t)c->n_cells * HSG_HD))) return 1;
+        if (c->k2v2) {
+            if (launch_convert_static2(c, c->binV, c->binS, c->n_bins, 1, c->binV16, c->binSb, c->stream)) return 1;
+            if (launch_convert_static2(c, c->cellV, c->cellS, c->n_cells, 0, c->cellV16, c->cellSb, c->stream)) return 1;
+        } else {
         if (launch_convert_static(c, c->binV, c->binS, c->n_bins, c->binV16, c->binSb, c->umma_hi ? c->binV32p : nullptr, c->stream)) return 1;
         if (launch_convert_static(c, c->cellV, c->cellS, c->n_cells, c->cellV16, c->cellSb, c->umma_hi ? c->cellV32p : nullptr, c->stream)) return 1;
+        }
         per_cell = (size_t)c->n_bins * ((c->umma_hi ? 2 * HSG_HD * sizeof(float) : 2 * HSG_HD * sizeof(__half)) + 16 * sizeof(float) + d * sizeof(float));
     } else {
         per_cell = (size_t)c->n_bins * (2 * HSG_HD + d) * sizeof(float);
@@ -553,12 +591,17 @@ extern "C" int hsg_prepare(hsg_ctx* c, int precision, int local_transfer_range, 
     if (dev_alloc(&c->neigh, (size_t)batch * c->n_bins * d)) return 1;
     if (c->use_umma) {
         __half* qk16 = nullptr;
-        if (dev_alloc(&qk16, c->umma_hi ? (size_t)1 : (size_t)batch * c->n_bins * 2 * HSG_HD) ||
-            dev_alloc(&c->XS, (size_t)batch * c->n_bins * 16) ||
+        const size_t bins_pad = (size_t)((c->n_bins + HSG_GRP - 1) / HSG_GRP) * HSG_GRP;
+        if (dev_alloc(&qk16, c->umma_hi ? (size_t)1 : (size_t)batch * bins_pad * 2 * HSG_HD) ||
+            dev_alloc(&c->XS, (size_t)batch * bins_pad * 16) ||
             dev_alloc(&c->QK, (size_t)(c->umma_hi ? batch : 1) * c->n_bins * 2 * HSG_HD)) return 1;
         c->QK16 = qk16;
     } else {
         if (dev_alloc(&c->QK, (size_t)batch * c->n_bins * 2 * HSG_HD)) return 1;
+    }
+    if (c->k2v2) {      // the padding bins of the last group are never written by K1b: keep them finite
+        HSG_CUDA(cudaMemsetAsync(c->QK16, 0, (size_t)batch * (size_t)((c->n_bins + HSG_GRP - 1) / HSG_GRP) * HSG_GRP * 2 * HSG_HD * sizeof(__half), c->stream));
+        HSG_CUDA(cudaMemsetAsync(c->XS, 0, (size_t)batch * (size_t)((c->n_bins + HSG_GRP - 1) / HSG_GRP) * HSG_GRP * 16 * sizeof(float), c->stream));
     }
     HSG_CUDA(cudaStreamSynchronize(c->stream));
     c->fixed_cell = -1;
@@ -566,14 +609,15 @@ extern "C" int hsg_prepare(hsg_ctx* c, int precision, int local_transfer_range, 
     return 0;
 }
 
-static int run_batch(hsg_ctx* c, int cell0, int nb, float* out, cudaStream_t s, bool prof) {
+static int run_batch(hsg_ctx* c, int cell0, int nb, float* out, cudaStream_t s, bool prof, void* out16 = nullptr) {
     if (prof) HSG_CUDA(cudaEventRecord(c->ev[0], s));
     if (launch_gather(c, nullptr, cell0, nb, s)) return 1;
     if (prof) HSG_CUDA(cudaEventRecord(c->ev[1], s));
     if (c->use_umma && c->use_proj_umma) { if (launch_token_project_umma(c, cell0, nb, s)) return 1; }
     else if (launch_token_project(c, cell0, nb, c->use_umma ? (c->umma_hi ? 2 : 1) : 0, s)) return 1;
     if (prof) HSG_CUDA(cudaEventRecord(c->ev[2], s));
-    if (c->use_umma) { if (launch_score_pairs_umma(c, cell0, nb, out, s)) return 1; }
+    if (c->k2v2) { if (launch_score_pairs_umma2(c, cell0, nb, out, out16, s)) return 1; }
+    else if (c->use_umma) { if (launch_score_pairs_umma(c, cell0, nb, out, s)) return 1; }
     else if (launch_score_pairs_f32(c, cell0, nb, out, s)) return 1;
     if (prof) {
         HSG_CUDA(cudaEventRecord(c->ev[3], s));
@@ -587,31 +631,55 @@ static int run_batch(hsg_ctx* c, int cell0, int nb, float* out, cudaStream_t s, 
     return 0;
 }
 
-extern "C" int hsg_impute_cells(hsg_ctx* c, int cell_start, int cell_end, float* out_dev, void* stream) {
-    CTX_GUARD(c);
+// work queued on `s` must see the rows hsg_refresh_contacts uploaded on the upload stream: an event wait, not a device-wide sync
+static int wait_for_uploads(hsg_ctx* c, cudaStream_t s) {
+    if (c->refresh_pending) {
+        HSG_CUDA(cudaStreamWaitEvent(s, c->refresh_ev, 0));
+        c->refresh_pending = false;
+    }
+    return 0;
+}
+
+static int impute_dev(hsg_ctx* c, int cell_start, int cell_end, void* out_dev, bool half, cudaStream_t s) {
     HSG_CHECK(c->prepared, "call hsg_prepare first");
     HSG_CHECK(cell_start >= 0 && cell_end <= c->n_cells && cell_start <= cell_end, "cell range out of bounds");
     HSG_CHECK(out_dev != nullptr || cell_start == cell_end || c->P == 0, "null output");
-    cudaStream_t s = (cudaStream_t)stream;
+    HSG_CHECK(!half || c->k2v2, "16-bit score blocks need the tensor-core scorer with a sigmoid head (HSG_PREC_TC16, HSG_ACT_SIGMOID, d_model 64)");
+    if (wait_for_uploads(c, s)) return 1;
     for (int i = 0; i < 4; ++i) c->last_ms[i] = 0.f;
     for (int c0 = cell_start; c0 < cell_end; c0 += c->batch_cells) {
         int nb = std::min(c->batch_cells, cell_end - c0);
-        if (run_batch(c, c0, nb, out_dev + (size_t)(c0 - cell_start) * c->P, s, c->profiling)) return 1;
+        const size_t off = (size_t)(c0 - cell_start) * c->P;
+        if (run_batch(c, c0, nb, half ? nullptr : (float*)out_dev + off, s, c->profiling, half ? (void*)((__half*)out_dev + off) : nullptr)) return 1;
     }
+    HSG_CUDA(cudaEventRecord(c->work_ev, s));        // hsg_refresh_contacts orders its copies behind the reads queued here
+    c->work_pending = true;
     c->fixed_cell = -1;
     return 0;
 }
 
-extern "C" int hsg_impute_cells_host(hsg_ctx* c, int cell_start, int cell_end, float* out_host) {
+extern "C" int hsg_impute_cells(hsg_ctx* c, int cell_start, int cell_end, float* out_dev, void* stream) {
     CTX_GUARD(c);
+    return impute_dev(c, cell_start, cell_end, out_dev, false, (cudaStream_t)stream);
+}
+
+extern "C" int hsg_impute_cells_f16(hsg_ctx* c, int cell_start, int cell_end, void* out_dev_half, void* stream) {
+    CTX_GUARD(c);
+    return impute_dev(c, cell_start, cell_end, out_dev_half, true, (cudaStream_t)stream);
+}
+
+static int impute_host(hsg_ctx* c, int cell_start, int cell_end, void* out_host, bool half) {
     HSG_CHECK(c->prepared, "call hsg_prepare first");
     HSG_CHECK(cell_start >= 0 && cell_end <= c->n_cells && cell_start <= cell_end, "cell range out of bounds");
     HSG_CHECK(out_host != nullptr || cell_start == cell_end || c->P == 0, "null output");
+    HSG_CHECK(!half || c->k2v2, "16-bit score blocks need the tensor-core scorer with a sigmoid head (HSG_PREC_TC16, HSG_ACT_SIGMOID, d_model 64)");
+    const size_t esz = half ? sizeof(__half) : sizeof(float);
     size_t need = (size_t)c->batch_cells * std::max<int64_t>(c->P, 1) * sizeof(float);
     if (c->stage_bytes < need) {
         if (dev_alloc(&c->stage_out[0], need / sizeof(float)) || dev_alloc(&c->stage_out[1], need / sizeof(float))) return 1;
         c->stage_bytes = need;
     }
+    if (wait_for_uploads(c, c->stream)) return 1;
     for (int i = 0; i < 4; ++i) c->last_ms[i] = 0.f;
     cudaEvent_t copied[2] = {c->ev[4], c->ev[5]};
     bool used[2] = {false, false};
@@ -619,17 +687,54 @@ extern "C" int hsg_impute_cells_host(hsg_ctx* c, int cell_start, int cell_end, f
     for (int c0 = cell_start; c0 < cell_end; c0 += c->batch_cells, ++it) {
         int nb = std::min(c->batch_cells, cell_end - c0), slot = it & 1;
         if (used[slot]) HSG_CUDA(cudaStreamWaitEvent(c->stream, copied[slot], 0));   // staging buffer free again
-        if (run_batch(c, c0, nb, c->stage_out[slot], c->stream, c->profiling)) return 1;
+        if (run_batch(c, c0, nb, half ? nullptr : c->stage_out[slot], c->stream, c->profiling, half ? (void*)c->stage_out[slot] : nullptr)) return 1;
         HSG_CUDA(cudaEventRecord(c->stage_ev[slot], c->stream));
         HSG_CUDA(cudaStreamWaitEvent(c->copy_stream, c->stage_ev[slot], 0));
-        HSG_CUDA(cudaMemcpyAsync(out_host + (size_t)(c0 - cell_start) * c->P, c->stage_out[slot],
-                                 (size_t)nb * c->P * sizeof(float), cudaMemcpyDeviceToHost, c->copy_stream));
+        HSG_CUDA(cudaMemcpyAsync((char*)out_host + (size_t)(c0 - cell_start) * c->P * esz, c->stage_out[slot],
+                                 (size_t)nb * c->P * esz, cudaMemcpyDeviceToHost, c->copy_stream));
         HSG_CUDA(cudaEventRecord(copied[slot], c->copy_stream));
         used[slot] = true;
     }
+    HSG_CUDA(cudaEventRecord(c->work_ev, c->stream));
+    c->work_pending = true;
     HSG_CUDA(cudaStreamSynchronize(c->stream));
     HSG_CUDA(cudaStreamSynchronize(c->copy_stream));
     c->fixed_cell = -1;
+    return 0;
+}
+
+extern "C" int hsg_impute_cells_host(hsg_ctx* c, int cell_start, int cell_end, float* out_host) {
+    CTX_GUARD(c);
+    return impute_host(c, cell_start, cell_end, out_host, false);
+}
+
+extern "C" int hsg_impute_cells_host_f16(hsg_ctx* c, int cell_start, int cell_end, void* out_host_half) {
+    CTX_GUARD(c);
+    return impute_host(c, cell_start, cell_end, out_host_half, true);
+}
+
+extern "C" int hsg_refresh_contacts(hsg_ctx* c, int cell_start, int cell_end, const int32_t* col, const float* val, int64_t nnz_range) {
+    CTX_GUARD(c);
+    HSG_CHECK(c->row_ptr != nullptr && !c->h_cell_ptr.empty(), "hsg_refresh_contacts: call hsg_set_contacts first");
+    HSG_CHECK(cell_start >= 0 && cell_end <= c->n_cells && cell_start <= cell_end, "cell range out of bounds");
+    const int64_t lo = c->h_cell_ptr[cell_start], hi = c->h_cell_ptr[cell_end];
+    HSG_CHECK(nnz_range == hi - lo, "hsg_refresh_contacts: the block must hold exactly the stored entries of these cells' rows");
+    if (nnz_range == 0) return 0;
+    HSG_CHECK(col != nullptr && val != nullptr, "null contact arrays");
+    if (!c->h2d_stream) HSG_CUDA(cudaStreamCreateWithFlags(&c->h2d_stream, cudaStreamNonBlocking));
+    // imputation work already queued may still read these rows: the copies go behind it (event, no device-wide sync)
+    if (c->work_pending) { HSG_CUDA(cudaStreamWaitEvent(c->h2d_stream, c->work_ev, 0)); c->work_pending = false; }
+    HSG_CUDA(cudaMemcpyAsync(c->col + lo, col, (size_t)nnz_range * sizeof(int32_t), cudaMemcpyHostToDevice, c->h2d_stream));
+    HSG_CUDA(cudaMemcpyAsync(c->val + lo, val, (size_t)nnz_range * sizeof(float), cudaMemcpyHostToDevice, c->h2d_stream));
+    HSG_CUDA(cudaEventRecord(c->refresh_ev, c->h2d_stream));
+    c->refresh_pending = true;
+    return 0;
+}
+
+extern "C" int hsg_scorer_variant(hsg_ctx* c, int* variant_out) {
+    HSG_CHECK(c != nullptr && variant_out != nullptr, "bad arguments");
+    HSG_CHECK(c->prepared, "call hsg_prepare first");
+    *variant_out = !c->use_umma ? HSG_PREC_FP32 : (c->umma_hi ? HSG_PREC_TC16_HI : HSG_PREC_TC16);
     return 0;
 }
 

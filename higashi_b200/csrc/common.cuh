@@ -24,6 +24,8 @@
 // high-accuracy scorer tables: a 128-float Q / K / V row is stored as [4 quads][8 heads][4 floats], so that the 8 lanes of a row
 // (lane = head) read one contiguous 128-byte line per 128-bit load.  Column c = 16 h + 4 e + r  ->  32 e + 4 h + r
 #define HSG_HI_POS(c) ((((c) >> 2) & 3) * 32 + ((c) >> 4) * 4 + ((c) & 3))
+// score_umma2.cu tables: bins in groups of 32, chunk-major inside a group (table[bin >> 5][chunk][bin & 31])
+#define HSG_GRP 32
 #define HSG_L2E_QUARTER 0.36067376022224085f      // log2(e) / 4: attention logits of the tensor-core scorer are kept in log2 units
 #define HSG_PDF0 0.3989422804014327f   // scipy.stats.norm.pdf(0)   (Impute.py:19)
 
@@ -83,6 +85,10 @@ struct hsg_ctx {
     int64_t* row_ptr2 = nullptr; int32_t* col2 = nullptr; float* val2 = nullptr;
     int64_t cap_rows2 = 0, cap_nnz2 = 0, staged_rows = 0, staged_nnz = 0;
     cudaStream_t h2d_stream = nullptr; cudaEvent_t staged_ev = nullptr; bool staged = false;
+    // hsg_refresh_contacts: per-cell extents of the installed matrix (host), the event its copies signal and the event the last
+    // imputation call recorded (copies wait for it: they may overwrite rows that call still reads)
+    std::vector<int64_t> h_cell_ptr, h_cell_ptr2;
+    cudaEvent_t refresh_ev = nullptr, work_ev = nullptr; bool refresh_pending = false, work_pending = false;
     // neighbours
     int32_t* nbr = nullptr; float* nbr_w = nullptr; int k1 = 1; bool weighted = false;
 
@@ -117,6 +123,7 @@ struct hsg_ctx {
     unsigned char* wimg = nullptr; float* cst = nullptr; float h_cst[512] = {0};
     unsigned char* pj_wimg = nullptr; float h_pj_cst[320] = {0}; bool use_proj_umma = false;   // tensor-core K1b (project_umma.cu)
     bool use_umma = false;
+    bool k2v2 = false;                       // fast tensor-core variant runs score_umma2.cu: chunk-major QK16 / XS / binV16 tables
     bool umma_hi = false;                    // high-accuracy tensor-core variant (fp32 tables, hi/lo operand splits)
     int n_sm = 148;
     int fixed_cell = -1;                     // 0-based cell whose tokens sit in QK slot 0 (hsg_fix_cell)
@@ -141,10 +148,15 @@ int launch_gather(hsg_ctx* c, const int* cells_dev_unused, int cell_start, int n
 int launch_token_project(hsg_ctx* c, int cell_start, int n_cells_batch, int mode, cudaStream_t s);   // mode 0: fp32 QK, 1: fp16 QK + XS, 2: fp32 QK + XS
 int launch_score_pairs_umma(hsg_ctx* c, int cell_start, int n_cells_batch, float* out, cudaStream_t s);
 int launch_convert_static(hsg_ctx* c, const float* V, const float* S, long long rows, void* V16, float* Sb, float* V32p, cudaStream_t s);
+int launch_convert_static2(hsg_ctx* c, const float* V, const float* S, long long rows, int chunk_major, void* V16, float* Sb, cudaStream_t s);
+int launch_score_pairs_umma2(hsg_ctx* c, int cell_start, int n_cells_batch, float* out, void* out16, cudaStream_t s);
 int umma_build_weights(const float* fc1, const float* w0, const float* b0, const float* pff_g, const float* pff_b,
                        const float* w1, const float* b1, const float* ln1_g, const float* c0, const float* cb0,
-                       const float* cw1, const float* cb1, int hi, unsigned char* wimg_host, float* cst_host);
+                       const float* cw1, const float* cb1, int hi, int natural_k, unsigned char* wimg_host, float* cst_host);
 int umma_gain_foldable(const float* ln1_g);
+int umma_range_level(const float* wq, const float* wk, const float* wv, const float* g1, const float* b1, const float* g2, const float* b2,
+                     const float* g3, const float* b3, const float* w0, const float* b0, const float* pff_g, const float* pff_b,
+                     const float* ln1_g, const float* ln1_b, const float* S, long long s_rows, int d);
 void train_release(hsg_ctx* c);     // train.cu: frees every per-context training / sampler buffer (called by hsg_destroy)
 int umma_wimg_bytes();
 int proj_wimg_bytes();

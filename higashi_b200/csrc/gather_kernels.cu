@@ -777,7 +777,7 @@ __global__ void __launch_bounds__(256) token_project_kernel(
     const float* __restrict__ g1, const float* __restrict__ b1, const float* __restrict__ g2,
     const float* __restrict__ b2, const float* __restrict__ wqT, const float* __restrict__ wkT,
     float* __restrict__ QK, __half* __restrict__ QK16, float* __restrict__ XS,
-    const float* __restrict__ cellQ, const float* __restrict__ cellK, int cell_start) {
+    const float* __restrict__ cellQ, const float* __restrict__ cellK, int cell_start, int chunk_major) {
     extern __shared__ __align__(16) float sm[];
     float* xT = sm;                              // [2D][LDA]
     float* dT = xT + 2 * D * TP_LDA;             // [D][LDA]   dyn, then LN1 input
@@ -871,6 +871,9 @@ __global__ void __launch_bounds__(256) token_project_kernel(
             uint4 pk;
             pk.x = *reinterpret_cast<uint32_t*>(&h0); pk.y = *reinterpret_cast<uint32_t*>(&h1);
             pk.z = *reinterpret_cast<uint32_t*>(&h2); pk.w = *reinterpret_cast<uint32_t*>(&h3);
+            if (chunk_major)      // score_umma2.cu: table[slot][bin >> 5][chunk][bin & 31], natural chunk order
+                reinterpret_cast<uint4*>(QK16)[(((size_t)(tok / n_bins) * (size_t)((n_bins + HSG_GRP - 1) / HSG_GRP) + (size_t)((tok % n_bins) >> 5)) * 32u + (size_t)ch) * HSG_GRP + (size_t)((tok % n_bins) & 31)] = pk;
+            else
             *reinterpret_cast<uint4*>(QK16 + tok * 256 + (ch & 16) * 8 + HSG_CHUNK_POS(ch & 15) * 8) = pk;      // head-per-lane chunk order
         }
         // cross terms with the cell token: qcK[h] = Q_cell,h . K_b,h / 4 ; kcQ[h] = Q_b,h . K_cell,h / 4
@@ -887,8 +890,15 @@ __global__ void __launch_bounds__(256) token_project_kernel(
                     a = fmaf(__ldg(qc + e), qkT[(HSG_HD + h * 16 + e) * TP_LDA + tk], a);
                     b = fmaf(qkT[(h * 16 + e) * TP_LDA + tk], __ldg(kc + e), b);
                 }
+                if (chunk_major) {        // XS[slot][bin >> 5][quad][bin & 31][4]: quads 0, 1 = qcK, quads 2, 3 = kcQ
+                    const size_t sl = (size_t)(tok / n_bins), g = (size_t)(tok % n_bins), ng = (size_t)((n_bins + HSG_GRP - 1) / HSG_GRP);
+                    float* xg = XS + (((sl * ng + (g >> 5)) * 4) * HSG_GRP + (g & 31)) * 4;      // quad q of this bin at + q * HSG_GRP * 4 floats
+                    xg[(size_t)(h >> 2) * HSG_GRP * 4 + (h & 3)] = a * HSG_L2E_QUARTER;
+                    xg[(size_t)(2 + (h >> 2)) * HSG_GRP * 4 + (h & 3)] = b * HSG_L2E_QUARTER;
+                } else {
                 XS[tok * 16 + HSG_XS_POS(h)] = a * HSG_L2E_QUARTER;
                 XS[tok * 16 + 8 + HSG_XS_POS(h)] = b * HSG_L2E_QUARTER;
+                }
             }
         }
     }
@@ -903,7 +913,7 @@ static int launch_tp(hsg_ctx* c, int cell_start, int64_t n_tok, cudaStream_t s) 
     token_project_kernel<D, MODE><<<grid, 256, smem, s>>>(c->neigh, c->E_bin, c->n_bins, n_tok, c->dw.sageT, w[HSG_W_SAGE_B],
                                                            w[HSG_W_ALN1_G], w[HSG_W_ALN1_B], w[HSG_W_ALN2_G], w[HSG_W_ALN2_B],
                                                            c->dw.wqT, c->dw.wkT, c->QK, (__half*)c->QK16, c->XS, c->cellQ, c->cellK,
-                                                           cell_start);
+                                                           cell_start, (MODE == 1 && c->k2v2) ? 1 : 0);
     c->launches++;
     HSG_CUDA(cudaGetLastError());
     return 0;

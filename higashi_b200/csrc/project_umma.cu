@@ -37,6 +37,7 @@ struct ProjParams {
     __half* QK16; float* XS;
     long long n_tok;
     int n_bins, cell_start, n_tiles;
+    int chunk_major;         // 1: the grouped chunk-major tables of score_umma2.cu: QK16 [slot][n_grp][32 chunks][32 bins], XS [slot][n_grp][4 quads][32 bins]
 };
 
 __global__ void __launch_bounds__(128, 2) project_umma_kernel(ProjParams p) {
@@ -73,6 +74,7 @@ __global__ void __launch_bounds__(128, 2) project_umma_kernel(ProjParams p) {
 
     uint32_t phase = 0;
     const int j = lane & 7, rsub = lane >> 3;
+    const size_t n_grp = (size_t)((p.n_bins + HSG_GRP - 1) / HSG_GRP);
     for (int tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x) {
         const long long tok0 = (long long)tile * 128;
         const int cb0 = (int)(tok0 / p.n_bins);
@@ -149,10 +151,11 @@ __global__ void __launch_bounds__(128, 2) project_umma_kernel(ProjParams p) {
 
         // ---------------------------------------------------------------- Q | K: bias, cross terms, fp16, coalesced copy-out
         const long long tokr = tok0 + tid;
-        int slot_r = 0;
+        int slot_r = 0, g_r = 0;
         {
             int g = g0 + tid;
             while (g >= p.n_bins) { g -= p.n_bins; ++slot_r; }
+            g_r = g;
             if (slot_r >= PJ_SLOTS) slot_r = PJ_SLOTS - 1;         // rows past n_tok only (never stored)
         }
         float xs[16];
@@ -180,6 +183,12 @@ __global__ void __launch_bounds__(128, 2) project_umma_kernel(ProjParams p) {
                         cr = fmaf(v[q], kk[q], cr);
                     }
                     if (c8 < 2) crA += cr; else crB += cr;
+                    if (p.chunk_major) {
+                        // thread = token: consecutive threads write consecutive 16-byte chunks of table[chunk][bin] -- coalesced, no staging
+                        if (tokr < p.n_tok)
+                            reinterpret_cast<uint4*>(p.QK16)[(((size_t)(cb0 + slot_r) * n_grp + (size_t)(g_r >> 5)) * 32u + (size_t)(half * 16 + cc * 4 + c8)) * HSG_GRP + (size_t)(g_r & 31)] =
+                                make_uint4(pack_h2(v[0] * qs, v[1] * qs), pack_h2(v[2] * qs, v[3] * qs), pack_h2(v[4] * qs, v[5] * qs), pack_h2(v[6] * qs, v[7] * qs));
+                    } else
                     sts128(a_chunk_addr(a_base, tid, HSG_CHUNK_POS(cc * 4 + c8)), pack_h2(v[0] * qs, v[1] * qs), pack_h2(v[2] * qs, v[3] * qs),
                            pack_h2(v[4] * qs, v[5] * qs), pack_h2(v[6] * qs, v[7] * qs));
                 }
@@ -187,6 +196,7 @@ __global__ void __launch_bounds__(128, 2) project_umma_kernel(ProjParams p) {
                 xs[(half == 0 ? 8 : 0) + HSG_XS_POS(cc * 2)] = crA * HSG_L2E_QUARTER;          // heads 2 cc and 2 cc + 1 of this 32-column chunk
                 xs[(half == 0 ? 8 : 0) + HSG_XS_POS(cc * 2 + 1)] = crB * HSG_L2E_QUARTER;
             }
+            if (p.chunk_major) continue;                      // rows already stored (block-uniform)
             __syncthreads();
             // copy-out: lane j of a row group moves chunks j and 8 + j (8 lanes = one contiguous 128-byte line)
 #pragma unroll 2
@@ -204,11 +214,18 @@ __global__ void __launch_bounds__(128, 2) project_umma_kernel(ProjParams p) {
             }
             __syncthreads();
         }
-        if (tokr < p.n_tok) {
+        if (p.chunk_major) {
+            if (tokr < p.n_tok) {
+                float4* xd = reinterpret_cast<float4*>(p.XS) + ((size_t)(cb0 + slot_r) * n_grp + (size_t)(g_r >> 5)) * (4u * HSG_GRP) + (size_t)(g_r & 31);
+                xd[0] = make_float4(xs[0], xs[1], xs[2], xs[3]); xd[HSG_GRP] = make_float4(xs[4], xs[5], xs[6], xs[7]);
+                xd[2 * HSG_GRP] = make_float4(xs[8], xs[9], xs[10], xs[11]); xd[3 * HSG_GRP] = make_float4(xs[12], xs[13], xs[14], xs[15]);
+            }
+        } else if (tokr < p.n_tok) {
             float4* xd = reinterpret_cast<float4*>(p.XS + tokr * 16);
             xd[0] = make_float4(xs[0], xs[1], xs[2], xs[3]); xd[1] = make_float4(xs[4], xs[5], xs[6], xs[7]);
             xd[2] = make_float4(xs[8], xs[9], xs[10], xs[11]); xd[3] = make_float4(xs[12], xs[13], xs[14], xs[15]);
         }
+        if (p.chunk_major) __syncthreads();      // the next tile overwrites s_cell: every thread must be done with its cross terms
         tc_fence_before();      // TMEM reads done before the next tile's MMA overwrites the columns (ordered by its __syncthreads)
     }
 
@@ -258,6 +275,7 @@ int launch_token_project_umma(hsg_ctx* c, int cell_start, int n_batch, cudaStrea
     memcpy(p.cst, c->h_pj_cst, sizeof(p.cst));
     p.QK16 = (__half*)c->QK16; p.XS = c->XS; p.n_tok = n_tok; p.n_bins = c->n_bins; p.cell_start = cell_start;
     p.n_tiles = (int)((n_tok + 127) / 128);
+    p.chunk_major = c->k2v2 ? 1 : 0;
     static bool attr_set[64] = {};               // per device: the attribute belongs to the device's function instance
     if (!attr_set[c->device & 63]) {
         HSG_CUDA(cudaFuncSetAttribute(project_umma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, PJ_TOTAL + 1024));

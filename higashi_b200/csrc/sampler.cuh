@@ -22,6 +22,7 @@ struct SamplerWs {
     cudaStream_t side = nullptr; cudaEvent_t sized = nullptr, consumed = nullptr; int* h_counts = nullptr;
     bool pending = false, consumed_valid = false;
     int p_Bp = 0, p_chrom = 0, p_training = 0; unsigned long long p_seed = 0;
+    float* draws = nullptr; int n_draws = 0;      // hsg_sample_set_removal_draws: caller-supplied uniform draws of the partner removal
 };
 static std::map<hsg_ctx*, SamplerWs*> g_sampler;
 
@@ -166,7 +167,7 @@ __global__ void cand_count_kernel(const int64_t* __restrict__ x, const int* __re
 __global__ void neigh_rows_kernel(const int64_t* __restrict__ x, int B, const int64_t* __restrict__ row_ptr, const int32_t* __restrict__ col,
                                   const float* __restrict__ val, const int32_t* __restrict__ nbr, const float* __restrict__ nbr_w, int k1,
                                   int weighted, int n_bins, int bin_off_c, int bin_base, int training, unsigned long long seed,
-                                  const int* __restrict__ cand_off, int* __restrict__ s_col, float* __restrict__ s_val,
+                                  const float* __restrict__ draws, int n_draws, const int* __restrict__ cand_off, int* __restrict__ s_col, float* __restrict__ s_val,
                                   float* __restrict__ s_sum, int* __restrict__ s_first, int* __restrict__ indptr, int* __restrict__ rowcnt,
                                   int* __restrict__ out_col, float* __restrict__ out_val) {
     const int r = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5), lane = threadIdx.x & 31;
@@ -207,7 +208,8 @@ __global__ void neigh_rows_kernel(const int64_t* __restrict__ x, int B, const in
     }
     __syncwarp();
     // partner removal (training, 40 %, only if another neighbour remains)                 (wrapper:296-300)
-    bool drop = training && n_own > 1 && rnd_uniform(seed, 2, (unsigned long long)r, 0) >= 0.6f;
+    const float u_rm = (draws != nullptr && r < n_draws) ? draws[r] : rnd_uniform(seed, 2, (unsigned long long)r, 0);
+    bool drop = training && n_own > 1 && u_rm >= 0.6f;
     // phase 2: rank among the kept owners = sorted position; log1p; L1 normalisation
     float part = 0.f;
     int partner_present = 0;
@@ -250,6 +252,18 @@ static int grow(T** p, size_t n) {
     return 0;
 }
 
+static int sampler_ws_create(hsg_ctx* c) {
+    SamplerWs*& sw = g_sampler[c];
+    if (sw) return 0;
+    sw = new SamplerWs();
+    HSG_CUDA(cudaMalloc((void**)&sw->counts, 2 * sizeof(int)));
+    HSG_CUDA(cudaStreamCreateWithFlags(&sw->side, cudaStreamNonBlocking));
+    HSG_CUDA(cudaEventCreateWithFlags(&sw->sized, cudaEventDisableTiming));
+    HSG_CUDA(cudaEventCreateWithFlags(&sw->consumed, cudaEventDisableTiming));
+    HSG_CUDA(cudaHostAlloc((void**)&sw->h_counts, 2 * sizeof(int), cudaHostAllocDefault));
+    return 0;
+}
+
 // Phase 1 (asynchronous, on the producer's own stream): negatives, labels / weights, candidate counts; the two sizes the host
 // needs (hyperedges in the batch, neighbour candidates) are copied to pinned memory and an event is recorded.
 extern "C" int hsg_sample_batch_begin(hsg_ctx* c, const int64_t* pos_host, const float* pos_w_host, int Bp, int chrom, int neg_num,
@@ -259,15 +273,8 @@ extern "C" int hsg_sample_batch_begin(hsg_ctx* c, const int64_t* pos_host, const
     HSG_CHECK(c->row_ptr != nullptr, "hsg_sample_batch: contacts not set (hsg_set_contacts)");
     HSG_CHECK(pos_host && Bp > 0 && chrom >= 0 && chrom < c->n_chrom && neg_num >= 0, "bad arguments");
     HSG_CHECK(!c->weighted || c->nbr != nullptr, "neighbour graph flagged but missing");
-    SamplerWs*& sw = g_sampler[c];
-    if (!sw) {
-        sw = new SamplerWs();
-        HSG_CUDA(cudaMalloc((void**)&sw->counts, 2 * sizeof(int)));
-        HSG_CUDA(cudaStreamCreateWithFlags(&sw->side, cudaStreamNonBlocking));
-        HSG_CUDA(cudaEventCreateWithFlags(&sw->sized, cudaEventDisableTiming));
-        HSG_CUDA(cudaEventCreateWithFlags(&sw->consumed, cudaEventDisableTiming));
-        HSG_CUDA(cudaHostAlloc((void**)&sw->h_counts, 2 * sizeof(int), cudaHostAllocDefault));
-    }
+    if (sampler_ws_create(c)) return 1;
+    SamplerWs* sw = g_sampler[c];
     HSG_CHECK(!sw->pending, "hsg_sample_batch_begin: the previous batch has not been finished (hsg_sample_batch_end)");
     cudaStream_t s = sw->side;
     // the scratch of the previous batch may still be read by work queued on the consumer's stream
@@ -352,7 +359,8 @@ extern "C" int hsg_sample_batch_end(hsg_ctx* c, int* B_out, int64_t* nnz_out, vo
     HSG_CUDA(cudaMemcpyAsync(w->y, sw->y_all, (size_t)B * sizeof(float), cudaMemcpyDeviceToDevice, s));
     HSG_CUDA(cudaMemcpyAsync(w->w, sw->w_all, (size_t)B * sizeof(float), cudaMemcpyDeviceToDevice, s));
     neigh_rows_kernel<<<(2 * B + 7) / 8, 256, 0, s>>>(w->x, B, c->row_ptr, c->col, c->val, c->nbr, c->nbr_w, c->k1, c->weighted ? 1 : 0,
-                                                      c->n_bins, c->bin_off[chrom], bin_base, sw->p_training ? 1 : 0, sw->p_seed, sw->cand_off,
+                                                      c->n_bins, c->bin_off[chrom], bin_base, sw->p_training ? 1 : 0, sw->p_seed, sw->draws,
+                                                      sw->n_draws, sw->cand_off,
                                                       sw->s_col, sw->s_val, sw->s_sum, sw->s_first, w->indptr, w->rowcnt, w->cols, w->vals);
     TR_CHECK_LAUNCH(c);
     HSG_CUDA(cudaEventRecord(sw->consumed, s));
@@ -369,6 +377,25 @@ extern "C" int hsg_sample_batch(hsg_ctx* c, const int64_t* pos_host, const float
     if (hsg_sample_batch_begin(c, pos_host, pos_w_host, Bp, chrom, neg_num, pair_ratio, max_bin, wide_check, training, neg_weight, seed))
         return 1;
     return hsg_sample_batch_end(c, B_out, nnz_out, stream);
+}
+
+// reproducibility hook: the uniform draws of the 40 % partner removal (one per bin-token row, `np.random.rand` of wrapper:270)
+// come from this array for all following batches (rows past n use the generator); NULL / n = 0 restores the generator
+extern "C" int hsg_sample_set_removal_draws(hsg_ctx* c, const float* draws_host, int n) {
+    HSG_CHECK(c && c->d > 0, "context not initialised");
+    HSG_CUDA(cudaSetDevice(c->device));
+    HSG_CHECK(n >= 0 && (n == 0 || draws_host != nullptr), "bad arguments");
+    if (sampler_ws_create(c)) return 1;
+    SamplerWs* sw = g_sampler[c];
+    HSG_CUDA(cudaDeviceSynchronize());
+    if (sw->draws) { cudaFree(sw->draws); sw->draws = nullptr; }
+    sw->n_draws = 0;
+    if (n > 0 && draws_host) {
+        HSG_CUDA(cudaMalloc((void**)&sw->draws, (size_t)n * sizeof(float)));
+        HSG_CUDA(cudaMemcpy(sw->draws, draws_host, (size_t)n * sizeof(float), cudaMemcpyHostToDevice));
+        sw->n_draws = n;
+    }
+    return 0;
 }
 
 // debug / test access to the batch the producer left on the device (any pointer may be NULL)

@@ -18,6 +18,9 @@
 //   * template flag HI: high-accuracy variant (fp32 tables and attention, hi + lo weight / operand splits) for softplus heads.
 // Operands are fp16, not bf16: with bf16 operands the measured score error is 1.5e-3..2e-3 (above the 1e-3
 // parity bar), with fp16 it is <= 5e-4 at identical tensor throughput (scripts/bf16_emulation.py, scripts/tail_error.py).
+#include <algorithm>
+#include <cmath>
+
 #include "umma_common.cuh"
 
 // 1: build the ctx tile of token t + 1 between the issue and the wait of token t's classifier MMA.  Measured on the B200
@@ -348,7 +351,7 @@ __global__ void __launch_bounds__(UM_THREADS, 1) score_umma_kernel(UmmaParams p)
 
 int umma_build_weights(const float* fc1, const float* w0, const float* b0, const float* pff_g, const float* pff_b,
                        const float* w1, const float* b1, const float* ln1_g, const float* c0, const float* cb0,
-                       const float* cw1, const float* cb1, int hi, unsigned char* wimg_host, float* cst_host) {
+                       const float* cw1, const float* cb1, int hi, int natural_k, unsigned char* wimg_host, float* cst_host) {
     const int d = UM_D;
     std::vector<float> w0f((size_t)d * d);
     for (int n = 0; n < d; ++n) {
@@ -379,7 +382,7 @@ int umma_build_weights(const float* fc1, const float* w0, const float* b0, const
             for (int j = 0; j < d; ++j) acc += (double)w0f[(size_t)n * d + j] * fc1c[(size_t)j * HSG_HD + k];
             comb[(size_t)(d + n) * HSG_HD + k] = (float)acc;
         }
-    {   // the ctx A tile arrives with its 16-byte chunks in HSG_CHUNK_POS order: permute the K columns of the image to match
+    if (!natural_k) {   // the ctx A tile arrives with its 16-byte chunks in HSG_CHUNK_POS order: permute the K columns of the image to match (score_umma2.cu keeps the natural order)
         std::vector<float> perm(comb.size());
         for (int n = 0; n < 2 * d; ++n)
             for (int k = 0; k < HSG_HD; ++k) perm[(size_t)n * HSG_HD + HSG_COL_POS(k)] = comb[(size_t)n * HSG_HD + k];
@@ -429,6 +432,45 @@ int umma_build_weights(const float* fc1, const float* w0, const float* b0, const
 int umma_gain_foldable(const float* ln1_g) {
     for (int i = 0; i < UM_D; ++i) if (!(fabsf(ln1_g[i]) >= 0.05f)) return 0;
     return 1;
+}
+
+// fp16 range analysis of a model (host, once per hsg_prepare).  Every 16-bit operand of the tensor-core scorer is bounded from
+// the weights (a LayerNorm output obeys |x_hat_k| <= sqrt(d - 1)) and from the model's own S tables:
+//   Q, K rows (fast variant: the half2 chains of a head hold sums of 4 products), V rows / ctx, h = swish(.) and the squared
+//   difference u -- fast variant u' = (z rstd + (beta - S) / gamma)^2, high-accuracy variant u = (z rstd gamma + beta - S)^2.
+// returns 0: the fast variant is safe; 1: take the high-accuracy variant; 2: take the fp32 kernels.
+int umma_range_level(const float* wq, const float* wk, const float* wv, const float* g1, const float* b1, const float* g2, const float* b2,
+                     const float* g3, const float* b3, const float* w0, const float* b0, const float* pff_g, const float* pff_b,
+                     const float* ln1_g, const float* ln1_b, const float* S, long long s_rows, int d) {
+    const double L = sqrt((double)d - 1.0), LIM = 6.0e4, ULIM = 240.0;      // 240^2 = 57600 < 65504
+    auto row_bound = [&](const float* w, const float* g, const float* b, int rows) {
+        double worst = 0;
+        for (int n = 0; n < rows; ++n) {
+            double a = 0, c0 = 0;
+            for (int k = 0; k < d; ++k) { a += fabs((double)w[(size_t)n * d + k] * g[k]); c0 += (double)w[(size_t)n * d + k] * b[k]; }
+            worst = std::max(worst, a * L + fabs(c0));
+        }
+        return worst;
+    };
+    const double qmax = row_bound(wq, g1, b1, HSG_HD) * HSG_L2E_QUARTER, kmax = row_bound(wk, g2, b2, HSG_HD), vmax = row_bound(wv, g3, b3, HSG_HD);
+    double hmax = 0;
+    for (int n = 0; n < d; ++n) {
+        double a = 0, c0 = b0[n];
+        for (int k = 0; k < d; ++k) { a += fabs(0.5 * (double)w0[(size_t)n * d + k] * pff_g[k]); c0 += (double)w0[(size_t)n * d + k] * pff_b[k]; }
+        hmax = std::max(hmax, a * L + fabs(0.5 * c0));
+    }
+    double u_fast = 0, u_hi = 0;
+    for (int f = 0; f < d; ++f) {
+        double dmax = 0;
+        for (long long r = 0; r < s_rows; ++r) dmax = std::max(dmax, fabs((double)ln1_b[f] - (double)S[r * d + f]));
+        const double g = fabs((double)ln1_g[f]);
+        u_hi = std::max(u_hi, dmax + L * g);
+        u_fast = std::max(u_fast, (g > 0 ? dmax / g : 1e30) + L);
+    }
+    const bool finite_ok = std::isfinite(qmax) && std::isfinite(kmax) && std::isfinite(vmax) && std::isfinite(hmax) && std::isfinite(u_hi);
+    if (!finite_ok || vmax > LIM || hmax > LIM || u_hi > ULIM) return 2;
+    if (qmax > LIM || kmax > LIM || 4.0 * qmax * kmax > LIM || u_fast > ULIM) return 1;
+    return 0;
 }
 
 int umma_wimg_bytes() { return SMH_WIMG_BYTES; }

@@ -1282,7 +1282,7 @@ void train_release(hsg_ctx* c) {
         if (sw) {
             cudaFree(sw->pos); cudaFree(sw->pos_w); cudaFree(sw->neg); cudaFree(sw->flag); cudaFree(sw->scan); cudaFree(sw->x_all);
             cudaFree(sw->y_all); cudaFree(sw->w_all); cudaFree(sw->cand_cnt); cudaFree(sw->cand_off); cudaFree(sw->s_col);
-            cudaFree(sw->s_val); cudaFree(sw->s_sum); cudaFree(sw->s_first); cudaFree(sw->counts);
+            cudaFree(sw->s_val); cudaFree(sw->s_sum); cudaFree(sw->s_first); cudaFree(sw->counts); cudaFree(sw->draws);
             if (sw->h_counts) cudaFreeHost(sw->h_counts);
             if (sw->sized) cudaEventDestroy(sw->sized);
             if (sw->consumed) cudaEventDestroy(sw->consumed);

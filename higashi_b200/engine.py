@@ -87,18 +87,29 @@ class ScorerEngine:
         self.ctx.prepare(precision, local_transfer_range, activation)
 
     # ------------------------------------------------------------------ compute
-    def impute_to_host(self, cell_start, cell_end, out: Optional[np.ndarray] = None) -> np.ndarray:
+    def impute_to_host(self, cell_start, cell_end, out: Optional[np.ndarray] = None, half: bool = False) -> np.ndarray:
+        """half=True: fp16 score block (hsg_impute_cells_host_f16), half the D2H bytes; widen with .astype(np.float32)."""
         n = cell_end - cell_start
         if out is None:
-            out = np.empty((n, self.P), dtype=np.float32)
-        self.ctx.impute_cells_host(cell_start, cell_end, out)
+            out = np.empty((n, self.P), dtype=np.float16 if half else np.float32)
+        if half:
+            self.ctx.impute_cells_host_f16(cell_start, cell_end, out)
+        else:
+            self.ctx.impute_cells_host(cell_start, cell_end, out)
         return out
+
+    def scorer_variant(self) -> int:
+        """PREC_FP32 / PREC_TC16 / PREC_TC16_HI: the scorer hsg_prepare selected (after the fp16 range guard)."""
+        return self.ctx.scorer_variant()
 
     def impute_to_device(self, cell_start, cell_end, out_tensor, stream_ptr: int = 0):
         """out_tensor: CUDA float32 torch tensor [n, P] (contiguous)."""
         assert out_tensor.is_cuda and out_tensor.is_contiguous() and out_tensor.dtype.is_floating_point
         assert out_tensor.numel() >= (cell_end - cell_start) * self.P
-        self.ctx.impute_cells(cell_start, cell_end, out_tensor.data_ptr(), stream_ptr)
+        if out_tensor.element_size() == 2:
+            self.ctx.impute_cells_f16(cell_start, cell_end, out_tensor.data_ptr(), stream_ptr)
+        else:
+            self.ctx.impute_cells(cell_start, cell_end, out_tensor.data_ptr(), stream_ptr)
         return out_tensor
 
     def fix_cell(self, cell_1based, stream_ptr: int = 0):

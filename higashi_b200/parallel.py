@@ -38,14 +38,22 @@ def link_parts(name, shards, temp_dir, impute_list, normalise=True):
     for chrom in impute_list:
         out = S.ChromSink(temp_dir, chrom, name)
         for i, (c0, c1) in enumerate(shards):
-            part = S.read_container(temp_dir, chrom, "%s_part_%d" % (name, i))
-            if i == 0:
-                out.create_dataset("coordinates", part["coordinates"])
-            for cell in range(c0, c1):
-                v = part["cell_%d" % cell]
+            # one dataset of the part file in memory at a time (the reference reads one `cell_%d` at a time too)
+            seen = set()
+            for key, v in S.iter_container(temp_dir, chrom, "%s_part_%d" % (name, i)):
+                if key == "coordinates":
+                    if i == 0:
+                        out.create_dataset("coordinates", v)
+                    continue
+                cell = int(key[5:])
+                if not (c0 <= cell < c1):
+                    continue
                 if normalise:
                     v = v / np.mean(v)
-                out.create_dataset("cell_%d" % cell, v.astype(np.float32), compress=True)
+                out.create_dataset(key, v.astype(np.float32), compress=True)
+                seen.add(cell)
+            if len(seen) != c1 - c0:
+                raise RuntimeError("part %d of %s misses cells: %s" % (i, chrom, sorted(set(range(c0, c1)) - seen)[:8]))
         out.close()
         for i in range(len(shards)):
             for ext in (".hdf5", ".npz"):

@@ -48,13 +48,16 @@ class ChromSink:
 
 class AsyncDrain:
     """One background thread that drains finished score blocks into the sinks while the GPU computes the next block
-    (SURVEY 8f rank 2).  submit(job) hands over a callable; at most `depth` jobs are in flight, so with depth + 1 pinned host
-    buffers the producer never overwrites a block that is still being written.  Exceptions of the writer are re-raised in the
-    caller by the next submit() / close()."""
+    (SURVEY 8f rank 2).  submit(job) hands over a callable and returns a ticket (threading.Event) that is set once the job has
+    RUN TO ITS END; at most `depth` jobs wait in the queue next to the one the writer is running.  A producer that recycles host
+    buffers must wait for the ticket of the job that last read a buffer before refilling it -- the queue bound alone does not
+    protect a buffer: the job the writer has already dequeued is still reading its block while the next one is queued.
+    Exceptions of the writer are re-raised in the caller by the next submit() / wait() / close()."""
 
     def __init__(self, depth: int = 1):
         import queue
         import threading
+        self._threading = threading
         self._q = queue.Queue(maxsize=depth)
         self._err = None
         self._t = threading.Thread(target=self._run, daemon=True)
@@ -62,12 +65,16 @@ class AsyncDrain:
 
     def _run(self):
         while True:
-            job = self._q.get()
+            item = self._q.get()
             try:
-                if job is None:
+                if item is None:
                     return
-                if self._err is None:
-                    job()
+                job, done = item
+                try:
+                    if self._err is None:
+                        job()
+                finally:
+                    done.set()
             except BaseException as e:      # noqa: BLE001 - handed to the caller
                 self._err = e
             finally:
@@ -80,7 +87,9 @@ class AsyncDrain:
 
     def submit(self, job):
         self._raise()
-        self._q.put(job)                    # blocks while `depth` jobs are pending
+        done = self._threading.Event()
+        self._q.put((job, done))            # blocks while `depth` jobs are queued
+        return done
 
     def wait(self):
         self._q.join()
@@ -94,12 +103,23 @@ class AsyncDrain:
 
 
 def read_container(temp_dir, chrom, name):
+    """Every dataset of one output container in memory (tests, small runs); use iter_container to stream a large one."""
+    return {k: np.asarray(v) for k, v in iter_container(temp_dir, chrom, name)}
+
+
+def iter_container(temp_dir, chrom, name):
+    """Yields (key, array) one dataset at a time -- a part file is never held in memory as a whole (linkhdf5_one_chrom reads one
+    `cell_%d` at a time, utils.py:217-253).  `coordinates` comes first."""
     base = os.path.join(temp_dir, "%s_%s" % (chrom, name))
     if h5py is not None and os.path.exists(base + ".hdf5"):
         with h5py.File(base + ".hdf5", "r") as f:
-            return {k: np.asarray(f[k]) for k in f.keys()}
+            keys = list(f.keys())
+            for k in sorted(keys, key=lambda q: q != "coordinates"):
+                yield k, np.asarray(f[k])
+        return
     with np.load(base + ".npz") as f:
-        return {k: f[k] for k in f.files}
+        for k in sorted(f.files, key=lambda q: q != "coordinates"):
+            yield k, f[k]
 
 
 def read_num(temp_dir):

@@ -169,6 +169,14 @@ class TrainEngine:
             C.c_float(1.0 if classification else 0.0), C.c_uint64(int(seed) & (2 ** 64 - 1)), C.byref(B), C.byref(nnz), C.c_void_p(stream)))
         return int(B.value), int(nnz.value)
 
+    def set_removal_draws(self, draws=None):
+        """Reproducibility hook (hsg_sample_set_removal_draws): uniform draws of the partner removal, one per bin-token row."""
+        if draws is None:
+            self.ctx._check(self.ctx.lib.hsg_sample_set_removal_draws(self.ctx.h, None, 0))
+            return
+        d = np.ascontiguousarray(_np(draws), dtype=np.float32).reshape(-1)
+        self.ctx._check(self.ctx.lib.hsg_sample_set_removal_draws(self.ctx.h, d.ctypes.data_as(C.POINTER(C.c_float)), d.size))
+
     def sample_batch_begin(self, pos, chrom: int, neg_num: int, pair_ratio: float, max_bin: int, pos_w=None, training: bool = True,
                            classification: bool = True, wide_check: bool = True, seed: int = 0):
         """Asynchronous first half of sample_batch (own stream): call it for batch i+1 before stepping on batch i."""

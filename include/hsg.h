@@ -132,6 +132,22 @@ int  hsg_prepare(hsg_ctx* ctx, int precision, int local_transfer_range, int acti
 int  hsg_impute_cells(hsg_ctx* ctx, int cell_start, int cell_end, float* out_dev, void* stream);
 /* same, result delivered to HOST memory (D2H overlapped with compute); out_host [n, P_total]. */
 int  hsg_impute_cells_host(hsg_ctx* ctx, int cell_start, int cell_end, float* out_host);
+/* reduced-precision score blocks (the sink's option): the same scores rounded once to IEEE fp16 by the
+ * scorer's epilogue -- half the bytes written to HBM and moved to the host; the sink widens them back to the fp32 `cell_%d`
+ * datasets of Impute.py:274-277.  Sigmoid outputs lie in [0, 1]: the rounding adds at most 2.44e-4.  Tensor-core scorer with a
+ * sigmoid head only (HSG_PREC_TC16, HSG_ACT_SIGMOID, d_model 64); any other configuration fails.  out: __half [n, P_total]. */
+int  hsg_impute_cells_f16(hsg_ctx* ctx, int cell_start, int cell_end, void* out_dev_half, void* stream);
+int  hsg_impute_cells_host_f16(hsg_ctx* ctx, int cell_start, int cell_end, void* out_host_half);
+/* replaces: the per-cell host-to-device copy of fix_cell2 (Modules.py:1432-1469, the `.to(device)` of the cell's sparse
+ * matrices) for a block of cells: re-uploads the stored entries (col / val, nnz_range of them = the extent of the rows of cells
+ * [cell_start, cell_end) in the matrix installed by hsg_set_contacts; the row extents do not change) on the context's upload
+ * stream and returns at once.  The copies are ordered behind the imputation work already queued (it may read these rows) and
+ * the next hsg_impute_cells* call waits for them -- events, no device-wide synchronisation.  col / val must stay untouched
+ * (pinned memory makes the copy asynchronous) until that call has been issued.                                             */
+int  hsg_refresh_contacts(hsg_ctx* ctx, int cell_start, int cell_end, const int32_t* col, const float* val, int64_t nnz_range);
+/* which scorer hsg_prepare selected: HSG_PREC_FP32, HSG_PREC_TC16 or HSG_PREC_TC16_HI.  A model whose fp16 operands could leave
+ * the fp16 range (bounds from the weights and the S tables, DESIGN.md "range guard") is moved to the next safer variant.      */
+int  hsg_scorer_variant(hsg_ctx* ctx, int* variant_out);
 
 /* ---- explicit triplets (Hyper_SAGNN.predict / forward) ------------------------------------- */
 /* replaces: GraphSageEncoder_with_weights.fix_cell2 (Modules.py:1432-1469) for one 1-based cell id */
@@ -190,6 +206,10 @@ int  hsg_sample_batch(hsg_ctx* ctx, const int64_t* pos_host, const float* pos_w_
 int  hsg_sample_batch_begin(hsg_ctx* ctx, const int64_t* pos_host, const float* pos_w_host, int Bp, int chrom, int neg_num,
                             float pair_ratio, int max_bin, int wide_check, int training, float neg_weight, uint64_t seed);
 int  hsg_sample_batch_end(hsg_ctx* ctx, int* B_out, int64_t* nnz_out, void* stream);
+/* reproducibility hook: the uniform draws of the 40 % partner removal (`np.random.rand(len(x), 2)` of Higashi_wrapper.py:270, one
+ * per bin-token row 2r + t) are taken from draws_host [n] for all following batches instead of the counter-based generator
+ * (rows past n use the generator); NULL / n = 0 restores the generator.                                                   */
+int  hsg_sample_set_removal_draws(hsg_ctx* ctx, const float* draws_host, int n);
 /* copies the produced batch to the host (tests / debugging); row r of the neighbour CSR = [indptr[r], indptr[r] + rowcnt[r]);
  * any pointer may be NULL                                                                                               */
 int  hsg_sampled_fetch(hsg_ctx* ctx, int64_t* x_host, float* y_host, float* w_host, int32_t* indptr_host, int32_t* rowcnt_host,

@@ -56,3 +56,41 @@ def test_c2_full_pair_set_properties():
     err = np.abs(outs["tc16"][:24] - outs["fp32"])
     print("C2 full pair set, 24 cells x 225023 pairs: max |tc16 - fp32| = %.3g, mean %.3g" % (err.max(), err.mean()))
     assert err.max() <= TOL_16BIT
+
+
+@pytest.mark.parametrize("workload,n_cells,cells", [("C2", 48, [0, 17, 47]), ("C3", 24, [5]), ("C5", 24, [11])])
+def test_full_size_cells_against_the_oracle(workload, n_cells, cells):
+    """whole cells at BASELINE.json's per-cell sizes against the ORACLE (oracle.impute.impute_cells, pinned to
+    the reference's goldens), not against another path of this library: C2 (P = 225 023 pairs per cell, 3 cells), one cell of C3
+    (500 kb genome-wide, P = 899 k) and one of C5 (50 kb chr2, 10 Mb band, P = 948 k), in the fast tensor-core mode (1e-3),
+    the high-accuracy mode (5e-4) and fp32 (1e-5)."""
+    import torch
+    import bench
+    from higashi_b200 import engine as E
+    from higashi_b200 import synthetic as S
+    from oracle import impute as OI, scorer as OS
+    ds = S.make_dataset(workload, shard=0, n_cells=n_cells)
+    sd, feats = S.random_state_dict(ds, ds.d, seed=0)
+    nbr, w = bench.knn_lists(ds, ds.k, 99)
+    chroms = list(range(len(ds.bins)))
+    tsd = {k: torch.from_numpy(np.asarray(v)) for k, v in sd.items()}
+    with torch.no_grad():
+        tables = OS.embed_tables(tsd, feats)
+    mx = int(1e5) if ds.max_bin < 0 else ds.max_bin
+    big, _, _, coords = OI.enumerate_pairs(ds.num_list, chroms, ds.min_bin, mx)
+    ref = OI.impute_cells(tsd, tables, ds.cell_feats, ds.num_list, lambda c, cell: ds.csr.matrix(c, cell - 1), cells, chroms, big, 0,
+                          nbr, w, "sigmoid")
+    eng = E.ScorerEngine(0)
+    eng.load_model(sd, ds.num, feats=feats, cell_feats=ds.cell_feats)
+    eng.set_contacts(ds.csr)
+    eng.set_neighbors(nbr, w)
+    assert eng.set_pairs(chroms, ds.min_bin, ds.max_bin) == len(big)
+    for j in chroms[:2]:
+        assert np.array_equal(eng.coordinates(j), coords[j])
+    for prec, tol, name in ((E.PREC_TC16, 1e-3, "tc16"), (E.PREC_TC16_HI, 5e-4, "tc16-hi"), (E.PREC_FP32, 1e-5, "fp32")):
+        eng.prepare(prec, 0, E.ACT_SIGMOID)
+        got = np.concatenate([eng.impute_to_host(c, c + 1) for c in cells])
+        err = np.abs(got - ref)
+        print("%s %s: %d cells x %d pairs vs oracle: max |err| = %.3g, mean %.3g" % (workload, name, len(cells), len(big), err.max(), err.mean()))
+        assert err.max() <= tol, (workload, name, float(err.max()))
+    eng.close()

@@ -236,7 +236,7 @@ def test_tiny_layernorm_gain_takes_high_accuracy_variant():
     _synthetic_case(4, 0, 64, "tc16", [120, 40], [0, 5, 39], mutate=shrink)
 
 
-def _synthetic_case(k, ltr, d, prec, bins, cells, density=None, band=-1, n_cells=40, mutate=None):
+def _synthetic_case(k, ltr, d, prec, bins, cells, density=None, band=-1, n_cells=40, mutate=None, expect_variant=None, tol=None):
     from higashi_b200 import engine as E
     from higashi_b200 import synthetic as S
     from oracle import impute as OI
@@ -259,8 +259,12 @@ def _synthetic_case(k, ltr, d, prec, bins, cells, density=None, band=-1, n_cells
     chroms = list(range(len(bins)))
     eng.set_pairs(chroms, 1, band)
     eng.prepare(E.PREC_FP32 if prec == "fp32" else E.PREC_TC16, ltr, E.ACT_SIGMOID)
-    tol = TOL_FP32 if prec == "fp32" else TOL_BF16
+    if expect_variant is not None:
+        assert eng.scorer_variant() == expect_variant, (eng.scorer_variant(), expect_variant)
+    if tol is None:
+        tol = TOL_FP32 if prec == "fp32" else TOL_BF16
     got_all = eng.impute_to_host(0, ds.n_cells)
+    assert np.isfinite(got_all).all()
     # oracle
     tsd = {k_: torch.from_numpy(np.asarray(v)) for k_, v in sd.items()}
     with torch.no_grad():
@@ -273,6 +277,101 @@ def _synthetic_case(k, ltr, d, prec, bins, cells, density=None, band=-1, n_cells
         assert np.array_equal(eng.coordinates(j), coords[j])
     print("max |err| (%s) = %.3g" % (prec, float(np.abs(got_all[cells] - ref).max())))
     np.testing.assert_allclose(got_all[cells], ref, atol=tol, rtol=0)
+    eng.close()
+
+
+# ------------------------------------------------------------------ fp16 range guard
+def test_range_guard_keeps_ordinary_models_on_the_fast_variant():
+    from higashi_b200 import engine as E
+    _synthetic_case(4, 0, 64, "tc16", [120, 40], [0, 5, 39], expect_variant=E.PREC_TC16)
+
+
+def test_range_guard_large_beta_over_gamma_routes_to_high_accuracy():
+    """Adversarial weights: layer_norm1 with a gain of 0.06 (above the 0.05 folding gate) and a bias of 30.  The fast variant would
+    store S' = (beta - S) / gamma ~ 500 and square it into fp16 (2.5e5 > 65504 -> inf -> sigmoid 0 / 1).  hsg_prepare must bound
+    |S'| from the model's own S tables and take the high-accuracy variant (unfolded layer_norm1: |u| ~ 30^2); scores stay finite
+    and inside the 16-bit bar."""
+    from higashi_b200 import engine as E
+
+    def big_bias(sd):
+        g = np.array(sd["layer_norm1.weight"], copy=True); b = np.array(sd["layer_norm1.bias"], copy=True)
+        g[5] = 0.06; b[5] = 30.0
+        g[40] = -0.07; b[40] = -25.0
+        sd["layer_norm1.weight"], sd["layer_norm1.bias"] = g, b
+    _synthetic_case(4, 0, 64, "tc16", [120, 40], [0, 5, 39], mutate=big_bias, expect_variant=E.PREC_TC16_HI)
+
+
+def test_range_guard_large_attention_projections_route_to_high_accuracy():
+    """Adversarial weights: w_qs / w_ks scaled by 40.  The half2 chains of a head's logit (4 products each) could pass 65504 in the
+    fast variant; the bound 4 |Q|max |K|max sends the model to the variant with fp32 Q / K tables and fp32 logits.  The logits are
+    huge, so the softmax saturates and the reference itself is insensitive: the plain 1e-3 bar applies."""
+    from higashi_b200 import engine as E
+
+    def big_qk(sd):
+        for nm in ("w_qs", "w_ks"):
+            key = "encode1.mul_head_attn.%s.weight" % nm
+            sd[key] = (np.array(sd[key], copy=True) * 40.0).astype(np.float32)
+    _synthetic_case(4, 0, 64, "tc16", [120, 40], [0, 5, 39], mutate=big_qk, expect_variant=E.PREC_TC16_HI)
+
+
+def test_range_guard_falls_back_to_fp32_kernels():
+    """layer_norm1.bias = 400: even the unfolded u = (LN1(z) gamma + beta - S)^2 ~ 1.6e5 leaves the fp16 range, the model must run on
+    the fp32 kernels (and then meets the fp32 bar scaled for the size of the logits)."""
+    from higashi_b200 import engine as E
+
+    def huge_bias(sd):
+        b = np.array(sd["layer_norm1.bias"], copy=True)
+        b[7] = 400.0
+        sd["layer_norm1.bias"] = b
+    _synthetic_case(0, 0, 64, "tc16", [90], [0, 3], mutate=huge_bias, expect_variant=E.PREC_FP32, tol=1e-3)
+
+
+def test_f16_score_block_and_refresh_contacts():
+    """the reduced-precision score block (hsg_impute_cells_host_f16) is the fp32 block rounded once to fp16
+    (<= 2.44e-4 on sigmoid outputs, so the 1e-3 bar vs the reference still holds: checked on the golden fixture), and
+    hsg_refresh_contacts (the per-block re-upload of the cells' own rows) leaves every score bit-identical."""
+    from higashi_b200 import engine as E
+    g = load("impute_k4_r0.npz")
+    ds = FixtureDataset(g)
+    sd = {k[3:]: v for k, v in g.items() if k.startswith("sd/")}
+    eng = _engine()
+    eng.load_model(sd, ds.num, feats=ds.feats, cell_feats=ds.cell_feats)
+    eng.set_contacts(ds.csr)
+    eng.set_neighbors(g["knn/nbr"], g["knn/w"])
+    chroms = list(range(len(ds.bins)))
+    mn, mx = [int(v) for v in g["cfg/band"]]
+    eng.set_pairs(chroms, mn, mx, g["cfg/skip"])
+    c0, c1 = [int(v) for v in g["cfg/cell_range"]]
+    eng.prepare(E.PREC_TC16, int(g["cfg/ltr"]), E.ACT_SIGMOID)
+    assert eng.scorer_variant() == E.PREC_TC16
+    full = eng.impute_to_host(c0, c1)
+    half = eng.impute_to_host(c0, c1, half=True)
+    assert half.dtype == np.float16
+    assert np.array_equal(half, full.astype(np.float16))                      # one rounding, nothing else changes
+    ref = np.concatenate([g["out/chr%d/cells" % (j + 1)] for j in chroms], axis=1)
+    err = float(np.abs(half.astype(np.float32) - ref).max())
+    print("fp16 score block vs reference: max |err| = %.3g" % err)
+    assert err <= TOL_BF16
+    dev = torch.empty((c1 - c0, eng.P), dtype=torch.float16, device="cuda")
+    eng.impute_to_device(c0, c1, dev)
+    torch.cuda.synchronize()
+    assert np.array_equal(dev.cpu().numpy(), half)
+    # refresh the rows of every cell in two blocks (pinned buffers), scores must not move
+    col = torch.from_numpy(np.ascontiguousarray(ds.csr.col)).pin_memory()
+    val = torch.from_numpy(np.ascontiguousarray(ds.csr.val)).pin_memory()
+    rp, nb = ds.csr.row_ptr, int(sum(ds.bins))
+    mid = ds.n_cells // 2
+    for a, b in ((0, mid), (mid, ds.n_cells)):
+        lo, hi = int(rp[a * nb]), int(rp[b * nb])
+        eng.ctx.refresh_contacts_ptr(a, b, col.data_ptr() + 4 * lo, val.data_ptr() + 4 * lo, hi - lo)
+    again = eng.impute_to_host(c0, c1)
+    assert np.array_equal(again, full)
+    with pytest.raises(Exception):
+        eng.ctx.refresh_contacts_ptr(0, mid, col.data_ptr(), val.data_ptr(), int(rp[mid * nb]) + 1)      # wrong extent
+    # the fp32 kernels have no 16-bit epilogue: the call must fail, not fall back
+    eng.prepare(E.PREC_FP32, int(g["cfg/ltr"]), E.ACT_SIGMOID)
+    with pytest.raises(Exception):
+        eng.impute_to_host(c0, c1, half=True)
     eng.close()
 
 

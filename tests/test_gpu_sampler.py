@@ -129,3 +129,51 @@ def test_forward_backward_on_device_batch_equals_host_fed_batch():
     scale = float(eng.grads.abs().max())
     assert float((g_dev - eng.grads).abs().max()) <= 1e-5 * max(scale, 1.0)
     eng.close()
+
+
+@pytest.mark.parametrize("tag", ["plain_eval", "knn_eval", "plain_train", "knn_train"])
+def test_device_neighbour_lists_match_the_reference_golden(tag):
+    """the device neighbour CSR against the UNMODIFIED reference (tests/golden/neighs.npz was minted by
+    one_thread_generate_neg + to_neighs_to_mask, Higashi_wrapper.py:236-333, 171-221), not against the repo's own host restatement.
+    The golden hyperedges (positives and the reference's negatives alike) go in as the batch, neg_num = 0; the `*_train` cases
+    replay the reference's stored uniform draws of the 40 % partner removal through hsg_sample_set_removal_draws."""
+    from higashi_b200 import synthetic as S
+    from higashi_b200.train_engine import TrainEngine
+    from tests._util import FixtureDataset, load
+    g = load("neighs.npz")
+    ds = FixtureDataset(g)
+    sd, _ = S.random_state_dict(ds, 64, seed=3)
+    eng = TrainEngine(sd, ds.num, ds.feats, ds.cell_feats, device=0)
+    knn = tag.startswith("knn")
+    eng.set_graph(ds.csr, g["knn/nbr"] if knn else None, g["knn/w"].astype(np.float32) if knn else None)
+    x, x_chrom = g[tag + "/x"], g[tag + "/x_chrom"]
+    training = bool(g[tag + "/training"])
+    draws = g[tag + "/remove_draw"].astype(np.float32)
+    ind, val, uniq = g[tag + "/indices"], g[tag + "/values"], g[tag + "/unique"]
+    # golden rows: token row 2r + t of hyperedge r, columns = index into `unique` (global node ids, first-seen order)
+    gold = {}
+    for row, cidx, v in zip(ind[0], ind[1], val):
+        gold.setdefault(int(row), []).append((int(uniq[cidx]), float(v)))
+    checked = 0
+    for chrom in np.unique(x_chrom):
+        sel = np.nonzero(x_chrom == chrom)[0]
+        xs = np.ascontiguousarray(x[sel])
+        assert np.all(xs[:, 1] <= xs[:, 2])
+        if training:
+            eng.set_removal_draws(np.stack([draws[2 * sel], draws[2 * sel + 1]], axis=1).reshape(-1))
+        B, nnz = eng.sample_batch(xs, int(chrom), 0, 0.5, 10 ** 6, training=training, seed=1)
+        assert B == len(xs)
+        xb, _, _, indptr, rowcnt, cols, vals = eng.fetch_sampled(B, nnz)
+        assert np.array_equal(xb, xs)
+        base = int(ds.num_list[chrom]) + 1
+        for i, r in enumerate(sel):
+            for t in range(2):
+                lo, n = indptr[2 * i + t], rowcnt[2 * i + t]
+                want = sorted(gold.get(2 * int(r) + t, []))
+                assert n == len(want), (tag, int(r), t)
+                assert np.array_equal(cols[lo:lo + n] + base, np.array([w_[0] for w_ in want], dtype=np.int64)), (tag, int(r), t)
+                np.testing.assert_allclose(vals[lo:lo + n], np.array([w_[1] for w_ in want], dtype=np.float32), rtol=2e-6, atol=1e-7)
+                checked += n
+    assert checked == len(val)
+    eng.set_removal_draws(None)
+    eng.close()

@@ -202,3 +202,29 @@ def test_async_drain_orders_jobs_and_propagates_errors():
     d.submit(lambda: (_ for _ in ()).throw(ValueError("disk full")))
     with pytest.raises(ValueError):
         d.close()
+
+
+def test_recycled_score_buffers_wait_for_their_writer():
+    """the producer of Impute.impute_process recycles two pinned blocks.  A slow writer (gzip) must never see
+    a block overwritten under it: block k + 2 may only be filled after the ticket of block k's write job is set.  Same protocol
+    as Impute.py, CPU only, 6 blocks, writer 20x slower than the producer."""
+    import time
+    from higashi_b200.sink import AsyncDrain
+    bufs = [np.zeros(64, dtype=np.float32) for _ in range(2)]
+    tickets = [None, None]
+    written = {}
+    drain = AsyncDrain(depth=1)
+
+    def write(view, k):
+        time.sleep(0.02)                      # slow sink
+        written[k] = view.copy()              # lazy copy, as write_block does per cell
+
+    for k in range(6):
+        if tickets[k % 2] is not None:
+            tickets[k % 2].wait()
+        bufs[k % 2][:] = float(k)             # the GPU + D2H refill of this block
+        tickets[k % 2] = drain.submit(lambda v=bufs[k % 2], k=k: write(v, k))
+    drain.close()
+    assert sorted(written) == list(range(6))
+    for k in range(6):
+        assert np.all(written[k] == float(k)), (k, written[k][:4])
