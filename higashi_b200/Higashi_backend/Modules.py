@@ -312,6 +312,7 @@ class GraphSageEncoder_with_weights(nn.Module):
         argument of the reference is what `prep_one` would have produced from the same data)."""
         self.fix = True
         self.fixed_cell = int(cell)
+        self.local_transfer_range = int(local_transfer_range)      # Hyper_SAGNN.predict prepares the engine with it
 
     def forward_off_hook(self, nodes, to_neighs, *args, route_nn=None):
         raise RuntimeError("forward_off_hook is fused into Hyper_SAGNN.predict on the CUDA path")
@@ -406,12 +407,13 @@ class Hyper_SAGNN(nn.Module):
             eng.set_contacts(csr)
             eng.set_neighbors(nbr, nbr_w)
         self._engine = eng
+        self._prepared = None           # a new engine has not been prepared for any (activation, local_transfer_range) yet
         return eng
 
     def __getstate__(self):
         st = self.__dict__.copy()
         st["_engine"] = None            # the CUDA contexts are not part of the pickle (torch.save(model))
-        for k in ("_teng", "_teng_key", "_tmap", "_tflat", "_tversion", "_tseed"):
+        for k in ("_teng", "_teng_key", "_tmap", "_tflat", "_tversion", "_tseed", "_prepared"):
             st.pop(k, None)
         return st
 
@@ -492,7 +494,7 @@ class Hyper_SAGNN(nn.Module):
                torch.nn.functional.softplus: _engine.ACT_SOFTPLUS}.get(activation, None)
         if act is None:
             raise ValueError("activation must be None, torch.sigmoid or F.softplus")
-        key = (act, getattr(self, "_ltr", 0))
+        key = (act, int(getattr(dyn, "local_transfer_range", 0)))
         if getattr(self, "_prepared", None) != key:
             eng.prepare(_engine.PREC_FP32, key[1], act)
             self._prepared = key

@@ -295,14 +295,35 @@ __device__ __forceinline__ void attn_part(const Umma2Params& p, const TileRow& t
     }
 }
 
+__device__ __forceinline__ void named_bar_sync(int id, int count) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(count) : "memory"); }
+__device__ __forceinline__ void named_bar_arrive(int id, int count) { asm volatile("bar.arrive %0, %1;" ::"r"(id), "r"(count) : "memory"); }
+__device__ __forceinline__ uint32_t tmem_base_of(const unsigned char* smem, int off) { return *reinterpret_cast<const uint32_t*>(smem + off); }
+// operand ready -> MMA group: with issue warps the warpgroup only arrives (operand writes fenced first), otherwise its thread 0 issues
+#define REQ_MMA1()                                                                                                        \
+    if constexpr (ISS) { fence_async_smem(); tc_fence_before(); named_bar_arrive(5 + wg, 160); }                          \
+    else { ISSUE_BEGIN() mma_group<8, 128>(a_base, sbase + SMF_B_FC1, 128, t_y, 0u); ISSUE_END() }
+#define REQ_MMA2()                                                                                                        \
+    if constexpr (ISS) { tmem_st_wait(); tc_fence_before(); named_bar_arrive(5 + wg, 160); }                              \
+    else { ISSUE_BEGIN_TS() mma_group_ts<4, 64>(t_h, sbase + SMF_B_W1, 64, t_y, 1u);                                       \
+           umma_f16_ts(t_y, t_h + 32, umma_desc(sbase + SMF_X_W1B), umma_idesc_f16(128, 64), 1u); ISSUE_END() }
+#define REQ_MMA3()                                                                                                        \
+    if constexpr (ISS) { tmem_st_wait(); tc_fence_before(); named_bar_arrive(5 + wg, 160); }                              \
+    else { ISSUE_BEGIN_TS() mma_group_ts<4, 32>(t_h, sbase + SMF_B_C0, 32, t_y, 0u);                                       \
+           umma_f16_ts(t_y, t_h + 32, umma_desc(sbase + SMF_X_C0B), umma_idesc_f16(128, 32), 1u); ISSUE_END() }
+
 // TANH2: packed tanh.approx.f16x2 in the feed-forward swish (MUFU work of h: 64 -> 32 per row and token)
 // PIPE : software pipeline over the tokens of a warpgroup's own chain.  0: attention, MMA 1, epilogues strictly one after the
 //        other (every tensor-core round trip and every load burst is exposed).  1: the softmax weights of the NEXT token (Q / K /
 //        cross-term loads, 8 head dots) are computed while MMA 1 of the current token is in flight, its ctx tile (V loads, 16
 //        chunk products) is built while MMA 3 is in flight (the A tile is free once MMA 1 has completed) -- across tile
 //        boundaries too; the warpgroup carries only the 8 packed weight pairs from one part to the other.
-template <bool TANH2, int PIPE>
-__global__ void __launch_bounds__(UM_THREADS, 1) score_umma2_kernel(Umma2Params p) {
+// ISS  : dedicated MMA-issue warps.  0: thread 0 of a warpgroup issues its MMAs after a warpgroup barrier (its warp runs ~300
+//        uniform-datapath instructions per token while the three sibling warps wait, and every issue point is a barrier).
+//        1: a fifth warpgroup of four issue warps, warp w serving warpgroup w: the 128 epilogue threads only ARRIVE on a named
+//        barrier (no wait) once their operand is written and go on; the issue warp completes the barrier, issues the MMA group
+//        and commits to the warpgroup's mbarrier.  Register budget by setmaxnreg out of the 640 x 96 registers of the launch: 4 x 128 threads x 112 + 128 x 24.
+template <bool TANH2, int PIPE, bool ISS>
+__global__ void __launch_bounds__(ISS ? UM_THREADS + 128 : UM_THREADS, 1) score_umma2_kernel(Umma2Params p) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int tid = threadIdx.x, wg = tid >> 7, wtid = tid & 127, warp_in_wg = (tid >> 5) & 3;
     const uint32_t sraw = smem_u32(smem_raw);
@@ -337,8 +358,48 @@ __global__ void __launch_bounds__(UM_THREADS, 1) score_umma2_kernel(Umma2Params 
     const uint32_t a_row_x = a_base + (uint32_t)(wtid >> 3) * 1024u + (uint32_t)(wtid & 7) * (128u + 16u);
     mbar_wait(bar_w, 0);
 
-    uint32_t phase = 0;
     const long long n_tiles = (long long)p.n_batch * p.tiles_per_cell;
+    if constexpr (ISS) {
+        if (wg == UM_WG) {
+            // ---------------------------------------------------------------- issue warps: warp w serves warpgroup w
+            asm volatile("setmaxnreg.dec.sync.aligned.u32 24;");
+            // warp-uniform values go through a shuffle so that the compiler keeps them (and the MMA descriptors derived from them) in
+            // uniform registers: a UTCHMMA then needs no per-instruction R2UR / election sequence
+            const int sw = __shfl_sync(0xffffffffu, warp_in_wg, 0);                      // the warpgroup this warp serves
+            const uint32_t s_ty = __shfl_sync(0xffffffffu, tmem_base, 0) + (uint32_t)(sw * 128), s_th = s_ty + 64;
+            const uint32_t s_a = sbase + SM_A0_OF(0) + sw * SM_A_BYTES, s_bar = sbase + SM_BAR_OF(0) + 8 + sw * 8;
+            uint32_t lead_p;
+            asm volatile("{\n\t.reg .pred p;\n\telect.sync _|p, 0xffffffff;\n\tselp.u32 %0, 1, 0, p;\n\t}" : "=r"(lead_p));
+            const bool lead = lead_p != 0;
+            const long long nq = p.quad_cells ? (long long)((p.n_batch + p.nwg - 1) / p.nwg) * p.tiles_per_cell : (n_tiles + p.nwg - 1) / p.nwg;
+            long long n_tok = 0;
+            for (long long q = blockIdx.x; q < nq; q += gridDim.x) n_tok += 3;            // tokens this CTA scores per warpgroup
+            for (long long i = 0; i < n_tok; ++i) {
+                named_bar_sync(5 + sw, 160); tc_fence_after();                            // ctx tile complete in shared memory
+                if (lead) { mma_group<8, 128>(s_a, sbase + SMF_B_FC1, 128, s_ty, 0u); umma_commit(s_bar); }
+                __syncwarp();
+                named_bar_sync(5 + sw, 160); tc_fence_after();                            // h complete in TMEM
+                if (lead) {
+                    mma_group_ts<4, 64>(s_th, sbase + SMF_B_W1, 64, s_ty, 1u);
+                    umma_f16_ts(s_ty, s_th + 32, umma_desc(sbase + SMF_X_W1B), umma_idesc_f16(128, 64), 1u);
+                    umma_commit(s_bar);
+                }
+                __syncwarp();
+                named_bar_sync(5 + sw, 160); tc_fence_after();                            // u' complete in TMEM
+                if (lead) {
+                    mma_group_ts<4, 32>(s_th, sbase + SMF_B_C0, 32, s_ty, 0u);
+                    umma_f16_ts(s_ty, s_th + 32, umma_desc(sbase + SMF_X_C0B), umma_idesc_f16(128, 32), 1u);
+                    umma_commit(s_bar);
+                }
+                __syncwarp();
+            }
+            tc_fence_before();
+            __syncthreads();
+            return;
+        }
+        asm volatile("setmaxnreg.inc.sync.aligned.u32 112;");
+    }
+    uint32_t phase = 0;
     // quad_cells: the four warpgroups of a CTA score the SAME 128-pair tile for four consecutive cells, so everything
     // cell-invariant a tile reads (pairs, pair bias, V and S rows of its bins: about half of the operand bytes) comes from L2 once
     // per CTA and the siblings find it in L1.  The loop bound depends on the block only: control flow stays warp-uniform; a
@@ -356,25 +417,17 @@ __global__ void __launch_bounds__(UM_THREADS, 1) score_umma2_kernel(Umma2Params 
                 if (t == 0) attn_part<0, 3>(p, tr, a_row_x, w);
                 else if (t == 1) attn_part<1, 3>(p, tr, a_row_x, w);
                 else attn_part<2, 3>(p, tr, a_row_x, w);
-                ISSUE_BEGIN()                                   // MMA 1: [y_c | g] = ctx . [fc1c ; W0' fc1c]^T
-                mma_group<8, 128>(a_base, sbase + SMF_B_FC1, 128, t_y, 0u);
-                ISSUE_END()
+                REQ_MMA1()                                      // MMA 1: [y_c | g] = ctx . [fc1c ; W0' fc1c]^T
                 mbar_wait(bar_mma, phase); phase ^= 1;
                 tc_fence_after();
                 epi_h<TANH2>(t_y, t_h, t_lane, cst);
-                ISSUE_BEGIN_TS()                                // MMA 2: z_c = y_c + h . W1c^T + b1c
-                mma_group_ts<4, 64>(t_h, sbase + SMF_B_W1, 64, t_y, 1u);
-                umma_f16_ts(t_y, t_h + 32, umma_desc(sbase + SMF_X_W1B), umma_idesc_f16(128, 64), 1u);
-                ISSUE_END()
+                REQ_MMA2()                                      // MMA 2: z_c = y_c + h . W1c^T + b1c
                 float4 sreg[16];
                 load_s_row(p, t, cell, tr.pr, sreg);
                 mbar_wait(bar_mma, phase); phase ^= 1;
                 tc_fence_after();
                 epi_u(t_y, t_h, t_lane, sreg);
-                ISSUE_BEGIN_TS()                                // MMA 3: c = u' . C0'^T + cb0 / 2
-                mma_group_ts<4, 32>(t_h, sbase + SMF_B_C0, 32, t_y, 0u);
-                umma_f16_ts(t_y, t_h + 32, umma_desc(sbase + SMF_X_C0B), umma_idesc_f16(128, 32), 1u);
-                ISSUE_END()
+                REQ_MMA3()                                      // MMA 3: c = u' . C0'^T + cb0 / 2
                 mbar_wait(bar_mma, phase); phase ^= 1;
                 tc_fence_after();
                 osum += epi_o(t_y, t_lane, cst);
@@ -387,9 +440,7 @@ __global__ void __launch_bounds__(UM_THREADS, 1) score_umma2_kernel(Umma2Params 
         TileRow cur = decode_tile(p, blockIdx.x < n_quads ? (long long)blockIdx.x : 0, wg, wtid);
         if ((long long)blockIdx.x < n_quads) {
             attn_part<0, 3>(p, cur, a_row_x, w);
-            ISSUE_BEGIN()
-            mma_group<8, 128>(a_base, sbase + SMF_B_FC1, 128, t_y, 0u);
-            ISSUE_END()
+            REQ_MMA1()
         }
         for (long long q = blockIdx.x; q < n_quads; q += gridDim.x) {
             const bool has_next = q + gridDim.x < n_quads;                                  // block-uniform
@@ -407,19 +458,13 @@ __global__ void __launch_bounds__(UM_THREADS, 1) score_umma2_kernel(Umma2Params 
                 mbar_wait(bar_mma, phase); phase ^= 1;
                 tc_fence_after();
                 epi_h<TANH2>(t_y, t_h, t_lane, cst);
-                ISSUE_BEGIN_TS()
-                mma_group_ts<4, 64>(t_h, sbase + SMF_B_W1, 64, t_y, 1u);
-                umma_f16_ts(t_y, t_h + 32, umma_desc(sbase + SMF_X_W1B), umma_idesc_f16(128, 64), 1u);
-                ISSUE_END()
+                REQ_MMA2()
                 float4 sreg[16];
                 load_s_row(p, t, cell, cur.pr, sreg);
                 mbar_wait(bar_mma, phase); phase ^= 1;
                 tc_fence_after();
                 epi_u(t_y, t_h, t_lane, sreg);
-                ISSUE_BEGIN_TS()
-                mma_group_ts<4, 32>(t_h, sbase + SMF_B_C0, 32, t_y, 0u);
-                umma_f16_ts(t_y, t_h + 32, umma_desc(sbase + SMF_X_C0B), umma_idesc_f16(128, 32), 1u);
-                ISSUE_END()
+                REQ_MMA3()
                 // MMA 3 is in flight and MMA 1 of this token has completed: the A tile is free -> ctx tile of the next token
                 if (PIPE == 1) {
                     if (t == 0) attn_part<1, 2>(p, cur, a_row_x, w);
@@ -434,9 +479,7 @@ __global__ void __launch_bounds__(UM_THREADS, 1) score_umma2_kernel(Umma2Params 
                 tc_fence_after();
                 osum += epi_o(t_y, t_lane, cst);
                 if (t < 2 || has_next) {
-                    ISSUE_BEGIN()                               // orders the TMEM reads above and the A-tile writes before MMA 1
-                    mma_group<8, 128>(a_base, sbase + SMF_B_FC1, 128, t_y, 0u);
-                    ISSUE_END()
+                    REQ_MMA1()                                  // orders the TMEM reads above and the A-tile writes before MMA 1
                 }
             }
             store_score(p, cur, osum);
@@ -493,7 +536,8 @@ int launch_score_pairs_umma2(hsg_ctx* c, int cell_start, int n_batch, float* out
     p.tiles_per_cell = (int)((c->P + 127) / 128); p.act = c->act; p.out = out; p.out16 = (__half*)out16;
     static const bool env_quad = getenv("HSG_K2_QUAD") && getenv("HSG_K2_QUAD")[0] == '1';      // measured slower: off by default
     static const bool env_tanh2 = getenv("HSG_K2_TANH2") && getenv("HSG_K2_TANH2")[0] == '1';
-    static const int env_pipe = getenv("HSG_K2_PIPE") ? (getenv("HSG_K2_PIPE")[0] - '0') % 3 : 1;     // 0 serial, 1 split pipeline (default), 2 whole attention under MMA 3
+    static const int env_pipe = getenv("HSG_K2_PIPE") ? (getenv("HSG_K2_PIPE")[0] - '0') % 3 : 0;     // 0 serial (default: measured fastest), 1 split pipeline, 2 whole attention under MMA 3
+    static const bool env_iss = !(getenv("HSG_K2_ISS") && getenv("HSG_K2_ISS")[0] == '0');
     static const int env_nwg = getenv("HSG_K2_NWG") ? std::max(1, std::min(UM_WG, atoi(getenv("HSG_K2_NWG")))) : UM_WG;
     static const int env_exp = getenv("HSG_K2_EXP") ? atoi(getenv("HSG_K2_EXP")) : 0;
     p.quad_cells = env_quad ? 1 : 0; p.nwg = env_nwg; p.exp_flags = env_exp;
@@ -503,24 +547,23 @@ int launch_score_pairs_umma2(hsg_ctx* c, int cell_start, int n_batch, float* out
     static bool attr_set[64] = {};
     if (!attr_set[c->device & 63]) {
         const int sm_bytes = SM_PAIRS_OF(0) + 1024;
-        HSG_CUDA(cudaFuncSetAttribute(score_umma2_kernel<false, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, sm_bytes));
-        HSG_CUDA(cudaFuncSetAttribute(score_umma2_kernel<false, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, sm_bytes));
-        HSG_CUDA(cudaFuncSetAttribute(score_umma2_kernel<false, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, sm_bytes));
-        HSG_CUDA(cudaFuncSetAttribute(score_umma2_kernel<true, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, sm_bytes));
-        HSG_CUDA(cudaFuncSetAttribute(score_umma2_kernel<true, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, sm_bytes));
-        HSG_CUDA(cudaFuncSetAttribute(score_umma2_kernel<true, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, sm_bytes));
+#define K2ATTR(T2, PP, II) HSG_CUDA(cudaFuncSetAttribute(score_umma2_kernel<T2, PP, II>, cudaFuncAttributeMaxDynamicSharedMemorySize, sm_bytes))
+        K2ATTR(false, 0, false); K2ATTR(false, 1, false); K2ATTR(false, 2, false); K2ATTR(true, 0, false); K2ATTR(true, 1, false); K2ATTR(true, 2, false);
+        K2ATTR(false, 0, true); K2ATTR(false, 1, true); K2ATTR(false, 2, true); K2ATTR(true, 0, true); K2ATTR(true, 1, true); K2ATTR(true, 2, true);
+#undef K2ATTR
         attr_set[c->device & 63] = true;
     }
     const size_t smem = SM_PAIRS_OF(0) + 1024;
-    const int variant = (env_tanh2 ? 3 : 0) + env_pipe;
+    if (env_iss) p.nwg = UM_WG;
+#define K2V(T2, PP, II) score_umma2_kernel<T2, PP, II><<<grid, (II) ? UM_THREADS + 128 : p.nwg * 128, smem, s>>>(p)
+    const int variant = (env_iss ? 6 : 0) + (env_tanh2 ? 3 : 0) + env_pipe;
     switch (variant) {
-        case 0: score_umma2_kernel<false, 0><<<grid, env_nwg * 128, smem, s>>>(p); break;
-        case 1: score_umma2_kernel<false, 1><<<grid, env_nwg * 128, smem, s>>>(p); break;
-        case 2: score_umma2_kernel<false, 2><<<grid, env_nwg * 128, smem, s>>>(p); break;
-        case 3: score_umma2_kernel<true, 0><<<grid, env_nwg * 128, smem, s>>>(p); break;
-        case 4: score_umma2_kernel<true, 1><<<grid, env_nwg * 128, smem, s>>>(p); break;
-        default: score_umma2_kernel<true, 2><<<grid, env_nwg * 128, smem, s>>>(p); break;
+        case 0: K2V(false, 0, false); break;  case 1: K2V(false, 1, false); break;  case 2: K2V(false, 2, false); break;
+        case 3: K2V(true, 0, false); break;   case 4: K2V(true, 1, false); break;   case 5: K2V(true, 2, false); break;
+        case 6: K2V(false, 0, true); break;   case 7: K2V(false, 1, true); break;   case 8: K2V(false, 2, true); break;
+        case 9: K2V(true, 0, true); break;    case 10: K2V(true, 1, true); break;   default: K2V(true, 2, true); break;
     }
+#undef K2V
     c->launches++;
     HSG_CUDA(cudaGetLastError());
     return 0;

@@ -227,6 +227,43 @@ def test_stage1_trainer_step_runs_and_learns():
     eng.close()
 
 
+def test_stage1_composed_update_matches_the_reference():
+    """ONE composed stage-1 update (train_epoch with use_recon=True, Higashi_wrapper.py:970-1010: gradient norm
+    of the main loss, gradient norm of the reconstruction loss, ratio1, contractive term, Adam step) against a golden minted from
+    the UNMODIFIED reference in eval mode (tests/golden/make_golden_stage1_step.py): the losses, both norms, ratio1 and EVERY
+    parameter after the step."""
+    from higashi_b200 import parallel
+    from higashi_b200.train_engine import TrainEngine
+    g = load("stage1_step_d64.npz")
+    ds = FixtureDataset(g)
+    sd = {k[len("before/"):]: v for k, v in g.items() if k.startswith("before/")}
+    eng = TrainEngine(sd, ds.num, ds.feats, ds.cell_feats, device=0, cell_on_hook=True)
+    tr = parallel.DataParallelTrainer(eng, lr=float(g["cfg/lr"]))
+    loss = tr.step(g["x"], 0, None, g["y"], g["w"], stage=1, train_mode=False, alpha=float(g["cfg/alpha"]), beta=float(g["cfg/beta"]),
+                   median_sparsity=float(g["cfg/median_sparsity"]), contractive_weight=float(g["cfg/contractive_weight"]))
+    assert abs(loss - float(g["loss_bce"])) < 2e-5 and abs(tr.recon_loss - float(g["loss_mse"])) < 2e-5, (loss, tr.recon_loss)
+    torch.cuda.synchronize()
+    got = {k: v.detach().cpu().numpy() for k, v in eng.named_params().items()}
+    checked = moved = 0
+    for k in g:
+        if not k.startswith("after/"):
+            continue
+        name = k[len("after/"):]
+        if name not in got:
+            continue
+        want, before = g[k], g["before/" + name]
+        # Adam's first step moves a parameter by lr * sign(grad) (|update| = 1e-3 where the gradient is not tiny): comparing the
+        # parameters to 5e-5 checks the sign and presence of every gradient entry and the composition (ratio1, contractive term)
+        # (entries whose gradient is within rounding noise of zero may take a different fraction of the step: at most 0.5 % of a
+        # tensor may deviate, and never by more than the step itself)
+        diff = np.abs(got[name].reshape(want.shape) - want)
+        assert diff.max() <= 2.1e-3 and (diff > 5e-5).mean() <= 0.005, (name, float(diff.max()), float((diff > 5e-5).mean()))
+        checked += 1
+        moved += int(np.abs(want - before).max() > 0)
+    assert checked >= 40 and moved >= 20, (checked, moved)
+    eng.close()
+
+
 def test_module_forward_is_differentiable_like_the_reference():
     """Hyper_SAGNN.forward of the mirror under torch autograd (the reference's train_epoch body: model(x, (chrom, to_neighs)),
     F.binary_cross_entropy_with_logits, loss.backward()): heads, loss and every parameter gradient against the reference's

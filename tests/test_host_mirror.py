@@ -164,6 +164,42 @@ def test_predict_api_like_reference():
         np.testing.assert_allclose(out.reshape(-1), g["impute/sigmoid"][n], atol=1e-5, rtol=0)
 
 
+@pytest.mark.gpu
+def test_predict_honours_local_transfer_range_and_survives_pickle():
+    """the drop-in loop of Impute.py:253-277 (fix_cell2(cell, ..., local_transfer_range) then predict) must
+    score with the requested local_transfer_range (golden fixture with range 1), and a model that went through torch.save /
+    torch.load or a rebuilt engine must prepare the new engine again instead of failing with "call hsg_prepare first"."""
+    import io
+    g = load("impute_k0_r1_band.npz")
+    ds = FixtureDataset(g)
+    sd = {k[3:]: v for k, v in g.items() if k.startswith("sd/")}
+    model = build_mirror_model(ds, 64, sd)
+    model.eval()
+    model.only_model = True
+    ltr = int(g["cfg/ltr"])
+    assert ltr == 1
+    c0, c1 = [int(v) for v in g["cfg/cell_range"]]
+
+    def check(m):
+        m.build_engine(ds.csr)
+        for cell in (c0, c1 - 1):
+            m.encode1.dynamic_nn.fix_cell2(cell + 1, None, None, ltr, route_nn_list=None)
+            for j in range(len(ds.bins)):
+                coords = g["out/chr%d/coordinates" % (j + 1)]
+                base = int(ds.num_list[j]) + 1
+                x = np.concatenate([np.full((len(coords), 1), cell + 1, dtype=np.int64), coords + base], axis=-1)
+                out = m.predict(x, np.full(len(x), j, dtype=int), activation=torch.sigmoid)
+                np.testing.assert_allclose(out.reshape(-1), g["out/chr%d/cells" % (j + 1)][cell - c0], atol=1e-5, rtol=0)
+    check(model)
+    check(model)                       # rebuilt engine: prepared again
+    buf = io.BytesIO()
+    torch.save(model, buf)
+    buf.seek(0)
+    clone = torch.load(buf, map_location="cpu", weights_only=False)
+    assert getattr(clone, "_prepared", None) is None and clone._engine is None
+    check(clone)
+
+
 def test_packed_contact_blob_round_trip(tmp_path):
     """Stable binary layout of the packed contact CSR (8f rank 3): save -> memmap load -> identical arrays, and the object-array
     route of the reference (sparse_nondiag_adj_nbr_1.npy) packs to the same blob."""
