@@ -418,6 +418,8 @@ def train_bench(args, rank, world, local, steps=None, want_cpu=True):
         barrier()
         dt = parallel.max_over_ranks(time.perf_counter() - t0)
         e2e = {"value": world * n_steps * B / dt, "unit": "hyperedges/s", "h2d_bytes_per_step": int(h2d[0] // n_steps), "d2h_bytes_per_step": 4}
+        eng.sample_batch_end()                          # drain the batch the last step started: the next schedule begins afresh
+        torch.cuda.synchronize()
         rec = {"value": val, "ms_per_step": float(ms.item()) / done, "steps_timed": done, "e2e": e2e, "gpu_launches_per_step": launches / done}
         if uniform:
             rec["clocks"] = clocks

@@ -244,7 +244,7 @@ def test_stage1_composed_update_matches_the_reference():
     assert abs(loss - float(g["loss_bce"])) < 2e-5 and abs(tr.recon_loss - float(g["loss_mse"])) < 2e-5, (loss, tr.recon_loss)
     torch.cuda.synchronize()
     got = {k: v.detach().cpu().numpy() for k, v in eng.named_params().items()}
-    checked = moved = 0
+    checked = moved = n_sat = n_moved = 0
     for k in g:
         if not k.startswith("after/"):
             continue
@@ -252,14 +252,22 @@ def test_stage1_composed_update_matches_the_reference():
         if name not in got:
             continue
         want, before = g[k], g["before/" + name]
-        # Adam's first step moves a parameter by lr * sign(grad) (|update| = 1e-3 where the gradient is not tiny): comparing the
-        # parameters to 5e-5 checks the sign and presence of every gradient entry and the composition (ratio1, contractive term)
-        # (entries whose gradient is within rounding noise of zero may take a different fraction of the step: at most 0.5 % of a
-        # tensor may deviate, and never by more than the step itself)
-        diff = np.abs(got[name].reshape(want.shape) - want)
-        assert diff.max() <= 2.1e-3 and (diff > 5e-5).mean() <= 0.005, (name, float(diff.max()), float((diff > 5e-5).mean()))
+        # Adam's first step moves an entry by lr * g / (|g| + 1e-8): a full step of lr wherever |g| >> 1e-8.  Those entries check the sign
+        # and presence of every gradient and the composition (ratio1, contractive term): they must agree to 5e-5.  Entries whose
+        # reference step is not saturated have a gradient of the order of 1e-8 (e.g. the key LayerNorm bias, which only acts through
+        # the masked diagonal): there the step size is rounding noise of the gradient, so only its bound is checked.
+        lr = float(g["cfg/lr"])
+        gotv = got[name].reshape(want.shape)
+        sat = np.abs(want - before) >= 0.95 * lr
+        if sat.any():
+            assert np.abs(gotv - want)[sat].max() <= 5e-5, (name, float(np.abs(gotv - want)[sat].max()))
+        assert np.abs(gotv - before).max() <= 1.05 * lr, name
+        if not (want != before).any():                                  # no gradient at all in the reference (grad = None): untouched here
+            assert np.array_equal(gotv, before), name
+        n_sat += int(sat.sum()); n_moved += int((want != before).sum())
         checked += 1
         moved += int(np.abs(want - before).max() > 0)
+    assert n_sat >= 0.9 * n_moved, (n_sat, n_moved)
     assert checked >= 40 and moved >= 20, (checked, moved)
     eng.close()
 
