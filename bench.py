@@ -12,8 +12,9 @@ and writes a fresh [cells, P] fp32 block far above 126 MB).
 `value`  : whole-job triplets/s with inputs resident in HBM, device-timed (CUDA events, max over ranks).
 `e2e`    : same metric through the C ABI with HOST buffers: every step uploads the stored contacts of its own cells from
            pinned host memory (hsg_refresh_contacts) and reads the scores back into pinned host memory.
-`--impl reference` : the reference's CPU algorithm (oracle/ port, torch-CPU fp32, all host threads) on a
-           bounded sample of the same workload.
+`--impl reference` : the UNMODIFIED reference's own Impute.impute_process (baseline/_ref, a pip --target install of the reference
+           that is git-ignored and travels to the GPU box; import shims in oracle/ref_shims.py) on all host threads, one cell
+           per step of a 64-cell sample of the same shape; the oracle/ port only if that import fails (`cpu_baseline.kind`).
 
 Multi-GPU (torchrun): imputation shards by cell range, one rank per GPU, no data-path collective; every
 rank imputes its own synthetic shard (weak scaling); torch.distributed is only the barrier + max-time.
@@ -178,48 +179,92 @@ def knn_lists(ds, k, seed):
 
 
 # ------------------------------------------------------------------------------------------ reference arm
+def _reference_imputer(args, n_small):
+    """The reference's own modules on a shrunken shard of the workload (oracle/ref_runner.py), or None when the reference is not
+    importable on this box (no baseline/_ref install): the callers then time the oracle port and say so."""
+    if os.environ.get("HSG_REFERENCE_ARM", "") == "port":
+        return None, None, "forced by HSG_REFERENCE_ARM=port"
+    try:
+        from oracle import ref_runner as RR
+        if not RR.available():
+            return None, None, "baseline/_ref/higashi not found"
+        from higashi_b200 import synthetic as S
+        ds = S.make_dataset(args.workload, shard=0, n_cells=n_small)
+        nbr, w = knn_lists(ds, ds.k, 99)
+        return RR.ReferenceImputer(ds, nbr, w), ds, ""
+    except Exception as e:                                   # missing dependency of the reference on this box
+        return None, None, "reference import failed: %r" % (e,)
+
+
 def run_reference(args):
+    """`--impl reference`: the UNMODIFIED reference (Impute.impute_process from baseline/_ref through oracle/ref_shims.py) on the
+    host cores; the oracle port only when the reference cannot be imported."""
+    os.environ["CUDA_VISIBLE_DEVICES"] = ""          # the reference moves tensors to cuda when it sees one: this arm is its CPU path
     import torch
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    from oracle import impute as OI, scorer as OS
     cores = os.cpu_count() or 1
-    torch.set_num_threads(cores)
-    # the oracle needs only the cells it imputes (+ neighbours): a shrunken shard of the same shape
     n_small = 64
-    from higashi_b200 import synthetic as S
-    ds = S.make_dataset(args.workload, shard=0, n_cells=n_small)
-    sd, feats = S.random_state_dict(ds, ds.d, seed=0)
-    nbr, w = knn_lists(ds, ds.k, 99)
-    tsd = {k: torch.from_numpy(np.asarray(v)) for k, v in sd.items()}
-    chroms = list(range(len(ds.bins)))
-    with torch.no_grad():
-        tables = OS.embed_tables(tsd, feats)
-    mx = int(1e5) if ds.max_bin < 0 else ds.max_bin
-    big, _, _, _ = OI.enumerate_pairs(ds.num_list, chroms, ds.min_bin, mx)
-    P = len(big)
-    mats = lambda c, cell: ds.csr.matrix(c, cell - 1)
     cells_per_step = 1
-    times = []
-    for it in range(args.warmup + args.steps):
-        cells = [(it * cells_per_step + q) % n_small for q in range(cells_per_step)]
-        t0 = time.perf_counter()
-        OI.impute_cells(tsd, tables, ds.cell_feats, ds.num_list, mats, cells, chroms, big, 0, nbr, w, "sigmoid")
-        dt = time.perf_counter() - t0
-        if it >= args.warmup:
-            times.append(dt)
+    R, ds, why = _reference_imputer(args, n_small)
+    one_thread = None
+    if R is not None:
+        kind = "reference"
+        P = None
+        if not args.no_cpu_baseline:
+            dt, n = R.impute(0, 1)                   # Impute.py:14 pins torch to ONE thread at import: the reference's default
+            one_thread = n / dt
+        R.set_threads(cores)
+        times = []
+        for it in range(args.warmup + args.steps):
+            c0 = (it * cells_per_step) % (n_small - cells_per_step + 1)
+            dt, n = R.impute(c0, c0 + cells_per_step)
+            P = n // cells_per_step
+            if it >= args.warmup:
+                times.append(dt)
+        sample = ("%d cell(s) per step x %d steps of %s: the reference's Impute.impute_process (prep_one + fix_cell2 + "
+                  "predict(batch 1e5) + one cell_%%d dataset per chromosome; dict-backed h5py, no gzip) imported from %s, "
+                  "torch.set_num_threads(%d) after the import" % (cells_per_step, args.steps, args.workload,
+                                                                   os.path.relpath(R.shims.REFERENCE_ROOT, ROOT), cores))
+    else:
+        from oracle import impute as OI, scorer as OS
+        kind = "port"
+        torch.set_num_threads(cores)
+        # the oracle needs only the cells it imputes (+ neighbours): a shrunken shard of the same shape
+        from higashi_b200 import synthetic as S
+        ds = S.make_dataset(args.workload, shard=0, n_cells=n_small)
+        sd, feats = S.random_state_dict(ds, ds.d, seed=0)
+        nbr, w = knn_lists(ds, ds.k, 99)
+        tsd = {k: torch.from_numpy(np.asarray(v)) for k, v in sd.items()}
+        chroms = list(range(len(ds.bins)))
+        with torch.no_grad():
+            tables = OS.embed_tables(tsd, feats)
+        mx = int(1e5) if ds.max_bin < 0 else ds.max_bin
+        big, _, _, _ = OI.enumerate_pairs(ds.num_list, chroms, ds.min_bin, mx)
+        P = len(big)
+        mats = lambda c, cell: ds.csr.matrix(c, cell - 1)
+        times = []
+        for it in range(args.warmup + args.steps):
+            cells = [(it * cells_per_step + q) % n_small for q in range(cells_per_step)]
+            t0 = time.perf_counter()
+            OI.impute_cells(tsd, tables, ds.cell_feats, ds.num_list, mats, cells, chroms, big, 0, nbr, w, "sigmoid")
+            dt = time.perf_counter() - t0
+            if it >= args.warmup:
+                times.append(dt)
+        sample = ("%d cell(s) per step x %d steps of %s (oracle/ torch-CPU fp32 restatement of Impute.impute_process: prep_one + "
+                  "fix_cell2 + predict(batch 1e5)); the reference itself was not used: %s" % (cells_per_step, args.steps, args.workload, why))
     total = sum(times)
     val = args.steps * cells_per_step * P / total
+    cb = {"value": val, "unit": "triplets/s", "cores": cores, "kind": kind, "sample": sample}
+    if one_thread is not None:
+        cb["value_1_thread"] = one_thread
     line = {"impl": "reference", "metric": "imputed (cell,bin_i,bin_j) triplets/s", "value": val, "unit": "triplets/s",
             "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * total / args.steps,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": {"workload": "%s: %d-cell sample of the synthetic shape, %d bins, P=%d pairs/cell, k=%d, d=%d"
                        % (args.workload, n_small, sum(ds.bins), P, ds.k, ds.d)},
-            "cpu_baseline": {"value": val, "unit": "triplets/s", "cores": cores, "kind": "port",
-                             "sample": "%d cell(s) per step x %d steps of %s (oracle/ torch-CPU fp32 restatement of "
-                                       "Impute.impute_process: prep_one + fix_cell2 + predict(batch 1e5))"
-                                       % (cells_per_step, args.steps, args.workload)},
+            "cpu_baseline": cb,
             "e2e": {"value": val, "unit": "triplets/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
     emit(line)
@@ -283,7 +328,26 @@ def run_reference_train(args):
 
 
 def cpu_baseline(args, ds_shape):
-    """Bounded CPU sample (oracle port) for the `cpu_baseline` object of the main line."""
+    """Bounded CPU sample for the `cpu_baseline` object of the main line: the reference arm of this script in a child process
+    (the reference's CPU path must not see the GPU this process holds), 3 steps of one cell; the in-process oracle port when the
+    child fails."""
+    try:
+        env = dict(os.environ, CUDA_VISIBLE_DEVICES="")
+        for k in ("RANK", "LOCAL_RANK", "WORLD_SIZE", "MASTER_ADDR", "MASTER_PORT"):
+            env.pop(k, None)
+        out = subprocess.run([sys.executable, os.path.abspath(__file__), "--impl", "reference", "--workload", args.workload,
+                              "--steps", "3", "--warmup", "1"], capture_output=True, text=True, timeout=240, env=env, cwd=ROOT)
+        lines = [l for l in out.stdout.splitlines() if l.strip().startswith("{")]
+        cb = json.loads(lines[-1])["cpu_baseline"]
+        if cb.get("value", 0) > 0:
+            return cb
+    except Exception:
+        pass
+    return cpu_baseline_port(args, ds_shape)
+
+
+def cpu_baseline_port(args, ds_shape):
+    """Bounded CPU sample (oracle port)."""
     import torch
     from higashi_b200 import synthetic as S
     from oracle import impute as OI, scorer as OS

@@ -80,6 +80,9 @@ static void free_derived(hsg_ctx* c) {
     { __half* p = (__half*)c->binV16; dev_free(p); c->binV16 = nullptr; }
     { __half* p = (__half*)c->cellV16; dev_free(p); c->cellV16 = nullptr; }
     dev_free(c->XS); dev_free(c->binSb); dev_free(c->cellSb); dev_free(c->binV32p); dev_free(c->cellV32p); dev_free(c->wimg); dev_free(c->cst); dev_free(c->pj_wimg); dev_free(c->ovf_list);
+    dev_free(c->tiles4); c->n_tiles4 = 0; c->k2v4 = false;
+    { __half* p = (__half*)c->binP; dev_free(p); c->binP = nullptr; }
+    { __half* p = (__half*)c->cellP; dev_free(p); c->cellP = nullptr; }
     c->ovf_cap = 0;                          // the overflow list is gone: the next gather must allocate it again
     c->use_umma = false;
     dev_free(c->stage_out[0]); dev_free(c->stage_out[1]); c->stage_bytes = 0;
@@ -544,11 +547,12 @@ extern "C" int hsg_prepare(hsg_ctx* c, int precision, int local_transfer_range, 
     if (c->use_umma) {
         std::vector<unsigned char> wimg(umma_wimg_bytes());
         std::vector<float> cst(umma_cst_count(), 0.f);
+        std::vector<float> fcomb((size_t)2 * 64 * HSG_HD);
         umma_build_weights(h->v[HSG_W_FC1].data(), h->v[HSG_W_PFF_W0].data(), h->v[HSG_W_PFF_B0].data(),
                            h->v[HSG_W_PFF_LN_G].data(), h->v[HSG_W_PFF_LN_B].data(), h->v[HSG_W_PFF_W1].data(),
                            h->v[HSG_W_PFF_B1].data(), h->v[HSG_W_LN1_G].data(), h->v[HSG_W_CLS_W0].data(),
                            h->v[HSG_W_CLS_B0].data(), h->v[HSG_W_CLS_W1].data(), h->v[HSG_W_CLS_B1].data(), c->umma_hi ? 1 : 0, c->k2v2 ? 1 : 0,
-                           wimg.data(), cst.data());
+                           wimg.data(), cst.data(), fcomb.data());
         if (dev_alloc(&c->wimg, wimg.size()) || dev_alloc(&c->cst, cst.size())) return 1;
         HSG_CUDA(cudaMemcpy(c->wimg, wimg.data(), wimg.size(), cudaMemcpyHostToDevice));
         HSG_CUDA(cudaMemcpy(c->cst, cst.data(), cst.size() * sizeof(float), cudaMemcpyHostToDevice));
@@ -577,6 +581,24 @@ extern "C" int hsg_prepare(hsg_ctx* c, int precision, int local_transfer_range, 
         if (c->k2v2) {
             if (launch_convert_static2(c, c->binV, c->binS, c->n_bins, 1, c->binV16, c->binSb, c->stream)) return 1;
             if (launch_convert_static2(c, c->cellV, c->cellS, c->n_cells, 0, c->cellV16, c->cellSb, c->stream)) return 1;
+            // generation 4 (default; HSG_K2_GEN=2 / 3 select the earlier kernels): P tables + tile table of the pair list
+            const char* gen = getenv("HSG_K2_GEN");
+            c->k2v4 = !(gen && (gen[0] == '2' || gen[0] == '3')) && c->P > 0;
+            if (c->k2v4) {
+                float* dF = nullptr; __half *bp = nullptr, *cp = nullptr;
+                if (dev_alloc(&dF, fcomb.size()) || dev_alloc(&bp, (size_t)c->n_bins * 128 * 8) || dev_alloc(&cp, (size_t)c->n_cells * 128 * 8)) return 1;
+                c->binP = bp; c->cellP = cp;
+                HSG_CUDA(cudaMemcpyAsync(dF, fcomb.data(), fcomb.size() * sizeof(float), cudaMemcpyHostToDevice, c->stream));
+                if (launch_build_ptable(c, c->binV, dF, c->n_bins, c->binP, c->stream)) return 1;
+                if (launch_build_ptable(c, c->cellV, dF, c->n_cells, c->cellP, c->stream)) return 1;
+                HSG_CUDA(cudaStreamSynchronize(c->stream));
+                dev_free(dF);
+                std::vector<int> tiles;
+                build_tiles4(c->h_pairs.data(), c->P, tiles);       // host copy of the pair list kept by hsg_set_pairs
+                c->n_tiles4 = (int)(tiles.size() / 8);
+                if (dev_alloc(&c->tiles4, tiles.size())) return 1;
+                HSG_CUDA(cudaMemcpy(c->tiles4, tiles.data(), tiles.size() * sizeof(int), cudaMemcpyHostToDevice));
+            }
         } else {
         if (launch_convert_static(c, c->binV, c->binS, c->n_bins, c->binV16, c->binSb, c->umma_hi ? c->binV32p : nullptr, c->stream)) return 1;
         if (launch_convert_static(c, c->cellV, c->cellS, c->n_cells, c->cellV16, c->cellSb, c->umma_hi ? c->cellV32p : nullptr, c->stream)) return 1;
@@ -616,7 +638,8 @@ static int run_batch(hsg_ctx* c, int cell0, int nb, float* out, cudaStream_t s, 
     if (c->use_umma && c->use_proj_umma) { if (launch_token_project_umma(c, cell0, nb, s)) return 1; }
     else if (launch_token_project(c, cell0, nb, c->use_umma ? (c->umma_hi ? 2 : 1) : 0, s)) return 1;
     if (prof) HSG_CUDA(cudaEventRecord(c->ev[2], s));
-    if (c->k2v2) { if (launch_score_pairs_umma2(c, cell0, nb, out, out16, s)) return 1; }
+    if (c->k2v4) { if (launch_score_pairs_umma4(c, cell0, nb, out, out16, s)) return 1; }
+    else if (c->k2v2) { if (launch_score_pairs_umma2(c, cell0, nb, out, out16, s)) return 1; }
     else if (c->use_umma) { if (launch_score_pairs_umma(c, cell0, nb, out, s)) return 1; }
     else if (launch_score_pairs_f32(c, cell0, nb, out, s)) return 1;
     if (prof) {

@@ -123,6 +123,8 @@ struct hsg_ctx {
     unsigned char* wimg = nullptr; float* cst = nullptr; float h_cst[512] = {0};
     unsigned char* pj_wimg = nullptr; float h_pj_cst[320] = {0}; bool use_proj_umma = false;   // tensor-core K1b (project_umma.cu)
     bool use_umma = false;
+    // generation 4 of the fast scorer (score_umma4.cu): tile table of the pair list, P tables of the bins and cells
+    int* tiles4 = nullptr; int n_tiles4 = 0; void* binP = nullptr; void* cellP = nullptr; bool k2v4 = false;
     bool k2v2 = false;                       // fast tensor-core variant runs score_umma2.cu: chunk-major QK16 / XS / binV16 tables
     bool umma_hi = false;                    // high-accuracy tensor-core variant (fp32 tables, hi/lo operand splits)
     int n_sm = 148;
@@ -150,9 +152,12 @@ int launch_score_pairs_umma(hsg_ctx* c, int cell_start, int n_cells_batch, float
 int launch_convert_static(hsg_ctx* c, const float* V, const float* S, long long rows, void* V16, float* Sb, float* V32p, cudaStream_t s);
 int launch_convert_static2(hsg_ctx* c, const float* V, const float* S, long long rows, int chunk_major, void* V16, float* Sb, cudaStream_t s);
 int launch_score_pairs_umma2(hsg_ctx* c, int cell_start, int n_cells_batch, float* out, void* out16, cudaStream_t s);
+int launch_score_pairs_umma4(hsg_ctx* c, int cell_start, int n_cells_batch, float* out, void* out16, cudaStream_t s);
+int launch_build_ptable(hsg_ctx* c, const float* V, const float* F, long long rows, void* P, cudaStream_t s);
+void build_tiles4(const int2* pairs, long long P, std::vector<int>& out);
 int umma_build_weights(const float* fc1, const float* w0, const float* b0, const float* pff_g, const float* pff_b,
                        const float* w1, const float* b1, const float* ln1_g, const float* c0, const float* cb0,
-                       const float* cw1, const float* cb1, int hi, int natural_k, unsigned char* wimg_host, float* cst_host);
+                       const float* cw1, const float* cb1, int hi, int natural_k, unsigned char* wimg_host, float* cst_host, float* comb_out = nullptr);
 int umma_gain_foldable(const float* ln1_g);
 int umma_range_level(const float* wq, const float* wk, const float* wv, const float* g1, const float* b1, const float* g2, const float* b2,
                      const float* g3, const float* b3, const float* w0, const float* b0, const float* pff_g, const float* pff_b,

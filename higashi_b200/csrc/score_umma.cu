@@ -351,7 +351,8 @@ __global__ void __launch_bounds__(UM_THREADS, 1) score_umma_kernel(UmmaParams p)
 
 int umma_build_weights(const float* fc1, const float* w0, const float* b0, const float* pff_g, const float* pff_b,
                        const float* w1, const float* b1, const float* ln1_g, const float* c0, const float* cb0,
-                       const float* cw1, const float* cb1, int hi, int natural_k, unsigned char* wimg_host, float* cst_host) {
+                       const float* cw1, const float* cb1, int hi, int natural_k, unsigned char* wimg_host, float* cst_host,
+                       float* comb_out) {
     const int d = UM_D;
     std::vector<float> w0f((size_t)d * d);
     for (int n = 0; n < d; ++n) {
@@ -382,6 +383,7 @@ int umma_build_weights(const float* fc1, const float* w0, const float* b0, const
             for (int j = 0; j < d; ++j) acc += (double)w0f[(size_t)n * d + j] * fc1c[(size_t)j * HSG_HD + k];
             comb[(size_t)(d + n) * HSG_HD + k] = (float)acc;
         }
+    if (comb_out) memcpy(comb_out, comb.data(), comb.size() * sizeof(float));      // F = [fc1c ; W0' fc1c], natural K order (score_umma4.cu)
     if (!natural_k) {   // the ctx A tile arrives with its 16-byte chunks in HSG_CHUNK_POS order: permute the K columns of the image to match (score_umma2.cu keeps the natural order)
         std::vector<float> perm(comb.size());
         for (int n = 0; n < 2 * d; ++n)
