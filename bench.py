@@ -70,6 +70,7 @@ def parse():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-train", action="store_true", help="skip the secondary training line of the default invocation")
+    ap.add_argument("--no-c3", action="store_true", help="skip the secondary strong-scaling C3 job of the default invocation")
     return ap.parse_args()
 
 
@@ -563,6 +564,101 @@ def run_train(args):
         dist.destroy_process_group()
 
 
+def c3_strong(args, rank, world, local):
+    """Strong scaling on the configuration the north star names (BASELINE.json configs[2]): ONE synthetic 4200-cell, 500 kb,
+    genome-wide dataset (5776 bins, P = 898 321 pairs per cell, k = 4), its cells split over the ranks the way the reference splits
+    them over its worker processes (np.array_split, Higashi_wrapper.py:1457-1475); a rank holds its own cells plus the kNN halo
+    (the neighbour cells its cells aggregate, replicated), no collective.  One "job" = every rank imputes all of its own cells;
+    `value` = 4200 * P / (max over ranks of the device time of the job); `e2e` = the same job through host buffers (contacts of
+    own + halo cells uploaded from pinned memory once per job, every score block read back into pinned memory)."""
+    import types
+    import torch
+    import torch.distributed as dist
+    from higashi_b200 import engine as E, parallel, synthetic as S
+    n_glob, k = S.CONFIGS["C3"]["n_cells"], S.CONFIGS["C3"]["k"]
+    nbr_g, w_g = knn_lists(types.SimpleNamespace(n_cells=n_glob), k, 4242)          # the same graph on every rank
+    c0, c1 = parallel.cell_shards(n_glob, world)[rank]
+    own = np.arange(c0, c1)
+    local_cells = np.unique(np.concatenate([own, (nbr_g[own] - 1).reshape(-1)]))
+    t_gen = time.perf_counter()
+    ds = S.make_dataset_cells("C3", local_cells, threads=max(2, min(16, (os.cpu_count() or 8) // max(world, 1))))
+    t_gen = time.perf_counter() - t_gen
+    g2l = np.full(n_glob, -1, dtype=np.int64)
+    g2l[local_cells] = np.arange(len(local_cells))
+    nbr_l = np.repeat(np.arange(1, len(local_cells) + 1, dtype=np.int64)[:, None], k + 1, axis=1)     # halo cells: themselves only
+    w_l = np.zeros((len(local_cells), k + 1), dtype=np.float32)
+    w_l[:, 0] = 1.0
+    nbr_l[g2l[own]] = g2l[nbr_g[own] - 1] + 1
+    w_l[g2l[own]] = w_g[own]
+    l0 = int(g2l[c0])
+    assert np.array_equal(g2l[own], np.arange(l0, l0 + len(own)))                    # own cells stay contiguous
+    sd, feats = S.random_state_dict(ds, ds.d, seed=0)
+    eng = E.ScorerEngine(local)
+    eng.load_model(sd, ds.num, feats=feats, cell_feats=ds.cell_feats)
+    P = eng.set_pairs(list(range(len(ds.bins))), ds.min_bin, ds.max_bin)
+    pin = lambda a: torch.from_numpy(np.ascontiguousarray(a)).pin_memory()
+    h_rowptr, h_col, h_val = pin(ds.csr.row_ptr), pin(ds.csr.col), pin(ds.csr.val)
+    eng.ctx.set_contacts(h_rowptr.numpy(), h_col.numpy(), h_val.numpy())
+    eng.set_neighbors(nbr_l, w_l)
+    eng.prepare(getattr(E, "DEFAULT_PRECISION", E.PREC_TC16), 0, E.ACT_SIGMOID)
+    cps = 250
+    out = torch.empty((cps, P), dtype=torch.float32, device="cuda")
+    stream = torch.cuda.current_stream()
+    chunks = [(a, min(a + cps, l0 + len(own))) for a in range(l0, l0 + len(own), cps)]
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def job():
+        for a, b in chunks:
+            eng.impute_to_device(a, b, out[: b - a], stream.cuda_stream)
+    job()                                                                            # warm-up pass
+    barrier()
+    reps = 1 if world == 1 else 3
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    ev0.record(stream)
+    for _ in range(reps):
+        job()
+    ev1.record(stream)
+    barrier()
+    ms = parallel.max_over_ranks(ev0.elapsed_time(ev1) / reps)
+    res = {"metric": "imputed (cell,bin_i,bin_j) triplets/s", "unit": "triplets/s", "scaling": "strong", "n_gpus": world,
+           "value": n_glob * P / (ms * 1e-3), "ms_per_job": ms, "jobs_timed": reps,
+           "config": {"workload": "C3: ONE synthetic dataset of %d cells x %d bins, P=%d pairs/cell, k=%d, d_model=%d, all-bin-pair "
+                                  "imputation sharded by cell range (np.array_split), kNN halo replicated, no collective"
+                                  % (n_glob, sum(ds.bins), P, k, ds.d),
+                      "cells_this_rank": int(len(own)), "halo_cells_this_rank": int(len(local_cells) - len(own)),
+                      "cells_per_call": cps, "host_seconds_generating_the_shard": round(t_gen, 1)}}
+
+    def e2e_leg(half):
+        h_out = torch.empty((cps, P), dtype=torch.float16 if half else torch.float32).pin_memory()
+        nnz = int(ds.csr.row_ptr[-1])
+
+        def e2e_job():
+            eng.ctx.refresh_contacts_ptr(0, len(local_cells), h_col.data_ptr(), h_val.data_ptr(), nnz)      # H2D, once per job
+            for a, b in chunks:
+                eng.ctx.impute_cells_host_ptr(a, b, h_out.data_ptr(), half=half)
+        e2e_job()
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(reps):
+            e2e_job()
+        barrier()
+        dt = parallel.max_over_ranks((time.perf_counter() - t0) / reps)
+        return {"value": n_glob * P / dt, "unit": "triplets/s", "h2d_bytes_per_job": nnz * 8,
+                "d2h_bytes_per_job": int(len(own)) * P * (2 if half else 4)}
+    if not args.no_e2e:
+        res["e2e"] = e2e_leg(False)
+        res["e2e_f16"] = e2e_leg(True)
+    eng.close()
+    del out
+    torch.cuda.empty_cache()
+    return res
+
+
 def main():
     args = parse()
     _claim_stdout()
@@ -734,6 +830,12 @@ def main():
             train_line = train_bench(args, rank, world, local, steps=20)
         except Exception as e:                                       # never lose the headline line over the secondary figure
             train_line = {"error": repr(e)}
+    c3_line = None
+    if not args.no_c3 and not args.n_cells and args.workload == "C2":
+        try:
+            c3_line = c3_strong(args, rank, world, local)
+        except Exception as e:
+            c3_line = {"error": repr(e)}
     if rank == 0:
         cpu = None
         if not args.no_cpu_baseline and world == 1:
@@ -753,6 +855,8 @@ def main():
             line["e2e_f16"] = e2e_f16
         if train_line is not None:
             line["secondary"] = {"train": train_line}
+        if c3_line is not None:
+            line.setdefault("secondary", {})["c3_strong"] = c3_line
         if args.n_cells:
             line["invalid"] = "dataset shrunk with --n-cells (debug run)"
         emit(line)

@@ -32,6 +32,18 @@
 #include "score_rows.cuh"
 
 #define U4_WG 3
+// ablation switches (HSG_K2_EXP bits, HSG_K2_NWG) are compiled in only with -DHSG_K2_ABLATE=1: as run-time tests they cost the default
+// kernel 14 % (measured); results are WRONG with any bit set.  bit 0 no softmax weights, 1 no ctx rows, 2 no S' loads, 3 / 4 / 5 no
+// h / u / o epilogue.  Round 2, 600 cells of C2, K2 ms: all 33.2 | 2 warpgroups 46.0 | 1 warpgroup 74.8 | -weights 26.7 | -ctx 30.6 |
+// -S' 31.6 | -h 29.3 | -u 30.7 | -o 30.6 | -all three epilogues 24.9 | MMA chain + barriers only 12.8.
+#ifndef HSG_K2_ABLATE
+#define HSG_K2_ABLATE 0
+#endif
+#if HSG_K2_ABLATE
+#define ABL(bit) (p.exp_flags & (bit))
+#else
+#define ABL(bit) false
+#endif
 #define U4_SM_BAR SMF_WIMG_BYTES                 // 8 mbarriers
 #define U4_SM_TMEM (U4_SM_BAR + 64)
 #define U4_SM_SLOT (U4_SM_TMEM + 16)             // int owner[2], int slot_of[U4_WG]
@@ -144,7 +156,11 @@ __global__ void __launch_bounds__(512, 1) score_umma4_kernel(Umma4Params pp) {
     const uint32_t tmem_base = *tmem_slot;
     mbar_wait(bar_w, 0);
     const long long n_tiles = (long long)p.n_batch * pp.n_tiles_cell;
-    const int nwg = p.nwg;                                                     // active warpgroups (U4_WG; fewer only in experiments)
+#if HSG_K2_ABLATE
+    const int nwg = p.nwg;                                                     // active warpgroups (fewer than U4_WG only in experiments)
+#else
+    constexpr int nwg = U4_WG;
+#endif
     const long long n_quads = (n_tiles + nwg - 1) / nwg;
 
     if (wg == U4_WG) {
@@ -265,7 +281,7 @@ __global__ void __launch_bounds__(512, 1) score_umma4_kernel(Umma4Params pp) {
             }
             wg_bar(wg);
             tc_fence_after();                // the previous owner's MMA 1 (its reads of the slot) completed before it released
-            if (!(p.exp_flags & 2)) ctx_var_tmem(p.binVc, (uint32_t)tr.pr.y, tmem_base + 384u + 64u * (uint32_t)slot_of[wg] + t_lane, WB);
+            if (!ABL(2)) ctx_var_tmem(p.binVc, (uint32_t)tr.pr.y, tmem_base + 384u + 64u * (uint32_t)slot_of[wg] + t_lane, WB);
         }
     };
     auto request = [&]() { tmem_st_wait(); tc_fence_before(); named_bar_arrive(5 + wg, 160); };
@@ -288,23 +304,23 @@ __global__ void __launch_bounds__(512, 1) score_umma4_kernel(Umma4Params pp) {
 #pragma unroll 1
             for (int t = 0; t < 3; ++t) {
                 const bool more = t < 2 || has_next;
-                if (more && !(p.exp_flags & 1)) weights(t < 2 ? cur : nxt, t < 2 ? t + 1 : 0, WA, WB);       // MMA 1 of token t is in flight
+                if (more && !ABL(1)) weights(t < 2 ? cur : nxt, t < 2 ? t + 1 : 0, WA, WB);       // MMA 1 of token t is in flight
                 wait_mma();
                 if (t != 2) release_slot();                                    // MMA 1 has read the slot
-                if (!(p.exp_flags & 8)) epi_h<false>(t_y, t_h, t_lane, cst);
+                if (!ABL(8)) epi_h<false>(t_y, t_h, t_lane, cst);
                 request();                                                     // MMA 2
                 float4 sreg[16];
-                if (!(p.exp_flags & 4)) load_s_row(p, t, cell, cur.pr, sreg);
+                if (!ABL(4)) load_s_row(p, t, cell, cur.pr, sreg);
                 else {
 #pragma unroll
                     for (int i = 0; i < 16; ++i) sreg[i] = make_float4(0.f, 0.f, 0.f, 0.f);
                 }
                 wait_mma();
-                if (!(p.exp_flags & 16)) epi_u(t_y, t_h, t_lane, sreg);
+                if (!ABL(16)) epi_u(t_y, t_h, t_lane, sreg);
                 request();                                                     // MMA 3
                 if (more) ctx_build(t < 2 ? cur : nxt, t < 2 ? t + 1 : 0, WA, WB);      // MMA 3 is in flight
                 wait_mma();
-                if (!(p.exp_flags & 32)) osum += epi_o(t_y, t_lane, cst);
+                if (!ABL(32)) osum += epi_o(t_y, t_lane, cst);
                 if (more) request();                                           // MMA 1 of the next token (orders the TMEM reads above)
                 else tc_fence_before();
             }

@@ -425,3 +425,48 @@ def write_temp_dir(ds: "SynthDataset", temp_dir: str, chrom_names=None, test_fra
     np.save(os.path.join(temp_dir, "chrom_start_end.npy"), np.array(cse, dtype=np.int64))
     np.save(os.path.join(temp_dir, "sparse_nondiag_adj_nbr_1.npy"), csr.to_object_array(), allow_pickle=True)
     return chrom_names
+
+
+def make_dataset_cells(name: str, cells, *, block: int = 64, threads: int = 4, seed: Optional[int] = None) -> "SynthDataset":
+    """ONE dataset of the named configuration, materialised for a SUBSET of its cells (strong scaling: a rank holds its own cell
+    range plus the kNN halo).  The dataset is defined block-wise -- cells [b * block, (b + 1) * block) come from
+    generate_contacts(seed = base + 7919 * (b + 1)) -- so every rank that needs a cell generates the same contacts for it without
+    generating the other blocks.  Returns a SynthDataset over the selected cells in ascending order of their global ids (local id =
+    position in `cells`), `ds.global_cells` holds the global ids, `ds.n_cells_global` the size of the full dataset."""
+    from concurrent.futures import ThreadPoolExecutor
+    cfg = dict(CONFIGS[name])
+    bins = chrom_bins(cfg["genome"], cfg["res"], cfg["chroms"])
+    base = 1000 * int(name[1:]) if seed is None else seed
+    cells = np.unique(np.asarray(cells, dtype=np.int64))
+    n_glob = cfg["n_cells"]
+    assert len(cells) and cells[0] >= 0 and cells[-1] < n_glob
+    blocks = np.unique(np.concatenate([[0], cells // block]))     # block 0 always: the bin features are defined on it
+
+    def one(b):
+        nb = int(min(block, n_glob - b * block))
+        return int(b), generate_contacts(nb, bins, cfg["density"], base + 7919 * (int(b) + 1))
+    with ThreadPoolExecutor(max_workers=max(1, threads)) as ex:
+        parts = dict(ex.map(one, blocks))
+    n_bins = int(sum(bins))
+    rp_parts, col_parts, val_parts, off = [np.zeros(1, dtype=np.int64)], [], [], 0
+    for c in cells:
+        blk = parts[int(c // block)]
+        q = int(c % block)
+        lo, hi = int(blk.row_ptr[q * n_bins]), int(blk.row_ptr[(q + 1) * n_bins])
+        rp_parts.append(blk.row_ptr[q * n_bins + 1:(q + 1) * n_bins + 1] - lo + off)
+        col_parts.append(blk.col[lo:hi]); val_parts.append(blk.val[lo:hi])
+        off += hi - lo
+    any_blk = next(iter(parts.values()))
+    csr = PackedCSR(len(cells), any_blk.bins, any_blk.bin_off, np.concatenate(rp_parts), np.concatenate(col_parts), np.concatenate(val_parts))
+    ds = SynthDataset(name=name, n_cells=len(cells), bins=list(bins), d=cfg["d"], k=cfg["k"], min_bin=cfg["min_bin"],
+                      max_bin=cfg["max_bin"], csr=csr)
+    rng = np.random.Generator(np.random.PCG64(base + 7919))
+    ds.bin_feats = pseudo_bulk_features(parts[0])                 # the same on every rank, whatever cells it holds
+    F = int(min(max(4, 0.5 * n_glob), 2400))
+    ds.cell_embed_feats = rng.standard_normal((n_glob, F)).astype(np.float32)[cells]
+    ds.attribute_dict = make_attributes(ds.n_cells, ds.bins)
+    reads = np.add.reduceat(csr.val.astype(np.float64), np.minimum(csr.row_ptr[:-1:csr.n_bins], len(csr.val) - 1))
+    ds.cell_feats = np.concatenate([np.zeros((1, 1)), np.log1p(reads.reshape(-1, 1))], axis=0).astype(np.float32)
+    ds.global_cells = cells
+    ds.n_cells_global = n_glob
+    return ds
