@@ -584,6 +584,7 @@ extern "C" int hsg_prepare(hsg_ctx* c, int precision, int local_transfer_range, 
             // generation 4 (default; HSG_K2_GEN=2 / 3 select the earlier kernels): P tables + tile table of the pair list
             const char* gen = getenv("HSG_K2_GEN");
             c->k2v4 = !(gen && (gen[0] == '2' || gen[0] == '3')) && c->P > 0;
+            c->k2gen = (gen && gen[0] == '5') ? 5 : 4;            // HSG_K2_GEN=5: generation 4's MMA chain with two threads per row (measured 28 % slower)
             if (c->k2v4) {
                 float* dF = nullptr; __half *bp = nullptr, *cp = nullptr;
                 if (dev_alloc(&dF, fcomb.size()) || dev_alloc(&bp, (size_t)c->n_bins * 128 * 8) || dev_alloc(&cp, (size_t)c->n_cells * 128 * 8)) return 1;
@@ -638,7 +639,7 @@ static int run_batch(hsg_ctx* c, int cell0, int nb, float* out, cudaStream_t s, 
     if (c->use_umma && c->use_proj_umma) { if (launch_token_project_umma(c, cell0, nb, s)) return 1; }
     else if (launch_token_project(c, cell0, nb, c->use_umma ? (c->umma_hi ? 2 : 1) : 0, s)) return 1;
     if (prof) HSG_CUDA(cudaEventRecord(c->ev[2], s));
-    if (c->k2v4) { if (launch_score_pairs_umma4(c, cell0, nb, out, out16, s)) return 1; }
+    if (c->k2v4) { if ((c->k2gen == 4 ? launch_score_pairs_umma4 : launch_score_pairs_umma5)(c, cell0, nb, out, out16, s)) return 1; }
     else if (c->k2v2) { if (launch_score_pairs_umma2(c, cell0, nb, out, out16, s)) return 1; }
     else if (c->use_umma) { if (launch_score_pairs_umma(c, cell0, nb, out, s)) return 1; }
     else if (launch_score_pairs_f32(c, cell0, nb, out, s)) return 1;

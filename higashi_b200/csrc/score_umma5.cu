@@ -1,4 +1,9 @@
 // score_umma5.cu -- K2, fast tensor-core variant, FIFTH generation: generation 4's MMA chain with TWO threads per triplet row.
+// EXPERIMENT, NOT THE DEFAULT (HSG_K2_GEN=5): parity-green, but K2 takes 62.3 ms per 225 M triplets against generation 4's 48.7 --
+// the two exchanges per token couple eight warps, every warp repeats the tile bookkeeping, the mbarrier polls and the waits, and at
+// 80 registers the epilogues spill.  What the hypothesis below missed: the chain of a row tile is a SUM of unit round trips (tensor
+// pipe ~28 %, tensor-memory reads at 64 B/clk per quadrant ~23 %, XU 37 %, L1 data pipe ~50 %, issue 42 %) that more threads per row
+// do not shorten; only more row tiles in flight would overlap them, and tensor memory (512 columns) holds three.
 //
 // Ablations on generation 4 (score_umma4.cu, -DHSG_K2_ABLATE=1; 600 cells of C2): one warpgroup alone 74.8 ms, two 46.0, three
 // 33.2 -- throughput follows the number of independent row chains almost linearly, and no pipe is the bound (L1 data pipe, XU,
