@@ -70,6 +70,7 @@ def parse():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-train", action="store_true", help="skip the secondary training line of the default invocation")
+    ap.add_argument("--d-model", type=int, default=0, help="override d_model of the workload (64 or 128)")
     ap.add_argument("--no-c3", action="store_true", help="skip the secondary strong-scaling C3 job of the default invocation")
     return ap.parse_args()
 
@@ -151,6 +152,8 @@ def build_dataset(args, rank):
     if args.n_cells:
         kw["n_cells"] = args.n_cells
     ds = S.make_dataset(args.workload, shard=rank, **kw)
+    if getattr(args, "d_model", 0):
+        ds.d = int(args.d_model)
     sd, feats = S.random_state_dict(ds, ds.d, seed=0)
     return ds, sd, feats
 
@@ -748,7 +751,10 @@ def main():
     except Exception:
         pass
     peak_tf = float(peaks.get("bf16_tflops_sustained", 1400.0))
-    achieved_tf = FLOP_PER_TRIPLET_TENSOR * cps * P / (k2_ms_per_step * 1e-3) / 1e12 * (ds.d / 64.0) ** 2 if k2_ms_per_step > 0 else 0.0
+    # fc1 (128 -> d), W0, W1 (d -> d), C0 (d -> d / 2), three tokens per triplet: 110 592 FLOP at d = 64, 344 064 at d = 128
+    flop_per_triplet = 3.0 * (256.0 * ds.d + 5.0 * ds.d * ds.d)
+    assert ds.d != 64 or flop_per_triplet == FLOP_PER_TRIPLET_TENSOR
+    achieved_tf = flop_per_triplet * cps * P / (k2_ms_per_step * 1e-3) / 1e12 if k2_ms_per_step > 0 else 0.0
     traffic = None
     try:        # DRAM bytes per launch of the dominant kernel from the committed ncu capture, scaled to this run's launch size
         tj = json.load(open(os.path.join(ROOT, "profiles", "r01_k2_traffic.json")))
@@ -825,13 +831,13 @@ def main():
     torch.cuda.empty_cache()
     # ---- secondary metric of BASELINE.json: train hyperedges/s (same process group, same GPUs)
     train_line = None
-    if not args.no_train and not args.n_cells:
+    if not args.no_train and not args.n_cells and not args.d_model:
         try:
             train_line = train_bench(args, rank, world, local, steps=20)
         except Exception as e:                                       # never lose the headline line over the secondary figure
             train_line = {"error": repr(e)}
     c3_line = None
-    if not args.no_c3 and not args.n_cells and args.workload == "C2":
+    if not args.no_c3 and not args.n_cells and args.workload == "C2" and not args.d_model:
         try:
             c3_line = c3_strong(args, rank, world, local)
         except Exception as e:

@@ -516,13 +516,16 @@ extern "C" int hsg_prepare(hsg_ctx* c, int precision, int local_transfer_range, 
     // pair bias
     if (dev_alloc(&c->pair_bias, (size_t)std::max<int64_t>(c->P, 1))) return 1;
     if (launch_pair_bias(c, c->stream)) return 1;
-    // Tensor-core mode exists for d_model = 64; d_model = 128 keeps the (more precise) fp32 kernels for now.
-    c->use_umma = (precision != HSG_PREC_FP32 && d == 64);
+    // Tensor-core mode: d_model = 64 (fast and high-accuracy variants) and d_model = 128 (fast variant only: a model that needs the
+    // high-accuracy variant -- softplus / raw head, layer_norm1 gain too close to zero, fp16 range -- runs the fp32 kernels there).
+    c->use_umma = (precision != HSG_PREC_FP32 && (d == 64 || d == 128));
     c->use_proj_umma = false;
+    c->k2d128 = false;
     // softplus / raw heads pass the logit error through with slope ~1: they get the high-accuracy variant
     // (so does a layer_norm1 gain too close to zero for the fast variant's gain folding)
     c->umma_hi = c->use_umma && (precision == HSG_PREC_TC16_HI || activation != HSG_ACT_SIGMOID ||
-                                 !umma_gain_foldable(h->v[HSG_W_LN1_G].data()));
+                                 !(d == 64 ? umma_gain_foldable(h->v[HSG_W_LN1_G].data()) : umma128_gain_foldable(h->v[HSG_W_LN1_G].data())));
+    if (d == 128 && c->umma_hi) { c->use_umma = false; c->umma_hi = false; }
     if (c->use_umma) {
         // fp16 RANGE guard: the 16-bit operands (Q / K / V rows, ctx, h, the squared difference u) top out at 65504.  Bound every one
         // of them from the weights and from the S tables of THIS model; a model outside the fast variant's range takes the
@@ -537,14 +540,36 @@ extern "C" int hsg_prepare(hsg_ctx* c, int precision, int local_transfer_range, 
                                          h->v[HSG_W_PFF_B0].data(), h->v[HSG_W_PFF_LN_G].data(), h->v[HSG_W_PFF_LN_B].data(),
                                          h->v[HSG_W_LN1_G].data(), h->v[HSG_W_LN1_B].data(), hS.data(), (long long)(c->n_bins + c->n_cells), d);
         if (lvl >= 1) c->umma_hi = true;
-        if (lvl >= 2) { c->use_umma = false; c->umma_hi = false; }
+        if (lvl >= 2 || (lvl >= 1 && d == 128)) { c->use_umma = false; c->umma_hi = false; }
     }
     {
         const char* v1 = getenv("HSG_K2V1");
-        c->k2v2 = c->use_umma && !c->umma_hi && !(v1 && v1[0] == '1');
+        c->k2v2 = c->use_umma && !c->umma_hi && (d == 128 || !(v1 && v1[0] == '1'));
+        c->k2d128 = c->use_umma && d == 128;
     }
     size_t per_cell;
-    if (c->use_umma) {
+    if (c->k2d128) {
+        std::vector<unsigned char> wimg(umma128_wimg_bytes());
+        std::vector<float> cst(umma128_cst_count(), 0.f);
+        umma128_build_weights(h->v[HSG_W_FC1].data(), h->v[HSG_W_PFF_W0].data(), h->v[HSG_W_PFF_B0].data(),
+                              h->v[HSG_W_PFF_LN_G].data(), h->v[HSG_W_PFF_LN_B].data(), h->v[HSG_W_PFF_W1].data(),
+                              h->v[HSG_W_PFF_B1].data(), h->v[HSG_W_LN1_G].data(), h->v[HSG_W_CLS_W0].data(),
+                              h->v[HSG_W_CLS_B0].data(), h->v[HSG_W_CLS_W1].data(), h->v[HSG_W_CLS_B1].data(), wimg.data(), cst.data());
+        if (dev_alloc(&c->wimg, wimg.size())) return 1;
+        HSG_CUDA(cudaMemcpy(c->wimg, wimg.data(), wimg.size(), cudaMemcpyHostToDevice));
+        HSG_CHECK(cst.size() <= 512, "constant block too large");
+        memcpy(c->h_cst, cst.data(), cst.size() * sizeof(float));
+        __half *bv = nullptr, *cv = nullptr;
+        const size_t bins_pad = (size_t)((c->n_bins + HSG_GRP - 1) / HSG_GRP) * HSG_GRP;
+        if (dev_alloc(&bv, bins_pad * HSG_HD) || dev_alloc(&cv, (size_t)c->n_cells * HSG_HD) ||
+            dev_alloc(&c->binSb, bins_pad * d) || dev_alloc(&c->cellSb, (size_t)c->n_cells * d)) return 1;
+        HSG_CUDA(cudaMemsetAsync(bv, 0, bins_pad * HSG_HD * sizeof(__half), c->stream));
+        HSG_CUDA(cudaMemsetAsync(c->binSb, 0, bins_pad * d * sizeof(float), c->stream));
+        c->binV16 = bv; c->cellV16 = cv;
+        if (launch_convert_static128(c, c->binV, c->binS, c->n_bins, 1, c->binV16, c->binSb, c->stream)) return 1;
+        if (launch_convert_static128(c, c->cellV, c->cellS, c->n_cells, 0, c->cellV16, c->cellSb, c->stream)) return 1;
+        per_cell = (size_t)c->n_bins * (2 * HSG_HD * sizeof(__half) + 16 * sizeof(float) + d * sizeof(float));
+    } else if (c->use_umma) {
         std::vector<unsigned char> wimg(umma_wimg_bytes());
         std::vector<float> cst(umma_cst_count(), 0.f);
         std::vector<float> fcomb((size_t)2 * 64 * HSG_HD);
@@ -639,7 +664,8 @@ static int run_batch(hsg_ctx* c, int cell0, int nb, float* out, cudaStream_t s, 
     if (c->use_umma && c->use_proj_umma) { if (launch_token_project_umma(c, cell0, nb, s)) return 1; }
     else if (launch_token_project(c, cell0, nb, c->use_umma ? (c->umma_hi ? 2 : 1) : 0, s)) return 1;
     if (prof) HSG_CUDA(cudaEventRecord(c->ev[2], s));
-    if (c->k2v4) { if ((c->k2gen == 4 ? launch_score_pairs_umma4 : launch_score_pairs_umma5)(c, cell0, nb, out, out16, s)) return 1; }
+    if (c->k2d128) { if (launch_score_pairs_umma128(c, cell0, nb, out, out16, s)) return 1; }
+    else if (c->k2v4) { if ((c->k2gen == 4 ? launch_score_pairs_umma4 : launch_score_pairs_umma5)(c, cell0, nb, out, out16, s)) return 1; }
     else if (c->k2v2) { if (launch_score_pairs_umma2(c, cell0, nb, out, out16, s)) return 1; }
     else if (c->use_umma) { if (launch_score_pairs_umma(c, cell0, nb, out, s)) return 1; }
     else if (launch_score_pairs_f32(c, cell0, nb, out, s)) return 1;

