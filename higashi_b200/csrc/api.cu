@@ -60,6 +60,9 @@ extern "C" int hsg_create(hsg_ctx** out, int device_ordinal) {
     if (const char* e = getenv("HSG_GATHER_SPARSE")) c->gather_sparse = (e[0] != '0');
     if (const char* e = getenv("HSG_GATHER_CHROM")) c->gather_chrom = (e[0] != '0');
     if (const char* e = getenv("HSG_GATHER_HASH")) c->gather_hash = (e[0] != '0');
+    if (const char* e = getenv("HSG_GATHER_STREAM")) c->gather_stream = (e[0] != '0');
+    if (const char* e = getenv("HSG_GATHER_STREAM_CAP")) c->gather_stream_cap = atoi(e);
+    if (const char* e = getenv("HSG_GATHER_STREAM_LCAP")) c->gather_stream_lcap = atoi(e);
     HSG_CUDA(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
     HSG_CUDA(cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking));
     for (int i = 0; i < 8; ++i) HSG_CUDA(cudaEventCreate(&c->ev[i]));
@@ -234,11 +237,11 @@ extern "C" int hsg_set_contacts(hsg_ctx* c, const int64_t* row_ptr, const int32_
     // a re-upload of a same-sized (or smaller) matrix reuses the device buffers: no cudaFree / cudaMalloc round trip
     if (c->col != nullptr) HSG_CUDA(cudaDeviceSynchronize());      // work queued on any stream may still read the old contents
     if (n_rows + 1 > c->cap_rows) {
-        if (dev_alloc(&c->row_ptr, (size_t)n_rows + 1)) return 1;
+        if (dev_alloc(&c->row_ptr, (size_t)n_rows + 1 + HSG_CSR_PAD)) return 1;
         c->cap_rows = n_rows + 1;
     }
     if (nnz > c->cap_nnz || c->col == nullptr) {
-        if (dev_alloc(&c->col, (size_t)nnz) || dev_alloc(&c->val, (size_t)nnz)) return 1;
+        if (dev_alloc(&c->col, (size_t)nnz + HSG_CSR_PAD) || dev_alloc(&c->val, (size_t)nnz + HSG_CSR_PAD)) return 1;
         c->cap_nnz = nnz;
     }
     // three back-to-back DMA transfers on the context stream (truly asynchronous from pinned memory), one wait at the end:
@@ -268,11 +271,11 @@ extern "C" int hsg_stage_contacts(hsg_ctx* c, const int64_t* row_ptr, const int3
         HSG_CUDA(cudaEventCreateWithFlags(&c->staged_ev, cudaEventDisableTiming));
     }
     if (n_rows + 1 > c->cap_rows2) {
-        if (dev_alloc(&c->row_ptr2, (size_t)n_rows + 1)) return 1;
+        if (dev_alloc(&c->row_ptr2, (size_t)n_rows + 1 + HSG_CSR_PAD)) return 1;
         c->cap_rows2 = n_rows + 1;
     }
     if (nnz > c->cap_nnz2 || c->col2 == nullptr) {
-        if (dev_alloc(&c->col2, (size_t)nnz) || dev_alloc(&c->val2, (size_t)nnz)) return 1;
+        if (dev_alloc(&c->col2, (size_t)nnz + HSG_CSR_PAD) || dev_alloc(&c->val2, (size_t)nnz + HSG_CSR_PAD)) return 1;
         c->cap_nnz2 = nnz;
     }
     HSG_CUDA(cudaMemcpyAsync(c->row_ptr2, row_ptr, (size_t)(n_rows + 1) * sizeof(int64_t), cudaMemcpyHostToDevice, c->h2d_stream));

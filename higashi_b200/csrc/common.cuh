@@ -28,6 +28,8 @@
 #define HSG_GRP 32
 #define HSG_L2E_QUARTER 0.36067376022224085f      // log2(e) / 4: attention logits of the tensor-core scorer are kept in log2 units
 #define HSG_PDF0 0.3989422804014327f   // scipy.stats.norm.pdf(0)   (Impute.py:19)
+// the streaming gather copies 16-byte aligned spans of row_ptr / col / val: the device arrays carry this many spare elements
+#define HSG_CSR_PAD 4
 
 void hsg_set_error(const std::string& msg);
 
@@ -114,6 +116,8 @@ struct hsg_ctx {
     bool gather_sparse = true;               // sparse-row K1a fast path enabled (HSG_GATHER_SPARSE=0 disables it)
     bool gather_hash = true;                 // hash-merge K1a for long chromosomes enabled (HSG_GATHER_HASH=0 disables it)
     bool gather_chrom = true;                // chromosome-block K1a for dense rows enabled (HSG_GATHER_CHROM=0 disables it)
+    bool gather_stream = true;               // streaming K1a (gather_stream.cu) enabled (HSG_GATHER_STREAM=0 disables it)
+    int gather_stream_cap = 0, gather_stream_lcap = 0;   // test hooks: force a small stage / candidate-list capacity (HSG_GATHER_STREAM_CAP / _LCAP)
     float* QK = nullptr;                     // fp32 [qk_cells, n_bins, 2, 128] (fp32 mode: batch; tensor-core mode: 1 cell for hsg_fix_cell)
     // tensor-core mode (HSG_PREC_TC16): 16-bit token tables + pre-swizzled weight images
     void* QK16 = nullptr;                    // half [batch, n_bins, 256]
@@ -148,6 +152,7 @@ int launch_embed_table(hsg_ctx* c, const float* x, int64_t rows, int in_dim, con
 int launch_static_tokens(hsg_ctx* c, const float* E, int64_t rows, float* Q, float* K, float* V, float* S, cudaStream_t s);
 int launch_pair_bias(hsg_ctx* c, cudaStream_t s);
 int launch_gather(hsg_ctx* c, const int* cells_dev_unused, int cell_start, int n_cells_batch, cudaStream_t s);
+int try_launch_gather_stream(hsg_ctx* c, int cell_start, int n_cells_batch, int max_nc, int* ovf_count, cudaStream_t s, bool* done);
 int launch_token_project(hsg_ctx* c, int cell_start, int n_cells_batch, int mode, cudaStream_t s);   // mode 0: fp32 QK, 1: fp16 QK + XS, 2: fp32 QK + XS
 int launch_score_pairs_umma(hsg_ctx* c, int cell_start, int n_cells_batch, float* out, cudaStream_t s);
 int launch_convert_static(hsg_ctx* c, const float* V, const float* S, long long rows, void* V16, float* Sb, float* V32p, cudaStream_t s);

@@ -683,7 +683,7 @@ int launch_gather(hsg_ctx* c, const int*, int cell_start, int n_batch, cudaStrea
     // long rows (> 16 merged candidates): the hash-merge kernel wherever the fast path applies (measured: C5 7.28 -> 2.54 ms against
     // the 96-candidate register kernel, C3 3.53 -> 3.38 ms against the chromosome-block kernel); with it switched off the old rule
     // stands (register kernel only for chromosomes too long for a dense per-warp accumulator)
-    const bool to_sparse = sparse_ok && (avg_cand <= 16.0 || max_nc > 1536 || c->gather_hash);
+    const bool to_sparse = sparse_ok && (avg_cand <= 16.0 || max_nc > 1536 || c->gather_hash || c->gather_stream);
     if (!to_sparse && c->gather_chrom) {        // dense rows, short chromosomes: one chromosome per block, E_c in shared memory
         bool done = false;
         if (try_launch_gather_chrom(c, cell_start, n_batch, max_nc, s, &done)) return 1;
@@ -703,10 +703,15 @@ int launch_gather(hsg_ctx* c, const int*, int cell_start, int n_batch, cudaStrea
         // register capacity from the average number of merged candidates per token (k+1 rows of nnz / n_rows entries each)
         const double avg = avg_cand;
         const unsigned g = (unsigned)(gb < gcap ? gb : gcap);
+        // the streaming kernel (gather_stream.cu: bulk-copied CSR segments, E table of the chromosome in shared memory) whenever
+        // its stages fit next to the chromosome's E table; it leaves what it cannot hold on the same overflow list
+        bool streamed = false;
+        if (c->gather_stream && try_launch_gather_stream(c, cell_start, n_batch, max_nc, cnt, s, &streamed)) return 1;
 #define GS_LAUNCH(SL) neigh_gather_sparse_kernel<SL><<<g, GS_WPB * 32, 0, s>>>(                                                    \
             c->row_ptr, c->col, c->val, c->nbr, c->nbr_w, c->k1, c->weighted ? 1 : 0, c->E_bin, c->d_bin_chrom, c->d_bin_off,      \
             c->n_bins, cell_start, (int)n_tok, c->neigh, c->ovf_list, cnt)
-        if (avg > 16.0 && c->gather_hash && max_nc < 65536) {
+        if (streamed) {
+        } else if (avg > 16.0 && c->gather_hash && max_nc < 65536) {
             // long chromosome, tens of candidates per token: shared-memory hash merge instead of the SLOTS^2 register dedup
             GatherHashParams hp;
             hp.row_ptr = c->row_ptr; hp.col = c->col; hp.val = c->val; hp.nbr = c->nbr; hp.nbr_w = c->nbr_w; hp.E_bin = c->E_bin;
@@ -719,7 +724,7 @@ int launch_gather(hsg_ctx* c, const int*, int cell_start, int n_batch, cudaStrea
         else if (avg <= 36.0) GS_LAUNCH(8);
         else GS_LAUNCH(12);
 #undef GS_LAUNCH
-        c->launches++;
+        if (!streamed) c->launches++;
         HSG_CUDA(cudaGetLastError());
         list = c->ovf_list; count = cnt;
         grid = (unsigned)std::min<int64_t>(grid, (int64_t)c->n_sm * 2);

@@ -86,12 +86,35 @@ def install():
         sys.path.insert(0, p)
 
 
+_REF_CACHE = None
+
+
 def import_reference():
-    """Returns (Modules, Impute, Higashi_wrapper) of the reference."""
+    """Returns (Modules, Impute, Higashi_wrapper) of the reference.
+
+    `higashi_b200.install_aliases()` may have registered the host mirror under the reference's module names
+    (`Higashi_backend.Modules`, ...) in this process; those entries are set aside while the reference's own files are imported
+    and put back afterwards, so both can live in one interpreter (the reference modules stay reachable through the returned
+    objects only)."""
+    global _REF_CACHE
+    if _REF_CACHE is not None:
+        return _REF_CACHE
     install()
     import warnings
     warnings.filterwarnings("ignore")
-    import Higashi_backend.Modules as RM
-    import Impute as RI
-    import Higashi_wrapper as RW
-    return RM, RI, RW
+    names = [n for n in list(sys.modules) if n == "Higashi_backend" or n.startswith("Higashi_backend.") or n in ("Impute", "Higashi_wrapper")]
+    saved = {n: sys.modules.pop(n) for n in names}
+    try:
+        import Higashi_backend.Modules as RM
+        import Impute as RI
+        import Higashi_wrapper as RW
+    finally:
+        for n in [n for n in list(sys.modules) if n == "Higashi_backend" or n.startswith("Higashi_backend.") or n in ("Impute", "Higashi_wrapper")]:
+            if n in saved:
+                sys.modules[n] = saved[n]
+            elif saved:
+                del sys.modules[n]
+    root = os.path.realpath(REFERENCE_ROOT)
+    assert os.path.realpath(RM.__file__).startswith(root), "reference import resolved to %s" % RM.__file__
+    _REF_CACHE = (RM, RI, RW)
+    return _REF_CACHE

@@ -174,9 +174,11 @@ def test_small_genomes_tensor_core(bins):
 
 
 @pytest.mark.parametrize("density,k", [(0.3, 4), (0.3, 0), (0.08, 4), (0.02, 9), (0.02, 7), (0.0, 4)])
-def test_gather_paths(density, k):
-    """K1a has a sparse-row fast path (<= 32 merged candidates per token, <= 8 neighbour rows) and a generic kernel that
-    finishes the overflow list: dense rows (every token overflows), mixed, k+1 > 8 (generic only), k+1 = 8, empty contacts."""
+def test_gather_paths(density, k, monkeypatch):
+    """Without the streaming kernel, K1a has a sparse-row fast path (<= 32 merged candidates per token, <= 8 neighbour rows) and
+    a generic kernel that finishes the overflow list: dense rows (every token overflows), mixed, k+1 > 8 (generic only),
+    k+1 = 8, empty contacts."""
+    monkeypatch.setenv("HSG_GATHER_STREAM", "0")
     _synthetic_case(k, 0, 64, "fp32", [120, 40], [0, 5, 39], density=density)
 
 
@@ -186,6 +188,7 @@ def test_gather_without_hash_kernel(density, k, bins, band, n_cells, monkeypatch
     """Rows with more than 16 merged candidates normally take the hash-merge kernel; with it switched off dense rows on short
     chromosomes take the chromosome-block kernel and long chromosomes the 64 / 96-candidate register kernels."""
     monkeypatch.setenv("HSG_GATHER_HASH", "0")
+    monkeypatch.setenv("HSG_GATHER_STREAM", "0")
     _synthetic_case(k, 0, 64, "fp32", bins, [0, 5, 23], density=density, band=band, n_cells=n_cells)
 
 
@@ -195,13 +198,36 @@ def test_gather_generic_kernel(density, k, monkeypatch):
     with it switched off the generic warp-per-token kernel must give the same answer."""
     monkeypatch.setenv("HSG_GATHER_CHROM", "0")
     monkeypatch.setenv("HSG_GATHER_HASH", "0")
+    monkeypatch.setenv("HSG_GATHER_STREAM", "0")
     _synthetic_case(k, 0, 64, "fp32", [120, 40], [0, 5, 39], density=density)
 
 
+@pytest.mark.parametrize("density,k,bins", [(0.3, 4, [120, 40]), (0.3, 0, [120, 40]), (0.08, 4, [130, 70, 5]), (0.02, 7, [120, 40]),
+                                            (0.02, 4, [250, 97]), (0.0, 4, [120, 40]), (0.004, 4, [700])])
+def test_gather_stream_kernel(density, k, bins):
+    """The default K1a (gather_stream.cu): CSR segments of a (cell, bin tile) item bulk-copied into a 3-stage shared-memory ring,
+    sparse tokens merged with match.any, longer ones through the dense accumulator, E table of the chromosome in shared memory.
+    Dense rows, no neighbours, tiles that straddle chromosome ends and a 5-bin chromosome, k + 1 = 8 rows, empty contacts,
+    a chromosome longer than one E tile of the chromosome-block kernel."""
+    _synthetic_case(k, 0, 64, "fp32", bins, [0, 5, 39], density=density, **({"band": 40} if bins == [700] else {}))
+
+
+@pytest.mark.parametrize("density,cap,lcap", [(0.08, 64, 0), (0.3, 0, 16), (0.05, 256, 24)])
+def test_gather_stream_overflow_paths(density, cap, lcap, monkeypatch):
+    """Items whose segments exceed the stage capacity and tokens with more distinct columns than the candidate list holds leave
+    the streaming kernel through the overflow list (forced here with tiny capacities); the generic kernel finishes them."""
+    if cap:
+        monkeypatch.setenv("HSG_GATHER_STREAM_CAP", str(cap))
+    if lcap:
+        monkeypatch.setenv("HSG_GATHER_STREAM_LCAP", str(lcap))
+    _synthetic_case(4, 0, 64, "fp32", [120, 40], [0, 5, 39], density=density)
+
+
 @pytest.mark.parametrize("density", [0.004, 0.009])
-def test_gather_long_chromosome(density):
+def test_gather_long_chromosome(density, monkeypatch):
     """Chromosomes longer than 1536 bins with medium-dense rows take the 64- / 96-candidate register kernels (plus the overflow
     list); banded pairs keep the oracle fast."""
+    monkeypatch.setenv("HSG_GATHER_STREAM", "0")
     _synthetic_case(4, 0, 64, "fp32", [1600], [0, 7, 23], density=density, band=40, n_cells=24)
 
 
