@@ -274,7 +274,8 @@ __global__ void __launch_bounds__(1056, 1) neigh_gather_stream_kernel(const __gr
                 }
                 const float tv = own ? log1pf(__fmul_rn(sum, HSG_PDF0)) : 0.f;      // x pdf(0), log1p (Impute.py:19, 91)
                 const unsigned ob = __ballot_sync(0xffffffffu, own);
-                if (own) { const int pos = __popc(ob & ((1u << lane) - 1u)); lc[pos] = ccol; lv[pos] = tv; }
+                const int pos = __popc(ob & ((1u << lane) - 1u));
+                if (own && pos < p.LCAP) { lc[pos] = ccol; lv[pos] = tv; }
                 acount = __popc(ob);
                 part = fabsf(tv);
             } else {
@@ -305,11 +306,11 @@ __global__ void __launch_bounds__(1056, 1) neigh_gather_stream_kernel(const __gr
                         part += fabsf(tv);
                     }
                 }
-                if (acount > p.LCAP) {                     // more distinct columns than the list holds: the generic kernel finishes it
-                    if (lane == 0) p.tok_list[atomicAdd(p.tok_count, 1)] = tok;
-                    __syncwarp();
-                    continue;
-                }
+            }
+            if (acount > p.LCAP) {                         // more distinct columns than the list holds: the generic kernel finishes it
+                if (lane == 0) p.tok_list[atomicAdd(p.tok_count, 1)] = tok;
+                __syncwarp();
+                continue;
             }
             const float total = warp_sum(part);
             __syncwarp();

@@ -1,0 +1,22 @@
+#!/bin/bash
+# K1a A/B on the GPU box: parity tests of the gather kernels, then the per-stage times of C2 and C3 with and without the
+# streaming kernel.  Output under gpurun_out/.
+set -x
+mkdir -p gpurun_out
+timeout 600 python -m pytest tests/test_gpu_parity.py -x -q -k "gather or impute_golden or synthetic_vs_oracle or small_genomes" > gpurun_out/gather_tests.log 2>&1
+echo "pytest rc=$?" >> gpurun_out/gather_tests.log
+tail -5 gpurun_out/gather_tests.log
+B="--no-cpu-baseline --no-e2e --no-train --no-c3"
+timeout 300 python bench.py --steps 6 --warmup 3 $B > gpurun_out/ab_c2_stream.json 2> gpurun_out/ab_c2_stream.err
+HSG_GATHER_STREAM=0 timeout 300 python bench.py --steps 6 --warmup 3 $B > gpurun_out/ab_c2_old.json 2> gpurun_out/ab_c2_old.err
+timeout 400 python bench.py --workload C3 --cells-per-step 250 --steps 4 --warmup 3 $B > gpurun_out/ab_c3_stream.json 2> gpurun_out/ab_c3_stream.err
+HSG_GATHER_STREAM=0 timeout 400 python bench.py --workload C3 --cells-per-step 250 --steps 4 --warmup 3 $B > gpurun_out/ab_c3_old.json 2> gpurun_out/ab_c3_old.err
+python - <<'P'
+import json, glob
+for f in sorted(glob.glob('gpurun_out/ab_*.json')):
+    try:
+        d = json.loads(open(f).read().strip().splitlines()[-1])
+        print(f, d['value'], d['roofline']['stage_ms_per_step'], d['roofline'].get('gather_K1a', {}).get('frac'))
+    except Exception as e:
+        print(f, 'ERR', e)
+P
