@@ -100,7 +100,7 @@ __device__ __forceinline__ GstItem gst_decode(const GatherStreamParams& p, int i
     return it;
 }
 
-__global__ void __launch_bounds__(1056, 1) neigh_gather_stream_kernel(const __grid_constant__ GatherStreamParams p) {
+__global__ void __launch_bounds__(1024, 1) neigh_gather_stream_kernel(const __grid_constant__ GatherStreamParams p) {
     extern __shared__ __align__(128) unsigned char smem[];
     const GstLayout L = gst_layout(p.max_nc, p.k1, p.TB, p.CAP, p.LCAP, p.n_warps);
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -358,12 +358,16 @@ int try_launch_gather_stream(hsg_ctx* c, int cell_start, int n_batch, int max_nc
     int best_tb = 0;
     // consumer warps: as many as fit (the merge of a token is a chain of dependent shared-memory / shuffle steps: warps, not
     // issue slots, are what a scheduler runs out of); tile: the largest whose stages fit next to the E table
-    for (int nw = 32; nw >= 8 && !best_tb; nw >>= 1) {
+    // (31 + the producer = 1024 threads; fewer than 16 -- long chromosomes with dense rows, whose E table leaves little room
+    // -- and the hash-merge kernel with its 48 warps per SM is faster: measured on C3, 5.4 ms with 8 warps against 3.4 ms)
+    static const int nw_opts[2] = {31, 16};
+    for (int o = 0; o < 2 && !best_tb; ++o) {
+        const int nw = nw_opts[o];
         const int lcap = c->gather_stream_lcap > 0 ? c->gather_stream_lcap : (int)std::min(512.0, std::max(64.0, 32.0 * std::ceil(4.0 * avg_cand / 32.0)));
         for (int tb = 128; tb >= 8; tb -= 4) {
             const int cap = c->gather_stream_cap > 0 ? (c->gather_stream_cap & ~3) : ((int)(1.5 * avg_cand * tb) + 128 + 3) & ~3;
             const GstLayout L = gst_layout(max_nc, c->k1, tb, cap, lcap, nw);
-            if (L.total <= budget && (tb >= 2 * nw || nw == 8)) { best_tb = tb; p.TB = tb; p.CAP = cap; p.LCAP = lcap; p.n_warps = nw; break; }
+            if (L.total <= budget && tb >= (nw > 16 ? 2 * nw : nw)) { best_tb = tb; p.TB = tb; p.CAP = cap; p.LCAP = lcap; p.n_warps = nw; break; }
         }
     }
     if (!best_tb) return 0;

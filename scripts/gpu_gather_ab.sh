@@ -1,6 +1,5 @@
 #!/bin/bash
-# K1a A/B on the GPU box: parity tests of the gather kernels, then the per-stage times of C2 and C3 with and without the
-# streaming kernel.  Output under gpurun_out/.
+# K1a A/B on the GPU box: parity tests of the gather kernels, then the per-stage times of C2 with and without the streaming kernel.
 set -x
 mkdir -p gpurun_out
 timeout 600 python -m pytest tests/test_gpu_parity.py -x -q -k "gather or impute_golden or synthetic_vs_oracle or small_genomes" > gpurun_out/gather_tests.log 2>&1
@@ -8,9 +7,7 @@ echo "pytest rc=$?" >> gpurun_out/gather_tests.log
 tail -5 gpurun_out/gather_tests.log
 B="--no-cpu-baseline --no-e2e --no-train --no-c3"
 timeout 300 python bench.py --steps 6 --warmup 3 $B > gpurun_out/ab_c2_stream.json 2> gpurun_out/ab_c2_stream.err
-HSG_GATHER_STREAM=0 timeout 300 python bench.py --steps 6 --warmup 3 $B > gpurun_out/ab_c2_old.json 2> gpurun_out/ab_c2_old.err
-timeout 400 python bench.py --workload C3 --cells-per-step 250 --steps 4 --warmup 3 $B > gpurun_out/ab_c3_stream.json 2> gpurun_out/ab_c3_stream.err
-HSG_GATHER_STREAM=0 timeout 400 python bench.py --workload C3 --cells-per-step 250 --steps 4 --warmup 3 $B > gpurun_out/ab_c3_old.json 2> gpurun_out/ab_c3_old.err
+timeout 300 python bench.py --workload C1 --cells-per-step 620 --steps 6 --warmup 3 $B > gpurun_out/ab_c1_stream.json 2> gpurun_out/ab_c1_stream.err
 python - <<'P'
 import json, glob
 for f in sorted(glob.glob('gpurun_out/ab_*.json')):
