@@ -227,6 +227,20 @@ extern "C" int hsg_set_table(hsg_ctx* c, int branch, const float* table, int64_t
     return 0;
 }
 
+// mean number of entries per row on every chromosome (rows of long chromosomes are denser: the streaming gather sizes its
+// shared-memory stages for the densest one)
+static void chrom_row_stats(hsg_ctx* c, const int64_t* row_ptr, std::vector<double>& out) {
+    out.assign((size_t)c->n_chrom, 0.0);
+    for (int j = 0; j < c->n_chrom; ++j) {
+        int64_t tot = 0;
+        for (int i = 0; i < c->n_cells; ++i) {
+            const int64_t r0 = (int64_t)i * c->n_bins + c->bin_off[j];
+            tot += row_ptr[r0 + c->bins[j]] - row_ptr[r0];
+        }
+        out[(size_t)j] = (double)tot / std::max<double>(1.0, (double)c->n_cells * c->bins[j]);
+    }
+}
+
 extern "C" int hsg_set_contacts(hsg_ctx* c, const int64_t* row_ptr, const int32_t* col, const float* val, int64_t n_rows,
                                 int64_t nnz) {
     CTX_GUARD(c);
@@ -255,6 +269,7 @@ extern "C" int hsg_set_contacts(hsg_ctx* c, const int64_t* row_ptr, const int32_
     c->n_rows = n_rows; c->nnz = nnz;
     c->h_cell_ptr.resize((size_t)c->n_cells + 1);
     for (int i = 0; i <= c->n_cells; ++i) c->h_cell_ptr[i] = row_ptr[(int64_t)i * c->n_bins];
+    chrom_row_stats(c, row_ptr, c->chrom_row_avg);
     return 0;
 }
 
@@ -286,6 +301,7 @@ extern "C" int hsg_stage_contacts(hsg_ctx* c, const int64_t* row_ptr, const int3
     HSG_CUDA(cudaEventRecord(c->staged_ev, c->h2d_stream));
     c->h_cell_ptr2.resize((size_t)c->n_cells + 1);
     for (int i = 0; i <= c->n_cells; ++i) c->h_cell_ptr2[i] = row_ptr[(int64_t)i * c->n_bins];
+    chrom_row_stats(c, row_ptr, c->chrom_row_avg2);
     c->staged_rows = n_rows; c->staged_nnz = nnz; c->staged = true;
     return 0;
 }
@@ -296,7 +312,7 @@ extern "C" int hsg_commit_contacts(hsg_ctx* c) {
     HSG_CUDA(cudaEventSynchronize(c->staged_ev));       // the staged copy has landed
     // nothing queued may still read the current matrix: wait for the last imputation call's event (not for the whole device)
     if (c->work_pending) { HSG_CUDA(cudaEventSynchronize(c->work_ev)); c->work_pending = false; }
-    c->h_cell_ptr.swap(c->h_cell_ptr2);
+    c->h_cell_ptr.swap(c->h_cell_ptr2); c->chrom_row_avg.swap(c->chrom_row_avg2);
     std::swap(c->row_ptr, c->row_ptr2); std::swap(c->col, c->col2); std::swap(c->val, c->val2);
     std::swap(c->cap_rows, c->cap_rows2); std::swap(c->cap_nnz, c->cap_nnz2);
     c->n_rows = c->staged_rows; c->nnz = c->staged_nnz; c->staged = false;

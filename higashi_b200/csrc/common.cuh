@@ -90,6 +90,7 @@ struct hsg_ctx {
     // hsg_refresh_contacts: per-cell extents of the installed matrix (host), the event its copies signal and the event the last
     // imputation call recorded (copies wait for it: they may overwrite rows that call still reads)
     std::vector<int64_t> h_cell_ptr, h_cell_ptr2;
+    std::vector<double> chrom_row_avg, chrom_row_avg2;   // mean entries per row on each chromosome (sizes the streaming gather's stages)
     cudaEvent_t refresh_ev = nullptr, work_ev = nullptr; bool refresh_pending = false, work_pending = false;
     // neighbours
     int32_t* nbr = nullptr; float* nbr_w = nullptr; int k1 = 1; bool weighted = false;

@@ -8,6 +8,7 @@
 #include <cuda_fp16.h>
 
 #include <algorithm>
+#include <cstdio>
 #include <cstdlib>
 
 #include "common.cuh"
@@ -742,6 +743,13 @@ int launch_gather(hsg_ctx* c, const int*, int cell_start, int n_batch, cudaStrea
     }
     c->launches++;
     HSG_CUDA(cudaGetLastError());
+    static const bool dbg = getenv("HSG_GATHER_DEBUG") != nullptr;
+    if (dbg && count) {                              // diagnostics: how many tokens the fast path left to the generic kernel
+        int h = 0;
+        HSG_CUDA(cudaStreamSynchronize(s));
+        HSG_CUDA(cudaMemcpy(&h, count, sizeof(int), cudaMemcpyDeviceToHost));
+        fprintf(stderr, "[hsg] K1a overflow tokens: %d of %lld\n", h, (long long)n_tok);
+    }
     return 0;
 }
 

@@ -365,7 +365,12 @@ int try_launch_gather_stream(hsg_ctx* c, int cell_start, int n_batch, int max_nc
         const int nw = nw_opts[o];
         const int lcap = c->gather_stream_lcap > 0 ? c->gather_stream_lcap : (int)std::min(512.0, std::max(64.0, 32.0 * std::ceil(4.0 * avg_cand / 32.0)));
         for (int tb = 128; tb >= 8; tb -= 4) {
-            const int cap = c->gather_stream_cap > 0 ? (c->gather_stream_cap & ~3) : ((int)(1.5 * avg_cand * tb) + 128 + 3) & ~3;
+            double worst = 0.0;                           // expected entries of an item on the densest chromosome
+            for (int j = 0; j < c->n_chrom; ++j) {
+                const double a = (size_t)j < c->chrom_row_avg.size() ? c->chrom_row_avg[(size_t)j] : avg_row;
+                worst = std::max(worst, a * c->k1 * std::min(tb, c->bins[j]));
+            }
+            const int cap = c->gather_stream_cap > 0 ? (c->gather_stream_cap & ~3) : ((int)(2.0 * worst) + 128 + 3) & ~3;
             const GstLayout L = gst_layout(max_nc, c->k1, tb, cap, lcap, nw);
             if (L.total <= budget && tb >= (nw > 16 ? 2 * nw : nw)) { best_tb = tb; p.TB = tb; p.CAP = cap; p.LCAP = lcap; p.n_warps = nw; break; }
         }
