@@ -72,10 +72,11 @@ __device__ __forceinline__ void mbar_arrive(uint32_t bar) {
 __device__ __forceinline__ void mbar_wait_wd(uint32_t bar, uint32_t parity) {
     uint32_t ok;
     unsigned long long t0 = 0;
+    unsigned polls = 0;
     do {
         asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\tselp.u32 %0, 1, 0, p;\n\t}"
-                     : "=r"(ok) : "r"(bar), "r"(parity), "r"(100000u) : "memory");
-        if (!ok) {
+                     : "=r"(ok) : "r"(bar), "r"(parity), "r"(1000000u) : "memory");
+        if (!ok && (++polls & 255u) == 0u) {
             unsigned long long now;
             asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(now));
             if (t0 == 0) t0 = now;
@@ -220,12 +221,9 @@ __global__ void __launch_bounds__(1024, 1) neigh_gather_stream_kernel(const __gr
         const int over_item = reinterpret_cast<const int*>(st + 128)[0];
         const int* scol = reinterpret_cast<const int*>(st + L.col_off);
         const float* sval = reinterpret_cast<const float*>(st + L.val_off);
-        for (int t = warp; t < it.nt; t += p.n_warps) {
+        // one token with the whole warp (tokens with more than 16 entries, or a small candidate list)
+        auto slow_token = [&](const int t) {
             const int tok = it.cb * p.n_bins + it.off + it.l0 + t;
-            if (over_item) {
-                if (lane == 0) p.tok_list[atomicAdd(p.tok_count, 1)] = tok;
-                continue;
-            }
             // ---- extents of the k1 rows of this token (lane n < k1)
             int len = 0, idx0 = 0;
             float w = 1.0f;
@@ -247,12 +245,12 @@ __global__ void __launch_bounds__(1024, 1) neigh_gather_stream_kernel(const __gr
             float4* dst = reinterpret_cast<float4*>(p.neigh + (int64_t)tok * 64);
             if (m == 0) {                                  // empty rows: A_hat row = 0
                 if (lane < 16) dst[lane] = make_float4(0.f, 0.f, 0.f, 0.f);
-                continue;
+                return;
             }
             int acount = 0;
             float part = 0.f;
             if (m <= 32) {
-                // ---- sparse token: one entry per lane in row-major order
+                // ---- one entry per lane in row-major order
                 int r = 0;
                 for (int q = 0; q + 1 < p.k1; ++q) r += (lane >= __shfl_sync(0xffffffffu, end, q)) ? 1 : 0;
                 const int start_r = __shfl_sync(0xffffffffu, end - len, r);
@@ -279,7 +277,7 @@ __global__ void __launch_bounds__(1024, 1) neigh_gather_stream_kernel(const __gr
                 acount = __popc(ob);
                 part = fabsf(tv);
             } else {
-                // ---- longer token: dense accumulator, rows one after the other (neighbour order), then first-visitor ownership
+                // ---- dense accumulator, rows one after the other (neighbour order), then first-visitor ownership
                 for (int n = 0; n < p.k1; ++n) {
                     const int ln = __shfl_sync(0xffffffffu, len, n), i0n = __shfl_sync(0xffffffffu, idx0, n);
                     const float wn = __shfl_sync(0xffffffffu, w, n);
@@ -310,7 +308,7 @@ __global__ void __launch_bounds__(1024, 1) neigh_gather_stream_kernel(const __gr
             if (acount > p.LCAP) {                         // more distinct columns than the list holds: the generic kernel finishes it
                 if (lane == 0) p.tok_list[atomicAdd(p.tok_count, 1)] = tok;
                 __syncwarp();
-                continue;
+                return;
             }
             const float total = warp_sum(part);
             __syncwarp();
@@ -339,6 +337,94 @@ __global__ void __launch_bounds__(1024, 1) neigh_gather_stream_kernel(const __gr
             if (grp == 0) dst[gl] = o0;
             else if (grp == 1) dst[8 + gl] = o1;
             __syncwarp();
+        };
+
+        if (over_item) {
+            for (int t = warp; t < it.nt; t += p.n_warps)
+                if (lane == 0) p.tok_list[atomicAdd(p.tok_count, 1)] = it.cb * p.n_bins + it.off + it.l0 + t;
+        } else {
+            // TWO tokens per pass, 16 lanes each (the sparse regime: a token's k1 rows hold a handful of entries): every
+            // instruction below serves both tokens; a pair with a token of more than 16 entries takes slow_token() twice
+            const int half = lane >> 4, le = lane & 15, hg = le >> 3;
+            for (int tp = 2 * warp; tp < it.nt; tp += 2 * p.n_warps) {
+                const int t = tp + half;
+                const bool tvalid = t < it.nt;
+                int len = 0, idx0 = 0;
+                float w = 1.0f;
+                if (le < p.k1 && tvalid) {
+                    const int64_t* rp = reinterpret_cast<const int64_t*>(st + L.meta_bytes) + (size_t)le * (size_t)(p.TB + 4);
+                    const int d = reinterpret_cast<const int*>(st + 96)[le];
+                    const int64_t e_lo = rp[d + t], e_hi = rp[d + t + 1];
+                    len = (int)(e_hi - e_lo);
+                    idx0 = (int)(e_lo + reinterpret_cast<const int64_t*>(st)[le]);
+                    w = reinterpret_cast<const float*>(st + 64)[le];
+                }
+                int end = len;
+#pragma unroll
+                for (int o = 1; o < GST_MAX_K1; o <<= 1) {
+                    const int x = __shfl_up_sync(0xffffffffu, end, o, GST_MAX_K1);
+                    if ((lane & (GST_MAX_K1 - 1)) >= o) end += x;
+                }
+                const int m = __shfl_sync(0xffffffffu, end, p.k1 - 1, 16);                 // entries of this half's token
+                if (__any_sync(0xffffffffu, m > 16) || p.LCAP < 32) {
+                    slow_token(tp);
+                    if (tp + 1 < it.nt) slow_token(tp + 1);
+                    continue;
+                }
+                int r = 0;
+                for (int q = 0; q + 1 < p.k1; ++q) r += (le >= __shfl_sync(0xffffffffu, end, q, 16)) ? 1 : 0;
+                const int start_r = __shfl_sync(0xffffffffu, end - len, r, 16);
+                const int idx = __shfl_sync(0xffffffffu, idx0, r, 16) + (le - start_r);
+                const float wr = __shfl_sync(0xffffffffu, w, r, 16);
+                const bool valid = le < m;
+                const int ccol = valid ? scol[idx] : 0;
+                float v = valid ? sval[idx] : 0.f;
+                if (p.weighted) v = __fmul_rn(wr, v);
+                const unsigned peers = __match_any_sync(0xffffffffu, valid ? (ccol | (half << 24)) : (-1 - lane));
+                const int first = __ffs(peers) - 1;
+                const bool own = valid && first == lane;
+                unsigned mm = peers & (peers - 1);                   // peers after the first occurrence, in lane (= neighbour) order
+                float sum = __shfl_sync(0xffffffffu, v, first);
+                for (int q = 1; q < p.k1; ++q) {
+                    const int src = mm ? __ffs(mm) - 1 : lane;
+                    const float x = __shfl_sync(0xffffffffu, v, src);
+                    if (mm) sum = __fadd_rn(sum, x);
+                    mm &= mm - 1;
+                }
+                float tv = own ? log1pf(__fmul_rn(sum, HSG_PDF0)) : 0.f;              // x pdf(0), log1p (Impute.py:19, 91)
+                float total = fabsf(tv);
+#pragma unroll
+                for (int o = 8; o > 0; o >>= 1) total += __shfl_xor_sync(0xffffffffu, total, o);
+                if (total > 0.f) tv = __fdiv_rn(tv, total);                          // L1 normalisation (Impute.py:92)
+                const unsigned ob = (__ballot_sync(0xffffffffu, own) >> (half * 16)) & 0xffffu;
+                if (own) { const int pos = half * 16 + __popc(ob & ((1u << le) - 1u)); lc[pos] = ccol; lv[pos] = tv; }
+                const int acount = __popc(ob);
+                const int amax = max(acount, __shfl_xor_sync(0xffffffffu, acount, 16));
+                __syncwarp();
+                // ---- gather: the two 8-lane groups of a half take the token's candidates alternately; lane gl owns columns
+                //      4 gl .. 4 gl + 3 and 32 + 4 gl .. 32 + 4 gl + 3
+                float4 o0 = make_float4(0.f, 0.f, 0.f, 0.f), o1 = o0;
+                const float4* E4 = reinterpret_cast<const float4*>(Es) + gl;
+                for (int i = hg; i < amax; i += 2) {
+                    if (i < acount) {
+                        const int ci = lc[half * 16 + i];
+                        const float a = lv[half * 16 + i];
+                        const float4 x0 = E4[ci * 16], x1 = E4[ci * 16 + 8];
+                        o0.x = fmaf(a, x0.x, o0.x); o0.y = fmaf(a, x0.y, o0.y); o0.z = fmaf(a, x0.z, o0.z); o0.w = fmaf(a, x0.w, o0.w);
+                        o1.x = fmaf(a, x1.x, o1.x); o1.y = fmaf(a, x1.y, o1.y); o1.z = fmaf(a, x1.z, o1.z); o1.w = fmaf(a, x1.w, o1.w);
+                    }
+                }
+                o0.x += __shfl_xor_sync(0xffffffffu, o0.x, 8); o0.y += __shfl_xor_sync(0xffffffffu, o0.y, 8);
+                o0.z += __shfl_xor_sync(0xffffffffu, o0.z, 8); o0.w += __shfl_xor_sync(0xffffffffu, o0.w, 8);
+                o1.x += __shfl_xor_sync(0xffffffffu, o1.x, 8); o1.y += __shfl_xor_sync(0xffffffffu, o1.y, 8);
+                o1.z += __shfl_xor_sync(0xffffffffu, o1.z, 8); o1.w += __shfl_xor_sync(0xffffffffu, o1.w, 8);
+                if (tvalid) {
+                    float4* dst = reinterpret_cast<float4*>(p.neigh + (int64_t)(it.cb * p.n_bins + it.off + it.l0 + t) * 64);
+                    if (hg == 0) dst[gl] = o0;
+                    else dst[8 + gl] = o1;
+                }
+                __syncwarp();
+            }
         }
         __syncwarp();
         if (lane == 0) mbar_arrive(bar_empty(s));
@@ -364,7 +450,7 @@ int try_launch_gather_stream(hsg_ctx* c, int cell_start, int n_batch, int max_nc
     for (int o = 0; o < 2 && !best_tb; ++o) {
         const int nw = nw_opts[o];
         const int lcap = c->gather_stream_lcap > 0 ? c->gather_stream_lcap : (int)std::min(512.0, std::max(64.0, 32.0 * std::ceil(4.0 * avg_cand / 32.0)));
-        for (int tb = 128; tb >= 8; tb -= 4) {
+        for (int tb = (128 / (2 * nw)) * (2 * nw); tb >= 2 * nw; tb -= 2 * nw) {      // whole passes of the consumers (2 tokens per warp)
             double worst = 0.0;                           // expected entries of an item on the densest chromosome
             for (int j = 0; j < c->n_chrom; ++j) {
                 const double a = (size_t)j < c->chrom_row_avg.size() ? c->chrom_row_avg[(size_t)j] : avg_row;
@@ -372,7 +458,7 @@ int try_launch_gather_stream(hsg_ctx* c, int cell_start, int n_batch, int max_nc
             }
             const int cap = c->gather_stream_cap > 0 ? (c->gather_stream_cap & ~3) : ((int)(2.0 * worst) + 128 + 3) & ~3;
             const GstLayout L = gst_layout(max_nc, c->k1, tb, cap, lcap, nw);
-            if (L.total <= budget && tb >= (nw > 16 ? 2 * nw : nw)) { best_tb = tb; p.TB = tb; p.CAP = cap; p.LCAP = lcap; p.n_warps = nw; break; }
+            if (L.total <= budget) { best_tb = tb; p.TB = tb; p.CAP = cap; p.LCAP = lcap; p.n_warps = nw; break; }
         }
     }
     if (!best_tb) return 0;
