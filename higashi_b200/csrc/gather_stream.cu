@@ -9,13 +9,16 @@
 //     every block takes ONE contiguous range of them (equal ranges: one wave, no tail), so a block works on one chromosome
 //     (two or three when its range straddles a boundary) and keeps that chromosome's E table [n_c x 64] fp32 in shared memory
 //     (one bulk copy per chromosome change).
-//   * a PRODUCER warp runs two hops ahead of the consumers through a 3-stage ring:
-//       hop A (item i + 2): the k+1 row_ptr slices [row0, row0 + nt] of the neighbour cells -> shared memory (k+1 bulk copies);
-//       hop B (item i + 1): with the extents of hop A in shared memory, the k+1 col and val segments [lo, hi) of the item
-//                           (16-byte aligned outwards) -> shared memory (2 (k+1) bulk copies);
+//   * a PRODUCER warp runs ahead of the consumers through a ring of NS stages (one consumer pass of tokens each; as many stages
+//     as shared memory holds, <= 12):
+//       hop A (item i + NS):     the k+1 row_ptr slices [row0, row0 + nt] of the neighbour cells -> shared memory (k+1 bulk copies);
+//       hop B (item i + NS / 2): with the extents of hop A in shared memory, the k+1 col and val segments [lo, hi) of the item
+//                                (16-byte aligned outwards) -> shared memory (2 (k+1) bulk copies);
 //     the consumers merge item i from shared memory meanwhile.  Three dependent global round trips per TOKEN in the older
-//     kernels become three per ITEM (16-64 tokens), all of them overlapped with the merge of the previous items.
-//   * CONSUMER warps take the tokens of the item round-robin.  Sparse token (at most 32 entries in its k+1 rows): one entry per
+//     kernels become two per ITEM (62 tokens), several items deep (measured: with one item of lookahead the consumers spent
+//     most of their time polling the full barrier -- they finish an item in about a microsecond).
+//   * CONSUMER warps take the tokens of the item two at a time (16 lanes per token while both hold at most 16 entries, else one
+//     token per warp).  Sparse token (at most 32 entries in its k+1 rows): one entry per
 //     lane in row-major order, duplicates found with match.any, the owner (first occurrence) adds its peers' values in lane
 //     order = neighbour order.  Longer token: a dense per-warp accumulator in shared memory, rows added one after the other,
 //     then one atomicExch per entry hands each column's sum to its first visitor (and clears the accumulator).  Either way the
@@ -30,7 +33,7 @@
 #include "umma_common.cuh"
 
 #define GST_MAX_CHROM 64
-#define GST_NS 3
+#define GST_MAX_NS 16
 #define GST_MAX_K1 8
 #define GST_MAX_GRID 256
 
@@ -38,7 +41,7 @@ struct GatherStreamParams {
     const int64_t* row_ptr; const int32_t* col; const float* val; const int32_t* nbr; const float* nbr_w;
     const float* E_bin; const int* bin_off; float* neigh; int* tok_list; int* tok_count;
     int k1, weighted, n_bins, cell_start, n_batch, n_chrom, max_nc;
-    int TB, CAP, LCAP, n_warps, n_items;
+    int TB, CAP, LCAP, n_warps, n_items, NS, AH;     // NS ring stages; hop A runs AH items ahead of hop B
     int item_first[GST_MAX_CHROM + 1];        // items [item_first[c], item_first[c + 1]) belong to chromosome c
     int tiles[GST_MAX_CHROM];                 // bin tiles per cell on chromosome c
     int blk_first[GST_MAX_GRID + 1];          // block b works on items [blk_first[b], blk_first[b + 1]): equal TOKEN counts
@@ -48,17 +51,17 @@ struct GstLayout {
     uint32_t e_bytes, bar_off, stage_off, stage_bytes, meta_bytes, rp_bytes, col_off, val_off, warp_off, warp_bytes, acc_bytes, total;
 };
 // meta of a stage: int64 sbase[8] | float w[8] | int d[8] | int flag
-__host__ __device__ inline GstLayout gst_layout(int max_nc, int k1, int TB, int CAP, int LCAP, int n_warps) {
+__host__ __device__ inline GstLayout gst_layout(int max_nc, int k1, int TB, int CAP, int LCAP, int n_warps, int NS) {
     GstLayout L;
     L.e_bytes = (uint32_t)max_nc * 256u;
     L.bar_off = L.e_bytes;
-    L.stage_off = L.bar_off + 128u;
+    L.stage_off = L.bar_off + 512u;
     L.meta_bytes = 144u;
     L.rp_bytes = (uint32_t)k1 * (uint32_t)(TB + 4) * 8u;
     L.col_off = L.meta_bytes + L.rp_bytes;
     L.val_off = L.col_off + (uint32_t)CAP * 4u;
     L.stage_bytes = L.val_off + (uint32_t)CAP * 4u;
-    L.warp_off = L.stage_off + GST_NS * L.stage_bytes;
+    L.warp_off = L.stage_off + (uint32_t)NS * L.stage_bytes;
     L.acc_bytes = (((uint32_t)max_nc + 3u) & ~3u) * 4u;
     L.warp_bytes = L.acc_bytes + (uint32_t)LCAP * 8u;
     L.total = L.warp_off + (uint32_t)n_warps * L.warp_bytes;
@@ -103,16 +106,17 @@ __device__ __forceinline__ GstItem gst_decode(const GatherStreamParams& p, int i
 
 __global__ void __launch_bounds__(1024, 1) neigh_gather_stream_kernel(const __grid_constant__ GatherStreamParams p) {
     extern __shared__ __align__(128) unsigned char smem[];
-    const GstLayout L = gst_layout(p.max_nc, p.k1, p.TB, p.CAP, p.LCAP, p.n_warps);
+    const GstLayout L = gst_layout(p.max_nc, p.k1, p.TB, p.CAP, p.LCAP, p.n_warps, p.NS);
+    const int NS = p.NS;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const uint32_t sbase = smem_u32(smem);
     const uint32_t bar_e = sbase + L.bar_off;
     auto bar_a = [&](int s) { return sbase + L.bar_off + 8u + (uint32_t)s * 8u; };
-    auto bar_b = [&](int s) { return sbase + L.bar_off + 8u + (uint32_t)(GST_NS + s) * 8u; };
-    auto bar_empty = [&](int s) { return sbase + L.bar_off + 8u + (uint32_t)(2 * GST_NS + s) * 8u; };
+    auto bar_b = [&](int s) { return sbase + L.bar_off + 8u + (uint32_t)(NS + s) * 8u; };
+    auto bar_empty = [&](int s) { return sbase + L.bar_off + 8u + (uint32_t)(2 * NS + s) * 8u; };
     if (threadIdx.x == 0) {
         mbar_init(bar_e, 1);
-        for (int s = 0; s < GST_NS; ++s) { mbar_init(bar_a(s), 1); mbar_init(bar_b(s), 1); mbar_init(bar_empty(s), (uint32_t)p.n_warps); }
+        for (int s = 0; s < NS; ++s) { mbar_init(bar_a(s), 1); mbar_init(bar_b(s), 1); mbar_init(bar_empty(s), (uint32_t)p.n_warps); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     __syncthreads();
@@ -123,23 +127,27 @@ __global__ void __launch_bounds__(1024, 1) neigh_gather_stream_kernel(const __gr
     if (warp == p.n_warps) {
         // ------------------------------------------------------------------ producer warp (lane n < k1 <-> neighbour row n)
         int c_hint_a = 0, c_hint_b = 0;
+        int nb_cell = -1, nb_src = 0;                    // neighbour id / weight of lane n, reloaded when the cell changes
+        float nb_w = 1.0f;
         auto stage_ptr = [&](int s) { return smem + L.stage_off + (uint32_t)s * L.stage_bytes; };
         auto hop_a = [&](int j) {                       // row_ptr slices of item i0 + j
-            const int s = j % GST_NS, use = j / GST_NS;
+            const int s = j % NS, use = j / NS;
             if (use > 0) mbar_wait_wd(bar_empty(s), (uint32_t)(use - 1) & 1u);
             const GstItem it = gst_decode(p, i0 + j, c_hint_a);
             unsigned char* st = stage_ptr(s);
             uint32_t bytes = 0;
             int64_t row0 = 0;
             int d = 0;
+            const int cell = p.cell_start + it.cb;
+            if (cell != nb_cell) {
+                nb_cell = cell; nb_src = cell; nb_w = 1.0f;
+                if (p.weighted && lane < p.k1) { nb_src = __ldg(p.nbr + (int64_t)cell * p.k1 + lane); nb_w = __ldg(p.nbr_w + (int64_t)cell * p.k1 + lane); }
+            }
             if (lane < p.k1) {
-                const int cell = p.cell_start + it.cb;
-                const int src = p.weighted ? __ldg(p.nbr + (int64_t)cell * p.k1 + lane) : cell;
-                const float w = p.weighted ? __ldg(p.nbr_w + (int64_t)cell * p.k1 + lane) : 1.0f;
-                row0 = (int64_t)src * p.n_bins + it.off + it.l0;
+                row0 = (int64_t)nb_src * p.n_bins + it.off + it.l0;
                 d = (int)(row0 & 1);
                 bytes = (uint32_t)((d + it.nt + 2) & ~1) * 8u;
-                reinterpret_cast<float*>(st + 64)[lane] = w;
+                reinterpret_cast<float*>(st + 64)[lane] = nb_w;
                 reinterpret_cast<int*>(st + 96)[lane] = d;
             }
             uint32_t tot = bytes;
@@ -151,7 +159,7 @@ __global__ void __launch_bounds__(1024, 1) neigh_gather_stream_kernel(const __gr
                 tma_bulk_g2s(smem_u32(st + L.meta_bytes) + (uint32_t)lane * (uint32_t)(p.TB + 4) * 8u, p.row_ptr + (row0 - d), bytes, bar_a(s));
         };
         auto hop_b = [&](int j) {                       // col / val segments of item i0 + j
-            const int s = j % GST_NS, use = j / GST_NS;
+            const int s = j % NS, use = j / NS;
             mbar_wait_wd(bar_a(s), (uint32_t)use & 1u);
             const GstItem it = gst_decode(p, i0 + j, c_hint_b);
             unsigned char* st = stage_ptr(s);
@@ -183,9 +191,9 @@ __global__ void __launch_bounds__(1024, 1) neigh_gather_stream_kernel(const __gr
                 tma_bulk_g2s(smem_u32(st + L.val_off) + (uint32_t)base * 4u, p.val + a_lo, (uint32_t)cnt * 4u, bar_b(s));
             }
         };
-        hop_a(0);
+        for (int j = 0; j < p.AH && j < n_my; ++j) hop_a(j);
         for (int j = 0; j < n_my; ++j) {
-            if (j + 1 < n_my) hop_a(j + 1);
+            if (j + p.AH < n_my) hop_a(j + p.AH);
             hop_b(j);
         }
         return;
@@ -204,7 +212,7 @@ __global__ void __launch_bounds__(1024, 1) neigh_gather_stream_kernel(const __gr
     int cur_c = -1, c_hint = 0;
     uint32_t e_phase = 0;
     for (int j = 0; j < n_my; ++j) {
-        const int s = j % GST_NS, use = j / GST_NS;
+        const int s = j % NS, use = j / NS;
         const GstItem it = gst_decode(p, i0 + j, c_hint);
         if (it.c != cur_c) {                               // (block-uniform) new chromosome: its E table -> shared memory
             asm volatile("bar.sync 1, %0;" ::"r"(n_cons) : "memory");
@@ -446,19 +454,22 @@ int try_launch_gather_stream(hsg_ctx* c, int cell_start, int n_batch, int max_nc
     // issue slots, are what a scheduler runs out of); tile: the largest whose stages fit next to the E table
     // (31 + the producer = 1024 threads; fewer than 16 -- long chromosomes with dense rows, whose E table leaves little room
     // -- and the hash-merge kernel with its 48 warps per SM is faster: measured on C3, 5.4 ms with 8 warps against 3.4 ms)
+    // ring depth: the consumers finish an item of the sparse regime in about a microsecond, a hop takes a few -- so the ring is
+    // as deep as shared memory allows (<= 12 stages of ONE consumer pass each), hop A running half a ring ahead of hop B
     static const int nw_opts[2] = {31, 16};
     for (int o = 0; o < 2 && !best_tb; ++o) {
         const int nw = nw_opts[o];
         const int lcap = c->gather_stream_lcap > 0 ? c->gather_stream_lcap : (int)std::min(512.0, std::max(64.0, 32.0 * std::ceil(4.0 * avg_cand / 32.0)));
-        for (int tb = (128 / (2 * nw)) * (2 * nw); tb >= 2 * nw; tb -= 2 * nw) {      // whole passes of the consumers (2 tokens per warp)
-            double worst = 0.0;                           // expected entries of an item on the densest chromosome
-            for (int j = 0; j < c->n_chrom; ++j) {
-                const double a = (size_t)j < c->chrom_row_avg.size() ? c->chrom_row_avg[(size_t)j] : avg_row;
-                worst = std::max(worst, a * c->k1 * std::min(tb, c->bins[j]));
-            }
-            const int cap = c->gather_stream_cap > 0 ? (c->gather_stream_cap & ~3) : ((int)(2.0 * worst) + 128 + 3) & ~3;
-            const GstLayout L = gst_layout(max_nc, c->k1, tb, cap, lcap, nw);
-            if (L.total <= budget) { best_tb = tb; p.TB = tb; p.CAP = cap; p.LCAP = lcap; p.n_warps = nw; break; }
+        const int tb = 2 * nw;
+        double worst = 0.0;                               // expected entries of an item on the densest chromosome
+        for (int j = 0; j < c->n_chrom; ++j) {
+            const double a = (size_t)j < c->chrom_row_avg.size() ? c->chrom_row_avg[(size_t)j] : avg_row;
+            worst = std::max(worst, a * c->k1 * std::min(tb, c->bins[j]));
+        }
+        const int cap = c->gather_stream_cap > 0 ? (c->gather_stream_cap & ~3) : ((int)(2.0 * worst) + 128 + 3) & ~3;
+        for (int ns = 12; ns >= 4; --ns) {
+            const GstLayout L = gst_layout(max_nc, c->k1, tb, cap, lcap, nw, ns);
+            if (L.total <= budget) { best_tb = tb; p.TB = tb; p.CAP = cap; p.LCAP = lcap; p.n_warps = nw; p.NS = ns; p.AH = ns / 2; break; }
         }
     }
     if (!best_tb) return 0;
@@ -476,7 +487,7 @@ int try_launch_gather_stream(hsg_ctx* c, int cell_start, int n_batch, int max_nc
     for (int j = c->n_chrom; j <= GST_MAX_CHROM; ++j) p.item_first[j] = (int)first;
     for (int j = c->n_chrom; j < GST_MAX_CHROM; ++j) p.tiles[j] = 1;
     p.n_items = (int)first;
-    const GstLayout L = gst_layout(max_nc, c->k1, p.TB, p.CAP, p.LCAP, p.n_warps);
+    const GstLayout L = gst_layout(max_nc, c->k1, p.TB, p.CAP, p.LCAP, p.n_warps, p.NS);
     static bool attr_set[64] = {};
     if (!attr_set[c->device & 63]) {
         HSG_CUDA(cudaFuncSetAttribute(neigh_gather_stream_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
