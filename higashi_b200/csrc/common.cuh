@@ -117,7 +117,7 @@ struct hsg_ctx {
     bool gather_sparse = true;               // sparse-row K1a fast path enabled (HSG_GATHER_SPARSE=0 disables it)
     bool gather_hash = true;                 // hash-merge K1a for long chromosomes enabled (HSG_GATHER_HASH=0 disables it)
     bool gather_chrom = true;                // chromosome-block K1a for dense rows enabled (HSG_GATHER_CHROM=0 disables it)
-    bool gather_stream = true;               // streaming K1a (gather_stream.cu) enabled (HSG_GATHER_STREAM=0 disables it)
+    bool gather_stream = false;              // streaming K1a (gather_stream.cu): opt-in with HSG_GATHER_STREAM=1 (measured slower than the register kernel, see its header)
     int gather_stream_cap = 0, gather_stream_lcap = 0;   // test hooks: force a small stage / candidate-list capacity (HSG_GATHER_STREAM_CAP / _LCAP)
     float* QK = nullptr;                     // fp32 [qk_cells, n_bins, 2, 128] (fp32 mode: batch; tensor-core mode: 1 cell for hsg_fix_cell)
     // tensor-core mode (HSG_PREC_TC16): 16-bit token tables + pre-swizzled weight images

@@ -204,11 +204,12 @@ def test_gather_generic_kernel(density, k, monkeypatch):
 
 @pytest.mark.parametrize("density,k,bins", [(0.3, 4, [120, 40]), (0.3, 0, [120, 40]), (0.08, 4, [130, 70, 5]), (0.02, 7, [120, 40]),
                                             (0.02, 4, [250, 97]), (0.0, 4, [120, 40]), (0.004, 4, [700])])
-def test_gather_stream_kernel(density, k, bins):
-    """The default K1a (gather_stream.cu): CSR segments of a (cell, bin tile) item bulk-copied into a 3-stage shared-memory ring,
+def test_gather_stream_kernel(density, k, bins, monkeypatch):
+    """The streaming K1a (gather_stream.cu, opt-in): CSR segments of a (cell, bin tile) item bulk-copied into a 3-stage shared-memory ring,
     sparse tokens merged with match.any, longer ones through the dense accumulator, E table of the chromosome in shared memory.
     Dense rows, no neighbours, tiles that straddle chromosome ends and a 5-bin chromosome, k + 1 = 8 rows, empty contacts,
     a chromosome longer than one E tile of the chromosome-block kernel."""
+    monkeypatch.setenv("HSG_GATHER_STREAM", "1")
     _synthetic_case(k, 0, 64, "fp32", bins, [0, 5, 39], density=density, **({"band": 40} if bins == [700] else {}))
 
 
@@ -216,6 +217,7 @@ def test_gather_stream_kernel(density, k, bins):
 def test_gather_stream_overflow_paths(density, cap, lcap, monkeypatch):
     """Items whose segments exceed the stage capacity and tokens with more distinct columns than the candidate list holds leave
     the streaming kernel through the overflow list (forced here with tiny capacities); the generic kernel finishes them."""
+    monkeypatch.setenv("HSG_GATHER_STREAM", "1")
     if cap:
         monkeypatch.setenv("HSG_GATHER_STREAM_CAP", str(cap))
     if lcap:
