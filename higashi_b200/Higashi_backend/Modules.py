@@ -334,11 +334,10 @@ class _HyperedgeScoreFn(torch.autograd.Function):
         eng.set_dropout(bool(model.training), seed=0x51ED0000 + model._tseed)
         xx = np.ascontiguousarray(np.asarray(x.detach().cpu() if hasattr(x, "detach") else x), dtype=np.int64)
         eng.forward(xx, chrom, to_neighs, stage=stage, loss_mode=2, only_model=bool(model.only_model), want_outputs=False)
-        mean, var, proba, _ = eng.heads(len(xx), zinb=True)
+        mean, var, proba = eng.heads_device(len(xx), zinb=True)          # stays on the device: no numpy round trip
         ctx.set_materialize_grads(False)
         ctx.model, ctx.eng, ctx.chrom, ctx.stage = model, eng, chrom, stage
-        dev = eng.device
-        return tuple(torch.from_numpy(a).to(dev).view(-1, 1) for a in (mean, var, proba))
+        return mean.view(-1, 1), var.view(-1, 1), proba.view(-1, 1)
 
     @staticmethod
     def backward(ctx, gmean, gvar, gproba):
@@ -452,12 +451,20 @@ class Hyper_SAGNN(nn.Module):
 
     def _pull_grads(self, eng, chrom, stage, zinb):
         from ..train_engine import grad_presence
-        flat = eng.grads.detach().cpu()
+        dev_flat = eng.grads.detach()
+        host_flat = None                 # one device-to-host copy, and only when some parameter lives on the host
         names = [t[0] for t in self._tmap]
         for (name, prm, o, n), on in zip(self._tmap, grad_presence(names, chrom, stage, zinb, eng.cell_on_hook)):
             if not on or not prm.requires_grad:
                 continue
-            g = flat[o:o + n].view(prm.shape).to(prm.device)
+            if prm.device == dev_flat.device:
+                g = dev_flat[o:o + n].view(prm.shape)
+            elif prm.device.type == "cpu":
+                if host_flat is None:
+                    host_flat = dev_flat.cpu()
+                g = host_flat[o:o + n].view(prm.shape)
+            else:
+                g = dev_flat[o:o + n].view(prm.shape).to(prm.device)
             prm.grad = g.clone() if prm.grad is None else prm.grad + g
 
     def forward(self, x, x_chrom, mask=None, chroms_in_batch=None):

@@ -894,10 +894,10 @@ extern "C" int hsg_score_heads(hsg_ctx* c, float* mean_host, float* var_host, fl
     HSG_CHECK(c && g_ws.count(c) && g_ws[c]->B > 0, "no forward batch");
     TrainWs* w = g_ws[c];
     cudaStream_t s = (cudaStream_t)stream;
-    if (mean_host) HSG_CUDA(cudaMemcpyAsync(mean_host, w->mean, w->B * sizeof(float), cudaMemcpyDeviceToHost, s));
-    if (var_host) HSG_CUDA(cudaMemcpyAsync(var_host, w->varh, w->B * sizeof(float), cudaMemcpyDeviceToHost, s));
-    if (proba_host) HSG_CUDA(cudaMemcpyAsync(proba_host, w->probah, w->B * sizeof(float), cudaMemcpyDeviceToHost, s));
-    if (pred_host) HSG_CUDA(cudaMemcpyAsync(pred_host, w->pred, w->B * sizeof(float), cudaMemcpyDeviceToHost, s));
+    if (mean_host) HSG_CUDA(cudaMemcpyAsync(mean_host, w->mean, w->B * sizeof(float), cudaMemcpyDefault, s));
+    if (var_host) HSG_CUDA(cudaMemcpyAsync(var_host, w->varh, w->B * sizeof(float), cudaMemcpyDefault, s));
+    if (proba_host) HSG_CUDA(cudaMemcpyAsync(proba_host, w->probah, w->B * sizeof(float), cudaMemcpyDefault, s));
+    if (pred_host) HSG_CUDA(cudaMemcpyAsync(pred_host, w->pred, w->B * sizeof(float), cudaMemcpyDefault, s));
     HSG_CUDA(cudaStreamSynchronize(s));
     return 0;
 }

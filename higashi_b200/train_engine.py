@@ -265,6 +265,17 @@ class TrainEngine:
                                                      C.c_void_p(stream)))
         return mean, var, proba, pred
 
+    def heads_device(self, B: int, zinb: bool = False):
+        """(mean, var, proba) of the last forward batch as CUDA tensors [B] (no host round trip: hsg_score_heads copies with
+        cudaMemcpyDefault, so device destinations are device-to-device copies on the caller's stream)."""
+        n = 3 if zinb else 1
+        out = torch.empty((n, B), dtype=torch.float32, device=self.device)
+        ptr = lambda i: C.cast(C.c_void_p(out[i].data_ptr()), C.POINTER(C.c_float))
+        stream = torch.cuda.current_stream(self.device).cuda_stream
+        self.ctx._check(self.ctx.lib.hsg_score_heads(self.ctx.h, ptr(0), ptr(1) if zinb else None, ptr(2) if zinb else None, None,
+                                                     C.c_void_p(stream)))
+        return (out[0], out[1], out[2]) if zinb else (out[0], None, None)
+
     def set_head_grads(self, dmean, dvar=None, dproba=None):
         """Upstream gradients (CUDA float32 tensors [B]) of the heads of the last forward, from an external loss."""
         keep = [None if t is None else t.detach().to(self.device, torch.float32).contiguous().reshape(-1) for t in (dmean, dvar, dproba)]

@@ -185,7 +185,8 @@ int  hsg_train_options(hsg_ctx* ctx, const float* cell2weight_host, float rank_t
  * identical in hsg_score_fwd and hsg_score_bwd; change the seed every step.  enabled = 0: eval-mode semantics.          */
 int  hsg_train_set_dropout(hsg_ctx* ctx, int enabled, uint64_t seed);
 /* the three heads of the last forward batch (var / proba are produced by loss_mode 2 = zinb only) and, in zinb mode, the
- * clamped mean `pred` that forward_batch_hyperedge returns; host float [B] each, any may be NULL                       */
+ * clamped mean `pred` that forward_batch_hyperedge returns; float [B] each, HOST OR DEVICE memory (copied with
+ * cudaMemcpyDefault on `stream`, which is synchronised before the call returns), any may be NULL                     */
 int  hsg_score_heads(hsg_ctx* ctx, float* mean_host, float* var_host, float* proba_host, float* pred_host, void* stream);
 /* ---- training batch producer on the device ------------------------------
  * replaces: generate_negative_cpu + check_nonzero (Higashi_wrapper.py:71-168), the label / weight assembly and the neighbour-
