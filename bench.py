@@ -80,13 +80,13 @@ class ClockSampler:
     Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
          "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
 
-    def __init__(self, index):
-        self.index, self.rows, self.proc = index, [], None
+    def __init__(self, index, period_ms=100):
+        self.index, self.rows, self.proc, self.period_ms = index, [], None, int(period_ms)
 
     def start(self):
         try:
             self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
-                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                          "--format=csv,noheader,nounits", "-lms", str(self.period_ms)],
                                          stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.t = threading.Thread(target=self._read, daemon=True)
             self.t.start()
@@ -451,7 +451,7 @@ def train_bench(args, rank, world, local, steps=None, want_cpu=True):
         n_steps = max(steps, 1)
         # device-timed leg: >= 2 s of steps, loss read back every 10th step
         l0 = eng.ctx.launch_count()
-        sampler = ClockSampler(local) if uniform else None
+        sampler = ClockSampler(local, period_ms=250) if uniform else None      # launch-bound step: poll the driver less often
         if sampler:
             sampler.start()
         ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)

@@ -78,12 +78,13 @@ __global__ void neigh_gather_kernel(const int64_t* __restrict__ row_ptr, const i
     S.tmp = (float*)b2;
     S.tmask = (unsigned*)(b2 + (size_t)max_nc * 4);
     S.tlist = (unsigned short*)(b2 + (size_t)max_nc * 4 + (size_t)words * 4);
+    // list mode: only the tokens the sub-warp kernel could not hold in registers (tok_list / tok_count written by it)
+    const int64_t n_tok = tok_list ? (int64_t)*tok_count : (int64_t)n_batch_cells * n_bins;
+    if ((int64_t)blockIdx.x * wpb + warp >= n_tok) return;          // nothing for this warp (the usual case in list mode)
     for (int i = lane; i < max_nc; i += 32) { S.acc[i] = 0.f; if (ltr > 0) S.tmp[i] = 0.f; }
     for (int i = lane; i < words; i += 32) { S.amask[i] = 0u; if (ltr > 0) S.tmask[i] = 0u; }
     __syncwarp();
 
-    // list mode: only the tokens the sub-warp kernel could not hold in registers (tok_list / tok_count written by it)
-    const int64_t n_tok = tok_list ? (int64_t)*tok_count : (int64_t)n_batch_cells * n_bins;
     for (int64_t ti = (int64_t)blockIdx.x * wpb + warp; ti < n_tok; ti += (int64_t)gridDim.x * wpb) {
         const int64_t tok = tok_list ? (int64_t)tok_list[ti] : ti;
         const int cb = (int)(tok / n_bins), g = (int)(tok - (int64_t)cb * n_bins);
@@ -537,6 +538,7 @@ struct GatherHashParams {
     const float* E_bin; const int* bin_chrom; const int* bin_off; float* neigh; int* tok_list; int* tok_count;
     int k1, weighted, n_bins, cell_start;
     int64_t n_tok;
+    const int* in_list; const int* in_count;      // list mode: only the tokens in_list[0 .. *in_count) (the register kernel's overflow)
 };
 
 __global__ void __launch_bounds__(GH_WARPS * 32) neigh_gather_hash_kernel(GatherHashParams p) {
@@ -550,9 +552,13 @@ __global__ void __launch_bounds__(GH_WARPS * 32) neigh_gather_hash_kernel(Gather
     __syncwarp();
     const int grp = lane >> 3, gl = lane & 7;
 
-    auto fetch_extents = [&](int64_t t, int64_t& lo, int64_t& hi, float& w) {
+    const int64_t n_work = p.in_list ? (int64_t)*p.in_count : p.n_tok;
+    if ((int64_t)blockIdx.x * GH_WARPS + warp >= n_work) return;
+    auto token_of = [&](int64_t ti) -> int64_t { return p.in_list ? (int64_t)__ldg(p.in_list + ti) : ti; };
+    auto fetch_extents = [&](int64_t ti, int64_t& lo, int64_t& hi, float& w) {
         lo = 0; hi = 0; w = 1.0f;
-        if (lane < p.k1 && t < p.n_tok) {
+        if (lane < p.k1 && ti < n_work) {
+            const int64_t t = token_of(ti);
             const int cb = (int)(t / p.n_bins), g = (int)(t - (int64_t)cb * p.n_bins);
             const int cell = p.cell_start + cb;
             const int src = p.weighted ? __ldg(p.nbr + (int64_t)cell * p.k1 + lane) : cell;
@@ -576,12 +582,13 @@ __global__ void __launch_bounds__(GH_WARPS * 32) neigh_gather_hash_kernel(Gather
     int64_t lo_n, hi_n;
     float w_n;
     fetch_extents(t_first, lo_n, hi_n, w_n);
-    for (int64_t t = t_first; t < p.n_tok; t += t_step) {
+    for (int64_t ti = t_first; ti < n_work; ti += t_step) {
+        const int64_t t = token_of(ti);
         const int g = (int)(t % p.n_bins);
         const int off = p.bin_off[p.bin_chrom[g]];
         const int64_t lo_l = lo_n, hi_l = hi_n;
         const float w_l = w_n;
-        fetch_extents(t + t_step, lo_n, hi_n, w_n);
+        fetch_extents(ti + t_step, lo_n, hi_n, w_n);
         bool fail = false;
         for (int nb0 = 0; nb0 < p.k1; nb0 += 8) {
             int cc[8]; float vv[8];
@@ -693,9 +700,10 @@ int launch_gather(hsg_ctx* c, const int*, int cell_start, int n_batch, cudaStrea
     if (to_sparse) {
         if (c->ovf_cap < n_tok + 1) {
             if (c->ovf_list) cudaFree(c->ovf_list);
-            HSG_CUDA(cudaMalloc((void**)&c->ovf_list, (size_t)(n_tok + 1) * sizeof(int)));
+            HSG_CUDA(cudaMalloc((void**)&c->ovf_list, (size_t)(2 * n_tok + 2) * sizeof(int)));      // two lists, each followed by its counter
             c->ovf_cap = n_tok + 1;
         }
+        bool second_list = false;
         int* cnt = c->ovf_list + n_tok;
         HSG_CUDA(cudaMemsetAsync(cnt, 0, sizeof(int), s));
         int64_t quads = (n_tok + 3) / 4;
@@ -718,16 +726,35 @@ int launch_gather(hsg_ctx* c, const int*, int cell_start, int n_batch, cudaStrea
             hp.row_ptr = c->row_ptr; hp.col = c->col; hp.val = c->val; hp.nbr = c->nbr; hp.nbr_w = c->nbr_w; hp.E_bin = c->E_bin;
             hp.bin_chrom = c->d_bin_chrom; hp.bin_off = c->d_bin_off; hp.neigh = c->neigh; hp.tok_list = c->ovf_list; hp.tok_count = cnt;
             hp.k1 = c->k1; hp.weighted = c->weighted ? 1 : 0; hp.n_bins = c->n_bins; hp.cell_start = cell_start; hp.n_tok = n_tok;
+            hp.in_list = nullptr; hp.in_count = nullptr;
             const int64_t hb = (n_tok + GH_WARPS - 1) / GH_WARPS;
             neigh_gather_hash_kernel<<<(unsigned)std::min<int64_t>(hb, (int64_t)c->n_sm * 6), GH_WARPS * 32, 0, s>>>(hp);
         }
-        else if (avg <= 16.0) GS_LAUNCH(4);
+        else if (avg <= 16.0) {
+            GS_LAUNCH(4);
+            if (c->gather_hash) {
+                // the few tokens with more than 32 entries: the hash-merge kernel in list mode (one exposed round trip per stage)
+                // instead of the generic kernel's 2 (k+1) dependent ones (26 -> ~10 us per launch on C2); what even the hash
+                // table cannot hold goes on to a second list for the generic kernel
+                int* cnt2 = c->ovf_list + 2 * n_tok + 1;
+                HSG_CUDA(cudaMemsetAsync(cnt2, 0, sizeof(int), s));
+                GatherHashParams hp;
+                hp.row_ptr = c->row_ptr; hp.col = c->col; hp.val = c->val; hp.nbr = c->nbr; hp.nbr_w = c->nbr_w; hp.E_bin = c->E_bin;
+                hp.bin_chrom = c->d_bin_chrom; hp.bin_off = c->d_bin_off; hp.neigh = c->neigh;
+                hp.tok_list = c->ovf_list + n_tok + 1; hp.tok_count = cnt2;
+                hp.k1 = c->k1; hp.weighted = c->weighted ? 1 : 0; hp.n_bins = c->n_bins; hp.cell_start = cell_start; hp.n_tok = n_tok;
+                hp.in_list = c->ovf_list; hp.in_count = cnt;
+                neigh_gather_hash_kernel<<<(unsigned)std::min<int64_t>((n_tok + GH_WARPS - 1) / GH_WARPS, (int64_t)c->n_sm), GH_WARPS * 32, 0, s>>>(hp);
+                c->launches++;
+                second_list = true;
+            }
+        }
         else if (avg <= 36.0) GS_LAUNCH(8);
         else GS_LAUNCH(12);
 #undef GS_LAUNCH
         if (!streamed) c->launches++;
         HSG_CUDA(cudaGetLastError());
-        list = c->ovf_list; count = cnt;
+        list = second_list ? c->ovf_list + n_tok + 1 : c->ovf_list; count = second_list ? c->ovf_list + 2 * n_tok + 1 : cnt;
         grid = (unsigned)std::min<int64_t>(grid, (int64_t)c->n_sm * 2);
     }
     if (c->d == 64) {
