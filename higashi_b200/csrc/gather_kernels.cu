@@ -730,25 +730,9 @@ int launch_gather(hsg_ctx* c, const int*, int cell_start, int n_batch, cudaStrea
             const int64_t hb = (n_tok + GH_WARPS - 1) / GH_WARPS;
             neigh_gather_hash_kernel<<<(unsigned)std::min<int64_t>(hb, (int64_t)c->n_sm * 6), GH_WARPS * 32, 0, s>>>(hp);
         }
-        else if (avg <= 16.0) {
-            GS_LAUNCH(4);
-            if (c->gather_hash) {
-                // the few tokens with more than 32 entries: the hash-merge kernel in list mode (one exposed round trip per stage)
-                // instead of the generic kernel's 2 (k+1) dependent ones (26 -> ~10 us per launch on C2); what even the hash
-                // table cannot hold goes on to a second list for the generic kernel
-                int* cnt2 = c->ovf_list + 2 * n_tok + 1;
-                HSG_CUDA(cudaMemsetAsync(cnt2, 0, sizeof(int), s));
-                GatherHashParams hp;
-                hp.row_ptr = c->row_ptr; hp.col = c->col; hp.val = c->val; hp.nbr = c->nbr; hp.nbr_w = c->nbr_w; hp.E_bin = c->E_bin;
-                hp.bin_chrom = c->d_bin_chrom; hp.bin_off = c->d_bin_off; hp.neigh = c->neigh;
-                hp.tok_list = c->ovf_list + n_tok + 1; hp.tok_count = cnt2;
-                hp.k1 = c->k1; hp.weighted = c->weighted ? 1 : 0; hp.n_bins = c->n_bins; hp.cell_start = cell_start; hp.n_tok = n_tok;
-                hp.in_list = c->ovf_list; hp.in_count = cnt;
-                neigh_gather_hash_kernel<<<(unsigned)std::min<int64_t>((n_tok + GH_WARPS - 1) / GH_WARPS, (int64_t)c->n_sm), GH_WARPS * 32, 0, s>>>(hp);
-                c->launches++;
-                second_list = true;
-            }
-        }
+        // (tried: finishing the register kernel's overflow list with the hash-merge kernel in list mode before the generic kernel --
+        //  C2 K1a 1.94 -> 2.06 ms per 1000 cells: the list is almost always empty and a third launch costs more than it saves)
+        else if (avg <= 16.0) GS_LAUNCH(4);
         else if (avg <= 36.0) GS_LAUNCH(8);
         else GS_LAUNCH(12);
 #undef GS_LAUNCH
