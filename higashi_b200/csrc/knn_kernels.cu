@@ -81,15 +81,18 @@ int knn_build(hsg_ctx* c, const float* embed_host, int dim, int k1, int32_t* nbr
     HSG_CHECK(k1 >= 1 && k1 <= n, "k+1 must be in [1, n_cells]");
     float *d_emb = nullptr, *d_scratch = nullptr, *d_dist = nullptr;
     int32_t* d_nbr = nullptr;
-    HSG_CUDA(cudaMalloc(&d_emb, (size_t)n * dim * sizeof(float)));
-    HSG_CUDA(cudaMalloc(&d_scratch, (size_t)n * n * sizeof(float)));
-    HSG_CUDA(cudaMalloc(&d_dist, (size_t)n * k1 * sizeof(float)));
-    HSG_CUDA(cudaMalloc(&d_nbr, (size_t)n * k1 * sizeof(int32_t)));
-    HSG_CUDA(cudaMemcpy(d_emb, embed_host, (size_t)n * dim * sizeof(float), cudaMemcpyHostToDevice));
-    knn_rows_kernel<<<n, 256, dim * sizeof(double), c->stream>>>(d_emb, n, dim, k1, d_scratch, d_nbr, d_dist);
-    c->launches++;
+    // every error path frees what was allocated before it (the n x n scratch is the allocation most likely to fail)
+    cudaError_t e = cudaMalloc(&d_emb, (size_t)n * dim * sizeof(float));
+    if (e == cudaSuccess) e = cudaMalloc(&d_scratch, (size_t)n * n * sizeof(float));
+    if (e == cudaSuccess) e = cudaMalloc(&d_dist, (size_t)n * k1 * sizeof(float));
+    if (e == cudaSuccess) e = cudaMalloc(&d_nbr, (size_t)n * k1 * sizeof(int32_t));
+    if (e == cudaSuccess) e = cudaMemcpy(d_emb, embed_host, (size_t)n * dim * sizeof(float), cudaMemcpyHostToDevice);
     std::vector<float> dist((size_t)n * k1);
-    cudaError_t e = cudaGetLastError();
+    if (e == cudaSuccess) {
+        knn_rows_kernel<<<n, 256, dim * sizeof(double), c->stream>>>(d_emb, n, dim, k1, d_scratch, d_nbr, d_dist);
+        c->launches++;
+        e = cudaGetLastError();
+    }
     if (e == cudaSuccess) e = cudaMemcpyAsync(dist.data(), d_dist, dist.size() * sizeof(float), cudaMemcpyDeviceToHost, c->stream);
     if (e == cudaSuccess) e = cudaMemcpyAsync(nbr_out, d_nbr, (size_t)n * k1 * sizeof(int32_t), cudaMemcpyDeviceToHost, c->stream);
     if (e == cudaSuccess) e = cudaStreamSynchronize(c->stream);

@@ -142,10 +142,17 @@ class PackedCSR:
         except (OSError, ValueError):
             pass
         csr = PackedCSR.from_object_array(np.load(npy_path, allow_pickle=True))
+        # several workers may reach this point together (impute_multi_gpu starts one per GPU) while others already memmap the
+        # blob: write a private temporary next to it and rename it into place (atomic on POSIX), never truncate a live file
+        tmp = "%s.tmp.%d" % (blob, os.getpid())
         try:
-            csr.save_blob(blob)
+            csr.save_blob(tmp)
+            os.replace(tmp, blob)
         except OSError:
-            pass
+            try:
+                os.remove(tmp)
+            except OSError:
+                pass
         return csr
 
     @staticmethod
