@@ -33,6 +33,23 @@
 
 void hsg_set_error(const std::string& msg);
 
+// In-kernel bounds checks for a debug build (`make DEBUG_ASSERTS=1`): compute-sanitizer is not available on the GPU pool, so the
+// indices a wrong table / list / tile entry would send out of range are checked in the kernels themselves; a failed check prints
+// its location and traps (the launch fails, nothing hangs).  Compiled out of the product build.
+#ifndef HSG_DEBUG_ASSERTS
+#define HSG_DEBUG_ASSERTS 0
+#endif
+#if HSG_DEBUG_ASSERTS
+#include <cstdio>
+#define HSG_DASSERT(cond)                                                                                         \
+    do {                                                                                                          \
+        if (!(cond)) { printf("HSG_DASSERT failed: %s at %s:%d (block %d thread %d)\n", #cond, __FILE__, __LINE__, \
+                              (int)blockIdx.x, (int)threadIdx.x); __trap(); }                                     \
+    } while (0)
+#else
+#define HSG_DASSERT(cond) do { } while (0)
+#endif
+
 #define HSG_CUDA(call)                                                                         \
     do {                                                                                       \
         cudaError_t e__ = (call);                                                              \

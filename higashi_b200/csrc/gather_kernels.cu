@@ -42,6 +42,7 @@ __device__ __forceinline__ void merge_row(const int32_t* __restrict__ col, const
         int cidx = 0;
         if (valid) {
             cidx = __ldg(col + e);
+            HSG_DASSERT(cidx >= 0 && (cidx >> 5) < 2048);          // chromosome-local column inside the per-warp accumulator
             float v = __ldg(val + e);
             float prod = scale ? __fmul_rn(w, v) : v;
             T[cidx] = __fadd_rn(T[cidx], prod);
@@ -87,6 +88,7 @@ __global__ void neigh_gather_kernel(const int64_t* __restrict__ row_ptr, const i
 
     for (int64_t ti = (int64_t)blockIdx.x * wpb + warp; ti < n_tok; ti += (int64_t)gridDim.x * wpb) {
         const int64_t tok = tok_list ? (int64_t)tok_list[ti] : ti;
+        HSG_DASSERT(tok >= 0 && tok < (int64_t)n_batch_cells * n_bins);
         const int cb = (int)(tok / n_bins), g = (int)(tok - (int64_t)cb * n_bins);
         const int cell = cell_start + cb;
         const int c = bin_chrom[g], off = bin_off[c], nc = bin_off[c + 1] - off, l = g - off;
@@ -270,7 +272,7 @@ __global__ void __launch_bounds__(GS_WPB * 32) neigh_gather_sparse_kernel(
         const int n = __shfl_sync(0xffffffffu, start, 7, 8);
         start -= len;
         const bool over = n > GS_CAP;
-        if (over && gl == 0 && tvalid) tok_list[atomicAdd(tok_count, 1)] = tok;
+        if (over && gl == 0 && tvalid) { const int slot = atomicAdd(tok_count, 1); HSG_DASSERT(slot >= 0 && slot < n_tok); tok_list[slot] = tok; }
         // ---- push the (weighted) entries into the staging strip in row order
         if (!over) {
             for (int i = 0; i < len; ++i) {
@@ -572,6 +574,7 @@ __global__ void __launch_bounds__(GH_WARPS * 32) neigh_gather_hash_kernel(Gather
         unsigned h = ((unsigned)cidx * 0x9E3779B1u) >> 24;
         for (int pr = 0; pr < GH_PROBES; ++pr) {
             const int slot = (int)((h + pr) & (GH_SLOTS - 1));
+            HSG_DASSERT(cidx >= 0 && cidx < 65536 && slot >= 0 && slot < GH_SLOTS);
             const int old = atomicCAS(&key[slot], -1, cidx);
             if (old == -1 || old == cidx) { hv[slot] = __fadd_rn(hv[slot], prod); return true; }
         }
@@ -628,6 +631,7 @@ __global__ void __launch_bounds__(GH_WARPS * 32) neigh_gather_hash_kernel(Gather
             if (used) {
                 const float v = log1pf(__fmul_rn(hv[sidx], HSG_PDF0));       // x pdf(0), log1p (Impute.py:19, 91)
                 const int pos = acount + __popc(b & ((1u << lane) - 1u));
+                HSG_DASSERT(pos >= 0 && pos < GH_SLOTS);
                 ccol[pos] = (unsigned short)kcol; cval[pos] = v;
                 part += fabsf(v);
                 key[sidx] = -1; hv[sidx] = 0.f;

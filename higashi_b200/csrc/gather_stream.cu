@@ -181,6 +181,7 @@ __global__ void __launch_bounds__(1024, 1) neigh_gather_stream_kernel(const __gr
             const int total = __shfl_sync(0xffffffffu, end, GST_MAX_K1 - 1);
             const int base = end - cnt;
             const bool over = total > p.CAP;
+            HSG_DASSERT(cnt >= 0 && base >= 0 && (over || base + cnt <= p.CAP));
             if (lane < p.k1) reinterpret_cast<int64_t*>(st)[lane] = (int64_t)base - a_lo;          // smem index of entry e = e + sbase
             if (lane == 0) reinterpret_cast<int*>(st + 128)[0] = over ? 1 : 0;
             __syncwarp();
@@ -290,8 +291,10 @@ __global__ void __launch_bounds__(1024, 1) neigh_gather_stream_kernel(const __gr
                     const int ln = __shfl_sync(0xffffffffu, len, n), i0n = __shfl_sync(0xffffffffu, idx0, n);
                     const float wn = __shfl_sync(0xffffffffu, w, n);
                     for (int e = lane; e < ln; e += 32) {
+                        HSG_DASSERT(i0n + e >= 0 && i0n + e < p.CAP);
                         const int ccol = scol[i0n + e];
                         const float v = sval[i0n + e];
+                        HSG_DASSERT(ccol >= 0 && ccol < it.nc);
                         acc[ccol] = __fadd_rn(acc[ccol], p.weighted ? __fmul_rn(wn, v) : v);
                     }
                     __syncwarp();
@@ -385,7 +388,9 @@ __global__ void __launch_bounds__(1024, 1) neigh_gather_stream_kernel(const __gr
                 const int idx = __shfl_sync(0xffffffffu, idx0, r, 16) + (le - start_r);
                 const float wr = __shfl_sync(0xffffffffu, w, r, 16);
                 const bool valid = le < m;
+                HSG_DASSERT(!valid || (idx >= 0 && idx < p.CAP));
                 const int ccol = valid ? scol[idx] : 0;
+                HSG_DASSERT(ccol >= 0 && ccol < it.nc);
                 float v = valid ? sval[idx] : 0.f;
                 if (p.weighted) v = __fmul_rn(wr, v);
                 const unsigned peers = __match_any_sync(0xffffffffu, valid ? (ccol | (half << 24)) : (-1 - lane));

@@ -231,6 +231,9 @@ __global__ void __launch_bounds__(512, 1) score_umma4_kernel(Umma4Params pp) {
         tr.pr = __ldg(p.pairs + (wtid < ta.y ? tr.pi : (long long)ta.x + ta.y - 1));
         tr.bias = tr.valid ? __ldg(p.pair_bias + tr.pi) : 0.f;
         tr.seg = (wtid >= ta.z ? 1 : 0) + (wtid >= ta.w ? 1 : 0);
+        HSG_DASSERT(pt >= 0 && pt < pp.n_tiles_cell && ta.y >= 1 && ta.y <= 128 && (long long)ta.x + ta.y <= p.P);
+        HSG_DASSERT(tr.pr.x >= 0 && tr.pr.x < p.n_bins && tr.pr.y >= 0 && tr.pr.y < p.n_bins);
+        HSG_DASSERT(tb4.x >= 0 && tb4.x < p.n_bins && tb4.y >= 0 && tb4.y < p.n_bins && tb4.z >= 0 && tb4.z < p.n_bins);
         tr.bi0 = tb4.x; tr.bi1 = tb4.y; tr.bi2 = tb4.z;
         return tr;
     };
@@ -277,6 +280,7 @@ __global__ void __launch_bounds__(512, 1) score_umma4_kernel(Umma4Params pp) {
                     else if (atomicCAS((int*)&slot_owner[1], -1, wg) == -1) sl = 1;
                     else __nanosleep(64);
                 }
+                HSG_DASSERT(sl == 0 || sl == 1);          // tensor-memory columns 384 + 64 sl .. + 63 of the 512 allocated
                 slot_of[wg] = sl;
             }
             wg_bar(wg);
