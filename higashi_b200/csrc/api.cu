@@ -587,6 +587,18 @@ extern "C" int hsg_prepare(hsg_ctx* c, int precision, int local_transfer_range, 
         c->binV16 = bv; c->cellV16 = cv;
         if (launch_convert_static128(c, c->binV, c->binS, c->n_bins, 1, c->binV16, c->binSb, c->stream)) return 1;
         if (launch_convert_static128(c, c->cellV, c->cellS, c->n_cells, 0, c->cellV16, c->cellSb, c->stream)) return 1;
+        // K1b on the tensor cores for d_model = 128 too (project_umma.cu, chunk-major tables)
+        c->use_proj_umma = c->n_bins >= proj_min_bins() && !(getenv("HSG_PROJ128_F32") && getenv("HSG_PROJ128_F32")[0] == '1');
+        if (c->use_proj_umma) {
+            std::vector<unsigned char> pimg(proj_wimg_bytes(d));
+            std::vector<float> pcst(proj_cst_count(), 0.f);
+            proj_build_weights(d, h->v[HSG_W_SAGE_W].data(), h->v[HSG_W_SAGE_B].data(), h->v[HSG_W_QS].data(), h->v[HSG_W_KS].data(),
+                               h->v[HSG_W_ALN1_G].data(), h->v[HSG_W_ALN1_B].data(), h->v[HSG_W_ALN2_G].data(),
+                               h->v[HSG_W_ALN2_B].data(), pimg.data(), pcst.data());
+            if (dev_alloc(&c->pj_wimg, pimg.size())) return 1;
+            HSG_CUDA(cudaMemcpy(c->pj_wimg, pimg.data(), pimg.size(), cudaMemcpyHostToDevice));
+            memcpy(c->h_pj_cst, pcst.data(), pcst.size() * sizeof(float));
+        }
         per_cell = (size_t)c->n_bins * (2 * HSG_HD * sizeof(__half) + 16 * sizeof(float) + d * sizeof(float));
     } else if (c->use_umma) {
         std::vector<unsigned char> wimg(umma_wimg_bytes());
@@ -605,9 +617,9 @@ extern "C" int hsg_prepare(hsg_ctx* c, int precision, int local_transfer_range, 
         // K1b on the tensor cores (fast variant only; a 128-token tile may touch at most 4 cells)
         c->use_proj_umma = !c->umma_hi && c->n_bins >= proj_min_bins();
         if (c->use_proj_umma) {
-            std::vector<unsigned char> pimg(proj_wimg_bytes());
+            std::vector<unsigned char> pimg(proj_wimg_bytes(d));
             std::vector<float> pcst(proj_cst_count(), 0.f);
-            proj_build_weights(h->v[HSG_W_SAGE_W].data(), h->v[HSG_W_SAGE_B].data(), h->v[HSG_W_QS].data(), h->v[HSG_W_KS].data(),
+            proj_build_weights(d, h->v[HSG_W_SAGE_W].data(), h->v[HSG_W_SAGE_B].data(), h->v[HSG_W_QS].data(), h->v[HSG_W_KS].data(),
                                h->v[HSG_W_ALN1_G].data(), h->v[HSG_W_ALN1_B].data(), h->v[HSG_W_ALN2_G].data(),
                                h->v[HSG_W_ALN2_B].data(), pimg.data(), pcst.data());
             if (dev_alloc(&c->pj_wimg, pimg.size())) return 1;

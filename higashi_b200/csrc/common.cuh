@@ -143,7 +143,7 @@ struct hsg_ctx {
     void* binV16 = nullptr; float* binSb = nullptr; void* cellV16 = nullptr; float* cellSb = nullptr;
     float* binV32p = nullptr; float* cellV32p = nullptr;   // high-accuracy variant: fp32 V rows in (quad e, head h) order (HSG_HI_POS)
     unsigned char* wimg = nullptr; float* cst = nullptr; float h_cst[512] = {0};
-    unsigned char* pj_wimg = nullptr; float h_pj_cst[320] = {0}; bool use_proj_umma = false;   // tensor-core K1b (project_umma.cu)
+    unsigned char* pj_wimg = nullptr; float h_pj_cst[384] = {0}; bool use_proj_umma = false;   // tensor-core K1b (project_umma.cu)
     bool use_umma = false;
     // generation 4 of the fast scorer (score_umma4.cu): tile table of the pair list, P tables of the bins and cells
     int* tiles4 = nullptr; int n_tiles4 = 0; void* binP = nullptr; void* cellP = nullptr; bool k2v4 = false; int k2gen = 4;
@@ -197,10 +197,10 @@ int umma_range_level(const float* wq, const float* wk, const float* wv, const fl
                      const float* ln1_g, const float* ln1_b, const float* S, long long s_rows, int d);
 void train_release(hsg_ctx* c);     // train.cu: frees every per-context training / sampler buffer (called by hsg_destroy)
 int umma_wimg_bytes();
-int proj_wimg_bytes();
+int proj_wimg_bytes(int d);
 int proj_cst_count();
 int proj_min_bins();
-int proj_build_weights(const float* sage_w, const float* sage_b, const float* wq, const float* wk, const float* g1, const float* b1,
+int proj_build_weights(int d, const float* sage_w, const float* sage_b, const float* wq, const float* wk, const float* g1, const float* b1,
                        const float* g2, const float* b2, unsigned char* wimg_host, float* cst_host);
 int launch_token_project_umma(hsg_ctx* c, int cell_start, int n_cells_batch, cudaStream_t s);
 int umma_cst_count();

@@ -14,33 +14,43 @@
 //     rounds to fp16 (Q pre-scaled by log2(e)/4, chunks in HSG_CHUNK_POS order, see score_umma.cu) into a swizzled staging tile and the CTA copies the tile
 //     out with fully coalesced 128-bit stores (a tile's Q|K rows are one contiguous 64 KB block of the table).
 // fp16 operands / fp32 accumulation: measured effect on the final score 1.9e-4 -> 2.0e-4 (scripts/bf16_emulation.py).
+// Templated on d_model: 64 (K = 128 / 64, two CTAs per SM) and 128 (the reference's 4DN configuration: GEMM1 [128 x 128] over
+// K = 256, GEMM2 [128 x 256] over K = 128; 128 KB of weight images + a 64 KB A tile -> one CTA per SM; chunk-major tables only).
 #include "umma_common.cuh"
 
-#define PJ_B_G 0                 // [64 x 128] fp16, 2 K-atoms of 8 KB
-#define PJ_B_QK 16384            // [256 x 64] fp16, 1 K-atom of 32 KB
-#define PJ_WIMG_BYTES 49152
-#define PJ_A 49152               // A1 (32 KB: 2 atoms); A2 = atom 0; output staging (32 KB) reuses the region
-#define PJ_CELL 81920            // PJ_SLOTS x 256 floats: [cell K (128) | cell Q (128)] of the cells this tile touches
-#define PJ_SLOTS 4
-#define PJ_BAR (PJ_CELL + PJ_SLOTS * 1024)
-#define PJ_TMEM (PJ_BAR + 16)
-#define PJ_TOTAL (PJ_TMEM + 16)
-#define PJC_GB 0                 // constants: sage bias [64], Q bias [128], K bias [128]
-#define PJC_BQ 64
-#define PJC_BK 192
-#define PJC_COUNT 320
+// shared-memory map as a function of d_model D (64: two CTAs per SM; 128: one):
+//   [0, PJ_B_QK)        G image   [D x 2D]  fp16, 2D/64 K-atoms of D x 128 bytes
+//   [PJ_B_QK, PJ_WIMG)  Q|K image [256 x D] fp16, D/64 K-atoms of 32 KB
+//   [PJ_A, PJ_CELL)     A1 (2D/64 atoms of 16 KB); A2 = its first D/64 atoms; (row-major tables only) output staging reuses it
+#define PJ_B_G 0
+__host__ __device__ constexpr int pj_b_qk(int D) { return D * 2 * D * 2; }
+__host__ __device__ constexpr int pj_wimg(int D) { return pj_b_qk(D) + 256 * D * 2; }
+__host__ __device__ constexpr int pj_a(int D) { return pj_wimg(D); }
+__host__ __device__ constexpr int pj_cell(int D) { return pj_a(D) + (2 * D / 64) * 16384; }
+#define PJ_SLOTS 4               // PJ_SLOTS x 256 floats: [cell K (128) | cell Q (128)] of the cells this tile touches
+__host__ __device__ constexpr int pj_bar(int D) { return pj_cell(D) + PJ_SLOTS * 1024; }
+__host__ __device__ constexpr int pj_tmem(int D) { return pj_bar(D) + 16; }
+__host__ __device__ constexpr int pj_total(int D) { return pj_tmem(D) + 16; }
+#define PJC_GB 0                 // constants: sage bias [D], Q bias [128], K bias [128]
+__host__ __device__ constexpr int pjc_bq(int D) { return D; }
+__host__ __device__ constexpr int pjc_bk(int D) { return D + 128; }
+#define PJC_MAX 384
 
 struct ProjParams {
     const float* neigh; const float* E_bin; const float* cellQ; const float* cellK;
     const unsigned char* wimg;
-    float cst[PJC_COUNT];
+    float cst[PJC_MAX];
     __half* QK16; float* XS;
     long long n_tok;
     int n_bins, cell_start, n_tiles;
     int chunk_major;         // 1: the grouped chunk-major tables of score_umma2.cu: QK16 [slot][n_grp][32 chunks][32 bins], XS [slot][n_grp][4 quads][32 bins]
 };
 
-__global__ void __launch_bounds__(128, 2) project_umma_kernel(ProjParams p) {
+template <int D>
+__global__ void __launch_bounds__(128, D == 64 ? 2 : 1) project_umma_kernel(ProjParams p) {
+    constexpr int PJ_B_QK = pj_b_qk(D), PJ_WIMG_BYTES = pj_wimg(D), PJ_A = pj_a(D), PJ_CELL = pj_cell(D), PJ_BAR = pj_bar(D), PJ_TMEM = pj_tmem(D);
+    constexpr int PJC_BQ = pjc_bq(D), PJC_BK = pjc_bk(D);
+    constexpr int DQ = D / 64;                   // 8-chunk groups per operand half / K-atoms of the second GEMM
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const uint32_t sraw = smem_u32(smem_raw);
@@ -96,18 +106,21 @@ __global__ void __launch_bounds__(128, 2) project_umma_kernel(ProjParams p) {
             if (tok >= p.n_tok) tok = p.n_tok - 1;
             int g = g0 + (int)(tok - tok0);
             while (g >= p.n_bins) g -= p.n_bins;
-            const float4* sn = reinterpret_cast<const float4*>(p.neigh + tok * 64 + j * 8);
-            const float4* se = reinterpret_cast<const float4*>(p.E_bin + (long long)g * 64 + j * 8);
-            const float4 n0 = __ldg(sn), n1 = __ldg(sn + 1), e0 = __ldg(se), e1 = __ldg(se + 1);
-            sts128(a_chunk_addr(a_base, rw, j), pack_h2(n0.x, n0.y), pack_h2(n0.z, n0.w), pack_h2(n1.x, n1.y), pack_h2(n1.z, n1.w));
-            sts128(a_chunk_addr(a_base, rw, 8 + j), pack_h2(e0.x, e0.y), pack_h2(e0.z, e0.w), pack_h2(e1.x, e1.y), pack_h2(e1.z, e1.w));
+#pragma unroll
+            for (int q = 0; q < DQ; ++q) {
+                const float4* sn = reinterpret_cast<const float4*>(p.neigh + tok * D + (q * 8 + j) * 8);
+                const float4* se = reinterpret_cast<const float4*>(p.E_bin + (long long)g * D + (q * 8 + j) * 8);
+                const float4 n0 = __ldg(sn), n1 = __ldg(sn + 1), e0 = __ldg(se), e1 = __ldg(se + 1);
+                sts128(a_chunk_addr(a_base, rw, q * 8 + j), pack_h2(n0.x, n0.y), pack_h2(n0.z, n0.w), pack_h2(n1.x, n1.y), pack_h2(n1.z, n1.w));
+                sts128(a_chunk_addr(a_base, rw, D / 8 + q * 8 + j), pack_h2(e0.x, e0.y), pack_h2(e0.z, e0.w), pack_h2(e1.x, e1.y), pack_h2(e1.z, e1.w));
+            }
         }
         fence_async_smem();
         tc_fence_before();
         __syncthreads();
         if (tid == 0) {
             tc_fence_after();
-            mma_group<8, 64>(a_base, sbase + PJ_B_G, 64, t0, 0u);
+            mma_group<2 * D / 16, D>(a_base, sbase + PJ_B_G, D, t0, 0u);
             umma_commit(bar_mma);
         }
         mbar_wait(bar_mma, phase); phase ^= 1;
@@ -115,26 +128,28 @@ __global__ void __launch_bounds__(128, 2) project_umma_kernel(ProjParams p) {
 
         // ---------------------------------------------------------------- dyn = swish(. + b) ; xhat = LayerNorm statistics only
         {
-            uint32_t r0[32], r1[32];
-            tmem_ld32(t0 + t_lane, r0);
-            tmem_ld32(t0 + t_lane + 32, r1);
-            tmem_ld_wait();
-            float x[64];
+            float x[D];
             float s = 0.f;
 #pragma unroll
-            for (int i = 0; i < 64; ++i) {
-                const float v = __uint_as_float(i < 32 ? r0[i] : r1[i - 32]) + cst[PJC_GB + i];
-                const float d = v * rcp_approx(1.0f + ex2_approx(v * -1.4426950408889634f));      // v * sigmoid(v)
-                x[i] = d;
-                s += d;
+            for (int cc = 0; cc < D / 32; ++cc) {
+                uint32_t r[32];
+                tmem_ld32(t0 + t_lane + cc * 32, r);
+                tmem_ld_wait();
+#pragma unroll
+                for (int i = 0; i < 32; ++i) {
+                    const float v = __uint_as_float(r[i]) + cst[PJC_GB + cc * 32 + i];
+                    const float d = v * rcp_approx(1.0f + ex2_approx(v * -1.4426950408889634f));      // v * sigmoid(v)
+                    x[cc * 32 + i] = d;
+                    s += d;
+                }
             }
-            const float mean = s * (1.0f / 64.0f);
+            const float mean = s * (1.0f / (float)D);
             float vs = 0.f;
 #pragma unroll
-            for (int i = 0; i < 64; ++i) { x[i] -= mean; vs = fmaf(x[i], x[i], vs); }
-            const float rstd = rsqrtf(vs * (1.0f / 64.0f) + HSG_LN_EPS);
+            for (int i = 0; i < D; ++i) { x[i] -= mean; vs = fmaf(x[i], x[i], vs); }
+            const float rstd = rsqrtf(vs * (1.0f / (float)D) + HSG_LN_EPS);
 #pragma unroll
-            for (int c = 0; c < 8; ++c)
+            for (int c = 0; c < D / 8; ++c)
                 sts128(a_chunk_addr(a_base, tid, c), pack_h2(x[c * 8] * rstd, x[c * 8 + 1] * rstd), pack_h2(x[c * 8 + 2] * rstd, x[c * 8 + 3] * rstd),
                        pack_h2(x[c * 8 + 4] * rstd, x[c * 8 + 5] * rstd), pack_h2(x[c * 8 + 6] * rstd, x[c * 8 + 7] * rstd));
         }
@@ -143,7 +158,7 @@ __global__ void __launch_bounds__(128, 2) project_umma_kernel(ProjParams p) {
         __syncthreads();
         if (tid == 0) {
             tc_fence_after();
-            mma_group<4, 256>(a_base, sbase + PJ_B_QK, 256, t0, 0u);
+            mma_group<D / 16, 256>(a_base, sbase + PJ_B_QK, 256, t0, 0u);
             umma_commit(bar_mma);
         }
         mbar_wait(bar_mma, phase); phase ^= 1;
@@ -240,15 +255,15 @@ __global__ void __launch_bounds__(128, 2) project_umma_kernel(ProjParams p) {
 // ---------------------------------------------------------------------------------------------
 // host side
 // ---------------------------------------------------------------------------------------------
-int proj_wimg_bytes() { return PJ_WIMG_BYTES; }
-int proj_cst_count() { return PJC_COUNT; }
+int proj_wimg_bytes(int d) { return d == 128 ? pj_wimg(128) : pj_wimg(64); }
+int proj_cst_count() { return PJC_MAX; }
 int proj_min_bins() { return (127 + PJ_SLOTS - 2) / (PJ_SLOTS - 1); }        // a 128-token tile must touch at most PJ_SLOTS cells
 
-// sage [64][128], wq / wk [128][64], LayerNorm gains / biases [64]
-int proj_build_weights(const float* sage_w, const float* sage_b, const float* wq, const float* wk, const float* g1, const float* b1,
+// sage [d][2d], wq / wk [128][d], LayerNorm gains / biases [d]
+int proj_build_weights(int d, const float* sage_w, const float* sage_b, const float* wq, const float* wk, const float* g1, const float* b1,
                        const float* g2, const float* b2, unsigned char* wimg_host, float* cst_host) {
-    const int d = UM_D;
-    memset(wimg_host, 0, PJ_WIMG_BYTES);
+    const int b_qk = d == 128 ? pj_b_qk(128) : pj_b_qk(64), bq0 = d, bk0 = d + 128;
+    memset(wimg_host, 0, (size_t)proj_wimg_bytes(d));
     swizzle_image(sage_w, d, 2 * d, reinterpret_cast<__half*>(wimg_host + PJ_B_G));
     std::vector<float> qk((size_t)2 * HSG_HD * d);
     for (int n = 0; n < HSG_HD; ++n) {
@@ -259,11 +274,26 @@ int proj_build_weights(const float* sage_w, const float* sage_b, const float* wq
             bq += (double)wq[(size_t)n * d + k] * b1[k];
             bk += (double)wk[(size_t)n * d + k] * b2[k];
         }
-        cst_host[PJC_BQ + n] = (float)bq;
-        cst_host[PJC_BK + n] = (float)bk;
+        cst_host[bq0 + n] = (float)bq;
+        cst_host[bk0 + n] = (float)bk;
     }
-    swizzle_image(qk.data(), 2 * HSG_HD, d, reinterpret_cast<__half*>(wimg_host + PJ_B_QK));
+    swizzle_image(qk.data(), 2 * HSG_HD, d, reinterpret_cast<__half*>(wimg_host + b_qk));
     for (int i = 0; i < d; ++i) cst_host[PJC_GB + i] = sage_b[i];
+    return 0;
+}
+
+template <int D>
+static int launch_tpu(hsg_ctx* c, const ProjParams& p, cudaStream_t s) {
+    static bool attr_set[64] = {};               // per device: the attribute belongs to the device's function instance
+    if (!attr_set[c->device & 63]) {
+        HSG_CUDA(cudaFuncSetAttribute(project_umma_kernel<D>, cudaFuncAttributeMaxDynamicSharedMemorySize, pj_total(D) + 1024));
+        attr_set[c->device & 63] = true;
+    }
+    const int per_sm = D == 64 ? 2 : 1;
+    const int grid = p.n_tiles < per_sm * c->n_sm ? p.n_tiles : per_sm * c->n_sm;
+    project_umma_kernel<D><<<grid, 128, pj_total(D) + 1024, s>>>(p);
+    c->launches++;
+    HSG_CUDA(cudaGetLastError());
     return 0;
 }
 
@@ -276,14 +306,6 @@ int launch_token_project_umma(hsg_ctx* c, int cell_start, int n_batch, cudaStrea
     p.QK16 = (__half*)c->QK16; p.XS = c->XS; p.n_tok = n_tok; p.n_bins = c->n_bins; p.cell_start = cell_start;
     p.n_tiles = (int)((n_tok + 127) / 128);
     p.chunk_major = c->k2v2 ? 1 : 0;
-    static bool attr_set[64] = {};               // per device: the attribute belongs to the device's function instance
-    if (!attr_set[c->device & 63]) {
-        HSG_CUDA(cudaFuncSetAttribute(project_umma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, PJ_TOTAL + 1024));
-        attr_set[c->device & 63] = true;
-    }
-    int grid = p.n_tiles < 2 * c->n_sm ? p.n_tiles : 2 * c->n_sm;
-    project_umma_kernel<<<grid, 128, PJ_TOTAL + 1024, s>>>(p);
-    c->launches++;
-    HSG_CUDA(cudaGetLastError());
-    return 0;
+    HSG_CHECK(c->d == 64 || (c->d == 128 && p.chunk_major), "tensor-core projection: d_model 64, or 128 with chunk-major tables");
+    return c->d == 128 ? launch_tpu<128>(c, p, s) : launch_tpu<64>(c, p, s);
 }
