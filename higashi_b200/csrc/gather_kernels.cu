@@ -233,7 +233,7 @@ __device__ __forceinline__ void gs_dedup_dispatch(int nmax, const int (&col)[SLO
     }
 }
 
-template <int SLOTS>
+template <int SLOTS, int D>
 __global__ void __launch_bounds__(GS_WPB * 32) neigh_gather_sparse_kernel(
     const int64_t* __restrict__ row_ptr, const int32_t* __restrict__ col, const float* __restrict__ val,
     const int32_t* __restrict__ nbr, const float* __restrict__ nbr_w, int k1, int weighted, const float* __restrict__ E_bin,
@@ -315,9 +315,12 @@ __global__ void __launch_bounds__(GS_WPB * 32) neigh_gather_sparse_kernel(
 #pragma unroll
             for (int s = 0; s < GS_SLOTS; ++s) sum[s] = __fdiv_rn(sum[s], part);
         }
-        // ---- neigh = sum_t A_hat[b,t] * E_bin[t,:] : lane gl owns columns [8 gl, 8 gl + 8)
-        float4 o0 = make_float4(0.f, 0.f, 0.f, 0.f), o1 = o0;
-        const float4* Eg = reinterpret_cast<const float4*>(E_bin + (int64_t)off * 64) + gl * 2;
+        // ---- neigh = sum_t A_hat[b,t] * E_bin[t,:] : lane gl owns columns [8 gl, 8 gl + 8) of every 64-column block
+        constexpr int NB = D / 64;
+        float4 o0[NB], o1[NB];
+#pragma unroll
+        for (int b = 0; b < NB; ++b) { o0[b] = make_float4(0.f, 0.f, 0.f, 0.f); o1[b] = o0[b]; }
+        const float4* Eg = reinterpret_cast<const float4*>(E_bin + (int64_t)off * D) + gl * 2;
 #pragma unroll
         for (int s = 0; s < GS_SLOTS; ++s) {
             if (s * 8 < nmax) {
@@ -326,16 +329,20 @@ __global__ void __launch_bounds__(GS_WPB * 32) neigh_gather_sparse_kernel(
                     const float a = __shfl_sync(0xffffffffu, sum[s], l2, 8);
                     const int c = __shfl_sync(0xffffffffu, ec[s], l2, 8);
                     if (a != 0.f) {
-                        const float4 x0 = __ldg(Eg + (int64_t)c * 16), x1 = __ldg(Eg + (int64_t)c * 16 + 1);
-                        o0.x = fmaf(a, x0.x, o0.x); o0.y = fmaf(a, x0.y, o0.y); o0.z = fmaf(a, x0.z, o0.z); o0.w = fmaf(a, x0.w, o0.w);
-                        o1.x = fmaf(a, x1.x, o1.x); o1.y = fmaf(a, x1.y, o1.y); o1.z = fmaf(a, x1.z, o1.z); o1.w = fmaf(a, x1.w, o1.w);
+#pragma unroll
+                        for (int b = 0; b < NB; ++b) {
+                            const float4 x0 = __ldg(Eg + (int64_t)c * (D / 4) + b * 16), x1 = __ldg(Eg + (int64_t)c * (D / 4) + b * 16 + 1);
+                            o0[b].x = fmaf(a, x0.x, o0[b].x); o0[b].y = fmaf(a, x0.y, o0[b].y); o0[b].z = fmaf(a, x0.z, o0[b].z); o0[b].w = fmaf(a, x0.w, o0[b].w);
+                            o1[b].x = fmaf(a, x1.x, o1[b].x); o1[b].y = fmaf(a, x1.y, o1[b].y); o1[b].z = fmaf(a, x1.z, o1[b].z); o1[b].w = fmaf(a, x1.w, o1[b].w);
+                        }
                     }
                 }
             }
         }
         if (tvalid && !over) {
-            float4* dst = reinterpret_cast<float4*>(neigh + (int64_t)tok * 64) + gl * 2;
-            dst[0] = o0; dst[1] = o1;
+            float4* dst = reinterpret_cast<float4*>(neigh + (int64_t)tok * D) + gl * 2;
+#pragma unroll
+            for (int b = 0; b < NB; ++b) { dst[b * 16] = o0[b]; dst[b * 16 + 1] = o1[b]; }
         }
     }
 }
@@ -691,11 +698,12 @@ int launch_gather(hsg_ctx* c, const int*, int cell_start, int n_batch, cudaStrea
     // all-pairs dedup (SLOTS^2) loses to the generic kernel's dense accumulator -- unless the chromosomes are so long that the
     // accumulator (4 B x max_nc per warp) leaves the generic kernel with a handful of warps per SM (measured, C3 / C4 / C5 shapes).
     const double avg_cand = (double)c->k1 * (double)c->nnz / (double)std::max<int64_t>(c->n_rows, 1);
-    const bool sparse_ok = c->d == 64 && c->ltr == 0 && c->k1 <= 8 && n_tok < (1LL << 31) && c->gather_sparse;
+    const bool sparse_ok = (c->d == 64 || c->d == 128) && c->ltr == 0 && c->k1 <= 8 && n_tok < (1LL << 31) && c->gather_sparse;
     // long rows (> 16 merged candidates): the hash-merge kernel wherever the fast path applies (measured: C5 7.28 -> 2.54 ms against
     // the 96-candidate register kernel, C3 3.53 -> 3.38 ms against the chromosome-block kernel); with it switched off the old rule
     // stands (register kernel only for chromosomes too long for a dense per-warp accumulator)
-    const bool to_sparse = sparse_ok && (avg_cand <= 16.0 || max_nc > 1536 || c->gather_hash || c->gather_stream);
+    // (d_model = 128: only the register kernel is templated on the width; longer rows stay on the generic kernel there)
+    const bool to_sparse = sparse_ok && (c->d == 64 ? (avg_cand <= 16.0 || max_nc > 1536 || c->gather_hash || c->gather_stream) : avg_cand <= 16.0);
     if (!to_sparse && c->gather_chrom) {        // dense rows, short chromosomes: one chromosome per block, E_c in shared memory
         bool done = false;
         if (try_launch_gather_chrom(c, cell_start, n_batch, max_nc, s, &done)) return 1;
@@ -719,11 +727,15 @@ int launch_gather(hsg_ctx* c, const int*, int cell_start, int n_batch, cudaStrea
         // the streaming kernel (gather_stream.cu: bulk-copied CSR segments, E table of the chromosome in shared memory) whenever
         // its stages fit next to the chromosome's E table; it leaves what it cannot hold on the same overflow list
         bool streamed = false;
-        if (c->gather_stream && try_launch_gather_stream(c, cell_start, n_batch, max_nc, cnt, s, &streamed)) return 1;
-#define GS_LAUNCH(SL) neigh_gather_sparse_kernel<SL><<<g, GS_WPB * 32, 0, s>>>(                                                    \
+        if (c->gather_stream && c->d == 64 && try_launch_gather_stream(c, cell_start, n_batch, max_nc, cnt, s, &streamed)) return 1;
+#define GS_LAUNCH(SL) neigh_gather_sparse_kernel<SL, 64><<<g, GS_WPB * 32, 0, s>>>(                                                    \
             c->row_ptr, c->col, c->val, c->nbr, c->nbr_w, c->k1, c->weighted ? 1 : 0, c->E_bin, c->d_bin_chrom, c->d_bin_off,      \
             c->n_bins, cell_start, (int)n_tok, c->neigh, c->ovf_list, cnt)
         if (streamed) {
+        } else if (c->d == 128) {
+            neigh_gather_sparse_kernel<4, 128><<<g, GS_WPB * 32, 0, s>>>(
+                c->row_ptr, c->col, c->val, c->nbr, c->nbr_w, c->k1, c->weighted ? 1 : 0, c->E_bin, c->d_bin_chrom, c->d_bin_off,
+                c->n_bins, cell_start, (int)n_tok, c->neigh, c->ovf_list, cnt);
         } else if (avg > 16.0 && c->gather_hash && max_nc < 65536) {
             // long chromosome, tens of candidates per token: shared-memory hash merge instead of the SLOTS^2 register dedup
             GatherHashParams hp;
