@@ -108,8 +108,66 @@ __device__ __forceinline__ void attn_ctx(const uint4* __restrict__ binVc, const 
 // ---- the three row-wise epilogues of a token (thread r <-> row r <-> TMEM lane r), packed fp32x2 math -----------------------
 // after MMA 1: rstd of y_c (columns [0, 64) of t_y), h = swish(rstd g + b0') -> fp16 A operand over the consumed g columns, plus
 // the constant K columns 64 / 65 = 1 that pick up the bias rows of the W1 / C0 images
+// HSG_EPI_PIPE = 1: the tensor-memory reads of the row epilogues are software-pipelined (the next tcgen05.ld is in flight while the
+// registers of the previous one are consumed; a tcgen05.ld x32 of a warp occupies the 64 B/clk read port for 64 cycles) and the u
+// epilogue keeps z in registers instead of reading it twice
+#ifndef HSG_EPI_PIPE
+#define HSG_EPI_PIPE 0
+#endif
+template <bool TANH2>
+__device__ __forceinline__ void epi_h_half(const uint32_t (&r)[32], const float2 rs, const int half, const uint32_t t_h, const uint32_t t_lane,
+                                           const float* cst) {
+    uint32_t hp[16];
+#pragma unroll
+    for (int c = 0; c < 4; ++c) {
+        const float* bq = cst + CST_B0F + half * 32 + c * 8;
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+            float2 w = __ffma2_rn(f2(r[c * 8 + 2 * q], r[c * 8 + 2 * q + 1]), rs, make_float2(bq[2 * q], bq[2 * q + 1]));
+            if constexpr (TANH2) {
+                const __half2 wh = __floats2half2_rn(w.x, w.y);
+                uint32_t th;
+                asm("tanh.approx.f16x2 %0, %1;" : "=r"(th) : "r"(h2u(wh)));
+                hp[c * 4 + q] = h2u(__hfma2(wh, u2h(th), wh));
+            } else {
+                float2 th = make_float2(fast_tanh(w.x), fast_tanh(w.y));
+                float2 hh = __ffma2_rn(w, th, w);
+                hp[c * 4 + q] = pack_h2(hh.x, hh.y);
+            }
+        }
+    }
+    tmem_st16(t_h + t_lane + half * 16, hp);
+}
+
 template <bool TANH2>
 __device__ __forceinline__ void epi_h(const uint32_t t_y, const uint32_t t_h, const uint32_t t_lane, const float* cst) {
+#if HSG_EPI_PIPE
+    {
+        uint32_t r0[32], r1[32], g0[32];
+        tmem_ld32(t_y + t_lane, r0);
+        tmem_ld32(t_y + t_lane + 32, r1);
+        tmem_ld_wait();
+        tmem_ld32(t_h + t_lane, g0);                       // first half of g: in flight during the variance
+        float2 vA = make_float2(0.f, 0.f), vB = vA, vC = vA, vD = vA;
+#pragma unroll
+        for (int i = 0; i < 16; i += 2) {
+            float2 a = f2(r0[2 * i], r0[2 * i + 1]), b = f2(r0[2 * i + 2], r0[2 * i + 3]);
+            float2 c2 = f2(r1[2 * i], r1[2 * i + 1]), d2 = f2(r1[2 * i + 2], r1[2 * i + 3]);
+            vA = __ffma2_rn(a, a, vA); vB = __ffma2_rn(b, b, vB); vC = __ffma2_rn(c2, c2, vC); vD = __ffma2_rn(d2, d2, vD);
+        }
+        vA = __fadd2_rn(__fadd2_rn(vA, vB), __fadd2_rn(vC, vD));
+        const float rstd = rsqrtf((vA.x + vA.y) * (1.0f / 64.0f) + HSG_LN_EPS);
+        const float2 rs = make_float2(rstd, rstd);
+        tmem_ld_wait();
+        tmem_ld32(t_h + t_lane + 32, r0);                  // second half of g: in flight during the first half of h
+        epi_h_half<TANH2>(g0, rs, 0, t_h, t_lane, cst);    // (h columns [0, 16) of the slot: not the columns being read)
+        tmem_ld_wait();
+        epi_h_half<TANH2>(r0, rs, 1, t_h, t_lane, cst);
+        const uint32_t one[8] = {0x3C003C00u, 0u, 0u, 0u, 0u, 0u, 0u, 0u};
+        tmem_st8(t_h + t_lane + 32, one);
+        return;
+    }
+#endif
     float2 rs;
     {
         uint32_t r0[32], r1[32];
@@ -172,6 +230,50 @@ __device__ __forceinline__ void load_s_row(const Umma2Params& p, const int t, co
 
 // after MMA 2: z_c (centred by construction) -> rstd, u' = (z_c rstd + S')^2 -> fp16 A operand over the consumed h columns
 __device__ __forceinline__ void epi_u(const uint32_t t_y, const uint32_t t_h, const uint32_t t_lane, const float4 (&sreg)[16]) {
+#if HSG_EPI_PIPE
+    {
+        uint32_t za[32], zb[32];
+        tmem_ld32(t_y + t_lane, za);
+        tmem_ld_wait();
+        tmem_ld32(t_y + t_lane + 32, zb);                  // second half of z: in flight during the first half of the variance
+        float2 vA = make_float2(0.f, 0.f), vB = vA, vC = vA, vD = vA;
+#pragma unroll
+        for (int i = 0; i < 16; i += 4) {
+            float2 a = f2(za[2 * i], za[2 * i + 1]), b = f2(za[2 * i + 2], za[2 * i + 3]);
+            float2 c2 = f2(za[2 * i + 4], za[2 * i + 5]), d2 = f2(za[2 * i + 6], za[2 * i + 7]);
+            vA = __ffma2_rn(a, a, vA); vB = __ffma2_rn(b, b, vB); vC = __ffma2_rn(c2, c2, vC); vD = __ffma2_rn(d2, d2, vD);
+        }
+        tmem_ld_wait();
+#pragma unroll
+        for (int i = 0; i < 16; i += 4) {
+            float2 a = f2(zb[2 * i], zb[2 * i + 1]), b = f2(zb[2 * i + 2], zb[2 * i + 3]);
+            float2 c2 = f2(zb[2 * i + 4], zb[2 * i + 5]), d2 = f2(zb[2 * i + 6], zb[2 * i + 7]);
+            vA = __ffma2_rn(a, a, vA); vB = __ffma2_rn(b, b, vB); vC = __ffma2_rn(c2, c2, vC); vD = __ffma2_rn(d2, d2, vD);
+        }
+        vA = __fadd2_rn(__fadd2_rn(vA, vB), __fadd2_rn(vC, vD));
+        const float rstd = rsqrtf((vA.x + vA.y) * (1.0f / 64.0f) + HSG_LN_EPS);
+        const float2 rs = make_float2(rstd, rstd);
+#pragma unroll
+        for (int qt = 0; qt < 4; ++qt) {                  // z stays in registers: no second read of the accumulator
+            uint32_t up[8];
+#pragma unroll
+            for (int c = 0; c < 2; ++c) {
+                const float4 s0 = sreg[qt * 4 + 2 * c], s1 = sreg[qt * 4 + 2 * c + 1];
+                const float svv[8] = {s0.x, s0.y, s0.z, s0.w, s1.x, s1.y, s1.z, s1.w};
+#pragma unroll
+                for (int q = 0; q < 4; ++q) {
+                    const int col = (qt & 1) * 16 + c * 8 + 2 * q;
+                    const uint32_t z0 = qt < 2 ? za[col] : zb[col], z1 = qt < 2 ? za[col + 1] : zb[col + 1];
+                    float2 u = __ffma2_rn(f2(z0, z1), rs, make_float2(svv[2 * q], svv[2 * q + 1]));
+                    u = __fmul2_rn(u, u);
+                    up[c * 4 + q] = pack_h2(u.x, u.y);
+                }
+            }
+            tmem_st8(t_h + t_lane + qt * 8, up);
+        }
+        return;
+    }
+#endif
     float2 rs;
     {
         float2 vA = make_float2(0.f, 0.f), vB = vA, vC = vA, vD = vA;
