@@ -108,11 +108,15 @@ __device__ __forceinline__ void attn_ctx(const uint4* __restrict__ binVc, const 
 // ---- the three row-wise epilogues of a token (thread r <-> row r <-> TMEM lane r), packed fp32x2 math -----------------------
 // after MMA 1: rstd of y_c (columns [0, 64) of t_y), h = swish(rstd g + b0') -> fp16 A operand over the consumed g columns, plus
 // the constant K columns 64 / 65 = 1 that pick up the bias rows of the W1 / C0 images
-// HSG_EPI_PIPE = 1: the tensor-memory reads of the row epilogues are software-pipelined (the next tcgen05.ld is in flight while the
-// registers of the previous one are consumed; a tcgen05.ld x32 of a warp occupies the 64 B/clk read port for 64 cycles) and the u
-// epilogue keeps z in registers instead of reading it twice
+// HSG_EPI_PIPE bits (B200, C2, K2 ms per 225 M triplets; plain code 48.67):
+//   1 (default)  h epilogue: the next tcgen05.ld is in flight while the registers of the previous one are consumed (a tcgen05.ld
+//                x32 of a warp occupies the 64 B/clk tensor-memory read port for 64 cycles)                              48.24
+//   2            u epilogue keeps z in registers instead of reading it twice (z + S' = 128 live registers: spills)      50.7
+//   4            u epilogue two-pass with pipelined loads (with bit 1)                                                   48.6
+//   8            L1 prefetch of the S' row before the h epilogue (with bit 1)                                            49.1
+//   (-DHSG_K2_TANH2: packed tanh.approx.f16x2 in the h epilogue, with bit 1: 48.41)
 #ifndef HSG_EPI_PIPE
-#define HSG_EPI_PIPE 0
+#define HSG_EPI_PIPE 1
 #endif
 template <bool TANH2>
 __device__ __forceinline__ void epi_h_half(const uint32_t (&r)[32], const float2 rs, const int half, const uint32_t t_h, const uint32_t t_lane,
@@ -141,7 +145,7 @@ __device__ __forceinline__ void epi_h_half(const uint32_t (&r)[32], const float2
 
 template <bool TANH2>
 __device__ __forceinline__ void epi_h(const uint32_t t_y, const uint32_t t_h, const uint32_t t_lane, const float* cst) {
-#if HSG_EPI_PIPE
+#if HSG_EPI_PIPE & 1
     {
         uint32_t r0[32], r1[32], g0[32];
         tmem_ld32(t_y + t_lane, r0);
@@ -228,9 +232,22 @@ __device__ __forceinline__ void load_s_row(const Umma2Params& p, const int t, co
     }
 }
 
+// HSG_EPI_PIPE & 8: the S' row is pulled into L1 before the h epilogue, so that the loads issued behind MMA 2 are L1 hits
+__device__ __forceinline__ void prefetch_s_row(const Umma2Params& p, const int t, const int cell, const int2 pr) {
+    if (t == 0) {
+        const float4* Srow = p.cellSb + (size_t)cell * 16u;
+#pragma unroll
+        for (int c = 0; c < 16; c += 8) asm volatile("prefetch.global.L1 [%0];" ::"l"(Srow + c));
+    } else {
+        const float4* Scol = p.binSb + grp_off<16>((uint32_t)(t == 1 ? pr.x : pr.y));
+#pragma unroll
+        for (int c = 0; c < 16; ++c) asm volatile("prefetch.global.L1 [%0];" ::"l"(Scol + c * HSG_GRP));
+    }
+}
+
 // after MMA 2: z_c (centred by construction) -> rstd, u' = (z_c rstd + S')^2 -> fp16 A operand over the consumed h columns
 __device__ __forceinline__ void epi_u(const uint32_t t_y, const uint32_t t_h, const uint32_t t_lane, const float4 (&sreg)[16]) {
-#if HSG_EPI_PIPE
+#if HSG_EPI_PIPE & 2
     {
         uint32_t za[32], zb[32];
         tmem_ld32(t_y + t_lane, za);
@@ -271,6 +288,61 @@ __device__ __forceinline__ void epi_u(const uint32_t t_y, const uint32_t t_h, co
             }
             tmem_st8(t_h + t_lane + qt * 8, up);
         }
+        return;
+    }
+#endif
+#if HSG_EPI_PIPE & 4
+    {
+        // two passes over z as in the plain version (registers), every tcgen05.ld issued before the previous block is consumed
+        uint32_t za[32], zb[32];
+        tmem_ld32(t_y + t_lane, za);
+        tmem_ld_wait();
+        tmem_ld32(t_y + t_lane + 32, zb);
+        float2 vA = make_float2(0.f, 0.f), vB = vA, vC = vA, vD = vA;
+#pragma unroll
+        for (int i = 0; i < 16; i += 4) {
+            float2 a = f2(za[2 * i], za[2 * i + 1]), b = f2(za[2 * i + 2], za[2 * i + 3]);
+            float2 c2 = f2(za[2 * i + 4], za[2 * i + 5]), d2 = f2(za[2 * i + 6], za[2 * i + 7]);
+            vA = __ffma2_rn(a, a, vA); vB = __ffma2_rn(b, b, vB); vC = __ffma2_rn(c2, c2, vC); vD = __ffma2_rn(d2, d2, vD);
+        }
+        tmem_ld_wait();
+        uint32_t q0[16], q1[16];
+        tmem_ld16(t_y + t_lane, q0);                       // first 16 columns again: in flight during the second half of the variance
+#pragma unroll
+        for (int i = 0; i < 16; i += 4) {
+            float2 a = f2(zb[2 * i], zb[2 * i + 1]), b = f2(zb[2 * i + 2], zb[2 * i + 3]);
+            float2 c2 = f2(zb[2 * i + 4], zb[2 * i + 5]), d2 = f2(zb[2 * i + 6], zb[2 * i + 7]);
+            vA = __ffma2_rn(a, a, vA); vB = __ffma2_rn(b, b, vB); vC = __ffma2_rn(c2, c2, vC); vD = __ffma2_rn(d2, d2, vD);
+        }
+        vA = __fadd2_rn(__fadd2_rn(vA, vB), __fadd2_rn(vC, vD));
+        const float rstd = rsqrtf((vA.x + vA.y) * (1.0f / 64.0f) + HSG_LN_EPS);
+        const float2 rs = make_float2(rstd, rstd);
+        auto u_block = [&](const uint32_t (&r)[16], const int qt) {
+            uint32_t up[8];
+#pragma unroll
+            for (int c = 0; c < 2; ++c) {
+                const float4 s0 = sreg[qt * 4 + 2 * c], s1 = sreg[qt * 4 + 2 * c + 1];
+                const float svv[8] = {s0.x, s0.y, s0.z, s0.w, s1.x, s1.y, s1.z, s1.w};
+#pragma unroll
+                for (int q = 0; q < 4; ++q) {
+                    float2 u = __ffma2_rn(f2(r[c * 8 + 2 * q], r[c * 8 + 2 * q + 1]), rs, make_float2(svv[2 * q], svv[2 * q + 1]));
+                    u = __fmul2_rn(u, u);
+                    up[c * 4 + q] = pack_h2(u.x, u.y);
+                }
+            }
+            tmem_st8(t_h + t_lane + qt * 8, up);
+        };
+        tmem_ld_wait();
+        tmem_ld16(t_y + t_lane + 16, q1);
+        u_block(q0, 0);
+        tmem_ld_wait();
+        tmem_ld16(t_y + t_lane + 32, q0);
+        u_block(q1, 1);
+        tmem_ld_wait();
+        tmem_ld16(t_y + t_lane + 48, q1);
+        u_block(q0, 2);
+        tmem_ld_wait();
+        u_block(q1, 3);
         return;
     }
 #endif

@@ -311,7 +311,14 @@ __global__ void __launch_bounds__(512, 1) score_umma4_kernel(Umma4Params pp) {
                 if (more && !ABL(1)) weights(t < 2 ? cur : nxt, t < 2 ? t + 1 : 0, WA, WB);       // MMA 1 of token t is in flight
                 wait_mma();
                 if (t != 2) release_slot();                                    // MMA 1 has read the slot
+#if HSG_EPI_PIPE & 8
+                prefetch_s_row(p, t, cell, cur.pr);
+#endif
+#ifdef HSG_K2_TANH2
+                if (!ABL(8)) epi_h<true>(t_y, t_h, t_lane, cst);
+#else
                 if (!ABL(8)) epi_h<false>(t_y, t_h, t_lane, cst);
+#endif
                 request();                                                     // MMA 2
                 float4 sreg[16];
                 if (!ABL(4)) load_s_row(p, t, cell, cur.pr, sreg);
