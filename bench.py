@@ -451,7 +451,9 @@ def train_bench(args, rank, world, local, steps=None, want_cpu=True):
         n_steps = max(steps, 1)
         # device-timed leg: >= 2 s of steps, loss read back every 10th step
         l0 = eng.ctx.launch_count()
-        sampler = ClockSampler(local, period_ms=250) if uniform else None      # launch-bound step: poll the driver less often
+        # nvidia-smi polling takes the driver lock the launches need: at -lms 100 the launch-bound step ran 1.4x - 2.2x slower under
+        # it (measured: 0.83 -> 1.19 / 1.9 ms per step), so this leg is sampled once a second (>= 2 samples in its >= 2.5 s)
+        sampler = ClockSampler(local, period_ms=1000) if uniform else None
         if sampler:
             sampler.start()
         ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -463,7 +465,7 @@ def train_bench(args, rank, world, local, steps=None, want_cpu=True):
                 step(warm + done + i, (done + i) % 10 == 0)
             done += n_steps
             torch.cuda.synchronize()
-            enough = torch.tensor([1.0 if time.perf_counter() - t0 >= 2.0 else 0.0], device="cuda")
+            enough = torch.tensor([1.0 if time.perf_counter() - t0 >= 2.5 else 0.0], device="cuda")
             if world > 1:
                 dist.all_reduce(enough, op=dist.ReduceOp.MIN)
             if enough.item() > 0 or done >= 200 * n_steps:
