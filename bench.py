@@ -580,36 +580,55 @@ def c3_strong(args, rank, world, local):
     import torch
     import torch.distributed as dist
     from higashi_b200 import engine as E, parallel, synthetic as S
-    n_glob, k = S.CONFIGS["C3"]["n_cells"], S.CONFIGS["C3"]["k"]
-    nbr_g, w_g = knn_lists(types.SimpleNamespace(n_cells=n_glob), k, 4242)          # the same graph on every rank
-    c0, c1 = parallel.cell_shards(n_glob, world)[rank]
-    own = np.arange(c0, c1)
-    local_cells = np.unique(np.concatenate([own, (nbr_g[own] - 1).reshape(-1)]))
-    t_gen = time.perf_counter()
-    ds = S.make_dataset_cells("C3", local_cells, threads=max(2, min(16, (os.cpu_count() or 8) // max(world, 1))))
-    t_gen = time.perf_counter() - t_gen
-    g2l = np.full(n_glob, -1, dtype=np.int64)
-    g2l[local_cells] = np.arange(len(local_cells))
-    nbr_l = np.repeat(np.arange(1, len(local_cells) + 1, dtype=np.int64)[:, None], k + 1, axis=1)     # halo cells: themselves only
-    w_l = np.zeros((len(local_cells), k + 1), dtype=np.float32)
-    w_l[:, 0] = 1.0
-    nbr_l[g2l[own]] = g2l[nbr_g[own] - 1] + 1
-    w_l[g2l[own]] = w_g[own]
-    l0 = int(g2l[c0])
-    assert np.array_equal(g2l[own], np.arange(l0, l0 + len(own)))                    # own cells stay contiguous
-    sd, feats = S.random_state_dict(ds, ds.d, seed=0)
-    eng = E.ScorerEngine(local)
-    eng.load_model(sd, ds.num, feats=feats, cell_feats=ds.cell_feats)
-    P = eng.set_pairs(list(range(len(ds.bins))), ds.min_bin, ds.max_bin)
-    pin = lambda a: torch.from_numpy(np.ascontiguousarray(a)).pin_memory()
-    h_rowptr, h_col, h_val = pin(ds.csr.row_ptr), pin(ds.csr.col), pin(ds.csr.val)
-    eng.ctx.set_contacts(h_rowptr.numpy(), h_col.numpy(), h_val.numpy())
-    eng.set_neighbors(nbr_l, w_l)
-    eng.prepare(getattr(E, "DEFAULT_PRECISION", E.PREC_TC16), 0, E.ACT_SIGMOID)
-    cps = 250
-    out = torch.empty((cps, P), dtype=torch.float32, device="cuda")
-    stream = torch.cuda.current_stream()
-    chunks = [(a, min(a + cps, l0 + len(own))) for a in range(l0, l0 + len(own), cps)]
+    def setup():
+        n_glob, k = S.CONFIGS["C3"]["n_cells"], S.CONFIGS["C3"]["k"]
+        nbr_g, w_g = knn_lists(types.SimpleNamespace(n_cells=n_glob), k, 4242)          # the same graph on every rank
+        c0, c1 = parallel.cell_shards(n_glob, world)[rank]
+        own = np.arange(c0, c1)
+        local_cells = np.unique(np.concatenate([own, (nbr_g[own] - 1).reshape(-1)]))
+        t_gen = time.perf_counter()
+        ds = S.make_dataset_cells("C3", local_cells, threads=max(2, min(16, (os.cpu_count() or 8) // max(world, 1))))
+        t_gen = time.perf_counter() - t_gen
+        g2l = np.full(n_glob, -1, dtype=np.int64)
+        g2l[local_cells] = np.arange(len(local_cells))
+        nbr_l = np.repeat(np.arange(1, len(local_cells) + 1, dtype=np.int64)[:, None], k + 1, axis=1)     # halo cells: themselves only
+        w_l = np.zeros((len(local_cells), k + 1), dtype=np.float32)
+        w_l[:, 0] = 1.0
+        nbr_l[g2l[own]] = g2l[nbr_g[own] - 1] + 1
+        w_l[g2l[own]] = w_g[own]
+        l0 = int(g2l[c0])
+        assert np.array_equal(g2l[own], np.arange(l0, l0 + len(own)))                    # own cells stay contiguous
+        sd, feats = S.random_state_dict(ds, ds.d, seed=0)
+        eng = E.ScorerEngine(local)
+        eng.load_model(sd, ds.num, feats=feats, cell_feats=ds.cell_feats)
+        P = eng.set_pairs(list(range(len(ds.bins))), ds.min_bin, ds.max_bin)
+        pin = lambda a: torch.from_numpy(np.ascontiguousarray(a)).pin_memory()
+        h_rowptr, h_col, h_val = pin(ds.csr.row_ptr), pin(ds.csr.col), pin(ds.csr.val)
+        eng.ctx.set_contacts(h_rowptr.numpy(), h_col.numpy(), h_val.numpy())
+        eng.set_neighbors(nbr_l, w_l)
+        eng.prepare(getattr(E, "DEFAULT_PRECISION", E.PREC_TC16), 0, E.ACT_SIGMOID)
+        cps = 250
+        out = torch.empty((cps, P), dtype=torch.float32, device="cuda")
+        stream = torch.cuda.current_stream()
+        chunks = [(a, min(a + cps, l0 + len(own))) for a in range(l0, l0 + len(own), cps)]
+        return n_glob, k, own, local_cells, t_gen, ds, l0, eng, P, h_rowptr, h_col, h_val, cps, out, stream, chunks
+
+    # a rank that fails while it builds its shard must not leave the others waiting in a barrier: every rank reports, all agree
+    err, st = None, None
+    try:
+        st = setup()
+    except Exception as e:                                                            # noqa: BLE001
+        err = repr(e)
+    if world > 1:
+        flag = torch.tensor([0.0 if err else 1.0], device="cuda")
+        dist.all_reduce(flag, op=dist.ReduceOp.MIN)
+        if flag.item() < 1.0:
+            if st is not None:
+                st[7].close()
+            return {"error": err or "another rank failed while building its C3 shard"}
+    elif err:
+        return {"error": err}
+    n_glob, k, own, local_cells, t_gen, ds, l0, eng, P, h_rowptr, h_col, h_val, cps, out, stream, chunks = st
 
     def barrier():
         torch.cuda.synchronize()
