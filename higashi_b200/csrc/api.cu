@@ -651,7 +651,9 @@ extern "C" int hsg_prepare(hsg_ctx* c, int precision, int local_transfer_range, 
                 HSG_CUDA(cudaStreamSynchronize(c->stream));
                 dev_free(dF);
                 std::vector<int> tiles;
-                build_tiles4(c->h_pairs.data(), c->P, tiles);       // host copy of the pair list kept by hsg_set_pairs
+                // host copy of the pair list kept by hsg_set_pairs; dense tiles for the short rows at chromosome ends: generation 4 only
+                static const bool no_dense = getenv("HSG_K2_DENSE_TILES") && getenv("HSG_K2_DENSE_TILES")[0] == '0';
+                build_tiles4(c->h_pairs.data(), c->P, tiles, c->k2gen == 4 && !no_dense);
                 c->n_tiles4 = (int)(tiles.size() / 8);
                 if (dev_alloc(&c->tiles4, tiles.size())) return 1;
                 HSG_CUDA(cudaMemcpy(c->tiles4, tiles.data(), tiles.size() * sizeof(int), cudaMemcpyHostToDevice));

@@ -187,7 +187,7 @@ int umma128_cst_count();
 int umma128_gain_foldable(const float* ln1_g);
 int launch_score_pairs_umma5(hsg_ctx* c, int cell_start, int n_cells_batch, float* out, void* out16, cudaStream_t s);
 int launch_build_ptable(hsg_ctx* c, const float* V, const float* F, long long rows, void* P, cudaStream_t s);
-void build_tiles4(const int2* pairs, long long P, std::vector<int>& out);
+void build_tiles4(const int2* pairs, long long P, std::vector<int>& out, bool allow_dense);
 int umma_build_weights(const float* fc1, const float* w0, const float* b0, const float* pff_g, const float* pff_b,
                        const float* w1, const float* b1, const float* ln1_g, const float* c0, const float* cb0,
                        const float* cw1, const float* cb1, int hi, int natural_k, unsigned char* wimg_host, float* cst_host, float* comb_out = nullptr);

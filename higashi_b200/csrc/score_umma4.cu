@@ -63,6 +63,8 @@ struct TileRow4 {
     int cb; long long pi; bool valid; int2 pr; float bias;
     int seg;                 // segment of this row inside its tile (0..2)
     int bi0, bi1, bi2;       // bin_i of the tile's segments (unused ones repeat segment 0)
+    bool dense;              // tile with more than three segments (the short rows at the end of a chromosome): no segment slots,
+                             // both bin terms of every token go through the varying ctx operand (all three tokens take a slot)
 };
 
 // softmax weights of a row as two chunks of 8 halves: WA = w_a[0..7], WB = w_b[0..7] (same arithmetic as attn_weights)
@@ -91,6 +93,27 @@ __device__ __forceinline__ void ctx_var_tmem(const uint4* __restrict__ binVc, co
             const uint4 b = __ldg(vb + c * HSG_GRP);
             o[cc * 4 + 0] = h2u(__hmul2(wb2, u2h(b.x))); o[cc * 4 + 1] = h2u(__hmul2(wb2, u2h(b.y)));
             o[cc * 4 + 2] = h2u(__hmul2(wb2, u2h(b.z))); o[cc * 4 + 3] = h2u(__hmul2(wb2, u2h(b.w)));
+        }
+        tmem_st16(t_a + (uint32_t)c4 * 16u, o);
+    }
+}
+
+// dense tiles: ctx_var = w_a (.) V[x] + w_b (.) V[y]  (token 0: x = bin_i, y = bin_j) -> the 64 TMEM columns of an A slot
+__device__ __forceinline__ void ctx_var2_tmem(const uint4* __restrict__ binVc, const uint32_t bx, const uint32_t by, const uint32_t t_a,
+                                              const uint32_t (&WA)[4], const uint32_t (&WB)[4]) {
+    const uint4* va = binVc + grp_off<16>(bx);
+    const uint4* vb = binVc + grp_off<16>(by);
+#pragma unroll
+    for (int c4 = 0; c4 < 4; ++c4) {
+        uint32_t o[16];
+#pragma unroll
+        for (int cc = 0; cc < 4; ++cc) {
+            const int c = c4 * 4 + cc, h = c >> 1;
+            const __half2 wa2 = (h & 1) ? __high2half2(u2h(WA[h >> 1])) : __low2half2(u2h(WA[h >> 1]));
+            const __half2 wb2 = (h & 1) ? __high2half2(u2h(WB[h >> 1])) : __low2half2(u2h(WB[h >> 1]));
+            const uint4 a = __ldg(va + c * HSG_GRP), b = __ldg(vb + c * HSG_GRP);
+            o[cc * 4 + 0] = h2u(__hfma2(wb2, u2h(b.x), __hmul2(wa2, u2h(a.x)))); o[cc * 4 + 1] = h2u(__hfma2(wb2, u2h(b.y), __hmul2(wa2, u2h(a.y))));
+            o[cc * 4 + 2] = h2u(__hfma2(wb2, u2h(b.z), __hmul2(wa2, u2h(a.z)))); o[cc * 4 + 3] = h2u(__hfma2(wb2, u2h(b.w), __hmul2(wa2, u2h(a.w))));
         }
         tmem_st16(t_a + (uint32_t)c4 * 16u, o);
     }
@@ -135,6 +158,7 @@ __global__ void __launch_bounds__(512, 1) score_umma4_kernel(Umma4Params pp) {
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + U4_SM_TMEM);
     volatile int* slot_owner = reinterpret_cast<volatile int*>(smem + U4_SM_SLOT);       // [2]: -1 free, else the owning warpgroup
     volatile int* slot_of = slot_owner + 2;                                             // [U4_WG]: the slot a warpgroup holds
+    volatile int* tile_dense = slot_of + U4_WG;                                         // [U4_WG]: MMA 1 of the token just requested has a K = 128 part for token 2 too
 
     if (tid == 0) {
         mbar_init(bar_w, 1);
@@ -181,12 +205,13 @@ __global__ void __launch_bounds__(512, 1) score_umma4_kernel(Umma4Params pp) {
 #pragma unroll 1
                 for (int t = 0; t < 3; ++t) {
                     named_bar_sync(5 + sw, 160); tc_fence_after();                        // ctx_var / weight slots / P images complete
-                    if (t != 2) {
+                    const bool has_var = t != 2 || __shfl_sync(0xffffffffu, tile_dense[sw], 0) != 0;      // (warp-uniform)
+                    if (has_var) {
                         const uint32_t s_a = tb + 384u + 64u * (uint32_t)__shfl_sync(0xffffffffu, slot_of[sw], 0);
                         if (lead) mma_group_ts<8, 128>(s_a, sbase + SMF_B_FC1, 128, s_ty, 0u);
                     }
                     if (lead) {
-                        umma_f16(s_ty, umma_desc(s_aw), umma_desc(s_aw + 64u), idesc1, (t != 2) ? 1u : 0u);
+                        umma_f16(s_ty, umma_desc(s_aw), umma_desc(s_aw + 64u), idesc1, has_var ? 1u : 0u);
                         umma_f16(s_ty, umma_desc(s_aw + 32u), umma_desc(s_aw + 96u), idesc1, 1u);
                         umma_commit(s_bar);
                     }
@@ -234,7 +259,7 @@ __global__ void __launch_bounds__(512, 1) score_umma4_kernel(Umma4Params pp) {
         HSG_DASSERT(pt >= 0 && pt < pp.n_tiles_cell && ta.y >= 1 && ta.y <= 128 && (long long)ta.x + ta.y <= p.P);
         HSG_DASSERT(tr.pr.x >= 0 && tr.pr.x < p.n_bins && tr.pr.y >= 0 && tr.pr.y < p.n_bins);
         HSG_DASSERT(tb4.x >= 0 && tb4.x < p.n_bins && tb4.y >= 0 && tb4.y < p.n_bins && tb4.z >= 0 && tb4.z < p.n_bins);
-        tr.bi0 = tb4.x; tr.bi1 = tb4.y; tr.bi2 = tb4.z;
+        tr.bi0 = tb4.x; tr.bi1 = tb4.y; tr.bi2 = tb4.z; tr.dense = tb4.w != 0;
         return tr;
     };
     auto weights = [&](const TileRow4& tr, int tk, uint32_t (&WA)[4], uint32_t (&WB)[4]) {
@@ -267,12 +292,13 @@ __global__ void __launch_bounds__(512, 1) score_umma4_kernel(Umma4Params pp) {
             else if (tk == 2) { s0 = WB[0]; s1 = WB[1]; s2 = WB[2]; s3 = WB[3]; }
 #pragma unroll
             for (int s = 0; s < 3; ++s) {
-                const bool on = tr.seg == s;
+                const bool on = tr.seg == s && !tr.dense;
                 sts_chunk(1 + s, on ? s0 : 0u, on ? s1 : 0u, on ? s2 : 0u, on ? s3 : 0u);
             }
         }
         fence_async_smem();
-        if (tk != 2) {
+        if (wtid == 0) tile_dense[wg] = tr.dense ? 1 : 0;
+        if (tk != 2 || tr.dense) {                                  // (warpgroup-uniform)
             if (wtid == 0) {
                 int sl = -1;
                 while (sl < 0) {
@@ -285,7 +311,10 @@ __global__ void __launch_bounds__(512, 1) score_umma4_kernel(Umma4Params pp) {
             }
             wg_bar(wg);
             tc_fence_after();                // the previous owner's MMA 1 (its reads of the slot) completed before it released
-            if (!ABL(2)) ctx_var_tmem(p.binVc, (uint32_t)tr.pr.y, tmem_base + 384u + 64u * (uint32_t)slot_of[wg] + t_lane, WB);
+            const uint32_t t_slot = tmem_base + 384u + 64u * (uint32_t)slot_of[wg] + t_lane;
+            if (!tr.dense) { if (!ABL(2)) ctx_var_tmem(p.binVc, (uint32_t)tr.pr.y, t_slot, WB); }
+            else if (tk == 0) ctx_var2_tmem(p.binVc, (uint32_t)tr.pr.x, (uint32_t)tr.pr.y, t_slot, WA, WB);      // attends bin_i (w_a), bin_j (w_b)
+            else ctx_var_tmem(p.binVc, (uint32_t)(tk == 1 ? tr.pr.y : tr.pr.x), t_slot, WB);                     // cell through its slot; bin_j / bin_i here
         }
     };
     auto request = [&]() { tmem_st_wait(); tc_fence_before(); named_bar_arrive(5 + wg, 160); };
@@ -310,7 +339,7 @@ __global__ void __launch_bounds__(512, 1) score_umma4_kernel(Umma4Params pp) {
                 const bool more = t < 2 || has_next;
                 if (more && !ABL(1)) weights(t < 2 ? cur : nxt, t < 2 ? t + 1 : 0, WA, WB);       // MMA 1 of token t is in flight
                 wait_mma();
-                if (t != 2) release_slot();                                    // MMA 1 has read the slot
+                if (t != 2 || cur.dense) release_slot();                       // MMA 1 has read the slot
 #if HSG_EPI_PIPE & 8
                 prefetch_s_row(p, t, cell, cur.pr);
 #endif
@@ -354,9 +383,13 @@ __global__ void __launch_bounds__(512, 1) score_umma4_kernel(Umma4Params pp) {
 // host side
 // ---------------------------------------------------------------------------------------------
 // Tile table of a pair list in generate_binpair order: greedy runs of at most 128 consecutive pairs with at most three distinct
-// bin_i (a new segment starts where bin_i changes).  Entry = (p0, cnt, s1, s2), (bin_i of segment 0, 1, 2, 0); rows [0, s1) are
+// bin_i (a new segment starts where bin_i changes).  Entry = (p0, cnt, s1, s2), (bin_i of segment 0, 1, 2, dense); rows [0, s1) are
 // segment 0, [s1, s2) segment 1, [s2, cnt) segment 2; unused segments start at 128 and repeat bin_i of segment 0.
-void build_tiles4(const int2* pairs, long long P, std::vector<int>& out) {
+// The rows at the end of a chromosome are short (row i of n bins has n - i - 1 pairs): three of them fill a fraction of a tile (C2:
+// 1904 tiles per cell for 1758 full ones, 8 % of the rows idle).  With `allow_dense`, a run whose three-segment prefix would leave
+// more than 16 rows idle becomes a DENSE tile instead: 128 pairs whatever their bin_i, flagged in the last field; the kernel then
+// sends both bin terms of every token through the varying ctx operand (no segment slots).
+void build_tiles4(const int2* pairs, long long P, std::vector<int>& out, bool allow_dense) {
     out.clear();
     long long p0 = 0;
     while (p0 < P) {
@@ -370,7 +403,13 @@ void build_tiles4(const int2* pairs, long long P, std::vector<int>& out) {
             }
             ++cnt;
         }
-        const int e[8] = {(int)p0, cnt, s[1], s[2], bi[0], bi[1], bi[2], 0};
+        int dense = 0;
+        if (allow_dense && cnt < 112 && p0 + cnt < P) {             // cut short by the segment limit, not by the end of the list
+            cnt = (int)std::min<long long>(128, P - p0);
+            s[1] = s[2] = 128; bi[1] = bi[2] = bi[0];
+            dense = 1;
+        }
+        const int e[8] = {(int)p0, cnt, s[1], s[2], bi[0], bi[1], bi[2], dense};
         out.insert(out.end(), e, e + 8);
         p0 += cnt;
     }
