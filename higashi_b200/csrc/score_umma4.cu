@@ -63,8 +63,9 @@ struct TileRow4 {
     int cb; long long pi; bool valid; int2 pr; float bias;
     int seg;                 // segment of this row inside its tile (0..2)
     int bi0, bi1, bi2;       // bin_i of the tile's segments (unused ones repeat segment 0)
-    bool dense;              // tile with more than three segments (the short rows at the end of a chromosome): no segment slots,
-                             // both bin terms of every token go through the varying ctx operand (all three tokens take a slot)
+    // seg == 3 for every row of a DENSE tile (more than three segments: the short rows at the end of a chromosome): no segment
+    // slot matches, both bin terms of every token go through the varying ctx operand (all three tokens take a slot)
+    __device__ __forceinline__ bool dense() const { return seg == 3; }
 };
 
 // softmax weights of a row as two chunks of 8 halves: WA = w_a[0..7], WB = w_b[0..7] (same arithmetic as attn_weights)
@@ -161,7 +162,6 @@ __global__ void __launch_bounds__(512, 1) score_umma4_kernel(Umma4Params pp) {
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + U4_SM_TMEM);
     volatile int* slot_owner = reinterpret_cast<volatile int*>(smem + U4_SM_SLOT);       // [2]: -1 free, else the owning warpgroup
     volatile int* slot_of = slot_owner + 2;                                             // [U4_WG]: the slot a warpgroup holds
-    volatile int* tile_dense = slot_of + U4_WG;                                         // [U4_WG]: MMA 1 of the token just requested has a K = 128 part for token 2 too
 
     if (tid == 0) {
         mbar_init(bar_w, 1);
@@ -205,10 +205,14 @@ __global__ void __launch_bounds__(512, 1) score_umma4_kernel(Umma4Params pp) {
             long long n_tile_own = 0;
             for (long long q = blockIdx.x; q < n_quads; q += gridDim.x) ++n_tile_own;
             for (long long i = 0; i < n_tile_own; ++i) {
+                // dense tile (flag in the tile table): token 2 has a K = 128 part too
+                const long long tile_i = ((long long)blockIdx.x + i * gridDim.x) * nwg + sw;
+                const long long tile_c = tile_i < n_tiles ? tile_i : n_tiles - 1;           // (a warpgroup past the end re-runs the last tile, unstored)
+                const int dense_i = __ldg(reinterpret_cast<const int*>(pp.tiles + 2 * (int)(tile_c % pp.n_tiles_cell) + 1) + 3);
 #pragma unroll 1
                 for (int t = 0; t < 3; ++t) {
                     named_bar_sync(5 + sw, 160); tc_fence_after();                        // ctx_var / weight slots / P images complete
-                    const bool has_var = t != 2 || __shfl_sync(0xffffffffu, tile_dense[sw], 0) != 0;      // (warp-uniform)
+                    const bool has_var = t != 2 || dense_i != 0;                                   // (warp-uniform)
                     if (has_var) {
                         const uint32_t s_a = tb + 384u + 64u * (uint32_t)__shfl_sync(0xffffffffu, slot_of[sw], 0);
                         if (lead) mma_group_ts<8, 128>(s_a, sbase + SMF_B_FC1, 128, s_ty, 0u);
@@ -258,11 +262,11 @@ __global__ void __launch_bounds__(512, 1) score_umma4_kernel(Umma4Params pp) {
         tr.valid = tile_ok && wtid < ta.y;
         tr.pr = __ldg(p.pairs + (wtid < ta.y ? tr.pi : (long long)ta.x + ta.y - 1));
         tr.bias = tr.valid ? __ldg(p.pair_bias + tr.pi) : 0.f;
-        tr.seg = (wtid >= ta.z ? 1 : 0) + (wtid >= ta.w ? 1 : 0);
+        tr.seg = (wtid >= ta.z ? 1 : 0) + (wtid >= ta.w ? 1 : 0) + tb4.w;          // dense tile: s1 = s2 = 0 and flag 1 -> 3
         HSG_DASSERT(pt >= 0 && pt < pp.n_tiles_cell && ta.y >= 1 && ta.y <= 128 && (long long)ta.x + ta.y <= p.P);
         HSG_DASSERT(tr.pr.x >= 0 && tr.pr.x < p.n_bins && tr.pr.y >= 0 && tr.pr.y < p.n_bins);
         HSG_DASSERT(tb4.x >= 0 && tb4.x < p.n_bins && tb4.y >= 0 && tb4.y < p.n_bins && tb4.z >= 0 && tb4.z < p.n_bins);
-        tr.bi0 = tb4.x; tr.bi1 = tb4.y; tr.bi2 = tb4.z; tr.dense = tb4.w != 0;
+        tr.bi0 = tb4.x; tr.bi1 = tb4.y; tr.bi2 = tb4.z;
         return tr;
     };
     auto weights = [&](const TileRow4& tr, int tk, uint32_t (&WA)[4], uint32_t (&WB)[4]) {
@@ -295,13 +299,12 @@ __global__ void __launch_bounds__(512, 1) score_umma4_kernel(Umma4Params pp) {
             else if (tk == 2) { s0 = WB[0]; s1 = WB[1]; s2 = WB[2]; s3 = WB[3]; }
 #pragma unroll
             for (int s = 0; s < 3; ++s) {
-                const bool on = tr.seg == s && !tr.dense;
+                const bool on = tr.seg == s;
                 sts_chunk(1 + s, on ? s0 : 0u, on ? s1 : 0u, on ? s2 : 0u, on ? s3 : 0u);
             }
         }
         fence_async_smem();
-        if (wtid == 0) tile_dense[wg] = tr.dense ? 1 : 0;
-        if (tk != 2 || tr.dense) {                                  // (warpgroup-uniform)
+        if (tk != 2 || tr.dense()) {                                // (warpgroup-uniform)
             if (wtid == 0) {
                 int sl = -1;
                 while (sl < 0) {
@@ -317,9 +320,9 @@ __global__ void __launch_bounds__(512, 1) score_umma4_kernel(Umma4Params pp) {
             const uint32_t t_slot = tmem_base + 384u + 64u * (uint32_t)slot_of[wg] + t_lane;
             // dense tile: token 0 attends bin_i (w_a) and bin_j (w_b) through the operand; tokens 1 / 2 the cell through its slot and
             // bin_j / bin_i here
-            if (tr.dense && tk == 0)
+            if (tr.dense() && tk == 0)
                 ctx_var2_tmem(p.binVc, (uint32_t)tr.pr.x, (uint32_t)tr.pr.y, t_slot, make_uint4(WA[0], WA[1], WA[2], WA[3]), make_uint4(WB[0], WB[1], WB[2], WB[3]));
-            else if (!ABL(2)) ctx_var_tmem(p.binVc, (uint32_t)((tr.dense && tk == 2) ? tr.pr.x : tr.pr.y), t_slot, WB);
+            else if (!ABL(2)) ctx_var_tmem(p.binVc, (uint32_t)((tr.dense() && tk == 2) ? tr.pr.x : tr.pr.y), t_slot, WB);
         }
     };
     auto request = [&]() { tmem_st_wait(); tc_fence_before(); named_bar_arrive(5 + wg, 160); };
@@ -344,7 +347,7 @@ __global__ void __launch_bounds__(512, 1) score_umma4_kernel(Umma4Params pp) {
                 const bool more = t < 2 || has_next;
                 if (more && !ABL(1)) weights(t < 2 ? cur : nxt, t < 2 ? t + 1 : 0, WA, WB);       // MMA 1 of token t is in flight
                 wait_mma();
-                if (t != 2 || cur.dense) release_slot();                       // MMA 1 has read the slot
+                if (t != 2 || cur.dense()) release_slot();                       // MMA 1 has read the slot
 #if HSG_EPI_PIPE & 8
                 prefetch_s_row(p, t, cell, cur.pr);
 #endif
@@ -411,7 +414,7 @@ void build_tiles4(const int2* pairs, long long P, std::vector<int>& out, bool al
         int dense = 0;
         if (allow_dense && cnt < 112 && p0 + cnt < P) {             // cut short by the segment limit, not by the end of the list
             cnt = (int)std::min<long long>(128, P - p0);
-            s[1] = s[2] = 128; bi[1] = bi[2] = bi[0];
+            s[1] = s[2] = 0; bi[1] = bi[2] = bi[0];            // every row gets segment index 1 + 1 + flag = 3 in the kernel
             dense = 1;
         }
         const int e[8] = {(int)p0, cnt, s[1], s[2], bi[0], bi[1], bi[2], dense};
