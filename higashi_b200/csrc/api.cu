@@ -652,8 +652,16 @@ extern "C" int hsg_prepare(hsg_ctx* c, int precision, int local_transfer_range, 
                 dev_free(dF);
                 std::vector<int> tiles;
                 // host copy of the pair list kept by hsg_set_pairs; dense tiles for the short rows at chromosome ends: generation 4 only
-                static const bool no_dense = getenv("HSG_K2_DENSE_TILES") && getenv("HSG_K2_DENSE_TILES")[0] == '0';
-                build_tiles4(c->h_pairs.data(), c->P, tiles, c->k2gen == 4 && !no_dense);
+                // (they pay when they remove more than ~4 % of the tiles -- C2: 1904 -> 1762 per cell; on C3 / C5 the tails are a
+                //  small share and the kernel instantiation without the dense-tile code is the faster one)
+                const char* dt = getenv("HSG_K2_DENSE_TILES");
+                build_tiles4(c->h_pairs.data(), c->P, tiles, false);
+                c->k2_dense_tiles = false;
+                if (c->k2gen == 4 && !(dt && dt[0] == '0')) {
+                    std::vector<int> tiles_d;
+                    build_tiles4(c->h_pairs.data(), c->P, tiles_d, true);
+                    if ((dt && dt[0] == '1') || (double)tiles_d.size() <= 0.96 * (double)tiles.size()) { tiles.swap(tiles_d); c->k2_dense_tiles = true; }
+                }
                 c->n_tiles4 = (int)(tiles.size() / 8);
                 if (dev_alloc(&c->tiles4, tiles.size())) return 1;
                 HSG_CUDA(cudaMemcpy(c->tiles4, tiles.data(), tiles.size() * sizeof(int), cudaMemcpyHostToDevice));

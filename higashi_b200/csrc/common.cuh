@@ -146,7 +146,7 @@ struct hsg_ctx {
     unsigned char* pj_wimg = nullptr; float h_pj_cst[384] = {0}; bool use_proj_umma = false;   // tensor-core K1b (project_umma.cu)
     bool use_umma = false;
     // generation 4 of the fast scorer (score_umma4.cu): tile table of the pair list, P tables of the bins and cells
-    int* tiles4 = nullptr; int n_tiles4 = 0; void* binP = nullptr; void* cellP = nullptr; bool k2v4 = false; int k2gen = 4;
+    int* tiles4 = nullptr; int n_tiles4 = 0; void* binP = nullptr; void* cellP = nullptr; bool k2v4 = false; int k2gen = 4; bool k2_dense_tiles = false;
     bool k2d128 = false;                     // d_model = 128 runs score_umma128.cu (chunk-major tables of score_umma2.cu, 32 S' quads per row)
     bool k2v2 = false;                       // fast tensor-core variant runs score_umma2.cu: chunk-major QK16 / XS / binV16 tables
     bool umma_hi = false;                    // high-accuracy tensor-core variant (fp32 tables, hi/lo operand splits)

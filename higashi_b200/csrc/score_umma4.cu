@@ -150,6 +150,10 @@ __global__ void build_ptable_kernel(const float* __restrict__ V, const float* __
     reinterpret_cast<uint4*>(P)[x * 128 + n] = make_uint4(o[0], o[1], o[2], o[3]);
 }
 
+// DENSE: the tile table may hold dense tiles (see build_tiles4).  A second instantiation rather than a run-time flag: the mere
+// presence of the dense-tile code costs the plain tiles ~3 % (B200: C3 45.1 -> 46.7 ms per 250 cells), so pair sets whose
+// chromosome tails are a small share of the tiles (C3, C5) keep the kernel without it.
+template <bool DENSE>
 __global__ void __launch_bounds__(512, 1) score_umma4_kernel(Umma4Params pp) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const Umma2Params& p = pp.b;
@@ -208,11 +212,12 @@ __global__ void __launch_bounds__(512, 1) score_umma4_kernel(Umma4Params pp) {
                 // dense tile (flag in the tile table): token 2 has a K = 128 part too
                 const long long tile_i = ((long long)blockIdx.x + i * gridDim.x) * nwg + sw;
                 const long long tile_c = tile_i < n_tiles ? tile_i : n_tiles - 1;           // (a warpgroup past the end re-runs the last tile, unstored)
-                const int dense_i = __ldg(reinterpret_cast<const int*>(pp.tiles + 2 * (int)(tile_c % pp.n_tiles_cell) + 1) + 3);
+                int dense_i = 0;
+                if constexpr (DENSE) dense_i = __ldg(reinterpret_cast<const int*>(pp.tiles + 2 * (int)(tile_c % pp.n_tiles_cell) + 1) + 3);
 #pragma unroll 1
                 for (int t = 0; t < 3; ++t) {
                     named_bar_sync(5 + sw, 160); tc_fence_after();                        // ctx_var / weight slots / P images complete
-                    const bool has_var = t != 2 || dense_i != 0;                                   // (warp-uniform)
+                    const bool has_var = t != 2 || (DENSE && dense_i != 0);                        // (warp-uniform)
                     if (has_var) {
                         const uint32_t s_a = tb + 384u + 64u * (uint32_t)__shfl_sync(0xffffffffu, slot_of[sw], 0);
                         if (lead) mma_group_ts<8, 128>(s_a, sbase + SMF_B_FC1, 128, s_ty, 0u);
@@ -262,7 +267,8 @@ __global__ void __launch_bounds__(512, 1) score_umma4_kernel(Umma4Params pp) {
         tr.valid = tile_ok && wtid < ta.y;
         tr.pr = __ldg(p.pairs + (wtid < ta.y ? tr.pi : (long long)ta.x + ta.y - 1));
         tr.bias = tr.valid ? __ldg(p.pair_bias + tr.pi) : 0.f;
-        tr.seg = (wtid >= ta.z ? 1 : 0) + (wtid >= ta.w ? 1 : 0) + tb4.w;          // dense tile: s1 = s2 = 0 and flag 1 -> 3
+        tr.seg = (wtid >= ta.z ? 1 : 0) + (wtid >= ta.w ? 1 : 0);
+        if constexpr (DENSE) tr.seg += tb4.w;                                   // dense tile: s1 = s2 = 0 and flag 1 -> 3
         HSG_DASSERT(pt >= 0 && pt < pp.n_tiles_cell && ta.y >= 1 && ta.y <= 128 && (long long)ta.x + ta.y <= p.P);
         HSG_DASSERT(tr.pr.x >= 0 && tr.pr.x < p.n_bins && tr.pr.y >= 0 && tr.pr.y < p.n_bins);
         HSG_DASSERT(tb4.x >= 0 && tb4.x < p.n_bins && tb4.y >= 0 && tb4.y < p.n_bins && tb4.z >= 0 && tb4.z < p.n_bins);
@@ -304,7 +310,7 @@ __global__ void __launch_bounds__(512, 1) score_umma4_kernel(Umma4Params pp) {
             }
         }
         fence_async_smem();
-        if (tk != 2 || tr.dense()) {                                // (warpgroup-uniform)
+        if (tk != 2 || (DENSE && tr.dense())) {                     // (warpgroup-uniform)
             if (wtid == 0) {
                 int sl = -1;
                 while (sl < 0) {
@@ -320,9 +326,13 @@ __global__ void __launch_bounds__(512, 1) score_umma4_kernel(Umma4Params pp) {
             const uint32_t t_slot = tmem_base + 384u + 64u * (uint32_t)slot_of[wg] + t_lane;
             // dense tile: token 0 attends bin_i (w_a) and bin_j (w_b) through the operand; tokens 1 / 2 the cell through its slot and
             // bin_j / bin_i here
-            if (tr.dense() && tk == 0)
-                ctx_var2_tmem(p.binVc, (uint32_t)tr.pr.x, (uint32_t)tr.pr.y, t_slot, make_uint4(WA[0], WA[1], WA[2], WA[3]), make_uint4(WB[0], WB[1], WB[2], WB[3]));
-            else if (!ABL(2)) ctx_var_tmem(p.binVc, (uint32_t)((tr.dense() && tk == 2) ? tr.pr.x : tr.pr.y), t_slot, WB);
+            if constexpr (DENSE) {
+                if (tr.dense() && tk == 0)
+                    ctx_var2_tmem(p.binVc, (uint32_t)tr.pr.x, (uint32_t)tr.pr.y, t_slot, make_uint4(WA[0], WA[1], WA[2], WA[3]), make_uint4(WB[0], WB[1], WB[2], WB[3]));
+                else if (!ABL(2)) ctx_var_tmem(p.binVc, (uint32_t)((tr.dense() && tk == 2) ? tr.pr.x : tr.pr.y), t_slot, WB);
+            } else {
+                if (!ABL(2)) ctx_var_tmem(p.binVc, (uint32_t)tr.pr.y, t_slot, WB);
+            }
         }
     };
     auto request = [&]() { tmem_st_wait(); tc_fence_before(); named_bar_arrive(5 + wg, 160); };
@@ -347,7 +357,7 @@ __global__ void __launch_bounds__(512, 1) score_umma4_kernel(Umma4Params pp) {
                 const bool more = t < 2 || has_next;
                 if (more && !ABL(1)) weights(t < 2 ? cur : nxt, t < 2 ? t + 1 : 0, WA, WB);       // MMA 1 of token t is in flight
                 wait_mma();
-                if (t != 2 || cur.dense()) release_slot();                       // MMA 1 has read the slot
+                if (t != 2 || (DENSE && cur.dense())) release_slot();                       // MMA 1 has read the slot
 #if HSG_EPI_PIPE & 8
                 prefetch_s_row(p, t, cell, cur.pr);
 #endif
@@ -449,10 +459,12 @@ int launch_score_pairs_umma4(hsg_ctx* c, int cell_start, int n_batch, float* out
     const int g4 = (int)(q4 < c->n_sm ? q4 : c->n_sm);
     static bool attr4[64] = {};
     if (!attr4[c->device & 63]) {
-        HSG_CUDA(cudaFuncSetAttribute(score_umma4_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, U4_SM_TOTAL + 1024));
+        HSG_CUDA(cudaFuncSetAttribute(score_umma4_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, U4_SM_TOTAL + 1024));
+        HSG_CUDA(cudaFuncSetAttribute(score_umma4_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, U4_SM_TOTAL + 1024));
         attr4[c->device & 63] = true;
     }
-    score_umma4_kernel<<<g4, 512, U4_SM_TOTAL + 1024, s>>>(pp);
+    if (c->k2_dense_tiles) score_umma4_kernel<true><<<g4, 512, U4_SM_TOTAL + 1024, s>>>(pp);
+    else score_umma4_kernel<false><<<g4, 512, U4_SM_TOTAL + 1024, s>>>(pp);
     c->launches++;
     HSG_CUDA(cudaGetLastError());
     return 0;
