@@ -715,7 +715,7 @@ int launch_gather(hsg_ctx* c, const int*, int cell_start, int n_batch, cudaStrea
             HSG_CUDA(cudaMalloc((void**)&c->ovf_list, (size_t)(2 * n_tok + 2) * sizeof(int)));      // two lists, each followed by its counter
             c->ovf_cap = n_tok + 1;
         }
-        bool second_list = false;
+        const bool second_list = false;      // (list mode of the hash-merge kernel: see the note at the register-kernel launch below)
         int* cnt = c->ovf_list + n_tok;
         HSG_CUDA(cudaMemsetAsync(cnt, 0, sizeof(int), s));
         int64_t quads = (n_tok + 3) / 4;

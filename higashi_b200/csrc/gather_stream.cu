@@ -26,6 +26,14 @@
 //     shared memory (8 lanes x 8 columns, two conflict-free 128-bit loads per 8 FMAs) like the hash / chromosome kernels.
 //   * items whose segments exceed the stage capacity and tokens with more distinct columns than the candidate list holds go to
 //     the overflow list that the generic kernel finishes.
+//
+// MEASURED (B200, round 2) -- opt-in, NOT the default: parity-green (tests/test_gpu_parity.py::test_gather_stream_*), but C2 K1a takes
+// 2.16 - 2.39 ms per 1000 cells against 1.93 for the register kernel (C1 0.26 vs 0.21; C3, where only 8 consumer warps fit next to
+// the 128 KB E table, 5.4 vs 3.4 for the hash-merge kernel).  ncu (profiles/r02_k1_stream_ncu.txt): DRAM 1.7 % of peak, issue
+// 0.64 per scheduler, short scoreboard 30 % -- with the three global hops gone, the per-token dependency chain (extents -> prefix
+// -> entry -> match.any -> log1p -> norm -> gather) is what bounds the kernel, at ~220 warp instructions per token; one item of
+// lookahead or nine made no difference.  What would: four tokens per warp for rows of <= 8 entries and a densified-tile x E_c MMA
+// for the long ones.
 #include <algorithm>
 #include <cmath>
 #include <cstdlib>
