@@ -76,6 +76,7 @@ EXPORTS = [
     "hsg_train_bind_recon", "hsg_recon_loss", "hsg_recon_apply", "hsg_train_set_dropout",
     "hsg_score_set_head_grads", "hsg_sample_batch", "hsg_sample_batch_begin", "hsg_sample_batch_end", "hsg_sampled_fetch",
     "hsg_insulation", "hsg_impute_cells_f16", "hsg_impute_cells_host_f16", "hsg_refresh_contacts", "hsg_scorer_variant", "hsg_sample_set_removal_draws",
+    "hsg_debug_tile_table",
 ]
 
 
@@ -142,6 +143,7 @@ def load():
     lib.hsg_recon_apply.argtypes = [p, C.c_float, p]
     lib.hsg_train_set_dropout.argtypes = [p, i32, C.c_uint64]
     lib.hsg_insulation.argtypes = [p, i32, p, i32, i32, i32, p, p, f32p, p, p]
+    lib.hsg_debug_tile_table.argtypes = [C.POINTER(C.c_int32), i64, i32, C.POINTER(C.c_int32), i64]
     for name in EXPORTS:
         if name not in ("hsg_last_error", "hsg_launch_count", "hsg_abi_version"):
             getattr(lib, name).restype = i32

@@ -241,6 +241,16 @@ static void chrom_row_stats(hsg_ctx* c, const int64_t* row_ptr, std::vector<doub
     }
 }
 
+extern "C" int hsg_debug_tile_table(const int32_t* pairs_xy, int64_t P, int allow_dense, int32_t* tiles_out, int64_t tiles_cap) {
+    if (!pairs_xy || !tiles_out || P < 0) return -1;
+    std::vector<int> t;
+    build_tiles4(reinterpret_cast<const int2*>(pairs_xy), P, t, allow_dense != 0);
+    const int64_t n = (int64_t)t.size() / 8;
+    if (n > tiles_cap) return -1;
+    memcpy(tiles_out, t.data(), t.size() * sizeof(int));
+    return (int)n;
+}
+
 extern "C" int hsg_set_contacts(hsg_ctx* c, const int64_t* row_ptr, const int32_t* col, const float* val, int64_t n_rows,
                                 int64_t nnz) {
     CTX_GUARD(c);

@@ -246,6 +246,11 @@ int  hsg_insulation(hsg_ctx* ctx, int sel_slot, const float* scores_dev, int n_b
                     unsigned char* border_out_host, void* stream);
 
 /* ---- introspection ------------------------------------------------------------------------ */
+/* HOST-ONLY test hook (no device, no context): the generation-4 tile table of a pair list in generate_binpair order
+ * (utils.py:generate_binpair via Impute.py:49; score_umma4.cu build_tiles4).  `pairs_xy` = P (bin_i, bin_j) int32 pairs;
+ * `tiles_out` receives 8 ints per tile: (p0, cnt, s1, s2, bin_i of segment 0, 1, 2, dense flag).  Returns the number of
+ * tiles, or -1 when `tiles_cap` (in tiles) is too small.                                                                */
+int  hsg_debug_tile_table(const int32_t* pairs_xy, int64_t P, int allow_dense, int32_t* tiles_out, int64_t tiles_cap);
 /* number of kernels this library launched since the context was created (bench.py gpu_launches) */
 int64_t hsg_launch_count(hsg_ctx* ctx);
 /* device time (ms, CUDA events on the work stream) of the last hsg_impute_cells* call, split by stage:

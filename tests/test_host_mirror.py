@@ -264,3 +264,52 @@ def test_recycled_score_buffers_wait_for_their_writer():
     assert sorted(written) == list(range(6))
     for k in range(6):
         assert np.all(written[k] == float(k)), (k, written[k][:4])
+
+
+# ------------------------------------------------------------------ generation-4 tile table (host logic of the fast scorer)
+def _tile_table(pairs, allow_dense):
+    import ctypes as C
+    from higashi_b200 import _lib
+    lib = _lib.load()
+    pairs = np.ascontiguousarray(pairs, dtype=np.int32)
+    out = np.zeros((len(pairs) + 1, 8), dtype=np.int32)
+    n = lib.hsg_debug_tile_table(pairs.ctypes.data_as(C.POINTER(C.c_int32)), len(pairs), int(allow_dense),
+                                 out.ctypes.data_as(C.POINTER(C.c_int32)), len(out))
+    assert n >= 0
+    return out[:n]
+
+
+@pytest.mark.parametrize("bins,band", [([120, 40], -1), ([250, 97, 30], -1), ([300], 40), ([5, 3, 129], -1)])
+def test_tile_table_covers_the_pair_list(bins, band):
+    """score_umma4.cu `build_tiles4` (pure host code): tiles are consecutive runs of the pair list in generate_binpair order, cover
+    it exactly once, hold at most 128 pairs; a plain tile has at most three bin_i segments with the recorded boundaries and bins;
+    dense tiles (the short rows at the end of a chromosome) appear only where the three-segment prefix would leave more than 16 rows
+    idle, hold 128 pairs unless the list ends, and make the table strictly shorter."""
+    from oracle import impute as OI
+    num_list = np.concatenate([[0], np.cumsum(bins)]) + 10                      # bins are numbered after 10 cells
+    big, _, _, _ = OI.enumerate_pairs(num_list, list(range(len(bins))), 1, int(1e5) if band < 0 else band)
+    pairs = np.asarray(big)[:, -2:].astype(np.int32)
+    P = len(pairs)
+    plain, dense = _tile_table(pairs, False), _tile_table(pairs, True)
+    for tab, allow in ((plain, False), (dense, True)):
+        p0 = 0
+        for (s0, cnt, s1, s2, b0, b1, b2, flag) in tab:
+            assert s0 == p0 and 1 <= cnt <= 128
+            bi = pairs[p0:p0 + cnt, 0]
+            starts = np.flatnonzero(np.r_[True, bi[1:] != bi[:-1]])
+            if flag:
+                assert allow and s1 == 0 and s2 == 0 and (cnt == 128 or p0 + cnt == P) and len(starts) > 3
+                assert starts[3] < 112                                          # the three-segment prefix was short
+            else:
+                assert len(starts) <= 3
+                want = list(starts[1:]) + [128] * (3 - len(starts))
+                assert [s1, s2] == want
+                segb = list(bi[starts]) + [bi[0]] * (3 - len(starts))
+                assert [b0, b1, b2] == segb
+                if allow and p0 + cnt < P and cnt < 128:
+                    assert cnt >= 112                                           # a shorter prefix would have become a dense tile
+            p0 += cnt
+        assert p0 == P
+    assert len(dense) <= len(plain)
+    if len(bins) > 1 or band < 0:
+        assert len(dense) < len(plain)
