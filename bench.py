@@ -200,6 +200,17 @@ def _reference_imputer(args, n_small):
         return None, None, "reference import failed: %r" % (e,)
 
 
+def workload_string(name, n_cells, ds, P):
+    """One spelling of the workload for both arms (`--impl ours` and `--impl reference`)."""
+    return ("%s: synthetic %d cells x %d bins (%d chromosomes), P=%d pairs/cell, k=%d, d_model=%d, impute_with_nbr"
+            % (name, n_cells, sum(ds.bins), len(ds.bins), P, ds.k, ds.d))
+
+
+def _full_cells(name):
+    from higashi_b200 import synthetic as S
+    return int(S.CONFIGS[name]["n_cells"])
+
+
 def run_reference(args):
     """`--impl reference`: the UNMODIFIED reference (Impute.impute_process from baseline/_ref through oracle/ref_shims.py) on the
     host cores; the oracle port only when the reference cannot be imported."""
@@ -266,8 +277,11 @@ def run_reference(args):
     line = {"impl": "reference", "metric": "imputed (cell,bin_i,bin_j) triplets/s", "value": val, "unit": "triplets/s",
             "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * total / args.steps,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": "%s: %d-cell sample of the synthetic shape, %d bins, P=%d pairs/cell, k=%d, d=%d"
-                       % (args.workload, n_small, sum(ds.bins), P, ds.k, ds.d)},
+            # the SAME workload string as the GPU arm prints (the job is the full configuration); what was actually timed -- a bounded
+            # sample of it, per-triplet cost being independent of the cell count -- is spelled out next to it and in cpu_baseline.sample
+            "config": {"workload": workload_string(args.workload, _full_cells(args.workload), ds, P),
+                       "cells_per_step": cells_per_step, "triplets_per_step": cells_per_step * P,
+                       "sample": "%d-cell sample of the same synthetic shape, %d cell(s) per step" % (n_small, cells_per_step)},
             "cpu_baseline": cb,
             "e2e": {"value": val, "unit": "triplets/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
@@ -871,8 +885,7 @@ def main():
                 "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_all / args.steps, "higher_is_better": True,
                 "scaling": "weak", "vs_baseline": None,
                 "dtype": "f32" if precision == E.PREC_FP32 else "f16 operands / f32 accumulate (tcgen05 kind::f16)", "data": "synthetic",
-                "config": {"workload": "%s: synthetic %d cells x %d bins (%d chromosomes), P=%d pairs/cell, k=%d, d_model=%d, "
-                                       "impute_with_nbr" % (args.workload, ds.n_cells, sum(ds.bins), len(ds.bins), P, ds.k, ds.d),
+                "config": {"workload": workload_string(args.workload, ds.n_cells, ds, P),
                            "cells_per_step": cps, "triplets_per_step": cps * P, "sharding": "cell range per rank, no collective",
                            "numa_node": numa_node,
                            "l2_policy": "each step reads a new cell range and writes a fresh %d MB score block (> 126 MB L2)"
